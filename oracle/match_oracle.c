@@ -1,0 +1,89 @@
+/*
+ * oracle/match_oracle.c -- TEST INFRASTRUCTURE (see oracle.h).  CPU restatement of the 256-bit Hamming matchers.
+ * Pinned by the reference's own known-answer tests (test/stella_vslam/match/base.cc:11-57) for the distance;
+ * brute_force_match has no reference test ("parity unpinned" beyond the restatement itself).
+ */
+#include "oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* match::compute_descriptor_distance_32 (match/base.h:20-41): SWAR popcount over 8 x u32. */
+unsigned orc_hamming_32(const uint8_t* a, const uint8_t* b) {
+    unsigned dist = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t x, y;
+        memcpy(&x, a + 4 * i, 4);
+        memcpy(&y, b + 4 * i, 4);
+        uint32_t v = x ^ y;
+        v -= ((v >> 1) & 0x55555555U);
+        v = (v & 0x33333333U) + ((v >> 2) & 0x33333333U);
+        dist += (((v + (v >> 4)) & 0x0F0F0F0FU) * 0x01010101U) >> 24;
+    }
+    return dist;
+}
+
+/* match::compute_descriptor_distance_64 (match/base.h:44-65): SWAR popcount over 4 x u64. */
+unsigned orc_hamming_64(const uint8_t* a, const uint8_t* b) {
+    unsigned dist = 0;
+    for (int i = 0; i < 4; ++i) {
+        uint64_t x, y;
+        memcpy(&x, a + 8 * i, 8);
+        memcpy(&y, b + 8 * i, 8);
+        uint64_t v = x ^ y;
+        v -= (v >> 1) & 0x5555555555555555ULL;
+        v = (v & 0x3333333333333333ULL) + ((v >> 2) & 0x3333333333333333ULL);
+        dist += (unsigned)((((v + (v >> 4)) & 0x0F0F0F0F0F0F0F0FULL) * 0x0101010101010101ULL) >> 56);
+    }
+    return dist;
+}
+
+/* util::angle::diff (util/angle.cc:7-16): float subtraction, comparisons against double literals. */
+float orc_angle_diff(float a1, float a2) {
+    float ret = a1 - a2;
+    if (ret <= -180.0) ret += 360.0;
+    if (ret > 180.0) ret -= 360.0;
+    return ret;
+}
+
+/* match::robust::brute_force_match (match/robust.cc:232-328). */
+int orc_brute_force_match(const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2, const float* angle2,
+                          const uint8_t* valid2, int n2, float lowe_ratio, int check_orientation, int32_t* pairs_out) {
+    int* matched_2_in_1 = (int*)malloc(sizeof(int) * (n1 ? n1 : 1));
+    uint8_t* taken_1 = (uint8_t*)calloc(n1 ? n1 : 1, 1);
+    for (int i = 0; i < n1; ++i) matched_2_in_1[i] = -1;
+    for (int idx_2 = 0; idx_2 < n2; ++idx_2) {
+        if (valid2 && !valid2[idx_2]) continue; /* no landmark / will_be_erased (robust.cc:255-262) */
+        const uint8_t* d2 = desc2 + (size_t)idx_2 * 32;
+        unsigned best = 256, second = 256;
+        int best_idx_1 = -1;
+        for (int idx_1 = 0; idx_1 < n1; ++idx_1) {
+            if (taken_1[idx_1]) continue;
+            if (check_orientation && fabsf(orc_angle_diff(angle1[idx_1], angle2[idx_2])) > 30.0) continue;
+            const unsigned hd = orc_hamming_32(d2, desc1 + (size_t)idx_1 * 32);
+            if (hd < best) {
+                second = best;
+                best = hd;
+                best_idx_1 = idx_1;
+            } else if (hd < second) {
+                second = hd;
+            }
+        }
+        if (50 < best) continue;
+        if (best_idx_1 < 0) continue;
+        if (lowe_ratio * second < (float)best) continue;
+        matched_2_in_1[best_idx_1] = idx_2;
+        taken_1[best_idx_1] = 1;
+    }
+    int n = 0;
+    for (int idx_1 = 0; idx_1 < n1; ++idx_1) {
+        if (matched_2_in_1[idx_1] < 0) continue;
+        pairs_out[2 * n] = idx_1;
+        pairs_out[2 * n + 1] = matched_2_in_1[idx_1];
+        ++n;
+    }
+    free(matched_2_in_1);
+    free(taken_1);
+    return n;
+}

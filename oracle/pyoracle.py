@@ -1,0 +1,195 @@
+"""ctypes loader for the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+The product package (stella_vslam_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force=False):
+    """Compile the oracle with the committed Makefile (gcc only)."""
+    if force or not os.path.exists(_LIB_PATH) or any(
+            os.path.getmtime(os.path.join(_HERE, f)) > os.path.getmtime(_LIB_PATH)
+            for f in os.listdir(_HERE) if f.endswith((".c", ".h"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+class Keypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32)]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4")])
+
+
+class OrbConfig(C.Structure):
+    _fields_ = [("scale_factor", C.c_float), ("num_levels", C.c_int32), ("ini_fast_thr", C.c_int32),
+                ("min_fast_thr", C.c_int32), ("min_area", C.c_uint32)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        u8p, f32p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        L.orc_scale_factors.argtypes = [C.c_float, C.c_int, f32p, f32p, f32p, f32p]
+        L.orc_level_size.argtypes = [C.c_int, C.c_int, C.c_float, i32p, i32p]
+        L.orc_resize_linear_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_fast9_16_nms.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_fast9_16_nms.restype = C.c_int
+        L.orc_gaussian7_s2_u8.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_fast_atan2.argtypes = [C.c_float, C.c_float]
+        L.orc_fast_atan2.restype = C.c_float
+        L.orc_ic_angle.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_ic_angle.restype = C.c_float
+        L.orc_util_cos.argtypes = [C.c_float]
+        L.orc_util_cos.restype = C.c_float
+        L.orc_util_sin.argtypes = [C.c_float]
+        L.orc_util_sin.restype = C.c_float
+        L.orc_rbrief.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_void_p]
+        L.orc_rect_mask.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_orb_extract.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(OrbConfig),
+                                      C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_orb_extract.restype = C.c_int
+        L.orc_hamming_32.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_hamming_32.restype = C.c_uint
+        L.orc_hamming_64.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_hamming_64.restype = C.c_uint
+        L.orc_angle_diff.argtypes = [C.c_float, C.c_float]
+        L.orc_angle_diff.restype = C.c_float
+        L.orc_brute_force_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                            C.c_float, C.c_int, C.c_void_p]
+        L.orc_brute_force_match.restype = C.c_int
+        if hasattr(L, "orc_lba_solve"):
+            L.orc_lba_solve.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def scale_factors(scale_factor=1.2, n=8):
+    out = [np.zeros(n, np.float32) for _ in range(4)]
+    lib().orc_scale_factors(scale_factor, n, *[o.ctypes.data_as(C.POINTER(C.c_float)) for o in out])
+    return out  # sf, inv_sf, sigma_sq, inv_sigma_sq
+
+
+def level_sizes(w, h, scale_factor=1.2, n=8):
+    sf = scale_factors(scale_factor, n)[0]
+    sizes = [(w, h)]
+    for l in range(1, n):
+        lw, lh = C.c_int32(), C.c_int32()
+        lib().orc_level_size(w, h, float(sf[l]), C.byref(lw), C.byref(lh))
+        sizes.append((lw.value, lh.value))
+    return sizes
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dw, dh, dw)
+    return dst
+
+
+def fast9_16_nms(img, thr):
+    """cv::FAST(img, thr, nonmax=True) on a (possibly non-contiguous) 2-D u8 view."""
+    assert img.dtype == np.uint8 and img.strides[1] == 1
+    h, w = img.shape
+    cap = w * h
+    xs, ys, sc = np.empty(cap, np.int16), np.empty(cap, np.int16), np.empty(cap, np.uint8)
+    n = lib().orc_fast9_16_nms(img.ctypes.data, img.strides[0], w, h, thr, _p(xs), _p(ys), _p(sc), cap)
+    return xs[:n].copy(), ys[:n].copy(), sc[:n].copy()
+
+
+def gaussian7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().orc_gaussian7_s2_u8(_p(src), src.shape[1], src.shape[0], src.strides[0], _p(dst), dst.strides[0])
+    return dst
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def ic_angle(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    return lib().orc_ic_angle(_p(img), img.strides[0], int(x), int(y))
+
+
+def rbrief(blurred, x, y, angle_deg):
+    blurred = np.ascontiguousarray(blurred, np.uint8)
+    d = np.zeros(32, np.uint8)
+    lib().orc_rbrief(_p(blurred), blurred.strides[0], float(x), float(y), float(angle_deg), _p(d))
+    return d
+
+
+def rect_mask(cols, rows, rects):
+    r = np.ascontiguousarray(np.asarray(rects, np.float32).reshape(-1, 4))
+    m = np.empty((rows, cols), np.uint8)
+    lib().orc_rect_mask(cols, rows, _p(r), r.shape[0], _p(m), cols)
+    return m
+
+
+def orb_extract(img, mask=None, scale_factor=1.2, num_levels=8, ini_fast_thr=20, min_fast_thr=7, min_area=800,
+                want_pyramid=False, cap=None):
+    """feature::orb_extractor::extract.  Returns dict(kps=structured array, desc=(N,32) u8, level_counts, raw_counts[, pyramid])."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    cfg = OrbConfig(scale_factor, num_levels, ini_fast_thr, min_fast_thr, min_area)
+    if cap is None:
+        cap = max(1024, (w * h) // 64)
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    lc, rc = np.zeros(num_levels, np.int32), np.zeros(num_levels, np.int32)
+    pyr, pyr_ptrs = None, None
+    if want_pyramid:
+        pyr = [np.empty((lh, lw), np.uint8) for (lw, lh) in level_sizes(w, h, scale_factor, num_levels)]
+        pyr_ptrs = (C.c_void_p * num_levels)(*[p.ctypes.data for p in pyr])
+    if mask is not None:
+        mask = np.ascontiguousarray(mask, np.uint8)
+    n = lib().orc_orb_extract(_p(img), w, h, img.strides[0], _p(mask), mask.strides[0] if mask is not None else 0,
+                              C.byref(cfg), _p(kps), _p(desc), cap, _p(lc), _p(rc), pyr_ptrs)
+    if n < 0:
+        raise RuntimeError("oracle keypoint capacity too small")
+    out = dict(kps=kps[:n].copy(), desc=desc[:n].copy(), level_counts=lc, raw_counts=rc)
+    if want_pyramid:
+        out["pyramid"] = pyr
+    return out
+
+
+def hamming_32(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return lib().orc_hamming_32(_p(a), _p(b))
+
+
+def hamming_64(a, b):
+    a, b = np.ascontiguousarray(a, np.uint8), np.ascontiguousarray(b, np.uint8)
+    return lib().orc_hamming_64(_p(a), _p(b))
+
+
+def brute_force_match(desc1, angle1, desc2, angle2, valid2=None, lowe_ratio=0.8, check_orientation=True):
+    desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    angle1, angle2 = np.ascontiguousarray(angle1, np.float32), np.ascontiguousarray(angle2, np.float32)
+    n1, n2 = desc1.shape[0], desc2.shape[0]
+    if valid2 is not None:
+        valid2 = np.ascontiguousarray(valid2, np.uint8)
+    pairs = np.zeros((max(n1, 1), 2), np.int32)
+    n = lib().orc_brute_force_match(_p(desc1), _p(angle1), n1, _p(desc2), _p(angle2), _p(valid2), n2, lowe_ratio,
+                                    int(check_orientation), _p(pairs))
+    return pairs[:n].copy()
