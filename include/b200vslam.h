@@ -1,0 +1,138 @@
+/*
+ * b200vslam.h -- C ABI of the B200-native stella_vslam hot path (ORB extract -> Hamming match -> local BA).
+ *
+ * The reference has no FFI of its own: its "operator API" for this path is three C++ class surfaces
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it replaces (paths relative to the
+ * reference checkout); the C++ adapters in stella_vslam_b200/host/ and INTEGRATION.md show the binding.
+ *
+ * Conventions: plain pointers and sizes only, caller-allocated outputs, int status (0 = OK, <0 = error, see
+ * b200_last_error()), no exceptions cross the boundary.  One opaque handle per instance owns a CUDA stream and its
+ * device arenas; handles are not thread-safe, distinct handles are independent (the reference runs the left/right
+ * extractors in two threads, system.cc:427-434).  There is NO CPU fallback: every entry point fails with
+ * B200_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef B200VSLAM_H
+#define B200VSLAM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_OK 0
+#define B200_ERR_INVALID (-1)  /* bad argument (also: image type/size the reference would assert on) */
+#define B200_ERR_CUDA (-2)     /* CUDA runtime/driver failure or no device */
+#define B200_ERR_CAPACITY (-3) /* caller buffer too small; counts are still written */
+#define B200_ERR_ABORTED (-4)  /* local BA: force-stop flag was set before the first solve (no write-back) */
+
+const char* b200_last_error(void);
+int b200_device_count(void);
+/* bytes of the library's version string: "b200vslam <semver> sm_100a" */
+const char* b200_version(void);
+
+/* Pinned host memory helpers (the end-to-end path copies from/to pinned buffers). */
+int b200_host_alloc(void** ptr, size_t bytes);
+int b200_host_free(void* ptr);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * feature::orb_extractor  (src/stella_vslam/feature/orb_extractor.h:51-61, orb_extractor.cc:16-136)
+ * ---------------------------------------------------------------------------------------------------------------- */
+
+/* cv::KeyPoint as the reference fills it (orb_extractor.cc:273-283, 337-345); class_id is always -1. */
+typedef struct {
+    float x, y;      /* level-0 pixel coordinates (pt * scale_factor[octave]) */
+    float size;      /* (unsigned)(31 * scale_factor[octave]) */
+    float angle;     /* IC angle, degrees [0,360) */
+    float response;  /* FAST score */
+    int32_t octave;  /* pyramid level */
+} b200_keypoint_t;
+
+/* feature::orb_params (orb_params.cc:12-27) + orb_extractor ctor arguments (orb_extractor.cc:16-20). */
+typedef struct {
+    float scale_factor;       /* Feature.scale_factor, default 1.2 */
+    int32_t num_levels;       /* Feature.num_levels, default 8 (max 16) */
+    int32_t ini_fast_thr;     /* Feature.ini_fast_threshold, default 20 */
+    int32_t min_fast_thr;     /* Feature.min_fast_threshold, default 7 */
+    uint32_t min_area;        /* Preprocessing.min_size (system.cc:95), default 800 */
+    int32_t n_mask_rects;     /* mask_rects ctor argument: n x {x_min, x_max, y_min, y_max} as image fractions */
+    const float* mask_rects;  /* may be NULL when n_mask_rects == 0 */
+    int32_t device;           /* CUDA device ordinal */
+    int32_t max_batch;        /* frames per extract call this instance is sized for (>=1); grows on demand */
+} b200_orb_params_t;
+
+typedef struct b200_orb_s* b200_orb_t;
+
+void b200_orb_default_params(b200_orb_params_t* p);
+int b200_orb_create(const b200_orb_params_t* p, b200_orb_t* out);
+int b200_orb_destroy(b200_orb_t h);
+
+/* Upper bound of keypoints one w x h frame can yield (sum over levels of selection-grid cells). */
+int b200_orb_max_keypoints(b200_orb_t h, int width, int height);
+
+/* orb_extractor::extract (orb_extractor.cc:28-136) for `batch` same-sized CV_8UC1 frames held in HOST memory.
+ *   images      : frame f starts at images + f*frame_stride, rows `pitch` bytes apart.
+ *   mask        : optional CV_8UC1 image mask at level-0 resolution shared by the batch (0 = masked), or NULL; when
+ *                 NULL the rectangle mask built from mask_rects is used if any (orb_extractor.cc:50-64).
+ *   kps/descs   : frame f writes kps[f*cap ..], descs[(f*cap + i)*32 ..]; counts[f] = N_f.
+ * width==0 || height==0 || batch==0 -> B200_OK with nothing written (orb_extractor.cc:30-32).
+ * Includes the host->device copy of the frames and the device->host copy of the results. */
+int b200_orb_extract(b200_orb_t h, const uint8_t* images, int width, int height, size_t pitch, size_t frame_stride,
+                     int batch, const uint8_t* mask, size_t mask_pitch, b200_keypoint_t* kps, uint8_t* descs, int cap,
+                     int32_t* counts);
+
+/* Same, with frames already resident in device memory (and the mask, if any); results stay on the device until
+ * b200_orb_fetch.  Runs on the instance's stream; `wait_stream` (a cudaStream_t, may be 0) is waited on first. */
+int b200_orb_extract_device(b200_orb_t h, const void* d_images, int width, int height, size_t pitch, size_t frame_stride,
+                            int batch, const void* d_mask, size_t mask_pitch, void* wait_stream);
+/* Copy the last extract's results to host buffers (synchronises the instance stream). */
+int b200_orb_fetch(b200_orb_t h, b200_keypoint_t* kps, uint8_t* descs, int cap, int32_t* counts);
+/* Device views of the last extract's results: keypoints [batch][stride_kps], descriptors [batch][stride_kps][32],
+ * counts [batch].  Valid until the next extract on this handle. */
+int b200_orb_device_results(b200_orb_t h, const b200_keypoint_t** d_kps, const uint8_t** d_descs, const int32_t** d_counts,
+                            int* stride_kps);
+int b200_orb_sync(b200_orb_t h);
+
+/* orb_extractor::image_pyramid_ (orb_extractor.h:71; read by match::stereo via system.cc:443): level geometry and a
+ * device view / host copy of one level of one frame of the last extract. */
+int b200_orb_level_info(b200_orb_t h, int level, int* width, int* height, size_t* pitch, float* scale_factor);
+int b200_orb_pyramid_level_device(b200_orb_t h, int frame, int level, const uint8_t** d_ptr);
+int b200_orb_pyramid_level_host(b200_orb_t h, int frame, int level, uint8_t* dst, size_t dst_pitch);
+
+/* Per-stage kernel time of the last extract, in ms, measured with CUDA events on the instance stream.
+ * stage: 0 pyramid, 1 FAST+NMS+grid arg-max, 2 select+orientation, 3 descriptor blur, 4 rBRIEF, 5 whole extract. */
+int b200_orb_stage_ms(b200_orb_t h, int stage, float* ms);
+int b200_orb_enable_timing(b200_orb_t h, int enable);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * match::compute_descriptor_distance_32 / match::robust::brute_force_match
+ * (src/stella_vslam/match/base.h:15-41, match/robust.cc:232-328)
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct b200_matcher_s* b200_matcher_t;
+
+int b200_matcher_create(int device, b200_matcher_t* out);
+int b200_matcher_destroy(b200_matcher_t h);
+
+/* All-pairs 256-bit Hamming distances: dist[i*n2 + j] = popcount(desc1[i] ^ desc2[j])  (host buffers). */
+int b200_hamming_matrix(b200_matcher_t h, const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, uint16_t* dist);
+
+/* robust::brute_force_match for `n_problems` independent (frame, keyframe) pairs, host buffers.
+ * Problem p: frame side  = desc1 + off1[p]*32, angle1 + off1[p], n1 = off1[p+1]-off1[p]   (frm_obs descriptors/angles)
+ *            keyframe side likewise with off2; valid2[i] != 0 <=> keyframe keypoint i has a live landmark.
+ * pairs: problem p writes (idx_1, idx_2) int32 pairs sorted by idx_1 at pairs + 2*off1[p]; n_pairs[p] = count.
+ * lowe_ratio / check_orientation: the matcher's ctor arguments (match/base.h:81-91). */
+int b200_match_bruteforce(b200_matcher_t h, int n_problems, const uint8_t* desc1, const float* angle1, const int32_t* off1,
+                          const uint8_t* desc2, const float* angle2, const uint8_t* valid2, const int32_t* off2,
+                          float lowe_ratio, int check_orientation, int32_t* pairs, int32_t* n_pairs);
+/* Device-resident variant (all pointers are device pointers; results stay on the device). */
+int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, int total1, int total2, const void* d_desc1,
+                                 const void* d_angle1, const void* d_off1, const void* d_desc2, const void* d_angle2,
+                                 const void* d_valid2, const void* d_off2, int max_n1, int max_n2, float lowe_ratio,
+                                 int check_orientation, void* d_pairs, void* d_n_pairs, void* wait_stream);
+int b200_matcher_sync(b200_matcher_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VSLAM_H */

@@ -1,0 +1,129 @@
+"""ctypes binding of libb200vslam.so (the C ABI declared in include/b200vslam.h).
+
+There is no fallback: if the CUDA extension is missing or no sm_100 device is present, calls fail loudly.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libb200vslam.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_ABORTED = 0, -1, -2, -3, -4
+
+
+class B200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200vslam error {code}: {msg}")
+        self.code = code
+
+
+class OrbParams(C.Structure):
+    _fields_ = [("scale_factor", C.c_float), ("num_levels", C.c_int32), ("ini_fast_thr", C.c_int32),
+                ("min_fast_thr", C.c_int32), ("min_area", C.c_uint32), ("n_mask_rects", C.c_int32),
+                ("mask_rects", C.POINTER(C.c_float)), ("device", C.c_int32), ("max_batch", C.c_int32)]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4")])
+
+_lib = None
+
+# every symbol include/b200vslam.h declares (tests check that the .so exports all of them)
+SYMBOLS = [
+    "b200_last_error", "b200_device_count", "b200_version", "b200_host_alloc", "b200_host_free",
+    "b200_orb_default_params", "b200_orb_create", "b200_orb_destroy", "b200_orb_max_keypoints", "b200_orb_extract",
+    "b200_orb_extract_device", "b200_orb_fetch", "b200_orb_device_results", "b200_orb_sync", "b200_orb_level_info",
+    "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_stage_ms", "b200_orb_enable_timing",
+    "b200_matcher_create", "b200_matcher_destroy", "b200_hamming_matrix", "b200_match_bruteforce",
+    "b200_match_bruteforce_device", "b200_matcher_sync",
+]
+
+
+def lib():
+    """Load the shared library (raises if it has not been built: run `python __graft_entry__.py` / build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200Error(ERR_CUDA, f"{LIB_PATH} is missing: the CUDA extension must be built (__graft_entry__.build()); "
+                                  "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+    L.b200_last_error.restype = C.c_char_p
+    L.b200_version.restype = C.c_char_p
+    L.b200_host_alloc.argtypes = [C.POINTER(vp), sz]
+    L.b200_host_free.argtypes = [vp]
+    L.b200_orb_default_params.argtypes = [C.POINTER(OrbParams)]
+    L.b200_orb_default_params.restype = None
+    L.b200_orb_create.argtypes = [C.POINTER(OrbParams), C.POINTER(vp)]
+    L.b200_orb_destroy.argtypes = [vp]
+    L.b200_orb_max_keypoints.argtypes = [vp, i32, i32]
+    L.b200_orb_extract.argtypes = [vp, vp, i32, i32, sz, sz, i32, vp, sz, vp, vp, i32, vp]
+    L.b200_orb_extract_device.argtypes = [vp, vp, i32, i32, sz, sz, i32, vp, sz, vp]
+    L.b200_orb_fetch.argtypes = [vp, vp, vp, i32, vp]
+    L.b200_orb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]
+    L.b200_orb_sync.argtypes = [vp]
+    L.b200_orb_level_info.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(sz), C.POINTER(C.c_float)]
+    L.b200_orb_pyramid_level_device.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.b200_orb_pyramid_level_host.argtypes = [vp, i32, i32, vp, sz]
+    L.b200_orb_stage_ms.argtypes = [vp, i32, C.POINTER(C.c_float)]
+    L.b200_orb_enable_timing.argtypes = [vp, i32]
+    L.b200_matcher_create.argtypes = [i32, C.POINTER(vp)]
+    L.b200_matcher_destroy.argtypes = [vp]
+    L.b200_matcher_sync.argtypes = [vp]
+    L.b200_hamming_matrix.argtypes = [vp, vp, i32, vp, i32, vp]
+    L.b200_match_bruteforce.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, C.c_float, i32, vp, vp]
+    L.b200_match_bruteforce_device.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.c_float, i32, vp,
+                                               vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc, allow=()):
+    if rc != OK and rc not in allow:
+        raise B200Error(rc, lib().b200_last_error().decode(errors="replace"))
+    return rc
+
+
+def ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class _PinnedOwner:
+    def __init__(self, address):
+        self.address = address
+
+    def __del__(self):
+        try:
+            lib().b200_host_free(C.c_void_p(self.address))
+        except Exception:
+            pass
+
+
+_PINNED = {}
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by cudaHostAlloc'd memory (freed by pinned_free or at interpreter exit)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(lib().b200_host_alloc(C.byref(p), max(n, 1)))
+    buf = (C.c_uint8 * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8, count=n).view(dtype).reshape(shape)
+    _PINNED[arr.ctypes.data] = _PinnedOwner(p.value)
+    return arr
+
+
+def pinned_free(arr):
+    _PINNED.pop(arr.ctypes.data, None)

@@ -1,0 +1,445 @@
+// match_kernels.cu -- 256-bit Hamming matchers on sm_100a.
+//
+// Reference path:
+//   match::compute_descriptor_distance_32      src/stella_vslam/match/base.h:20-41
+//   match::robust::brute_force_match           src/stella_vslam/match/robust.cc:232-328
+//   util::angle::diff                          src/stella_vslam/util/angle.cc:7-16
+//
+// brute_force_match is sequential in the reference: keyframe keypoints idx_2 are visited in order and every accepted
+// match removes its frame keypoint idx_1 from all later searches.  Restated here as
+//   (1) a fully parallel pass that keeps, per idx_2, the K smallest (distance, idx_1) keys over the orientation-gated
+//       frame keypoints (uint4 loads of the descriptors, __popc on the XOR), and
+//   (2) an in-order resolve (one warp per problem) that walks each list skipping taken idx_1; when a list cannot decide
+//       the outcome exactly (too many of its entries were taken) the warp recomputes that row against the live set.
+// Both steps are exact, so the match pairs equal the reference's bit for bit.
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+namespace match {
+
+constexpr int kTopK = 8;            // candidates kept per keyframe keypoint
+constexpr int kRowsPerBlock = 128;  // one keyframe keypoint per thread
+constexpr int kChunk = 256;         // frame descriptors staged per shared-memory tile (8 KB)
+constexpr unsigned kInfKey = 0xFFFFFFFFu;
+constexpr int kThrLow = 50;         // HAMMING_DIST_THR_LOW  (match/base.h:15)
+constexpr int kMaxDist = 256;       // MAX_HAMMING_DIST      (match/base.h:17)
+
+// key = distance << 22 | idx_1 : unsigned order == (distance, then first index) == the reference's strict '<' scan
+__device__ __forceinline__ unsigned make_key(unsigned dist, unsigned idx) { return (dist << 22) | idx; }
+__device__ __forceinline__ unsigned key_dist(unsigned key) { return key >> 22; }
+__device__ __forceinline__ unsigned key_idx(unsigned key) { return key & 0x3FFFFFu; }
+
+__device__ __forceinline__ float angle_diff(float a1, float a2) {  // util/angle.cc:7-16
+    float ret = __fsub_rn(a1, a2);
+    if ((double)ret <= -180.0) ret = (float)((double)ret + 360.0);
+    if ((double)ret > 180.0) ret = (float)((double)ret - 360.0);
+    return ret;
+}
+__device__ __forceinline__ bool orientation_rejects(float a1, float a2) {  // robust.cc:279
+    return (double)fabsf(angle_diff(a1, a2)) > 30.0;
+}
+
+__device__ __forceinline__ unsigned hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) + __popc(a1.x ^ b1.x)
+           + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// all-pairs distance matrix (diagnostics / landmark::compute_descriptor-style consumers)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hamming_matrix_kernel(const uint4* __restrict__ d1, int n1, const uint4* __restrict__ d2, int n2,
+                                                             unsigned short* __restrict__ out) {
+    __shared__ uint4 s2[64 * 2];
+    const int j0 = blockIdx.x * 64, i = blockIdx.y * blockDim.x + threadIdx.x;
+    for (int t = threadIdx.x; t < 128; t += blockDim.x) s2[t] = (j0 + t / 2 < n2) ? d2[(size_t)j0 * 2 + t] : make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    if (i >= n1) return;
+    const uint4 a0 = d1[(size_t)i * 2], a1 = d1[(size_t)i * 2 + 1];
+    for (int j = 0; j < 64 && j0 + j < n2; ++j) out[(size_t)i * n2 + j0 + j] = (unsigned short)hamming256(a0, a1, s2[2 * j], s2[2 * j + 1]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (1) top-K candidate lists.  grid = (ceil(max_n2 / 128), n_problems); thread = one keyframe keypoint idx_2.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kRowsPerBlock) topk_kernel(const uint4* __restrict__ desc1, const float* __restrict__ angle1,
+                                                            const int* __restrict__ off1, const uint4* __restrict__ desc2,
+                                                            const float* __restrict__ angle2, const unsigned char* __restrict__ valid2,
+                                                            const int* __restrict__ off2, int check_orientation,
+                                                            unsigned* __restrict__ lists) {
+    __shared__ uint4 s1[kChunk * 2];
+    __shared__ float sa[kChunk];
+    const int p = blockIdx.y;
+    const int b1 = off1[p], n1 = off1[p + 1] - b1;
+    const int b2 = off2[p], n2 = off2[p + 1] - b2;
+    if ((int)(blockIdx.x * kRowsPerBlock) >= n2) return;
+    const int row = blockIdx.x * kRowsPerBlock + threadIdx.x;
+    const bool active = row < n2 && (!valid2 || valid2[b2 + row]);
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    float qa = 0.f;
+    if (active) {
+        q0 = desc2[(size_t)(b2 + row) * 2];
+        q1 = desc2[(size_t)(b2 + row) * 2 + 1];
+        qa = angle2[b2 + row];
+    }
+    unsigned top[kTopK];
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k) top[k] = kInfKey;
+    for (int c0 = 0; c0 < n1; c0 += kChunk) {
+        const int cn = min(kChunk, n1 - c0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cn * 2; t += blockDim.x) s1[t] = desc1[(size_t)(b1 + c0) * 2 + t];
+        for (int t = threadIdx.x; t < cn; t += blockDim.x) sa[t] = angle1[b1 + c0 + t];
+        __syncthreads();
+        if (!active) continue;
+#pragma unroll 4
+        for (int j = 0; j < cn; ++j) {
+            const unsigned dist = hamming256(q0, q1, s1[2 * j], s1[2 * j + 1]);
+            const unsigned key = make_key(dist, (unsigned)(c0 + j));
+            if (key < top[kTopK - 1]) {
+                if (check_orientation && orientation_rejects(sa[j], qa)) continue;
+                top[kTopK - 1] = key;
+#pragma unroll
+                for (int k = kTopK - 1; k > 0; --k) {
+                    if (top[k] < top[k - 1]) {
+                        const unsigned t = top[k];
+                        top[k] = top[k - 1];
+                        top[k - 1] = t;
+                    }
+                }
+            }
+        }
+    }
+    if (row < n2) {
+        unsigned* o = lists + (size_t)(b2 + row) * kTopK;
+#pragma unroll
+        for (int k = 0; k < kTopK; ++k) o[k] = top[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (2) in-order resolve + compaction.  One warp per problem.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned warp_min(unsigned v) {
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v = min(v, __shfl_xor_sync(0xFFFFFFFFu, v, s));
+    return v;
+}
+
+// exact best/second over the live (not taken, orientation-gated) frame keypoints: the reference's inner loop
+__device__ void exact_row(const uint4* desc1, const float* angle1, int n1, const unsigned* taken, uint4 q0, uint4 q1, float qa,
+                          int check_orientation, int lane, unsigned* best_key, unsigned* second_dist) {
+    unsigned k1 = kInfKey, k2 = kInfKey;  // two smallest keys seen by this lane
+    for (int i = lane; i < n1; i += 32) {
+        if ((taken[i >> 5] >> (i & 31)) & 1u) continue;
+        if (check_orientation && orientation_rejects(angle1[i], qa)) continue;
+        const unsigned key = make_key(hamming256(q0, q1, desc1[(size_t)i * 2], desc1[(size_t)i * 2 + 1]), (unsigned)i);
+        if (key < k1) {
+            k2 = k1;
+            k1 = key;
+        } else if (key < k2) {
+            k2 = key;
+        }
+    }
+    const unsigned b = warp_min(k1);
+    const unsigned mine = (k1 == b) ? k2 : k1;  // keys are unique (they embed idx_1), so exactly one lane owns b
+    const unsigned s = warp_min(mine);
+    *best_key = b;
+    *second_dist = (s == kInfKey) ? (unsigned)kMaxDist : key_dist(s);
+}
+
+__global__ void __launch_bounds__(32) resolve_kernel(const uint4* __restrict__ desc1, const float* __restrict__ angle1,
+                                                     const int* __restrict__ off1, const uint4* __restrict__ desc2,
+                                                     const float* __restrict__ angle2, const unsigned char* __restrict__ valid2,
+                                                     const int* __restrict__ off2, const unsigned* __restrict__ lists, float lowe_ratio,
+                                                     int check_orientation, int* __restrict__ matched, unsigned* __restrict__ taken_g,
+                                                     int taken_words, int* __restrict__ pairs, int* __restrict__ n_pairs) {
+    const int p = blockIdx.x, lane = threadIdx.x;
+    const int b1 = off1[p], n1 = off1[p + 1] - b1;
+    const int b2 = off2[p], n2 = off2[p + 1] - b2;
+    unsigned* taken = taken_g + (size_t)p * taken_words;
+    int* m21 = matched + b1;
+    for (int i = lane; i < (n1 + 31) / 32; i += 32) taken[i] = 0u;
+    for (int i = lane; i < n1; i += 32) m21[i] = -1;
+    __syncwarp();
+    const uint4* d1 = desc1 + (size_t)b1 * 2;
+    const float* a1 = angle1 + b1;
+    unsigned next_key = (lane < kTopK && n2 > 0) ? lists[(size_t)b2 * kTopK + lane] : kInfKey;
+    for (int r = 0; r < n2; ++r) {
+        const unsigned key = next_key;
+        if (r + 1 < n2 && lane < kTopK) next_key = lists[(size_t)(b2 + r + 1) * kTopK + lane];
+        if (valid2 && !valid2[b2 + r]) continue;  // robust.cc:255-262
+        // walk the sorted list, skipping taken frame keypoints
+        const bool listed = key != kInfKey;
+        bool live = false;
+        if (listed) {
+            const unsigned i1 = key_idx(key);
+            live = !((taken[i1 >> 5] >> (i1 & 31)) & 1u);
+        }
+        const unsigned live_mask = __ballot_sync(0xFFFFFFFFu, live);
+        const unsigned listed_mask = __ballot_sync(0xFFFFFFFFu, listed);
+        const bool full = listed_mask == ((1u << kTopK) - 1u);  // unlisted candidates exist only if the list is full
+        const unsigned tail_dist = key_dist(__shfl_sync(0xFFFFFFFFu, key, kTopK - 1));  // every unlisted distance >= this
+        unsigned best_key = kInfKey, second_dist = kMaxDist;
+        bool decided = false, accept = false;
+        const int l1 = __ffs(live_mask) - 1;
+        const unsigned rest = live_mask & (live_mask - 1u);
+        const int l2 = __ffs(rest) - 1;
+        if (l1 >= 0) best_key = __shfl_sync(0xFFFFFFFFu, key, l1);
+        if (l2 >= 0) second_dist = key_dist(__shfl_sync(0xFFFFFFFFu, key, l2));
+        if (!full) {
+            decided = true;  // the list holds every gated candidate: best/second are exact (256 when absent)
+        } else if (l1 >= 0 && l2 >= 0) {
+            decided = true;  // both found inside the list: nothing unlisted can precede them
+        } else if (l1 >= 0) {
+            // best is exact; the true second distance lies in [tail_dist, 256]
+            const unsigned bd = key_dist(best_key);
+            if (bd > (unsigned)kThrLow) {
+                decided = true;
+            } else if (!(__fmul_rn(lowe_ratio, (float)tail_dist) < (float)bd)) {
+                decided = true;  // passes the ratio test even with the smallest possible second distance
+                second_dist = tail_dist;
+            }
+        } else {
+            // every listed candidate is taken: the best live distance is >= tail_dist
+            if (tail_dist > (unsigned)kThrLow) {
+                decided = true;
+                best_key = kInfKey;
+            }
+        }
+        if (!decided)
+            exact_row(d1, a1, n1, taken, desc2[(size_t)(b2 + r) * 2], desc2[(size_t)(b2 + r) * 2 + 1], angle2[b2 + r], check_orientation, lane,
+                      &best_key, &second_dist);
+        if (best_key != kInfKey) {
+            const unsigned bd = key_dist(best_key);
+            // robust.cc:297-308: threshold, then Lowe ratio in float
+            accept = !(bd > (unsigned)kThrLow) && !(__fmul_rn(lowe_ratio, (float)second_dist) < (float)bd);
+        }
+        if (accept) {
+            const unsigned i1 = key_idx(best_key);
+            if (lane == 0) {
+                taken[i1 >> 5] |= 1u << (i1 & 31);
+                m21[i1] = r;
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    // robust.cc:317-325: pairs sorted by idx_1
+    int total = 0;
+    for (int base = 0; base < n1; base += 32) {
+        const int i = base + lane;
+        const int v = (i < n1) ? m21[i] : -1;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, v >= 0);
+        if (v >= 0) {
+            const int pos = total + __popc(bal & ((1u << lane) - 1u));
+            pairs[2 * ((size_t)b1 + pos)] = i;
+            pairs[2 * ((size_t)b1 + pos) + 1] = v;
+        }
+        total += __popc(bal);
+    }
+    if (lane == 0) n_pairs[p] = total;
+}
+
+struct Matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_wait = nullptr;
+    // scratch (grown on demand)
+    unsigned* d_lists = nullptr;
+    size_t lists_cap = 0;
+    int* d_matched = nullptr;
+    size_t matched_cap = 0;
+    unsigned* d_taken = nullptr;
+    size_t taken_cap = 0;
+    // staging for the host-buffer entry points
+    unsigned char* d_stage = nullptr;
+    size_t stage_cap = 0;
+
+    int grow(void** p, size_t* cap, size_t bytes) {
+        if (bytes <= *cap) return B200_OK;
+        B200_CUDA(cudaStreamSynchronize(stream));
+        if (*p) B200_CUDA(cudaFree(*p));
+        *p = nullptr;
+        *cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        B200_CUDA(cudaMalloc(p, want));
+        *cap = want;
+        return B200_OK;
+    }
+
+    int run(int n_problems, int total1, int total2, const void* desc1, const void* angle1, const void* off1, const void* desc2,
+            const void* angle2, const void* valid2, const void* off2, int max_n1, int max_n2, float lowe, int check_ori, void* pairs,
+            void* n_pairs) {
+        if (n_problems <= 0) return B200_OK;
+        if (max_n1 >= (1 << 22)) {
+            set_error("brute-force matcher supports < 4194304 keypoints per frame");
+            return B200_ERR_INVALID;
+        }
+        int rc;
+        const int taken_words = ceil_div(std::max(max_n1, 1), 32);
+        if ((rc = grow((void**)&d_lists, &lists_cap, sizeof(unsigned) * kTopK * (size_t)std::max(total2, 1)))) return rc;
+        if ((rc = grow((void**)&d_matched, &matched_cap, sizeof(int) * (size_t)std::max(total1, 1)))) return rc;
+        if ((rc = grow((void**)&d_taken, &taken_cap, sizeof(unsigned) * (size_t)taken_words * n_problems))) return rc;
+        if (max_n2 > 0)
+            topk_kernel<<<dim3(ceil_div(max_n2, kRowsPerBlock), n_problems), kRowsPerBlock, 0, stream>>>(
+                (const uint4*)desc1, (const float*)angle1, (const int*)off1, (const uint4*)desc2, (const float*)angle2,
+                (const unsigned char*)valid2, (const int*)off2, check_ori, d_lists);
+        resolve_kernel<<<n_problems, 32, 0, stream>>>((const uint4*)desc1, (const float*)angle1, (const int*)off1, (const uint4*)desc2,
+                                                      (const float*)angle2, (const unsigned char*)valid2, (const int*)off2, d_lists, lowe,
+                                                      check_ori, d_matched, d_taken, taken_words, (int*)pairs, (int*)n_pairs);
+        B200_CUDA(cudaGetLastError());
+        return B200_OK;
+    }
+};
+
+}  // namespace match
+}  // namespace b200
+
+struct b200_matcher_s {
+    b200::match::Matcher m;
+};
+
+extern "C" {
+
+int b200_matcher_create(int device, b200_matcher_t* out) {
+    if (!out) return B200_ERR_INVALID;
+    int rc = b200::require_device(device);
+    if (rc) return rc;
+    b200_matcher_s* h = new (std::nothrow) b200_matcher_s();
+    if (!h) return B200_ERR_INVALID;
+    h->m.device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->m.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->m.ev_wait, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        delete h;
+        return b200::cuda_fail(e, "stream creation", __FILE__, __LINE__);
+    }
+    *out = h;
+    return B200_OK;
+}
+
+int b200_matcher_destroy(b200_matcher_t h) {
+    if (!h) return B200_OK;
+    cudaSetDevice(h->m.device);
+    cudaStreamSynchronize(h->m.stream);
+    cudaFree(h->m.d_lists);
+    cudaFree(h->m.d_matched);
+    cudaFree(h->m.d_taken);
+    cudaFree(h->m.d_stage);
+    if (h->m.ev_wait) cudaEventDestroy(h->m.ev_wait);
+    if (h->m.stream) cudaStreamDestroy(h->m.stream);
+    delete h;
+    return B200_OK;
+}
+
+int b200_matcher_sync(b200_matcher_t h) {
+    if (!h) return B200_ERR_INVALID;
+    B200_CUDA(cudaStreamSynchronize(h->m.stream));
+    return B200_OK;
+}
+
+int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, int total1, int total2, const void* d_desc1, const void* d_angle1,
+                                 const void* d_off1, const void* d_desc2, const void* d_angle2, const void* d_valid2, const void* d_off2,
+                                 int max_n1, int max_n2, float lowe_ratio, int check_orientation, void* d_pairs, void* d_n_pairs,
+                                 void* wait_stream) {
+    if (!h || n_problems < 0 || total1 < 0 || total2 < 0) return B200_ERR_INVALID;
+    if (n_problems == 0) return B200_OK;
+    if (!d_off1 || !d_off2 || !d_pairs || !d_n_pairs || (total1 > 0 && (!d_desc1 || !d_angle1)) || (total2 > 0 && (!d_desc2 || !d_angle2))) {
+        b200::set_error("b200_match_bruteforce_device: null argument");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(h->m.device));
+    if (wait_stream) {
+        B200_CUDA(cudaEventRecord(h->m.ev_wait, (cudaStream_t)wait_stream));
+        B200_CUDA(cudaStreamWaitEvent(h->m.stream, h->m.ev_wait, 0));
+    }
+    return h->m.run(n_problems, total1, total2, d_desc1, d_angle1, d_off1, d_desc2, d_angle2, d_valid2, d_off2, max_n1, max_n2, lowe_ratio,
+                    check_orientation, d_pairs, d_n_pairs);
+}
+
+int b200_match_bruteforce(b200_matcher_t h, int n_problems, const uint8_t* desc1, const float* angle1, const int32_t* off1,
+                          const uint8_t* desc2, const float* angle2, const uint8_t* valid2, const int32_t* off2, float lowe_ratio,
+                          int check_orientation, int32_t* pairs, int32_t* n_pairs) {
+    if (!h || n_problems < 0) return B200_ERR_INVALID;
+    if (n_problems == 0) return B200_OK;
+    if (!off1 || !off2 || !pairs || !n_pairs) {
+        b200::set_error("b200_match_bruteforce: null argument");
+        return B200_ERR_INVALID;
+    }
+    auto& m = h->m;
+    B200_CUDA(cudaSetDevice(m.device));
+    const int total1 = off1[n_problems], total2 = off2[n_problems];
+    int max_n1 = 0, max_n2 = 0;
+    for (int p = 0; p < n_problems; ++p) {
+        if (off1[p + 1] < off1[p] || off2[p + 1] < off2[p]) {
+            b200::set_error("b200_match_bruteforce: offsets must be non-decreasing");
+            return B200_ERR_INVALID;
+        }
+        max_n1 = std::max(max_n1, off1[p + 1] - off1[p]);
+        max_n2 = std::max(max_n2, off2[p + 1] - off2[p]);
+    }
+    if ((total1 > 0 && (!desc1 || !angle1)) || (total2 > 0 && (!desc2 || !angle2))) {
+        b200::set_error("b200_match_bruteforce: null descriptor/angle buffer");
+        return B200_ERR_INVALID;
+    }
+    // staging layout (all 256-byte aligned): desc1 | desc2 | angle1 | angle2 | valid2 | off1 | off2 | pairs | n_pairs
+    auto al = [](size_t v) { return b200::round_up(v, (size_t)256); };
+    size_t o = 0;
+    const size_t o_d1 = o; o += al((size_t)32 * std::max(total1, 1));
+    const size_t o_d2 = o; o += al((size_t)32 * std::max(total2, 1));
+    const size_t o_a1 = o; o += al(sizeof(float) * (size_t)std::max(total1, 1));
+    const size_t o_a2 = o; o += al(sizeof(float) * (size_t)std::max(total2, 1));
+    const size_t o_v2 = o; o += al((size_t)std::max(total2, 1));
+    const size_t o_o1 = o; o += al(sizeof(int) * (size_t)(n_problems + 1));
+    const size_t o_o2 = o; o += al(sizeof(int) * (size_t)(n_problems + 1));
+    const size_t o_pr = o; o += al(sizeof(int) * 2 * (size_t)std::max(total1, 1));
+    const size_t o_np = o; o += al(sizeof(int) * (size_t)n_problems);
+    int rc = m.grow((void**)&m.d_stage, &m.stage_cap, o);
+    if (rc) return rc;
+    unsigned char* s = m.d_stage;
+    cudaStream_t st = m.stream;
+    if (total1 > 0) {
+        B200_CUDA(cudaMemcpyAsync(s + o_d1, desc1, (size_t)32 * total1, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(s + o_a1, angle1, sizeof(float) * total1, cudaMemcpyHostToDevice, st));
+    }
+    if (total2 > 0) {
+        B200_CUDA(cudaMemcpyAsync(s + o_d2, desc2, (size_t)32 * total2, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(s + o_a2, angle2, sizeof(float) * total2, cudaMemcpyHostToDevice, st));
+        if (valid2) B200_CUDA(cudaMemcpyAsync(s + o_v2, valid2, total2, cudaMemcpyHostToDevice, st));
+    }
+    B200_CUDA(cudaMemcpyAsync(s + o_o1, off1, sizeof(int) * (n_problems + 1), cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemcpyAsync(s + o_o2, off2, sizeof(int) * (n_problems + 1), cudaMemcpyHostToDevice, st));
+    rc = m.run(n_problems, total1, total2, s + o_d1, s + o_a1, s + o_o1, s + o_d2, s + o_a2, valid2 ? s + o_v2 : nullptr, s + o_o2, max_n1,
+               max_n2, lowe_ratio, check_orientation, s + o_pr, s + o_np);
+    if (rc) return rc;
+    B200_CUDA(cudaMemcpyAsync(n_pairs, s + o_np, sizeof(int) * n_problems, cudaMemcpyDeviceToHost, st));
+    if (total1 > 0) B200_CUDA(cudaMemcpyAsync(pairs, s + o_pr, sizeof(int) * 2 * (size_t)total1, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_hamming_matrix(b200_matcher_t h, const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, uint16_t* dist) {
+    if (!h || n1 < 0 || n2 < 0) return B200_ERR_INVALID;
+    if (n1 == 0 || n2 == 0) return B200_OK;
+    if (!desc1 || !desc2 || !dist) return B200_ERR_INVALID;
+    auto& m = h->m;
+    B200_CUDA(cudaSetDevice(m.device));
+    const size_t o_d2 = b200::round_up((size_t)32 * n1, (size_t)256), o_out = o_d2 + b200::round_up((size_t)32 * n2, (size_t)256);
+    int rc = m.grow((void**)&m.d_stage, &m.stage_cap, o_out + sizeof(uint16_t) * (size_t)n1 * n2);
+    if (rc) return rc;
+    unsigned char* s = m.d_stage;
+    B200_CUDA(cudaMemcpyAsync(s, desc1, (size_t)32 * n1, cudaMemcpyHostToDevice, m.stream));
+    B200_CUDA(cudaMemcpyAsync(s + o_d2, desc2, (size_t)32 * n2, cudaMemcpyHostToDevice, m.stream));
+    b200::match::hamming_matrix_kernel<<<dim3(b200::ceil_div(n2, 64), b200::ceil_div(n1, 256)), 256, 0, m.stream>>>(
+        (const uint4*)s, n1, (const uint4*)(s + o_d2), n2, (unsigned short*)(s + o_out));
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpyAsync(dist, s + o_out, sizeof(uint16_t) * (size_t)n1 * n2, cudaMemcpyDeviceToHost, m.stream));
+    B200_CUDA(cudaStreamSynchronize(m.stream));
+    return B200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,986 @@
+// orb_kernels.cu -- batched feature::orb_extractor on sm_100a.
+//
+// Reference path (paths relative to the reference checkout):
+//   orb_extractor::extract                src/stella_vslam/feature/orb_extractor.cc:28-136
+//   compute_image_pyramid (cv::resize)    orb_extractor.cc:153-162
+//   compute_fast_keypoints (cv::FAST)     orb_extractor.cc:164-287
+//   distribute_keypoints                  orb_extractor.cc:289-329
+//   ic_angle / compute_orb_descriptor     feature/orb_impl.cc:68-91, 93-154
+//   cv::GaussianBlur 7x7 sigma 2          orb_extractor.cc:103
+//
+// Design: every kernel takes a batch of same-sized frames (blockIdx.y = frame).  The order-dependent
+// parts of the reference are restated as order-free reductions: FAST candidates are never materialised as a list --
+// each surviving corner does one 64-bit atomicMax (score, inverse scan order) into its selection-grid cell, which is
+// exactly "first candidate with strictly greatest response" (orb_extractor.cc:314-323).  Keypoints are then emitted
+// by an ordered compaction of the grid (level-major, cell-index order = the reference's output order).
+//
+// Integer work is bit-exact by construction; the only floating point (fastAtan2, util::cos/sin, the rBRIEF rotation,
+// pt *= scale) uses explicit round-to-nearest intrinsics, never FMA (this file is also compiled with -fmad=false).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+namespace orb {
+
+constexpr int kMaxLevels = 16;
+constexpr int kBorder = 19;       // orb_extractor.h:107 orb_patch_radius_
+constexpr int kCell = 64;         // orb_extractor.cc:173
+constexpr int kOverlap = 6;       // orb_extractor.cc:172
+constexpr int kTileMax = kCell + kOverlap;  // 70
+constexpr int kTilePitch = 80;    // smem row pitch of a FAST tile (multiple of 16 for TMA boxes)
+
+struct LevelGeom {
+    int w, h, pitch;
+    unsigned long long offset;    // byte offset of the level inside one frame's pyramid (level 0: unused)
+    float sf;                     // scale_factors_[l]
+    int nx, ny;                   // selection grid (orb_extractor.cc:293-294)
+    double delta_x, delta_y;      // orb_extractor.cc:295-296
+    int grid_base;                // first grid cell of this level in the per-frame grid array
+    int ncols;                    // FAST cell columns (for the scan-order key)
+    float size;                   // (float)(unsigned)(31 * sf)  orb_extractor.cc:274
+    int tab_x, tab_y;             // offsets into the resize tables (level l is resampled from level l-1)
+    int blur_tile_base, blur_tiles_x;
+};
+
+struct Geom {
+    int num_levels;
+    int grid_cells;               // selection-grid cells per frame (all levels)
+    int ini_thr, min_thr;
+    LevelGeom lv[kMaxLevels];
+};
+
+struct CellDesc {                 // one FAST cell (orb_extractor.cc:199-217)
+    unsigned short level, i, j, min_x, min_y, w, h, pad;
+};
+
+struct BlurTile {
+    unsigned short level, tx, ty, pad;
+};
+
+struct RawKp {                    // keypoint before orientation/description
+    short x, y;                   // level coordinates (border already added)
+    unsigned char m;              // FAST m value; response = m - 1
+    unsigned char level;
+    unsigned short pad;
+};
+
+struct ResizeTap {                // per destination column/row: source index and the two Q11 weights
+    short ofs, w0, w1, pad;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// image access helpers: level 0 aliases the caller's frames (orb_extractor.cc:154), levels >= 1 live in the pyramid
+// ---------------------------------------------------------------------------------------------------------------
+struct Images {
+    const unsigned char* img0;
+    unsigned long long pitch0, fstride0;
+    unsigned char* pyr;
+    unsigned long long pyr_fstride;
+};
+
+__device__ __forceinline__ const unsigned char* level_ptr(const Images& im, const Geom& g, int level, int frame, int* pitch) {
+    if (level == 0) {
+        *pitch = (int)im.pitch0;
+        return im.img0 + (size_t)frame * im.fstride0;
+    }
+    *pitch = g.lv[level].pitch;
+    return im.pyr + (size_t)frame * im.pyr_fstride + g.lv[level].offset;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1: cv::resize(INTER_LINEAR) level l-1 -> l, fixed point (OpenCV resize.cpp HResizeLinear/VResizeLinear, 11 bits)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geom g, Images im, const ResizeTap* __restrict__ taps, int level) {
+    const LevelGeom& L = g.lv[level];
+    const int frame = blockIdx.z;
+    int spitch;
+    const unsigned char* src = level_ptr(im, g, level - 1, frame, &spitch);
+    unsigned char* dst = im.pyr + (size_t)frame * im.pyr_fstride + L.offset;
+    const int sw = g.lv[level - 1].w;
+    const int dy = blockIdx.y * blockDim.y + threadIdx.y;
+    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (dy >= L.h || dx0 >= L.pitch) return;
+    const ResizeTap ty = taps[L.tab_y + dy];
+    const int sh = g.lv[level - 1].h;
+    const int sy0 = min(max((int)ty.ofs, 0), sh - 1), sy1 = min(max((int)ty.ofs + 1, 0), sh - 1);
+    const unsigned char* r0 = src + (size_t)sy0 * spitch;
+    const unsigned char* r1 = src + (size_t)sy1 * spitch;
+    unsigned out = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int dx = dx0 + k;
+        unsigned v = 0;
+        if (dx < L.w) {
+            const ResizeTap tx = taps[L.tab_x + dx];
+            const int sx = tx.ofs, sx1 = min(sx + 1, sw - 1);
+            const int h0 = r0[sx] * tx.w0 + r0[sx1] * tx.w1;
+            const int h1 = r1[sx] * tx.w0 + r1[sx1] * tx.w1;
+            const int val = (((ty.w0 * (h0 >> 4)) >> 16) + ((ty.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
+            v = (unsigned)min(max(val, 0), 255);
+        }
+        out |= v << (8 * k);
+    }
+    *reinterpret_cast<unsigned*>(dst + (size_t)dy * L.pitch + dx0) = out;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2: FAST-9/16 + 3x3 NMS per 64-px cell with the per-cell threshold retry, mask tests, and the selection-grid
+//     arg-max.  One block per (cell, frame).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool has_run9(unsigned m16) {
+    unsigned m = m16 | (m16 << 16);
+    unsigned x = m & (m >> 1);
+    x &= x >> 2;
+    x &= x >> 4;
+    x &= m >> 8;
+    return (x & 0xFFFFu) != 0;
+}
+
+// circle offsets in a tile of pitch kTilePitch, OpenCV order (fast.cpp makeOffsets, patternSize 16)
+#define FAST_OFF(k, P)                                                                                              \
+    ((k) == 0 ? 3 * (P) : (k) == 1 ? 3 * (P) + 1 : (k) == 2 ? 2 * (P) + 2 : (k) == 3 ? (P) + 3 : (k) == 4 ? 3      \
+     : (k) == 5 ? -(P) + 3 : (k) == 6 ? -2 * (P) + 2 : (k) == 7 ? -3 * (P) + 1 : (k) == 8 ? -3 * (P)              \
+     : (k) == 9 ? -3 * (P)-1 : (k) == 10 ? -2 * (P)-2 : (k) == 11 ? -(P)-3 : (k) == 12 ? -3                        \
+     : (k) == 13 ? (P)-3 : (k) == 14 ? 2 * (P)-2 : 3 * (P)-1)
+
+__device__ __forceinline__ bool mask_zero(const unsigned char* mask, unsigned long long mask_pitch, unsigned y, unsigned x, float sf) {
+    // orb_extractor.cc:168-170: mask.at<uchar>(y * scale_factor, x * scale_factor): float product, truncation
+    const int r = (int)__fmul_rn((float)y, sf), c = (int)__fmul_rn((float)x, sf);
+    return mask[(size_t)r * mask_pitch + c] == 0;
+}
+
+__global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ Geom g, Images im, const CellDesc* __restrict__ cells,
+                                                         const unsigned char* __restrict__ mask, unsigned long long mask_pitch,
+                                                         unsigned long long* __restrict__ grid) {
+    __shared__ __align__(16) unsigned char tile[kTileMax * kTilePitch];
+    __shared__ __align__(16) unsigned char mmap[kTileMax * kTilePitch];
+    __shared__ unsigned short queue[kCell * kCell];
+    __shared__ int q_count;
+    __shared__ int skip;
+
+    const CellDesc cd = cells[blockIdx.x];
+    const int frame = blockIdx.y;
+    const int level = cd.level;
+    const LevelGeom& L = g.lv[level];
+    const int cw = cd.w, ch = cd.h;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        q_count = 0;
+        int s = 0;
+        if (mask) {  // orb_extractor.cc:219-225: skip the cell if one of its corners is masked
+            const unsigned max_x = cd.min_x + cw, max_y = cd.min_y + ch;
+            s = mask_zero(mask, mask_pitch, cd.min_y, cd.min_x, L.sf) || mask_zero(mask, mask_pitch, max_y, cd.min_x, L.sf)
+                || mask_zero(mask, mask_pitch, cd.min_y, max_x, L.sf) || mask_zero(mask, mask_pitch, max_y, max_x, L.sf);
+        }
+        skip = s;
+    }
+    int pitch;
+    const unsigned char* src = level_ptr(im, g, level, frame, &pitch);
+    src += (size_t)cd.min_y * pitch + cd.min_x;
+    for (int idx = tid; idx < ch * kTilePitch; idx += blockDim.x) {
+        const int y = idx / kTilePitch, x = idx - y * kTilePitch;
+        tile[idx] = (x < cw) ? src[(size_t)y * pitch + x] : 0;
+        mmap[idx] = 0;
+    }
+    __syncthreads();
+    if (skip) return;
+
+    const int t_low = min(g.ini_thr, g.min_thr);
+    const int ccw = cw - 6, cch = ch - 6;  // candidate region x in [3, w-4], y in [3, h-4]
+    // phase A: corner test at the lower threshold with 16-bit brighter/darker masks
+    for (int idx = tid; idx < ccw * cch; idx += blockDim.x) {
+        const int ly = 3 + idx / ccw, lx = 3 + idx % ccw;
+        const unsigned char* c = tile + ly * kTilePitch + lx;
+        const int v = c[0], hi = v + t_low, lo = v - t_low;
+        unsigned br = 0, dk = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int p = c[FAST_OFF(k, kTilePitch)];
+            br |= (unsigned)(p > hi) << k;
+            dk |= (unsigned)(p < lo) << k;
+        }
+        if (has_run9(br) || has_run9(dk)) {
+            const int q = atomicAdd(&q_count, 1);
+            queue[q] = (unsigned short)(ly * kTilePitch + lx);
+        }
+    }
+    __syncthreads();
+    // phase B: exact m = max over 9-arcs of min(v - p) / min(p - v) for the corners only (cornerScore<16> + 1)
+    const int nq = q_count;
+    for (int qi = tid; qi < nq; qi += blockDim.x) {
+        const int pos = queue[qi];
+        const unsigned char* c = tile + pos;
+        const int v = c[0];
+        int d[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) d[k] = v - (int)c[FAST_OFF(k, kTilePitch)];
+        int mn[16], mx[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            mn[k] = min(d[k], d[(k + 1) & 15]);
+            mx[k] = max(d[k], d[(k + 1) & 15]);
+        }
+        int mn4[16], mx4[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            mn4[k] = min(mn[k], mn[(k + 2) & 15]);
+            mx4[k] = max(mx[k], mx[(k + 2) & 15]);
+        }
+        int best = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int a = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);   // min over d[k..k+8]
+            const int b = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);   // max over d[k..k+8]
+            best = max(best, max(a, -b));
+        }
+        mmap[pos] = (unsigned char)min(best, 255);
+    }
+    __syncthreads();
+    // phase C: strict 3x3 local maximum of m (threshold independent), then the per-cell threshold choice
+    //          (orb_extractor.cc:228-235: retry the whole cell at min_fast_thr only if it is empty at ini_fast_thr)
+    unsigned keep_bits = 0;  // one bit per loop iteration of this thread
+    bool any_ini = false;
+    {
+        int it = 0;
+        for (int idx = tid; idx < ccw * cch; idx += blockDim.x, ++it) {
+            const int ly = 3 + idx / ccw, lx = 3 + idx % ccw;
+            const unsigned char* p = mmap + ly * kTilePitch + lx;
+            const int mv = p[0];
+            if (mv < 2) continue;
+            // neighbours outside the candidate region are non-candidates (score 0): rows/cols 2 and w-3/h-3 hold 0
+            const bool is_max = mv > p[-1] && mv > p[1] && mv > p[-kTilePitch - 1] && mv > p[-kTilePitch] && mv > p[-kTilePitch + 1]
+                                && mv > p[kTilePitch - 1] && mv > p[kTilePitch] && mv > p[kTilePitch + 1];
+            if (is_max) {
+                keep_bits |= 1u << it;
+                any_ini |= (mv > g.ini_thr);
+            }
+        }
+    }
+    const int cell_has_ini = __syncthreads_or(any_ini);
+    const int thr = cell_has_ini ? g.ini_thr : g.min_thr;
+    // phase D: mask test per keypoint, selection-grid cell, ordered arg-max via 64-bit atomicMax
+    {
+        int it = 0;
+        for (int idx = tid; idx < ccw * cch; idx += blockDim.x, ++it) {
+            if (!((keep_bits >> it) & 1u)) continue;
+            const int ly = 3 + idx / ccw, lx = 3 + idx % ccw;
+            const int mv = mmap[ly * kTilePitch + lx];
+            if (mv <= thr) continue;
+            // keypt.pt += (j*64, i*64) (orb_extractor.cc:241-244): coordinates relative to the (19,19) border origin
+            const int px = lx + cd.j * kCell, py = ly + cd.i * kCell;
+            if (mask && mask_zero(mask, mask_pitch, (unsigned)(kBorder + py), (unsigned)(kBorder + px), L.sf)) continue;
+            const unsigned ix = (unsigned)((double)(float)px / L.delta_x);  // orb_extractor.cc:303-305
+            const unsigned iy = (unsigned)((double)(float)py / L.delta_y);
+            const unsigned cell = ix + iy * (unsigned)L.nx;
+            const unsigned order = ((unsigned)(cd.i * L.ncols + cd.j) << 14) | ((unsigned)ly << 7) | (unsigned)lx;
+            const unsigned long long val = ((unsigned long long)mv << 32) | (unsigned long long)(0xFFFFFFFFu - order);
+            atomicMax(grid + (size_t)frame * g.grid_cells + L.grid_base + cell, val);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K3: ordered compaction of the selection grid -> per-frame raw keypoint list in the reference's output order
+//     (level-major, grid-cell index ascending; orb_extractor.cc:309-326, 132-135).  One block per (level, frame).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Geom g, const unsigned long long* __restrict__ grid,
+                                                     RawKp* __restrict__ raw, int raw_stride, int* __restrict__ counts,
+                                                     int* __restrict__ level_counts) {
+    __shared__ int warp_sums[8];
+    __shared__ int running;
+    const int level = blockIdx.x, frame = blockIdx.y;
+    const LevelGeom& L = g.lv[level];
+    const unsigned long long* gf = grid + (size_t)frame * g.grid_cells;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // offset = keypoints of all lower levels
+    int below = 0;
+    for (int base = 0; base < L.grid_base; base += blockDim.x) {
+        const int i = base + tid;
+        below += __syncthreads_count(i < L.grid_base && gf[i] != 0ull);
+    }
+    if (tid == 0) running = below;
+    __syncthreads();
+    const int n_cells = L.nx * L.ny;
+    for (int base = 0; base < n_cells; base += blockDim.x) {
+        const int i = base + tid;
+        const unsigned long long v = (i < n_cells) ? gf[L.grid_base + i] : 0ull;
+        const bool has = v != 0ull;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, has);
+        if (lane == 0) warp_sums[wid] = __popc(bal);
+        __syncthreads();
+        int off = running;
+        for (int w = 0; w < wid; ++w) off += warp_sums[w];
+        if (has) {
+            const int pos = off + __popc(bal & ((1u << lane) - 1u));
+            const unsigned order = 0xFFFFFFFFu - (unsigned)(v & 0xFFFFFFFFull);
+            const int lx = order & 127, ly = (order >> 7) & 127, cidx = order >> 14;
+            const int ci = cidx / L.ncols, cj = cidx - ci * L.ncols;
+            RawKp k;
+            k.x = (short)(kBorder + cj * kCell + lx);
+            k.y = (short)(kBorder + ci * kCell + ly);
+            k.m = (unsigned char)(v >> 32);
+            k.level = (unsigned char)level;
+            k.pad = 0;
+            raw[(size_t)frame * raw_stride + pos] = k;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int s = 0;
+            for (int w = 0; w < 8; ++w) s += warp_sums[w];
+            running += s;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        level_counts[frame * kMaxLevels + level] = running - below;
+        if (level == g.num_levels - 1) counts[frame] = running;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K4: cv::GaussianBlur 7x7 sigma 2 REFLECT_101 on u8, OpenCV's fixed-point path: Q8.8 taps {18,34,48,56,48,34,18},
+//     16-bit horizontal pass, Q16.16 vertical pass, round to nearest.  One block per 64x32 output tile.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBlurTW = 64, kBlurTH = 32;
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return min(max(i, 0), n - 1);  // (levels narrower than 4 px never carry keypoints)
+}
+
+__global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geom g, Images im, const BlurTile* __restrict__ tiles,
+                                                   unsigned char* __restrict__ blurred, unsigned long long blur_fstride) {
+    __shared__ unsigned char in[(kBlurTH + 6) * (kBlurTW + 8)];
+    __shared__ unsigned short hp[(kBlurTH + 6) * kBlurTW];
+    const BlurTile bt = tiles[blockIdx.x];
+    const int frame = blockIdx.y, level = bt.level;
+    const LevelGeom& L = g.lv[level];
+    int pitch;
+    const unsigned char* src = level_ptr(im, g, level, frame, &pitch);
+    const int x0 = bt.tx * kBlurTW, y0 = bt.ty * kBlurTH;
+    constexpr int IW = kBlurTW + 8;  // 6 halo columns + 2 pad
+    for (int idx = threadIdx.x; idx < (kBlurTH + 6) * (kBlurTW + 6); idx += blockDim.x) {
+        const int r = idx / (kBlurTW + 6), c = idx - r * (kBlurTW + 6);
+        const int sy = reflect101(y0 + r - 3, L.h), sx = reflect101(x0 + c - 3, L.w);
+        in[r * IW + c] = (sy >= 0 && sy < L.h && sx >= 0 && sx < L.w) ? src[(size_t)sy * pitch + sx] : 0;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < (kBlurTH + 6) * kBlurTW; idx += blockDim.x) {
+        const int r = idx / kBlurTW, c = idx - r * kBlurTW;
+        const unsigned char* p = in + r * IW + c;
+        hp[idx] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    }
+    __syncthreads();
+    unsigned char* dst = blurred + (size_t)frame * blur_fstride + L.offset;
+    for (int idx = threadIdx.x; idx < kBlurTH * kBlurTW / 4; idx += blockDim.x) {
+        const int r = idx / (kBlurTW / 4), c4 = (idx - r * (kBlurTW / 4)) * 4;
+        const int y = y0 + r;
+        if (y >= L.h || x0 + c4 >= L.pitch) continue;
+        unsigned out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned short* q = hp + r * kBlurTW + c4 + k;
+            unsigned acc = 18u * (q[0] + q[6 * kBlurTW]) + 34u * (q[kBlurTW] + q[5 * kBlurTW]) + 48u * (q[2 * kBlurTW] + q[4 * kBlurTW])
+                           + 56u * q[3 * kBlurTW];
+            acc = (acc + 32768u) >> 16;
+            out |= min(acc, 255u) << (8 * k);
+        }
+        *reinterpret_cast<unsigned*>(dst + (size_t)y * L.pitch + x0 + c4) = out;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K5: IC-angle orientation on the un-blurred level + rBRIEF on the blurred level + scale correction.
+//     One warp per keypoint; lane u-15 sums column u of the disc, lane i produces descriptor byte i.
+// ---------------------------------------------------------------------------------------------------------------
+__constant__ signed char c_pattern[1024] = {
+#include "orb_pattern.inc"
+};
+__constant__ int c_umax[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // orb_impl.cc:51-66
+
+// cv::fastAtan2 scalar path (OpenCV mathfuncs_core atan_f32), degrees
+__device__ __forceinline__ float fast_atan2_deg(float y, float x) {
+    const float rad2deg = (float)(180 / 3.1415926535897932384626433832795);
+    const float p1 = __fmul_rn(0.9997878412794807f, rad2deg), p3 = __fmul_rn(-0.3258083974640975f, rad2deg);
+    const float p5 = __fmul_rn(0.1555786518463281f, rad2deg), p7 = __fmul_rn(-0.04432655554792128f, rad2deg);
+    const float eps = (float)2.2204460492503131e-16;
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+    } else {
+        c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+        c2 = __fmul_rn(c, c);
+        a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+    }
+    if (x < 0) a = __fsub_rn(180.f, a);
+    if (y < 0) a = __fsub_rn(360.f, a);
+    return a;
+}
+
+// util::cos / util::sin (util/trigonometric.h:11-46)
+__device__ __forceinline__ float poly_cos(float v) {
+    const float v2 = __fmul_rn(v, v);
+    return __fadd_rn(0.99940307f, __fmul_rn(v2, __fadd_rn(-0.49558072f, __fmul_rn(0.03679168f, v2))));
+}
+__device__ __forceinline__ float util_cos(float v) {
+    const float PI = 3.14159265358979f;
+    const float PI_2 = __fdiv_rn(PI, 2.0f), TWO_PI = __fmul_rn(2.0f, PI);
+    const float INV_TWO_PI = __fdiv_rn(1.0f, TWO_PI), THREE_PI_2 = __fmul_rn(3.0f, PI_2);
+    v = __fsub_rn(v, __fmul_rn((float)__float2int_rd(__fmul_rn(v, INV_TWO_PI)), TWO_PI));
+    v = (0.0f < v) ? v : -v;
+    if (v < PI_2) return poly_cos(v);
+    if (v < PI) return -poly_cos(__fsub_rn(PI, v));
+    if (v < THREE_PI_2) return -poly_cos(__fsub_rn(v, PI));
+    return poly_cos(__fsub_rn(TWO_PI, v));
+}
+__device__ __forceinline__ float util_sin(float v) {
+    const float PI_2 = __fdiv_rn(3.14159265358979f, 2.0f);
+    return util_cos(__fsub_rn(PI_2, v));
+}
+
+constexpr int kDescWarps = 8;           // warps per block
+constexpr int kDescBlocksPerFrame = 16;  // blockIdx.x range; each warp strides over its frame's keypoints
+
+__global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_constant__ Geom g, Images im,
+                                                                   const unsigned char* __restrict__ blurred, unsigned long long blur_fstride,
+                                                                   const RawKp* __restrict__ raw, int raw_stride, const int* __restrict__ counts,
+                                                                   b200_keypoint_t* __restrict__ kps, unsigned char* __restrict__ descs) {
+    const int frame = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int warp = blockIdx.x * kDescWarps + (threadIdx.x >> 5);
+    const int n = counts[frame];
+    for (int k = warp; k < n; k += kDescBlocksPerFrame * kDescWarps) {
+        const RawKp rk = raw[(size_t)frame * raw_stride + k];
+        const int level = rk.level;
+        const LevelGeom& L = g.lv[level];
+        int pitch;
+        const unsigned char* img = level_ptr(im, g, level, frame, &pitch);
+        const unsigned char* c = img + (size_t)rk.y * pitch + rk.x;
+        // ---- ic_angle (orb_impl.cc:68-91): m10 = sum u*I, m01 = sum v*I over the radius-15 disc
+        int m10 = 0, m01 = 0;
+        if (lane < 31) {
+            const int u = lane - 15, au = abs(u);
+            int col = 0;
+#pragma unroll
+            for (int v = -15; v <= 15; ++v) {
+                if (au <= c_umax[v < 0 ? -v : v]) {
+                    const int val = c[v * pitch + u];
+                    col += val;
+                    m01 += v * val;
+                }
+            }
+            m10 = u * col;
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, s);
+            m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, s);
+        }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        // ---- compute_orb_descriptor (orb_impl.cc:93-154) on the blurred level
+        const float arad = (float)((double)angle * 3.14159265358979323846 / 180.0);
+        const float ca = util_cos(arad), sa = util_sin(arad);
+        const unsigned char* bc = blurred + (size_t)frame * blur_fstride + L.offset + (size_t)rk.y * L.pitch + rk.x;
+        const int bp = L.pitch;
+        unsigned val = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            const signed char* p = c_pattern + (lane * 8 + b) * 4;
+            const float x0 = p[0], y0 = p[1], x1 = p[2], y1 = p[3];
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
+            val |= (unsigned)(bc[r0 * bp + c0] < bc[r1 * bp + c1]) << b;
+        }
+        const size_t o = (size_t)frame * raw_stride + k;
+        descs[o * 32 + lane] = (unsigned char)val;
+        if (lane == 0) {
+            b200_keypoint_t kp;
+            float x = (float)rk.x, y = (float)rk.y;
+            if (level > 0) {  // correct_keypoint_scale (orb_extractor.cc:337-345)
+                x = __fmul_rn(x, L.sf);
+                y = __fmul_rn(y, L.sf);
+            }
+            kp.x = x;
+            kp.y = y;
+            kp.size = L.size;
+            kp.angle = angle;
+            kp.response = (float)(rk.m - 1);
+            kp.octave = level;
+            kps[o] = kp;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side: geometry, tables, arenas
+// ---------------------------------------------------------------------------------------------------------------
+static inline short sat_short_rint(float v) {
+    long r = lrintf(v);
+    return (short)std::min(32767L, std::max(-32768L, r));
+}
+static inline int floor_to_int(float v) {
+    int i = (int)v;
+    return i - (v < (float)i);
+}
+
+struct Extractor {
+    b200_orb_params_t prm{};
+    std::vector<float> mask_rects;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_wait = nullptr;
+    cudaEvent_t ev[8] = {};
+    bool timing = false;
+    float stage_ms[6] = {};
+    // configured geometry
+    int width = 0, height = 0, batch_cap = 0;
+    Geom geom{};
+    std::vector<float> sf;
+    int n_cells = 0, n_blur_tiles = 0, raw_stride = 0;
+    size_t pyr_fstride = 0, img0_pitch = 0, img0_fstride = 0;
+    // device arenas
+    unsigned char *d_img0 = nullptr, *d_pyr = nullptr, *d_blur = nullptr, *d_rect_mask = nullptr, *d_user_mask = nullptr;
+    CellDesc* d_cells = nullptr;
+    BlurTile* d_tiles = nullptr;
+    ResizeTap* d_taps = nullptr;
+    unsigned long long* d_grid = nullptr;
+    RawKp* d_raw = nullptr;
+    int *d_counts = nullptr, *d_level_counts = nullptr;
+    b200_keypoint_t* d_kps = nullptr;
+    unsigned char* d_descs = nullptr;
+    int* h_counts = nullptr;  // pinned
+    int last_batch = 0;
+    bool rect_mask_ready = false;
+
+    void free_arenas() {
+        cudaFree(d_img0); cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_rect_mask); cudaFree(d_user_mask);
+        cudaFree(d_cells); cudaFree(d_tiles); cudaFree(d_taps); cudaFree(d_grid); cudaFree(d_raw);
+        cudaFree(d_counts); cudaFree(d_level_counts); cudaFree(d_kps); cudaFree(d_descs);
+        if (h_counts) cudaFreeHost(h_counts);
+        d_img0 = d_pyr = d_blur = d_rect_mask = d_user_mask = nullptr;
+        d_cells = nullptr; d_tiles = nullptr; d_taps = nullptr; d_grid = nullptr; d_raw = nullptr;
+        d_counts = d_level_counts = nullptr; d_kps = nullptr; d_descs = nullptr; h_counts = nullptr;
+        rect_mask_ready = false;
+    }
+
+    static int level_geometry(const b200_orb_params_t& prm, int w, int h, Geom& g, std::vector<float>& sf) {
+        const int nl = prm.num_levels;
+        sf.assign(nl, 1.0f);
+        for (int l = 1; l < nl; ++l) sf[l] = prm.scale_factor * sf[l - 1];  // orb_params.cc:37-43
+        g = Geom{};
+        g.num_levels = nl;
+        g.ini_thr = std::min(255, std::max(0, prm.ini_fast_thr));
+        g.min_thr = std::min(255, std::max(0, prm.min_fast_thr));
+        const unsigned min_area_sqrt = (unsigned)std::sqrt((double)prm.min_area);  // orb_extractor.cc:20
+        unsigned long long off = 0;
+        int grid_base = 0;
+        for (int l = 0; l < nl; ++l) {
+            LevelGeom& L = g.lv[l];
+            if (l == 0) {
+                L.w = w;
+                L.h = h;
+            } else {  // orb_extractor.cc:157-158
+                const double scale = sf[l];
+                L.w = (int)std::round(w * 1.0 / scale);
+                L.h = (int)std::round(h * 1.0 / scale);
+            }
+            if (L.w < 1 || L.h < 1) {
+                set_error("pyramid level %d of a %dx%d image is empty", l, w, h);
+                return B200_ERR_INVALID;
+            }
+            L.pitch = round_up(L.w, 64);
+            L.offset = off;
+            off += round_up((unsigned long long)L.pitch * L.h, 256ull);
+            L.sf = sf[l];
+            L.size = (float)(unsigned)(31 * sf[l]);
+            L.grid_base = grid_base;
+            if (L.w > 2 * kBorder && L.h > 2 * kBorder) {
+                const int span_x = L.w - 2 * kBorder, span_y = L.h - 2 * kBorder;
+                const double s = (double)((float)min_area_sqrt / sf[l]);  // unsigned / float, then widened
+                L.nx = (int)(unsigned)std::ceil(span_x / s);
+                L.ny = (int)(unsigned)std::ceil(span_y / s);
+                L.delta_x = (double)span_x / L.nx;
+                L.delta_y = (double)span_y / L.ny;
+                L.ncols = span_x / kCell + 1;
+            } else {
+                L.nx = L.ny = 0;
+                L.delta_x = L.delta_y = 1.0;
+                L.ncols = 1;
+            }
+            grid_base += L.nx * L.ny;
+        }
+        g.grid_cells = grid_base;
+        return B200_OK;
+    }
+
+    int configure(int w, int h, int batch) {
+        if (w == width && h == height && batch <= batch_cap) return B200_OK;
+        B200_CUDA(cudaStreamSynchronize(stream));
+        free_arenas();
+        width = height = batch_cap = 0;
+        int rc = level_geometry(prm, w, h, geom, sf);
+        if (rc) return rc;
+        const int nl = geom.num_levels;
+        // FAST cells in the reference's scan order (orb_extractor.cc:199-217)
+        std::vector<CellDesc> cells;
+        std::vector<BlurTile> tiles;
+        std::vector<ResizeTap> taps;
+        for (int l = 0; l < nl; ++l) {
+            LevelGeom& L = geom.lv[l];
+            if (L.w > 2 * kBorder && L.h > 2 * kBorder) {
+                const unsigned max_bx = L.w - kBorder, max_by = L.h - kBorder;
+                const unsigned ncols = (max_bx - kBorder) / kCell + 1, nrows = (max_by - kBorder) / kCell + 1;
+                for (unsigned i = 0; i < nrows; ++i) {
+                    const unsigned min_y = kBorder + i * kCell;
+                    if (max_by - kOverlap <= min_y) continue;
+                    const unsigned max_y = std::min(min_y + kCell + kOverlap, max_by);
+                    for (unsigned j = 0; j < ncols; ++j) {
+                        const unsigned min_x = kBorder + j * kCell;
+                        if (max_bx - kOverlap <= min_x) continue;
+                        const unsigned max_x = std::min(min_x + kCell + kOverlap, max_bx);
+                        CellDesc c{};
+                        c.level = (unsigned short)l; c.i = (unsigned short)i; c.j = (unsigned short)j;
+                        c.min_x = (unsigned short)min_x; c.min_y = (unsigned short)min_y;
+                        c.w = (unsigned short)(max_x - min_x); c.h = (unsigned short)(max_y - min_y);
+                        cells.push_back(c);
+                    }
+                }
+            }
+            L.blur_tile_base = (int)tiles.size();
+            L.blur_tiles_x = ceil_div(L.w, kBlurTW);
+            for (int ty = 0; ty < ceil_div(L.h, kBlurTH); ++ty)
+                for (int tx = 0; tx < L.blur_tiles_x; ++tx) tiles.push_back(BlurTile{(unsigned short)l, (unsigned short)tx, (unsigned short)ty, 0});
+            // resize taps l-1 -> l (OpenCV resize.cpp: fx clamped at the borders, rows clipped)
+            if (l > 0) {
+                const LevelGeom& S = geom.lv[l - 1];
+                const double inv_sx = (double)L.w / S.w, inv_sy = (double)L.h / S.h;
+                const double scale_x = 1. / inv_sx, scale_y = 1. / inv_sy;
+                L.tab_x = (int)taps.size();
+                for (int dx = 0; dx < L.w; ++dx) {
+                    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+                    int sx = floor_to_int(fx);
+                    fx -= sx;
+                    if (sx < 0) { fx = 0; sx = 0; }
+                    if (sx >= S.w - 1) { fx = 0; sx = S.w - 1; }
+                    taps.push_back(ResizeTap{(short)sx, sat_short_rint((1.f - fx) * 2048.f), sat_short_rint(fx * 2048.f), 0});
+                }
+                L.tab_y = (int)taps.size();
+                for (int dy = 0; dy < L.h; ++dy) {
+                    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+                    int sy = floor_to_int(fy);
+                    fy -= sy;
+                    taps.push_back(ResizeTap{(short)sy, sat_short_rint((1.f - fy) * 2048.f), sat_short_rint(fy * 2048.f), 0});
+                }
+            }
+        }
+        if (geom.lv[0].w > 32767 || geom.lv[0].h > 32767) {
+            set_error("image %dx%d too large", w, h);
+            return B200_ERR_INVALID;
+        }
+        n_cells = (int)cells.size();
+        n_blur_tiles = (int)tiles.size();
+        raw_stride = std::max(1, geom.grid_cells);
+        unsigned long long total = 0;
+        for (int l = 0; l < nl; ++l) total = geom.lv[l].offset + round_up((unsigned long long)geom.lv[l].pitch * geom.lv[l].h, 256ull);
+        pyr_fstride = total;
+        img0_pitch = geom.lv[0].pitch;
+        img0_fstride = round_up((size_t)img0_pitch * h, (size_t)256);
+
+        B200_CUDA(cudaMalloc(&d_img0, img0_fstride * batch));
+        B200_CUDA(cudaMalloc(&d_pyr, pyr_fstride * batch));
+        B200_CUDA(cudaMalloc(&d_blur, pyr_fstride * batch));
+        B200_CUDA(cudaMalloc(&d_user_mask, img0_fstride));
+        B200_CUDA(cudaMalloc(&d_cells, sizeof(CellDesc) * std::max(1, n_cells)));
+        B200_CUDA(cudaMalloc(&d_tiles, sizeof(BlurTile) * std::max(1, n_blur_tiles)));
+        B200_CUDA(cudaMalloc(&d_taps, sizeof(ResizeTap) * std::max<size_t>(1, taps.size())));
+        B200_CUDA(cudaMalloc(&d_grid, sizeof(unsigned long long) * (size_t)raw_stride * batch));
+        B200_CUDA(cudaMalloc(&d_raw, sizeof(RawKp) * (size_t)raw_stride * batch));
+        B200_CUDA(cudaMalloc(&d_counts, sizeof(int) * batch));
+        B200_CUDA(cudaMalloc(&d_level_counts, sizeof(int) * kMaxLevels * batch));
+        B200_CUDA(cudaMalloc(&d_kps, sizeof(b200_keypoint_t) * (size_t)raw_stride * batch));
+        B200_CUDA(cudaMalloc(&d_descs, (size_t)32 * raw_stride * batch));
+        B200_CUDA(cudaHostAlloc(&h_counts, sizeof(int) * (kMaxLevels + 1) * batch, cudaHostAllocDefault));
+        if (n_cells) B200_CUDA(cudaMemcpyAsync(d_cells, cells.data(), sizeof(CellDesc) * n_cells, cudaMemcpyHostToDevice, stream));
+        if (n_blur_tiles) B200_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(BlurTile) * n_blur_tiles, cudaMemcpyHostToDevice, stream));
+        if (!taps.empty()) B200_CUDA(cudaMemcpyAsync(d_taps, taps.data(), sizeof(ResizeTap) * taps.size(), cudaMemcpyHostToDevice, stream));
+        // create_rectangle_mask (orb_extractor.cc:138-151): zero set of the filled rectangles
+        if (!mask_rects.empty()) {
+            std::vector<unsigned char> m((size_t)img0_pitch * h, 255);
+            for (size_t r = 0; r + 3 < mask_rects.size(); r += 4) {
+                const unsigned x_min = (unsigned)std::round(w * mask_rects[r]), x_max = (unsigned)std::round(w * mask_rects[r + 1]);
+                const unsigned y_min = (unsigned)std::round(h * mask_rects[r + 2]), y_max = (unsigned)std::round(h * mask_rects[r + 3]);
+                for (unsigned y = y_min; y <= y_max && y < (unsigned)h; ++y)
+                    for (unsigned x = x_min; x <= x_max && x < (unsigned)w; ++x) m[(size_t)y * img0_pitch + x] = 0;
+            }
+            B200_CUDA(cudaMalloc(&d_rect_mask, (size_t)img0_pitch * h));
+            B200_CUDA(cudaMemcpyAsync(d_rect_mask, m.data(), m.size(), cudaMemcpyHostToDevice, stream));
+            B200_CUDA(cudaStreamSynchronize(stream));
+            rect_mask_ready = true;
+        }
+        B200_CUDA(cudaStreamSynchronize(stream));
+        width = w;
+        height = h;
+        batch_cap = batch;
+        return B200_OK;
+    }
+
+    int run(const void* d_images, size_t pitch, size_t fstride, int batch, const void* d_mask, size_t mask_pitch) {
+        Images im{(const unsigned char*)d_images, pitch, fstride, d_pyr, pyr_fstride};
+        const unsigned char* mask = (const unsigned char*)d_mask;
+        unsigned long long mpitch = mask_pitch;
+        if (!mask && rect_mask_ready) {  // orb_extractor.cc:50-64: image mask first, else rectangle mask
+            mask = d_rect_mask;
+            mpitch = img0_pitch;
+        }
+        const int nl = geom.num_levels;
+        if (timing) B200_CUDA(cudaEventRecord(ev[0], stream));
+        for (int l = 1; l < nl; ++l) {
+            const LevelGeom& L = geom.lv[l];
+            dim3 blk(64, 4), grd(ceil_div(L.pitch / 4, 64), ceil_div(L.h, 4), batch);
+            resize_kernel<<<grd, blk, 0, stream>>>(geom, im, d_taps, l);
+        }
+        if (timing) B200_CUDA(cudaEventRecord(ev[1], stream));
+        B200_CUDA(cudaMemsetAsync(d_grid, 0, sizeof(unsigned long long) * (size_t)raw_stride * batch, stream));
+        if (n_cells) fast_cells_kernel<<<dim3(n_cells, batch), 256, 0, stream>>>(geom, im, d_cells, mask, mpitch, d_grid);
+        if (timing) B200_CUDA(cudaEventRecord(ev[2], stream));
+        select_kernel<<<dim3(nl, batch), 256, 0, stream>>>(geom, d_grid, d_raw, raw_stride, d_counts, d_level_counts);
+        if (timing) B200_CUDA(cudaEventRecord(ev[3], stream));
+        blur_kernel<<<dim3(n_blur_tiles, batch), 256, 0, stream>>>(geom, im, d_tiles, d_blur, pyr_fstride);
+        if (timing) B200_CUDA(cudaEventRecord(ev[4], stream));
+        describe_kernel<<<dim3(kDescBlocksPerFrame, batch), kDescWarps * 32, 0, stream>>>(geom, im, d_blur, pyr_fstride, d_raw, raw_stride,
+                                                                                         d_counts, d_kps, d_descs);
+        if (timing) B200_CUDA(cudaEventRecord(ev[5], stream));
+        B200_CUDA(cudaGetLastError());
+        last_batch = batch;
+        return B200_OK;
+    }
+};
+
+}  // namespace orb
+}  // namespace b200
+
+using b200::orb::Extractor;
+
+struct b200_orb_s {
+    Extractor ex;
+};
+
+extern "C" {
+
+void b200_orb_default_params(b200_orb_params_t* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->scale_factor = 1.2f;  // orb_params.cc:9-10
+    p->num_levels = 8;
+    p->ini_fast_thr = 20;
+    p->min_fast_thr = 7;
+    p->min_area = 800;       // system.cc:95
+    p->max_batch = 1;
+}
+
+int b200_orb_create(const b200_orb_params_t* p, b200_orb_t* out) {
+    if (!p || !out) {
+        b200::set_error("b200_orb_create: null argument");
+        return B200_ERR_INVALID;
+    }
+    if (p->num_levels < 1 || p->num_levels > b200::orb::kMaxLevels || !(p->scale_factor > 1.0f) || p->min_area < 1
+        || p->n_mask_rects < 0 || (p->n_mask_rects > 0 && !p->mask_rects)) {
+        b200::set_error("b200_orb_create: invalid parameters (levels %d, scale %f, min_area %u)", p->num_levels, p->scale_factor, p->min_area);
+        return B200_ERR_INVALID;
+    }
+    int rc = b200::require_device(p->device);
+    if (rc) return rc;
+    b200_orb_s* h = new (std::nothrow) b200_orb_s();
+    if (!h) return B200_ERR_INVALID;
+    h->ex.prm = *p;
+    h->ex.prm.mask_rects = nullptr;
+    if (p->n_mask_rects > 0) h->ex.mask_rects.assign(p->mask_rects, p->mask_rects + 4 * (size_t)p->n_mask_rects);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->ex.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ex.ev_wait, cudaEventDisableTiming);
+    for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ex.ev[i]);
+    if (e != cudaSuccess) {
+        delete h;
+        return b200::cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
+    }
+    *out = h;
+    return B200_OK;
+}
+
+int b200_orb_destroy(b200_orb_t h) {
+    if (!h) return B200_OK;
+    cudaSetDevice(h->ex.prm.device);
+    cudaStreamSynchronize(h->ex.stream);
+    h->ex.free_arenas();
+    for (auto& e : h->ex.ev)
+        if (e) cudaEventDestroy(e);
+    if (h->ex.ev_wait) cudaEventDestroy(h->ex.ev_wait);
+    if (h->ex.stream) cudaStreamDestroy(h->ex.stream);
+    delete h;
+    return B200_OK;
+}
+
+int b200_orb_max_keypoints(b200_orb_t h, int width, int height) {
+    if (!h || width <= 0 || height <= 0) return B200_ERR_INVALID;
+    b200::orb::Geom g;
+    std::vector<float> sf;
+    int rc = Extractor::level_geometry(h->ex.prm, width, height, g, sf);
+    if (rc) return rc;
+    return g.grid_cells;
+}
+
+int b200_orb_extract_device(b200_orb_t h, const void* d_images, int width, int height, size_t pitch, size_t frame_stride, int batch,
+                            const void* d_mask, size_t mask_pitch, void* wait_stream) {
+    if (!h) return B200_ERR_INVALID;
+    if (width == 0 || height == 0 || batch == 0) {  // orb_extractor.cc:30-32: empty image -> silent return
+        h->ex.last_batch = 0;
+        return B200_OK;
+    }
+    if (!d_images || width < 0 || height < 0 || batch < 0 || pitch < (size_t)width || (batch > 1 && frame_stride < pitch * (size_t)height)) {
+        b200::set_error("b200_orb_extract_device: invalid image arguments");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(h->ex.prm.device));
+    int rc = h->ex.configure(width, height, std::max(batch, h->ex.prm.max_batch));
+    if (rc) return rc;
+    if (wait_stream) {
+        B200_CUDA(cudaEventRecord(h->ex.ev_wait, (cudaStream_t)wait_stream));
+        B200_CUDA(cudaStreamWaitEvent(h->ex.stream, h->ex.ev_wait, 0));
+    }
+    return h->ex.run(d_images, pitch, frame_stride, batch, d_mask, mask_pitch);
+}
+
+int b200_orb_fetch(b200_orb_t h, b200_keypoint_t* kps, uint8_t* descs, int cap, int32_t* counts) {
+    if (!h) return B200_ERR_INVALID;
+    Extractor& ex = h->ex;
+    if (ex.last_batch == 0) return B200_OK;
+    if (!counts || cap < 0) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(ex.prm.device));
+    const int B = ex.last_batch;
+    B200_CUDA(cudaMemcpyAsync(ex.h_counts, ex.d_counts, sizeof(int) * B, cudaMemcpyDeviceToHost, ex.stream));
+    B200_CUDA(cudaStreamSynchronize(ex.stream));
+    int rc = B200_OK;
+    for (int f = 0; f < B; ++f) {
+        const int n = ex.h_counts[f];
+        counts[f] = n;
+        const int m = std::min(n, cap);
+        if (n > cap) {
+            b200::set_error("frame %d has %d keypoints but the caller's capacity is %d", f, n, cap);
+            rc = B200_ERR_CAPACITY;
+        }
+        if (m > 0 && kps)
+            B200_CUDA(cudaMemcpyAsync(kps + (size_t)f * cap, ex.d_kps + (size_t)f * ex.raw_stride, sizeof(b200_keypoint_t) * m,
+                                      cudaMemcpyDeviceToHost, ex.stream));
+        if (m > 0 && descs)
+            B200_CUDA(cudaMemcpyAsync(descs + (size_t)f * cap * 32, ex.d_descs + (size_t)f * ex.raw_stride * 32, (size_t)32 * m,
+                                      cudaMemcpyDeviceToHost, ex.stream));
+    }
+    B200_CUDA(cudaStreamSynchronize(ex.stream));
+    if (ex.timing) {
+        for (int s = 0; s < 5; ++s) cudaEventElapsedTime(&ex.stage_ms[s], ex.ev[s], ex.ev[s + 1]);
+        cudaEventElapsedTime(&ex.stage_ms[5], ex.ev[0], ex.ev[5]);
+    }
+    return rc;
+}
+
+int b200_orb_extract(b200_orb_t h, const uint8_t* images, int width, int height, size_t pitch, size_t frame_stride, int batch,
+                     const uint8_t* mask, size_t mask_pitch, b200_keypoint_t* kps, uint8_t* descs, int cap, int32_t* counts) {
+    if (!h) return B200_ERR_INVALID;
+    if (width == 0 || height == 0 || batch == 0) {
+        h->ex.last_batch = 0;
+        return B200_OK;
+    }
+    if (!images || width < 0 || height < 0 || batch < 0 || pitch < (size_t)width) {
+        b200::set_error("b200_orb_extract: invalid image arguments");
+        return B200_ERR_INVALID;
+    }
+    Extractor& ex = h->ex;
+    B200_CUDA(cudaSetDevice(ex.prm.device));
+    int rc = ex.configure(width, height, std::max(batch, ex.prm.max_batch));
+    if (rc) return rc;
+    for (int f = 0; f < batch; ++f)
+        B200_CUDA(cudaMemcpy2DAsync(ex.d_img0 + (size_t)f * ex.img0_fstride, ex.img0_pitch, images + (size_t)f * frame_stride, pitch, width,
+                                    height, cudaMemcpyHostToDevice, ex.stream));
+    const unsigned char* d_mask = nullptr;
+    if (mask) {
+        B200_CUDA(cudaMemcpy2DAsync(ex.d_user_mask, ex.img0_pitch, mask, mask_pitch, width, height, cudaMemcpyHostToDevice, ex.stream));
+        d_mask = ex.d_user_mask;
+    }
+    rc = ex.run(ex.d_img0, ex.img0_pitch, ex.img0_fstride, batch, d_mask, ex.img0_pitch);
+    if (rc) return rc;
+    return b200_orb_fetch(h, kps, descs, cap, counts);
+}
+
+int b200_orb_device_results(b200_orb_t h, const b200_keypoint_t** d_kps, const uint8_t** d_descs, const int32_t** d_counts, int* stride_kps) {
+    if (!h) return B200_ERR_INVALID;
+    if (d_kps) *d_kps = h->ex.d_kps;
+    if (d_descs) *d_descs = h->ex.d_descs;
+    if (d_counts) *d_counts = h->ex.d_counts;
+    if (stride_kps) *stride_kps = h->ex.raw_stride;
+    return B200_OK;
+}
+
+int b200_orb_sync(b200_orb_t h) {
+    if (!h) return B200_ERR_INVALID;
+    B200_CUDA(cudaStreamSynchronize(h->ex.stream));
+    if (h->ex.timing && h->ex.last_batch > 0) {
+        for (int s = 0; s < 5; ++s) cudaEventElapsedTime(&h->ex.stage_ms[s], h->ex.ev[s], h->ex.ev[s + 1]);
+        cudaEventElapsedTime(&h->ex.stage_ms[5], h->ex.ev[0], h->ex.ev[5]);
+    }
+    return B200_OK;
+}
+
+int b200_orb_level_info(b200_orb_t h, int level, int* width, int* height, size_t* pitch, float* scale_factor) {
+    if (!h || h->ex.width == 0 || level < 0 || level >= h->ex.geom.num_levels) return B200_ERR_INVALID;
+    const auto& L = h->ex.geom.lv[level];
+    if (width) *width = L.w;
+    if (height) *height = L.h;
+    if (pitch) *pitch = (size_t)L.pitch;
+    if (scale_factor) *scale_factor = L.sf;
+    return B200_OK;
+}
+
+int b200_orb_pyramid_level_device(b200_orb_t h, int frame, int level, const uint8_t** d_ptr) {
+    if (!h || !d_ptr || h->ex.width == 0 || level < 1 || level >= h->ex.geom.num_levels || frame < 0 || frame >= h->ex.last_batch) {
+        b200::set_error("b200_orb_pyramid_level_device: bad frame/level (level 0 aliases the caller's image)");
+        return B200_ERR_INVALID;
+    }
+    *d_ptr = h->ex.d_pyr + (size_t)frame * h->ex.pyr_fstride + h->ex.geom.lv[level].offset;
+    return B200_OK;
+}
+
+int b200_orb_pyramid_level_host(b200_orb_t h, int frame, int level, uint8_t* dst, size_t dst_pitch) {
+    const uint8_t* d = nullptr;
+    int rc = b200_orb_pyramid_level_device(h, frame, level, &d);
+    if (rc) return rc;
+    const auto& L = h->ex.geom.lv[level];
+    if (!dst || dst_pitch < (size_t)L.w) return B200_ERR_INVALID;
+    B200_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, d, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->ex.stream));
+    B200_CUDA(cudaStreamSynchronize(h->ex.stream));
+    return B200_OK;
+}
+
+int b200_orb_enable_timing(b200_orb_t h, int enable) {
+    if (!h) return B200_ERR_INVALID;
+    h->ex.timing = enable != 0;
+    return B200_OK;
+}
+
+int b200_orb_stage_ms(b200_orb_t h, int stage, float* ms) {
+    if (!h || !ms || stage < 0 || stage > 5) return B200_ERR_INVALID;
+    *ms = h->ex.stage_ms[stage];
+    return B200_OK;
+}
+
+}  // extern "C"
