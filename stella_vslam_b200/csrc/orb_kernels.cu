@@ -218,9 +218,12 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
         const int pos = queue[qi];
         const unsigned char* c = tile + pos;
         const int v = c[0];
+        // d[k] = (v - p_k) + 255 in [0, 510]: keeps everything non-negative.  (ptxas 12.9 for sm_100a fuses
+        // max(a, -b) into VIMNMX3 and DROPS the negation -- measured on the B200, see DESIGN.md "toolchain hazards" --
+        // so the brighter-arc term is formed as 510 - min_k(max-arc) once, never as a negated max.)
         int d[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = v - (int)c[FAST_OFF(k, kTilePitch)];
+        for (int k = 0; k < 16; ++k) d[k] = v + 255 - (int)c[FAST_OFF(k, kTilePitch)];
         int mn[16], mx[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
@@ -233,13 +236,16 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
             mn4[k] = min(mn[k], mn[(k + 2) & 15]);
             mx4[k] = max(mx[k], mx[(k + 2) & 15]);
         }
-        int best = 0;
+        int best_dark = 0, best_bright = 510;
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
             const int a = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);   // min over d[k..k+8]
             const int b = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);   // max over d[k..k+8]
-            best = max(best, max(a, -b));
+            best_dark = max(best_dark, a);
+            best_bright = min(best_bright, b);
         }
+        // darker arcs: min(v-p) = best_dark - 255; brighter arcs: min(p-v) = 255 - best_bright
+        const int best = max(max(best_dark, 510 - best_bright) - 255, 0);
         mmap[pos] = (unsigned char)min(best, 255);
     }
     __syncthreads();
