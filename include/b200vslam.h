@@ -83,9 +83,18 @@ int b200_orb_extract(b200_orb_t h, const uint8_t* images, int width, int height,
                      int32_t* counts);
 
 /* Same, with frames already resident in device memory (and the mask, if any); results stay on the device until
- * b200_orb_fetch.  Runs on the instance's stream; `wait_stream` (a cudaStream_t, may be 0) is waited on first. */
+ * b200_orb_fetch.  Enqueued on the instance's stream (see b200_orb_set_stream) without synchronising. */
 int b200_orb_extract_device(b200_orb_t h, const void* d_images, int width, int height, size_t pitch, size_t frame_stride,
-                            int batch, const void* d_mask, size_t mask_pitch, void* wait_stream);
+                            int batch, const void* d_mask, size_t mask_pitch);
+/* Run on the caller's stream (a cudaStream_t, e.g. torch's current stream; NULL is the legacy default stream).
+ * use_own != 0 ignores `stream` and restores the instance's own non-blocking stream. */
+int b200_orb_set_stream(b200_orb_t h, void* stream, int use_own);
+/* Write results into caller-owned DEVICE buffers (e.g. torch tensors) instead of the instance's arenas:
+ * keypoints [batch][stride_kps], descriptors [batch][stride_kps][32], counts [batch]; stride_kps must be >=
+ * b200_orb_max_keypoints().  d_kps == NULL unbinds. */
+int b200_orb_bind_outputs(b200_orb_t h, void* d_kps, void* d_descs, void* d_counts, int stride_kps);
+/* Size the arenas for `batch` w x h frames now (otherwise done lazily by the first extract). */
+int b200_orb_reserve(b200_orb_t h, int width, int height, int batch);
 /* Copy the last extract's results to host buffers (synchronises the instance stream). */
 int b200_orb_fetch(b200_orb_t h, b200_keypoint_t* kps, uint8_t* descs, int cap, int32_t* counts);
 /* Device views of the last extract's results: keypoints [batch][stride_kps], descriptors [batch][stride_kps][32],
@@ -101,7 +110,7 @@ int b200_orb_pyramid_level_device(b200_orb_t h, int frame, int level, const uint
 int b200_orb_pyramid_level_host(b200_orb_t h, int frame, int level, uint8_t* dst, size_t dst_pitch);
 
 /* Per-stage kernel time of the last extract, in ms, measured with CUDA events on the instance stream.
- * stage: 0 pyramid, 1 FAST+NMS+grid arg-max, 2 select+orientation, 3 descriptor blur, 4 rBRIEF, 5 whole extract. */
+ * stage: 0 pyramid, 1 FAST+NMS+grid arg-max, 2 ordered selection, 3 descriptor blur, 4 orientation+rBRIEF, 5 whole extract. */
 int b200_orb_stage_ms(b200_orb_t h, int stage, float* ms);
 int b200_orb_enable_timing(b200_orb_t h, int enable);
 
@@ -117,19 +126,31 @@ int b200_matcher_destroy(b200_matcher_t h);
 /* All-pairs 256-bit Hamming distances: dist[i*n2 + j] = popcount(desc1[i] ^ desc2[j])  (host buffers). */
 int b200_hamming_matrix(b200_matcher_t h, const uint8_t* desc1, int n1, const uint8_t* desc2, int n2, uint16_t* dist);
 
-/* robust::brute_force_match for `n_problems` independent (frame, keyframe) pairs, host buffers.
- * Problem p: frame side  = desc1 + off1[p]*32, angle1 + off1[p], n1 = off1[p+1]-off1[p]   (frm_obs descriptors/angles)
- *            keyframe side likewise with off2; valid2[i] != 0 <=> keyframe keypoint i has a live landmark.
- * pairs: problem p writes (idx_1, idx_2) int32 pairs sorted by idx_1 at pairs + 2*off1[p]; n_pairs[p] = count.
- * lowe_ratio / check_orientation: the matcher's ctor arguments (match/base.h:81-91). */
-int b200_match_bruteforce(b200_matcher_t h, int n_problems, const uint8_t* desc1, const float* angle1, const int32_t* off1,
-                          const uint8_t* desc2, const float* angle2, const uint8_t* valid2, const int32_t* off2,
-                          float lowe_ratio, int check_orientation, int32_t* pairs, int32_t* n_pairs);
-/* Device-resident variant (all pointers are device pointers; results stay on the device). */
-int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, int total1, int total2, const void* d_desc1,
-                                 const void* d_angle1, const void* d_off1, const void* d_desc2, const void* d_angle2,
-                                 const void* d_valid2, const void* d_off2, int max_n1, int max_n2, float lowe_ratio,
-                                 int check_orientation, void* d_pairs, void* d_n_pairs, void* wait_stream);
+/* robust::brute_force_match for `n_problems` independent (frame, keyframe) pairs.  Problem p reads
+ *   frame side    (frm_obs):  descriptors desc1 + 32*(off1[p]+i), angle *(float*)((char*)angle1 + (off1[p]+i)*angle1_stride),
+ *                             i < cnt1[p]   (angle1_stride = 4 for a float array, sizeof(b200_keypoint_t) for &kps[0].angle)
+ *   keyframe side (keyfrm) :  likewise with off2/cnt2; valid2[off2[p]+i] != 0 <=> keypoint i has a live landmark
+ *                             (robust.cc:255-262); valid2 == NULL means all valid.
+ * and writes (idx_1, idx_2) int32 pairs sorted by idx_1 at pairs + 2*p*pairs_stride, and n_pairs[p].
+ * pairs_stride >= max_p cnt1[p].  lowe_ratio / check_orientation: the matcher's ctor arguments (match/base.h:81-91).
+ * Host buffers; includes the uploads and the download of the results. */
+int b200_match_bruteforce(b200_matcher_t h, int n_problems, const uint8_t* desc1, const void* angle1, size_t angle1_stride,
+                          const int32_t* off1, const int32_t* cnt1, const uint8_t* desc2, const void* angle2, size_t angle2_stride,
+                          const uint8_t* valid2, const int32_t* off2, const int32_t* cnt2, float lowe_ratio, int check_orientation,
+                          int32_t* pairs, int pairs_stride, int32_t* n_pairs);
+/* Device-resident variant: every pointer is a device pointer and the work is enqueued on the matcher's stream
+ * (see b200_matcher_set_stream) without synchronising.  Problem p reads
+ *   frame side    : descriptors d_desc1 + 32*(off1[p]+i), angle *(float*)((char*)d_angle1 + (off1[p]+i)*angle1_stride), i < cnt1[p]
+ *   keyframe side : likewise with off2/cnt2 (cnt arrays live on the device, e.g. the extractor's d_counts)
+ * and writes its pairs at d_pairs + 2*p*pairs_stride and its count at d_n_pairs[p].  max_n1/max_n2 bound cnt1/cnt2 (host-side
+ * upper bounds used to size the launch); pairs_stride >= max_n1. */
+int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, const void* d_desc1, const void* d_angle1, size_t angle1_stride,
+                                 const void* d_off1, const void* d_cnt1, const void* d_desc2, const void* d_angle2,
+                                 size_t angle2_stride, const void* d_valid2, const void* d_off2, const void* d_cnt2, int max_n1,
+                                 int max_n2, float lowe_ratio, int check_orientation, void* d_pairs, int pairs_stride,
+                                 void* d_n_pairs);
+/* Run on the caller's stream (a cudaStream_t; NULL is the legacy default stream); use_own != 0 restores the own stream. */
+int b200_matcher_set_stream(b200_matcher_t h, void* stream, int use_own);
 int b200_matcher_sync(b200_matcher_t h);
 
 #ifdef __cplusplus

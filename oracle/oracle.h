@@ -62,6 +62,10 @@ float orc_angle_diff(float a1, float a2);
 int orc_brute_force_match(const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2, const float* angle2,
                           const uint8_t* valid2, int n2, float lowe_ratio, int check_orientation, int32_t* pairs_out);
 
+/* timed CPU baseline driver (batch_oracle.c): n frames on n_threads pthreads, extract then match to predecessor */
+int orc_frontend_batch(const uint8_t* frames, int n_unique, int n, int w, int h, const orc_orb_config_t* cfg, int cap, float lowe,
+                       int check_ori, int n_threads, int* counts, int* n_matches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,9 @@ def lib():
         L.orc_brute_force_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                             C.c_float, C.c_int, C.c_void_p]
         L.orc_brute_force_match.restype = C.c_int
+        L.orc_frontend_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(OrbConfig), C.c_int, C.c_float, C.c_int,
+                                         C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_frontend_batch.restype = C.c_int
         if hasattr(L, "orc_lba_solve"):
             L.orc_lba_solve.restype = C.c_int
         _lib = L
@@ -193,3 +196,15 @@ def brute_force_match(desc1, angle1, desc2, angle2, valid2=None, lowe_ratio=0.8,
     n = lib().orc_brute_force_match(_p(desc1), _p(angle1), n1, _p(desc2), _p(angle2), _p(valid2), n2, lowe_ratio,
                                     int(check_orientation), _p(pairs))
     return pairs[:n].copy()
+
+
+def frontend_batch(frames, n, min_area=800, lowe_ratio=0.8, check_orientation=True, threads=1, cap=4096):
+    """Timed CPU baseline: extract n frames (cycling through `frames`) on `threads` pthreads, match each to its predecessor."""
+    frames = np.ascontiguousarray(frames, np.uint8)
+    nu, h, w = frames.shape
+    cfg = OrbConfig(1.2, 8, 20, 7, min_area)
+    counts, matches = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    lib().orc_frontend_batch(_p(frames), nu, n, w, h, C.byref(cfg), cap, lowe_ratio, int(check_orientation), threads, _p(counts), _p(matches))
+    if (counts < 0).any():
+        raise RuntimeError("oracle keypoint capacity too small")
+    return counts, matches

@@ -34,10 +34,10 @@ _lib = None
 SYMBOLS = [
     "b200_last_error", "b200_device_count", "b200_version", "b200_host_alloc", "b200_host_free",
     "b200_orb_default_params", "b200_orb_create", "b200_orb_destroy", "b200_orb_max_keypoints", "b200_orb_extract",
-    "b200_orb_extract_device", "b200_orb_fetch", "b200_orb_device_results", "b200_orb_sync", "b200_orb_level_info",
+    "b200_orb_extract_device", "b200_orb_set_stream", "b200_orb_bind_outputs", "b200_orb_reserve", "b200_orb_fetch", "b200_orb_device_results", "b200_orb_sync", "b200_orb_level_info",
     "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_stage_ms", "b200_orb_enable_timing",
     "b200_matcher_create", "b200_matcher_destroy", "b200_hamming_matrix", "b200_match_bruteforce",
-    "b200_match_bruteforce_device", "b200_matcher_sync",
+    "b200_match_bruteforce_device", "b200_matcher_set_stream", "b200_matcher_sync",
 ]
 
 
@@ -61,7 +61,10 @@ def lib():
     L.b200_orb_destroy.argtypes = [vp]
     L.b200_orb_max_keypoints.argtypes = [vp, i32, i32]
     L.b200_orb_extract.argtypes = [vp, vp, i32, i32, sz, sz, i32, vp, sz, vp, vp, i32, vp]
-    L.b200_orb_extract_device.argtypes = [vp, vp, i32, i32, sz, sz, i32, vp, sz, vp]
+    L.b200_orb_extract_device.argtypes = [vp, vp, i32, i32, sz, sz, i32, vp, sz]
+    L.b200_orb_set_stream.argtypes = [vp, vp, i32]
+    L.b200_orb_reserve.argtypes = [vp, i32, i32, i32]
+    L.b200_orb_bind_outputs.argtypes = [vp, vp, vp, vp, i32]
     L.b200_orb_fetch.argtypes = [vp, vp, vp, i32, vp]
     L.b200_orb_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i32)]
     L.b200_orb_sync.argtypes = [vp]
@@ -74,9 +77,10 @@ def lib():
     L.b200_matcher_destroy.argtypes = [vp]
     L.b200_matcher_sync.argtypes = [vp]
     L.b200_hamming_matrix.argtypes = [vp, vp, i32, vp, i32, vp]
-    L.b200_match_bruteforce.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, vp, C.c_float, i32, vp, vp]
-    L.b200_match_bruteforce_device.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, i32, i32, C.c_float, i32, vp,
-                                               vp, vp]
+    L.b200_match_bruteforce.argtypes = [vp, i32, vp, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp, C.c_float, i32, vp, i32, vp]
+    L.b200_match_bruteforce_device.argtypes = [vp, i32, vp, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp, i32, i32, C.c_float, i32,
+                                               vp, i32, vp]
+    L.b200_matcher_set_stream.argtypes = [vp, vp, i32]
     _lib = L
     return L
 

@@ -13,6 +13,7 @@
 //       the outcome exactly (too many of its entries were taken) the warp recomputes that row against the live set.
 // Both steps are exact, so the match pairs equal the reference's bit for bit.
 #include <algorithm>
+#include <climits>
 #include <new>
 #include <vector>
 
@@ -65,16 +66,26 @@ __global__ void __launch_bounds__(256) hamming_matrix_kernel(const uint4* __rest
 // ---------------------------------------------------------------------------------------------------------------
 // (1) top-K candidate lists.  grid = (ceil(max_n2 / 128), n_problems); thread = one keyframe keypoint idx_2.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRowsPerBlock) topk_kernel(const uint4* __restrict__ desc1, const float* __restrict__ angle1,
-                                                            const int* __restrict__ off1, const uint4* __restrict__ desc2,
-                                                            const float* __restrict__ angle2, const unsigned char* __restrict__ valid2,
-                                                            const int* __restrict__ off2, int check_orientation,
-                                                            unsigned* __restrict__ lists) {
+struct Side {                       // one side of the problems: descriptors, strided angles, per-problem (offset, count)
+    const uint4* desc;
+    const unsigned char* angle;     // angle of keypoint i = *(const float*)(angle + i * angle_stride)
+    long long angle_stride;
+    const int* off;
+    const int* cnt;
+};
+__device__ __forceinline__ float side_angle(const Side& s, int i) {
+    return *reinterpret_cast<const float*>(s.angle + (long long)i * s.angle_stride);
+}
+
+__global__ void __launch_bounds__(kRowsPerBlock) topk_kernel(Side S1, Side S2, const unsigned char* __restrict__ valid2,
+                                                            int check_orientation, unsigned* __restrict__ lists) {
     __shared__ uint4 s1[kChunk * 2];
     __shared__ float sa[kChunk];
+    const uint4* __restrict__ desc1 = S1.desc;
+    const uint4* __restrict__ desc2 = S2.desc;
     const int p = blockIdx.y;
-    const int b1 = off1[p], n1 = off1[p + 1] - b1;
-    const int b2 = off2[p], n2 = off2[p + 1] - b2;
+    const int b1 = S1.off[p], n1 = S1.cnt[p];
+    const int b2 = S2.off[p], n2 = S2.cnt[p];
     if ((int)(blockIdx.x * kRowsPerBlock) >= n2) return;
     const int row = blockIdx.x * kRowsPerBlock + threadIdx.x;
     const bool active = row < n2 && (!valid2 || valid2[b2 + row]);
@@ -83,7 +94,7 @@ __global__ void __launch_bounds__(kRowsPerBlock) topk_kernel(const uint4* __rest
     if (active) {
         q0 = desc2[(size_t)(b2 + row) * 2];
         q1 = desc2[(size_t)(b2 + row) * 2 + 1];
-        qa = angle2[b2 + row];
+        qa = side_angle(S2, b2 + row);
     }
     unsigned top[kTopK];
 #pragma unroll
@@ -92,7 +103,7 @@ __global__ void __launch_bounds__(kRowsPerBlock) topk_kernel(const uint4* __rest
         const int cn = min(kChunk, n1 - c0);
         __syncthreads();
         for (int t = threadIdx.x; t < cn * 2; t += blockDim.x) s1[t] = desc1[(size_t)(b1 + c0) * 2 + t];
-        for (int t = threadIdx.x; t < cn; t += blockDim.x) sa[t] = angle1[b1 + c0 + t];
+        for (int t = threadIdx.x; t < cn; t += blockDim.x) sa[t] = side_angle(S1, b1 + c0 + t);
         __syncthreads();
         if (!active) continue;
 #pragma unroll 4
@@ -114,7 +125,7 @@ __global__ void __launch_bounds__(kRowsPerBlock) topk_kernel(const uint4* __rest
         }
     }
     if (row < n2) {
-        unsigned* o = lists + (size_t)(b2 + row) * kTopK;
+        unsigned* o = lists + ((size_t)p * gridDim.x * kRowsPerBlock + row) * kTopK;
 #pragma unroll
         for (int k = 0; k < kTopK; ++k) o[k] = top[k];
     }
@@ -130,12 +141,12 @@ __device__ __forceinline__ unsigned warp_min(unsigned v) {
 }
 
 // exact best/second over the live (not taken, orientation-gated) frame keypoints: the reference's inner loop
-__device__ void exact_row(const uint4* desc1, const float* angle1, int n1, const unsigned* taken, uint4 q0, uint4 q1, float qa,
+__device__ void exact_row(const uint4* desc1, const Side& S1, int b1, int n1, const unsigned* taken, uint4 q0, uint4 q1, float qa,
                           int check_orientation, int lane, unsigned* best_key, unsigned* second_dist) {
     unsigned k1 = kInfKey, k2 = kInfKey;  // two smallest keys seen by this lane
     for (int i = lane; i < n1; i += 32) {
         if ((taken[i >> 5] >> (i & 31)) & 1u) continue;
-        if (check_orientation && orientation_rejects(angle1[i], qa)) continue;
+        if (check_orientation && orientation_rejects(side_angle(S1, b1 + i), qa)) continue;
         const unsigned key = make_key(hamming256(q0, q1, desc1[(size_t)i * 2], desc1[(size_t)i * 2 + 1]), (unsigned)i);
         if (key < k1) {
             k2 = k1;
@@ -151,26 +162,28 @@ __device__ void exact_row(const uint4* desc1, const float* angle1, int n1, const
     *second_dist = (s == kInfKey) ? (unsigned)kMaxDist : key_dist(s);
 }
 
-__global__ void __launch_bounds__(32) resolve_kernel(const uint4* __restrict__ desc1, const float* __restrict__ angle1,
-                                                     const int* __restrict__ off1, const uint4* __restrict__ desc2,
-                                                     const float* __restrict__ angle2, const unsigned char* __restrict__ valid2,
-                                                     const int* __restrict__ off2, const unsigned* __restrict__ lists, float lowe_ratio,
-                                                     int check_orientation, int* __restrict__ matched, unsigned* __restrict__ taken_g,
-                                                     int taken_words, int* __restrict__ pairs, int* __restrict__ n_pairs) {
+__global__ void __launch_bounds__(32) resolve_kernel(Side S1, Side S2, const unsigned char* __restrict__ valid2,
+                                                     const unsigned* __restrict__ lists, float lowe_ratio, int check_orientation,
+                                                     int* __restrict__ matched, unsigned* __restrict__ taken_g, int taken_words,
+                                                     int list_rows, int matched_stride, int pairs_stride,
+                                                     int* __restrict__ pairs_out, int* __restrict__ n_pairs) {
+    const uint4* __restrict__ desc1 = S1.desc;
+    const uint4* __restrict__ desc2 = S2.desc;
     const int p = blockIdx.x, lane = threadIdx.x;
-    const int b1 = off1[p], n1 = off1[p + 1] - b1;
-    const int b2 = off2[p], n2 = off2[p + 1] - b2;
+    const int b1 = S1.off[p], n1 = S1.cnt[p];
+    const int b2 = S2.off[p], n2 = S2.cnt[p];
     unsigned* taken = taken_g + (size_t)p * taken_words;
-    int* m21 = matched + b1;
+    int* m21 = matched + (size_t)p * matched_stride;
+    int* pairs = pairs_out + 2 * (size_t)p * pairs_stride;
+    lists += (size_t)p * list_rows * kTopK;
     for (int i = lane; i < (n1 + 31) / 32; i += 32) taken[i] = 0u;
     for (int i = lane; i < n1; i += 32) m21[i] = -1;
     __syncwarp();
     const uint4* d1 = desc1 + (size_t)b1 * 2;
-    const float* a1 = angle1 + b1;
-    unsigned next_key = (lane < kTopK && n2 > 0) ? lists[(size_t)b2 * kTopK + lane] : kInfKey;
+    unsigned next_key = (lane < kTopK && n2 > 0) ? lists[lane] : kInfKey;
     for (int r = 0; r < n2; ++r) {
         const unsigned key = next_key;
-        if (r + 1 < n2 && lane < kTopK) next_key = lists[(size_t)(b2 + r + 1) * kTopK + lane];
+        if (r + 1 < n2 && lane < kTopK) next_key = lists[(size_t)(r + 1) * kTopK + lane];
         if (valid2 && !valid2[b2 + r]) continue;  // robust.cc:255-262
         // walk the sorted list, skipping taken frame keypoints
         const bool listed = key != kInfKey;
@@ -211,7 +224,7 @@ __global__ void __launch_bounds__(32) resolve_kernel(const uint4* __restrict__ d
             }
         }
         if (!decided)
-            exact_row(d1, a1, n1, taken, desc2[(size_t)(b2 + r) * 2], desc2[(size_t)(b2 + r) * 2 + 1], angle2[b2 + r], check_orientation, lane,
+            exact_row(d1, S1, b1, n1, taken, desc2[(size_t)(b2 + r) * 2], desc2[(size_t)(b2 + r) * 2 + 1], side_angle(S2, b2 + r), check_orientation, lane,
                       &best_key, &second_dist);
         if (best_key != kInfKey) {
             const unsigned bd = key_dist(best_key);
@@ -236,8 +249,8 @@ __global__ void __launch_bounds__(32) resolve_kernel(const uint4* __restrict__ d
         const unsigned bal = __ballot_sync(0xFFFFFFFFu, v >= 0);
         if (v >= 0) {
             const int pos = total + __popc(bal & ((1u << lane) - 1u));
-            pairs[2 * ((size_t)b1 + pos)] = i;
-            pairs[2 * ((size_t)b1 + pos) + 1] = v;
+            pairs[2 * (size_t)pos] = i;
+            pairs[2 * (size_t)pos + 1] = v;
         }
         total += __popc(bal);
     }
@@ -246,8 +259,7 @@ __global__ void __launch_bounds__(32) resolve_kernel(const uint4* __restrict__ d
 
 struct Matcher {
     int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_wait = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
     // scratch (grown on demand)
     unsigned* d_lists = nullptr;
     size_t lists_cap = 0;
@@ -258,6 +270,7 @@ struct Matcher {
     // staging for the host-buffer entry points
     unsigned char* d_stage = nullptr;
     size_t stage_cap = 0;
+    size_t last_h2d = 0, last_d2h = 0;
 
     int grow(void** p, size_t* cap, size_t bytes) {
         if (bytes <= *cap) return B200_OK;
@@ -271,26 +284,27 @@ struct Matcher {
         return B200_OK;
     }
 
-    int run(int n_problems, int total1, int total2, const void* desc1, const void* angle1, const void* off1, const void* desc2,
-            const void* angle2, const void* valid2, const void* off2, int max_n1, int max_n2, float lowe, int check_ori, void* pairs,
-            void* n_pairs) {
+    int run(int n_problems, const Side& S1, const Side& S2, const void* valid2, int max_n1, int max_n2, float lowe, int check_ori,
+            void* pairs, int pairs_stride, void* n_pairs) {
         if (n_problems <= 0) return B200_OK;
         if (max_n1 >= (1 << 22)) {
             set_error("brute-force matcher supports < 4194304 keypoints per frame");
             return B200_ERR_INVALID;
         }
         int rc;
-        const int taken_words = ceil_div(std::max(max_n1, 1), 32);
-        if ((rc = grow((void**)&d_lists, &lists_cap, sizeof(unsigned) * kTopK * (size_t)std::max(total2, 1)))) return rc;
-        if ((rc = grow((void**)&d_matched, &matched_cap, sizeof(int) * (size_t)std::max(total1, 1)))) return rc;
+        max_n1 = std::max(max_n1, 1);
+        if (pairs_stride < max_n1) {
+            set_error("pairs_stride %d is smaller than the largest frame (%d keypoints)", pairs_stride, max_n1);
+            return B200_ERR_CAPACITY;
+        }
+        const int taken_words = ceil_div(max_n1, 32);
+        const int row_blocks = std::max(1, ceil_div(max_n2, kRowsPerBlock)), list_rows = row_blocks * kRowsPerBlock;
+        if ((rc = grow((void**)&d_lists, &lists_cap, sizeof(unsigned) * kTopK * (size_t)list_rows * n_problems))) return rc;
+        if ((rc = grow((void**)&d_matched, &matched_cap, sizeof(int) * (size_t)max_n1 * n_problems))) return rc;
         if ((rc = grow((void**)&d_taken, &taken_cap, sizeof(unsigned) * (size_t)taken_words * n_problems))) return rc;
-        if (max_n2 > 0)
-            topk_kernel<<<dim3(ceil_div(max_n2, kRowsPerBlock), n_problems), kRowsPerBlock, 0, stream>>>(
-                (const uint4*)desc1, (const float*)angle1, (const int*)off1, (const uint4*)desc2, (const float*)angle2,
-                (const unsigned char*)valid2, (const int*)off2, check_ori, d_lists);
-        resolve_kernel<<<n_problems, 32, 0, stream>>>((const uint4*)desc1, (const float*)angle1, (const int*)off1, (const uint4*)desc2,
-                                                      (const float*)angle2, (const unsigned char*)valid2, (const int*)off2, d_lists, lowe,
-                                                      check_ori, d_matched, d_taken, taken_words, (int*)pairs, (int*)n_pairs);
+        topk_kernel<<<dim3(row_blocks, n_problems), kRowsPerBlock, 0, stream>>>(S1, S2, (const unsigned char*)valid2, check_ori, d_lists);
+        resolve_kernel<<<n_problems, 32, 0, stream>>>(S1, S2, (const unsigned char*)valid2, d_lists, lowe, check_ori, d_matched, d_taken,
+                                                      taken_words, list_rows, max_n1, pairs_stride, (int*)pairs, (int*)n_pairs);
         B200_CUDA(cudaGetLastError());
         return B200_OK;
     }
@@ -303,6 +317,8 @@ struct b200_matcher_s {
     b200::match::Matcher m;
 };
 
+using b200::match::Side;
+
 extern "C" {
 
 int b200_matcher_create(int device, b200_matcher_t* out) {
@@ -312,12 +328,12 @@ int b200_matcher_create(int device, b200_matcher_t* out) {
     b200_matcher_s* h = new (std::nothrow) b200_matcher_s();
     if (!h) return B200_ERR_INVALID;
     h->m.device = device;
-    cudaError_t e = cudaStreamCreateWithFlags(&h->m.stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->m.ev_wait, cudaEventDisableTiming);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->m.own_stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         delete h;
         return b200::cuda_fail(e, "stream creation", __FILE__, __LINE__);
     }
+    h->m.stream = h->m.own_stream;
     *out = h;
     return B200_OK;
 }
@@ -330,9 +346,15 @@ int b200_matcher_destroy(b200_matcher_t h) {
     cudaFree(h->m.d_matched);
     cudaFree(h->m.d_taken);
     cudaFree(h->m.d_stage);
-    if (h->m.ev_wait) cudaEventDestroy(h->m.ev_wait);
-    if (h->m.stream) cudaStreamDestroy(h->m.stream);
+    if (h->m.own_stream) cudaStreamDestroy(h->m.own_stream);
     delete h;
+    return B200_OK;
+}
+
+int b200_matcher_set_stream(b200_matcher_t h, void* stream, int use_own) {
+    if (!h) return B200_ERR_INVALID;
+    B200_CUDA(cudaStreamSynchronize(h->m.stream));
+    h->m.stream = use_own ? h->m.own_stream : (cudaStream_t)stream;
     return B200_OK;
 }
 
@@ -342,82 +364,101 @@ int b200_matcher_sync(b200_matcher_t h) {
     return B200_OK;
 }
 
-int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, int total1, int total2, const void* d_desc1, const void* d_angle1,
-                                 const void* d_off1, const void* d_desc2, const void* d_angle2, const void* d_valid2, const void* d_off2,
-                                 int max_n1, int max_n2, float lowe_ratio, int check_orientation, void* d_pairs, void* d_n_pairs,
-                                 void* wait_stream) {
-    if (!h || n_problems < 0 || total1 < 0 || total2 < 0) return B200_ERR_INVALID;
+int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, const void* d_desc1, const void* d_angle1, size_t angle1_stride,
+                                 const void* d_off1, const void* d_cnt1, const void* d_desc2, const void* d_angle2, size_t angle2_stride,
+                                 const void* d_valid2, const void* d_off2, const void* d_cnt2, int max_n1, int max_n2, float lowe_ratio,
+                                 int check_orientation, void* d_pairs, int pairs_stride, void* d_n_pairs) {
+    if (!h || n_problems < 0 || max_n1 < 0 || max_n2 < 0) return B200_ERR_INVALID;
     if (n_problems == 0) return B200_OK;
-    if (!d_off1 || !d_off2 || !d_pairs || !d_n_pairs || (total1 > 0 && (!d_desc1 || !d_angle1)) || (total2 > 0 && (!d_desc2 || !d_angle2))) {
+    if (!d_off1 || !d_off2 || !d_cnt1 || !d_cnt2 || !d_pairs || !d_n_pairs || !d_desc1 || !d_angle1 || !d_desc2 || !d_angle2) {
         b200::set_error("b200_match_bruteforce_device: null argument");
         return B200_ERR_INVALID;
     }
     B200_CUDA(cudaSetDevice(h->m.device));
-    if (wait_stream) {
-        B200_CUDA(cudaEventRecord(h->m.ev_wait, (cudaStream_t)wait_stream));
-        B200_CUDA(cudaStreamWaitEvent(h->m.stream, h->m.ev_wait, 0));
-    }
-    return h->m.run(n_problems, total1, total2, d_desc1, d_angle1, d_off1, d_desc2, d_angle2, d_valid2, d_off2, max_n1, max_n2, lowe_ratio,
-                    check_orientation, d_pairs, d_n_pairs);
+    const Side S1{(const uint4*)d_desc1, (const unsigned char*)d_angle1, (long long)angle1_stride, (const int*)d_off1, (const int*)d_cnt1};
+    const Side S2{(const uint4*)d_desc2, (const unsigned char*)d_angle2, (long long)angle2_stride, (const int*)d_off2, (const int*)d_cnt2};
+    return h->m.run(n_problems, S1, S2, d_valid2, max_n1, max_n2, lowe_ratio, check_orientation, d_pairs, pairs_stride, d_n_pairs);
 }
 
-int b200_match_bruteforce(b200_matcher_t h, int n_problems, const uint8_t* desc1, const float* angle1, const int32_t* off1,
-                          const uint8_t* desc2, const float* angle2, const uint8_t* valid2, const int32_t* off2, float lowe_ratio,
-                          int check_orientation, int32_t* pairs, int32_t* n_pairs) {
+int b200_match_bruteforce(b200_matcher_t h, int n_problems, const uint8_t* desc1, const void* angle1, size_t angle1_stride,
+                          const int32_t* off1, const int32_t* cnt1, const uint8_t* desc2, const void* angle2, size_t angle2_stride,
+                          const uint8_t* valid2, const int32_t* off2, const int32_t* cnt2, float lowe_ratio, int check_orientation,
+                          int32_t* pairs, int pairs_stride, int32_t* n_pairs) {
     if (!h || n_problems < 0) return B200_ERR_INVALID;
     if (n_problems == 0) return B200_OK;
-    if (!off1 || !off2 || !pairs || !n_pairs) {
-        b200::set_error("b200_match_bruteforce: null argument");
+    if (!off1 || !off2 || !cnt1 || !cnt2 || !pairs || !n_pairs || angle1_stride < sizeof(float) || angle2_stride < sizeof(float)) {
+        b200::set_error("b200_match_bruteforce: null argument or angle stride < 4");
         return B200_ERR_INVALID;
     }
     auto& m = h->m;
     B200_CUDA(cudaSetDevice(m.device));
-    const int total1 = off1[n_problems], total2 = off2[n_problems];
-    int max_n1 = 0, max_n2 = 0;
+    // extents of the two sides that the problems touch
+    int lo1 = INT_MAX, hi1 = 0, lo2 = INT_MAX, hi2 = 0, max_n1 = 0, max_n2 = 0;
     for (int p = 0; p < n_problems; ++p) {
-        if (off1[p + 1] < off1[p] || off2[p + 1] < off2[p]) {
-            b200::set_error("b200_match_bruteforce: offsets must be non-decreasing");
+        if (off1[p] < 0 || off2[p] < 0 || cnt1[p] < 0 || cnt2[p] < 0) {
+            b200::set_error("b200_match_bruteforce: negative offset/count in problem %d", p);
             return B200_ERR_INVALID;
         }
-        max_n1 = std::max(max_n1, off1[p + 1] - off1[p]);
-        max_n2 = std::max(max_n2, off2[p + 1] - off2[p]);
+        if (cnt1[p] > 0) { lo1 = std::min(lo1, off1[p]); hi1 = std::max(hi1, off1[p] + cnt1[p]); }
+        if (cnt2[p] > 0) { lo2 = std::min(lo2, off2[p]); hi2 = std::max(hi2, off2[p] + cnt2[p]); }
+        max_n1 = std::max(max_n1, cnt1[p]);
+        max_n2 = std::max(max_n2, cnt2[p]);
     }
-    if ((total1 > 0 && (!desc1 || !angle1)) || (total2 > 0 && (!desc2 || !angle2))) {
+    if (hi1 == 0) lo1 = 0;
+    if (hi2 == 0) lo2 = 0;
+    const int ext1 = hi1 - lo1, ext2 = hi2 - lo2;
+    if ((ext1 > 0 && (!desc1 || !angle1)) || (ext2 > 0 && (!desc2 || !angle2))) {
         b200::set_error("b200_match_bruteforce: null descriptor/angle buffer");
         return B200_ERR_INVALID;
     }
-    // staging layout (all 256-byte aligned): desc1 | desc2 | angle1 | angle2 | valid2 | off1 | off2 | pairs | n_pairs
+    if (pairs_stride < std::max(max_n1, 1)) {
+        b200::set_error("pairs_stride %d is smaller than the largest frame (%d keypoints)", pairs_stride, max_n1);
+        return B200_ERR_CAPACITY;
+    }
+    std::vector<int> meta(4 * (size_t)n_problems);  // off1 | cnt1 | off2 | cnt2, rebased to the staged extents
+    for (int p = 0; p < n_problems; ++p) {
+        meta[p] = cnt1[p] > 0 ? off1[p] - lo1 : 0;
+        meta[n_problems + p] = cnt1[p];
+        meta[2 * n_problems + p] = cnt2[p] > 0 ? off2[p] - lo2 : 0;
+        meta[3 * n_problems + p] = cnt2[p];
+    }
+    // device staging (256-byte aligned): desc1 | desc2 | angle1 | angle2 | valid2 | meta | pairs | n_pairs
     auto al = [](size_t v) { return b200::round_up(v, (size_t)256); };
+    const size_t a1_bytes = ext1 > 0 ? (size_t)(ext1 - 1) * angle1_stride + sizeof(float) : 0;
+    const size_t a2_bytes = ext2 > 0 ? (size_t)(ext2 - 1) * angle2_stride + sizeof(float) : 0;
     size_t o = 0;
-    const size_t o_d1 = o; o += al((size_t)32 * std::max(total1, 1));
-    const size_t o_d2 = o; o += al((size_t)32 * std::max(total2, 1));
-    const size_t o_a1 = o; o += al(sizeof(float) * (size_t)std::max(total1, 1));
-    const size_t o_a2 = o; o += al(sizeof(float) * (size_t)std::max(total2, 1));
-    const size_t o_v2 = o; o += al((size_t)std::max(total2, 1));
-    const size_t o_o1 = o; o += al(sizeof(int) * (size_t)(n_problems + 1));
-    const size_t o_o2 = o; o += al(sizeof(int) * (size_t)(n_problems + 1));
-    const size_t o_pr = o; o += al(sizeof(int) * 2 * (size_t)std::max(total1, 1));
+    const size_t o_d1 = o; o += al((size_t)32 * std::max(ext1, 1));
+    const size_t o_d2 = o; o += al((size_t)32 * std::max(ext2, 1));
+    const size_t o_a1 = o; o += al(std::max(a1_bytes, (size_t)4));
+    const size_t o_a2 = o; o += al(std::max(a2_bytes, (size_t)4));
+    const size_t o_v2 = o; o += al((size_t)std::max(ext2, 1));
+    const size_t o_mt = o; o += al(sizeof(int) * meta.size());
+    const size_t o_pr = o; o += al(sizeof(int) * 2 * (size_t)pairs_stride * n_problems);
     const size_t o_np = o; o += al(sizeof(int) * (size_t)n_problems);
     int rc = m.grow((void**)&m.d_stage, &m.stage_cap, o);
     if (rc) return rc;
     unsigned char* s = m.d_stage;
     cudaStream_t st = m.stream;
-    if (total1 > 0) {
-        B200_CUDA(cudaMemcpyAsync(s + o_d1, desc1, (size_t)32 * total1, cudaMemcpyHostToDevice, st));
-        B200_CUDA(cudaMemcpyAsync(s + o_a1, angle1, sizeof(float) * total1, cudaMemcpyHostToDevice, st));
+    if (ext1 > 0) {
+        B200_CUDA(cudaMemcpyAsync(s + o_d1, desc1 + (size_t)32 * lo1, (size_t)32 * ext1, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(s + o_a1, (const unsigned char*)angle1 + (size_t)lo1 * angle1_stride, a1_bytes, cudaMemcpyHostToDevice, st));
     }
-    if (total2 > 0) {
-        B200_CUDA(cudaMemcpyAsync(s + o_d2, desc2, (size_t)32 * total2, cudaMemcpyHostToDevice, st));
-        B200_CUDA(cudaMemcpyAsync(s + o_a2, angle2, sizeof(float) * total2, cudaMemcpyHostToDevice, st));
-        if (valid2) B200_CUDA(cudaMemcpyAsync(s + o_v2, valid2, total2, cudaMemcpyHostToDevice, st));
+    if (ext2 > 0) {
+        B200_CUDA(cudaMemcpyAsync(s + o_d2, desc2 + (size_t)32 * lo2, (size_t)32 * ext2, cudaMemcpyHostToDevice, st));
+        B200_CUDA(cudaMemcpyAsync(s + o_a2, (const unsigned char*)angle2 + (size_t)lo2 * angle2_stride, a2_bytes, cudaMemcpyHostToDevice, st));
+        if (valid2) B200_CUDA(cudaMemcpyAsync(s + o_v2, valid2 + lo2, ext2, cudaMemcpyHostToDevice, st));
     }
-    B200_CUDA(cudaMemcpyAsync(s + o_o1, off1, sizeof(int) * (n_problems + 1), cudaMemcpyHostToDevice, st));
-    B200_CUDA(cudaMemcpyAsync(s + o_o2, off2, sizeof(int) * (n_problems + 1), cudaMemcpyHostToDevice, st));
-    rc = m.run(n_problems, total1, total2, s + o_d1, s + o_a1, s + o_o1, s + o_d2, s + o_a2, valid2 ? s + o_v2 : nullptr, s + o_o2, max_n1,
-               max_n2, lowe_ratio, check_orientation, s + o_pr, s + o_np);
+    B200_CUDA(cudaMemcpyAsync(s + o_mt, meta.data(), sizeof(int) * meta.size(), cudaMemcpyHostToDevice, st));
+    const int* dm = (const int*)(s + o_mt);
+    const Side S1{(const uint4*)(s + o_d1), s + o_a1, (long long)angle1_stride, dm, dm + n_problems};
+    const Side S2{(const uint4*)(s + o_d2), s + o_a2, (long long)angle2_stride, dm + 2 * n_problems, dm + 3 * n_problems};
+    rc = m.run(n_problems, S1, S2, valid2 ? s + o_v2 : nullptr, max_n1, max_n2, lowe_ratio, check_orientation, s + o_pr, pairs_stride,
+               s + o_np);
     if (rc) return rc;
+    m.last_h2d = (size_t)32 * (ext1 + ext2) + a1_bytes + a2_bytes + (valid2 ? ext2 : 0) + sizeof(int) * meta.size();
+    m.last_d2h = sizeof(int) * ((size_t)n_problems + 2 * (size_t)pairs_stride * n_problems);
     B200_CUDA(cudaMemcpyAsync(n_pairs, s + o_np, sizeof(int) * n_problems, cudaMemcpyDeviceToHost, st));
-    if (total1 > 0) B200_CUDA(cudaMemcpyAsync(pairs, s + o_pr, sizeof(int) * 2 * (size_t)total1, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaMemcpyAsync(pairs, s + o_pr, sizeof(int) * 2 * (size_t)pairs_stride * n_problems, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
     return B200_OK;
 }

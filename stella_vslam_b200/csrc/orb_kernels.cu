@@ -461,7 +461,8 @@ constexpr int kDescBlocksPerFrame = 16;  // blockIdx.x range; each warp strides 
 __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_constant__ Geom g, Images im,
                                                                    const unsigned char* __restrict__ blurred, unsigned long long blur_fstride,
                                                                    const RawKp* __restrict__ raw, int raw_stride, const int* __restrict__ counts,
-                                                                   b200_keypoint_t* __restrict__ kps, unsigned char* __restrict__ descs) {
+                                                                   b200_keypoint_t* __restrict__ kps, unsigned char* __restrict__ descs,
+                                                                   int out_stride) {
     const int frame = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int warp = blockIdx.x * kDescWarps + (threadIdx.x >> 5);
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
             const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
             val |= (unsigned)(bc[r0 * bp + c0] < bc[r1 * bp + c1]) << b;
         }
-        const size_t o = (size_t)frame * raw_stride + k;
+        const size_t o = (size_t)frame * out_stride + k;
         descs[o * 32 + lane] = (unsigned char)val;
         if (lane == 0) {
             b200_keypoint_t kp;
@@ -545,8 +546,7 @@ static inline int floor_to_int(float v) {
 struct Extractor {
     b200_orb_params_t prm{};
     std::vector<float> mask_rects;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_wait = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev[8] = {};
     bool timing = false;
     float stage_ms[6] = {};
@@ -569,6 +569,15 @@ struct Extractor {
     int* h_counts = nullptr;  // pinned
     int last_batch = 0;
     bool rect_mask_ready = false;
+    // caller-owned result buffers (b200_orb_bind_outputs); when null the instance's own arenas are used
+    b200_keypoint_t* out_kps = nullptr;
+    unsigned char* out_descs = nullptr;
+    int* out_counts = nullptr;
+    int out_stride = 0;
+    b200_keypoint_t* res_kps() const { return out_kps ? out_kps : d_kps; }
+    unsigned char* res_descs() const { return out_kps ? out_descs : d_descs; }
+    int* res_counts() const { return out_kps ? out_counts : d_counts; }
+    int res_stride() const { return out_kps ? out_stride : raw_stride; }
 
     void free_arenas() {
         cudaFree(d_img0); cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_rect_mask); cudaFree(d_user_mask);
@@ -702,7 +711,7 @@ struct Extractor {
         for (int l = 0; l < nl; ++l) total = geom.lv[l].offset + round_up((unsigned long long)geom.lv[l].pitch * geom.lv[l].h, 256ull);
         pyr_fstride = total;
         img0_pitch = geom.lv[0].pitch;
-        img0_fstride = round_up((size_t)img0_pitch * h, (size_t)256);
+        img0_fstride = (size_t)img0_pitch * h;
 
         B200_CUDA(cudaMalloc(&d_img0, img0_fstride * batch));
         B200_CUDA(cudaMalloc(&d_pyr, pyr_fstride * batch));
@@ -761,12 +770,16 @@ struct Extractor {
         B200_CUDA(cudaMemsetAsync(d_grid, 0, sizeof(unsigned long long) * (size_t)raw_stride * batch, stream));
         if (n_cells) fast_cells_kernel<<<dim3(n_cells, batch), 256, 0, stream>>>(geom, im, d_cells, mask, mpitch, d_grid);
         if (timing) B200_CUDA(cudaEventRecord(ev[2], stream));
-        select_kernel<<<dim3(nl, batch), 256, 0, stream>>>(geom, d_grid, d_raw, raw_stride, d_counts, d_level_counts);
+        if (out_kps && out_stride < geom.grid_cells) {
+            set_error("bound output stride %d is smaller than the keypoint upper bound %d", out_stride, geom.grid_cells);
+            return B200_ERR_CAPACITY;
+        }
+        select_kernel<<<dim3(nl, batch), 256, 0, stream>>>(geom, d_grid, d_raw, raw_stride, res_counts(), d_level_counts);
         if (timing) B200_CUDA(cudaEventRecord(ev[3], stream));
         blur_kernel<<<dim3(n_blur_tiles, batch), 256, 0, stream>>>(geom, im, d_tiles, d_blur, pyr_fstride);
         if (timing) B200_CUDA(cudaEventRecord(ev[4], stream));
         describe_kernel<<<dim3(kDescBlocksPerFrame, batch), kDescWarps * 32, 0, stream>>>(geom, im, d_blur, pyr_fstride, d_raw, raw_stride,
-                                                                                         d_counts, d_kps, d_descs);
+                                                                                         res_counts(), res_kps(), res_descs(), res_stride());
         if (timing) B200_CUDA(cudaEventRecord(ev[5], stream));
         B200_CUDA(cudaGetLastError());
         last_batch = batch;
@@ -813,8 +826,8 @@ int b200_orb_create(const b200_orb_params_t* p, b200_orb_t* out) {
     h->ex.prm = *p;
     h->ex.prm.mask_rects = nullptr;
     if (p->n_mask_rects > 0) h->ex.mask_rects.assign(p->mask_rects, p->mask_rects + 4 * (size_t)p->n_mask_rects);
-    cudaError_t e = cudaStreamCreateWithFlags(&h->ex.stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ex.ev_wait, cudaEventDisableTiming);
+    cudaError_t e = cudaStreamCreateWithFlags(&h->ex.own_stream, cudaStreamNonBlocking);
+    h->ex.stream = h->ex.own_stream;
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ex.ev[i]);
     if (e != cudaSuccess) {
         delete h;
@@ -831,8 +844,7 @@ int b200_orb_destroy(b200_orb_t h) {
     h->ex.free_arenas();
     for (auto& e : h->ex.ev)
         if (e) cudaEventDestroy(e);
-    if (h->ex.ev_wait) cudaEventDestroy(h->ex.ev_wait);
-    if (h->ex.stream) cudaStreamDestroy(h->ex.stream);
+    if (h->ex.own_stream) cudaStreamDestroy(h->ex.own_stream);
     delete h;
     return B200_OK;
 }
@@ -847,7 +859,7 @@ int b200_orb_max_keypoints(b200_orb_t h, int width, int height) {
 }
 
 int b200_orb_extract_device(b200_orb_t h, const void* d_images, int width, int height, size_t pitch, size_t frame_stride, int batch,
-                            const void* d_mask, size_t mask_pitch, void* wait_stream) {
+                            const void* d_mask, size_t mask_pitch) {
     if (!h) return B200_ERR_INVALID;
     if (width == 0 || height == 0 || batch == 0) {  // orb_extractor.cc:30-32: empty image -> silent return
         h->ex.last_batch = 0;
@@ -860,10 +872,6 @@ int b200_orb_extract_device(b200_orb_t h, const void* d_images, int width, int h
     B200_CUDA(cudaSetDevice(h->ex.prm.device));
     int rc = h->ex.configure(width, height, std::max(batch, h->ex.prm.max_batch));
     if (rc) return rc;
-    if (wait_stream) {
-        B200_CUDA(cudaEventRecord(h->ex.ev_wait, (cudaStream_t)wait_stream));
-        B200_CUDA(cudaStreamWaitEvent(h->ex.stream, h->ex.ev_wait, 0));
-    }
     return h->ex.run(d_images, pitch, frame_stride, batch, d_mask, mask_pitch);
 }
 
@@ -874,30 +882,62 @@ int b200_orb_fetch(b200_orb_t h, b200_keypoint_t* kps, uint8_t* descs, int cap, 
     if (!counts || cap < 0) return B200_ERR_INVALID;
     B200_CUDA(cudaSetDevice(ex.prm.device));
     const int B = ex.last_batch;
-    B200_CUDA(cudaMemcpyAsync(ex.h_counts, ex.d_counts, sizeof(int) * B, cudaMemcpyDeviceToHost, ex.stream));
+    // counts are not known on the host yet: copy min(cap, stride) records per frame with two strided copies
+    const size_t m = (size_t)std::min(cap, ex.res_stride());
+    B200_CUDA(cudaMemcpyAsync(ex.h_counts, ex.res_counts(), sizeof(int) * B, cudaMemcpyDeviceToHost, ex.stream));
+    if (m > 0 && kps)
+        B200_CUDA(cudaMemcpy2DAsync(kps, sizeof(b200_keypoint_t) * (size_t)cap, ex.res_kps(), sizeof(b200_keypoint_t) * (size_t)ex.res_stride(),
+                                    sizeof(b200_keypoint_t) * m, B, cudaMemcpyDeviceToHost, ex.stream));
+    if (m > 0 && descs)
+        B200_CUDA(cudaMemcpy2DAsync(descs, (size_t)32 * cap, ex.res_descs(), (size_t)32 * ex.res_stride(), (size_t)32 * m, B, cudaMemcpyDeviceToHost,
+                                    ex.stream));
     B200_CUDA(cudaStreamSynchronize(ex.stream));
     int rc = B200_OK;
     for (int f = 0; f < B; ++f) {
-        const int n = ex.h_counts[f];
-        counts[f] = n;
-        const int m = std::min(n, cap);
-        if (n > cap) {
-            b200::set_error("frame %d has %d keypoints but the caller's capacity is %d", f, n, cap);
+        counts[f] = ex.h_counts[f];
+        if (ex.h_counts[f] > cap) {
+            b200::set_error("frame %d has %d keypoints but the caller's capacity is %d", f, ex.h_counts[f], cap);
             rc = B200_ERR_CAPACITY;
         }
-        if (m > 0 && kps)
-            B200_CUDA(cudaMemcpyAsync(kps + (size_t)f * cap, ex.d_kps + (size_t)f * ex.raw_stride, sizeof(b200_keypoint_t) * m,
-                                      cudaMemcpyDeviceToHost, ex.stream));
-        if (m > 0 && descs)
-            B200_CUDA(cudaMemcpyAsync(descs + (size_t)f * cap * 32, ex.d_descs + (size_t)f * ex.raw_stride * 32, (size_t)32 * m,
-                                      cudaMemcpyDeviceToHost, ex.stream));
     }
-    B200_CUDA(cudaStreamSynchronize(ex.stream));
     if (ex.timing) {
-        for (int s = 0; s < 5; ++s) cudaEventElapsedTime(&ex.stage_ms[s], ex.ev[s], ex.ev[s + 1]);
+        for (int st = 0; st < 5; ++st) cudaEventElapsedTime(&ex.stage_ms[st], ex.ev[st], ex.ev[st + 1]);
         cudaEventElapsedTime(&ex.stage_ms[5], ex.ev[0], ex.ev[5]);
     }
     return rc;
+}
+
+int b200_orb_set_stream(b200_orb_t h, void* stream, int use_own) {
+    if (!h) return B200_ERR_INVALID;
+    B200_CUDA(cudaStreamSynchronize(h->ex.stream));
+    h->ex.stream = use_own ? h->ex.own_stream : (cudaStream_t)stream;
+    return B200_OK;
+}
+
+int b200_orb_bind_outputs(b200_orb_t h, void* d_kps, void* d_descs, void* d_counts, int stride_kps) {
+    if (!h) return B200_ERR_INVALID;
+    if (!d_kps) {  // unbind
+        h->ex.out_kps = nullptr;
+        h->ex.out_descs = nullptr;
+        h->ex.out_counts = nullptr;
+        h->ex.out_stride = 0;
+        return B200_OK;
+    }
+    if (!d_descs || !d_counts || stride_kps <= 0) {
+        b200::set_error("b200_orb_bind_outputs: all three buffers and a positive stride are required");
+        return B200_ERR_INVALID;
+    }
+    h->ex.out_kps = (b200_keypoint_t*)d_kps;
+    h->ex.out_descs = (unsigned char*)d_descs;
+    h->ex.out_counts = (int*)d_counts;
+    h->ex.out_stride = stride_kps;
+    return B200_OK;
+}
+
+int b200_orb_reserve(b200_orb_t h, int width, int height, int batch) {
+    if (!h || width <= 0 || height <= 0 || batch <= 0) return B200_ERR_INVALID;
+    B200_CUDA(cudaSetDevice(h->ex.prm.device));
+    return h->ex.configure(width, height, std::max(batch, h->ex.prm.max_batch));
 }
 
 int b200_orb_extract(b200_orb_t h, const uint8_t* images, int width, int height, size_t pitch, size_t frame_stride, int batch,
@@ -915,9 +955,13 @@ int b200_orb_extract(b200_orb_t h, const uint8_t* images, int width, int height,
     B200_CUDA(cudaSetDevice(ex.prm.device));
     int rc = ex.configure(width, height, std::max(batch, ex.prm.max_batch));
     if (rc) return rc;
-    for (int f = 0; f < batch; ++f)
-        B200_CUDA(cudaMemcpy2DAsync(ex.d_img0 + (size_t)f * ex.img0_fstride, ex.img0_pitch, images + (size_t)f * frame_stride, pitch, width,
-                                    height, cudaMemcpyHostToDevice, ex.stream));
+    if (batch == 1 || frame_stride == pitch * (size_t)height) {  // contiguous batch: one tall 2-D copy
+        B200_CUDA(cudaMemcpy2DAsync(ex.d_img0, ex.img0_pitch, images, pitch, width, (size_t)height * batch, cudaMemcpyHostToDevice, ex.stream));
+    } else {
+        for (int f = 0; f < batch; ++f)
+            B200_CUDA(cudaMemcpy2DAsync(ex.d_img0 + (size_t)f * ex.img0_fstride, ex.img0_pitch, images + (size_t)f * frame_stride, pitch,
+                                        width, height, cudaMemcpyHostToDevice, ex.stream));
+    }
     const unsigned char* d_mask = nullptr;
     if (mask) {
         B200_CUDA(cudaMemcpy2DAsync(ex.d_user_mask, ex.img0_pitch, mask, mask_pitch, width, height, cudaMemcpyHostToDevice, ex.stream));
@@ -930,10 +974,10 @@ int b200_orb_extract(b200_orb_t h, const uint8_t* images, int width, int height,
 
 int b200_orb_device_results(b200_orb_t h, const b200_keypoint_t** d_kps, const uint8_t** d_descs, const int32_t** d_counts, int* stride_kps) {
     if (!h) return B200_ERR_INVALID;
-    if (d_kps) *d_kps = h->ex.d_kps;
-    if (d_descs) *d_descs = h->ex.d_descs;
-    if (d_counts) *d_counts = h->ex.d_counts;
-    if (stride_kps) *stride_kps = h->ex.raw_stride;
+    if (d_kps) *d_kps = h->ex.res_kps();
+    if (d_descs) *d_descs = h->ex.res_descs();
+    if (d_counts) *d_counts = h->ex.res_counts();
+    if (stride_kps) *stride_kps = h->ex.res_stride();
     return B200_OK;
 }
 

@@ -60,21 +60,24 @@ class robust(base):
         P = len(problems)
         if P == 0:
             return []
-        off1, off2 = np.zeros(P + 1, np.int32), np.zeros(P + 1, np.int32)
-        for i, pr in enumerate(problems):
-            off1[i + 1] = off1[i] + len(pr[0])
-            off2[i + 1] = off2[i] + len(pr[2])
-        cat = lambda k, dt, shape: (np.ascontiguousarray(np.concatenate([np.asarray(pr[k], dt).reshape(shape) for pr in problems]))
-                                    if P else np.zeros(shape, dt))
+        cnt1 = np.array([len(pr[0]) for pr in problems], np.int32)
+        cnt2 = np.array([len(pr[2]) for pr in problems], np.int32)
+        off1 = np.concatenate([[0], np.cumsum(cnt1)[:-1]]).astype(np.int32)
+        off2 = np.concatenate([[0], np.cumsum(cnt2)[:-1]]).astype(np.int32)
+
+        def cat(k, dt, shape):
+            return np.ascontiguousarray(np.concatenate([np.asarray(pr[k], dt).reshape(shape) for pr in problems]))
+
         d1, a1 = cat(0, np.uint8, (-1, 32)), cat(1, np.float32, (-1,))
         d2, a2 = cat(2, np.uint8, (-1, 32)), cat(3, np.float32, (-1,))
-        any_valid = any(pr[4] is not None for pr in problems)
         v2 = None
-        if any_valid:
+        if any(pr[4] is not None for pr in problems):
             v2 = np.ascontiguousarray(np.concatenate([
                 (np.asarray(pr[4], np.uint8).reshape(-1) if pr[4] is not None else np.ones(len(pr[2]), np.uint8)) for pr in problems]))
-        pairs = np.zeros((max(int(off1[-1]), 1), 2), np.int32)
+        stride = max(int(cnt1.max()), 1)
+        pairs = np.zeros((P, stride, 2), np.int32)
         n_pairs = np.zeros(P, np.int32)
-        check(lib().b200_match_bruteforce(_matcher(self.device), P, ptr(d1), ptr(a1), ptr(off1), ptr(d2), ptr(a2), ptr(v2), ptr(off2),
-                                          float(self.lowe_ratio_), int(self.check_orientation_), ptr(pairs), ptr(n_pairs)))
-        return [pairs[off1[i]:off1[i] + n_pairs[i]].copy() for i in range(P)]
+        check(lib().b200_match_bruteforce(_matcher(self.device), P, ptr(d1), ptr(a1), 4, ptr(off1), ptr(cnt1), ptr(d2), ptr(a2), 4,
+                                          ptr(v2), ptr(off2), ptr(cnt2), float(self.lowe_ratio_), int(self.check_orientation_),
+                                          ptr(pairs), stride, ptr(n_pairs)))
+        return [pairs[i, :n_pairs[i]].copy() for i in range(P)]

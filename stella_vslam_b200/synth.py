@@ -20,20 +20,18 @@ def _value_noise(rng, h, w, cell):
     return (a * (1 - fx) + b * fx) * (1 - fy) + (c * (1 - fx) + d * fx) * fy
 
 
-def make_frame(w=1920, h=1080, seed=1234, shift=(0, 0), n_shapes=None, noise_sigma=2.0):
-    """u8 HxW frame: 4 octaves of value noise + random filled rectangles/discs + iid noise, then a 3x3 box blur.
+_PAD = 64
 
-    `shift` translates the underlying pattern (pixels), so consecutive frames of a stream overlap and match.
-    """
+
+def _make_pattern(w, h, seed, n_shapes=None):
+    """Padded float32 scene (h+2*PAD, w+2*PAD): 4 octaves of value noise + random filled rectangles/discs."""
     rng = np.random.default_rng(seed)
-    pad = 64
-    H, W = h + 2 * pad, w + 2 * pad
+    H, W = h + 2 * _PAD, w + 2 * _PAD
     img = np.zeros((H, W), np.float32)
     for cell, amp in ((96, 80.0), (32, 45.0), (11, 30.0), (4, 26.0)):
         img += amp * _value_noise(rng, H, W, cell)
     if n_shapes is None:
         n_shapes = max(40, int(400 * (w * h) / (1920 * 1080)))
-    yy, xx = np.mgrid[0:H, 0:W]
     for _ in range(n_shapes):
         cx, cy = int(rng.integers(0, W)), int(rng.integers(0, H))
         s = int(rng.integers(6, 48))
@@ -42,25 +40,39 @@ def make_frame(w=1920, h=1080, seed=1234, shift=(0, 0), n_shapes=None, noise_sig
         if rng.random() < 0.6:
             img[y0:y1, x0:x1] = g
         else:
-            m = (yy[y0:y1, x0:x1] - cy) ** 2 + (xx[y0:y1, x0:x1] - cx) ** 2 <= s * s
+            yy, xx = np.mgrid[y0:y1, x0:x1]
+            m = (yy - cy) ** 2 + (xx - cx) ** 2 <= s * s
             img[y0:y1, x0:x1][m] = g
+    return img
+
+
+def _render(pattern, w, h, seed, shift, noise_sigma):
     dx, dy = int(shift[0]), int(shift[1])
-    dx, dy = max(-pad, min(pad, dx)), max(-pad, min(pad, dy))
-    view = img[pad + dy:pad + dy + h, pad + dx:pad + dx + w]
+    dx, dy = max(-_PAD, min(_PAD, dx)), max(-_PAD, min(_PAD, dy))
+    view = pattern[_PAD + dy:_PAD + dy + h, _PAD + dx:_PAD + dx + w]
     nrng = np.random.default_rng(seed * 7919 + 17 * (dx + 101) + (dy + 103))
-    view = view + noise_sigma * nrng.standard_normal(view.shape).astype(np.float32)
+    view = view + noise_sigma * nrng.standard_normal(view.shape, dtype=np.float32)
     p = np.pad(view, 1, mode="edge")
-    box = sum(p[i:i + h, j:j + w] for i in range(3) for j in range(3)) / 9.0
+    box = sum(p[i:i + h, j:j + w] for i in range(3) for j in range(3)) / np.float32(9.0)
     return np.clip(np.rint(box), 0, 255).astype(np.uint8)
+
+
+def make_frame(w=1920, h=1080, seed=1234, shift=(0, 0), n_shapes=None, noise_sigma=2.0):
+    """u8 HxW frame: 4 octaves of value noise + random filled rectangles/discs + iid noise, then a 3x3 box blur.
+
+    `shift` translates the underlying pattern (pixels), so consecutive frames of a stream overlap and match.
+    """
+    return _render(_make_pattern(w, h, seed, n_shapes), w, h, seed, shift, noise_sigma)
 
 
 def make_stream(n_frames, w=1920, h=1080, stream=0, max_step=8):
     """Frames of one synthetic stream: the pattern follows a seeded 2-D random walk (<= max_step px per frame)."""
     rng = np.random.default_rng(99 + stream)
+    pattern = _make_pattern(w, h, 1234 + stream)
     pos = np.zeros(2, np.int64)
     frames = []
     for _ in range(n_frames):
-        frames.append(make_frame(w, h, seed=1234 + stream, shift=(int(pos[0]), int(pos[1]))))
+        frames.append(_render(pattern, w, h, 1234 + stream, (int(pos[0]), int(pos[1])), 2.0))
         pos = np.clip(pos + rng.integers(-max_step, max_step + 1, 2), -60, 60)
     return frames
 

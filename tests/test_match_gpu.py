@@ -99,3 +99,52 @@ def test_orientation_gate_boundaries(mods):
         got = match.robust(1.0, True).brute_force_match(d, a1, d[:1], a2)
         ref = O.brute_force_match(d, a1, d[:1], a2, None, 1.0, True)
         assert np.array_equal(got, ref)
+
+
+def test_device_path_with_bound_outputs(mods):
+    """Extractor writing into torch-owned buffers + the device matcher on (offset, count) views == oracle."""
+    import ctypes as C
+
+    import torch
+
+    O, match, synth = mods
+    from stella_vslam_b200 import feature
+    from stella_vslam_b200._lib import check, lib
+    L = lib()
+    B, w, h = 3, 640, 480
+    frames = np.stack([synth.make_frame(w, h, seed=50, shift=(4 * i, 3 * i)) for i in range(B)])
+    ex = feature.orb_extractor(feature.orb_params(), 800, max_batch=B)
+    stride = L.b200_orb_max_keypoints(ex._h, w, h)
+    dev = torch.device("cuda", 0)
+    kps = torch.zeros((B, stride, 6), dtype=torch.float32, device=dev)
+    desc = torch.zeros((B, stride, 32), dtype=torch.uint8, device=dev)
+    counts = torch.zeros(B, dtype=torch.int32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    check(L.b200_orb_set_stream(ex._h, C.c_void_p(s), 0))
+    check(L.b200_orb_bind_outputs(ex._h, C.c_void_p(kps.data_ptr()), C.c_void_p(desc.data_ptr()), C.c_void_p(counts.data_ptr()), stride))
+    fd = torch.from_numpy(frames).to(dev)
+    check(L.b200_orb_extract_device(ex._h, C.c_void_p(fd.data_ptr()), w, h, w, w * h, B, None, 0))
+    hm = C.c_void_p()
+    check(L.b200_matcher_create(0, C.byref(hm)))
+    check(L.b200_matcher_set_stream(hm, C.c_void_p(s), 0))
+    off = (torch.arange(B, dtype=torch.int32, device=dev) * stride).contiguous()
+    pairs = torch.zeros((B - 1, stride, 2), dtype=torch.int32, device=dev)
+    npairs = torch.zeros(B - 1, dtype=torch.int32, device=dev)
+    ang = kps.data_ptr() + 12
+    check(L.b200_match_bruteforce_device(hm, B - 1, C.c_void_p(desc.data_ptr()), C.c_void_p(ang), 24, C.c_void_p(off[1:].data_ptr()),
+                                         C.c_void_p(counts[1:].data_ptr()), C.c_void_p(desc.data_ptr()), C.c_void_p(ang), 24, None,
+                                         C.c_void_p(off.data_ptr()), C.c_void_p(counts.data_ptr()), stride, stride, 0.8, 1,
+                                         C.c_void_p(pairs.data_ptr()), stride, C.c_void_p(npairs.data_ptr())))
+    torch.cuda.synchronize()
+    cn, kn, dn = counts.cpu().numpy(), kps.cpu().numpy(), desc.cpu().numpy()
+    refs = [O.orb_extract(frames[f]) for f in range(B)]
+    for f in range(B):
+        assert cn[f] == len(refs[f]["kps"])
+        assert np.array_equal(dn[f, :cn[f]], refs[f]["desc"])
+        assert np.array_equal(kn[f, :cn[f], 3], refs[f]["kps"]["angle"])
+    pn, nn = pairs.cpu().numpy(), npairs.cpu().numpy()
+    for p in range(B - 1):
+        a, b = refs[p + 1], refs[p]
+        ref = O.brute_force_match(a["desc"], a["kps"]["angle"], b["desc"], b["kps"]["angle"], None, 0.8, True)
+        assert np.array_equal(pn[p, :nn[p]], ref) and len(ref) > 20
+    check(L.b200_matcher_destroy(hm))
