@@ -153,6 +153,62 @@ int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, const void* d
 int b200_matcher_set_stream(b200_matcher_t h, void* stream, int use_own);
 int b200_matcher_sync(b200_matcher_t h);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * optimize::local_bundle_adjuster  (src/stella_vslam/optimize/local_bundle_adjuster.h:15-24,
+ * optimize/local_bundle_adjuster_g2o.cc:36-431).  The host adapter does the pointer-chasing gather (steps 1-4,
+ * :41-304) and the write-back under the map mutex (step 8, :379-430); this entry point is steps 5-7: two rounds of
+ * Levenberg-Marquardt with Schur complement over the landmarks (g2o BlockSolver_6_3 semantics), outlier marking in
+ * between, on a flattened problem.  All arithmetic is fp64.
+ * ---------------------------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t model;          /* 0: perspective-family edge (Perspective / Fisheye / RadialDivision all use the perspective edges on
+                               undistorted keypoints, reproj_edge_wrapper.h:64-188); 1: equirectangular (:129-146) */
+    double fx, fy, cx, cy;  /* perspective_reproj_edge.h:34 */
+    double fxb;             /* focal_x_baseline_ (stereo rows, perspective_reproj_edge.h:148) */
+    double cols, rows;      /* equirectangular_reproj_edge.h */
+} b200_camera_t;
+
+typedef struct {
+    int32_t n_poses, n_points, n_edges, n_cams;
+    const double* pose_cw;           /* K x 16 row-major 4x4: keyfrm->get_pose_cw() (shot_vertex_container.h:103-117) */
+    const uint8_t* pose_fixed;       /* K: 1 = fixed keyframe (local_bundle_adjuster_g2o.cc:184-190) */
+    const double* points;            /* L x 3: lm->get_pos_in_world() */
+    const uint8_t* point_fixed;      /* L or NULL: marker corners of keep_fixed_ markers (:272) */
+    const int32_t* e_pose;           /* E: keyframe index of the observation */
+    const int32_t* e_point;          /* E: landmark index */
+    const uint8_t* e_cam;            /* E: index into cams */
+    const float* e_obs;              /* E x 3: undist_keypt.pt.x, .y, stereo_x_right (< 0 => monocular edge, reproj_edge_wrapper.h:62) */
+    const float* e_inv_sigma_sq;     /* E: inv_level_sigma_sq_[octave] (:238) */
+    const float* e_delta;            /* E: Huber delta = sqrt(chi-square) as float (:205-208, 239-241) */
+    const uint8_t* e_robust;         /* E or NULL (=1): Huber kernel in the first round (use_huber_loss, :297-299) */
+    const uint8_t* e_can_be_outlier; /* E or NULL (=1): 0 for marker-corner edges, which are never outlier-tested (:251-304) */
+    const b200_camera_t* cams;
+} b200_lba_problem_t;
+
+typedef struct {
+    int32_t iterations[2];   /* LM iterations run in the robust / non-robust round */
+    int32_t n_outliers;
+    double chi2[2];          /* active robust chi-square after each round */
+    double lambda_init;
+    double lambda_final[2];
+} b200_lba_stats_t;
+
+typedef struct b200_lba_s* b200_lba_t;
+
+int b200_lba_create(int device, b200_lba_t* out);
+int b200_lba_destroy(b200_lba_t h);
+/* local_bundle_adjuster_g2o::optimize steps 5-7.  iters1/iters2: num_first_iter_/num_second_iter_ (5 / 10,
+ * local_bundle_adjuster_g2o.h:25-27).  force_stop: the caller's abort flag (mapping_module.cc:124,199-206), polled
+ * between LM iterations; may be NULL.  As in the reference it is also WRITTEN: the gain-threshold terminate action
+ * sets it when it stops a round (terminate_action.cc:55-72 via g2o's setOptimizerStopFlag), which is what makes the
+ * reference skip the second round after an early first-round stop (:317-321).
+ * Returns B200_ERR_ABORTED (nothing written) when *force_stop is already set on entry (:308-310).
+ * pose_cw_out: K x 16, points_out: L x 3, outlier_out: E (1 = observation to erase, :354-375). */
+int b200_lba_solve(b200_lba_t h, const b200_lba_problem_t* problem, int iters1, int iters2, volatile uint8_t* force_stop,
+                   double* pose_cw_out, double* points_out, uint8_t* outlier_out, b200_lba_stats_t* stats);
+/* Device time (ms, CUDA events) spent in the kernels of the last solve, and the number of kernel launches. */
+int b200_lba_last_profile(b200_lba_t h, float* gpu_ms, int* launches);
+
 #ifdef __cplusplus
 }
 #endif

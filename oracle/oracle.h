@@ -62,6 +62,44 @@ float orc_angle_diff(float a1, float a2);
 int orc_brute_force_match(const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2, const float* angle2,
                           const uint8_t* valid2, int n2, float lowe_ratio, int check_orientation, int32_t* pairs_out);
 
+/* ---- local bundle adjustment (lba_oracle.c; PARITY UNPINNED, see its header) ------------------------------------- */
+typedef struct {
+    int32_t model;            /* 0: perspective-family edges (Perspective/Fisheye/RadialDivision, reproj_edge_wrapper.h:64-188), 1: equirectangular */
+    double fx, fy, cx, cy;    /* perspective */
+    double fxb;               /* focal_x_baseline_ (stereo rows) */
+    double cols, rows;        /* equirectangular */
+} orc_camera_t;
+
+typedef struct {
+    int32_t n_poses, n_points, n_edges, n_cams;
+    const double* pose_cw;          /* K x 16, row-major 4x4 (keyfrm->get_pose_cw()) */
+    const uint8_t* pose_fixed;      /* K: fixed keyframes (local_bundle_adjuster_g2o.cc:184-190) */
+    const double* points;           /* L x 3 (pos_w) */
+    const uint8_t* point_fixed;     /* L or NULL (marker corners with keep_fixed_) */
+    const int32_t* e_pose;          /* E */
+    const int32_t* e_point;         /* E */
+    const uint8_t* e_cam;           /* E: camera index */
+    const float* e_obs;             /* E x 3: undist x, y, x_right (x_right < 0 => monocular edge) */
+    const float* e_inv_sigma_sq;    /* E: inv_level_sigma_sq_[octave] */
+    const float* e_delta;           /* E: Huber delta (sqrt chi-square, float) */
+    const uint8_t* e_robust;        /* E or NULL(=1): Huber kernel in the first round (marker edges of fixed markers: 0) */
+    const uint8_t* e_can_be_outlier;/* E or NULL(=1): landmark edges 1, marker-corner edges 0 */
+    const orc_camera_t* cams;
+} orc_lba_problem_t;
+
+typedef struct {
+    int32_t iterations[2];
+    int32_t n_outliers;
+    double chi2[2];           /* active robust chi2 after each round */
+    double lambda_init;
+    double lambda_final[2];
+} orc_lba_stats_t;
+
+/* local_bundle_adjuster_g2o::optimize steps 5-8 (local_bundle_adjuster_g2o.cc:306-409) on a flattened problem.
+ * Returns 0, or 1 when *force_stop was already set (no write-back, :308-310). */
+int orc_lba_solve(const orc_lba_problem_t* P, int iters1, int iters2, volatile uint8_t* force_stop, double* pose_cw_out,
+                  double* points_out, uint8_t* outlier_out, orc_lba_stats_t* stats);
+
 /* timed CPU baseline driver (batch_oracle.c): n frames on n_threads pthreads, extract then match to predecessor */
 int orc_frontend_batch(const uint8_t* frames, int n_unique, int n, int w, int h, const orc_orb_config_t* cfg, int cap, float lowe,
                        int check_ori, int n_threads, int* counts, int* n_matches);

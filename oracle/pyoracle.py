@@ -208,3 +208,58 @@ def frontend_batch(frames, n, min_area=800, lowe_ratio=0.8, check_orientation=Tr
     if (counts < 0).any():
         raise RuntimeError("oracle keypoint capacity too small")
     return counts, matches
+
+
+# ---- local BA ---------------------------------------------------------------------------------------------------------
+class Camera(C.Structure):
+    _fields_ = [("model", C.c_int32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("fxb", C.c_double), ("cols", C.c_double), ("rows", C.c_double)]
+
+
+class LbaProblem(C.Structure):
+    _fields_ = [("n_poses", C.c_int32), ("n_points", C.c_int32), ("n_edges", C.c_int32), ("n_cams", C.c_int32),
+                ("pose_cw", C.c_void_p), ("pose_fixed", C.c_void_p), ("points", C.c_void_p), ("point_fixed", C.c_void_p),
+                ("e_pose", C.c_void_p), ("e_point", C.c_void_p), ("e_cam", C.c_void_p), ("e_obs", C.c_void_p),
+                ("e_inv_sigma_sq", C.c_void_p), ("e_delta", C.c_void_p), ("e_robust", C.c_void_p), ("e_can_be_outlier", C.c_void_p),
+                ("cams", C.c_void_p)]
+
+
+class LbaStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32 * 2), ("n_outliers", C.c_int32), ("chi2", C.c_double * 2), ("lambda_init", C.c_double),
+                ("lambda_final", C.c_double * 2)]
+
+
+def pack_lba_problem(prob, ProblemT=LbaProblem, CameraT=Camera):
+    """dict from synth.make_ba_problem -> (ctypes struct, keep-alive list)."""
+    keep = []
+
+    def arr(x, dt):
+        if x is None:
+            return None
+        a = np.ascontiguousarray(x, dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    cams = (CameraT * len(prob["cams"]))(*[CameraT(c["model"], c["fx"], c["fy"], c["cx"], c["cy"], c["fxb"], c["cols"], c["rows"])
+                                            for c in prob["cams"]])
+    keep.append(cams)
+    K, L, E = len(prob["pose_cw"]), len(prob["points"]), len(prob["e_pose"])
+    P = ProblemT(K, L, E, len(prob["cams"]), arr(prob["pose_cw"], np.float64), arr(prob["pose_fixed"], np.uint8),
+                 arr(prob["points"], np.float64), arr(prob.get("point_fixed"), np.uint8), arr(prob["e_pose"], np.int32),
+                 arr(prob["e_point"], np.int32), arr(prob["e_cam"], np.uint8), arr(prob["e_obs"], np.float32),
+                 arr(prob["e_inv_sigma_sq"], np.float32), arr(prob["e_delta"], np.float32), arr(prob.get("e_robust"), np.uint8),
+                 arr(prob.get("e_can_be_outlier"), np.uint8), C.cast(cams, C.c_void_p))
+    return P, keep
+
+
+def lba_solve(prob, iters1=5, iters2=10, force_stop=None):
+    """local_bundle_adjuster_g2o::optimize steps 5-8 on the CPU oracle.  force_stop: optional 1-element uint8 array."""
+    L_ = lib()
+    L_.orc_lba_solve.argtypes = [C.POINTER(LbaProblem), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(LbaStats)]
+    P, keep = pack_lba_problem(prob)
+    K, L, E = P.n_poses, P.n_points, P.n_edges
+    pose_out, pts_out, outl = np.zeros((K, 4, 4)), np.zeros((L, 3)), np.zeros(E, np.uint8)
+    st = LbaStats()
+    rc = L_.orc_lba_solve(C.byref(P), iters1, iters2, _p(force_stop), _p(pose_out), _p(pts_out), _p(outl), C.byref(st))
+    return dict(rc=rc, pose_cw=pose_out, points=pts_out, outliers=outl, iterations=list(st.iterations), n_outliers=st.n_outliers,
+                chi2=list(st.chi2), lambda_init=st.lambda_init, lambda_final=list(st.lambda_final))

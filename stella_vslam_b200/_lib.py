@@ -38,6 +38,7 @@ SYMBOLS = [
     "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_stage_ms", "b200_orb_enable_timing",
     "b200_matcher_create", "b200_matcher_destroy", "b200_hamming_matrix", "b200_match_bruteforce",
     "b200_match_bruteforce_device", "b200_matcher_set_stream", "b200_matcher_sync",
+    "b200_lba_create", "b200_lba_destroy", "b200_lba_solve", "b200_lba_last_profile",
 ]
 
 

@@ -1,0 +1,1063 @@
+// lba_kernels.cu -- optimize::local_bundle_adjuster on sm_100a (fp64).
+//
+// Reference path (paths relative to the reference checkout):
+//   local_bundle_adjuster_g2o::optimize steps 5-7     src/stella_vslam/optimize/local_bundle_adjuster_g2o.cc:306-375
+//   mono/stereo perspective reprojection edges         optimize/internal/se3/perspective_reproj_edge.h:67-120, 175-239
+//   equirectangular reprojection edge                  optimize/internal/se3/equirectangular_reproj_edge.h:64-134
+//   edge wrapper (information, Huber delta, mono test) optimize/internal/se3/reproj_edge_wrapper.h:57-268
+//   shot_vertex / landmark_vertex oplus                optimize/internal/se3/shot_vertex.h:55-58, internal/landmark_vertex.h:50-53
+//   terminate_action (gain threshold 1e-3)             optimize/terminate_action.cc:36-76
+// and g2o's published algorithm (tag 20230223_git, not vendored): BaseBinaryEdge::constructQuadraticForm with
+// RobustKernelHuber, BlockSolver_6_3 (Schur complement over the landmarks), OptimizationAlgorithmLevenberg.
+//
+// Layout: edges are sorted by landmark (CSR), so every landmark-side quantity (Hll, bl, Dinv, back-substitution) is a
+// contiguous, atomics-free reduction; pose-side blocks are built by one CTA per free keyframe; the Schur complement is a
+// block-sparse  Hschur(i,j) = Hpp(i,j) - sum_l Hpl(i,l) Dinv(l) Hpl(j,l)^T  evaluated by one warp per (i,j) block over a
+// pair list built once per solve.  Everything is deterministic (fixed reduction orders, no floating-point atomics).
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace b200 {
+namespace lba {
+
+constexpr double kPi = 3.14159265358979323846;
+
+struct Cam {
+    int model;
+    double fx, fy, cx, cy, fxb, cols, rows;
+};
+
+// per-edge static data (sorted by landmark)
+struct EdgeS {
+    int pose;        // keyframe index
+    int pcol;        // free-pose column or -1
+    int point;       // landmark index
+    int lcol;        // free-landmark column or -1
+    float ox, oy, oxr;
+    float inv_sigma_sq;
+    float delta;
+    unsigned char cam, robust, can_outlier, pad;
+};
+
+struct View {
+    int K, L, E, Kf, Lf;
+    const EdgeS* edges;
+    const Cam* cams;
+    const int* pt_start;     // L+1 (all landmarks)
+    const int* pose_start;   // Kf+1
+    const int* pose_edges;   // edge ids grouped by free pose
+    unsigned char* level;    // E: 0 active, 1 outlier
+    unsigned char* robust;   // E: Huber on/off for the current round
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline void quat_to_rot(const double* q, double* R) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double tx = 2 * x, ty = 2 * y, tz = 2 * z;
+    const double twx = tx * w, twy = ty * w, twz = tz * w, txx = tx * x, txy = ty * x, txz = tz * x, tyy = ty * y, tyz = tz * y, tzz = tz * z;
+    R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+    R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+__host__ __device__ inline void rot_to_quat(const double* R, double* q) {
+    double t = R[0] + R[4] + R[8];
+    if (t > 0) {
+        t = sqrt(t + 1.0);
+        q[3] = 0.5 * t;
+        t = 0.5 / t;
+        q[0] = (R[7] - R[5]) * t; q[1] = (R[2] - R[6]) * t; q[2] = (R[3] - R[1]) * t;
+    } else {
+        int i = 0;
+        if (R[4] > R[0]) i = 1;
+        if (R[8] > R[i * 3 + i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        t = sqrt(R[i * 3 + i] - R[j * 3 + j] - R[k * 3 + k] + 1.0);
+        double qq[4];
+        qq[i] = 0.5 * t;
+        t = 0.5 / t;
+        qq[3] = (R[k * 3 + j] - R[j * 3 + k]) * t;
+        qq[j] = (R[j * 3 + i] + R[i * 3 + j]) * t;
+        qq[k] = (R[k * 3 + i] + R[i * 3 + k]) * t;
+        q[0] = qq[0]; q[1] = qq[1]; q[2] = qq[2]; q[3] = qq[3];
+    }
+}
+__host__ __device__ inline void quat_normalize(double* q) {  // SE3Quat::normalizeRotation
+    if (q[3] < 0) { q[0] = -q[0]; q[1] = -q[1]; q[2] = -q[2]; q[3] = -q[3]; }
+    const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+
+// Residual of one edge at pose Rt = [R(9) t(3)], landmark p.  dim = 2 (mono / equirect) or 3 (stereo).
+__device__ __forceinline__ void edge_residual(const EdgeS& e, const Cam& c, const double* Rt, const double* p, double* err, double* pc) {
+    pc[0] = Rt[0] * p[0] + Rt[1] * p[1] + Rt[2] * p[2] + Rt[9];
+    pc[1] = Rt[3] * p[0] + Rt[4] * p[1] + Rt[5] * p[2] + Rt[10];
+    pc[2] = Rt[6] * p[0] + Rt[7] * p[1] + Rt[8] * p[2] + Rt[11];
+    if (c.model == 1) {  // equirectangular_reproj_edge.h:130-134
+        const double theta = atan2(pc[0], pc[2]);
+        const double phi = -asin(pc[1] / sqrt(pc[0] * pc[0] + pc[1] * pc[1] + pc[2] * pc[2]));
+        err[0] = (double)e.ox - c.cols * (0.5 + theta / (2 * kPi));
+        err[1] = (double)e.oy - c.rows * (0.5 - phi / kPi);
+        err[2] = 0.0;
+    } else {  // perspective_reproj_edge.h:118-120, 236-239
+        const double rx = c.fx * pc[0] / pc[2] + c.cx;
+        err[0] = (double)e.ox - rx;
+        err[1] = (double)e.oy - (c.fy * pc[1] / pc[2] + c.cy);
+        err[2] = (e.oxr < 0.f) ? 0.0 : (double)e.oxr - (rx - c.fxb / pc[2]);
+    }
+}
+
+// linearizeOplus: Ji (3 rows x 3, landmark) and Jj (3 rows x 6, pose, rotation first); unused rows are zero.
+__device__ __forceinline__ void edge_jacobians(const EdgeS& e, const Cam& c, const double* Rt, const double* pc, double* Ji, double* Jj) {
+    const double x = pc[0], y = pc[1], z = pc[2];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Ji[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 18; ++i) Jj[i] = 0.0;
+    if (c.model == 1) {  // equirectangular_reproj_edge.h:71-128
+        const double L = sqrt(x * x + y * y + z * z);
+        const double dx[9] = {0, z, -y, 1, 0, 0, Rt[0], Rt[1], Rt[2]};
+        const double dy[9] = {-z, 0, x, 0, 1, 0, Rt[3], Rt[4], Rt[5]};
+        const double dz[9] = {y, -x, 0, 0, 0, 1, Rt[6], Rt[7], Rt[8]};
+        const double k0 = -(c.cols / (2 * kPi)) * (1.0 / (x * x + z * z));
+        const double k1 = -(c.rows / kPi) * (1.0 / (L * sqrt(x * x + z * z)));
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+            const double dL = (1.0 / L) * (x * dx[j] + y * dy[j] + z * dz[j]);
+            const double j0 = k0 * (z * dx[j] - x * dz[j]);
+            const double j1 = k1 * (L * dy[j] - y * dL);
+            if (j < 6) {
+                Jj[j] = j0;
+                Jj[6 + j] = j1;
+            } else {
+                Ji[j - 6] = j0;
+                Ji[3 + j - 6] = j1;
+            }
+        }
+        return;
+    }
+    const double fx = c.fx, fy = c.fy, z_sq = z * z;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {  // perspective_reproj_edge.h:89-95
+        Ji[j] = -fx * Rt[j] / z + fx * x * Rt[6 + j] / z_sq;
+        Ji[3 + j] = -fy * Rt[3 + j] / z + fy * y * Rt[6 + j] / z_sq;
+    }
+    Jj[0] = x * y / z_sq * fx; Jj[1] = -(1.0 + (x * x / z_sq)) * fx; Jj[2] = y / z * fx;
+    Jj[3] = -1.0 / z * fx;     Jj[4] = 0.0;                            Jj[5] = x / z_sq * fx;
+    Jj[6] = (1.0 + y * y / z_sq) * fy; Jj[7] = -x * y / z_sq * fy; Jj[8] = -x / z * fy;
+    Jj[9] = 0.0;                       Jj[10] = -1.0 / z * fy;     Jj[11] = y / z_sq * fy;
+    if (e.oxr >= 0.f) {  // perspective_reproj_edge.h:203-205, 221-226
+        const double fxb = c.fxb;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) Ji[6 + j] = Ji[j] - fxb * Rt[6 + j] / z_sq;
+        Jj[12] = Jj[0] - fxb * y / z_sq; Jj[13] = Jj[1] + fxb * x / z_sq; Jj[14] = Jj[2];
+        Jj[15] = Jj[3];                  Jj[16] = 0.0;                    Jj[17] = Jj[5] - fxb / z_sq;
+    }
+}
+
+// RobustKernelHuber: rho[1] weight and rho[0] cost
+__device__ __forceinline__ double huber_weight(double e2, double delta) { return (e2 <= delta * delta) ? 1.0 : delta / sqrt(e2); }
+__device__ __forceinline__ double huber_cost(double e2, double delta) { return (e2 <= delta * delta) ? e2 : 2 * sqrt(e2) * delta - delta * delta; }
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {  // deterministic tree reduction, blockDim.x power of two <= 1024
+    const int tid = threadIdx.x;
+    sh[tid] = v;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (tid < s) sh[tid] += sh[tid + s];
+        __syncthreads();
+    }
+    const double r = sh[0];
+    __syncthreads();
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1: per edge -- residual, chi2, Huber weight, Hpl block and the landmark-side contribution
+//     out: chi[e] (plain chi2, only for active edges), Hpl[18][E], pl[9][E] (6 unique Hll + 3 bl), chi partials
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kEdgeThreads = 128;
+
+__global__ void __launch_bounds__(kEdgeThreads) edges_kernel(View v, const double* __restrict__ Rt, const double* __restrict__ pts,
+                                                             double* __restrict__ chi, double* __restrict__ Hpl, double* __restrict__ pl,
+                                                             double* __restrict__ chi_partials, int linearize) {
+    __shared__ double sh[kEdgeThreads];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    double cost = 0.0;
+    if (e < v.E) {
+        const EdgeS ed = v.edges[e];
+        const bool active = v.level[e] == 0;
+        if (active) {
+            const Cam c = v.cams[ed.cam];
+            double err[3], pc[3];
+            const double* P = pts + 3 * (size_t)ed.point;
+            const double* T = Rt + 12 * (size_t)ed.pose;
+            edge_residual(ed, c, T, P, err, pc);
+            const double w = (double)ed.inv_sigma_sq;
+            const double e2 = w * (err[0] * err[0] + err[1] * err[1] + err[2] * err[2]);
+            chi[e] = e2;
+            const bool rob = v.robust[e] != 0;
+            cost = rob ? huber_cost(e2, (double)ed.delta) : e2;
+            if (linearize) {
+                double Ji[9], Jj[18];
+                edge_jacobians(ed, c, T, pc, Ji, Jj);
+                const double ww = w * (rob ? huber_weight(e2, (double)ed.delta) : 1.0);
+                const bool lfree = ed.lcol >= 0, pfree = ed.pcol >= 0;
+                // Hll (upper 6) and bl
+                double h[9];
+                h[0] = ww * (Ji[0] * Ji[0] + Ji[3] * Ji[3] + Ji[6] * Ji[6]);
+                h[1] = ww * (Ji[0] * Ji[1] + Ji[3] * Ji[4] + Ji[6] * Ji[7]);
+                h[2] = ww * (Ji[0] * Ji[2] + Ji[3] * Ji[5] + Ji[6] * Ji[8]);
+                h[3] = ww * (Ji[1] * Ji[1] + Ji[4] * Ji[4] + Ji[7] * Ji[7]);
+                h[4] = ww * (Ji[1] * Ji[2] + Ji[4] * Ji[5] + Ji[7] * Ji[8]);
+                h[5] = ww * (Ji[2] * Ji[2] + Ji[5] * Ji[5] + Ji[8] * Ji[8]);
+                h[6] = -ww * (Ji[0] * err[0] + Ji[3] * err[1] + Ji[6] * err[2]);
+                h[7] = -ww * (Ji[1] * err[0] + Ji[4] * err[1] + Ji[7] * err[2]);
+                h[8] = -ww * (Ji[2] * err[0] + Ji[5] * err[1] + Ji[8] * err[2]);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) pl[(size_t)i * v.E + e] = lfree ? h[i] : 0.0;
+                // Hpl = Jj^T W Ji (6x3)
+#pragma unroll
+                for (int a = 0; a < 6; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) {
+                        const double s = ww * (Jj[a] * Ji[b] + Jj[6 + a] * Ji[3 + b] + Jj[12 + a] * Ji[6 + b]);
+                        Hpl[(size_t)(a * 3 + b) * v.E + e] = (lfree && pfree) ? s : 0.0;
+                    }
+            }
+        } else if (linearize) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) pl[(size_t)i * v.E + e] = 0.0;
+#pragma unroll
+            for (int i = 0; i < 18; ++i) Hpl[(size_t)i * v.E + e] = 0.0;
+        }
+    }
+    const double s = block_sum(cost, sh);
+    if (threadIdx.x == 0) chi_partials[blockIdx.x] = s;
+}
+
+// K2: per landmark -- Hll (6 unique), bl (3) from its contiguous edge range; partial max |diag|
+__global__ void __launch_bounds__(128) points_kernel(View v, const double* __restrict__ pl, double* __restrict__ Hll, double* __restrict__ bl,
+                                                     double* __restrict__ diag_partials) {
+    __shared__ double sh[128];
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    double mx = 0.0;
+    if (l < v.L) {
+        const int lc = v.edges[v.pt_start[l] < v.E ? v.pt_start[l] : 0].lcol;  // same for all edges of the landmark
+        const int a = v.pt_start[l], b = v.pt_start[l + 1];
+        if (a < b && lc >= 0) {
+            double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int e = a; e < b; ++e)
+#pragma unroll
+                for (int i = 0; i < 9; ++i) h[i] += pl[(size_t)i * v.E + e];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) Hll[(size_t)i * v.Lf + lc] = h[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) bl[(size_t)i * v.Lf + lc] = h[6 + i];
+            mx = fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5])));
+        }
+    }
+    // max is order independent
+    sh[threadIdx.x] = mx;
+    __syncthreads();
+    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+        if (threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) diag_partials[blockIdx.x] = sh[0];
+}
+
+// K3: one CTA per free keyframe -- Hpp (6x6) and bp (6) over all of its active edges
+constexpr int kPoseThreads = 128;
+__global__ void __launch_bounds__(kPoseThreads) poses_kernel(View v, const double* __restrict__ Rt, const double* __restrict__ pts,
+                                                             double* __restrict__ Hpp, double* __restrict__ bp) {
+    __shared__ double sh[kPoseThreads];
+    const int pc_ = blockIdx.x;
+    double acc[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+    for (int k = v.pose_start[pc_] + threadIdx.x; k < v.pose_start[pc_ + 1]; k += blockDim.x) {
+        const int e = v.pose_edges[k];
+        if (v.level[e]) continue;
+        const EdgeS ed = v.edges[e];
+        const Cam c = v.cams[ed.cam];
+        double err[3], pc[3], Ji[9], Jj[18];
+        const double* T = Rt + 12 * (size_t)ed.pose;
+        edge_residual(ed, c, T, pts + 3 * (size_t)ed.point, err, pc);
+        edge_jacobians(ed, c, T, pc, Ji, Jj);
+        const double w = (double)ed.inv_sigma_sq;
+        const double e2 = w * (err[0] * err[0] + err[1] * err[1] + err[2] * err[2]);
+        const double ww = w * (v.robust[e] ? huber_weight(e2, (double)ed.delta) : 1.0);
+        int t = 0;
+#pragma unroll
+        for (int a = 0; a < 6; ++a)
+#pragma unroll
+            for (int b = a; b < 6; ++b) acc[t++] += ww * (Jj[a] * Jj[b] + Jj[6 + a] * Jj[6 + b] + Jj[12 + a] * Jj[12 + b]);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) acc[21 + a] += -ww * (Jj[a] * err[0] + Jj[6 + a] * err[1] + Jj[12 + a] * err[2]);
+    }
+    double red[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) red[i] = block_sum(acc[i], sh);
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) {
+                Hpp[(size_t)pc_ * 36 + a * 6 + b] = red[t];
+                Hpp[(size_t)pc_ * 36 + b * 6 + a] = red[t];
+                ++t;
+            }
+        for (int a = 0; a < 6; ++a) bp[(size_t)pc_ * 6 + a] = red[21 + a];
+    }
+}
+
+// K4: per landmark -- Dinv = (Hll + lambda I)^-1, cl = Dinv bl, T(e) = Hpl(e) Dinv for its edges
+__global__ void __launch_bounds__(128) schur_prep_kernel(View v, double lambda, const double* __restrict__ Hll, const double* __restrict__ bl,
+                                                         const double* __restrict__ Hpl, double* __restrict__ Dinv, double* __restrict__ cl,
+                                                         double* __restrict__ Tm, int* __restrict__ fail) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= v.L) return;
+    const int a0 = v.pt_start[l], b0 = v.pt_start[l + 1];
+    if (a0 >= b0) return;
+    const int lc = v.edges[a0].lcol;
+    if (lc < 0) return;
+    const double A0 = Hll[lc] + lambda, A1 = Hll[(size_t)v.Lf + lc], A2 = Hll[(size_t)2 * v.Lf + lc];
+    const double A4 = Hll[(size_t)3 * v.Lf + lc] + lambda, A5 = Hll[(size_t)4 * v.Lf + lc], A8 = Hll[(size_t)5 * v.Lf + lc] + lambda;
+    // symmetric 3x3 inverse by cofactors (Eigen's fixed-size inverse)
+    const double c0 = A4 * A8 - A5 * A5, c1 = A5 * A2 - A1 * A8, c2 = A1 * A5 - A4 * A2;
+    const double det = A0 * c0 + A1 * c1 + A2 * c2;
+    if (det == 0.0 || !isfinite(det)) {
+        *fail = 1;
+        return;
+    }
+    const double id = 1.0 / det;
+    const double D0 = c0 * id, D1 = c1 * id, D2 = c2 * id;
+    const double D4 = (A0 * A8 - A2 * A2) * id, D5 = (A1 * A2 - A0 * A5) * id, D8 = (A0 * A4 - A1 * A1) * id;
+    Dinv[lc] = D0; Dinv[(size_t)v.Lf + lc] = D1; Dinv[(size_t)2 * v.Lf + lc] = D2;
+    Dinv[(size_t)3 * v.Lf + lc] = D4; Dinv[(size_t)4 * v.Lf + lc] = D5; Dinv[(size_t)5 * v.Lf + lc] = D8;
+    const double b0_ = bl[lc], b1_ = bl[(size_t)v.Lf + lc], b2_ = bl[(size_t)2 * v.Lf + lc];
+    cl[lc] = D0 * b0_ + D1 * b1_ + D2 * b2_;
+    cl[(size_t)v.Lf + lc] = D1 * b0_ + D4 * b1_ + D5 * b2_;
+    cl[(size_t)2 * v.Lf + lc] = D2 * b0_ + D5 * b1_ + D8 * b2_;
+    for (int e = a0; e < b0; ++e) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+            const double h0 = Hpl[(size_t)(r * 3) * v.E + e], h1 = Hpl[(size_t)(r * 3 + 1) * v.E + e], h2 = Hpl[(size_t)(r * 3 + 2) * v.E + e];
+            Tm[(size_t)(r * 3) * v.E + e] = h0 * D0 + h1 * D1 + h2 * D2;
+            Tm[(size_t)(r * 3 + 1) * v.E + e] = h0 * D1 + h1 * D4 + h2 * D5;
+            Tm[(size_t)(r * 3 + 2) * v.E + e] = h0 * D2 + h1 * D5 + h2 * D8;
+        }
+    }
+}
+
+// K5: one warp per upper block (i <= j) of the reduced pose system:
+//     Hs(i,j) = [i==j] (Hpp(i) + lambda I) - sum_pairs T(a) Hpl(c)^T ;  bs(i) = bp(i) - sum_{a of i} Hpl(a) cl(point(a))
+struct SchurBlock {
+    int i, j, start, end;  // pairs [start, end)
+};
+__global__ void __launch_bounds__(128) schur_blocks_kernel(View v, double lambda, const SchurBlock* __restrict__ blocks, int n_blocks,
+                                                           const int2* __restrict__ pairs, const double* __restrict__ Hpp,
+                                                           const double* __restrict__ bp, const double* __restrict__ Hpl,
+                                                           const double* __restrict__ Tm, const double* __restrict__ cl,
+                                                           double* __restrict__ Hs, double* __restrict__ bs, int n) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= n_blocks) return;
+    const SchurBlock sb = blocks[wid];
+    double acc[36];
+#pragma unroll
+    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
+    double accb[6] = {0, 0, 0, 0, 0, 0};
+    for (int k = sb.start + lane; k < sb.end; k += 32) {
+        const int2 pr = pairs[k];
+        double t[18], h[18];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) {
+            t[i] = Tm[(size_t)i * v.E + pr.x];
+            h[i] = Hpl[(size_t)i * v.E + pr.y];
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int c = 0; c < 6; ++c) acc[r * 6 + c] += t[r * 3] * h[c * 3] + t[r * 3 + 1] * h[c * 3 + 1] + t[r * 3 + 2] * h[c * 3 + 2];
+        if (sb.i == sb.j) {  // pr.x == pr.y: the edge of keyframe i to this landmark
+            const int lc = v.edges[pr.x].lcol;
+            const double c0 = cl[lc], c1 = cl[(size_t)v.Lf + lc], c2 = cl[(size_t)2 * v.Lf + lc];
+#pragma unroll
+            for (int r = 0; r < 6; ++r) accb[r] += h[r * 3] * c0 + h[r * 3 + 1] * c1 + h[r * 3 + 2] * c2;
+        }
+    }
+    // fixed-order warp reduction
+#pragma unroll
+    for (int i = 0; i < 36; ++i)
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc[i] += __shfl_down_sync(0xFFFFFFFFu, acc[i], s);
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) accb[i] += __shfl_down_sync(0xFFFFFFFFu, accb[i], s);
+    if (lane == 0) {
+        for (int r = 0; r < 6; ++r)
+            for (int c = 0; c < 6; ++c) {
+                double val = -acc[r * 6 + c];
+                if (sb.i == sb.j) val += Hpp[(size_t)sb.i * 36 + r * 6 + c] + (r == c ? lambda : 0.0);
+                Hs[(size_t)(6 * sb.i + r) * n + 6 * sb.j + c] = val;
+                Hs[(size_t)(6 * sb.j + c) * n + 6 * sb.i + r] = val;
+            }
+        if (sb.i == sb.j)
+            for (int r = 0; r < 6; ++r) bs[6 * sb.i + r] = bp[(size_t)sb.i * 6 + r] - accb[r];
+    }
+}
+
+// K6: dense Cholesky of the reduced system (<= 6*Kf unknowns), solve, then the keyframe updates
+//     (shot_vertex::oplusImpl: T <- exp(dx) * T) into the trial state.  One CTA.
+__device__ void se3_oplus(const double* q, const double* t, const double* upd, double* qo, double* to) {
+    const double* om = upd;
+    const double* up = upd + 3;
+    const double theta = sqrt(om[0] * om[0] + om[1] * om[1] + om[2] * om[2]);
+    const double O[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0};
+    double O2[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) O2[i * 3 + j] = O[i * 3] * O[j] + O[i * 3 + 1] * O[3 + j] + O[i * 3 + 2] * O[6 + j];
+    double a, b, c, d;
+    if (theta < 0.00001) {  // g2o SE3Quat::exp small-angle branch
+        a = 1.0; b = 0.5; c = 0.5; d = 1.0 / 6.0;
+    } else {
+        a = sin(theta) / theta;
+        b = (1 - cos(theta)) / (theta * theta);
+        c = b;
+        d = (theta - sin(theta)) / (theta * theta * theta);
+    }
+    double R[9], V[9];
+    for (int i = 0; i < 9; ++i) {
+        const double I = (i % 4 == 0) ? 1.0 : 0.0;
+        R[i] = I + a * O[i] + b * O2[i];
+        V[i] = I + c * O[i] + d * O2[i];
+    }
+    double dq[4], dt[3];
+    rot_to_quat(R, dq);
+    quat_normalize(dq);
+    for (int i = 0; i < 3; ++i) dt[i] = V[i * 3] * up[0] + V[i * 3 + 1] * up[1] + V[i * 3 + 2] * up[2];
+    // (dq, dt) * (q, t): rotate t by dq (Eigen: v + w*uv + qv x uv, uv = 2 qv x v)
+    double uv[3] = {dq[1] * t[2] - dq[2] * t[1], dq[2] * t[0] - dq[0] * t[2], dq[0] * t[1] - dq[1] * t[0]};
+    uv[0] += uv[0]; uv[1] += uv[1]; uv[2] += uv[2];
+    to[0] = dt[0] + t[0] + dq[3] * uv[0] + (dq[1] * uv[2] - dq[2] * uv[1]);
+    to[1] = dt[1] + t[1] + dq[3] * uv[1] + (dq[2] * uv[0] - dq[0] * uv[2]);
+    to[2] = dt[2] + t[2] + dq[3] * uv[2] + (dq[0] * uv[1] - dq[1] * uv[0]);
+    double nq[4];
+    nq[3] = dq[3] * q[3] - dq[0] * q[0] - dq[1] * q[1] - dq[2] * q[2];
+    nq[0] = dq[3] * q[0] + dq[0] * q[3] + dq[1] * q[2] - dq[2] * q[1];
+    nq[1] = dq[3] * q[1] + dq[1] * q[3] + dq[2] * q[0] - dq[0] * q[2];
+    nq[2] = dq[3] * q[2] + dq[2] * q[3] + dq[0] * q[1] - dq[1] * q[0];
+    quat_normalize(nq);
+    qo[0] = nq[0]; qo[1] = nq[1]; qo[2] = nq[2]; qo[3] = nq[3];
+}
+
+constexpr int kCholThreads = 512;
+__global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, double* __restrict__ A, const double* __restrict__ bs, double lambda,
+                                                                  const double* __restrict__ bp, double* __restrict__ xp, int K,
+                                                                  const int* __restrict__ pose_col, const double* __restrict__ q_cur,
+                                                                  const double* __restrict__ t_cur, double* __restrict__ q_new,
+                                                                  double* __restrict__ t_new, double* __restrict__ Rt_new,
+                                                                  double* __restrict__ result, int* __restrict__ fail) {
+    __shared__ double xs[1024];
+    __shared__ double sh[kCholThreads];
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad = *fail;
+    __syncthreads();
+    // right-looking Cholesky on the lower triangle, in place (A is L2 resident: n <= a few hundred)
+    for (int j = 0; j < n && !bad; ++j) {
+        if (tid == 0) {
+            const double d = A[(size_t)j * n + j];
+            if (!(d > 0.0) || !isfinite(d)) bad = 1;
+            else A[(size_t)j * n + j] = sqrt(d);
+        }
+        __syncthreads();
+        if (bad) break;
+        const double djj = A[(size_t)j * n + j];
+        for (int i = j + 1 + tid; i < n; i += blockDim.x) A[(size_t)i * n + j] /= djj;
+        __syncthreads();
+        const int m = n - j - 1;  // trailing update of the lower triangle: rows i > j, cols j < k <= i
+        for (int idx = tid; idx < m * m; idx += blockDim.x) {
+            const int i = j + 1 + idx / m, k = j + 1 + idx % m;
+            if (k <= i) A[(size_t)i * n + k] -= A[(size_t)i * n + j] * A[(size_t)k * n + j];
+        }
+        __syncthreads();
+    }
+    if (bad) {
+        if (tid == 0) {
+            *fail = 1;
+            result[0] = 0.0;
+        }
+    } else {
+        // forward / backward substitution (n small; column-oriented, parallel over rows)
+        for (int i = tid; i < n; i += blockDim.x) xs[i] = bs[i];
+        __syncthreads();
+        for (int j = 0; j < n; ++j) {
+            if (tid == 0) xs[j] /= A[(size_t)j * n + j];
+            __syncthreads();
+            const double xj = xs[j];
+            for (int i = j + 1 + tid; i < n; i += blockDim.x) xs[i] -= A[(size_t)i * n + j] * xj;
+            __syncthreads();
+        }
+        for (int j = n - 1; j >= 0; --j) {
+            if (tid == 0) xs[j] /= A[(size_t)j * n + j];
+            __syncthreads();
+            const double xj = xs[j];
+            for (int i = tid; i < j; i += blockDim.x) xs[i] -= A[(size_t)j * n + i] * xj;
+            __syncthreads();
+        }
+        double sc = 0.0;  // pose part of computeScale: sum x (lambda x + b)
+        for (int i = tid; i < n; i += blockDim.x) {
+            xp[i] = xs[i];
+            sc += xs[i] * (lambda * xs[i] + bp[i]);
+        }
+        const double tot = block_sum(sc, sh);
+        if (tid == 0) {
+            result[0] = 1.0;
+            result[1] = tot;
+        }
+    }
+    __syncthreads();
+    // trial keyframe states (fixed keyframes and failed solves keep the current state)
+    for (int k = tid; k < K; k += blockDim.x) {
+        double qn[4], tn[3];
+        const int pc = pose_col[k];
+        if (pc >= 0 && !bad) {
+            se3_oplus(q_cur + 4 * k, t_cur + 3 * k, xs + 6 * pc, qn, tn);
+        } else {
+            for (int i = 0; i < 4; ++i) qn[i] = q_cur[4 * k + i];
+            for (int i = 0; i < 3; ++i) tn[i] = t_cur[3 * k + i];
+        }
+        for (int i = 0; i < 4; ++i) q_new[4 * k + i] = qn[i];
+        for (int i = 0; i < 3; ++i) t_new[3 * k + i] = tn[i];
+        double R[9];
+        quat_to_rot(qn, R);
+        for (int i = 0; i < 9; ++i) Rt_new[12 * k + i] = R[i];
+        for (int i = 0; i < 3; ++i) Rt_new[12 * k + 9 + i] = tn[i];
+    }
+}
+
+// K7: per landmark -- back-substitution x_l = Dinv (bl - sum_e Hpl(e)^T x_p), trial landmark, scale partials
+__global__ void __launch_bounds__(128) backsub_kernel(View v, double lambda, const double* __restrict__ Dinv, const double* __restrict__ bl,
+                                                      const double* __restrict__ Hpl, const double* __restrict__ xp,
+                                                      const double* __restrict__ pts_cur, double* __restrict__ pts_new,
+                                                      double* __restrict__ scale_partials, const int* __restrict__ fail) {
+    __shared__ double sh[128];
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    double sc = 0.0;
+    if (l < v.L) {
+        double p0 = pts_cur[3 * (size_t)l], p1 = pts_cur[3 * (size_t)l + 1], p2 = pts_cur[3 * (size_t)l + 2];
+        const int a0 = v.pt_start[l], b0 = v.pt_start[l + 1];
+        const int lc = (a0 < b0) ? v.edges[a0].lcol : -1;
+        if (lc >= 0 && !*fail) {
+            const double bb0 = bl[lc], bb1 = bl[(size_t)v.Lf + lc], bb2 = bl[(size_t)2 * v.Lf + lc];
+            double c0 = bb0, c1 = bb1, c2 = bb2;
+            for (int e = a0; e < b0; ++e) {
+                const int pcol = v.edges[e].pcol;
+                if (pcol < 0) continue;
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    const double x = xp[6 * pcol + r];
+                    c0 -= Hpl[(size_t)(r * 3) * v.E + e] * x;
+                    c1 -= Hpl[(size_t)(r * 3 + 1) * v.E + e] * x;
+                    c2 -= Hpl[(size_t)(r * 3 + 2) * v.E + e] * x;
+                }
+            }
+            const double D0 = Dinv[lc], D1 = Dinv[(size_t)v.Lf + lc], D2 = Dinv[(size_t)2 * v.Lf + lc];
+            const double D4 = Dinv[(size_t)3 * v.Lf + lc], D5 = Dinv[(size_t)4 * v.Lf + lc], D8 = Dinv[(size_t)5 * v.Lf + lc];
+            const double x0 = D0 * c0 + D1 * c1 + D2 * c2, x1 = D1 * c0 + D4 * c1 + D5 * c2, x2 = D2 * c0 + D5 * c1 + D8 * c2;
+            sc = x0 * (lambda * x0 + bb0) + x1 * (lambda * x1 + bb1) + x2 * (lambda * x2 + bb2);
+            p0 += x0; p1 += x1; p2 += x2;  // landmark_vertex::oplusImpl
+        }
+        pts_new[3 * (size_t)l] = p0; pts_new[3 * (size_t)l + 1] = p1; pts_new[3 * (size_t)l + 2] = p2;
+    }
+    const double s = block_sum(sc, sh);
+    if (threadIdx.x == 0) scale_partials[blockIdx.x] = s;
+}
+
+// K8: outlier test (local_bundle_adjuster_g2o.cc:323-344, 357-375): chi2 of the last activation vs the chi-square
+//     threshold, or non-positive depth at the current estimate.  mode 0: mark level + drop the kernel; mode 1: report.
+__global__ void __launch_bounds__(128) outlier_kernel(View v, const double* __restrict__ Rt, const double* __restrict__ pts,
+                                                      const double* __restrict__ chi, int mode, unsigned char* __restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= v.E) return;
+    const EdgeS ed = v.edges[e];
+    unsigned char o = 0;
+    if (ed.can_outlier) {
+        const double thr = (ed.oxr < 0.f) ? (double)5.99146f : (double)7.81473f;
+        bool depth_ok = true;
+        if (v.cams[ed.cam].model != 1) {  // reproj_edge_wrapper.h:233-268 (equirectangular: always true)
+            const double* T = Rt + 12 * (size_t)ed.pose;
+            const double* P = pts + 3 * (size_t)ed.point;
+            depth_ok = 0.0 < T[6] * P[0] + T[7] * P[1] + T[8] * P[2] + T[11];
+        }
+        o = (thr < chi[e] || !depth_ok) ? 1 : 0;
+    }
+    if (mode == 0) {
+        if (ed.can_outlier) {
+            if (o) v.level[e] = 1;
+            v.robust[e] = 0;
+        }
+    } else {
+        out[e] = o;
+    }
+}
+
+// carry the chi2 of inactive edges across the trial/current swap
+__global__ void __launch_bounds__(128) carry_chi_kernel(View v, const double* __restrict__ chi_cur, double* __restrict__ chi_new) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < v.E && v.level[e]) chi_new[e] = chi_cur[e];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host
+// ---------------------------------------------------------------------------------------------------------------
+struct Solver {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    unsigned char* d_arena = nullptr;
+    size_t arena_cap = 0;
+    unsigned char* h_stage = nullptr;  // pinned upload staging
+    size_t h_cap = 0;
+    double* h_res = nullptr;           // pinned readback
+    size_t h_res_cap = 0;
+    float last_ms = 0.f;
+    int last_launches = 0;
+
+    int ensure(size_t dev_bytes, size_t host_bytes, size_t res_doubles) {
+        if (dev_bytes > arena_cap) {
+            if (d_arena) B200_CUDA(cudaFree(d_arena));
+            d_arena = nullptr;
+            arena_cap = 0;
+            B200_CUDA(cudaMalloc(&d_arena, dev_bytes + dev_bytes / 4));
+            arena_cap = dev_bytes + dev_bytes / 4;
+        }
+        if (host_bytes > h_cap) {
+            if (h_stage) B200_CUDA(cudaFreeHost(h_stage));
+            h_stage = nullptr;
+            h_cap = 0;
+            B200_CUDA(cudaHostAlloc(&h_stage, host_bytes + host_bytes / 4, cudaHostAllocDefault));
+            h_cap = host_bytes + host_bytes / 4;
+        }
+        if (res_doubles > h_res_cap) {
+            if (h_res) B200_CUDA(cudaFreeHost(h_res));
+            h_res = nullptr;
+            h_res_cap = 0;
+            B200_CUDA(cudaHostAlloc(&h_res, sizeof(double) * res_doubles * 2, cudaHostAllocDefault));
+            h_res_cap = res_doubles * 2;
+        }
+        return B200_OK;
+    }
+};
+
+struct Carver {
+    size_t off = 0;
+    template <typename T>
+    size_t take(size_t n) {
+        off = round_up(off, (size_t)256);
+        const size_t o = off;
+        off += sizeof(T) * std::max<size_t>(n, 1);
+        return o;
+    }
+};
+
+static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2, volatile uint8_t* force_stop, double* pose_out,
+                 double* points_out, uint8_t* outlier_out, b200_lba_stats_t* stats) {
+    const int K = P->n_poses, L = P->n_points, E = P->n_edges;
+    if (stats) std::memset(stats, 0, sizeof(*stats));
+    // ---- flatten / sort on the host ------------------------------------------------------------------------------
+    std::vector<int> pose_col(K), pt_col(L);
+    int Kf = 0, Lf = 0;
+    for (int k = 0; k < K; ++k) pose_col[k] = P->pose_fixed[k] ? -1 : Kf++;
+    for (int l = 0; l < L; ++l) pt_col[l] = (P->point_fixed && P->point_fixed[l]) ? -1 : Lf++;
+    std::vector<int> pt_start(L + 1, 0), order(E);
+    for (int e = 0; e < E; ++e) {
+        if (P->e_point[e] < 0 || P->e_point[e] >= L || P->e_pose[e] < 0 || P->e_pose[e] >= K || P->e_cam[e] >= P->n_cams) {
+            set_error("b200_lba_solve: edge %d references an invalid vertex/camera", e);
+            return B200_ERR_INVALID;
+        }
+        pt_start[P->e_point[e] + 1]++;
+    }
+    for (int l = 0; l < L; ++l) pt_start[l + 1] += pt_start[l];
+    {
+        std::vector<int> fill(pt_start.begin(), pt_start.end() - 1);
+        for (int e = 0; e < E; ++e) order[fill[P->e_point[e]]++] = e;  // stable: original order within a landmark
+    }
+    std::vector<EdgeS> edges(E);
+    std::vector<unsigned char> robust(E);
+    std::vector<int> pose_start(Kf + 1, 0), pose_edges;
+    for (int s = 0; s < E; ++s) {
+        const int e = order[s];
+        EdgeS& d = edges[s];
+        d.pose = P->e_pose[e];
+        d.pcol = pose_col[d.pose];
+        d.point = P->e_point[e];
+        d.lcol = pt_col[d.point];
+        d.ox = P->e_obs[3 * e]; d.oy = P->e_obs[3 * e + 1]; d.oxr = P->e_obs[3 * e + 2];
+        d.inv_sigma_sq = P->e_inv_sigma_sq[e];
+        d.delta = P->e_delta[e];
+        d.cam = P->e_cam[e];
+        d.robust = P->e_robust ? P->e_robust[e] : 1;
+        d.can_outlier = P->e_can_be_outlier ? P->e_can_be_outlier[e] : 1;
+        d.pad = 0;
+        robust[s] = d.robust;
+        if (d.pcol >= 0) pose_start[d.pcol + 1]++;
+    }
+    for (int k = 0; k < Kf; ++k) pose_start[k + 1] += pose_start[k];
+    pose_edges.resize(std::max(1, pose_start[Kf]));
+    {
+        std::vector<int> fill(pose_start.begin(), pose_start.end() - 1);
+        for (int s = 0; s < E; ++s)
+            if (edges[s].pcol >= 0) pose_edges[fill[edges[s].pcol]++] = s;
+    }
+    // Schur pair list grouped by upper block (i <= j)
+    const int n_blocks = Kf * (Kf + 1) / 2;
+    auto block_id = [Kf](int i, int j) { return i * Kf - i * (i - 1) / 2 + (j - i); };
+    std::vector<int> blk_count(n_blocks + 1, 0);
+    for (int l = 0; l < L; ++l) {
+        if (pt_col[l] < 0) continue;
+        for (int a = pt_start[l]; a < pt_start[l + 1]; ++a) {
+            if (edges[a].pcol < 0) continue;
+            for (int c = pt_start[l]; c < pt_start[l + 1]; ++c) {
+                if (edges[c].pcol < 0 || edges[c].pcol < edges[a].pcol) continue;
+                if (edges[c].pcol == edges[a].pcol && c != a) continue;  // a keyframe observes a landmark once
+                blk_count[block_id(edges[a].pcol, edges[c].pcol) + 1]++;
+            }
+        }
+    }
+    for (int b = 0; b < n_blocks; ++b) blk_count[b + 1] += blk_count[b];
+    const int n_pairs = blk_count[n_blocks];
+    std::vector<int2> pairs(std::max(1, n_pairs));
+    {
+        std::vector<int> fill(blk_count.begin(), blk_count.end() - 1);
+        for (int l = 0; l < L; ++l) {
+            if (pt_col[l] < 0) continue;
+            for (int a = pt_start[l]; a < pt_start[l + 1]; ++a) {
+                if (edges[a].pcol < 0) continue;
+                for (int c = pt_start[l]; c < pt_start[l + 1]; ++c) {
+                    if (edges[c].pcol < 0 || edges[c].pcol < edges[a].pcol) continue;
+                    if (edges[c].pcol == edges[a].pcol && c != a) continue;
+                    pairs[fill[block_id(edges[a].pcol, edges[c].pcol)]++] = make_int2(a, c);
+                }
+            }
+        }
+    }
+    std::vector<SchurBlock> blocks(std::max(1, n_blocks));
+    for (int i = 0, b = 0; i < Kf; ++i)
+        for (int j = i; j < Kf; ++j, ++b) blocks[b] = SchurBlock{i, j, blk_count[b], blk_count[b + 1]};
+    // initial state: util::converter::to_g2o_SE3 (util/converter.cc:17-21)
+    std::vector<double> q0(4 * (size_t)std::max(K, 1)), t0(3 * (size_t)std::max(K, 1)), Rt0(12 * (size_t)std::max(K, 1));
+    for (int k = 0; k < K; ++k) {
+        const double* M = P->pose_cw + 16 * (size_t)k;
+        const double R[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]};
+        rot_to_quat(R, &q0[4 * k]);
+        quat_normalize(&q0[4 * k]);
+        t0[3 * k] = M[3]; t0[3 * k + 1] = M[7]; t0[3 * k + 2] = M[11];
+        quat_to_rot(&q0[4 * k], &Rt0[12 * k]);
+        Rt0[12 * k + 9] = M[3]; Rt0[12 * k + 10] = M[7]; Rt0[12 * k + 11] = M[11];
+    }
+    std::vector<Cam> cams(std::max(1, P->n_cams));
+    for (int i = 0; i < P->n_cams; ++i) {
+        const b200_camera_t& c = P->cams[i];
+        cams[i] = Cam{c.model, c.fx, c.fy, c.cx, c.cy, c.fxb, c.cols, c.rows};
+    }
+
+    // ---- device arena ----------------------------------------------------------------------------------------------
+    const int n = 6 * Kf;
+    const int eb = ceil_div(std::max(E, 1), kEdgeThreads), lb = ceil_div(std::max(L, 1), 128);
+    Carver up;  // uploaded region (mirrors the pinned staging buffer)
+    const size_t o_edges = up.take<EdgeS>(E), o_cams = up.take<Cam>(P->n_cams), o_ptstart = up.take<int>(L + 1);
+    const size_t o_posestart = up.take<int>(Kf + 1), o_poseedges = up.take<int>(pose_edges.size()), o_robust = up.take<unsigned char>(E);
+    const size_t o_posecol = up.take<int>(K), o_blocks = up.take<SchurBlock>(n_blocks), o_pairs = up.take<int2>(n_pairs);
+    const size_t o_q0 = up.take<double>(4 * (size_t)K), o_t0 = up.take<double>(3 * (size_t)K), o_Rt0 = up.take<double>(12 * (size_t)K);
+    const size_t o_pts0 = up.take<double>(3 * (size_t)L);
+    const size_t upload_bytes = round_up(up.off, (size_t)256);
+    Carver dv;
+    dv.off = upload_bytes;
+    const size_t o_q1 = dv.take<double>(4 * (size_t)K), o_t1 = dv.take<double>(3 * (size_t)K), o_Rt1 = dv.take<double>(12 * (size_t)K);
+    const size_t o_pts1 = dv.take<double>(3 * (size_t)L);
+    const size_t o_level = dv.take<unsigned char>(E), o_chi0 = dv.take<double>(E), o_chi1 = dv.take<double>(E);
+    const size_t o_Hpl = dv.take<double>(18 * (size_t)E), o_T = dv.take<double>(18 * (size_t)E), o_pl = dv.take<double>(9 * (size_t)E);
+    const size_t o_Hll = dv.take<double>(6 * (size_t)Lf), o_bl = dv.take<double>(3 * (size_t)Lf), o_Dinv = dv.take<double>(6 * (size_t)Lf);
+    const size_t o_cl = dv.take<double>(3 * (size_t)Lf), o_Hpp = dv.take<double>(36 * (size_t)Kf), o_bp = dv.take<double>(6 * (size_t)Kf);
+    const size_t o_Hs = dv.take<double>((size_t)n * n), o_bs = dv.take<double>(n), o_xp = dv.take<double>(n);
+    // readback block: [chi partials eb][diag partials lb][scale partials lb][result 2][Hpp diag 6Kf]
+    const size_t res_n = (size_t)eb + 2 * (size_t)lb + 2 + (size_t)std::max(n, 1);
+    const size_t o_res = dv.take<double>(res_n), o_fail = dv.take<int>(1), o_out = dv.take<unsigned char>(E);
+    int rc = S.ensure(dv.off + 256, upload_bytes, res_n);
+    if (rc) return rc;
+    unsigned char* hs = S.h_stage;
+    std::memset(hs, 0, upload_bytes);
+    auto put = [&](size_t off, const void* src, size_t bytes) { if (bytes) std::memcpy(hs + off, src, bytes); };
+    put(o_edges, edges.data(), sizeof(EdgeS) * E);
+    put(o_cams, cams.data(), sizeof(Cam) * P->n_cams);
+    put(o_ptstart, pt_start.data(), sizeof(int) * (L + 1));
+    put(o_posestart, pose_start.data(), sizeof(int) * (Kf + 1));
+    put(o_poseedges, pose_edges.data(), sizeof(int) * pose_edges.size());
+    put(o_robust, robust.data(), E);
+    put(o_posecol, pose_col.data(), sizeof(int) * K);
+    put(o_blocks, blocks.data(), sizeof(SchurBlock) * n_blocks);
+    put(o_pairs, pairs.data(), sizeof(int2) * n_pairs);
+    put(o_q0, q0.data(), sizeof(double) * 4 * K);
+    put(o_t0, t0.data(), sizeof(double) * 3 * K);
+    put(o_Rt0, Rt0.data(), sizeof(double) * 12 * K);
+    put(o_pts0, P->points, sizeof(double) * 3 * (size_t)L);
+    unsigned char* d = S.d_arena;
+    cudaStream_t st = S.stream;
+    int launches = 0;
+    B200_CUDA(cudaEventRecord(S.ev0, st));
+    B200_CUDA(cudaMemcpyAsync(d, hs, upload_bytes, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemsetAsync(d + o_level, 0, E ? E : 1, st));
+    B200_CUDA(cudaMemsetAsync(d + o_chi0, 0, sizeof(double) * (E ? E : 1), st));
+    B200_CUDA(cudaMemsetAsync(d + o_fail, 0, sizeof(int), st));
+
+    View v{K, L, E, Kf, Lf, (const EdgeS*)(d + o_edges), (const Cam*)(d + o_cams), (const int*)(d + o_ptstart), (const int*)(d + o_posestart),
+           (const int*)(d + o_poseedges), d + o_level, d + o_robust};
+    double* qs[2] = {(double*)(d + o_q0), (double*)(d + o_q1)};
+    double* ts[2] = {(double*)(d + o_t0), (double*)(d + o_t1)};
+    double* Rts[2] = {(double*)(d + o_Rt0), (double*)(d + o_Rt1)};
+    double* ptss[2] = {(double*)(d + o_pts0), (double*)(d + o_pts1)};
+    double* chis[2] = {(double*)(d + o_chi0), (double*)(d + o_chi1)};
+    double *Hpl = (double*)(d + o_Hpl), *Tm = (double*)(d + o_T), *pl = (double*)(d + o_pl), *Hll = (double*)(d + o_Hll), *bl = (double*)(d + o_bl);
+    double *Dinv = (double*)(d + o_Dinv), *cl = (double*)(d + o_cl), *Hpp = (double*)(d + o_Hpp), *bp = (double*)(d + o_bp);
+    double *Hs = (double*)(d + o_Hs), *bs = (double*)(d + o_bs), *xp = (double*)(d + o_xp), *res = (double*)(d + o_res);
+    int* fail = (int*)(d + o_fail);
+    double* r_chi = res;                 // eb
+    double* r_diag = res + eb;           // lb
+    double* r_scale = res + eb + lb;     // lb
+    double* r_result = res + eb + 2 * lb;  // 2
+    double* h = S.h_res;
+    int cur = 0;
+
+    auto sum = [](const double* p, int cnt) { double s = 0; for (int i = 0; i < cnt; ++i) s += p[i]; return s; };
+
+    // one round of SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg + terminate_action
+    auto optimize = [&](int iterations, int round) -> int {
+        uint8_t aux = 0;
+        volatile uint8_t* flag = force_stop ? force_stop : &aux;
+        *flag = 0;  // terminate_action at iteration -1 resets the stop flag (terminate_action.cc:46-51)
+        double lambda = 0, ni = 2, last_chi = 0, chi_now = 0;
+        int it = 0;
+        bool ok = true;
+        for (; it < iterations && !*flag && ok; ++it) {
+            // computeActiveErrors + buildSystem at the current state
+            if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], Hpl, pl, r_chi, 1);
+            points_kernel<<<lb, 128, 0, st>>>(v, pl, Hll, bl, r_diag);
+            if (Kf) poses_kernel<<<Kf, kPoseThreads, 0, st>>>(v, Rts[cur], ptss[cur], Hpp, bp);
+            launches += 3;
+            const bool need_diag = (it == 0);
+            B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * (eb + (need_diag ? lb : 0)), cudaMemcpyDeviceToHost, st));
+            std::vector<double> hpp_diag;
+            if (need_diag && Kf) {
+                hpp_diag.resize(36 * (size_t)Kf);
+                B200_CUDA(cudaMemcpyAsync(h + eb + 2 * lb + 2, Hpp, 0, cudaMemcpyDeviceToHost, st));
+            }
+            B200_CUDA(cudaStreamSynchronize(st));
+            double current_chi = sum(h, eb);
+            if (it == 0) {  // computeLambdaInit: tau * max |H_jj| over all free vertices, tau = 1e-5
+                double mx = 0;
+                for (int i = 0; i < lb; ++i) mx = std::max(mx, h[eb + i]);
+                if (Kf) {
+                    hpp_diag.resize(36 * (size_t)Kf);
+                    B200_CUDA(cudaMemcpy(hpp_diag.data(), Hpp, sizeof(double) * 36 * Kf, cudaMemcpyDeviceToHost));
+                    for (int p = 0; p < Kf; ++p)
+                        for (int a = 0; a < 6; ++a) mx = std::max(mx, std::fabs(hpp_diag[36 * (size_t)p + a * 7]));
+                }
+                lambda = 1e-5 * mx;
+                ni = 2;
+                if (round == 0 && stats) stats->lambda_init = lambda;
+            }
+            double rho = 0;
+            int qmax = 0;
+            do {
+                const int nxt = cur ^ 1;
+                B200_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), st));
+                schur_prep_kernel<<<lb, 128, 0, st>>>(v, lambda, Hll, bl, Hpl, Dinv, cl, Tm, fail);
+                if (n_blocks) schur_blocks_kernel<<<ceil_div(n_blocks, 4), 128, 0, st>>>(v, lambda, (const SchurBlock*)(d + o_blocks), n_blocks,
+                                                                                         (const int2*)(d + o_pairs), Hpp, bp, Hpl, Tm, cl, Hs, bs, n);
+                chol_solve_kernel<<<1, kCholThreads, 0, st>>>(n, Hs, bs, lambda, bp, xp, K, (const int*)(d + o_posecol), qs[cur], ts[cur], qs[nxt],
+                                                              ts[nxt], Rts[nxt], r_result, fail);
+                backsub_kernel<<<lb, 128, 0, st>>>(v, lambda, Dinv, bl, Hpl, xp, ptss[cur], ptss[nxt], r_scale, fail);
+                if (E) {
+                    carry_chi_kernel<<<eb, 128, 0, st>>>(v, chis[cur], chis[nxt]);
+                    edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[nxt], ptss[nxt], chis[nxt], Hpl, pl, r_chi, 0);
+                }
+                launches += 6;
+                B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * res_n, cudaMemcpyDeviceToHost, st));
+                B200_CUDA(cudaStreamSynchronize(st));
+                const bool ok2 = h[eb + 2 * lb] != 0.0;
+                double temp_chi = ok2 ? sum(h, eb) : 1.7976931348623157e308;
+                rho = current_chi - temp_chi;
+                double scale = ok2 ? h[eb + 2 * lb + 1] + sum(h + eb + lb, lb) : 0.0;  // computeScale
+                scale += 1e-3;
+                rho /= scale;
+                if (rho > 0 && std::isfinite(temp_chi) && ok2) {
+                    double alpha = 1. - std::pow((2 * rho - 1), 3);
+                    alpha = std::min(alpha, 2. / 3.);
+                    lambda *= std::max(1. / 3., alpha);
+                    ni = 2;
+                    current_chi = temp_chi;
+                    cur = nxt;  // discardTop: keep the trial state
+                } else {
+                    lambda *= ni;
+                    ni *= 2;  // pop: the current state is untouched
+                    if (!std::isfinite(lambda)) break;
+                }
+                qmax++;
+            } while (rho < 0 && qmax < 10 && !*flag);
+            if (qmax == 10 || rho == 0 || !std::isfinite(lambda)) ok = false;  // SolverResult::Terminate
+            // postIteration: terminate_action (terminate_action.cc:52-73)
+            chi_now = current_chi;
+            if (it == 0) {
+                last_chi = chi_now;
+            } else {
+                const double gain = (last_chi - chi_now) / chi_now;
+                last_chi = chi_now;
+                if (gain >= 0 && gain < 1e-3) *flag = 1;
+            }
+            if (stats) {
+                stats->chi2[round] = chi_now;
+                stats->lambda_final[round] = lambda;
+            }
+        }
+        // chi2 of every active edge at the final state (the terminate action's computeActiveErrors)
+        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], Hpl, pl, r_chi, 0);
+        launches += 1;
+        if (it == 0 && stats) {
+            B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * eb, cudaMemcpyDeviceToHost, st));
+            B200_CUDA(cudaStreamSynchronize(st));
+            stats->chi2[round] = sum(h, eb);
+        }
+        B200_CUDA(cudaGetLastError());
+        return it;
+    };
+
+    // 5. first optimisation (local_bundle_adjuster_g2o.cc:312-313)
+    const int n1 = optimize(iters1, 0);
+    if (n1 < 0) return n1;
+    if (stats) stats->iterations[0] = n1;
+    // 6. outliers + second optimisation (:317-348)
+    bool run_robust = true;
+    if (force_stop && *force_stop) run_robust = false;
+    if (run_robust) {
+        if (E) outlier_kernel<<<eb, 128, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], 0, nullptr);
+        launches += 1;
+        const int n2 = optimize(iters2, 1);
+        if (n2 < 0) return n2;
+        if (stats) stats->iterations[1] = n2;
+    }
+    // 7. outlier observations (:354-375)
+    if (E) outlier_kernel<<<eb, 128, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], 1, d + o_out);
+    launches += 1;
+    B200_CUDA(cudaEventRecord(S.ev1, st));
+    // results
+    std::vector<unsigned char> out_sorted(std::max(E, 1));
+    std::vector<double> qf(4 * (size_t)std::max(K, 1)), tf(3 * (size_t)std::max(K, 1));
+    if (E) B200_CUDA(cudaMemcpyAsync(out_sorted.data(), d + o_out, E, cudaMemcpyDeviceToHost, st));
+    if (K) {
+        B200_CUDA(cudaMemcpyAsync(qf.data(), qs[cur], sizeof(double) * 4 * K, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaMemcpyAsync(tf.data(), ts[cur], sizeof(double) * 3 * K, cudaMemcpyDeviceToHost, st));
+    }
+    if (L) B200_CUDA(cudaMemcpyAsync(points_out, ptss[cur], sizeof(double) * 3 * (size_t)L, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    B200_CUDA(cudaEventElapsedTime(&S.last_ms, S.ev0, S.ev1));
+    S.last_launches = launches;
+    int n_out = 0;
+    for (int s = 0; s < E; ++s) {
+        if (outlier_out) outlier_out[order[s]] = out_sorted[s];
+        n_out += out_sorted[s];
+    }
+    if (stats) stats->n_outliers = n_out;
+    for (int k = 0; k < K; ++k) {  // util::converter::to_eigen_mat (util/converter.cc:23-25)
+        double* M = pose_out + 16 * (size_t)k;
+        if (P->pose_fixed[k]) {
+            std::memcpy(M, P->pose_cw + 16 * (size_t)k, sizeof(double) * 16);
+            continue;
+        }
+        double R[9];
+        quat_to_rot(&qf[4 * k], R);
+        M[0] = R[0]; M[1] = R[1]; M[2] = R[2]; M[3] = tf[3 * k];
+        M[4] = R[3]; M[5] = R[4]; M[6] = R[5]; M[7] = tf[3 * k + 1];
+        M[8] = R[6]; M[9] = R[7]; M[10] = R[8]; M[11] = tf[3 * k + 2];
+        M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
+    }
+    return B200_OK;
+}
+
+}  // namespace lba
+}  // namespace b200
+
+struct b200_lba_s {
+    b200::lba::Solver s;
+};
+
+extern "C" {
+
+int b200_lba_create(int device, b200_lba_t* out) {
+    if (!out) return B200_ERR_INVALID;
+    int rc = b200::require_device(device);
+    if (rc) return rc;
+    b200_lba_s* h = new (std::nothrow) b200_lba_s();
+    if (!h) return B200_ERR_INVALID;
+    h->s.device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&h->s.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->s.ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&h->s.ev1);
+    if (e != cudaSuccess) {
+        delete h;
+        return b200::cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
+    }
+    *out = h;
+    return B200_OK;
+}
+
+int b200_lba_destroy(b200_lba_t h) {
+    if (!h) return B200_OK;
+    cudaSetDevice(h->s.device);
+    if (h->s.stream) cudaStreamSynchronize(h->s.stream);
+    cudaFree(h->s.d_arena);
+    if (h->s.h_stage) cudaFreeHost(h->s.h_stage);
+    if (h->s.h_res) cudaFreeHost(h->s.h_res);
+    if (h->s.ev0) cudaEventDestroy(h->s.ev0);
+    if (h->s.ev1) cudaEventDestroy(h->s.ev1);
+    if (h->s.stream) cudaStreamDestroy(h->s.stream);
+    delete h;
+    return B200_OK;
+}
+
+int b200_lba_solve(b200_lba_t h, const b200_lba_problem_t* P, int iters1, int iters2, volatile uint8_t* force_stop, double* pose_cw_out,
+                   double* points_out, uint8_t* outlier_out, b200_lba_stats_t* stats) {
+    if (!h || !P || !pose_cw_out || !points_out) {
+        b200::set_error("b200_lba_solve: null argument");
+        return B200_ERR_INVALID;
+    }
+    if (P->n_poses < 0 || P->n_points < 0 || P->n_edges < 0 || P->n_cams < 0 || iters1 < 0 || iters2 < 0
+        || (P->n_poses > 0 && (!P->pose_cw || !P->pose_fixed)) || (P->n_points > 0 && !P->points)
+        || (P->n_edges > 0 && (!P->e_pose || !P->e_point || !P->e_cam || !P->e_obs || !P->e_inv_sigma_sq || !P->e_delta || !P->cams))) {
+        b200::set_error("b200_lba_solve: inconsistent problem description");
+        return B200_ERR_INVALID;
+    }
+    if (6 * (size_t)P->n_poses > 1024) {
+        b200::set_error("b200_lba_solve: more than 170 keyframes in one local window is not supported");
+        return B200_ERR_INVALID;
+    }
+    if (force_stop && *force_stop) return B200_ERR_ABORTED;  // local_bundle_adjuster_g2o.cc:308-310
+    B200_CUDA(cudaSetDevice(h->s.device));
+    return b200::lba::solve(h->s, P, iters1, iters2, force_stop, pose_cw_out, points_out, outlier_out, stats);
+}
+
+int b200_lba_last_profile(b200_lba_t h, float* gpu_ms, int* launches) {
+    if (!h) return B200_ERR_INVALID;
+    if (gpu_ms) *gpu_ms = h->s.last_ms;
+    if (launches) *launches = h->s.last_launches;
+    return B200_OK;
+}
+
+}  // extern "C"

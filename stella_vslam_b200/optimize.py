@@ -1,0 +1,126 @@
+"""Host-side mirror of optimize::local_bundle_adjuster (src/stella_vslam/optimize/local_bundle_adjuster.h:15-24,
+local_bundle_adjuster_g2o.{h,cc}, local_bundle_adjuster_factory.h:15-33).
+
+The reference's optimize(map_db, curr_keyfrm, force_stop_flag) first flattens the covisibility window into vertices and
+edges (steps 1-4) and writes the result back under the map mutex (step 8); both stay on the host.  This module takes the
+flattened problem (the layout of b200_lba_problem_t) and runs steps 5-7 on the GPU.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import ERR_ABORTED, check, lib, ptr
+
+
+class Camera(C.Structure):
+    _fields_ = [("model", C.c_int32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("fxb", C.c_double), ("cols", C.c_double), ("rows", C.c_double)]
+
+
+class LbaProblem(C.Structure):
+    _fields_ = [("n_poses", C.c_int32), ("n_points", C.c_int32), ("n_edges", C.c_int32), ("n_cams", C.c_int32),
+                ("pose_cw", C.c_void_p), ("pose_fixed", C.c_void_p), ("points", C.c_void_p), ("point_fixed", C.c_void_p),
+                ("e_pose", C.c_void_p), ("e_point", C.c_void_p), ("e_cam", C.c_void_p), ("e_obs", C.c_void_p),
+                ("e_inv_sigma_sq", C.c_void_p), ("e_delta", C.c_void_p), ("e_robust", C.c_void_p), ("e_can_be_outlier", C.c_void_p),
+                ("cams", C.c_void_p)]
+
+
+class LbaStats(C.Structure):
+    _fields_ = [("iterations", C.c_int32 * 2), ("n_outliers", C.c_int32), ("chi2", C.c_double * 2), ("lambda_init", C.c_double),
+                ("lambda_final", C.c_double * 2)]
+
+
+def _bind():
+    L = lib()
+    vp = C.c_void_p
+    L.b200_lba_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.b200_lba_destroy.argtypes = [vp]
+    L.b200_lba_solve.argtypes = [vp, C.POINTER(LbaProblem), C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(LbaStats)]
+    L.b200_lba_last_profile.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    return L
+
+
+def pack_problem(prob):
+    """dict (see synth.make_ba_problem) -> (LbaProblem, keep-alive list)."""
+    keep = []
+
+    def arr(x, dt):
+        if x is None:
+            return None
+        a = np.ascontiguousarray(x, dt)
+        keep.append(a)
+        return a.ctypes.data
+
+    cams = (Camera * len(prob["cams"]))(*[Camera(c["model"], c["fx"], c["fy"], c["cx"], c["cy"], c["fxb"], c["cols"], c["rows"])
+                                          for c in prob["cams"]])
+    keep.append(cams)
+    P = LbaProblem(len(prob["pose_cw"]), len(prob["points"]), len(prob["e_pose"]), len(prob["cams"]), arr(prob["pose_cw"], np.float64),
+                   arr(prob["pose_fixed"], np.uint8), arr(prob["points"], np.float64), arr(prob.get("point_fixed"), np.uint8),
+                   arr(prob["e_pose"], np.int32), arr(prob["e_point"], np.int32), arr(prob["e_cam"], np.uint8),
+                   arr(prob["e_obs"], np.float32), arr(prob["e_inv_sigma_sq"], np.float32), arr(prob["e_delta"], np.float32),
+                   arr(prob.get("e_robust"), np.uint8), arr(prob.get("e_can_be_outlier"), np.uint8), C.cast(cams, C.c_void_p))
+    return P, keep
+
+
+class local_bundle_adjuster:
+    """optimize::local_bundle_adjuster with the "b200" backend (factory key Mapping.backend, local_bundle_adjuster_factory.h:17-32)."""
+
+    def __init__(self, num_first_iter=5, num_second_iter=10, device=0):
+        self.num_first_iter_ = int(num_first_iter)    # local_bundle_adjuster_g2o.h:25-27
+        self.num_second_iter_ = int(num_second_iter)
+        self._L = _bind()
+        self._h = C.c_void_p()
+        check(self._L.b200_lba_create(device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200_lba_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def optimize(self, problem, force_stop_flag=None):
+        """problem: flattened window (dict).  force_stop_flag: optional 1-element uint8 array (read AND written, like the
+        reference's bool*).  Returns None if the flag was already set (local_bundle_adjuster_g2o.cc:308-310), else a dict."""
+        P, keep = pack_problem(problem)
+        K, L, E = P.n_poses, P.n_points, P.n_edges
+        pose_out, pts_out, outl = np.zeros((K, 4, 4)), np.zeros((L, 3)), np.zeros(E, np.uint8)
+        st = LbaStats()
+        rc = self._L.b200_lba_solve(self._h, C.byref(P), self.num_first_iter_, self.num_second_iter_, ptr(force_stop_flag), ptr(pose_out),
+                                    ptr(pts_out), ptr(outl), C.byref(st))
+        if rc == ERR_ABORTED:
+            return None
+        check(rc)
+        ms, launches = C.c_float(), C.c_int()
+        self._L.b200_lba_last_profile(self._h, C.byref(ms), C.byref(launches))
+        return dict(pose_cw=pose_out, points=pts_out, outliers=outl, iterations=list(st.iterations), n_outliers=st.n_outliers,
+                    chi2=list(st.chi2), lambda_init=st.lambda_init, lambda_final=list(st.lambda_final), gpu_ms=ms.value,
+                    launches=launches.value)
+
+
+def create(yaml_node=None, device=0):
+    """local_bundle_adjuster_factory::create (local_bundle_adjuster_factory.h:17-32): Mapping.backend must be "b200" here;
+    "g2o"/"gtsam" are the reference's CPU backends and are not part of this library."""
+    node = yaml_node or {}
+    backend = node.get("backend", "b200")
+    if backend != "b200":
+        raise RuntimeError(f"Invalid backend: {backend}")
+    return local_bundle_adjuster(node.get("num_first_iter", 5), node.get("num_second_iter", 10), device)
+
+
+def _smoke(O):
+    """Used by __graft_entry__.smoke(): small stereo window, CUDA vs oracle."""
+    from . import synth
+    pr = synth.make_ba_problem(10, 3, 400, seed=5, model="stereo")
+    ref = O.lba_solve(pr)
+    ba = local_bundle_adjuster()
+    got = ba.optimize(pr)
+    assert got["iterations"] == ref["iterations"], (got["iterations"], ref["iterations"])
+    assert np.array_equal(got["outliers"], ref["outliers"])
+    scale = np.abs(ref["points"]).max()
+    assert np.abs(got["points"] - ref["points"]).max() <= 1e-5 * scale
+    assert np.abs(got["pose_cw"] - ref["pose_cw"]).max() <= 1e-5 * np.abs(ref["pose_cw"]).max()

@@ -97,3 +97,128 @@ def make_descriptor_pair(n1=2000, n2=2000, seed=7, dup_frac=0.6, max_flips=40):
         a2[t] = np.float32((a1[s] + rng.normal(0, 8)) % 360)
     valid2 = (rng.random(n2) < 0.9).astype(np.uint8)
     return d1, a1, d2, a2, valid2
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# local-BA problems: K keyframes on an arc, L landmarks in the frustum union, E observations
+# ---------------------------------------------------------------------------------------------------------------------
+KITTI = dict(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, fxb=386.1448, cols=1241, rows=376)  # example/kitti/KITTI_stereo_00-02.yaml
+
+
+def _rot_y(a):
+    c, s = np.cos(a), np.sin(a)
+    return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+
+
+def _rodrigues(w):
+    th = np.linalg.norm(w)
+    if th < 1e-12:
+        return np.eye(3)
+    k = w / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+
+def make_ba_problem(n_poses=50, n_fixed=10, n_points=10000, seed=0, model="stereo", outlier_frac=0.05, pixel_sigma=1.0,
+                    min_obs=4, max_obs=8, arc_m=200.0, perturb=True):
+    """Synthetic local-BA problem in the flattened layout of the C ABI.
+
+    model: "mono" | "stereo" (perspective, KITTI intrinsics) | "equirect" (3840x1920).
+    Returns dict(pose_cw (K,4,4), pose_fixed (K,), points (L,3), e_pose, e_point, e_cam, e_obs (E,3) f32,
+                 e_inv_sigma_sq f32, e_delta f32, cams (list of dict), gt_pose_cw, gt_points).
+    """
+    rng = np.random.default_rng(seed)
+    K, L = n_poses, n_points
+    equirect = model == "equirect"
+    cam = dict(model=1 if equirect else 0, fx=KITTI["fx"], fy=KITTI["fy"], cx=KITTI["cx"], cy=KITTI["cy"], fxb=KITTI["fxb"],
+               cols=3840.0 if equirect else float(KITTI["cols"]), rows=1920.0 if equirect else float(KITTI["rows"]))
+    # keyframes on a gentle arc, looking along the direction of travel
+    s = np.linspace(0, arc_m, K)
+    radius = 4 * arc_m
+    ang = s / radius
+    centers = np.stack([radius * np.sin(ang), 0.3 * np.sin(s / 15.0), radius * (1 - np.cos(ang))], 1)
+    gt_pose = np.zeros((K, 4, 4))
+    for k in range(K):
+        Rwc = _rot_y(ang[k] + 0.02 * rng.standard_normal()) @ _rodrigues(0.01 * rng.standard_normal(3))
+        Rcw = Rwc.T
+        gt_pose[k, :3, :3] = Rcw
+        gt_pose[k, :3, 3] = -Rcw @ centers[k]
+        gt_pose[k, 3, 3] = 1
+    sf = np.float32(1.0)
+    inv_sigma = [np.float32(1.0)]
+    for _ in range(1, 8):
+        sf = np.float32(1.2) * sf
+        inv_sigma.append(np.float32(1.0) / (sf * sf))
+    inv_sigma = np.array(inv_sigma, np.float32)
+    sigma_lvl = 1.0 / np.sqrt(inv_sigma.astype(np.float64))
+
+    def project(Tcw, pw):
+        pc = pw @ Tcw[:3, :3].T + Tcw[:3, 3]
+        if equirect:
+            th = np.arctan2(pc[:, 0], pc[:, 2])
+            ph = -np.arcsin(pc[:, 1] / np.linalg.norm(pc, axis=1))
+            uv = np.stack([cam["cols"] * (0.5 + th / (2 * np.pi)), cam["rows"] * (0.5 - ph / np.pi)], 1)
+            vis = np.linalg.norm(pc, axis=1) > 2.0
+            return uv, pc, vis
+        z = pc[:, 2]
+        uv = np.stack([cam["fx"] * pc[:, 0] / z + cam["cx"], cam["fy"] * pc[:, 1] / z + cam["cy"]], 1)
+        vis = (z > 3.0) & (z < 80.0) & (uv[:, 0] > 0) & (uv[:, 0] < cam["cols"]) & (uv[:, 1] > 0) & (uv[:, 1] < cam["rows"])
+        return uv, pc, vis
+
+    # landmarks: sampled in front of random keyframes at 5..60 m
+    pts = np.zeros((L, 3))
+    owner = rng.integers(0, K, L)
+    depth = rng.uniform(5, 60, L)
+    u = rng.uniform(0.05, 0.95, L) * (KITTI["cols"] if not equirect else 1241)
+    v = rng.uniform(0.05, 0.95, L) * (KITTI["rows"] if not equirect else 376)
+    for l in range(L):
+        Tcw = gt_pose[owner[l]]
+        pc = np.array([(u[l] - KITTI["cx"]) / KITTI["fx"] * depth[l], (v[l] - KITTI["cy"]) / KITTI["fy"] * depth[l], depth[l]])
+        pts[l] = Tcw[:3, :3].T @ (pc - Tcw[:3, 3])
+    e_pose, e_point, e_obs, e_isq = [], [], [], []
+    order = np.argsort(np.abs(np.arange(K)[None, :] - owner[:, None]), axis=1)  # nearest keyframes first
+    proj = [project(gt_pose[k], pts) for k in range(K)]
+    for l in range(L):
+        want = int(rng.integers(min_obs, max_obs + 1))
+        got = 0
+        for k in order[l]:
+            uv, pc, vis = proj[k]
+            if not vis[l]:
+                continue
+            lvl = int(rng.integers(0, 8))
+            noise = pixel_sigma * sigma_lvl[lvl] * rng.standard_normal(3)
+            x, y = uv[l, 0] + noise[0], uv[l, 1] + noise[1]
+            xr = -1.0
+            if model == "stereo" and rng.random() < 0.85:
+                xr = uv[l, 0] - cam["fxb"] / pc[l, 2] + noise[2]
+                if xr < 0:
+                    xr = -1.0
+            if rng.random() < outlier_frac:
+                x += rng.choice([-1, 1]) * rng.uniform(15, 30)
+                y += rng.choice([-1, 1]) * rng.uniform(15, 30)
+            e_pose.append(k)
+            e_point.append(l)
+            e_obs.append((x, y, xr))
+            e_isq.append(inv_sigma[lvl])
+            got += 1
+            if got >= want:
+                break
+    E = len(e_pose)
+    chi = np.float32(np.sqrt(np.float32(5.99146))) if model != "stereo" else np.float32(np.sqrt(np.float32(7.81473)))
+    pose_fixed = np.zeros(K, np.uint8)
+    pose_fixed[:n_fixed] = 1   # the oldest keyframes play the "fixed" role (observers outside the local window)
+    pose0, pts0 = gt_pose.copy(), pts.copy()
+    if perturb:
+        for k in range(K):
+            if pose_fixed[k]:
+                continue
+            dR = _rodrigues(np.deg2rad(0.5) * rng.standard_normal(3) / np.sqrt(3))
+            Rn = dR @ gt_pose[k, :3, :3]                     # 0.5 deg about the camera centre, 5 cm of centre noise
+            cn = centers[k] + 0.05 * rng.standard_normal(3) / np.sqrt(3)
+            pose0[k, :3, :3] = Rn
+            pose0[k, :3, 3] = -Rn @ cn
+        pts0 = pts + 0.01 * depth[:, None] * rng.standard_normal((L, 3))
+    return dict(pose_cw=pose0, pose_fixed=pose_fixed, points=pts0, point_fixed=None, e_pose=np.array(e_pose, np.int32),
+                e_point=np.array(e_point, np.int32), e_cam=np.zeros(E, np.uint8), e_obs=np.array(e_obs, np.float32).reshape(E, 3),
+                e_inv_sigma_sq=np.array(e_isq, np.float32), e_delta=np.full(E, chi, np.float32), e_robust=None,
+                e_can_be_outlier=None, cams=[cam], gt_pose_cw=gt_pose, gt_points=pts)

@@ -1,0 +1,111 @@
+"""GPU parity tests for the local bundle adjuster: CUDA (through the C ABI) vs the CPU oracle.
+Tolerance: 1e-5 relative on poses and landmarks (BASELINE.json north_star); iteration counts, outlier flags and the
+abort protocol must be identical."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from oracle import pyoracle as O
+    from stella_vslam_b200 import optimize, synth
+    return O, optimize, synth
+
+
+def check_same(got, ref, pr):
+    assert got["iterations"] == ref["iterations"], (got["iterations"], ref["iterations"])
+    assert np.array_equal(got["outliers"], ref["outliers"])
+    assert got["n_outliers"] == ref["n_outliers"]
+    ps = max(1.0, np.abs(ref["points"]).max())
+    assert np.abs(got["points"] - ref["points"]).max() <= REL * ps
+    assert np.abs(got["pose_cw"] - ref["pose_cw"]).max() <= REL * max(1.0, np.abs(ref["pose_cw"]).max())
+    # per-element relative check where the magnitude allows it
+    big = np.abs(ref["points"]) > 1e-2
+    assert (np.abs(got["points"] - ref["points"])[big] / np.abs(ref["points"])[big]).max() <= 10 * REL
+    for a, b in zip(got["chi2"], ref["chi2"]):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b))
+    assert abs(got["lambda_init"] - ref["lambda_init"]) <= 1e-9 * ref["lambda_init"]
+    fixed = pr["pose_fixed"].astype(bool)
+    assert np.array_equal(got["pose_cw"][fixed], pr["pose_cw"][fixed])
+
+
+@pytest.mark.parametrize("model,K,F,L,seed", [("mono", 12, 3, 600, 1), ("stereo", 12, 3, 600, 2), ("equirect", 10, 2, 400, 3),
+                                              ("stereo", 4, 1, 60, 4), ("mono", 30, 6, 3000, 5)])
+def test_vs_oracle(mods, model, K, F, L, seed):
+    O, optimize, synth = mods
+    pr = synth.make_ba_problem(K, F, L, seed=seed, model=model)
+    ba = optimize.local_bundle_adjuster()
+    check_same(ba.optimize(pr), O.lba_solve(pr), pr)
+    ba.close()
+
+
+def test_full_size_kitti_window(mods):
+    # BASELINE config 4: 50 keyframes (10 fixed) / 10 000 landmarks
+    O, optimize, synth = mods
+    pr = synth.make_ba_problem(50, 10, 10000, seed=0, model="stereo")
+    ba = optimize.local_bundle_adjuster()
+    got = ba.optimize(pr)
+    check_same(got, O.lba_solve(pr), pr)
+    assert got["launches"] > 20 and got["gpu_ms"] > 0
+    # size-independent property: re-optimising the optimum changes (almost) nothing and removes no further inliers
+    pr2 = dict(pr)
+    pr2["pose_cw"], pr2["points"] = got["pose_cw"], got["points"]
+    keep = got["outliers"] == 0
+    for k in ("e_pose", "e_point", "e_cam", "e_obs", "e_inv_sigma_sq", "e_delta"):
+        pr2[k] = pr[k][keep]
+    again = ba.optimize(pr2)
+    assert again["chi2"][1] <= got["chi2"][1] * (1 + 1e-6)
+    assert again["n_outliers"] <= 0.01 * keep.sum()
+
+
+def test_force_stop_protocol(mods):
+    O, optimize, synth = mods
+    pr = synth.make_ba_problem(8, 3, 200, seed=2, model="mono")
+    ba = optimize.local_bundle_adjuster()
+    flag = np.array([1], np.uint8)
+    assert ba.optimize(pr, flag) is None                       # local_bundle_adjuster_g2o.cc:308-310
+    ba2 = optimize.local_bundle_adjuster(50, 10)
+    flag = np.array([0], np.uint8)
+    got = ba2.optimize(pr, flag)
+    rflag = np.array([0], np.uint8)
+    ref = O.lba_solve(pr, iters1=50, iters2=10, force_stop=rflag)
+    assert flag[0] == rflag[0] == 1 and got["iterations"] == ref["iterations"] and got["iterations"][1] == 0
+    check_same(got, ref, pr)
+
+
+def test_fixed_points_markers_and_plain_edges(mods):
+    O, optimize, synth = mods
+    pr = synth.make_ba_problem(6, 2, 80, seed=9, model="mono")
+    pf = np.zeros(80, np.uint8)
+    pf[:10] = 1
+    pr["point_fixed"] = pf
+    marker = np.isin(pr["e_point"], np.arange(10))
+    pr["e_can_be_outlier"] = (~marker).astype(np.uint8)
+    pr["e_robust"] = (~marker).astype(np.uint8)               # use_huber_loss = false for marker edges (:297-299)
+    ba = optimize.local_bundle_adjuster()
+    got = ba.optimize(pr)
+    check_same(got, O.lba_solve(pr), pr)
+    assert np.array_equal(got["points"][:10], pr["points"][:10])
+
+
+def test_degenerate_inputs(mods):
+    O, optimize, synth = mods
+    ba = optimize.local_bundle_adjuster()
+    pr = synth.make_ba_problem(3, 3, 20, seed=4, model="mono")   # every keyframe fixed: landmarks only
+    check_same(ba.optimize(pr), O.lba_solve(pr), pr)
+    pr = synth.make_ba_problem(4, 1, 10, seed=5, model="stereo")
+    for k in ("e_pose", "e_point", "e_cam", "e_obs", "e_inv_sigma_sq", "e_delta"):
+        pr[k] = pr[k][:0]
+    got = ba.optimize(pr)                                           # no edges at all
+    assert got["n_outliers"] == 0 and np.array_equal(got["points"], pr["points"])
+
+
+def test_factory():
+    from stella_vslam_b200 import optimize
+    with pytest.raises(RuntimeError):
+        optimize.create({"backend": "gtsam"})                       # local_bundle_adjuster_factory.h:26,30
+    assert optimize.create({"backend": "b200", "num_first_iter": 3}).num_first_iter_ == 3
