@@ -16,6 +16,7 @@
 // pair list built once per solve.  Everything is deterministic (fixed reduction orders, no floating-point atomics).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -227,14 +228,14 @@ __global__ void __launch_bounds__(kEdgeThreads) edges_kernel(View v, const doubl
 #pragma unroll
                     for (int b = 0; b < 3; ++b) {
                         const double s = ww * (Jj[a] * Ji[b] + Jj[6 + a] * Ji[3 + b] + Jj[12 + a] * Ji[6 + b]);
-                        Hpl[(size_t)(a * 3 + b) * v.E + e] = (lfree && pfree) ? s : 0.0;
+                        Hpl[(size_t)e * 18 + a * 3 + b] = (lfree && pfree) ? s : 0.0;
                     }
             }
         } else if (linearize) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) pl[(size_t)i * v.E + e] = 0.0;
 #pragma unroll
-            for (int i = 0; i < 18; ++i) Hpl[(size_t)i * v.E + e] = 0.0;
+            for (int i = 0; i < 18; ++i) Hpl[(size_t)e * 18 + i] = 0.0;
         }
     }
     const double s = block_sum(cost, sh);
@@ -272,16 +273,18 @@ __global__ void __launch_bounds__(128) points_kernel(View v, const double* __res
     if (threadIdx.x == 0) diag_partials[blockIdx.x] = sh[0];
 }
 
-// K3: one CTA per free keyframe -- Hpp (6x6) and bp (6) over all of its active edges
-constexpr int kPoseThreads = 128;
-__global__ void __launch_bounds__(kPoseThreads) poses_kernel(View v, const double* __restrict__ Rt, const double* __restrict__ pts,
-                                                             double* __restrict__ Hpp, double* __restrict__ bp) {
-    __shared__ double sh[kPoseThreads];
-    const int pc_ = blockIdx.x;
+// K3: keyframe-side blocks.  The edges of every free keyframe are cut into chunks of kPoseChunk; one warp reduces one
+//     chunk to 21 unique Hpp entries + 6 bp entries, pose_finish_kernel adds the chunk partials in index order.
+constexpr int kPoseChunk = 64;
+__global__ void __launch_bounds__(128) pose_chunks_kernel(View v, const int2* __restrict__ chunks, int n_chunks, const double* __restrict__ Rt,
+                                                          const double* __restrict__ pts, double* __restrict__ partials) {
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid >= n_chunks) return;
+    const int2 ch = chunks[wid];
     double acc[27];
 #pragma unroll
     for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-    for (int k = v.pose_start[pc_] + threadIdx.x; k < v.pose_start[pc_ + 1]; k += blockDim.x) {
+    for (int k = ch.x + lane; k < ch.y; k += 32) {
         const int e = v.pose_edges[k];
         if (v.level[e]) continue;
         const EdgeS ed = v.edges[e];
@@ -301,34 +304,43 @@ __global__ void __launch_bounds__(kPoseThreads) poses_kernel(View v, const doubl
 #pragma unroll
         for (int a = 0; a < 6; ++a) acc[21 + a] += -ww * (Jj[a] * err[0] + Jj[6 + a] * err[1] + Jj[12 + a] * err[2]);
     }
-    double red[27];
 #pragma unroll
-    for (int i = 0; i < 27; ++i) red[i] = block_sum(acc[i], sh);
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int a = 0; a < 6; ++a)
-            for (int b = a; b < 6; ++b) {
-                Hpp[(size_t)pc_ * 36 + a * 6 + b] = red[t];
-                Hpp[(size_t)pc_ * 36 + b * 6 + a] = red[t];
-                ++t;
-            }
-        for (int a = 0; a < 6; ++a) bp[(size_t)pc_ * 6 + a] = red[21 + a];
+    for (int i = 0; i < 27; ++i)
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) acc[i] += __shfl_down_sync(0xFFFFFFFFu, acc[i], s);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < 27; ++i) partials[(size_t)wid * 27 + i] = acc[i];
+}
+
+__global__ void __launch_bounds__(128) pose_finish_kernel(int Kf, const int* __restrict__ chunk_start, const double* __restrict__ partials,
+                                                          double* __restrict__ Hpp, double* __restrict__ bp) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = idx / 27, t = idx - p * 27;
+    if (p >= Kf) return;
+    double r = 0.0;
+    for (int c = chunk_start[p]; c < chunk_start[p + 1]; ++c) r += partials[(size_t)c * 27 + t];
+    if (t < 21) {
+        int a = 0, rem = t;
+        while (rem >= 6 - a) {
+            rem -= 6 - a;
+            ++a;
+        }
+        const int b = a + rem;
+        Hpp[(size_t)p * 36 + a * 6 + b] = r;
+        Hpp[(size_t)p * 36 + b * 6 + a] = r;
+    } else {
+        bp[(size_t)p * 6 + (t - 21)] = r;
     }
 }
 
-// K4: per landmark -- Dinv = (Hll + lambda I)^-1, cl = Dinv bl, T(e) = Hpl(e) Dinv for its edges
-__global__ void __launch_bounds__(128) schur_prep_kernel(View v, double lambda, const double* __restrict__ Hll, const double* __restrict__ bl,
-                                                         const double* __restrict__ Hpl, double* __restrict__ Dinv, double* __restrict__ cl,
-                                                         double* __restrict__ Tm, int* __restrict__ fail) {
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    if (l >= v.L) return;
-    const int a0 = v.pt_start[l], b0 = v.pt_start[l + 1];
-    if (a0 >= b0) return;
-    const int lc = v.edges[a0].lcol;
-    if (lc < 0) return;
-    const double A0 = Hll[lc] + lambda, A1 = Hll[(size_t)v.Lf + lc], A2 = Hll[(size_t)2 * v.Lf + lc];
-    const double A4 = Hll[(size_t)3 * v.Lf + lc] + lambda, A5 = Hll[(size_t)4 * v.Lf + lc], A8 = Hll[(size_t)5 * v.Lf + lc] + lambda;
-    // symmetric 3x3 inverse by cofactors (Eigen's fixed-size inverse)
+// K4: per landmark -- Dinv = (Hll + lambda I)^-1 (symmetric 3x3, cofactor inverse like Eigen's fixed-size path)
+__global__ void __launch_bounds__(128) dinv_kernel(int Lf, double lambda, const double* __restrict__ Hll, double* __restrict__ Dinv,
+                                                   int* __restrict__ fail) {
+    const int lc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (lc >= Lf) return;
+    const double A0 = Hll[lc] + lambda, A1 = Hll[(size_t)Lf + lc], A2 = Hll[(size_t)2 * Lf + lc];
+    const double A4 = Hll[(size_t)3 * Lf + lc] + lambda, A5 = Hll[(size_t)4 * Lf + lc], A8 = Hll[(size_t)5 * Lf + lc] + lambda;
     const double c0 = A4 * A8 - A5 * A5, c1 = A5 * A2 - A1 * A8, c2 = A1 * A5 - A4 * A2;
     const double det = A0 * c0 + A1 * c1 + A2 * c2;
     if (det == 0.0 || !isfinite(det)) {
@@ -336,80 +348,97 @@ __global__ void __launch_bounds__(128) schur_prep_kernel(View v, double lambda, 
         return;
     }
     const double id = 1.0 / det;
-    const double D0 = c0 * id, D1 = c1 * id, D2 = c2 * id;
-    const double D4 = (A0 * A8 - A2 * A2) * id, D5 = (A1 * A2 - A0 * A5) * id, D8 = (A0 * A4 - A1 * A1) * id;
-    Dinv[lc] = D0; Dinv[(size_t)v.Lf + lc] = D1; Dinv[(size_t)2 * v.Lf + lc] = D2;
-    Dinv[(size_t)3 * v.Lf + lc] = D4; Dinv[(size_t)4 * v.Lf + lc] = D5; Dinv[(size_t)5 * v.Lf + lc] = D8;
-    const double b0_ = bl[lc], b1_ = bl[(size_t)v.Lf + lc], b2_ = bl[(size_t)2 * v.Lf + lc];
-    cl[lc] = D0 * b0_ + D1 * b1_ + D2 * b2_;
-    cl[(size_t)v.Lf + lc] = D1 * b0_ + D4 * b1_ + D5 * b2_;
-    cl[(size_t)2 * v.Lf + lc] = D2 * b0_ + D5 * b1_ + D8 * b2_;
-    for (int e = a0; e < b0; ++e) {
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-            const double h0 = Hpl[(size_t)(r * 3) * v.E + e], h1 = Hpl[(size_t)(r * 3 + 1) * v.E + e], h2 = Hpl[(size_t)(r * 3 + 2) * v.E + e];
-            Tm[(size_t)(r * 3) * v.E + e] = h0 * D0 + h1 * D1 + h2 * D2;
-            Tm[(size_t)(r * 3 + 1) * v.E + e] = h0 * D1 + h1 * D4 + h2 * D5;
-            Tm[(size_t)(r * 3 + 2) * v.E + e] = h0 * D2 + h1 * D5 + h2 * D8;
-        }
-    }
+    Dinv[lc] = c0 * id;
+    Dinv[(size_t)Lf + lc] = c1 * id;
+    Dinv[(size_t)2 * Lf + lc] = c2 * id;
+    Dinv[(size_t)3 * Lf + lc] = (A0 * A8 - A2 * A2) * id;
+    Dinv[(size_t)4 * Lf + lc] = (A1 * A2 - A0 * A5) * id;
+    Dinv[(size_t)5 * Lf + lc] = (A0 * A4 - A1 * A1) * id;
 }
 
-// K5: one warp per upper block (i <= j) of the reduced pose system:
-//     Hs(i,j) = [i==j] (Hpp(i) + lambda I) - sum_pairs T(a) Hpl(c)^T ;  bs(i) = bp(i) - sum_{a of i} Hpl(a) cl(point(a))
+// K5: Schur complement of the landmarks.  The (edge a, edge c) pairs that share a landmark are grouped by the upper
+//     block (i <= j) of the reduced system they fall into and cut into chunks of kSchurChunk pairs; one warp reduces one
+//     chunk:  partial = sum T(a) Hpl(c)^T,  T(a) = Hpl(a) Dinv(l)   (+ for diagonal blocks  sum T(a) bl(l)).
+//     schur_finish_kernel then adds the chunk partials of every block in index order (deterministic) into
+//     M = [Hpp + lambda I - sum ; (bp - sum)^T].
+constexpr int kSchurChunk = 64;
 struct SchurBlock {
-    int i, j, start, end;  // pairs [start, end)
+    int i, j, chunk_start, chunk_end;
 };
-__global__ void __launch_bounds__(128) schur_blocks_kernel(View v, double lambda, const SchurBlock* __restrict__ blocks, int n_blocks,
-                                                           const int2* __restrict__ pairs, const double* __restrict__ Hpp,
-                                                           const double* __restrict__ bp, const double* __restrict__ Hpl,
-                                                           const double* __restrict__ Tm, const double* __restrict__ cl,
-                                                           double* __restrict__ Hs, double* __restrict__ bs, int n) {
+struct SchurChunk {
+    int start, end, diag, pad;
+};
+__device__ __forceinline__ void load18(const double* __restrict__ p, double* out) {
+    const double2* q = reinterpret_cast<const double2*>(p);  // 144-byte records, 16-byte aligned
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const double2 v = q[i];
+        out[2 * i] = v.x;
+        out[2 * i + 1] = v.y;
+    }
+}
+__global__ void __launch_bounds__(128) schur_chunks_kernel(View v, const SchurChunk* __restrict__ chunks, int n_chunks,
+                                                           const int2* __restrict__ pairs, const double* __restrict__ Hpl,
+                                                           const double* __restrict__ Dinv, const double* __restrict__ bl,
+                                                           double* __restrict__ partials) {
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (wid >= n_blocks) return;
-    const SchurBlock sb = blocks[wid];
-    double acc[36];
+    if (wid >= n_chunks) return;
+    const SchurChunk ch = chunks[wid];
+    double acc[42];
 #pragma unroll
-    for (int i = 0; i < 36; ++i) acc[i] = 0.0;
-    double accb[6] = {0, 0, 0, 0, 0, 0};
-    for (int k = sb.start + lane; k < sb.end; k += 32) {
+    for (int i = 0; i < 42; ++i) acc[i] = 0.0;
+    for (int k = ch.start + lane; k < ch.end; k += 32) {
         const int2 pr = pairs[k];
-        double t[18], h[18];
+        double ha[18], hc[18], t[18];
+        load18(Hpl + (size_t)pr.x * 18, ha);
+        load18(Hpl + (size_t)pr.y * 18, hc);
+        const int lc = v.edges[pr.x].lcol;
+        const double D0 = Dinv[lc], D1 = Dinv[(size_t)v.Lf + lc], D2 = Dinv[(size_t)2 * v.Lf + lc];
+        const double D4 = Dinv[(size_t)3 * v.Lf + lc], D5 = Dinv[(size_t)4 * v.Lf + lc], D8 = Dinv[(size_t)5 * v.Lf + lc];
 #pragma unroll
-        for (int i = 0; i < 18; ++i) {
-            t[i] = Tm[(size_t)i * v.E + pr.x];
-            h[i] = Hpl[(size_t)i * v.E + pr.y];
+        for (int r = 0; r < 6; ++r) {
+            t[r * 3] = ha[r * 3] * D0 + ha[r * 3 + 1] * D1 + ha[r * 3 + 2] * D2;
+            t[r * 3 + 1] = ha[r * 3] * D1 + ha[r * 3 + 1] * D4 + ha[r * 3 + 2] * D5;
+            t[r * 3 + 2] = ha[r * 3] * D2 + ha[r * 3 + 1] * D5 + ha[r * 3 + 2] * D8;
         }
 #pragma unroll
         for (int r = 0; r < 6; ++r)
 #pragma unroll
-            for (int c = 0; c < 6; ++c) acc[r * 6 + c] += t[r * 3] * h[c * 3] + t[r * 3 + 1] * h[c * 3 + 1] + t[r * 3 + 2] * h[c * 3 + 2];
-        if (sb.i == sb.j) {  // pr.x == pr.y: the edge of keyframe i to this landmark
-            const int lc = v.edges[pr.x].lcol;
-            const double c0 = cl[lc], c1 = cl[(size_t)v.Lf + lc], c2 = cl[(size_t)2 * v.Lf + lc];
+            for (int c = 0; c < 6; ++c) acc[r * 6 + c] += t[r * 3] * hc[c * 3] + t[r * 3 + 1] * hc[c * 3 + 1] + t[r * 3 + 2] * hc[c * 3 + 2];
+        if (ch.diag) {  // pr.x == pr.y: the edge of keyframe i to this landmark
+            const double b0 = bl[lc], b1 = bl[(size_t)v.Lf + lc], b2 = bl[(size_t)2 * v.Lf + lc];
 #pragma unroll
-            for (int r = 0; r < 6; ++r) accb[r] += h[r * 3] * c0 + h[r * 3 + 1] * c1 + h[r * 3 + 2] * c2;
+            for (int r = 0; r < 6; ++r) acc[36 + r] += t[r * 3] * b0 + t[r * 3 + 1] * b1 + t[r * 3 + 2] * b2;
         }
     }
-    // fixed-order warp reduction
 #pragma unroll
-    for (int i = 0; i < 36; ++i)
+    for (int i = 0; i < 42; ++i)
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) acc[i] += __shfl_down_sync(0xFFFFFFFFu, acc[i], s);
+    if (lane == 0)
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) accb[i] += __shfl_down_sync(0xFFFFFFFFu, accb[i], s);
-    if (lane == 0) {
-        for (int r = 0; r < 6; ++r)
-            for (int c = 0; c < 6; ++c) {
-                double val = -acc[r * 6 + c];
-                if (sb.i == sb.j) val += Hpp[(size_t)sb.i * 36 + r * 6 + c] + (r == c ? lambda : 0.0);
-                Hs[(size_t)(6 * sb.i + r) * n + 6 * sb.j + c] = val;
-                Hs[(size_t)(6 * sb.j + c) * n + 6 * sb.i + r] = val;
-            }
-        if (sb.i == sb.j)
-            for (int r = 0; r < 6; ++r) bs[6 * sb.i + r] = bp[(size_t)sb.i * 6 + r] - accb[r];
+        for (int i = 0; i < 42; ++i) partials[(size_t)wid * 42 + i] = acc[i];
+}
+
+__global__ void __launch_bounds__(128) schur_finish_kernel(double lambda, const SchurBlock* __restrict__ blocks, int n_blocks,
+                                                           const double* __restrict__ partials, const double* __restrict__ Hpp,
+                                                           const double* __restrict__ bp, double* __restrict__ M, int n, int ld) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = idx / 42, el = idx - b * 42;
+    if (b >= n_blocks) return;
+    const SchurBlock sb = blocks[b];
+    if (el >= 36 && sb.i != sb.j) return;
+    double sacc = 0.0;
+    for (int c = sb.chunk_start; c < sb.chunk_end; ++c) sacc += partials[(size_t)c * 42 + el];
+    if (el < 36) {
+        const int r = el / 6, c = el - r * 6;
+        double val = -sacc;
+        if (sb.i == sb.j) val += Hpp[(size_t)sb.i * 36 + el] + (r == c ? lambda : 0.0);
+        M[(size_t)(6 * sb.j + c) * ld + 6 * sb.i + r] = val;  // lower triangle (j >= i)
+        if (sb.i == sb.j) M[(size_t)(6 * sb.i + r) * ld + 6 * sb.j + c] = val;
+    } else {
+        const int r = el - 36;
+        M[(size_t)n * ld + 6 * sb.i + r] = bp[(size_t)sb.i * 6 + r] - sacc;  // rhs row
     }
 }
 
@@ -458,36 +487,125 @@ __device__ void se3_oplus(const double* q, const double* t, const double* upd, d
 }
 
 constexpr int kCholThreads = 512;
-__global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, double* __restrict__ A, const double* __restrict__ bs, double lambda,
+constexpr int kNB = 24;  // panel width: four 6x6 keyframe blocks
+
+// Blocked right-looking Cholesky of the augmented matrix M = [Hs ; bs^T] ((n+1) x ld, row-major, lower triangle): the
+// right-hand side rides along as row n, so after the factorisation M[n][0..n) = L^-1 bs and only the backward solve
+// remains.  Per panel of kNB columns: (1) one warp factors the diagonal block in registers (lane i owns row i, columns
+// are exchanged by shuffle); (2) every row below is solved against it, column oriented, with the reciprocal diagonal;
+// the solved panel is kept TRANSPOSED in shared memory; (3) rank-kNB trailing update with 4x4 register tiles whose
+// operands are two 32-byte vector loads per panel column.
+__global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld, double* __restrict__ M, double lambda,
                                                                   const double* __restrict__ bp, double* __restrict__ xp, int K,
                                                                   const int* __restrict__ pose_col, const double* __restrict__ q_cur,
                                                                   const double* __restrict__ t_cur, double* __restrict__ q_new,
                                                                   double* __restrict__ t_new, double* __restrict__ Rt_new,
                                                                   double* __restrict__ result, int* __restrict__ fail) {
+    extern __shared__ __align__(32) double dyn[];
+    double* D = dyn;                     // kNB x (kNB+1) diagonal block (lower, padded with the identity)
+    double* Pn = dyn + kNB * (kNB + 1);  // kNB x mp panel, transposed (k-major); the 600 doubles in front keep it 32-byte aligned
+    const int mp = (n + 1 + 3) & ~3;
     __shared__ double xs[1024];
+    __shared__ double invd_all[1024];    // 1 / L[j][j]
     __shared__ double sh[kCholThreads];
     __shared__ int bad;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, nt = blockDim.x;
     if (tid == 0) bad = *fail;
     __syncthreads();
-    // right-looking Cholesky on the lower triangle, in place (A is L2 resident: n <= a few hundred)
-    for (int j = 0; j < n && !bad; ++j) {
-        if (tid == 0) {
-            const double d = A[(size_t)j * n + j];
-            if (!(d > 0.0) || !isfinite(d)) bad = 1;
-            else A[(size_t)j * n + j] = sqrt(d);
+    long long t_diag = 0, t_panel = 0, t_trail = 0, t_back = 0, t0 = clock64(), t1;
+#define PHASE(acc) do { t1 = clock64(); acc += t1 - t0; t0 = t1; } while (0)
+    for (int kb = 0; kb < n && !bad; kb += kNB) {
+        const int nb = min(kNB, n - kb);
+        if (tid < 32) {
+            // (1) diagonal block, warp 0.  A short last block is padded with the identity so everything is fully unrolled.
+            double r[kNB];
+#pragma unroll
+            for (int k = 0; k < kNB; ++k) r[k] = (tid < nb && k <= tid) ? M[(size_t)(kb + tid) * ld + kb + k] : ((k == tid) ? 1.0 : 0.0);
+            int b = 0;
+#pragma unroll
+            for (int j = 0; j < kNB; ++j) {
+                const double djj = __shfl_sync(0xFFFFFFFFu, r[j], j);
+                b |= (!(djj > 0.0) || !isfinite(djj)) ? 1 : 0;
+                const double inv = rsqrt(djj), dd = djj * inv;  // one reciprocal square root instead of sqrt + divide
+                if (tid == 0) invd_all[kb + j] = inv;  // (entries past n are never read)
+                r[j] = (tid == j) ? dd : ((tid > j) ? r[j] * inv : r[j]);
+                const double mine = (tid > j) ? r[j] : 0.0;
+#pragma unroll
+                for (int k = j + 1; k < kNB; ++k) {
+                    const double lkj = __shfl_sync(0xFFFFFFFFu, r[j], k);
+                    r[k] = fma(-((tid >= k) ? mine : 0.0), lkj, r[k]);
+                }
+            }
+            if (tid < kNB) {
+#pragma unroll
+                for (int k = 0; k < kNB; ++k) {
+                    D[tid * (kNB + 1) + k] = r[k];
+                    if (tid < nb && k <= tid) M[(size_t)(kb + tid) * ld + kb + k] = r[k];
+                }
+            }
+            if (tid == 0 && b) bad = 1;
         }
         __syncthreads();
+        PHASE(t_diag);
         if (bad) break;
-        const double djj = A[(size_t)j * n + j];
-        for (int i = j + 1 + tid; i < n; i += blockDim.x) A[(size_t)i * n + j] /= djj;
-        __syncthreads();
-        const int m = n - j - 1;  // trailing update of the lower triangle: rows i > j, cols j < k <= i
-        for (int idx = tid; idx < m * m; idx += blockDim.x) {
-            const int i = j + 1 + idx / m, k = j + 1 + idx % m;
-            if (k <= i) A[(size_t)i * n + k] -= A[(size_t)i * n + j] * A[(size_t)k * n + j];
+        // (2) panel solve: every row below the block (including the rhs row n)
+        const int r0 = kb + nb, m = n + 1 - r0;
+        for (int t = tid; t < m; t += nt) {
+            double* row = M + (size_t)(r0 + t) * ld + kb;
+            double x[kNB];
+#pragma unroll
+            for (int j = 0; j < kNB; ++j) x[j] = (j < nb) ? row[j] : 0.0;
+#pragma unroll
+            for (int j = 0; j < kNB; ++j) {
+                x[j] *= invd_all[kb + j];
+#pragma unroll
+                for (int k = j + 1; k < kNB; ++k) x[k] = fma(-x[j], D[k * (kNB + 1) + j], x[k]);
+            }
+#pragma unroll
+            for (int j = 0; j < kNB; ++j) {
+                Pn[(size_t)j * mp + t] = x[j];
+                if (j < nb) row[j] = x[j];
+            }
+        }
+        for (int idx = tid; idx < kNB * 4; idx += nt) {  // zero the <= 3 padding rows read by the last 4-row tile
+            const int j = idx >> 2, t = m + (idx & 3);
+            if (t < mp) Pn[(size_t)j * mp + t] = 0.0;
         }
         __syncthreads();
+        PHASE(t_panel);
+        // (3) trailing update with 4x4 register tiles over the lower triangle (rhs row included, rhs column excluded)
+        const int tm = (m + 3) >> 2;
+        const int n_tiles = tm * (tm + 1) / 2;
+        for (int tile = tid; tile < n_tiles; tile += nt) {
+            int tr = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
+            while ((tr + 1) * (tr + 2) / 2 <= tile) ++tr;
+            while (tr * (tr + 1) / 2 > tile) --tr;
+            const int tc = tile - tr * (tr + 1) / 2;
+            double acc[16];
+#pragma unroll
+            for (int a = 0; a < 16; ++a) acc[a] = 0.0;
+            const int rb = tr * 4, cb = tc * 4;
+#pragma unroll 4
+            for (int k = 0; k < kNB; ++k) {
+                const double2* pa = reinterpret_cast<const double2*>(Pn + (size_t)k * mp + rb);
+                const double2* pb = reinterpret_cast<const double2*>(Pn + (size_t)k * mp + cb);
+                const double2 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+                const double a[4] = {a0.x, a0.y, a1.x, a1.y}, b[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) acc[u * 4 + w] = fma(a[u], b[w], acc[u * 4 + w]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                    const int r = rb + u, c = cb + w;
+                    if (r < m && c <= r && r0 + c < n) M[(size_t)(r0 + r) * ld + r0 + c] -= acc[u * 4 + w];
+                }
+        }
+        __syncthreads();
+        PHASE(t_trail);
     }
     if (bad) {
         if (tid == 0) {
@@ -495,37 +613,54 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, double*
             result[0] = 0.0;
         }
     } else {
-        // forward / backward substitution (n small; column-oriented, parallel over rows)
-        for (int i = tid; i < n; i += blockDim.x) xs[i] = bs[i];
+        // backward solve L^T x = y, y = M[n][0..n)
+        for (int i = tid; i < n; i += nt) xs[i] = M[(size_t)n * ld + i];
         __syncthreads();
-        for (int j = 0; j < n; ++j) {
-            if (tid == 0) xs[j] /= A[(size_t)j * n + j];
+        for (int kb = ((n - 1) / kNB) * kNB; kb >= 0; kb -= kNB) {
+            const int nb = min(kNB, n - kb);
+            for (int idx = tid; idx < kNB * kNB; idx += nt) {
+                const int i = idx / kNB, j = idx - i * kNB;
+                D[i * (kNB + 1) + j] = (i < nb && j <= i) ? M[(size_t)(kb + i) * ld + kb + j] : 0.0;
+            }
             __syncthreads();
-            const double xj = xs[j];
-            for (int i = j + 1 + tid; i < n; i += blockDim.x) xs[i] -= A[(size_t)i * n + j] * xj;
+            if (tid < 32) {  // diagonal block: lane k owns y[k]; x[j] is broadcast by shuffle
+                double y = (tid < nb) ? xs[kb + tid] : 0.0;
+#pragma unroll
+                for (int j = kNB - 1; j >= 0; --j) {
+                    const double xj = __shfl_sync(0xFFFFFFFFu, y, j) * ((j < nb) ? invd_all[kb + j] : 0.0);
+                    if (tid == j) y = xj;
+                    else if (tid < j) y = fma(-D[j * (kNB + 1) + tid], xj, y);
+                }
+                if (tid < nb) xs[kb + tid] = y;
+            }
             __syncthreads();
-        }
-        for (int j = n - 1; j >= 0; --j) {
-            if (tid == 0) xs[j] /= A[(size_t)j * n + j];
-            __syncthreads();
-            const double xj = xs[j];
-            for (int i = tid; i < j; i += blockDim.x) xs[i] -= A[(size_t)j * n + i] * xj;
+            for (int i = tid; i < kb; i += nt) {
+                double sacc = xs[i];
+                for (int k = 0; k < nb; ++k) sacc = fma(-M[(size_t)(kb + k) * ld + i], xs[kb + k], sacc);
+                xs[i] = sacc;
+            }
             __syncthreads();
         }
         double sc = 0.0;  // pose part of computeScale: sum x (lambda x + b)
-        for (int i = tid; i < n; i += blockDim.x) {
+        for (int i = tid; i < n; i += nt) {
             xp[i] = xs[i];
             sc += xs[i] * (lambda * xs[i] + bp[i]);
         }
         const double tot = block_sum(sc, sh);
+        PHASE(t_back);
         if (tid == 0) {
             result[0] = 1.0;
             result[1] = tot;
+            result[2] = (double)t_diag;
+            result[3] = (double)t_panel;
+            result[4] = (double)t_trail;
+            result[5] = (double)t_back;
         }
     }
+#undef PHASE
     __syncthreads();
     // trial keyframe states (fixed keyframes and failed solves keep the current state)
-    for (int k = tid; k < K; k += blockDim.x) {
+    for (int k = tid; k < K; k += nt) {
         double qn[4], tn[3];
         const int pc = pose_col[k];
         if (pc >= 0 && !bad) {
@@ -543,32 +678,48 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, double*
     }
 }
 
-// K7: per landmark -- back-substitution x_l = Dinv (bl - sum_e Hpl(e)^T x_p), trial landmark, scale partials
+// K7: back-substitution x_l = Dinv (bl - sum_e Hpl(e)^T x_p), trial landmark, scale partials.  Eight lanes share a landmark
+//     (they split its edges), sixteen landmarks per 128-thread CTA.
 __global__ void __launch_bounds__(128) backsub_kernel(View v, double lambda, const double* __restrict__ Dinv, const double* __restrict__ bl,
                                                       const double* __restrict__ Hpl, const double* __restrict__ xp,
                                                       const double* __restrict__ pts_cur, double* __restrict__ pts_new,
                                                       double* __restrict__ scale_partials, const int* __restrict__ fail) {
     __shared__ double sh[128];
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    const int sub = threadIdx.x & 7;
+    const int l = blockIdx.x * 16 + (threadIdx.x >> 3);
     double sc = 0.0;
-    if (l < v.L) {
-        double p0 = pts_cur[3 * (size_t)l], p1 = pts_cur[3 * (size_t)l + 1], p2 = pts_cur[3 * (size_t)l + 2];
-        const int a0 = v.pt_start[l], b0 = v.pt_start[l + 1];
-        const int lc = (a0 < b0) ? v.edges[a0].lcol : -1;
-        if (lc >= 0 && !*fail) {
-            const double bb0 = bl[lc], bb1 = bl[(size_t)v.Lf + lc], bb2 = bl[(size_t)2 * v.Lf + lc];
-            double c0 = bb0, c1 = bb1, c2 = bb2;
-            for (int e = a0; e < b0; ++e) {
-                const int pcol = v.edges[e].pcol;
-                if (pcol < 0) continue;
+    const bool valid = l < v.L;
+    const int a0 = valid ? v.pt_start[l] : 0, b0 = valid ? v.pt_start[l + 1] : 0;
+    const int lc = (a0 < b0) ? v.edges[a0].lcol : -1;
+    const bool solve = lc >= 0 && !*fail;
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+    if (solve) {
+        for (int e = a0 + sub; e < b0; e += 8) {
+            const int pcol = v.edges[e].pcol;
+            if (pcol < 0) continue;
+            double h[18];
+            load18(Hpl + (size_t)e * 18, h);
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
-                    const double x = xp[6 * pcol + r];
-                    c0 -= Hpl[(size_t)(r * 3) * v.E + e] * x;
-                    c1 -= Hpl[(size_t)(r * 3 + 1) * v.E + e] * x;
-                    c2 -= Hpl[(size_t)(r * 3 + 2) * v.E + e] * x;
-                }
+            for (int r = 0; r < 6; ++r) {
+                const double x = xp[6 * pcol + r];
+                c0 -= h[r * 3] * x;
+                c1 -= h[r * 3 + 1] * x;
+                c2 -= h[r * 3 + 2] * x;
             }
+        }
+    }
+    // fixed-order reduction over the 8 lanes of the landmark
+#pragma unroll
+    for (int s = 4; s > 0; s >>= 1) {
+        c0 += __shfl_down_sync(0xFFFFFFFFu, c0, s, 8);
+        c1 += __shfl_down_sync(0xFFFFFFFFu, c1, s, 8);
+        c2 += __shfl_down_sync(0xFFFFFFFFu, c2, s, 8);
+    }
+    if (valid && sub == 0) {
+        double p0 = pts_cur[3 * (size_t)l], p1 = pts_cur[3 * (size_t)l + 1], p2 = pts_cur[3 * (size_t)l + 2];
+        if (solve) {
+            const double bb0 = bl[lc], bb1 = bl[(size_t)v.Lf + lc], bb2 = bl[(size_t)2 * v.Lf + lc];
+            c0 += bb0; c1 += bb1; c2 += bb2;
             const double D0 = Dinv[lc], D1 = Dinv[(size_t)v.Lf + lc], D2 = Dinv[(size_t)2 * v.Lf + lc];
             const double D4 = Dinv[(size_t)3 * v.Lf + lc], D5 = Dinv[(size_t)4 * v.Lf + lc], D8 = Dinv[(size_t)5 * v.Lf + lc];
             const double x0 = D0 * c0 + D1 * c1 + D2 * c2, x1 = D1 * c0 + D4 * c1 + D5 * c2, x2 = D2 * c0 + D5 * c1 + D8 * c2;
@@ -577,8 +728,8 @@ __global__ void __launch_bounds__(128) backsub_kernel(View v, double lambda, con
         }
         pts_new[3 * (size_t)l] = p0; pts_new[3 * (size_t)l + 1] = p1; pts_new[3 * (size_t)l + 2] = p2;
     }
-    const double s = block_sum(sc, sh);
-    if (threadIdx.x == 0) scale_partials[blockIdx.x] = s;
+    const double tot = block_sum(sc, sh);
+    if (threadIdx.x == 0) scale_partials[blockIdx.x] = tot;
 }
 
 // K8: outlier test (local_bundle_adjuster_g2o.cc:323-344, 357-375): chi2 of the last activation vs the chi-square
@@ -750,8 +901,24 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
         }
     }
     std::vector<SchurBlock> blocks(std::max(1, n_blocks));
+    std::vector<SchurChunk> chunks;
     for (int i = 0, b = 0; i < Kf; ++i)
-        for (int j = i; j < Kf; ++j, ++b) blocks[b] = SchurBlock{i, j, blk_count[b], blk_count[b + 1]};
+        for (int j = i; j < Kf; ++j, ++b) {
+            const int c0 = (int)chunks.size();
+            for (int sidx = blk_count[b]; sidx < blk_count[b + 1]; sidx += kSchurChunk)
+                chunks.push_back(SchurChunk{sidx, std::min(sidx + kSchurChunk, blk_count[b + 1]), i == j ? 1 : 0, 0});
+            blocks[b] = SchurBlock{i, j, c0, (int)chunks.size()};
+        }
+    const int n_chunks = (int)chunks.size();
+    // pose-side chunks: kPoseChunk edges of one free keyframe per warp
+    std::vector<int2> pose_chunks;          // (start, end) into pose_edges
+    std::vector<int> pose_chunk_start(Kf + 1, 0);
+    for (int k = 0; k < Kf; ++k) {
+        for (int sidx = pose_start[k]; sidx < pose_start[k + 1]; sidx += kPoseChunk)
+            pose_chunks.push_back(make_int2(sidx, std::min(sidx + kPoseChunk, pose_start[k + 1])));
+        pose_chunk_start[k + 1] = (int)pose_chunks.size();
+    }
+    const int n_pose_chunks = (int)pose_chunks.size();
     // initial state: util::converter::to_g2o_SE3 (util/converter.cc:17-21)
     std::vector<double> q0(4 * (size_t)std::max(K, 1)), t0(3 * (size_t)std::max(K, 1)), Rt0(12 * (size_t)std::max(K, 1));
     for (int k = 0; k < K; ++k) {
@@ -771,11 +938,12 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
 
     // ---- device arena ----------------------------------------------------------------------------------------------
     const int n = 6 * Kf;
-    const int eb = ceil_div(std::max(E, 1), kEdgeThreads), lb = ceil_div(std::max(L, 1), 128);
+    const int eb = ceil_div(std::max(E, 1), kEdgeThreads), lb = ceil_div(std::max(L, 1), 128), lb2 = ceil_div(std::max(L, 1), 16);
     Carver up;  // uploaded region (mirrors the pinned staging buffer)
     const size_t o_edges = up.take<EdgeS>(E), o_cams = up.take<Cam>(P->n_cams), o_ptstart = up.take<int>(L + 1);
     const size_t o_posestart = up.take<int>(Kf + 1), o_poseedges = up.take<int>(pose_edges.size()), o_robust = up.take<unsigned char>(E);
     const size_t o_posecol = up.take<int>(K), o_blocks = up.take<SchurBlock>(n_blocks), o_pairs = up.take<int2>(n_pairs);
+    const size_t o_chunks = up.take<SchurChunk>(n_chunks), o_pchunks = up.take<int2>(n_pose_chunks), o_pcstart = up.take<int>(Kf + 1);
     const size_t o_q0 = up.take<double>(4 * (size_t)K), o_t0 = up.take<double>(3 * (size_t)K), o_Rt0 = up.take<double>(12 * (size_t)K);
     const size_t o_pts0 = up.take<double>(3 * (size_t)L);
     const size_t upload_bytes = round_up(up.off, (size_t)256);
@@ -784,12 +952,13 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     const size_t o_q1 = dv.take<double>(4 * (size_t)K), o_t1 = dv.take<double>(3 * (size_t)K), o_Rt1 = dv.take<double>(12 * (size_t)K);
     const size_t o_pts1 = dv.take<double>(3 * (size_t)L);
     const size_t o_level = dv.take<unsigned char>(E), o_chi0 = dv.take<double>(E), o_chi1 = dv.take<double>(E);
-    const size_t o_Hpl = dv.take<double>(18 * (size_t)E), o_T = dv.take<double>(18 * (size_t)E), o_pl = dv.take<double>(9 * (size_t)E);
+    const size_t o_Hpl = dv.take<double>(18 * (size_t)E), o_pl = dv.take<double>(9 * (size_t)E);
     const size_t o_Hll = dv.take<double>(6 * (size_t)Lf), o_bl = dv.take<double>(3 * (size_t)Lf), o_Dinv = dv.take<double>(6 * (size_t)Lf);
-    const size_t o_cl = dv.take<double>(3 * (size_t)Lf), o_Hpp = dv.take<double>(36 * (size_t)Kf), o_bp = dv.take<double>(6 * (size_t)Kf);
-    const size_t o_Hs = dv.take<double>((size_t)n * n), o_bs = dv.take<double>(n), o_xp = dv.take<double>(n);
-    // readback block: [chi partials eb][diag partials lb][scale partials lb][result 2][Hpp diag 6Kf]
-    const size_t res_n = (size_t)eb + 2 * (size_t)lb + 2 + (size_t)std::max(n, 1);
+    const size_t o_part = dv.take<double>(42 * (size_t)n_chunks), o_ppart = dv.take<double>(27 * (size_t)n_pose_chunks), o_Hpp = dv.take<double>(36 * (size_t)Kf), o_bp = dv.take<double>(6 * (size_t)Kf);
+    const int ld = n + 2;
+    const size_t o_Hs = dv.take<double>((size_t)(n + 1) * ld), o_xp = dv.take<double>(n);
+    // readback block: [chi partials eb][diag partials lb][scale partials lb2][result 2]
+    const size_t res_n = (size_t)eb + (size_t)lb + (size_t)lb2 + 6;
     const size_t o_res = dv.take<double>(res_n), o_fail = dv.take<int>(1), o_out = dv.take<unsigned char>(E);
     int rc = S.ensure(dv.off + 256, upload_bytes, res_n);
     if (rc) return rc;
@@ -804,6 +973,9 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     put(o_robust, robust.data(), E);
     put(o_posecol, pose_col.data(), sizeof(int) * K);
     put(o_blocks, blocks.data(), sizeof(SchurBlock) * n_blocks);
+    put(o_chunks, chunks.data(), sizeof(SchurChunk) * n_chunks);
+    put(o_pchunks, pose_chunks.data(), sizeof(int2) * n_pose_chunks);
+    put(o_pcstart, pose_chunk_start.data(), sizeof(int) * (Kf + 1));
     put(o_pairs, pairs.data(), sizeof(int2) * n_pairs);
     put(o_q0, q0.data(), sizeof(double) * 4 * K);
     put(o_t0, t0.data(), sizeof(double) * 3 * K);
@@ -825,14 +997,16 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     double* Rts[2] = {(double*)(d + o_Rt0), (double*)(d + o_Rt1)};
     double* ptss[2] = {(double*)(d + o_pts0), (double*)(d + o_pts1)};
     double* chis[2] = {(double*)(d + o_chi0), (double*)(d + o_chi1)};
-    double *Hpl = (double*)(d + o_Hpl), *Tm = (double*)(d + o_T), *pl = (double*)(d + o_pl), *Hll = (double*)(d + o_Hll), *bl = (double*)(d + o_bl);
-    double *Dinv = (double*)(d + o_Dinv), *cl = (double*)(d + o_cl), *Hpp = (double*)(d + o_Hpp), *bp = (double*)(d + o_bp);
-    double *Hs = (double*)(d + o_Hs), *bs = (double*)(d + o_bs), *xp = (double*)(d + o_xp), *res = (double*)(d + o_res);
+    double *Hpl = (double*)(d + o_Hpl), *pl = (double*)(d + o_pl), *Hll = (double*)(d + o_Hll), *bl = (double*)(d + o_bl);
+    double *Dinv = (double*)(d + o_Dinv), *part = (double*)(d + o_part), *ppart = (double*)(d + o_ppart), *Hpp = (double*)(d + o_Hpp), *bp = (double*)(d + o_bp);
+    double *Hs = (double*)(d + o_Hs), *xp = (double*)(d + o_xp), *res = (double*)(d + o_res);
+    const size_t chol_smem = sizeof(double) * ((size_t)kNB * (kNB + 1) + 4 + (size_t)((n + 1 + 3) & ~3) * kNB);
+    B200_CUDA(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
     int* fail = (int*)(d + o_fail);
     double* r_chi = res;                 // eb
     double* r_diag = res + eb;           // lb
     double* r_scale = res + eb + lb;     // lb
-    double* r_result = res + eb + 2 * lb;  // 2
+    double* r_result = res + eb + lb + lb2;  // 2
     double* h = S.h_res;
     int cur = 0;
 
@@ -850,15 +1024,17 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
             // computeActiveErrors + buildSystem at the current state
             if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], Hpl, pl, r_chi, 1);
             points_kernel<<<lb, 128, 0, st>>>(v, pl, Hll, bl, r_diag);
-            if (Kf) poses_kernel<<<Kf, kPoseThreads, 0, st>>>(v, Rts[cur], ptss[cur], Hpp, bp);
-            launches += 3;
+            if (n_pose_chunks) {
+                pose_chunks_kernel<<<ceil_div(n_pose_chunks, 4), 128, 0, st>>>(v, (const int2*)(d + o_pchunks), n_pose_chunks, Rts[cur], ptss[cur], ppart);
+                pose_finish_kernel<<<ceil_div(Kf * 27, 128), 128, 0, st>>>(Kf, (const int*)(d + o_pcstart), ppart, Hpp, bp);
+            } else if (Kf) {
+                B200_CUDA(cudaMemsetAsync(Hpp, 0, sizeof(double) * 36 * Kf, st));
+                B200_CUDA(cudaMemsetAsync(bp, 0, sizeof(double) * 6 * Kf, st));
+            }
+            launches += 4;
             const bool need_diag = (it == 0);
             B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * (eb + (need_diag ? lb : 0)), cudaMemcpyDeviceToHost, st));
             std::vector<double> hpp_diag;
-            if (need_diag && Kf) {
-                hpp_diag.resize(36 * (size_t)Kf);
-                B200_CUDA(cudaMemcpyAsync(h + eb + 2 * lb + 2, Hpp, 0, cudaMemcpyDeviceToHost, st));
-            }
             B200_CUDA(cudaStreamSynchronize(st));
             double current_chi = sum(h, eb);
             if (it == 0) {  // computeLambdaInit: tau * max |H_jj| over all free vertices, tau = 1e-5
@@ -879,23 +1055,30 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
             do {
                 const int nxt = cur ^ 1;
                 B200_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), st));
-                schur_prep_kernel<<<lb, 128, 0, st>>>(v, lambda, Hll, bl, Hpl, Dinv, cl, Tm, fail);
-                if (n_blocks) schur_blocks_kernel<<<ceil_div(n_blocks, 4), 128, 0, st>>>(v, lambda, (const SchurBlock*)(d + o_blocks), n_blocks,
-                                                                                         (const int2*)(d + o_pairs), Hpp, bp, Hpl, Tm, cl, Hs, bs, n);
-                chol_solve_kernel<<<1, kCholThreads, 0, st>>>(n, Hs, bs, lambda, bp, xp, K, (const int*)(d + o_posecol), qs[cur], ts[cur], qs[nxt],
-                                                              ts[nxt], Rts[nxt], r_result, fail);
-                backsub_kernel<<<lb, 128, 0, st>>>(v, lambda, Dinv, bl, Hpl, xp, ptss[cur], ptss[nxt], r_scale, fail);
+                if (Lf) dinv_kernel<<<ceil_div(Lf, 128), 128, 0, st>>>(Lf, lambda, Hll, Dinv, fail);
+                if (n_chunks)
+                    schur_chunks_kernel<<<ceil_div(n_chunks, 4), 128, 0, st>>>(v, (const SchurChunk*)(d + o_chunks), n_chunks, (const int2*)(d + o_pairs),
+                                                                              Hpl, Dinv, bl, part);
+                if (n_blocks)
+                    schur_finish_kernel<<<ceil_div(n_blocks * 42, 128), 128, 0, st>>>(lambda, (const SchurBlock*)(d + o_blocks), n_blocks, part, Hpp, bp, Hs,
+                                                                                     n, ld);
+                chol_solve_kernel<<<1, kCholThreads, chol_smem, st>>>(n, ld, Hs, lambda, bp, xp, K, (const int*)(d + o_posecol), qs[cur], ts[cur],
+                                                                      qs[nxt], ts[nxt], Rts[nxt], r_result, fail);
+                backsub_kernel<<<lb2, 128, 0, st>>>(v, lambda, Dinv, bl, Hpl, xp, ptss[cur], ptss[nxt], r_scale, fail);
                 if (E) {
                     carry_chi_kernel<<<eb, 128, 0, st>>>(v, chis[cur], chis[nxt]);
                     edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[nxt], ptss[nxt], chis[nxt], Hpl, pl, r_chi, 0);
                 }
-                launches += 6;
+                launches += 7;
                 B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * res_n, cudaMemcpyDeviceToHost, st));
                 B200_CUDA(cudaStreamSynchronize(st));
-                const bool ok2 = h[eb + 2 * lb] != 0.0;
+                const bool ok2 = h[eb + lb + lb2] != 0.0;
+                if (getenv("B200_LBA_DEBUG"))
+                    fprintf(stderr, "[lba] chol cycles: diag %.0f panel %.0f trailing %.0f backward %.0f\n", h[eb + lb + lb2 + 2], h[eb + lb + lb2 + 3],
+                            h[eb + lb + lb2 + 4], h[eb + lb + lb2 + 5]);
                 double temp_chi = ok2 ? sum(h, eb) : 1.7976931348623157e308;
                 rho = current_chi - temp_chi;
-                double scale = ok2 ? h[eb + 2 * lb + 1] + sum(h + eb + lb, lb) : 0.0;  // computeScale
+                double scale = ok2 ? h[eb + lb + lb2 + 1] + sum(h + eb + lb, lb2) : 0.0;  // computeScale
                 scale += 1e-3;
                 rho /= scale;
                 if (rho > 0 && std::isfinite(temp_chi) && ok2) {
@@ -1044,8 +1227,8 @@ int b200_lba_solve(b200_lba_t h, const b200_lba_problem_t* P, int iters1, int it
         b200::set_error("b200_lba_solve: inconsistent problem description");
         return B200_ERR_INVALID;
     }
-    if (6 * (size_t)P->n_poses > 1024) {
-        b200::set_error("b200_lba_solve: more than 170 keyframes in one local window is not supported");
+    if (6 * (size_t)P->n_poses > 1000) {
+        b200::set_error("b200_lba_solve: more than 166 keyframes in one local window is not supported");
         return B200_ERR_INVALID;
     }
     if (force_stop && *force_stop) return B200_ERR_ABORTED;  // local_bundle_adjuster_g2o.cc:308-310
