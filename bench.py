@@ -42,6 +42,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lba", action="store_true")
+    ap.add_argument("--lba-every", type=int, default=16, help="one local-BA window (50 keyframes / 10k landmarks) per this many frames")
     return ap.parse_args()
 
 
@@ -99,21 +100,47 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle on the host cores (kind "port")
 # ---------------------------------------------------------------------------------------------------------------------
-def cpu_frames_per_sec(frames, min_area, budget_s, threads=None):
-    """Extract + match on `threads` host threads (pthread pool inside the oracle, one frame per task).
-    Returns (frames/s, n_frames, threads, mean matches)."""
+def usable_cpus():
+    """Host cores this process may actually use: affinity mask and cgroup CPU quota, not just os.cpu_count()."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period) + 0.5)))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def cpu_frames_per_sec(frames, min_area, budget_s, threads=None, lba_problem=None, lba_every=16):
+    """The CPU oracle on `threads` host threads: extract + match (pthread pool, one frame per task) and, when
+    lba_problem is given, one local-BA solve per `lba_every` frames (one window per thread).
+    Returns (frames/s, n_frames, threads, mean matches, n_lba)."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from oracle import pyoracle as O
     O.lib()
-    threads = max(1, min(threads or os.cpu_count() or 1, 512))
+    threads = max(1, min(threads or usable_cpus(), 512))
     frames = np.ascontiguousarray(np.stack(frames))
     t0 = time.perf_counter()
     O.frontend_batch(frames, 2, min_area, LOWE, CHECK_ORI, 1)     # calibration on one thread
     per_frame = (time.perf_counter() - t0) / 2.0
     n = int(max(threads, min(16 * threads, budget_s * threads / max(per_frame, 1e-3))))
+    if lba_problem is not None:
+        n = max(lba_every, (n // lba_every) * lba_every)
     t0 = time.perf_counter()
     counts, matches = O.frontend_batch(frames, n, min_area, LOWE, CHECK_ORI, threads)
+    n_lba = 0
+    if lba_problem is not None:
+        n_lba = n // lba_every
+        with ThreadPoolExecutor(min(threads, n_lba)) as ex:
+            list(ex.map(lambda _: O.lba_solve(lba_problem)["n_outliers"], range(n_lba)))
     dt = time.perf_counter() - t0
-    return n / dt, n, threads, float(matches.mean())
+    return n / dt, n, threads, float(matches.mean()), n_lba
 
 
 def run_reference(args):
@@ -140,10 +167,11 @@ def run_reference(args):
         min_area = (lo + hi) // 2
     per_step = []
     total_frames = 0
-    threads = os.cpu_count() or 1
+    threads = usable_cpus()
     budget = max(1.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
+    lba_problem = None if args.no_lba else synth.make_ba_problem(50, 10, 10000, seed=0, model="stereo")
     for s in range(args.warmup + args.steps):
-        fps, n, threads, _ = cpu_frames_per_sec(frames, min_area, budget, threads)
+        fps, n, threads, _, _ = cpu_frames_per_sec(frames, min_area, budget, threads, lba_problem, args.lba_every)
         if s >= args.warmup:
             per_step.append((n, n / fps))
             total_frames += n
@@ -153,10 +181,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * t / max(1, len(per_step)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": "configs[1]: 1920x1080 synthetic stream, ~2000 kpts, ORB extract + brute-force match (CPU oracle port)",
+        "config": {"workload": "configs[1]: 1920x1080 synthetic stream, ~2000 kpts, ORB extract + brute-force match vs previous frame"
+                               + ("" if args.no_lba else f" + one local BA (50 KF / 10k landmarks, stereo) per {args.lba_every} frames") + " (CPU oracle port)",
                    "min_area": int(min_area), "frames_per_step": int(per_step[0][0]) if per_step else 0},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "kind": "port",
-                         "sample": f"{total_frames} frames of the synthetic 1080p stream, extract + match, {threads} threads "
+                         "sample": f"{total_frames} frames of the synthetic 1080p stream, extract + match (+ local BA), {threads} threads "
                                    "(oracle/: C restatement of the reference; the reference itself needs OpenCV/g2o)"},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -234,7 +263,32 @@ def main():
     angle_ptr = kps.data_ptr() + 12  # &kps[0].angle
     gathered = torch.zeros((world, B, 2), dtype=torch.int32, device=dev) if world > 1 else None
 
+    # local BA: one KITTI-sized window (BASELINE config 4) per --lba-every frames, solved concurrently on a pool of handles
+    n_lba = 0 if args.no_lba else max(1, B // args.lba_every)
+    lba_pool, lba_handles, lba_problem = None, [], None
+    if n_lba:
+        from concurrent.futures import ThreadPoolExecutor
+
+        from stella_vslam_b200 import optimize
+        lba_problem = synth.make_ba_problem(50, 10, 10000, seed=rank, model="stereo")
+        lba_handles = [optimize.local_bundle_adjuster(device=local_rank) for _ in range(n_lba)]
+        lba_pool = ThreadPoolExecutor(n_lba)
+    lba_launches = [0]
+
+    def lba_submit():
+        return [lba_pool.submit(hd.optimize, lba_problem) for hd in lba_handles] if n_lba else []
+
+    def lba_join(futs):
+        for f in futs:
+            r = f.result()
+            lba_launches[0] = r["launches"]
+
     def step_device():
+        futs = lba_submit()   # the mapping thread's local BA runs concurrently with tracking (mapping_module.cc:63,206)
+        step_frontend_device()
+        lba_join(futs)
+
+    def step_frontend_device():
         # previous step's last frame becomes slot 0
         kps[0].copy_(kps[B])
         desc[0].copy_(desc[B])
@@ -300,6 +354,11 @@ def main():
     h_angle = h_kps.ctypes.data + 12
 
     def step_e2e():
+        futs = lba_submit()
+        step_frontend_e2e()
+        lba_join(futs)
+
+    def step_frontend_e2e():
         h_kps[0] = h_kps[B]
         h_desc[0] = h_desc[B]
         h_counts[0] = h_counts[B]
@@ -376,9 +435,11 @@ def main():
 
     cpu = None
     if not args.no_cpu_baseline:
-        fps, n, threads, mean_matches = cpu_frames_per_sec(list(frames_np[:8]), min_area, args.cpu_seconds)
+        fps, n, threads, mean_matches, n_cpu_lba = cpu_frames_per_sec(list(frames_np[:8]), min_area, args.cpu_seconds, None, lba_problem,
+                                                                      args.lba_every)
         cpu = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": f"{n} frames of the same synthetic 1080p stream (extract + match vs previous frame) on {threads} host threads"}
+               "sample": f"{n} frames of the same synthetic 1080p stream (extract + match vs previous frame) + {n_cpu_lba} local-BA windows "
+                         f"on {threads} host threads"}
 
     line = {
         "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -387,11 +448,14 @@ def main():
         "config": {"workload": "configs[1]: 1920x1080 synthetic stream, ~2000 kpts, ORB extract + brute-force match vs previous frame",
                    "frames_per_gpu_per_step": B, "min_area": int(min_area), "keypoints_per_frame_mean": float(N),
                    "matches_per_frame_mean": float(n_mt.mean()), "raw_fast_corners_frame0": raw_c,
-                   "l2": f"inputs larger than L2: {B} frames x {W * H / 1e6:.2f} MB + {B} pyramids", "lba": "not in this line"},
+                   "l2": f"inputs larger than L2: {B} frames x {W * H / 1e6:.2f} MB + {B} pyramids",
+                   "lba": (f"{n_lba} local-BA windows per step (one per {args.lba_every} frames): 50 keyframes (10 fixed), 10000 landmarks, "
+                           f"{len(lba_problem['e_pose'])} stereo observations, 5+10 LM iterations, solved concurrently with the front end")
+                   if n_lba else "disabled"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / args.steps},
-        "gpu_launches": 13 * args.steps,
+        "gpu_launches": (13 + n_lba * lba_launches[0]) * args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "stage_ms": {n_: stage_ms[i] for i, n_ in enumerate(names + ["extract_total"])},
