@@ -215,7 +215,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from stella_vslam_b200 import _lib, feature, synth
+    from stella_vslam_b200 import _lib, feature, multi_gpu, synth
     from stella_vslam_b200._lib import check, lib, ptr
     L = lib()
     B = args.batch
@@ -262,6 +262,8 @@ def main():
     frames_dev = torch.from_numpy(frames_np).to(dev)
     angle_ptr = kps.data_ptr() + 12  # &kps[0].angle
     gathered = torch.zeros((world, B, 2), dtype=torch.int32, device=dev) if world > 1 else None
+    stream_id = multi_gpu.assign_streams(world, world, rank)[0]   # one stream per GPU (BASELINE config 5)
+    assert stream_id == rank
 
     # local BA: one KITTI-sized window (BASELINE config 4) per --lba-every frames, solved concurrently on a pool of handles
     n_lba = 0 if args.no_lba else max(1, B // args.lba_every)
@@ -299,8 +301,7 @@ def main():
                                              C.c_void_p(off.data_ptr()), C.c_void_p(counts.data_ptr()), stride, stride, LOWE, int(CHECK_ORI),
                                              C.c_void_p(pairs.data_ptr()), stride, C.c_void_p(n_pairs.data_ptr())))
         if world > 1:  # gather the per-stream records (keypoint and match counts) on every rank: NCCL over NVLink
-            rec = torch.stack([counts[1:], n_pairs], 1)
-            dist.all_gather_into_tensor(gathered, rec.unsqueeze(0))
+            multi_gpu.gather_records(torch.stack([counts[1:], n_pairs], 1), world, gathered)
 
     def barrier():
         if world > 1:
@@ -328,14 +329,11 @@ def main():
     check(L.b200_orb_sync(hx))
     stage_ms = ex.stage_ms()
     check(L.b200_orb_enable_timing(hx, 0))
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
+    ms_total = multi_gpu.max_over_ranks(ms_total, dev, world)
     clocks = sampler.stop() if rank == 0 else None
     n_kp = counts[1:].cpu().numpy()
     n_mt = n_pairs.cpu().numpy()
-    value = world * B * args.steps / (ms_total * 1e-3)
+    value = multi_gpu.frames_per_second(B, args.steps, world, ms_total)
 
     # ---- e2e: host buffers through the reference-facing C ABI calls ---------------------------------------------------
     cap = stride
@@ -376,10 +374,7 @@ def main():
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s = multi_gpu.max_over_ranks(e2e_s, dev, world)
     e2e_value = world * B * args.steps / e2e_s
     assert np.array_equal(h_counts[1:], n_kp), "host path and device path disagree on keypoint counts"
     assert np.array_equal(h_npairs, n_mt), "host path and device path disagree on match counts"

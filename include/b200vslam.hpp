@@ -1,0 +1,202 @@
+// b200vslam.hpp -- C++ host-side mirror of the reference's class surfaces on top of the C ABI (b200vslam.h).
+//
+// Header-only, no OpenCV/Eigen/g2o dependency: images are raw 8-bit buffers, keypoints are b200_keypoint_t.  The names,
+// constructor arguments and error behaviour follow the reference so that the thin adapters in
+// stella_vslam_b200/host/reference_adapters/ (which DO include the reference's headers) are one-liners:
+//   b200::feature::orb_params      <->  stella_vslam::feature::orb_params      (feature/orb_params.h:11-54)
+//   b200::feature::orb_extractor   <->  stella_vslam::feature::orb_extractor   (feature/orb_extractor.h:46-122)
+//   b200::match::robust            <->  stella_vslam::match::robust            (match/robust.h, match/base.h:81-91)
+//   b200::optimize::local_bundle_adjuster <-> stella_vslam::optimize::local_bundle_adjuster (optimize/local_bundle_adjuster.h:15-24)
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "b200vslam.h"
+
+namespace b200 {
+
+inline void check(int rc, const char* what) {
+    if (rc != B200_OK) throw std::runtime_error(std::string(what) + ": " + b200_last_error());
+}
+
+namespace feature {
+
+enum class descriptor_type { ORB, HASH_SIFT };  // feature/orb_extractor.h:17-44
+
+struct orb_params {  // feature/orb_params.cc:12-71 (float recurrences, not pow)
+    std::string name_;
+    float scale_factor_ = 1.2f;
+    float log_scale_factor_;
+    unsigned int num_levels_ = 8, ini_fast_thr_ = 20, min_fast_thr_ = 7;
+    std::vector<float> scale_factors_, inv_scale_factors_, level_sigma_sq_, inv_level_sigma_sq_;
+
+    explicit orb_params(const std::string& name = "default ORB feature extraction setting", float scale_factor = 1.2f,
+                        unsigned int num_levels = 8, unsigned int ini_fast_thr = 20, unsigned int min_fast_thr = 7)
+        : name_(name), scale_factor_(scale_factor), log_scale_factor_(std::log(scale_factor)), num_levels_(num_levels),
+          ini_fast_thr_(ini_fast_thr), min_fast_thr_(min_fast_thr) {
+        scale_factors_.assign(num_levels, 1.0f);
+        inv_scale_factors_.assign(num_levels, 1.0f);
+        level_sigma_sq_.assign(num_levels, 1.0f);
+        inv_level_sigma_sq_.assign(num_levels, 1.0f);
+        float s = 1.0f;
+        for (unsigned int l = 1; l < num_levels; ++l) {
+            scale_factors_[l] = scale_factor * scale_factors_[l - 1];
+            inv_scale_factors_[l] = (1.0f / scale_factor) * inv_scale_factors_[l - 1];
+            s = scale_factor * s;
+            level_sigma_sq_[l] = s * s;
+            inv_level_sigma_sq_[l] = 1.0f / (s * s);
+        }
+    }
+};
+
+class orb_extractor {
+public:
+    // orb_extractor(const orb_params*, unsigned min_area, descriptor_type, mask_rects) -- orb_extractor.h:51-54
+    orb_extractor(const orb_params* params, unsigned int min_area, descriptor_type desc_type = descriptor_type::ORB,
+                  const std::vector<std::vector<float>>& mask_rects = {}, int device = 0, int max_batch = 1)
+        : orb_params_(params), mask_rects_(mask_rects) {
+        if (desc_type == descriptor_type::HASH_SIFT) throw std::runtime_error("cuda_efficient_features is not available");  // orb_extractor.cc:121
+        b200_orb_params_t p;
+        b200_orb_default_params(&p);
+        p.scale_factor = params->scale_factor_;
+        p.num_levels = (int32_t)params->num_levels_;
+        p.ini_fast_thr = (int32_t)params->ini_fast_thr_;
+        p.min_fast_thr = (int32_t)params->min_fast_thr_;
+        p.min_area = min_area;
+        for (const auto& r : mask_rects) flat_rects_.insert(flat_rects_.end(), r.begin(), r.begin() + 4);
+        p.n_mask_rects = (int32_t)mask_rects.size();
+        p.mask_rects = flat_rects_.empty() ? nullptr : flat_rects_.data();
+        p.device = device;
+        p.max_batch = max_batch;
+        check(b200_orb_create(&p, &h_), "b200_orb_create");
+    }
+    ~orb_extractor() { b200_orb_destroy(h_); }
+    orb_extractor(const orb_extractor&) = delete;
+    orb_extractor& operator=(const orb_extractor&) = delete;
+
+    // extract(in_image, in_image_mask, keypts, out_descriptors) -- orb_extractor.h:60-61.  One CV_8UC1 frame in host memory;
+    // descriptors come back as N x 32 bytes (cv::Mat(N, 32, CV_8U) layout).  Empty image -> silent return (orb_extractor.cc:30-32).
+    void extract(const uint8_t* image, int width, int height, size_t pitch, const uint8_t* mask, size_t mask_pitch,
+                 std::vector<b200_keypoint_t>& keypts, std::vector<uint8_t>& descriptors) {
+        extract_batch(image, width, height, pitch, pitch * (size_t)height, 1, mask, mask_pitch, keypts, descriptors, counts_);
+        keypts.resize(counts_.empty() ? 0 : counts_[0]);
+        descriptors.resize(keypts.size() * 32);
+    }
+    // `batch` same-sized frames; frame f's results start at f * cap (cap = max_keypoints(width, height)).
+    void extract_batch(const uint8_t* images, int width, int height, size_t pitch, size_t frame_stride, int batch, const uint8_t* mask,
+                       size_t mask_pitch, std::vector<b200_keypoint_t>& keypts, std::vector<uint8_t>& descriptors, std::vector<int32_t>& counts) {
+        keypts.clear();
+        descriptors.clear();
+        counts.assign(batch > 0 ? batch : 0, 0);
+        if (!images || width == 0 || height == 0 || batch == 0) return;
+        const int cap = max_keypoints(width, height);
+        keypts.resize((size_t)cap * batch);
+        descriptors.resize((size_t)cap * batch * 32);
+        check(b200_orb_extract(h_, images, width, height, pitch, frame_stride, batch, mask, mask_pitch, keypts.data(), descriptors.data(), cap,
+                               counts.data()),
+              "b200_orb_extract");
+    }
+    int max_keypoints(int width, int height) const { return b200_orb_max_keypoints(h_, width, height); }
+    // image_pyramid_ (orb_extractor.h:71): level >= 1 of the last extract, tightly packed
+    std::vector<uint8_t> pyramid_level(int frame, int level, int* w = nullptr, int* hgt = nullptr) const {
+        int lw = 0, lh = 0;
+        check(b200_orb_level_info(h_, level, &lw, &lh, nullptr, nullptr), "b200_orb_level_info");
+        std::vector<uint8_t> out((size_t)lw * lh);
+        check(b200_orb_pyramid_level_host(h_, frame, level, out.data(), (size_t)lw), "b200_orb_pyramid_level_host");
+        if (w) *w = lw;
+        if (hgt) *hgt = lh;
+        return out;
+    }
+    b200_orb_t handle() const { return h_; }
+
+    const orb_params* orb_params_;                  // orb_extractor.h:64
+    std::vector<std::vector<float>> mask_rects_;    // orb_extractor.h:68
+
+private:
+    b200_orb_t h_ = nullptr;
+    std::vector<float> flat_rects_;
+    std::vector<int32_t> counts_;
+};
+
+}  // namespace feature
+
+namespace match {
+
+constexpr unsigned int HAMMING_DIST_THR_LOW = 50, HAMMING_DIST_THR_HIGH = 100, MAX_HAMMING_DIST = 256;  // match/base.h:15-17
+
+class base {  // match/base.h:81-91
+public:
+    base(float lowe_ratio, bool check_orientation) : lowe_ratio_(lowe_ratio), check_orientation_(check_orientation) {}
+    virtual ~base() = default;
+
+protected:
+    const float lowe_ratio_;
+    const bool check_orientation_;
+};
+
+class robust final : public base {
+public:
+    robust(float lowe_ratio, bool check_orientation, int device = 0) : base(lowe_ratio, check_orientation) {
+        check(b200_matcher_create(device, &h_), "b200_matcher_create");
+    }
+    ~robust() override { b200_matcher_destroy(h_); }
+    // brute_force_match (match/robust.cc:232-328): frame keypoints (descriptors 32 B each, angles with a byte stride) against the
+    // keyframe's; keyfrm_has_landmark[i] != 0 <=> lms_2[i] && !will_be_erased().  Returns (idx_1, idx_2) sorted by idx_1.
+    unsigned int brute_force_match(const uint8_t* frm_desc, const void* frm_angles, size_t frm_angle_stride, int n1, const uint8_t* keyfrm_desc,
+                                   const void* keyfrm_angles, size_t keyfrm_angle_stride, const uint8_t* keyfrm_has_landmark, int n2,
+                                   std::vector<std::pair<int, int>>& matches) const {
+        matches.clear();
+        if (n1 <= 0 || n2 <= 0) return 0;
+        std::vector<int32_t> pairs((size_t)2 * n1);
+        const int32_t off = 0;
+        int32_t n = 0;
+        check(b200_match_bruteforce(h_, 1, frm_desc, frm_angles, frm_angle_stride, &off, &n1, keyfrm_desc, keyfrm_angles, keyfrm_angle_stride,
+                                    keyfrm_has_landmark, &off, &n2, lowe_ratio_, check_orientation_ ? 1 : 0, pairs.data(), n1, &n),
+              "b200_match_bruteforce");
+        matches.reserve(n);
+        for (int i = 0; i < n; ++i) matches.emplace_back(pairs[2 * i], pairs[2 * i + 1]);
+        return (unsigned int)n;
+    }
+
+private:
+    b200_matcher_t h_ = nullptr;
+};
+
+}  // namespace match
+
+namespace optimize {
+
+class local_bundle_adjuster {  // optimize/local_bundle_adjuster_g2o.h:16-46 with Mapping.backend: "b200"
+public:
+    explicit local_bundle_adjuster(unsigned int num_first_iter = 5, unsigned int num_second_iter = 10, int device = 0)
+        : num_first_iter_(num_first_iter), num_second_iter_(num_second_iter) {
+        check(b200_lba_create(device, &h_), "b200_lba_create");
+    }
+    ~local_bundle_adjuster() { b200_lba_destroy(h_); }
+    local_bundle_adjuster(const local_bundle_adjuster&) = delete;
+    // steps 5-7 of local_bundle_adjuster_g2o::optimize on the flattened window; returns false when the abort flag was already set
+    // (local_bundle_adjuster_g2o.cc:308-310), in which case nothing is written.
+    bool optimize(const b200_lba_problem_t& problem, volatile uint8_t* force_stop_flag, std::vector<double>& pose_cw_out,
+                  std::vector<double>& points_out, std::vector<uint8_t>& outlier_out, b200_lba_stats_t* stats = nullptr) const {
+        pose_cw_out.resize((size_t)16 * problem.n_poses);
+        points_out.resize((size_t)3 * problem.n_points);
+        outlier_out.resize((size_t)problem.n_edges);
+        const int rc = b200_lba_solve(h_, &problem, (int)num_first_iter_, (int)num_second_iter_, force_stop_flag, pose_cw_out.data(),
+                                      points_out.data(), outlier_out.data(), stats);
+        if (rc == B200_ERR_ABORTED) return false;
+        check(rc, "b200_lba_solve");
+        return true;
+    }
+
+private:
+    const unsigned int num_first_iter_, num_second_iter_;
+    b200_lba_t h_ = nullptr;
+};
+
+}  // namespace optimize
+}  // namespace b200
