@@ -155,13 +155,68 @@ __device__ __forceinline__ bool mask_zero(const unsigned char* mask, unsigned lo
     return mask[(size_t)r * mask_pitch + c] == 0;
 }
 
-__global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__ Geom g, Images im, const CellDesc* __restrict__ cells,
-                                                         const unsigned char* __restrict__ mask, unsigned long long mask_pitch,
-                                                         unsigned long long* __restrict__ grid) {
-    __shared__ __align__(16) unsigned char tile[kTileMax * kTilePitch];
-    __shared__ __align__(16) unsigned char mmap[kTileMax * kTilePitch];
-    __shared__ unsigned short queue[kCell * kCell];
-    __shared__ int q_count;
+// Exact FAST score map for FOUR horizontally adjacent pixels (two u16x2 lane pairs: even = px 0,2 / odd = px 1,3).
+// m = max( v - min_s max_{arc s} p ,  max_s min_{arc s} p - v )  over the 16 arcs of 9 contiguous circle pixels, computed with
+// the sm_100 packed 3-input min/max (VIMNMX3.U16x2): 16 window-3 + 16 window-9 + 8 reduction ops per polarity and lane
+// pair.  Working on the raw pixel values (not on differences) keeps everything unsigned and never negates a min/max
+// result (see the ptxas note in DESIGN.md).  Returns max(m - t_low, 0) per pixel, packed as 4 bytes.
+__device__ __forceinline__ unsigned fast_m4(const unsigned (&w)[7][3], unsigned neg_tlow2) {
+    // circle offsets (dx, dy) in OpenCV order; row index = dy + 3, window = 4 bytes starting at column c0 + dx
+    constexpr int DX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+    constexpr int DY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+    unsigned pe[16], po[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int dx = DX[k], r = DY[k] + 3;
+        unsigned x;
+        if (dx == 0) x = w[r][1];
+        else if (dx > 0) x = __byte_perm(w[r][1], w[r][2], 0x3210 + 0x1111 * dx);
+        else x = __byte_perm(w[r][0], w[r][1], 0x3210 + 0x1111 * (4 + dx));
+        pe[k] = __byte_perm(x, 0, 0x4240);  // pixels 0 and 2 as u16x2
+        po[k] = __byte_perm(x, 0, 0x4341);  // pixels 1 and 3
+    }
+    const unsigned ve = __byte_perm(w[3][1], 0, 0x4240), vo = __byte_perm(w[3][1], 0, 0x4341);
+    unsigned res[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const unsigned* p = half ? po : pe;
+        const unsigned v = half ? vo : ve;
+        unsigned mx3[16], mn3[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            mx3[k] = __vimax3_u16x2(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
+            mn3[k] = __vimin3_u16x2(p[k], p[(k + 1) & 15], p[(k + 2) & 15]);
+        }
+        unsigned mx9[16], mn9[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            mx9[k] = __vimax3_u16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]);
+            mn9[k] = __vimin3_u16x2(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]);
+        }
+        // a = min over arcs of (max over the arc), b = max over arcs of (min over the arc)
+        unsigned a = __vimin3_u16x2(mx9[0], mx9[1], mx9[2]), b = __vimax3_u16x2(mn9[0], mn9[1], mn9[2]);
+#pragma unroll
+        for (int k = 3; k < 15; k += 2) {
+            a = __vimin3_u16x2(a, mx9[k], mx9[k + 1]);
+            b = __vimax3_u16x2(b, mn9[k], mn9[k + 1]);
+        }
+        a = __vminu2(a, mx9[15]);
+        b = __vmaxu2(b, mn9[15]);
+        const unsigned dark = __vsub2(v, a), bright = __vsub2(b, v);       // signed 16-bit lanes, |.| <= 255
+        const unsigned m = __vimax_s16x2_relu(dark, bright);               // max(dark, bright, 0)
+        res[half] = __viaddmax_s16x2_relu(m, neg_tlow2, 0u);               // max(m - t_low, 0)
+    }
+    return __byte_perm(res[0], res[1], 0x6240);  // bytes: px0, px1, px2, px3
+}
+
+constexpr int kFastThreads = 256;
+
+__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ Geom g, Images im, const CellDesc* __restrict__ cells,
+                                                                  const unsigned char* __restrict__ mask, unsigned long long mask_pitch,
+                                                                  unsigned long long* __restrict__ grid) {
+    // tile column c holds cell column c - 1 (so the first candidate column, lx = 3, is 4-byte aligned); pitch 80
+    __shared__ __align__(16) unsigned char tile[(kTileMax + 2) * kTilePitch];
+    __shared__ __align__(16) unsigned char mmap[(kTileMax + 2) * kTilePitch];
     __shared__ int skip;
 
     const CellDesc cd = cells[blockIdx.x];
@@ -172,7 +227,6 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
     const int tid = threadIdx.x;
 
     if (tid == 0) {
-        q_count = 0;
         int s = 0;
         if (mask) {  // orb_extractor.cc:219-225: skip the cell if one of its corners is masked
             const unsigned max_x = cd.min_x + cw, max_y = cd.min_y + ch;
@@ -184,110 +238,115 @@ __global__ void __launch_bounds__(256) fast_cells_kernel(const __grid_constant__
     int pitch;
     const unsigned char* src = level_ptr(im, g, level, frame, &pitch);
     src += (size_t)cd.min_y * pitch + cd.min_x;
-    for (int idx = tid; idx < ch * kTilePitch; idx += blockDim.x) {
-        const int y = idx / kTilePitch, x = idx - y * kTilePitch;
-        tile[idx] = (x < cw) ? src[(size_t)y * pitch + x] : 0;
-        mmap[idx] = 0;
+    // rows 0..ch-1 of the cell -> tile rows 0..ch-1; two extra zero rows keep the 4-row groups in bounds
+    for (int idx = tid; idx < (kTileMax + 2) * (kTilePitch / 4); idx += kFastThreads) {
+        const int y = idx / (kTilePitch / 4), c4 = (idx - y * (kTilePitch / 4)) * 4;
+        unsigned v = 0;
+        if (y < ch) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int x = c4 + b - 1;  // cell column
+                if (x >= 0 && x < cw) v |= (unsigned)src[(size_t)y * pitch + x] << (8 * b);
+            }
+        }
+        reinterpret_cast<unsigned*>(tile)[idx] = v;
+        reinterpret_cast<unsigned*>(mmap)[idx] = 0u;
     }
     __syncthreads();
     if (skip) return;
 
     const int t_low = min(g.ini_thr, g.min_thr);
-    const int ccw = cw - 6, cch = ch - 6;  // candidate region x in [3, w-4], y in [3, h-4]
-    // phase A: corner test at the lower threshold with 16-bit brighter/darker masks
-    for (int idx = tid; idx < ccw * cch; idx += blockDim.x) {
-        const int ly = 3 + idx / ccw, lx = 3 + idx % ccw;
-        const unsigned char* c = tile + ly * kTilePitch + lx;
-        const int v = c[0], hi = v + t_low, lo = v - t_low;
-        unsigned br = 0, dk = 0;
+    const unsigned neg_tlow2 = (unsigned)((-t_low) & 0xFFFF) * 0x10001u;
+    // phase 1: score map.  thread = (word column wq, group of 4 rows); candidate columns lx in [3, cw-4] <=> tile column lx+1
+    {
+        const int wq = tid & 15, rg = tid >> 4;       // 16 word columns x 16 row groups
+        const int c0 = 4 + 4 * wq;                    // tile column of the first pixel of the word
+        const int lx0 = c0 - 1;                       // its cell column
+        const int y0 = 3 + 4 * rg;                    // first candidate row of the group
+        if (lx0 <= cw - 4 && y0 <= ch - 4) {
+            unsigned w[10][3];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int p = c[FAST_OFF(k, kTilePitch)];
-            br |= (unsigned)(p > hi) << k;
-            dk |= (unsigned)(p < lo) << k;
-        }
-        if (has_run9(br) || has_run9(dk)) {
-            const int q = atomicAdd(&q_count, 1);
-            queue[q] = (unsigned short)(ly * kTilePitch + lx);
+            for (int r = 0; r < 10; ++r) {
+                const int y = y0 - 3 + r;  // <= ch + 2 < kTileMax + 2
+                const unsigned* row = reinterpret_cast<const unsigned*>(tile + y * kTilePitch + c0 - 4);
+                w[r][0] = row[0];
+                w[r][1] = row[1];
+                w[r][2] = row[2];
+            }
+            // pixels of this word that are candidates: lx0 + b <= cw - 4
+            const int nvalid = min(4, cw - 3 - lx0);
+            const unsigned keep = (nvalid >= 4) ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int y = y0 + i;
+                if (y <= ch - 4) {
+                    unsigned ww[7][3];
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) {
+                        ww[r][0] = w[i + r][0];
+                        ww[r][1] = w[i + r][1];
+                        ww[r][2] = w[i + r][2];
+                    }
+                    *reinterpret_cast<unsigned*>(mmap + y * kTilePitch + c0) = fast_m4(ww, neg_tlow2) & keep;
+                }
+            }
         }
     }
     __syncthreads();
-    // phase B: exact m = max over 9-arcs of min(v - p) / min(p - v) for the corners only (cornerScore<16> + 1)
-    const int nq = q_count;
-    for (int qi = tid; qi < nq; qi += blockDim.x) {
-        const int pos = queue[qi];
-        const unsigned char* c = tile + pos;
-        const int v = c[0];
-        // d[k] = (v - p_k) + 255 in [0, 510]: keeps everything non-negative.  (ptxas 12.9 for sm_100a fuses
-        // max(a, -b) into VIMNMX3 and DROPS the negation -- measured on the B200, see DESIGN.md "toolchain hazards" --
-        // so the brighter-arc term is formed as 510 - min_k(max-arc) once, never as a negated max.)
-        int d[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) d[k] = v + 255 - (int)c[FAST_OFF(k, kTilePitch)];
-        int mn[16], mx[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            mn[k] = min(d[k], d[(k + 1) & 15]);
-            mx[k] = max(d[k], d[(k + 1) & 15]);
-        }
-        int mn4[16], mx4[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            mn4[k] = min(mn[k], mn[(k + 2) & 15]);
-            mx4[k] = max(mx[k], mx[(k + 2) & 15]);
-        }
-        int best_dark = 0, best_bright = 510;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int a = min(min(mn4[k], mn4[(k + 4) & 15]), d[(k + 8) & 15]);   // min over d[k..k+8]
-            const int b = max(max(mx4[k], mx4[(k + 4) & 15]), d[(k + 8) & 15]);   // max over d[k..k+8]
-            best_dark = max(best_dark, a);
-            best_bright = min(best_bright, b);
-        }
-        // darker arcs: min(v-p) = best_dark - 255; brighter arcs: min(p-v) = 255 - best_bright
-        const int best = max(max(best_dark, 510 - best_bright) - 255, 0);
-        mmap[pos] = (unsigned char)min(best, 255);
-    }
-    __syncthreads();
-    // phase C: strict 3x3 local maximum of m (threshold independent), then the per-cell threshold choice
+    // phase 2: strict 3x3 local maximum of m (threshold independent), per-cell threshold choice
     //          (orb_extractor.cc:228-235: retry the whole cell at min_fast_thr only if it is empty at ini_fast_thr)
-    unsigned keep_bits = 0;  // one bit per loop iteration of this thread
+    const int ini_rel = g.ini_thr - t_low, min_rel = g.min_thr - t_low;  // thresholds relative to the stored m - t_low
+    unsigned long long kept = 0;  // up to 5 words x 4 pixels per thread, one bit each
     bool any_ini = false;
+    const int n_words = (kTileMax - 6) * 16;  // 64 candidate rows x 16 words
     {
         int it = 0;
-        for (int idx = tid; idx < ccw * cch; idx += blockDim.x, ++it) {
-            const int ly = 3 + idx / ccw, lx = 3 + idx % ccw;
-            const unsigned char* p = mmap + ly * kTilePitch + lx;
-            const int mv = p[0];
-            if (mv < 2) continue;
-            // neighbours outside the candidate region are non-candidates (score 0): rows/cols 2 and w-3/h-3 hold 0
-            const bool is_max = mv > p[-1] && mv > p[1] && mv > p[-kTilePitch - 1] && mv > p[-kTilePitch] && mv > p[-kTilePitch + 1]
-                                && mv > p[kTilePitch - 1] && mv > p[kTilePitch] && mv > p[kTilePitch + 1];
-            if (is_max) {
-                keep_bits |= 1u << it;
-                any_ini |= (mv > g.ini_thr);
+        for (int idx = tid; idx < n_words; idx += kFastThreads, ++it) {
+            const int y = 3 + (idx >> 4), c0 = 4 + 4 * (idx & 15);
+            if (y > ch - 4) continue;
+            const unsigned word = *reinterpret_cast<const unsigned*>(mmap + y * kTilePitch + c0);
+            if (word == 0u) continue;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int mv = (word >> (8 * b)) & 0xFF;
+                // stored value is m - t_low; a keypoint needs score m - 1 >= 1
+                if (mv == 0 || mv + t_low < 2) continue;
+                const unsigned char* p = mmap + y * kTilePitch + c0 + b;
+                const bool is_max = mv > p[-1] && mv > p[1] && mv > p[-kTilePitch - 1] && mv > p[-kTilePitch] && mv > p[-kTilePitch + 1]
+                                    && mv > p[kTilePitch - 1] && mv > p[kTilePitch] && mv > p[kTilePitch + 1];
+                if (is_max) {
+                    kept |= 1ull << (it * 4 + b);
+                    any_ini |= (mv > ini_rel);
+                }
             }
         }
     }
     const int cell_has_ini = __syncthreads_or(any_ini);
-    const int thr = cell_has_ini ? g.ini_thr : g.min_thr;
-    // phase D: mask test per keypoint, selection-grid cell, ordered arg-max via 64-bit atomicMax
-    {
+    const int thr_rel = cell_has_ini ? ini_rel : min_rel;
+    // phase 3: mask test per keypoint, selection-grid cell, ordered arg-max via 64-bit atomicMax
+    if (kept) {
         int it = 0;
-        for (int idx = tid; idx < ccw * cch; idx += blockDim.x, ++it) {
-            if (!((keep_bits >> it) & 1u)) continue;
-            const int ly = 3 + idx / ccw, lx = 3 + idx % ccw;
-            const int mv = mmap[ly * kTilePitch + lx];
-            if (mv <= thr) continue;
-            // keypt.pt += (j*64, i*64) (orb_extractor.cc:241-244): coordinates relative to the (19,19) border origin
-            const int px = lx + cd.j * kCell, py = ly + cd.i * kCell;
-            if (mask && mask_zero(mask, mask_pitch, (unsigned)(kBorder + py), (unsigned)(kBorder + px), L.sf)) continue;
-            const unsigned ix = (unsigned)((double)(float)px / L.delta_x);  // orb_extractor.cc:303-305
-            const unsigned iy = (unsigned)((double)(float)py / L.delta_y);
-            const unsigned cell = ix + iy * (unsigned)L.nx;
-            const unsigned order = ((unsigned)(cd.i * L.ncols + cd.j) << 14) | ((unsigned)ly << 7) | (unsigned)lx;
-            const unsigned long long val = ((unsigned long long)mv << 32) | (unsigned long long)(0xFFFFFFFFu - order);
-            atomicMax(grid + (size_t)frame * g.grid_cells + L.grid_base + cell, val);
+        for (int idx = tid; idx < n_words; idx += kFastThreads, ++it) {
+            const unsigned bits = (unsigned)(kept >> (it * 4)) & 0xFu;
+            if (!bits) continue;
+            const int y = 3 + (idx >> 4), c0 = 4 + 4 * (idx & 15);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (!((bits >> b) & 1u)) continue;
+                const int mrel = mmap[y * kTilePitch + c0 + b];
+                if (mrel <= thr_rel) continue;
+                const int mv = mrel + t_low;
+                const int lx = c0 + b - 1, ly = y;
+                // keypt.pt += (j*64, i*64) (orb_extractor.cc:241-244): coordinates relative to the (19,19) border origin
+                const int px = lx + cd.j * kCell, py = ly + cd.i * kCell;
+                if (mask && mask_zero(mask, mask_pitch, (unsigned)(kBorder + py), (unsigned)(kBorder + px), L.sf)) continue;
+                const unsigned ix = (unsigned)((double)(float)px / L.delta_x);  // orb_extractor.cc:303-305
+                const unsigned iy = (unsigned)((double)(float)py / L.delta_y);
+                const unsigned cell = ix + iy * (unsigned)L.nx;
+                const unsigned order = ((unsigned)(cd.i * L.ncols + cd.j) << 14) | ((unsigned)ly << 7) | (unsigned)lx;
+                const unsigned long long val = ((unsigned long long)mv << 32) | (unsigned long long)(0xFFFFFFFFu - order);
+                atomicMax(grid + (size_t)frame * g.grid_cells + L.grid_base + cell, val);
+            }
         }
     }
 }
@@ -355,6 +414,8 @@ __global__ void __launch_bounds__(256) select_kernel(const __grid_constant__ Geo
 //     16-bit horizontal pass, Q16.16 vertical pass, round to nearest.  One block per 64x32 output tile.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kBlurTW = 64, kBlurTH = 32;
+constexpr int kBlurInW = kBlurTW + 8;     // input tile bytes per row: columns x0-4 .. x0+67 (18 aligned words)
+constexpr int kBlurInH = kBlurTH + 6;     // rows y0-3 .. y0+34
 
 __device__ __forceinline__ int reflect101(int i, int n) {
     if (i < 0) i = -i;
@@ -362,44 +423,95 @@ __device__ __forceinline__ int reflect101(int i, int n) {
     return min(max(i, 0), n - 1);  // (levels narrower than 4 px never carry keypoints)
 }
 
+// Horizontal 7-tap pass for 4 consecutive outputs with two dp4a each: taps {18,34,48,56} on bytes c-3..c and
+// {48,34,18,0} on bytes c+1..c+4.  w0..w2 are the aligned words holding tile bytes 4q .. 4q+11 (output c = 4q+k <-> byte 4q+k+4).
+__device__ __forceinline__ void blur_h4(unsigned w0, unsigned w1, unsigned w2, unsigned (&h)[4]) {
+    constexpr unsigned TA = 18u | (34u << 8) | (48u << 16) | (56u << 24);
+    constexpr unsigned TB = 48u | (34u << 8) | (18u << 16);
+    h[0] = __dp4a(__byte_perm(w0, w1, 0x4321), TA, __dp4a(__byte_perm(w1, w2, 0x4321), TB, 0u));
+    h[1] = __dp4a(__byte_perm(w0, w1, 0x5432), TA, __dp4a(__byte_perm(w1, w2, 0x5432), TB, 0u));
+    h[2] = __dp4a(__byte_perm(w0, w1, 0x6543), TA, __dp4a(__byte_perm(w1, w2, 0x6543), TB, 0u));
+    h[3] = __dp4a(w1, TA, __dp4a(w2, TB, 0u));
+}
+
 __global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geom g, Images im, const BlurTile* __restrict__ tiles,
                                                    unsigned char* __restrict__ blurred, unsigned long long blur_fstride) {
-    __shared__ unsigned char in[(kBlurTH + 6) * (kBlurTW + 8)];
-    __shared__ unsigned short hp[(kBlurTH + 6) * kBlurTW];
+    __shared__ __align__(16) unsigned in[kBlurInH * (kBlurInW / 4)];          // 38 x 18 words
+    __shared__ __align__(16) unsigned hp[(kBlurInH / 2) * kBlurTW];           // 19 pair-rows x 64 columns: (H[2r][c], H[2r+1][c]) as u16x2
+    __shared__ __align__(16) unsigned char outb[kBlurTH * kBlurTW];
     const BlurTile bt = tiles[blockIdx.x];
     const int frame = blockIdx.y, level = bt.level;
     const LevelGeom& L = g.lv[level];
     int pitch;
     const unsigned char* src = level_ptr(im, g, level, frame, &pitch);
     const int x0 = bt.tx * kBlurTW, y0 = bt.ty * kBlurTH;
-    constexpr int IW = kBlurTW + 8;  // 6 halo columns + 2 pad
-    for (int idx = threadIdx.x; idx < (kBlurTH + 6) * (kBlurTW + 6); idx += blockDim.x) {
-        const int r = idx / (kBlurTW + 6), c = idx - r * (kBlurTW + 6);
-        const int sy = reflect101(y0 + r - 3, L.h), sx = reflect101(x0 + c - 3, L.w);
-        in[r * IW + c] = (sy >= 0 && sy < L.h && sx >= 0 && sx < L.w) ? src[(size_t)sy * pitch + sx] : 0;
+    const int tid = threadIdx.x;
+    // ---- input tile: aligned 32-bit loads for interior tiles, per-byte REFLECT_101 for tiles touching the border
+    const bool interior = x0 >= 4 && x0 + kBlurTW + 4 <= L.w && y0 >= 3 && y0 + kBlurTH + 3 <= L.h && ((pitch & 3) == 0)
+                          && ((reinterpret_cast<unsigned long long>(src) & 3ull) == 0);
+    if (interior) {
+        for (int idx = tid; idx < kBlurInH * (kBlurInW / 4); idx += 256) {
+            const int r = idx / (kBlurInW / 4), q = idx - r * (kBlurInW / 4);
+            in[idx] = *reinterpret_cast<const unsigned*>(src + (size_t)(y0 - 3 + r) * pitch + x0 - 4 + 4 * q);
+        }
+    } else {
+        for (int idx = tid; idx < kBlurInH * (kBlurInW / 4); idx += 256) {
+            const int r = idx / (kBlurInW / 4), q = idx - r * (kBlurInW / 4);
+            const int sy = reflect101(y0 - 3 + r, L.h);
+            unsigned v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v |= (unsigned)src[(size_t)sy * pitch + reflect101(x0 - 4 + 4 * q + b, L.w)] << (8 * b);
+            in[idx] = v;
+        }
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < (kBlurTH + 6) * kBlurTW; idx += blockDim.x) {
-        const int r = idx / kBlurTW, c = idx - r * kBlurTW;
-        const unsigned char* p = in + r * IW + c;
-        hp[idx] = (unsigned short)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    // ---- horizontal pass (exact: sum <= 65280), two rows x four columns per item, stored as vertical u16 pairs
+    for (int idx = tid; idx < (kBlurInH / 2) * (kBlurTW / 4); idx += 256) {
+        const int pr = idx / (kBlurTW / 4), q = idx - pr * (kBlurTW / 4);
+        const unsigned* r0 = in + (2 * pr) * (kBlurInW / 4) + q;
+        const unsigned* r1 = r0 + (kBlurInW / 4);
+        unsigned h0[4], h1[4];
+        blur_h4(r0[0], r0[1], r0[2], h0);
+        blur_h4(r1[0], r1[1], r1[2], h1);
+        uint4 o;
+        o.x = h0[0] | (h1[0] << 16);
+        o.y = h0[1] | (h1[1] << 16);
+        o.z = h0[2] | (h1[2] << 16);
+        o.w = h0[3] | (h1[3] << 16);
+        *reinterpret_cast<uint4*>(hp + pr * kBlurTW + 4 * q) = o;
+    }
+    __syncthreads();
+    // ---- vertical pass: Q16.16 accumulate with dp2a on the vertical pairs, round to nearest, saturate
+    {
+        // even output row y (tile rows y..y+6 = pairs y/2 .. y/2+3): taps (18,34)(48,56)(48,34)(18,0)
+        // odd  output row y (tile rows y-1..y+6, tap 0 first):        taps (0,18)(34,48)(56,48)(34,18)
+        constexpr unsigned E01 = 18u | (34u << 8) | (48u << 16) | (56u << 24), E23 = 48u | (34u << 8) | (18u << 16);
+        constexpr unsigned O01 = (18u << 8) | (34u << 16) | (48u << 24), O23 = 56u | (48u << 8) | (34u << 16) | (18u << 24);
+        const int c = tid & 63, rb = tid >> 6;  // column, block of 8 output rows
+        unsigned p[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) p[k] = hp[(4 * rb + k) * kBlurTW + c];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            unsigned e = __dp2a_lo(p[i], E01, 0u);
+            e = __dp2a_hi(p[i + 1], E01, e);
+            e = __dp2a_lo(p[i + 2], E23, e);
+            e = __dp2a_hi(p[i + 3], E23, e);
+            unsigned o = __dp2a_lo(p[i], O01, 0u);
+            o = __dp2a_hi(p[i + 1], O01, o);
+            o = __dp2a_lo(p[i + 2], O23, o);
+            o = __dp2a_hi(p[i + 3], O23, o);
+            outb[(8 * rb + 2 * i) * kBlurTW + c] = (unsigned char)min((e + 32768u) >> 16, 255u);
+            outb[(8 * rb + 2 * i + 1) * kBlurTW + c] = (unsigned char)min((o + 32768u) >> 16, 255u);
+        }
     }
     __syncthreads();
     unsigned char* dst = blurred + (size_t)frame * blur_fstride + L.offset;
-    for (int idx = threadIdx.x; idx < kBlurTH * kBlurTW / 4; idx += blockDim.x) {
+    for (int idx = tid; idx < kBlurTH * kBlurTW / 4; idx += 256) {
         const int r = idx / (kBlurTW / 4), c4 = (idx - r * (kBlurTW / 4)) * 4;
         const int y = y0 + r;
         if (y >= L.h || x0 + c4 >= L.pitch) continue;
-        unsigned out = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const unsigned short* q = hp + r * kBlurTW + c4 + k;
-            unsigned acc = 18u * (q[0] + q[6 * kBlurTW]) + 34u * (q[kBlurTW] + q[5 * kBlurTW]) + 48u * (q[2 * kBlurTW] + q[4 * kBlurTW])
-                           + 56u * q[3 * kBlurTW];
-            acc = (acc + 32768u) >> 16;
-            out |= min(acc, 255u) << (8 * k);
-        }
-        *reinterpret_cast<unsigned*>(dst + (size_t)y * L.pitch + x0 + c4) = out;
+        *reinterpret_cast<unsigned*>(dst + (size_t)y * L.pitch + x0 + c4) = *reinterpret_cast<const unsigned*>(outb + r * kBlurTW + c4);
     }
 }
 
