@@ -94,6 +94,41 @@ __device__ __forceinline__ const unsigned char* level_ptr(const Images& im, cons
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// TMA: one 3-D tensor map (x, y, frame) per pyramid level; a FAST cell tile is ONE bulk-tensor copy, out-of-image bytes are
+// zero-filled by the hardware.  (cp.async.bulk.tensor -> UTMALDG; completion through an mbarrier transaction count.)
+// ---------------------------------------------------------------------------------------------------------------
+struct TmapSet {
+    CUtensorMap m[kMaxLevels];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");  // make the init visible to the async proxy
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int x, int y, int z, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K1: cv::resize(INTER_LINEAR) level l-1 -> l, fixed point (OpenCV resize.cpp HResizeLinear/VResizeLinear, 11 bits)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kRzTW = 128, kRzTH = 16;             // output tile: warp w produces rows 2w, 2w+1; a lane produces 4 columns
@@ -264,13 +299,22 @@ __device__ __forceinline__ unsigned fast_m4(const unsigned (&w)[7][3], unsigned 
 }
 
 constexpr int kFastThreads = 256;
+constexpr int kTileRows = kTileMax + 2;  // 72
+constexpr int kRawPitch = 96;            // TMA box width: the box must start on a 16-byte boundary of the row (x0 = 16 + 64 j),
+                                         // i.e. 2 bytes left of the tile origin (x = 18 + 64 j), and cover 82 bytes
 
-__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ Geom g, Images im, const CellDesc* __restrict__ cells,
-                                                                  const unsigned char* __restrict__ mask, unsigned long long mask_pitch,
-                                                                  unsigned long long* __restrict__ grid) {
+// kUseTma: the tile arrives through the level's tensor map (needs a 16-byte aligned base and 16-byte multiples as
+// strides, always true for the pyramid arena; checked on the host for the caller's level-0 frames).  Otherwise the same
+// tile is assembled with ordinary loads.
+template <bool kUseTma>
+__global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ Geom g, const __grid_constant__ TmapSet tmaps, Images im,
+                                                                  const CellDesc* __restrict__ cells, const unsigned char* __restrict__ mask,
+                                                                  unsigned long long mask_pitch, unsigned long long* __restrict__ grid) {
     // tile column c holds cell column c - 1 (so the first candidate column, lx = 3, is 4-byte aligned); pitch 80
-    __shared__ __align__(16) unsigned char tile[(kTileMax + 2) * kTilePitch];
-    __shared__ __align__(16) unsigned char mmap[(kTileMax + 2) * kTilePitch];
+    __shared__ __align__(16) unsigned char tile[kTileRows * kTilePitch];
+    __shared__ __align__(16) unsigned char mmap[kTileRows * kTilePitch];
+    __shared__ __align__(128) unsigned char raw[kUseTma ? kTileRows * kRawPitch : 16];  // TMA landing zone
+    __shared__ __align__(8) unsigned long long tma_bar;
     __shared__ int skip;
 
     const CellDesc cd = cells[blockIdx.x];
@@ -289,24 +333,44 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
         }
         skip = s;
     }
-    int pitch;
-    const unsigned char* src = level_ptr(im, g, level, frame, &pitch);
-    src += (size_t)cd.min_y * pitch + cd.min_x;
-    // rows 0..ch-1 of the cell -> tile rows 0..ch-1; two extra zero rows keep the 4-row groups in bounds
-    for (int idx = tid; idx < (kTileMax + 2) * (kTilePitch / 4); idx += kFastThreads) {
-        const int y = idx / (kTilePitch / 4), c4 = (idx - y * (kTilePitch / 4)) * 4;
-        unsigned v = 0;
-        if (y < ch) {
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int x = c4 + b - 1;  // cell column
-                if (x >= 0 && x < cw) v |= (unsigned)src[(size_t)y * pitch + x] << (8 * b);
-            }
+    if constexpr (kUseTma) {
+        // one elected thread: arm the mbarrier with the tile's byte count and issue the bulk-tensor copy of the 80 x 72 box
+        // whose origin is (min_x - 1, min_y, frame); bytes outside the image come back as zeros
+        if (tid == 0) {
+            mbar_init(&tma_bar, 1);
+            mbar_expect_tx(&tma_bar, kTileRows * kRawPitch);
+            tma_load_3d(raw, &tmaps.m[level], (int)cd.min_x - 3, (int)cd.min_y, frame, &tma_bar);  // min_x - 3 = 16 + 64 j
         }
-        reinterpret_cast<unsigned*>(tile)[idx] = v;
-        reinterpret_cast<unsigned*>(mmap)[idx] = 0u;
+        __syncthreads();  // barrier initialised (and skip written) before anybody polls it
+        mbar_wait(&tma_bar, 0);
+        // re-pitch into the compute tile, shifting by the 2 alignment bytes: tile byte c = raw byte c + 2
+        for (int idx = tid; idx < kTileRows * (kTilePitch / 4); idx += kFastThreads) {
+            const int y = idx / (kTilePitch / 4), q = idx - y * (kTilePitch / 4);
+            const unsigned* rw = reinterpret_cast<const unsigned*>(raw + y * kRawPitch) + q;
+            reinterpret_cast<unsigned*>(tile)[idx] = __funnelshift_r(rw[0], rw[1], 16);
+            reinterpret_cast<unsigned*>(mmap)[idx] = 0u;
+        }
+        __syncthreads();
+    } else {
+        int pitch;
+        const unsigned char* src = level_ptr(im, g, level, frame, &pitch);
+        src += (size_t)cd.min_y * pitch + cd.min_x;
+        // rows 0..ch-1 of the cell -> tile rows 0..ch-1; two extra zero rows keep the 4-row groups in bounds
+        for (int idx = tid; idx < kTileRows * (kTilePitch / 4); idx += kFastThreads) {
+            const int y = idx / (kTilePitch / 4), c4 = (idx - y * (kTilePitch / 4)) * 4;
+            unsigned v = 0;
+            if (y < ch) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const int x = c4 + b - 1;  // cell column
+                    if (x >= 0 && x < cw) v |= (unsigned)src[(size_t)y * pitch + x] << (8 * b);
+                }
+            }
+            reinterpret_cast<unsigned*>(tile)[idx] = v;
+            reinterpret_cast<unsigned*>(mmap)[idx] = 0u;
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (skip) return;
 
     const int t_low = min(g.ini_thr, g.min_thr);
@@ -714,6 +778,38 @@ static inline int floor_to_int(float v) {
     return i - (v < (float)i);
 }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &p, 12000, cudaEnableDefault, &q) == cudaSuccess
+            && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// 3-D u8 tensor map (x, y, frame) with a 96 x 72 x 1 box; false if the buffer does not meet TMA's alignment rules
+// (16-byte aligned base and strides; the kernel additionally keeps the box origin x on a 16-byte boundary)
+static bool make_level_tmap(CUtensorMap* out, const void* base, int w, int h, size_t pitch, size_t fstride, int frames) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    if ((reinterpret_cast<unsigned long long>(base) & 15ull) || (pitch & 15) || (frames > 1 && (fstride & 15)) || w < 1 || h < 1) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)std::max(frames, 1)};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)(frames > 1 ? fstride : pitch * (size_t)h + ((16 - (pitch * (size_t)h) % 16) % 16))};
+    const cuuint32_t box[3] = {(cuuint32_t)kRawPitch, (cuuint32_t)kTileRows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
+           == CUDA_SUCCESS;
+}
+
 struct Extractor {
     b200_orb_params_t prm{};
     std::vector<float> mask_rects;
@@ -740,6 +836,9 @@ struct Extractor {
     int* h_counts = nullptr;  // pinned
     int last_batch = 0;
     bool rect_mask_ready = false;
+    TmapSet tmaps{};           // levels >= 1 are encoded once per configuration, level 0 per call (caller's pointer)
+    bool tmaps_ok = false, last_used_tma = false;
+    int tmap_frames = 0;
     // caller-owned result buffers (b200_orb_bind_outputs); when null the instance's own arenas are used
     b200_keypoint_t* out_kps = nullptr;
     unsigned char* out_descs = nullptr;
@@ -916,6 +1015,10 @@ struct Extractor {
             rect_mask_ready = true;
         }
         B200_CUDA(cudaStreamSynchronize(stream));
+        tmaps_ok = true;
+        tmap_frames = batch;
+        for (int l = 1; l < nl && tmaps_ok; ++l)
+            tmaps_ok = make_level_tmap(&tmaps.m[l], d_pyr + geom.lv[l].offset, geom.lv[l].w, geom.lv[l].h, geom.lv[l].pitch, pyr_fstride, batch);
         width = w;
         height = h;
         batch_cap = batch;
@@ -939,7 +1042,13 @@ struct Extractor {
         }
         if (timing) B200_CUDA(cudaEventRecord(ev[1], stream));
         B200_CUDA(cudaMemsetAsync(d_grid, 0, sizeof(unsigned long long) * (size_t)raw_stride * batch, stream));
-        if (n_cells) fast_cells_kernel<<<dim3(n_cells, batch), 256, 0, stream>>>(geom, im, d_cells, mask, mpitch, d_grid);
+        if (n_cells) {
+            // level 0 lives in the caller's buffer: encode its tensor map for this call (a host-side table fill, no GPU work)
+            const bool tma = tmaps_ok && make_level_tmap(&tmaps.m[0], d_images, geom.lv[0].w, geom.lv[0].h, pitch, fstride, batch);
+            if (tma) fast_cells_kernel<true><<<dim3(n_cells, batch), kFastThreads, 0, stream>>>(geom, tmaps, im, d_cells, mask, mpitch, d_grid);
+            else fast_cells_kernel<false><<<dim3(n_cells, batch), kFastThreads, 0, stream>>>(geom, tmaps, im, d_cells, mask, mpitch, d_grid);
+            last_used_tma = tma;
+        }
         if (timing) B200_CUDA(cudaEventRecord(ev[2], stream));
         if (out_kps && out_stride < geom.grid_cells) {
             set_error("bound output stride %d is smaller than the keypoint upper bound %d", out_stride, geom.grid_cells);

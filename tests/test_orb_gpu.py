@@ -174,3 +174,25 @@ def test_determinism_and_idempotence(mods):
 def ex_max(ex, w, h):
     from stella_vslam_b200._lib import lib
     return lib().b200_orb_max_keypoints(ex._h, w, h)
+
+
+def test_device_frames_unaligned_pitch_uses_non_tma_path(mods):
+    """Caller frames whose pitch is not a multiple of 16 cannot be described by a tensor map: the extractor falls back to
+    ordinary loads for level 0 and must produce the same bits."""
+    import ctypes as C
+
+    import torch
+
+    O, feature, synth = mods
+    from stella_vslam_b200._lib import KP_DTYPE, check, lib
+    L = lib()
+    w, h = 333, 217
+    img = synth.make_frame(w, h, seed=4)
+    ex = feature.orb_extractor(feature.orb_params(), 300)
+    d = torch.from_numpy(img).cuda()                     # pitch 333
+    check(L.b200_orb_extract_device(ex._h, C.c_void_p(d.data_ptr()), w, h, w, w * h, 1, None, 0))
+    cap = L.b200_orb_max_keypoints(ex._h, w, h)
+    kps, desc, cnt = np.zeros(cap, KP_DTYPE), np.zeros((cap, 32), np.uint8), np.zeros(1, np.int32)
+    check(L.b200_orb_fetch(ex._h, kps.ctypes.data_as(C.c_void_p), desc.ctypes.data_as(C.c_void_p), cap, cnt.ctypes.data_as(C.c_void_p)))
+    ref = O.orb_extract(img, min_area=300)
+    assert_same(kps[:cnt[0]], desc[:cnt[0]], ref)
