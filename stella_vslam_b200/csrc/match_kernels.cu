@@ -23,7 +23,7 @@ namespace b200 {
 namespace match {
 
 constexpr int kTopK = 8;            // candidates kept per keyframe keypoint
-constexpr int kRowsPerBlock = 128;  // one keyframe keypoint per thread
+constexpr int kRowsPerBlock = 64;   // one keyframe keypoint per thread (small CTAs: a 2000-row problem still yields 32 of them)
 constexpr int kChunk = 256;         // frame descriptors staged per shared-memory tile (8 KB)
 constexpr unsigned kInfKey = 0xFFFFFFFFu;
 constexpr int kThrLow = 50;         // HAMMING_DIST_THR_LOW  (match/base.h:15)
@@ -141,7 +141,7 @@ __device__ __forceinline__ unsigned warp_min(unsigned v) {
 }
 
 // exact best/second over the live (not taken, orientation-gated) frame keypoints: the reference's inner loop
-__device__ void exact_row(const uint4* desc1, const Side& S1, int b1, int n1, const unsigned* taken, uint4 q0, uint4 q1, float qa,
+__device__ void exact_row(const uint4* desc1, const Side& S1, int b1, int n1, const volatile unsigned* taken, uint4 q0, uint4 q1, float qa,
                           int check_orientation, int lane, unsigned* best_key, unsigned* second_dist) {
     unsigned k1 = kInfKey, k2 = kInfKey;  // two smallest keys seen by this lane
     for (int i = lane; i < n1; i += 32) {
@@ -162,82 +162,125 @@ __device__ void exact_row(const uint4* desc1, const Side& S1, int b1, int n1, co
     *second_dist = (s == kInfKey) ? (unsigned)kMaxDist : key_dist(s);
 }
 
+// Decision of one keyframe keypoint from its sorted candidate list against the current `taken` set.
+//   returns 0: decided, no match; 1: decided, match with key *best; 2: undecidable from the list (exact row scan needed)
+__device__ __forceinline__ int decide_row(const unsigned (&keys)[kTopK], const volatile unsigned* taken, float lowe_ratio, unsigned* best) {
+    unsigned best_key = kInfKey, second_dist = kMaxDist;
+    int n_live = 0;
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k) {
+        const unsigned key = keys[k];
+        if (key == kInfKey) continue;
+        const unsigned i1 = key_idx(key);
+        if ((taken[i1 >> 5] >> (i1 & 31)) & 1u) continue;
+        if (n_live == 0) best_key = key;
+        else if (n_live == 1) second_dist = key_dist(key);
+        ++n_live;
+    }
+    const bool full = keys[kTopK - 1] != kInfKey;  // unlisted candidates exist only if the list is full
+    const unsigned tail_dist = key_dist(keys[kTopK - 1]);  // every unlisted distance is >= this
+    if (full && n_live < 2) {
+        if (n_live == 1) {
+            // best is exact; the true second distance lies in [tail_dist, 256]
+            const unsigned bd = key_dist(best_key);
+            if (bd > (unsigned)kThrLow) return 0;
+            if (__fmul_rn(lowe_ratio, (float)tail_dist) < (float)bd) return 2;
+            second_dist = tail_dist;  // passes the ratio test even with the smallest possible second distance
+        } else {
+            // every listed candidate is taken: the best live distance is >= tail_dist
+            return (tail_dist > (unsigned)kThrLow) ? 0 : 2;
+        }
+    }
+    if (best_key == kInfKey) return 0;
+    const unsigned bd = key_dist(best_key);
+    // robust.cc:297-308: threshold, then Lowe ratio in float
+    if (bd > (unsigned)kThrLow || __fmul_rn(lowe_ratio, (float)second_dist) < (float)bd) return 0;
+    *best = best_key;
+    return 1;
+}
+
+// One warp per problem.  Rows (keyframe keypoints) are visited in batches of 32, one per lane.  Every lane decides its row
+// against the taken set as of the last commit; a lane's decision is final iff no earlier, not yet committed lane accepts a
+// frame keypoint that appears in its candidate list -- so the longest conflict-free prefix of the batch is committed at
+// once and the rest re-decided.  The result is identical to the reference's strictly sequential loop.
 __global__ void __launch_bounds__(32) resolve_kernel(Side S1, Side S2, const unsigned char* __restrict__ valid2,
                                                      const unsigned* __restrict__ lists, float lowe_ratio, int check_orientation,
                                                      int* __restrict__ matched, unsigned* __restrict__ taken_g, int taken_words,
                                                      int list_rows, int matched_stride, int pairs_stride,
-                                                     int* __restrict__ pairs_out, int* __restrict__ n_pairs) {
+                                                     int* __restrict__ pairs_out, int* __restrict__ n_pairs, int use_smem) {
     const uint4* __restrict__ desc1 = S1.desc;
     const uint4* __restrict__ desc2 = S2.desc;
+    extern __shared__ unsigned resolve_smem[];  // [taken_words] bitmap + [matched_stride] idx_1 -> idx_2 table when they fit
     const int p = blockIdx.x, lane = threadIdx.x;
     const int b1 = S1.off[p], n1 = S1.cnt[p];
     const int b2 = S2.off[p], n2 = S2.cnt[p];
-    unsigned* taken = taken_g + (size_t)p * taken_words;
-    int* m21 = matched + (size_t)p * matched_stride;
+    // the sequential state lives in shared memory (30-cycle instead of L2 latency on the critical path); very large frames fall
+    // back to the global scratch
+    unsigned* taken = use_smem ? resolve_smem : taken_g + (size_t)p * taken_words;
+    int* m21 = use_smem ? reinterpret_cast<int*>(resolve_smem + taken_words) : matched + (size_t)p * matched_stride;
     int* pairs = pairs_out + 2 * (size_t)p * pairs_stride;
     lists += (size_t)p * list_rows * kTopK;
     for (int i = lane; i < (n1 + 31) / 32; i += 32) taken[i] = 0u;
     for (int i = lane; i < n1; i += 32) m21[i] = -1;
     __syncwarp();
     const uint4* d1 = desc1 + (size_t)b1 * 2;
-    unsigned next_key = (lane < kTopK && n2 > 0) ? lists[lane] : kInfKey;
-    for (int r = 0; r < n2; ++r) {
-        const unsigned key = next_key;
-        if (r + 1 < n2 && lane < kTopK) next_key = lists[(size_t)(r + 1) * kTopK + lane];
-        if (valid2 && !valid2[b2 + r]) continue;  // robust.cc:255-262
-        // walk the sorted list, skipping taken frame keypoints
-        const bool listed = key != kInfKey;
-        bool live = false;
-        if (listed) {
-            const unsigned i1 = key_idx(key);
-            live = !((taken[i1 >> 5] >> (i1 & 31)) & 1u);
+    for (int base = 0; base < n2; base += 32) {
+        const int r = base + lane;
+        const bool has_row = r < n2 && (!valid2 || valid2[b2 + r]);  // robust.cc:255-262
+        unsigned keys[kTopK];
+        {
+            const uint4* lp = reinterpret_cast<const uint4*>(lists + (size_t)min(r, n2 - 1) * kTopK);
+            const uint4 k0 = lp[0], k1 = lp[1];
+            keys[0] = k0.x; keys[1] = k0.y; keys[2] = k0.z; keys[3] = k0.w;
+            keys[4] = k1.x; keys[5] = k1.y; keys[6] = k1.z; keys[7] = k1.w;
         }
-        const unsigned live_mask = __ballot_sync(0xFFFFFFFFu, live);
-        const unsigned listed_mask = __ballot_sync(0xFFFFFFFFu, listed);
-        const bool full = listed_mask == ((1u << kTopK) - 1u);  // unlisted candidates exist only if the list is full
-        const unsigned tail_dist = key_dist(__shfl_sync(0xFFFFFFFFu, key, kTopK - 1));  // every unlisted distance >= this
-        unsigned best_key = kInfKey, second_dist = kMaxDist;
-        bool decided = false, accept = false;
-        const int l1 = __ffs(live_mask) - 1;
-        const unsigned rest = live_mask & (live_mask - 1u);
-        const int l2 = __ffs(rest) - 1;
-        if (l1 >= 0) best_key = __shfl_sync(0xFFFFFFFFu, key, l1);
-        if (l2 >= 0) second_dist = key_dist(__shfl_sync(0xFFFFFFFFu, key, l2));
-        if (!full) {
-            decided = true;  // the list holds every gated candidate: best/second are exact (256 when absent)
-        } else if (l1 >= 0 && l2 >= 0) {
-            decided = true;  // both found inside the list: nothing unlisted can precede them
-        } else if (l1 >= 0) {
-            // best is exact; the true second distance lies in [tail_dist, 256]
-            const unsigned bd = key_dist(best_key);
-            if (bd > (unsigned)kThrLow) {
-                decided = true;
-            } else if (!(__fmul_rn(lowe_ratio, (float)tail_dist) < (float)bd)) {
-                decided = true;  // passes the ratio test even with the smallest possible second distance
-                second_dist = tail_dist;
+        unsigned pending = __ballot_sync(0xFFFFFFFFu, has_row);
+        while (pending) {
+            const bool mine = (pending >> lane) & 1u;
+            unsigned best = kInfKey;
+            const int st = mine ? decide_row(keys, taken, lowe_ratio, &best) : 0;
+            const unsigned accept_mask = __ballot_sync(0xFFFFFFFFu, mine && st == 1);
+            const unsigned exact_mask = __ballot_sync(0xFFFFFFFFu, mine && st == 2);
+            // conflicts with earlier accepting lanes of this round
+            bool conflict = false;
+            const unsigned my_best_idx = key_idx(best);
+            for (unsigned m = accept_mask; m; m &= m - 1) {
+                const int jl = __ffs(m) - 1;
+                const unsigned bj = __shfl_sync(0xFFFFFFFFu, my_best_idx, jl);
+                if (mine && lane > jl) {
+#pragma unroll
+                    for (int k = 0; k < kTopK; ++k) conflict |= (keys[k] != kInfKey && key_idx(keys[k]) == bj);
+                }
             }
-        } else {
-            // every listed candidate is taken: the best live distance is >= tail_dist
-            if (tail_dist > (unsigned)kThrLow) {
-                decided = true;
-                best_key = kInfKey;
-            }
-        }
-        if (!decided)
-            exact_row(d1, S1, b1, n1, taken, desc2[(size_t)(b2 + r) * 2], desc2[(size_t)(b2 + r) * 2 + 1], side_angle(S2, b2 + r), check_orientation, lane,
-                      &best_key, &second_dist);
-        if (best_key != kInfKey) {
-            const unsigned bd = key_dist(best_key);
-            // robust.cc:297-308: threshold, then Lowe ratio in float
-            accept = !(bd > (unsigned)kThrLow) && !(__fmul_rn(lowe_ratio, (float)second_dist) < (float)bd);
-        }
-        if (accept) {
-            const unsigned i1 = key_idx(best_key);
-            if (lane == 0) {
-                taken[i1 >> 5] |= 1u << (i1 & 31);
+            const unsigned unsafe = __ballot_sync(0xFFFFFFFFu, mine && (conflict || st == 2));
+            const int first_unsafe = unsafe ? __ffs(unsafe) - 1 : 32;
+            const unsigned commit = pending & ((first_unsafe >= 32) ? 0xFFFFFFFFu : ((1u << first_unsafe) - 1u));
+            if (((commit >> lane) & 1u) && st == 1) {
+                const unsigned i1 = key_idx(best);
+                atomicOr(&taken[i1 >> 5], 1u << (i1 & 31));  // distinct lanes may share a word
                 m21[i1] = r;
             }
+            pending &= ~commit;
             __syncwarp();
+            if (first_unsafe < 32 && ((exact_mask >> first_unsafe) & 1u) && !(((unsafe & ((1u << first_unsafe) - 1u)) != 0u))) {
+                // the first not-yet-committed row cannot be decided from its list: warp-cooperative exact scan (the reference's inner loop)
+                const int rr = base + first_unsafe;
+                unsigned bk, sd;
+                exact_row(d1, S1, b1, n1, taken, desc2[(size_t)(b2 + rr) * 2], desc2[(size_t)(b2 + rr) * 2 + 1], side_angle(S2, b2 + rr), check_orientation,
+                          lane, &bk, &sd);
+                if (bk != kInfKey) {
+                    const unsigned bd = key_dist(bk);
+                    if (!(bd > (unsigned)kThrLow) && !(__fmul_rn(lowe_ratio, (float)sd) < (float)bd)) {
+                        const unsigned i1 = key_idx(bk);
+                        if (lane == 0) {
+                            taken[i1 >> 5] |= 1u << (i1 & 31);
+                            m21[i1] = rr;
+                        }
+                    }
+                }
+                pending &= ~(1u << first_unsafe);
+                __syncwarp();
+            }
         }
     }
     __syncwarp();
@@ -303,8 +346,13 @@ struct Matcher {
         if ((rc = grow((void**)&d_matched, &matched_cap, sizeof(int) * (size_t)max_n1 * n_problems))) return rc;
         if ((rc = grow((void**)&d_taken, &taken_cap, sizeof(unsigned) * (size_t)taken_words * n_problems))) return rc;
         topk_kernel<<<dim3(row_blocks, n_problems), kRowsPerBlock, 0, stream>>>(S1, S2, (const unsigned char*)valid2, check_ori, d_lists);
-        resolve_kernel<<<n_problems, 32, 0, stream>>>(S1, S2, (const unsigned char*)valid2, d_lists, lowe, check_ori, d_matched, d_taken,
-                                                      taken_words, list_rows, max_n1, pairs_stride, (int*)pairs, (int*)n_pairs);
+        const size_t rs_bytes = sizeof(unsigned) * ((size_t)taken_words + (size_t)max_n1);
+        const int use_smem = rs_bytes <= 200 * 1024;
+        if (use_smem && rs_bytes > 48 * 1024)
+            B200_CUDA(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_bytes));
+        resolve_kernel<<<n_problems, 32, use_smem ? rs_bytes : 0, stream>>>(S1, S2, (const unsigned char*)valid2, d_lists, lowe, check_ori, d_matched,
+                                                                            d_taken, taken_words, list_rows, max_n1, pairs_stride, (int*)pairs,
+                                                                            (int*)n_pairs, use_smem);
         B200_CUDA(cudaGetLastError());
         return B200_OK;
     }
