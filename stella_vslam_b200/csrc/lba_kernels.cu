@@ -1190,7 +1190,11 @@ int b200_lba_create(int device, b200_lba_t* out) {
     b200_lba_s* h = new (std::nothrow) b200_lba_s();
     if (!h) return B200_ERR_INVALID;
     h->s.device = device;
-    cudaError_t e = cudaStreamCreateWithFlags(&h->s.stream, cudaStreamNonBlocking);
+    // local BA is a long chain of small dependent launches: give it the highest stream priority so its CTAs are not queued
+    // behind the wide front-end kernels that share the GPU (the mapping thread runs next to tracking, mapping_module.cc:63)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    cudaError_t e = cudaStreamCreateWithPriority(&h->s.stream, cudaStreamNonBlocking, prio_hi);
     if (e == cudaSuccess) e = cudaEventCreate(&h->s.ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->s.ev1);
     if (e != cudaSuccess) {

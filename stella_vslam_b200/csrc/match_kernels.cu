@@ -140,19 +140,35 @@ __device__ __forceinline__ unsigned warp_min(unsigned v) {
     return v;
 }
 
-// exact best/second over the live (not taken, orientation-gated) frame keypoints: the reference's inner loop
-__device__ void exact_row(const uint4* desc1, const Side& S1, int b1, int n1, const volatile unsigned* taken, uint4 q0, uint4 q1, float qa,
-                          int check_orientation, int lane, unsigned* best_key, unsigned* second_dist) {
+// exact best/second over the live (not taken, orientation-gated) frame keypoints: the reference's inner loop, one warp.
+// desc1/angle1 point either to the problem's frame side in global memory (angle stride in bytes) or to its staged copy in
+// shared memory.
+__device__ void exact_row(const uint4* desc1, const unsigned char* angle1, long long angle_stride, int n1, const volatile unsigned* taken,
+                          uint4 q0, uint4 q1, float qa, int check_orientation, int lane, unsigned* best_key, unsigned* second_dist) {
     unsigned k1 = kInfKey, k2 = kInfKey;  // two smallest keys seen by this lane
-    for (int i = lane; i < n1; i += 32) {
-        if ((taken[i >> 5] >> (i & 31)) & 1u) continue;
-        if (check_orientation && orientation_rejects(side_angle(S1, b1 + i), qa)) continue;
-        const unsigned key = make_key(hamming256(q0, q1, desc1[(size_t)i * 2], desc1[(size_t)i * 2 + 1]), (unsigned)i);
-        if (key < k1) {
-            k2 = k1;
-            k1 = key;
-        } else if (key < k2) {
-            k2 = key;
+    for (int i0 = lane; i0 < n1; i0 += 128) {
+        uint4 a0[4], a1[4];
+        float ang[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // four independent loads in flight per lane
+            const int i = min(i0 + 32 * u, n1 - 1);
+            a0[u] = desc1[(size_t)i * 2];
+            a1[u] = desc1[(size_t)i * 2 + 1];
+            ang[u] = *reinterpret_cast<const float*>(angle1 + (long long)i * angle_stride);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u;
+            if (i >= n1) continue;
+            if ((taken[i >> 5] >> (i & 31)) & 1u) continue;
+            if (check_orientation && orientation_rejects(ang[u], qa)) continue;
+            const unsigned key = make_key(hamming256(q0, q1, a0[u], a1[u]), (unsigned)i);
+            if (key < k1) {
+                k2 = k1;
+                k1 = key;
+            } else if (key < k2) {
+                k2 = key;
+            }
         }
     }
     const unsigned b = warp_min(k1);
@@ -210,20 +226,35 @@ __global__ void __launch_bounds__(32) resolve_kernel(Side S1, Side S2, const uns
                                                      int* __restrict__ pairs_out, int* __restrict__ n_pairs, int use_smem) {
     const uint4* __restrict__ desc1 = S1.desc;
     const uint4* __restrict__ desc2 = S2.desc;
-    extern __shared__ unsigned resolve_smem[];  // [taken_words] bitmap + [matched_stride] idx_1 -> idx_2 table when they fit
+    extern __shared__ __align__(16) unsigned resolve_smem[];  // [desc1 copy 32 B x n][angles][taken bitmap][idx_1 -> idx_2 table], as far as they fit
     const int p = blockIdx.x, lane = threadIdx.x;
     const int b1 = S1.off[p], n1 = S1.cnt[p];
     const int b2 = S2.off[p], n2 = S2.cnt[p];
     // the sequential state lives in shared memory (30-cycle instead of L2 latency on the critical path); very large frames fall
     // back to the global scratch
-    unsigned* taken = use_smem ? resolve_smem : taken_g + (size_t)p * taken_words;
-    int* m21 = use_smem ? reinterpret_cast<int*>(resolve_smem + taken_words) : matched + (size_t)p * matched_stride;
+    // use_smem: 0 = everything in global scratch, 1 = taken + table in shared memory, 2 = additionally the frame descriptors and
+    // angles (the exact fallback then scans shared memory instead of L2)
+    const int stage_words = (use_smem == 2) ? 9 * matched_stride : 0;  // 8 words of descriptor + 1 angle per keypoint
+    unsigned* taken = use_smem ? resolve_smem + stage_words : taken_g + (size_t)p * taken_words;
+    int* m21 = use_smem ? reinterpret_cast<int*>(resolve_smem + stage_words + taken_words) : matched + (size_t)p * matched_stride;
     int* pairs = pairs_out + 2 * (size_t)p * pairs_stride;
     lists += (size_t)p * list_rows * kTopK;
     for (int i = lane; i < (n1 + 31) / 32; i += 32) taken[i] = 0u;
     for (int i = lane; i < n1; i += 32) m21[i] = -1;
     __syncwarp();
     const uint4* d1 = desc1 + (size_t)b1 * 2;
+    const unsigned char* a1p = S1.angle + (long long)b1 * S1.angle_stride;
+    long long a1s = S1.angle_stride;
+    if (use_smem == 2) {
+        uint4* sd = reinterpret_cast<uint4*>(resolve_smem);
+        float* sa = reinterpret_cast<float*>(resolve_smem + 8 * matched_stride);
+        for (int i = lane; i < 2 * n1; i += 32) sd[i] = d1[i];
+        for (int i = lane; i < n1; i += 32) sa[i] = side_angle(S1, b1 + i);
+        d1 = sd;
+        a1p = reinterpret_cast<const unsigned char*>(sa);
+        a1s = sizeof(float);
+        __syncwarp();
+    }
     for (int base = 0; base < n2; base += 32) {
         const int r = base + lane;
         const bool has_row = r < n2 && (!valid2 || valid2[b2 + r]);  // robust.cc:255-262
@@ -266,8 +297,8 @@ __global__ void __launch_bounds__(32) resolve_kernel(Side S1, Side S2, const uns
                 // the first not-yet-committed row cannot be decided from its list: warp-cooperative exact scan (the reference's inner loop)
                 const int rr = base + first_unsafe;
                 unsigned bk, sd;
-                exact_row(d1, S1, b1, n1, taken, desc2[(size_t)(b2 + rr) * 2], desc2[(size_t)(b2 + rr) * 2 + 1], side_angle(S2, b2 + rr), check_orientation,
-                          lane, &bk, &sd);
+                exact_row(d1, a1p, a1s, n1, taken, desc2[(size_t)(b2 + rr) * 2], desc2[(size_t)(b2 + rr) * 2 + 1], side_angle(S2, b2 + rr),
+                          check_orientation, lane, &bk, &sd);
                 if (bk != kInfKey) {
                     const unsigned bd = key_dist(bk);
                     if (!(bd > (unsigned)kThrLow) && !(__fmul_rn(lowe_ratio, (float)sd) < (float)bd)) {
@@ -346,8 +377,10 @@ struct Matcher {
         if ((rc = grow((void**)&d_matched, &matched_cap, sizeof(int) * (size_t)max_n1 * n_problems))) return rc;
         if ((rc = grow((void**)&d_taken, &taken_cap, sizeof(unsigned) * (size_t)taken_words * n_problems))) return rc;
         topk_kernel<<<dim3(row_blocks, n_problems), kRowsPerBlock, 0, stream>>>(S1, S2, (const unsigned char*)valid2, check_ori, d_lists);
-        const size_t rs_bytes = sizeof(unsigned) * ((size_t)taken_words + (size_t)max_n1);
-        const int use_smem = rs_bytes <= 200 * 1024;
+        const size_t state_bytes = sizeof(unsigned) * ((size_t)taken_words + (size_t)max_n1);
+        const size_t stage_bytes = sizeof(unsigned) * 9 * (size_t)max_n1;
+        const int use_smem = (state_bytes + stage_bytes <= 200 * 1024) ? 2 : (state_bytes <= 200 * 1024 ? 1 : 0);
+        const size_t rs_bytes = use_smem == 2 ? state_bytes + stage_bytes : state_bytes;
         if (use_smem && rs_bytes > 48 * 1024)
             B200_CUDA(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_bytes));
         resolve_kernel<<<n_problems, 32, use_smem ? rs_bytes : 0, stream>>>(S1, S2, (const unsigned char*)valid2, d_lists, lowe, check_ori, d_matched,

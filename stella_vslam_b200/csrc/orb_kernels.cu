@@ -256,7 +256,8 @@ constexpr int kRawPitch = 96;            // TMA box width: the box must start on
 template <bool kUseTma>
 __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ Geom g, const __grid_constant__ TmapSet tmaps, Images im,
                                                                   const CellDesc* __restrict__ cells, const unsigned char* __restrict__ mask,
-                                                                  unsigned long long mask_pitch, unsigned long long* __restrict__ grid) {
+                                                                  unsigned long long mask_pitch, unsigned long long* __restrict__ grid,
+                                                                  int arena_frame0) {
     // tile column c holds cell column c - 1 (so the first candidate column, lx = 3, is 4-byte aligned); pitch 80
     __shared__ __align__(16) unsigned char tile[kTileRows * kTilePitch];
     __shared__ __align__(16) unsigned char mmap[kTileRows * kTilePitch];
@@ -286,7 +287,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
         if (tid == 0) {
             mbar_init(&tma_bar, 1);
             mbar_expect_tx(&tma_bar, kTileRows * kRawPitch);
-            tma_load_3d(raw, &tmaps.m[level], (int)cd.min_x - 3, (int)cd.min_y, frame, &tma_bar);  // min_x - 3 = 16 + 64 j
+            // min_x - 3 = 16 + 64 j.  Levels >= 1 are described over the whole arena, level 0 over this call's frames.
+            tma_load_3d(raw, &tmaps.m[level], (int)cd.min_x - 3, (int)cd.min_y, frame + (level ? arena_frame0 : 0), &tma_bar);
         }
         __syncthreads();  // barrier initialised (and skip written) before anybody polls it
         mbar_wait(&tma_bar, 0);
@@ -632,6 +634,7 @@ __device__ __forceinline__ float util_sin(float v) {
     return util_cos(__fsub_rn(PI_2, v));
 }
 
+constexpr int kUploadChunk = 16;        // frames per upload/compute chunk of the host-buffer path
 constexpr int kDescWarps = 8;           // warps per block
 constexpr int kDescBlocksPerFrame = 64;  // blockIdx.x range; each warp strides over its frame's keypoints
 
@@ -760,8 +763,17 @@ static bool make_level_tmap(CUtensorMap* out, const void* base, int w, int h, si
 struct Extractor {
     b200_orb_params_t prm{};
     std::vector<float> mask_rects;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[8] = {};
+    std::vector<cudaEvent_t> chunk_events;
+    cudaEvent_t chunk_event(int i) {
+        while ((int)chunk_events.size() <= i) {
+            cudaEvent_t e = nullptr;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+            chunk_events.push_back(e);
+        }
+        return chunk_events[i];
+    }
     bool timing = false;
     float stage_ms[6] = {};
     // configured geometry
@@ -972,44 +984,53 @@ struct Extractor {
         return B200_OK;
     }
 
-    int run(const void* d_images, size_t pitch, size_t fstride, int batch, const void* d_mask, size_t mask_pitch) {
-        Images im{(const unsigned char*)d_images, pitch, fstride, d_pyr, pyr_fstride};
+    // Enqueue the whole extractor for `batch` frames.  frame0: first slot of the arenas / result buffers to use, so that a large
+    // host batch can be processed in chunks while later chunks are still being uploaded.
+    int run(const void* d_images, size_t pitch, size_t fstride, int batch, const void* d_mask, size_t mask_pitch, int frame0 = 0,
+            bool record = true) {
+        Images im{(const unsigned char*)d_images, pitch, fstride, d_pyr + (size_t)frame0 * pyr_fstride, pyr_fstride};
         const unsigned char* mask = (const unsigned char*)d_mask;
         unsigned long long mpitch = mask_pitch;
         if (!mask && rect_mask_ready) {  // orb_extractor.cc:50-64: image mask first, else rectangle mask
             mask = d_rect_mask;
             mpitch = img0_pitch;
         }
+        if (out_kps && out_stride < geom.grid_cells) {
+            set_error("bound output stride %d is smaller than the keypoint upper bound %d", out_stride, geom.grid_cells);
+            return B200_ERR_CAPACITY;
+        }
         const int nl = geom.num_levels;
-        if (timing) B200_CUDA(cudaEventRecord(ev[0], stream));
+        const bool tm = timing && record;
+        unsigned long long* grid = d_grid + (size_t)frame0 * geom.grid_cells;
+        RawKp* raw = d_raw + (size_t)frame0 * raw_stride;
+        unsigned char* blur = d_blur + (size_t)frame0 * pyr_fstride;
+        int* counts = res_counts() + frame0;
+        if (tm) B200_CUDA(cudaEventRecord(ev[0], stream));
         for (int l = 1; l < nl; ++l) {
             const LevelGeom& L = geom.lv[l];
             dim3 blk(64, 4), grd(ceil_div(L.pitch / 4, 64), ceil_div(L.h, 4), batch);
             resize_kernel<<<grd, blk, 0, stream>>>(geom, im, d_taps, l);
         }
-        if (timing) B200_CUDA(cudaEventRecord(ev[1], stream));
-        B200_CUDA(cudaMemsetAsync(d_grid, 0, sizeof(unsigned long long) * (size_t)raw_stride * batch, stream));
+        if (tm) B200_CUDA(cudaEventRecord(ev[1], stream));
+        B200_CUDA(cudaMemsetAsync(grid, 0, sizeof(unsigned long long) * (size_t)std::max(1, geom.grid_cells) * batch, stream));
         if (n_cells) {
             // level 0 lives in the caller's buffer: encode its tensor map for this call (a host-side table fill, no GPU work)
             const bool tma = tmaps_ok && make_level_tmap(&tmaps.m[0], d_images, geom.lv[0].w, geom.lv[0].h, pitch, fstride, batch);
-            if (tma) fast_cells_kernel<true><<<dim3(n_cells, batch), kFastThreads, 0, stream>>>(geom, tmaps, im, d_cells, mask, mpitch, d_grid);
-            else fast_cells_kernel<false><<<dim3(n_cells, batch), kFastThreads, 0, stream>>>(geom, tmaps, im, d_cells, mask, mpitch, d_grid);
+            if (tma) fast_cells_kernel<true><<<dim3(n_cells, batch), kFastThreads, 0, stream>>>(geom, tmaps, im, d_cells, mask, mpitch, grid, frame0);
+            else fast_cells_kernel<false><<<dim3(n_cells, batch), kFastThreads, 0, stream>>>(geom, tmaps, im, d_cells, mask, mpitch, grid, frame0);
             last_used_tma = tma;
         }
-        if (timing) B200_CUDA(cudaEventRecord(ev[2], stream));
-        if (out_kps && out_stride < geom.grid_cells) {
-            set_error("bound output stride %d is smaller than the keypoint upper bound %d", out_stride, geom.grid_cells);
-            return B200_ERR_CAPACITY;
-        }
-        select_kernel<<<dim3(nl, batch), 256, 0, stream>>>(geom, d_grid, d_raw, raw_stride, res_counts(), d_level_counts);
-        if (timing) B200_CUDA(cudaEventRecord(ev[3], stream));
-        blur_kernel<<<dim3(n_blur_tiles, batch), 256, 0, stream>>>(geom, im, d_tiles, d_blur, pyr_fstride);
-        if (timing) B200_CUDA(cudaEventRecord(ev[4], stream));
-        describe_kernel<<<dim3(kDescBlocksPerFrame, batch), kDescWarps * 32, 0, stream>>>(geom, im, d_blur, pyr_fstride, d_raw, raw_stride,
-                                                                                         res_counts(), res_kps(), res_descs(), res_stride());
-        if (timing) B200_CUDA(cudaEventRecord(ev[5], stream));
+        if (tm) B200_CUDA(cudaEventRecord(ev[2], stream));
+        select_kernel<<<dim3(nl, batch), 256, 0, stream>>>(geom, grid, raw, raw_stride, counts, d_level_counts + (size_t)frame0 * kMaxLevels);
+        if (tm) B200_CUDA(cudaEventRecord(ev[3], stream));
+        blur_kernel<<<dim3(n_blur_tiles, batch), 256, 0, stream>>>(geom, im, d_tiles, blur, pyr_fstride);
+        if (tm) B200_CUDA(cudaEventRecord(ev[4], stream));
+        describe_kernel<<<dim3(kDescBlocksPerFrame, batch), kDescWarps * 32, 0, stream>>>(
+            geom, im, blur, pyr_fstride, raw, raw_stride, counts, res_kps() + (size_t)frame0 * res_stride(),
+            res_descs() + (size_t)frame0 * res_stride() * 32, res_stride());
+        if (tm) B200_CUDA(cudaEventRecord(ev[5], stream));
         B200_CUDA(cudaGetLastError());
-        last_batch = batch;
+        last_batch = frame0 + batch;
         return B200_OK;
     }
 };
@@ -1054,6 +1075,7 @@ int b200_orb_create(const b200_orb_params_t* p, b200_orb_t* out) {
     h->ex.prm.mask_rects = nullptr;
     if (p->n_mask_rects > 0) h->ex.mask_rects.assign(p->mask_rects, p->mask_rects + 4 * (size_t)p->n_mask_rects);
     cudaError_t e = cudaStreamCreateWithFlags(&h->ex.own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->ex.copy_stream, cudaStreamNonBlocking);
     h->ex.stream = h->ex.own_stream;
     for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->ex.ev[i]);
     if (e != cudaSuccess) {
@@ -1071,6 +1093,8 @@ int b200_orb_destroy(b200_orb_t h) {
     h->ex.free_arenas();
     for (auto& e : h->ex.ev)
         if (e) cudaEventDestroy(e);
+    for (auto& ce : h->ex.chunk_events) cudaEventDestroy(ce);
+    if (h->ex.copy_stream) cudaStreamDestroy(h->ex.copy_stream);
     if (h->ex.own_stream) cudaStreamDestroy(h->ex.own_stream);
     delete h;
     return B200_OK;
@@ -1182,20 +1206,35 @@ int b200_orb_extract(b200_orb_t h, const uint8_t* images, int width, int height,
     B200_CUDA(cudaSetDevice(ex.prm.device));
     int rc = ex.configure(width, height, std::max(batch, ex.prm.max_batch));
     if (rc) return rc;
-    if (batch == 1 || frame_stride == pitch * (size_t)height) {  // contiguous batch: one tall 2-D copy
-        B200_CUDA(cudaMemcpy2DAsync(ex.d_img0, ex.img0_pitch, images, pitch, width, (size_t)height * batch, cudaMemcpyHostToDevice, ex.stream));
-    } else {
-        for (int f = 0; f < batch; ++f)
-            B200_CUDA(cudaMemcpy2DAsync(ex.d_img0 + (size_t)f * ex.img0_fstride, ex.img0_pitch, images + (size_t)f * frame_stride, pitch,
-                                        width, height, cudaMemcpyHostToDevice, ex.stream));
-    }
     const unsigned char* d_mask = nullptr;
     if (mask) {
         B200_CUDA(cudaMemcpy2DAsync(ex.d_user_mask, ex.img0_pitch, mask, mask_pitch, width, height, cudaMemcpyHostToDevice, ex.stream));
         d_mask = ex.d_user_mask;
     }
-    rc = ex.run(ex.d_img0, ex.img0_pitch, ex.img0_fstride, batch, d_mask, ex.img0_pitch);
-    if (rc) return rc;
+    // Chunked pipeline: the upload of chunk c+1 (copy stream) overlaps the kernels of chunk c (compute stream).
+    const int chunk = batch > 2 * b200::orb::kUploadChunk ? b200::orb::kUploadChunk : batch;
+    const bool contiguous = frame_stride == pitch * (size_t)height;
+    int n_ev = 0;
+    for (int f0 = 0; f0 < batch; f0 += chunk) {
+        const int nb = std::min(chunk, batch - f0);
+        cudaStream_t cs = (chunk < batch) ? ex.copy_stream : ex.stream;
+        if (nb == 1 || contiguous) {  // one tall 2-D copy
+            B200_CUDA(cudaMemcpy2DAsync(ex.d_img0 + (size_t)f0 * ex.img0_fstride, ex.img0_pitch, images + (size_t)f0 * frame_stride, pitch, width,
+                                        (size_t)height * nb, cudaMemcpyHostToDevice, cs));
+        } else {
+            for (int f = f0; f < f0 + nb; ++f)
+                B200_CUDA(cudaMemcpy2DAsync(ex.d_img0 + (size_t)f * ex.img0_fstride, ex.img0_pitch, images + (size_t)f * frame_stride, pitch, width,
+                                            height, cudaMemcpyHostToDevice, cs));
+        }
+        if (cs != ex.stream) {
+            cudaEvent_t e = ex.chunk_event(n_ev++);
+            if (!e) return b200::cuda_fail(cudaErrorMemoryAllocation, "chunk event", __FILE__, __LINE__);
+            B200_CUDA(cudaEventRecord(e, cs));
+            B200_CUDA(cudaStreamWaitEvent(ex.stream, e, 0));
+        }
+        rc = ex.run(ex.d_img0 + (size_t)f0 * ex.img0_fstride, ex.img0_pitch, ex.img0_fstride, nb, d_mask, ex.img0_pitch, f0, chunk == batch);
+        if (rc) return rc;
+    }
     return b200_orb_fetch(h, kps, descs, cap, counts);
 }
 
