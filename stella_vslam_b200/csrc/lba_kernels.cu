@@ -186,9 +186,11 @@ constexpr int kEdgeThreads = 128;
 
 __global__ void __launch_bounds__(kEdgeThreads) edges_kernel(View v, const double* __restrict__ Rt, const double* __restrict__ pts,
                                                              double* __restrict__ chi, double* __restrict__ Hpl, double* __restrict__ pl,
-                                                             double* __restrict__ chi_partials, int linearize) {
+                                                             double* __restrict__ chi_partials, int linearize,
+                                                             const double* __restrict__ chi_carry, int* __restrict__ fail_reset) {
     __shared__ double sh[kEdgeThreads];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fail_reset && e == 0) *fail_reset = 0;  // last kernel of a trial: re-arm the solver's failure flag
     double cost = 0.0;
     if (e < v.E) {
         const EdgeS ed = v.edges[e];
@@ -236,6 +238,8 @@ __global__ void __launch_bounds__(kEdgeThreads) edges_kernel(View v, const doubl
             for (int i = 0; i < 9; ++i) pl[(size_t)i * v.E + e] = 0.0;
 #pragma unroll
             for (int i = 0; i < 18; ++i) Hpl[(size_t)e * 18 + i] = 0.0;
+        } else if (chi_carry) {
+            chi[e] = chi_carry[e];  // inactive edges keep the chi2 of their last activation across the current/trial swap
         }
     }
     const double s = block_sum(cost, sh);
@@ -487,7 +491,23 @@ __device__ void se3_oplus(const double* q, const double* t, const double* upd, d
 }
 
 constexpr int kCholThreads = 512;
-constexpr int kNB = 24;  // panel width: four 6x6 keyframe blocks
+constexpr int kNB = 24;       // panel width: four 6x6 keyframe blocks
+constexpr int kCholCluster = 8;  // CTAs (SMs) that share one factorisation
+
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// all threads of all CTAs of the cluster; release/acquire at cluster scope orders the global-memory updates of the trailing matrix
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 // Blocked right-looking Cholesky of the augmented matrix M = [Hs ; bs^T] ((n+1) x ld, row-major, lower triangle): the
 // right-hand side rides along as row n, so after the factorisation M[n][0..n) = L^-1 bs and only the backward solve
@@ -495,6 +515,9 @@ constexpr int kNB = 24;  // panel width: four 6x6 keyframe blocks
 // are exchanged by shuffle); (2) every row below is solved against it, column oriented, with the reciprocal diagonal;
 // the solved panel is kept TRANSPOSED in shared memory; (3) rank-kNB trailing update with 4x4 register tiles whose
 // operands are two 32-byte vector loads per panel column.
+// The kernel runs as ONE thread-block cluster: every CTA repeats the cheap steps (1) and (2) on its own SM (so no panel
+// exchange is needed), the tiles of step (3) -- 60 % of the flops -- are dealt round-robin to the CTAs of the cluster, and a
+// cluster barrier (release/acquire) separates the panels.  CTA 0 writes the factor back and does the backward solve.
 __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld, double* __restrict__ M, double lambda,
                                                                   const double* __restrict__ bp, double* __restrict__ xp, int K,
                                                                   const int* __restrict__ pose_col, const double* __restrict__ q_cur,
@@ -510,6 +533,8 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld,
     __shared__ double sh[kCholThreads];
     __shared__ int bad;
     const int tid = threadIdx.x, nt = blockDim.x;
+    const unsigned crank = cluster_ctarank(), csize = cluster_nctarank();
+    const bool lead = crank == 0;
     if (tid == 0) bad = *fail;
     __syncthreads();
     long long t_diag = 0, t_panel = 0, t_trail = 0, t_back = 0, t0 = clock64(), t1;
@@ -540,7 +565,6 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld,
 #pragma unroll
                 for (int k = 0; k < kNB; ++k) {
                     D[tid * (kNB + 1) + k] = r[k];
-                    if (tid < nb && k <= tid) M[(size_t)(kb + tid) * ld + kb + k] = r[k];
                 }
             }
             if (tid == 0 && b) bad = 1;
@@ -564,7 +588,6 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld,
 #pragma unroll
             for (int j = 0; j < kNB; ++j) {
                 Pn[(size_t)j * mp + t] = x[j];
-                if (j < nb) row[j] = x[j];
             }
         }
         for (int idx = tid; idx < kNB * 4; idx += nt) {  // zero the <= 3 padding rows read by the last 4-row tile
@@ -576,7 +599,7 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld,
         // (3) trailing update with 4x4 register tiles over the lower triangle (rhs row included, rhs column excluded)
         const int tm = (m + 3) >> 2;
         const int n_tiles = tm * (tm + 1) / 2;
-        for (int tile = tid; tile < n_tiles; tile += nt) {
+        for (int tile = tid * csize + crank; tile < n_tiles; tile += nt * csize) {
             int tr = (int)((sqrt(8.0 * tile + 1.0) - 1.0) * 0.5);
             while ((tr + 1) * (tr + 2) / 2 <= tile) ++tr;
             while (tr * (tr + 1) / 2 > tile) --tr;
@@ -605,8 +628,23 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld,
                 }
         }
         __syncthreads();
+        if (csize > 1) cluster_sync_all();  // every CTA's share of the trailing matrix is visible before the next panel is read
+        // The factor of this panel is written back only now: the other CTAs were still reading these columns of M (their own copy
+        // of steps 1-2) until the barrier; the next panel touches columns >= kb + nb only.
+        if (lead) {
+            for (int idx = tid; idx < nb * nb; idx += nt) {
+                const int i = idx / nb, j = idx - i * nb;
+                if (j <= i) M[(size_t)(kb + i) * ld + kb + j] = D[i * (kNB + 1) + j];
+            }
+            for (int idx = tid; idx < m * nb; idx += nt) {
+                const int t = idx / nb, j = idx - t * nb;
+                M[(size_t)(r0 + t) * ld + kb + j] = Pn[(size_t)j * mp + t];
+            }
+        }
+        __syncthreads();
         PHASE(t_trail);
     }
+    if (!lead) return;  // the backward solve and the keyframe updates are one CTA's work
     if (bad) {
         if (tid == 0) {
             *fail = 1;
@@ -758,12 +796,6 @@ __global__ void __launch_bounds__(128) outlier_kernel(View v, const double* __re
     } else {
         out[e] = o;
     }
-}
-
-// carry the chi2 of inactive edges across the trial/current swap
-__global__ void __launch_bounds__(128) carry_chi_kernel(View v, const double* __restrict__ chi_cur, double* __restrict__ chi_new) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < v.E && v.level[e]) chi_new[e] = chi_cur[e];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -960,7 +992,7 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     // readback block: [chi partials eb][diag partials lb][scale partials lb2][result 2]
     const size_t res_n = (size_t)eb + (size_t)lb + (size_t)lb2 + 6;
     const size_t o_res = dv.take<double>(res_n), o_fail = dv.take<int>(1), o_out = dv.take<unsigned char>(E);
-    int rc = S.ensure(dv.off + 256, upload_bytes, res_n);
+    int rc = S.ensure(dv.off + 256, upload_bytes, res_n + 36 * (size_t)std::max(Kf, 1));
     if (rc) return rc;
     unsigned char* hs = S.h_stage;
     std::memset(hs, 0, upload_bytes);
@@ -1017,12 +1049,12 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
         uint8_t aux = 0;
         volatile uint8_t* flag = force_stop ? force_stop : &aux;
         *flag = 0;  // terminate_action at iteration -1 resets the stop flag (terminate_action.cc:46-51)
-        double lambda = 0, ni = 2, last_chi = 0, chi_now = 0;
+        double lambda = 0, ni = 2, last_chi = 0, chi_now = 0, current_chi = 0;
         int it = 0;
         bool ok = true;
         for (; it < iterations && !*flag && ok; ++it) {
             // computeActiveErrors + buildSystem at the current state
-            if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], Hpl, pl, r_chi, 1);
+            if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], Hpl, pl, r_chi, 1, nullptr, nullptr);
             points_kernel<<<lb, 128, 0, st>>>(v, pl, Hll, bl, r_diag);
             if (n_pose_chunks) {
                 pose_chunks_kernel<<<ceil_div(n_pose_chunks, 4), 128, 0, st>>>(v, (const int2*)(d + o_pchunks), n_pose_chunks, Rts[cur], ptss[cur], ppart);
@@ -1032,20 +1064,20 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
                 B200_CUDA(cudaMemsetAsync(bp, 0, sizeof(double) * 6 * Kf, st));
             }
             launches += 4;
-            const bool need_diag = (it == 0);
-            B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * (eb + (need_diag ? lb : 0)), cudaMemcpyDeviceToHost, st));
-            std::vector<double> hpp_diag;
-            B200_CUDA(cudaStreamSynchronize(st));
-            double current_chi = sum(h, eb);
+            // The robust chi2 at the current state is needed on the host only at the first iteration of a round (afterwards it is the
+            // chi2 of the last accepted trial, computed by the same kernel in the same order), so later iterations enqueue the
+            // first trial right behind the build without a round trip.
+            if (it == 0) {
+                B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * (eb + lb), cudaMemcpyDeviceToHost, st));
+                if (Kf) B200_CUDA(cudaMemcpyAsync(h + res_n, Hpp, sizeof(double) * 36 * Kf, cudaMemcpyDeviceToHost, st));
+                B200_CUDA(cudaStreamSynchronize(st));
+                current_chi = sum(h, eb);
+            }
             if (it == 0) {  // computeLambdaInit: tau * max |H_jj| over all free vertices, tau = 1e-5
                 double mx = 0;
                 for (int i = 0; i < lb; ++i) mx = std::max(mx, h[eb + i]);
-                if (Kf) {
-                    hpp_diag.resize(36 * (size_t)Kf);
-                    B200_CUDA(cudaMemcpy(hpp_diag.data(), Hpp, sizeof(double) * 36 * Kf, cudaMemcpyDeviceToHost));
-                    for (int p = 0; p < Kf; ++p)
-                        for (int a = 0; a < 6; ++a) mx = std::max(mx, std::fabs(hpp_diag[36 * (size_t)p + a * 7]));
-                }
+                for (int p = 0; p < Kf; ++p)
+                    for (int a = 0; a < 6; ++a) mx = std::max(mx, std::fabs(h[res_n + 36 * (size_t)p + a * 7]));
                 lambda = 1e-5 * mx;
                 ni = 2;
                 if (round == 0 && stats) stats->lambda_init = lambda;
@@ -1054,7 +1086,6 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
             int qmax = 0;
             do {
                 const int nxt = cur ^ 1;
-                B200_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), st));
                 if (Lf) dinv_kernel<<<ceil_div(Lf, 128), 128, 0, st>>>(Lf, lambda, Hll, Dinv, fail);
                 if (n_chunks)
                     schur_chunks_kernel<<<ceil_div(n_chunks, 4), 128, 0, st>>>(v, (const SchurChunk*)(d + o_chunks), n_chunks, (const int2*)(d + o_pairs),
@@ -1062,14 +1093,26 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
                 if (n_blocks)
                     schur_finish_kernel<<<ceil_div(n_blocks * 42, 128), 128, 0, st>>>(lambda, (const SchurBlock*)(d + o_blocks), n_blocks, part, Hpp, bp, Hs,
                                                                                      n, ld);
-                chol_solve_kernel<<<1, kCholThreads, chol_smem, st>>>(n, ld, Hs, lambda, bp, xp, K, (const int*)(d + o_posecol), qs[cur], ts[cur],
-                                                                      qs[nxt], ts[nxt], Rts[nxt], r_result, fail);
-                backsub_kernel<<<lb2, 128, 0, st>>>(v, lambda, Dinv, bl, Hpl, xp, ptss[cur], ptss[nxt], r_scale, fail);
-                if (E) {
-                    carry_chi_kernel<<<eb, 128, 0, st>>>(v, chis[cur], chis[nxt]);
-                    edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[nxt], ptss[nxt], chis[nxt], Hpl, pl, r_chi, 0);
+                {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3(kCholCluster);
+                    cfg.blockDim = dim3(kCholThreads);
+                    cfg.dynamicSmemBytes = chol_smem;
+                    cfg.stream = st;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeClusterDimension;
+                    attr[0].val.clusterDim.x = kCholCluster;
+                    attr[0].val.clusterDim.y = 1;
+                    attr[0].val.clusterDim.z = 1;
+                    cfg.attrs = attr;
+                    cfg.numAttrs = 1;
+                    B200_CUDA(cudaLaunchKernelEx(&cfg, chol_solve_kernel, n, ld, Hs, lambda, (const double*)bp, xp, K, (const int*)(d + o_posecol),
+                                                 (const double*)qs[cur], (const double*)ts[cur], qs[nxt], ts[nxt], Rts[nxt], r_result, fail));
                 }
-                launches += 7;
+                backsub_kernel<<<lb2, 128, 0, st>>>(v, lambda, Dinv, bl, Hpl, xp, ptss[cur], ptss[nxt], r_scale, fail);
+                if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[nxt], ptss[nxt], chis[nxt], Hpl, pl, r_chi, 0, chis[cur], fail);
+                else B200_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), st));
+                launches += 6;
                 B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * res_n, cudaMemcpyDeviceToHost, st));
                 B200_CUDA(cudaStreamSynchronize(st));
                 const bool ok2 = h[eb + lb + lb2] != 0.0;
@@ -1111,7 +1154,7 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
             }
         }
         // chi2 of every active edge at the final state (the terminate action's computeActiveErrors)
-        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], Hpl, pl, r_chi, 0);
+        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], Hpl, pl, r_chi, 0, nullptr, nullptr);
         launches += 1;
         if (it == 0 && stats) {
             B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * eb, cudaMemcpyDeviceToHost, st));

@@ -83,6 +83,22 @@ class local_bundle_adjuster:
         except Exception:
             pass
 
+    def prepare(self, problem):
+        """Pack a problem once (ctypes struct + output buffers) for repeated, low-overhead optimize_prepared() calls."""
+        P, keep = pack_problem(problem)
+        K, L, E = P.n_poses, P.n_points, P.n_edges
+        return dict(P=P, keep=keep, pose=np.zeros((K, 4, 4)), pts=np.zeros((L, 3)), outl=np.zeros(E, np.uint8), st=LbaStats())
+
+    def optimize_prepared(self, prep, force_stop_flag=None):
+        rc = self._L.b200_lba_solve(self._h, C.byref(prep["P"]), self.num_first_iter_, self.num_second_iter_, ptr(force_stop_flag),
+                                    ptr(prep["pose"]), ptr(prep["pts"]), ptr(prep["outl"]), C.byref(prep["st"]))
+        if rc == ERR_ABORTED:
+            return None
+        check(rc)
+        launches = C.c_int()
+        self._L.b200_lba_last_profile(self._h, None, C.byref(launches))
+        return launches.value
+
     def optimize(self, problem, force_stop_flag=None):
         """problem: flattened window (dict).  force_stop_flag: optional 1-element uint8 array (read AND written, like the
         reference's bool*).  Returns None if the flag was already set (local_bundle_adjuster_g2o.cc:308-310), else a dict."""
