@@ -439,8 +439,12 @@ def main():
         gbs = alg[nm] * B / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kernels[nm] = {"ms_per_launch_batch": ms, "alg_bytes_per_frame": float(alg[nm]), "achieved_gbs": gbs, "frac": gbs / peak_gbs}
     dom = max(names, key=lambda k: kernels[k]["ms_per_launch_batch"])
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture
+    # (profiles/r1_ncu_full_frontend.csv, batch 64 at 1920x1080); null for any other configuration
+    ncu_traffic = {"pyramid": 519.9e6, "fast_nms_gridmax": 412.5e6, "blur": 803.0e6, "orient_describe": 594.1e6, "select": 1.2e6}
+    traffic = ncu_traffic.get(dom) if (B == 64 and (W, H) == (1920, 1080)) else None
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                 "note": "FAST is integer-ALU-bound by construction; HBM fraction reported as the contract asks", "kernels": kernels}
 
     cpu = None

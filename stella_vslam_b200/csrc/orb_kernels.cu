@@ -131,38 +131,69 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
 // ---------------------------------------------------------------------------------------------------------------
 // K1: cv::resize(INTER_LINEAR) level l-1 -> l, fixed point (OpenCV resize.cpp HResizeLinear/VResizeLinear, 11 bits)
 // ---------------------------------------------------------------------------------------------------------------
-// (a shared-memory staged variant measured slower than these L1-cached gathers on the B200: 1.33 vs 1.09 ms per 64 frames)
-__global__ void __launch_bounds__(256) resize_kernel(const __grid_constant__ Geom g, Images im, const ResizeTap* __restrict__ taps, int level) {
+// One thread produces a strip of 4 columns x kRzRows rows: the x taps are loaded once, and the horizontally interpolated value
+// of every source row is computed once and reused by the (usually two) output rows that blend it -- half the gathers and
+// multiplies of a row-at-a-time kernel.  Source bytes come straight from L1/L2 (a shared-memory staged variant measured
+// slower on the B200: the tile fill + barrier cost more than the cached gathers).
+constexpr int kRzRows = 8;
+
+__global__ void __launch_bounds__(128) resize_kernel(const __grid_constant__ Geom g, Images im, const ResizeTap* __restrict__ taps, int level) {
     const LevelGeom& L = g.lv[level];
     const int frame = blockIdx.z;
     int spitch;
     const unsigned char* src = level_ptr(im, g, level - 1, frame, &spitch);
     unsigned char* dst = im.pyr + (size_t)frame * im.pyr_fstride + L.offset;
-    const int sw = g.lv[level - 1].w;
-    const int dy = blockIdx.y * blockDim.y + threadIdx.y;
-    const int dx0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (dy >= L.h || dx0 >= L.pitch) return;
-    const ResizeTap ty = taps[L.tab_y + dy];
-    const int sh = g.lv[level - 1].h;
-    const int sy0 = min(max((int)ty.ofs, 0), sh - 1), sy1 = min(max((int)ty.ofs + 1, 0), sh - 1);
-    const unsigned char* r0 = src + (size_t)sy0 * spitch;
-    const unsigned char* r1 = src + (size_t)sy1 * spitch;
-    unsigned out = 0;
+    const int sw = g.lv[level - 1].w, sh = g.lv[level - 1].h;
+    const int dxq = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int dy0 = blockIdx.y * kRzRows;
+    if (dxq >= L.pitch) return;
+    const int n_valid = min(4, L.w - dxq);  // <= 0 in the padding columns (written as zero)
+    int ofs[4], ofs1[4], w0[4], w1[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        const int dx = dx0 + k;
-        unsigned v = 0;
-        if (dx < L.w) {
-            const ResizeTap tx = taps[L.tab_x + dx];
-            const int sx = tx.ofs, sx1 = min(sx + 1, sw - 1);
-            const int h0 = r0[sx] * tx.w0 + r0[sx1] * tx.w1;
-            const int h1 = r1[sx] * tx.w0 + r1[sx1] * tx.w1;
-            const int val = (((ty.w0 * (h0 >> 4)) >> 16) + ((ty.w1 * (h1 >> 4)) >> 16) + 2) >> 2;
-            v = (unsigned)min(max(val, 0), 255);
-        }
-        out |= v << (8 * k);
+        const ResizeTap t = taps[L.tab_x + min(dxq + k, L.w - 1)];
+        ofs[k] = t.ofs;
+        ofs1[k] = min((int)t.ofs + 1, sw - 1);  // weight 0 there
+        w0[k] = t.w0;
+        w1[k] = t.w1;
     }
-    *reinterpret_cast<unsigned*>(dst + (size_t)dy * L.pitch + dx0) = out;
+    int rowA = -1, rowB = -1;  // clipped source rows whose horizontal interpolation is cached
+    int hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
+    auto hrow = [&](int sy, int (&h)[4]) {
+        const unsigned char* r = src + (size_t)sy * spitch;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) h[k] = (k < n_valid) ? ((int)r[ofs[k]] * w0[k] + (int)r[ofs1[k]] * w1[k]) >> 4 : 0;
+    };
+    const int dy_end = min(dy0 + kRzRows, L.h);
+    for (int dy = dy0; dy < dy_end; ++dy) {
+        const ResizeTap ty = taps[L.tab_y + dy];
+        const int s0 = min(max((int)ty.ofs, 0), sh - 1), s1 = min(max((int)ty.ofs + 1, 0), sh - 1);  // rows clipped like OpenCV
+        if (s0 != rowA) {
+            if (s0 == rowB) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) hA[k] = hB[k];
+            } else {
+                hrow(s0, hA);
+            }
+            rowA = s0;
+        }
+        if (s1 != rowB) {
+            if (s1 == rowA) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) hB[k] = hA[k];
+            } else {
+                hrow(s1, hB);
+            }
+            rowB = s1;
+        }
+        unsigned out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int val = (((ty.w0 * hA[k]) >> 16) + ((ty.w1 * hB[k]) >> 16) + 2) >> 2;
+            out |= (unsigned)min(max(val, 0), 255) << (8 * k);
+        }
+        *reinterpret_cast<unsigned*>(dst + (size_t)dy * L.pitch + dxq) = out;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1008,8 +1039,8 @@ struct Extractor {
         if (tm) B200_CUDA(cudaEventRecord(ev[0], stream));
         for (int l = 1; l < nl; ++l) {
             const LevelGeom& L = geom.lv[l];
-            dim3 blk(64, 4), grd(ceil_div(L.pitch / 4, 64), ceil_div(L.h, 4), batch);
-            resize_kernel<<<grd, blk, 0, stream>>>(geom, im, d_taps, l);
+            dim3 grd(ceil_div(L.pitch / 4, 128), ceil_div(L.h, kRzRows), batch);
+            resize_kernel<<<grd, 128, 0, stream>>>(geom, im, d_taps, l);
         }
         if (tm) B200_CUDA(cudaEventRecord(ev[1], stream));
         B200_CUDA(cudaMemsetAsync(grid, 0, sizeof(unsigned long long) * (size_t)std::max(1, geom.grid_cells) * batch, stream));

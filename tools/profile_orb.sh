@@ -1,10 +1,16 @@
 #!/bin/bash
-# ncu recipe (B200_PROFILING.md): launch list of one bench run + one full capture of each extractor kernel.
+# ncu recipe (B200_PROFILING.md), run under gpurun: bench JSON, launch list of the same command, one full capture of every
+# front-end kernel of one timed step, clocks during the timed region.  Outputs land in gpurun_out/ and are copied to profiles/.
 set -x
 mkdir -p gpurun_out
-python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_r1.json 2> gpurun_out/bench_r1.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_r1.csv \
-    python bench.py --steps 2 --warmup 3 --batch 64 --min-area 7100 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
+nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap --format=csv -lms 200 > gpurun_out/clocks_r1.csv &
+SMI=$!
+python bench.py --steps 20 --warmup 3 > gpurun_out/bench_r1_final.json 2> gpurun_out/bench_r1_final.err
+kill $SMI
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r1_reference.json 2>> gpurun_out/bench_r1_final.err
+ncu --metrics gpu__time_duration.sum --clock-control none -s 39 -c 13 --csv --log-file gpurun_out/launches_r1_final.csv \
+    python bench.py --steps 2 --warmup 3 --batch 64 --min-area 7100 --no-cpu-baseline --no-lba > gpurun_out/ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'fast_cells|blur_kernel|describe_kernel|resize_kernel|topk_kernel|resolve_kernel|select_kernel' \
-    -s 39 -c 13 -o gpurun_out/prof_r1 -f python bench.py --steps 2 --warmup 3 --batch 64 --min-area 7100 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+    -s 39 -c 13 -o gpurun_out/prof_r1_final -f python bench.py --steps 2 --warmup 3 --batch 64 --min-area 7100 --no-cpu-baseline --no-lba > gpurun_out/ncu_full.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/lba_launches_r1_final.csv python tools/lba_time.py stereo 1 > gpurun_out/lba_ncu.log 2>&1
 ls -la gpurun_out
