@@ -149,6 +149,46 @@ int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, const void* d
                                  size_t angle2_stride, const void* d_valid2, const void* d_off2, const void* d_cnt2, int max_n1,
                                  int max_n2, float lowe_ratio, int check_orientation, void* d_pairs, int pairs_stride,
                                  void* d_n_pairs);
+/* Grid-guided projection matchers
+ *   mode 0 (B200_GUIDED_LANDMARKS): match::projection::match_frame_and_landmarks     (src/stella_vslam/match/projection.cc:13-93)
+ *   mode 1 (B200_GUIDED_LAST_FRAME): match::projection::match_current_and_last_frames (src/stella_vslam/match/projection.cc:95-207)
+ * including the keypoint grid they search: data::assign_keypoints_to_grid / get_keypoints_in_cell
+ * (src/stella_vslam/data/common.cc:83-190).  The caller (the adapter) does what needs the map: it walks the landmarks in the
+ * reference's order, reprojects them (camera::base::reproject_to_image), predicts the pyramid level and fills one query per
+ * landmark; q_valid[q] == 0 marks a landmark the reference skips before the search (will_be_erased, !is_observable_in_tracking,
+ * reprojection failed / outside the image, last-frame outlier).  All pointers are HOST buffers.
+ * Result: match_out[q] = index of the frame keypoint landmark q is attached to (frm.add_landmark(lm, idx)) or -1, n_matches;
+ * t_occupied is updated in place (a keypoint that received a landmark is not offered to later landmarks, projection.cc:50-53,
+ * 163-166).  `n_problems` independent frames are processed in one launch sequence. */
+enum { B200_GUIDED_LANDMARKS = 0, B200_GUIDED_LAST_FRAME = 1 };
+typedef struct b200_guided_problem {
+    int32_t n_train;                  /* keypoints of the frame that is searched */
+    const float* t_x;                 /* frm_obs_.undist_keypts_[i].pt.x */
+    const float* t_y;
+    const uint8_t* t_octave;
+    const float* t_angle;             /* needed when mode 1 checks orientation, else may be NULL */
+    const float* t_x_right;           /* frm_obs_.stereo_x_right_, NULL when empty (monocular) */
+    const uint8_t* t_desc;            /* n_train x 32 */
+    uint8_t* t_occupied;              /* in/out, n_train: keypoint already carries a landmark with observations; NULL = none (no write-back) */
+    float min_x, max_x, min_y, max_y; /* camera::base::img_bounds_ */
+    int32_t grid_cols, grid_rows;     /* camera::base::num_grid_cols_ / num_grid_rows_ (64 x 48) */
+    int32_t n_queries;                /* landmarks in the reference's iteration order */
+    const uint8_t* q_desc;            /* n_queries x 32 (landmark::get_descriptor) */
+    const float* q_x;                 /* reprojection */
+    const float* q_y;
+    const float* q_margin;            /* margin * scale_factors_[level], evaluated in float like the reference */
+    const int8_t* q_min_level;        /* octave window; < 0 = unchecked (data/common.cc:160-173) */
+    const int8_t* q_max_level;
+    const float* q_x_right;           /* reprojected x_right; read only when t_x_right != NULL */
+    const float* q_angle;             /* last-frame keypoint angle; read only in mode 1 with check_orientation */
+    const uint8_t* q_valid;           /* NULL = all valid */
+    int32_t* match_out;               /* out, n_queries */
+    int32_t n_matches;                /* out */
+} b200_guided_problem_t;
+/* thr: HAMMING_DIST_THR_HIGH (100) in both reference callers; lowe_ratio is used by mode 0 only; max_candidates bounds the
+ * keypoints one search window may return (0 = default 256); B200_ERR_CAPACITY reports the size that would have been needed. */
+int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* problems, int mode, unsigned thr, float lowe_ratio,
+                      int check_orientation, int max_candidates);
 /* Run on the caller's stream (a cudaStream_t; NULL is the legacy default stream); use_own != 0 restores the own stream. */
 int b200_matcher_set_stream(b200_matcher_t h, void* stream, int use_own);
 int b200_matcher_sync(b200_matcher_t h);

@@ -62,6 +62,33 @@ float orc_angle_diff(float a1, float a2);
 int orc_brute_force_match(const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2, const float* angle2,
                           const uint8_t* valid2, int n2, float lowe_ratio, int check_orientation, int32_t* pairs_out);
 
+/* ---- grid-guided projection matchers (guided_oracle.c) ------------------------------------------------------------ */
+typedef struct {
+    int32_t n_train;                 /* frame keypoints (the side that is searched) */
+    const float* t_x;                /* undist_keypts_[i].pt.x */
+    const float* t_y;
+    const uint8_t* t_octave;
+    const float* t_angle;            /* may be NULL when orientation is not checked */
+    const float* t_x_right;          /* frm_obs_.stereo_x_right_ or NULL when empty */
+    const uint8_t* t_desc;           /* N x 32 */
+    uint8_t* t_occupied;             /* N, in/out: keypoint already carries a landmark with observations */
+    float min_x, max_x, min_y, max_y; /* camera->img_bounds_ */
+    int32_t grid_cols, grid_rows;    /* num_grid_cols_/rows_ (64 x 48) */
+    int32_t n_queries;               /* landmarks, in the reference's iteration order */
+    const uint8_t* q_desc;           /* Q x 32 (landmark::get_descriptor) */
+    const float* q_x;                /* reprojection */
+    const float* q_y;
+    const float* q_margin;           /* margin * scale_factors_[level] (float product) */
+    const int8_t* q_min_level;       /* < 0: unchecked */
+    const int8_t* q_max_level;
+    const float* q_x_right;          /* reprojected x_right (used when t_x_right != NULL) */
+    const float* q_angle;            /* mode 1 */
+    const uint8_t* q_valid;          /* 0: skipped before the search (not reprojected / will_be_erased / outside the image); NULL = all */
+} orc_guided_t;
+/* mode 0: projection::match_frame_and_landmarks (projection.cc:13-93); mode 1: match_current_and_last_frames (:95-207).
+ * match_out[q] = frame keypoint index or -1.  Returns the number of matches. */
+int orc_match_guided(const orc_guided_t* P, int mode, unsigned thr, float lowe_ratio, int check_orientation, int32_t* match_out);
+
 /* ---- local bundle adjustment (lba_oracle.c; PARITY UNPINNED, see its header) ------------------------------------- */
 typedef struct {
     int32_t model;            /* 0: perspective-family edges (Perspective/Fisheye/RadialDivision, reproj_edge_wrapper.h:64-188), 1: equirectangular */

@@ -210,6 +210,47 @@ def frontend_batch(frames, n, min_area=800, lowe_ratio=0.8, check_orientation=Tr
     return counts, matches
 
 
+# ---- grid-guided projection matchers --------------------------------------------------------------------------------------
+class GuidedProblem(C.Structure):
+    """orc_guided_t (oracle.h)."""
+    _fields_ = [("n_train", C.c_int32), ("t_x", C.c_void_p), ("t_y", C.c_void_p), ("t_octave", C.c_void_p), ("t_angle", C.c_void_p),
+                ("t_x_right", C.c_void_p), ("t_desc", C.c_void_p), ("t_occupied", C.c_void_p),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("grid_cols", C.c_int32), ("grid_rows", C.c_int32), ("n_queries", C.c_int32),
+                ("q_desc", C.c_void_p), ("q_x", C.c_void_p), ("q_y", C.c_void_p), ("q_margin", C.c_void_p), ("q_min_level", C.c_void_p),
+                ("q_max_level", C.c_void_p), ("q_x_right", C.c_void_p), ("q_angle", C.c_void_p), ("q_valid", C.c_void_p)]
+
+
+_GUIDED_FIELDS = (("t_x", "f4"), ("t_y", "f4"), ("t_octave", "u1"), ("t_angle", "f4"), ("t_x_right", "f4"), ("t_desc", "u1"),
+                  ("t_occupied", "u1"), ("q_desc", "u1"), ("q_x", "f4"), ("q_y", "f4"), ("q_margin", "f4"), ("q_min_level", "i1"),
+                  ("q_max_level", "i1"), ("q_x_right", "f4"), ("q_angle", "f4"), ("q_valid", "u1"))
+
+
+def match_guided(prob, mode, thr=100, lowe_ratio=0.8, check_orientation=True):
+    """orc_match_guided on a problem dict (keys: _GUIDED_FIELDS, bounds, grid).  Returns (match_out, occupied_after, n)."""
+    S, keep = GuidedProblem(), {}
+    for name, dt in _GUIDED_FIELDS:
+        v = prob.get(name)
+        if v is None and name == "t_occupied":
+            v = np.zeros(len(prob["t_x"]), np.uint8)
+        if v is None:
+            setattr(S, name, None)
+            continue
+        a = np.ascontiguousarray(v, np.dtype(dt))
+        if name == "t_occupied":
+            a = a.copy()
+        keep[name] = a
+        setattr(S, name, a.ctypes.data)
+    S.n_train, S.n_queries = len(keep["t_x"]), len(keep["q_x"])
+    S.min_x, S.max_x, S.min_y, S.max_y = [float(v) for v in prob["bounds"]]
+    S.grid_cols, S.grid_rows = prob.get("grid", (64, 48))
+    out = np.full(max(S.n_queries, 1), -2, np.int32)
+    L = lib()
+    L.orc_match_guided.argtypes = [C.POINTER(GuidedProblem), C.c_int, C.c_uint, C.c_float, C.c_int, C.c_void_p]
+    n = L.orc_match_guided(C.byref(S), mode, thr, lowe_ratio, int(check_orientation), out.ctypes.data)
+    return out[:S.n_queries].copy(), keep["t_occupied"], n
+
+
 # ---- local BA ---------------------------------------------------------------------------------------------------------
 class Camera(C.Structure):
     _fields_ = [("model", C.c_int32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),

@@ -31,13 +31,55 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
 _lib = None
 
 # every symbol include/b200vslam.h declares (tests check that the .so exports all of them)
+class GuidedProblem(C.Structure):
+    """b200_guided_problem_t (include/b200vslam.h)."""
+    _fields_ = [("n_train", C.c_int32), ("t_x", C.c_void_p), ("t_y", C.c_void_p), ("t_octave", C.c_void_p), ("t_angle", C.c_void_p),
+                ("t_x_right", C.c_void_p), ("t_desc", C.c_void_p), ("t_occupied", C.c_void_p),
+                ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
+                ("grid_cols", C.c_int32), ("grid_rows", C.c_int32), ("n_queries", C.c_int32),
+                ("q_desc", C.c_void_p), ("q_x", C.c_void_p), ("q_y", C.c_void_p), ("q_margin", C.c_void_p), ("q_min_level", C.c_void_p),
+                ("q_max_level", C.c_void_p), ("q_x_right", C.c_void_p), ("q_angle", C.c_void_p), ("q_valid", C.c_void_p),
+                ("match_out", C.c_void_p), ("n_matches", C.c_int32)]
+
+
+GUIDED_FIELDS = (("t_x", "f4"), ("t_y", "f4"), ("t_octave", "u1"), ("t_angle", "f4"), ("t_x_right", "f4"), ("t_desc", "u1"), ("t_occupied", "u1"),
+                 ("q_desc", "u1"), ("q_x", "f4"), ("q_y", "f4"), ("q_margin", "f4"), ("q_min_level", "i1"), ("q_max_level", "i1"),
+                 ("q_x_right", "f4"), ("q_angle", "f4"), ("q_valid", "u1"))
+
+
+def pack_guided_problem(prob, StructT=None):
+    """dict -> (struct, keep-alive arrays).  Keys: GUIDED_FIELDS (missing / None -> NULL), bounds=(min_x,max_x,min_y,max_y),
+    grid=(cols, rows).  The struct's match_out / t_occupied point into the returned arrays."""
+    import numpy as np
+    S = (StructT or GuidedProblem)()
+    keep = {}
+    for name, dt in GUIDED_FIELDS:
+        v = prob.get(name)
+        if v is None:
+            setattr(S, name, None)
+            continue
+        a = np.ascontiguousarray(v, np.dtype(dt))
+        if name == "t_occupied":
+            a = a.copy()
+        keep[name] = a
+        setattr(S, name, a.ctypes.data)
+    S.n_train = len(keep["t_x"]) if "t_x" in keep else 0
+    S.n_queries = len(keep["q_x"]) if "q_x" in keep else 0
+    S.min_x, S.max_x, S.min_y, S.max_y = [float(v) for v in prob["bounds"]]
+    S.grid_cols, S.grid_rows = prob.get("grid", (64, 48))
+    if hasattr(S, "match_out"):
+        keep["match_out"] = np.full(max(S.n_queries, 1), -2, np.int32)
+        S.match_out = keep["match_out"].ctypes.data
+    return S, keep
+
+
 SYMBOLS = [
     "b200_last_error", "b200_device_count", "b200_version", "b200_host_alloc", "b200_host_free",
     "b200_orb_default_params", "b200_orb_create", "b200_orb_destroy", "b200_orb_max_keypoints", "b200_orb_extract",
     "b200_orb_extract_device", "b200_orb_set_stream", "b200_orb_bind_outputs", "b200_orb_reserve", "b200_orb_fetch", "b200_orb_device_results", "b200_orb_sync", "b200_orb_level_info",
     "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_stage_ms", "b200_orb_enable_timing",
     "b200_matcher_create", "b200_matcher_destroy", "b200_hamming_matrix", "b200_match_bruteforce",
-    "b200_match_bruteforce_device", "b200_matcher_set_stream", "b200_matcher_sync",
+    "b200_match_bruteforce_device", "b200_match_guided", "b200_matcher_set_stream", "b200_matcher_sync",
     "b200_lba_create", "b200_lba_destroy", "b200_lba_solve", "b200_lba_last_profile",
 ]
 
@@ -81,6 +123,7 @@ def lib():
     L.b200_match_bruteforce.argtypes = [vp, i32, vp, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp, C.c_float, i32, vp, i32, vp]
     L.b200_match_bruteforce_device.argtypes = [vp, i32, vp, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp, i32, i32, C.c_float, i32,
                                                vp, i32, vp]
+    L.b200_match_guided.argtypes = [vp, i32, C.POINTER(GuidedProblem), i32, C.c_uint, C.c_float, i32, i32]
     L.b200_matcher_set_stream.argtypes = [vp, vp, i32]
     _lib = L
     return L

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <climits>
 #include <new>
+#include <cstring>
 #include <vector>
 
 #include "common.cuh"
@@ -331,6 +332,218 @@ __global__ void __launch_bounds__(32) resolve_kernel(Side S1, Side S2, const uns
     if (lane == 0) n_pairs[p] = total;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Grid-guided projection matchers
+//   match::projection::match_frame_and_landmarks      src/stella_vslam/match/projection.cc:13-93    (mode 0)
+//   match::projection::match_current_and_last_frames  src/stella_vslam/match/projection.cc:95-207   (mode 1)
+//   data::assign_keypoints_to_grid / get_keypoints_in_cell   src/stella_vslam/data/common.cc:83-190, data/common.h:60-68
+// G1 builds the keypoint grid (cell-x major, indices ascending inside a cell = the reference's iteration order), G2 lets one
+// thread per landmark enumerate its search window in that order and record (distance, octave, index) for every candidate
+// that passes the static gates, G3 replays the reference's sequential loop (a match removes the keypoint from all later
+// searches) with the same prefix-commit scheme as the brute-force resolve.
+// ---------------------------------------------------------------------------------------------------------------
+struct GuidedDev {
+    int n_train, n_queries, grid_cols, grid_rows, cap;
+    float min_x, max_x, min_y, max_y;
+    const float *t_x, *t_y, *t_angle, *t_x_right;
+    const unsigned char* t_octave;
+    const uint4* t_desc;
+    const uint4* q_desc;
+    const float *q_x, *q_y, *q_margin, *q_x_right, *q_angle;
+    const signed char *q_min_level, *q_max_level;
+    const unsigned char* q_valid;
+    // scratch + outputs of this problem
+    int *cell_start, *cell_items, *cell_cursor;
+    uint2* lists;
+    int* list_len;
+    unsigned char* occupied;
+    int* match_out;
+    int* n_matches;
+};
+
+__device__ __forceinline__ int cell_index(const GuidedDev& g, float x, float y, double inv_w, double inv_h) {
+    const int cx = __double2int_rd((double)__fsub_rn(x, g.min_x) * inv_w), cy = __double2int_rd((double)__fsub_rn(y, g.min_y) * inv_h);
+    return (0 <= cx && cx < g.grid_cols && 0 <= cy && cy < g.grid_rows) ? cx * g.grid_rows + cy : -1;
+}
+
+// G1: one CTA.  cell_start[c .. c+1) delimits the ascending keypoint indices of cell c (cell = cx * rows + cy).
+__global__ void __launch_bounds__(1024) guided_grid_kernel(const GuidedDev* __restrict__ gs) {
+    const GuidedDev g = gs[blockIdx.x];
+    int *cell_start = g.cell_start, *cell_items = g.cell_items, *cell_cursor = g.cell_cursor;
+    const int n_cells = g.grid_cols * g.grid_rows;
+    const double inv_w = (double)g.grid_cols / (double)__fsub_rn(g.max_x, g.min_x), inv_h = (double)g.grid_rows / (double)__fsub_rn(g.max_y, g.min_y);
+    for (int c = threadIdx.x; c <= n_cells; c += blockDim.x) cell_start[c] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.n_train; i += blockDim.x) {
+        const int c = cell_index(g, g.t_x[i], g.t_y[i], inv_w, inv_h);
+        if (c >= 0) atomicAdd(&cell_start[c + 1], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {  // exclusive scan (a few thousand cells)
+        int run = 0;
+        for (int c = 0; c <= n_cells; ++c) {
+            run += cell_start[c];
+            cell_start[c] = run;
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n_cells; c += blockDim.x) cell_cursor[c] = cell_start[c];
+    __syncthreads();
+    for (int i = threadIdx.x; i < g.n_train; i += blockDim.x) {
+        const int c = cell_index(g, g.t_x[i], g.t_y[i], inv_w, inv_h);
+        if (c >= 0) cell_items[atomicAdd(&cell_cursor[c], 1)] = i;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n_cells; c += blockDim.x) {  // restore ascending index order inside each (short) cell list
+        const int a = cell_start[c], b = cell_start[c + 1];
+        for (int i = a + 1; i < b; ++i) {
+            const int v = cell_items[i];
+            int j = i - 1;
+            while (j >= a && cell_items[j] > v) {
+                cell_items[j + 1] = cell_items[j];
+                --j;
+            }
+            cell_items[j + 1] = v;
+        }
+    }
+}
+
+// G2: one thread per landmark: enumerate the window, apply the static gates, record candidates in iteration order.
+// entry = distance << 8 | octave, idx
+__global__ void __launch_bounds__(128) guided_candidates_kernel(const GuidedDev* __restrict__ gs, int mode, int check_orientation,
+                                                                int* __restrict__ overflow) {
+    const GuidedDev g = gs[blockIdx.y];
+    const int *cell_start = g.cell_start, *cell_items = g.cell_items;
+    uint2* lists = g.lists;
+    int* list_len = g.list_len;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= g.n_queries) return;
+    int len = 0;
+    if (!g.q_valid || g.q_valid[q]) {
+        const double inv_w = (double)g.grid_cols / (double)__fsub_rn(g.max_x, g.min_x), inv_h = (double)g.grid_rows / (double)__fsub_rn(g.max_y, g.min_y);
+        const float ref_x = g.q_x[q], ref_y = g.q_y[q], margin = g.q_margin[q];
+        const int min_level = g.q_min_level[q], max_level = g.q_max_level[q];
+        // data/common.cc:137-155
+        const int min_cx = max(0, __double2int_rd((double)__fsub_rn(__fsub_rn(ref_x, g.min_x), margin) * inv_w));
+        const int max_cx = min(g.grid_cols - 1, __double2int_ru((double)__fadd_rn(__fsub_rn(ref_x, g.min_x), margin) * inv_w));
+        const int min_cy = max(0, __double2int_rd((double)__fsub_rn(__fsub_rn(ref_y, g.min_y), margin) * inv_h));
+        const int max_cy = min(g.grid_rows - 1, __double2int_ru((double)__fadd_rn(__fsub_rn(ref_y, g.min_y), margin) * inv_h));
+        if (min_cx < g.grid_cols && max_cx >= 0 && min_cy < g.grid_rows && max_cy >= 0) {
+            const uint4 q0 = g.q_desc[(size_t)q * 2], q1 = g.q_desc[(size_t)q * 2 + 1];
+            uint2* out = lists + (size_t)q * g.cap;
+            for (int cx = min_cx; cx <= max_cx; ++cx)
+                for (int cy = min_cy; cy <= max_cy; ++cy) {
+                    const int c = cx * g.grid_rows + cy;
+                    for (int k = cell_start[c]; k < cell_start[c + 1]; ++k) {
+                        const int idx = cell_items[k];
+                        const int oct = g.t_octave[idx];
+                        if (0 <= min_level && oct < min_level) continue;
+                        if (0 <= max_level && max_level < oct) continue;
+                        const float dx = __fsub_rn(g.t_x[idx], ref_x), dy = __fsub_rn(g.t_y[idx], ref_y);
+                        if (!(fabsf(dx) < margin && fabsf(dy) < margin)) continue;
+                        if (g.t_x_right) {  // stereo gate (projection.cc:56-61, 168-173)
+                            const float xr = g.t_x_right[idx];
+                            if (0.f < xr && margin < fabsf(__fsub_rn(g.q_x_right[q], xr))) continue;
+                        }
+                        if (mode == 1 && check_orientation && orientation_rejects(g.q_angle[q], g.t_angle[idx])) continue;
+                        const unsigned d = hamming256(q0, q1, g.t_desc[(size_t)idx * 2], g.t_desc[(size_t)idx * 2 + 1]);
+                        if (len < g.cap) out[len] = make_uint2((d << 8) | (unsigned)oct, (unsigned)idx);
+                        ++len;
+                    }
+                }
+        }
+    }
+    if (len > g.cap) {
+        atomicMax(overflow, len);
+        len = g.cap;
+    }
+    list_len[q] = len;
+}
+
+// the reference's best / second update in iteration order over the keypoints that are still free; returns the accepted index or -1
+__device__ __forceinline__ int guided_decide(const uint2* __restrict__ list, int len, const volatile unsigned* occupied, int mode, unsigned thr,
+                                             float lowe_ratio) {
+    unsigned best = kMaxDist, second = kMaxDist;
+    int best_level = -1, second_level = -1, best_idx = -1;
+    for (int k = 0; k < len; ++k) {
+        const uint2 e = list[k];
+        const unsigned idx = e.y;
+        if ((occupied[idx >> 5] >> (idx & 31)) & 1u) continue;
+        const unsigned d = e.x >> 8;
+        const int oct = (int)(e.x & 0xFF);
+        if (d < best) {
+            second = best;
+            second_level = best_level;
+            best = d;
+            best_level = oct;
+            best_idx = (int)idx;
+        } else if (mode == 0 && d < second) {
+            second_level = oct;
+            second = d;
+        }
+    }
+    if (best_idx < 0 || best > thr) return -1;
+    if (mode == 0 && best_level == second_level && (float)best > __fmul_rn(lowe_ratio, (float)second)) return -1;
+    return best_idx;
+}
+
+// G3: one warp; shared memory: [occupied bitmap][claim per keypoint].  A lane's decision is safe to commit when no lower lane of
+// the batch wants ANY keypoint of its list (that is the only way an earlier landmark can change a later one's outcome).
+__global__ void __launch_bounds__(32) guided_resolve_kernel(const GuidedDev* __restrict__ gs, int mode, unsigned thr, float lowe_ratio) {
+    extern __shared__ unsigned guided_smem[];
+    const GuidedDev g = gs[blockIdx.x];
+    const uint2* lists = g.lists;
+    const int* list_len = g.list_len;
+    unsigned char* occupied_io = g.occupied;
+    int *match_out = g.match_out, *n_matches = g.n_matches;
+    const int lane = threadIdx.x, words = (g.n_train + 31) / 32;
+    unsigned* occupied = guided_smem;
+    int* claim = reinterpret_cast<int*>(guided_smem + words);
+    for (int w = lane; w < words; w += 32) {
+        unsigned bits = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int i = w * 32 + b;
+            if (i < g.n_train && occupied_io[i]) bits |= 1u << b;
+        }
+        occupied[w] = bits;
+    }
+    for (int i = lane; i < g.n_train; i += 32) claim[i] = 255;
+    __syncwarp();
+    int total = 0;
+    for (int base = 0; base < g.n_queries; base += 32) {
+        const int q = base + lane;
+        const int len = (q < g.n_queries) ? list_len[q] : 0;
+        const uint2* list = lists + (size_t)min(q, g.n_queries - 1) * g.cap;
+        if (q < g.n_queries) match_out[q] = -1;
+        unsigned pending = __ballot_sync(0xFFFFFFFFu, len > 0);
+        while (pending) {
+            const bool mine = (pending >> lane) & 1u;
+            const int acc = mine ? guided_decide(list, len, occupied, mode, thr, lowe_ratio) : -1;
+            if (acc >= 0) atomicMin(&claim[acc], lane);  // claim[idx] = lowest lane that wants idx this round
+            __syncwarp();
+            bool conflict = false;
+            if (mine)
+                for (int k = 0; k < len; ++k) conflict |= claim[list[k].y] < lane;
+            const unsigned unsafe = __ballot_sync(0xFFFFFFFFu, mine && conflict);
+            const int first_unsafe = unsafe ? __ffs(unsafe) - 1 : 32;
+            const unsigned commit = pending & ((first_unsafe >= 32) ? 0xFFFFFFFFu : ((1u << first_unsafe) - 1u));
+            const bool do_commit = (commit >> lane) & 1u;
+            __syncwarp();
+            if (acc >= 0) claim[acc] = 255;  // reset for the next round
+            if (do_commit && acc >= 0) {
+                atomicOr(&occupied[acc >> 5], 1u << (acc & 31));
+                match_out[q] = acc;
+            }
+            total += __popc(__ballot_sync(0xFFFFFFFFu, do_commit && acc >= 0));
+            pending &= ~commit;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    for (int i = lane; i < g.n_train; i += 32) occupied_io[i] = (occupied[i >> 5] >> (i & 31)) & 1u;
+    if (lane == 0) *n_matches = total;
+}
+
 struct Matcher {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -345,6 +558,23 @@ struct Matcher {
     unsigned char* d_stage = nullptr;
     size_t stage_cap = 0;
     size_t last_h2d = 0, last_d2h = 0;
+    // grid-guided matchers: pinned host staging + device arena
+    unsigned char* h_guided = nullptr;
+    size_t h_guided_cap = 0;
+    unsigned char* d_guided = nullptr;
+    size_t d_guided_cap = 0;
+
+    int grow_pinned(unsigned char** p, size_t* cap, size_t bytes) {
+        if (bytes <= *cap) return B200_OK;
+        B200_CUDA(cudaStreamSynchronize(stream));
+        if (*p) B200_CUDA(cudaFreeHost(*p));
+        *p = nullptr;
+        *cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        B200_CUDA(cudaMallocHost((void**)p, want));
+        *cap = want;
+        return B200_OK;
+    }
 
     int grow(void** p, size_t* cap, size_t bytes) {
         if (bytes <= *cap) return B200_OK;
@@ -427,6 +657,8 @@ int b200_matcher_destroy(b200_matcher_t h) {
     cudaFree(h->m.d_matched);
     cudaFree(h->m.d_taken);
     cudaFree(h->m.d_stage);
+    cudaFree(h->m.d_guided);
+    if (h->m.h_guided) cudaFreeHost(h->m.h_guided);
     if (h->m.own_stream) cudaStreamDestroy(h->m.own_stream);
     delete h;
     return B200_OK;
@@ -541,6 +773,184 @@ int b200_match_bruteforce(b200_matcher_t h, int n_problems, const uint8_t* desc1
     B200_CUDA(cudaMemcpyAsync(n_pairs, s + o_np, sizeof(int) * n_problems, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaMemcpyAsync(pairs, s + o_pr, sizeof(int) * 2 * (size_t)pairs_stride * n_problems, cudaMemcpyDeviceToHost, st));
     B200_CUDA(cudaStreamSynchronize(st));
+    return B200_OK;
+}
+
+int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* problems, int mode, unsigned thr, float lowe_ratio,
+                      int check_orientation, int max_candidates) {
+    using b200::match::GuidedDev;
+    if (!h || n_problems < 0 || (mode != B200_GUIDED_LANDMARKS && mode != B200_GUIDED_LAST_FRAME) || max_candidates < 0) return B200_ERR_INVALID;
+    if (n_problems == 0) return B200_OK;
+    if (!problems) return B200_ERR_INVALID;
+    auto& m = h->m;
+    B200_CUDA(cudaSetDevice(m.device));
+    const int cap = max_candidates ? max_candidates : 256;
+    auto al = [](size_t v) { return b200::round_up(v, (size_t)256); };
+    // layout of the arena: [GuidedDev x n][inputs of every problem][outputs of every problem][scratch]; the first two parts are
+    // mirrored in pinned host memory and go up in one copy, the output part comes back in one copy.
+    struct Lay {
+        size_t tx, ty, toct, tang, txr, tdesc, qdesc, qx, qy, qm, qlo, qhi, qxr, qang, qval;  // inputs
+        size_t occ, mout, nm;                                                                // outputs
+        size_t cstart, citems, ccur, lists, llen;                                            // scratch
+    };
+    std::vector<Lay> lay(n_problems);
+    size_t o = al(sizeof(GuidedDev) * (size_t)n_problems);
+    int max_q = 0, max_train = 0;
+    for (int p = 0; p < n_problems; ++p) {
+        const b200_guided_problem_t& P = problems[p];
+        const bool need_angle = mode == B200_GUIDED_LAST_FRAME && check_orientation;
+        if (P.n_train < 0 || P.n_queries < 0 || P.grid_cols <= 0 || P.grid_rows <= 0 || !(P.max_x > P.min_x) || !(P.max_y > P.min_y)
+            || (long long)P.grid_cols * P.grid_rows > (1 << 20)) {
+            b200::set_error("b200_match_guided: bad sizes / image bounds in problem %d", p);
+            return B200_ERR_INVALID;
+        }
+        if ((P.n_train > 0 && (!P.t_x || !P.t_y || !P.t_octave || !P.t_desc || (need_angle && !P.t_angle)))
+            || (P.n_queries > 0
+                && (!P.q_desc || !P.q_x || !P.q_y || !P.q_margin || !P.q_min_level || !P.q_max_level || !P.match_out
+                    || (need_angle && !P.q_angle) || (P.t_x_right && !P.q_x_right)))) {
+            b200::set_error("b200_match_guided: null buffer in problem %d", p);
+            return B200_ERR_INVALID;
+        }
+        Lay& L = lay[p];
+        const size_t nt = (size_t)std::max(P.n_train, 1), nq = (size_t)std::max(P.n_queries, 1);
+        L.tx = o; o += al(4 * nt);
+        L.ty = o; o += al(4 * nt);
+        L.toct = o; o += al(nt);
+        L.tang = o; o += al(4 * nt);
+        L.txr = o; o += al(4 * nt);
+        L.tdesc = o; o += al(32 * nt);
+        L.qdesc = o; o += al(32 * nq);
+        L.qx = o; o += al(4 * nq);
+        L.qy = o; o += al(4 * nq);
+        L.qm = o; o += al(4 * nq);
+        L.qlo = o; o += al(nq);
+        L.qhi = o; o += al(nq);
+        L.qxr = o; o += al(4 * nq);
+        L.qang = o; o += al(4 * nq);
+        L.qval = o; o += al(nq);
+        L.occ = o; o += al(nt);  // in AND out: kept at the end of the problem's input block
+        max_q = std::max(max_q, P.n_queries);
+        max_train = std::max(max_train, P.n_train);
+    }
+    const size_t in_bytes = o;
+    const size_t out_begin = o;
+    for (int p = 0; p < n_problems; ++p) {
+        Lay& L = lay[p];
+        L.mout = o; o += al(4 * (size_t)std::max(problems[p].n_queries, 1));
+        L.nm = o; o += al(4);
+    }
+    const size_t o_overflow = o;
+    o += al(4);
+    const size_t out_end = o;
+    for (int p = 0; p < n_problems; ++p) {
+        const b200_guided_problem_t& P = problems[p];
+        Lay& L = lay[p];
+        const size_t cells = (size_t)P.grid_cols * P.grid_rows;
+        L.cstart = o; o += al(4 * (cells + 1));
+        L.citems = o; o += al(4 * (size_t)std::max(P.n_train, 1));
+        L.ccur = o; o += al(4 * cells);
+        L.lists = o; o += al(8 * (size_t)cap * std::max(P.n_queries, 1));
+        L.llen = o; o += al(4 * (size_t)std::max(P.n_queries, 1));
+    }
+    const size_t rs_bytes = sizeof(unsigned) * ((size_t)b200::ceil_div(std::max(max_train, 1), 32) + (size_t)std::max(max_train, 1));
+    if (rs_bytes > 200 * 1024) {
+        b200::set_error("b200_match_guided: %d keypoints per frame exceed the on-chip occupancy table", max_train);
+        return B200_ERR_CAPACITY;
+    }
+    int rc;
+    if ((rc = m.grow((void**)&m.d_guided, &m.d_guided_cap, o))) return rc;
+    if ((rc = m.grow_pinned(&m.h_guided, &m.h_guided_cap, out_end))) return rc;
+    unsigned char *hb = m.h_guided, *db = m.d_guided;
+    GuidedDev* hg = reinterpret_cast<GuidedDev*>(hb);
+    auto put = [&](size_t off, const void* src, size_t bytes) {
+        if (src && bytes) std::memcpy(hb + off, src, bytes);
+    };
+    for (int p = 0; p < n_problems; ++p) {
+        const b200_guided_problem_t& P = problems[p];
+        const Lay& L = lay[p];
+        const size_t nt = (size_t)P.n_train, nq = (size_t)P.n_queries;
+        put(L.tx, P.t_x, 4 * nt);
+        put(L.ty, P.t_y, 4 * nt);
+        put(L.toct, P.t_octave, nt);
+        put(L.tang, P.t_angle, 4 * nt);
+        put(L.txr, P.t_x_right, 4 * nt);
+        put(L.tdesc, P.t_desc, 32 * nt);
+        put(L.qdesc, P.q_desc, 32 * nq);
+        put(L.qx, P.q_x, 4 * nq);
+        put(L.qy, P.q_y, 4 * nq);
+        put(L.qm, P.q_margin, 4 * nq);
+        put(L.qlo, P.q_min_level, nq);
+        put(L.qhi, P.q_max_level, nq);
+        put(L.qxr, P.q_x_right, 4 * nq);
+        put(L.qang, P.q_angle, 4 * nq);
+        put(L.qval, P.q_valid, nq);
+        if (P.t_occupied) put(L.occ, P.t_occupied, nt);
+        else std::memset(hb + L.occ, 0, nt);
+        GuidedDev g{};
+        g.n_train = P.n_train;
+        g.n_queries = P.n_queries;
+        g.grid_cols = P.grid_cols;
+        g.grid_rows = P.grid_rows;
+        g.cap = cap;
+        g.min_x = P.min_x; g.max_x = P.max_x; g.min_y = P.min_y; g.max_y = P.max_y;
+        g.t_x = (const float*)(db + L.tx);
+        g.t_y = (const float*)(db + L.ty);
+        g.t_angle = (const float*)(db + L.tang);
+        g.t_x_right = P.t_x_right ? (const float*)(db + L.txr) : nullptr;
+        g.t_octave = db + L.toct;
+        g.t_desc = (const uint4*)(db + L.tdesc);
+        g.q_desc = (const uint4*)(db + L.qdesc);
+        g.q_x = (const float*)(db + L.qx);
+        g.q_y = (const float*)(db + L.qy);
+        g.q_margin = (const float*)(db + L.qm);
+        g.q_x_right = (const float*)(db + L.qxr);
+        g.q_angle = (const float*)(db + L.qang);
+        g.q_min_level = (const signed char*)(db + L.qlo);
+        g.q_max_level = (const signed char*)(db + L.qhi);
+        g.q_valid = P.q_valid ? db + L.qval : nullptr;
+        g.cell_start = (int*)(db + L.cstart);
+        g.cell_items = (int*)(db + L.citems);
+        g.cell_cursor = (int*)(db + L.ccur);
+        g.lists = (uint2*)(db + L.lists);
+        g.list_len = (int*)(db + L.llen);
+        g.occupied = db + L.occ;
+        g.match_out = (int*)(db + L.mout);
+        g.n_matches = (int*)(db + L.nm);
+        hg[p] = g;
+    }
+    cudaStream_t st = m.stream;
+    B200_CUDA(cudaMemcpyAsync(db, hb, in_bytes, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemsetAsync(db + o_overflow, 0, 4, st));
+    const GuidedDev* dg = reinterpret_cast<const GuidedDev*>(db);
+    b200::match::guided_grid_kernel<<<n_problems, 1024, 0, st>>>(dg);
+    b200::match::guided_candidates_kernel<<<dim3(std::max(1, b200::ceil_div(max_q, 128)), n_problems), 128, 0, st>>>(dg, mode, check_orientation,
+                                                                                                                     (int*)(db + o_overflow));
+    if (rs_bytes > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(b200::match::guided_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_bytes));
+    b200::match::guided_resolve_kernel<<<n_problems, 32, rs_bytes, st>>>(dg, mode, thr, lowe_ratio);
+    B200_CUDA(cudaGetLastError());
+    // outputs: occupancy lives in the input block (copied back per problem only when asked for), the rest is contiguous
+    B200_CUDA(cudaMemcpyAsync(hb + out_begin, db + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, st));
+    size_t occ_bytes = 0;
+    for (int p = 0; p < n_problems; ++p)
+        if (problems[p].t_occupied && problems[p].n_train > 0) {
+            B200_CUDA(cudaMemcpyAsync(hb + lay[p].occ, db + lay[p].occ, (size_t)problems[p].n_train, cudaMemcpyDeviceToHost, st));
+            occ_bytes += (size_t)problems[p].n_train;
+        }
+    B200_CUDA(cudaStreamSynchronize(st));
+    m.last_h2d = in_bytes;
+    m.last_d2h = out_end - out_begin + occ_bytes;
+    const int overflow = *reinterpret_cast<const int*>(hb + o_overflow);
+    if (overflow > 0) {
+        b200::set_error("b200_match_guided: a search window returned %d keypoints, max_candidates is %d", overflow, cap);
+        return B200_ERR_CAPACITY;
+    }
+    for (int p = 0; p < n_problems; ++p) {
+        b200_guided_problem_t& P = problems[p];
+        if (P.n_queries > 0) std::memcpy(P.match_out, hb + lay[p].mout, 4 * (size_t)P.n_queries);
+        P.n_matches = *reinterpret_cast<const int*>(hb + lay[p].nm);
+        if (P.t_occupied && P.n_train > 0) std::memcpy(P.t_occupied, hb + lay[p].occ, (size_t)P.n_train);
+    }
     return B200_OK;
 }
 

@@ -4,7 +4,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import check, lib, ptr
+from ._lib import GuidedProblem, check, lib, pack_guided_problem, ptr
 
 HAMMING_DIST_THR_LOW = 50    # match/base.h:15
 HAMMING_DIST_THR_HIGH = 100  # match/base.h:16
@@ -81,3 +81,65 @@ class robust(base):
                                           ptr(v2), ptr(off2), ptr(cnt2), float(self.lowe_ratio_), int(self.check_orientation_),
                                           ptr(pairs), stride, ptr(n_pairs)))
         return [pairs[i, :n_pairs[i]].copy() for i in range(P)]
+
+
+class projection(base):
+    """match::projection (match/projection.h:24-67): the two per-frame grid-guided matchers
+    match_frame_and_landmarks (projection.cc:13-93) and match_current_and_last_frames (:95-207).
+
+    A frame is described by a dict `frm` with t_x, t_y, t_octave, t_angle, t_desc, optional t_x_right / t_occupied,
+    bounds=(min_x, max_x, min_y, max_y) = camera img_bounds_, grid=(64, 48), scale_factors (orb_params_->scale_factors_)."""
+
+    GUIDED_LANDMARKS, GUIDED_LAST_FRAME = 0, 1
+
+    def __init__(self, lowe_ratio=0.6, check_orientation=True, device=0):
+        super().__init__(lowe_ratio, check_orientation)
+        self.device = device
+
+    def match_guided_batch(self, problems, mode, thr=HAMMING_DIST_THR_HIGH, max_candidates=0):
+        """problems: flattened dicts (see _lib.pack_guided_problem).  Returns [(match_out, occupied_after | None, n_matches)]."""
+        if not problems:
+            return []
+        arr = (GuidedProblem * len(problems))()
+        keeps = []
+        for i, pr in enumerate(problems):
+            S, keep = pack_guided_problem(pr)
+            arr[i] = S
+            keeps.append(keep)
+        check(lib().b200_match_guided(_matcher(self.device), len(problems), arr, mode, thr, float(self.lowe_ratio_), int(self.check_orientation_),
+                                      max_candidates))
+        return [(k["match_out"][:arr[i].n_queries].copy(), k.get("t_occupied"), int(arr[i].n_matches)) for i, k in enumerate(keeps)]
+
+    @staticmethod
+    def _query_fields(frm, desc, reproj, level, min_level, max_level, margin, x_right, angle, valid):
+        sf = np.asarray(frm["scale_factors"], np.float32)
+        level = np.asarray(level, np.int64)
+        reproj = np.asarray(reproj, np.float64).reshape(-1, 2)
+        pr = {k: v for k, v in frm.items() if k.startswith("t_") or k in ("bounds", "grid")}
+        pr.update(q_desc=desc, q_x=reproj[:, 0].astype(np.float32), q_y=reproj[:, 1].astype(np.float32),
+                  q_margin=np.float32(margin) * sf[level], q_min_level=min_level, q_max_level=max_level, q_x_right=x_right, q_angle=angle,
+                  q_valid=valid)
+        return pr
+
+    def match_frame_and_landmarks(self, frm, lm_desc, lm_to_reproj, lm_to_scale, margin=5.0, lm_to_x_right=None, valid=None):
+        """Landmark q (in local_landmarks order) reprojects to lm_to_reproj[q] at predicted level lm_to_scale[q];
+        valid[q] = 0 for landmarks without a reprojection or about to be erased (projection.cc:23-28)."""
+        n_levels = len(frm["scale_factors"])
+        lv = np.asarray(lm_to_scale, np.int64)
+        pr = self._query_fields(frm, lm_desc, lm_to_reproj, lv, np.maximum(0, lv - 1), np.minimum(n_levels - 1, lv + 1), margin, lm_to_x_right,
+                                None, valid)
+        return self.match_guided_batch([pr], self.GUIDED_LANDMARKS)[0]
+
+    def match_current_and_last_frames(self, curr_frm, last_desc, last_reproj, last_octave, last_angle, margin, last_x_right=None, valid=None,
+                                      assume_forward=False, assume_backward=False):
+        """Query q = keypoint q of the last frame that carries a landmark (valid[q]), reprojected into the current frame
+        (projection.cc:121-160); level window per :140-154."""
+        n_levels = len(curr_frm["scale_factors"])
+        lv = np.asarray(last_octave, np.int64)
+        lo, hi = np.maximum(0, lv - 1), np.minimum(n_levels - 1, lv + 1)
+        if assume_forward:
+            lo = lv
+        elif assume_backward:
+            hi = lv
+        pr = self._query_fields(curr_frm, last_desc, last_reproj, lv, lo, hi, margin, last_x_right, last_angle, valid)
+        return self.match_guided_batch([pr], self.GUIDED_LAST_FRAME)[0]

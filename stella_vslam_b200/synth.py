@@ -222,3 +222,62 @@ def make_ba_problem(n_poses=50, n_fixed=10, n_points=10000, seed=0, model="stere
                 e_point=np.array(e_point, np.int32), e_cam=np.zeros(E, np.uint8), e_obs=np.array(e_obs, np.float32).reshape(E, 3),
                 e_inv_sigma_sq=np.array(e_isq, np.float32), e_delta=np.full(E, chi, np.float32), e_robust=None,
                 e_can_be_outlier=None, cams=[cam], gt_pose_cw=gt_pose, gt_points=pts)
+
+
+def make_guided_problem(seed, n_train=2000, n_queries=1500, mode=0, stereo=False, width=640, height=480, margin=5.0, num_levels=8,
+                        scale_factor=1.2):
+    """A synthetic problem for the grid-guided projection matchers (match.projection): a frame with `n_train` keypoints and
+    `n_queries` landmarks that reproject near some of them.  Built to exercise every gate: several landmarks compete for one
+    keypoint (the sequential occupancy matters), near-duplicate descriptors sit next to each other (ratio test), octaves fall
+    outside the level window, some keypoints are pre-occupied, some landmarks are invalid, undistorted bounds are fractional and
+    a few keypoints / reprojections fall outside them."""
+    rng = np.random.default_rng(seed)
+    sf = np.float32(1.0) * np.cumprod(np.concatenate([[np.float32(1.0)], np.full(num_levels - 1, np.float32(scale_factor))])).astype(np.float32)
+    bounds = (np.float32(-11.37), np.float32(width + 9.21), np.float32(-7.9), np.float32(height + 6.53))
+    # keypoints: uniform background + tight clusters
+    n_cl = n_train // 3
+    centers = rng.uniform([0, 0], [width, height], (max(n_cl // 12, 1), 2))
+    pts = np.concatenate([rng.uniform([bounds[0] - 3, bounds[2] - 3], [bounds[1] + 3, bounds[3] + 3], (n_train - n_cl, 2)),
+                          centers[rng.integers(0, len(centers), n_cl)] + rng.normal(0, 4.0, (n_cl, 2))])
+    pts = pts[rng.permutation(n_train)].astype(np.float32)
+    octave = rng.choice(num_levels, n_train, p=np.array([.3, .22, .16, .12, .08, .06, .04, .02])).astype(np.uint8)
+    angle = rng.uniform(0, 360, n_train).astype(np.float32)
+    desc = rng.integers(0, 256, (n_train, 32), dtype=np.uint8)
+    # near-duplicate descriptors between spatial neighbours (sorted by x so duplicates are usually inside one window)
+    order = np.argsort(pts[:, 0], kind="stable")
+    for a, b in zip(order[0:n_train - 1:7], order[1:n_train:7]):
+        noise = rng.integers(0, 256, 32, dtype=np.uint8) & rng.integers(0, 256, 32, dtype=np.uint8) & rng.integers(0, 256, 32, dtype=np.uint8) \
+            & rng.integers(0, 256, 32, dtype=np.uint8)
+        desc[b] = desc[a] ^ noise
+        if rng.random() < 0.5:
+            octave[b] = octave[a]
+    src = rng.integers(0, n_train, n_queries)
+    src[1::5] = src[0:n_queries - 1:5][:len(src[1::5])]          # two landmarks on one keypoint
+    strength = rng.integers(1, 6, n_queries)                     # AND of k random bytes: ~ 256 / 2^k flipped bits
+    q_desc = desc[src].copy()
+    for k in range(1, 6):  # per-landmark noise level
+        sel = strength == k
+        fl = rng.integers(0, 256, (sel.sum(), 32), dtype=np.uint8)
+        for _ in range(k):
+            fl &= rng.integers(0, 256, (sel.sum(), 32), dtype=np.uint8)
+        q_desc[sel] ^= fl
+    level = np.clip(octave[src].astype(np.int64) + rng.integers(-2, 3, n_queries), 0, num_levels - 1)
+    q_xy = pts[src].astype(np.float64) + rng.normal(0, 2.5, (n_queries, 2))
+    far = rng.random(n_queries) < 0.03
+    q_xy[far] += rng.normal(0, 400, (far.sum(), 2))
+    q_margin = (np.float32(margin) * sf[level]).astype(np.float32)
+    lo, hi = np.maximum(0, level - 1), np.minimum(num_levels - 1, level + 1)
+    unchecked = rng.random(n_queries) < 0.05
+    lo[unchecked], hi[unchecked] = -1, -1
+    prob = dict(t_x=pts[:, 0].copy(), t_y=pts[:, 1].copy(), t_octave=octave, t_angle=angle, t_desc=desc,
+                t_occupied=(rng.random(n_train) < 0.08).astype(np.uint8), bounds=bounds, grid=(64, 48), scale_factors=sf,
+                q_desc=q_desc, q_x=q_xy[:, 0].astype(np.float32), q_y=q_xy[:, 1].astype(np.float32), q_margin=q_margin,
+                q_min_level=lo.astype(np.int8), q_max_level=hi.astype(np.int8),
+                q_angle=((angle[src] + rng.normal(0, 18, n_queries)) % 360).astype(np.float32),
+                q_valid=(rng.random(n_queries) > 0.1).astype(np.uint8))
+    if stereo:
+        xr = (pts[:, 0] - rng.uniform(2, 60, n_train)).astype(np.float32)
+        xr[rng.random(n_train) < 0.3] = -1.0                    # no stereo match for this keypoint
+        prob["t_x_right"] = xr
+        prob["q_x_right"] = (xr[src] + rng.normal(0, q_margin * 0.6)).astype(np.float32)
+    return prob
