@@ -152,15 +152,23 @@ int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, const void* d
 /* Grid-guided projection matchers
  *   mode 0 (B200_GUIDED_LANDMARKS): match::projection::match_frame_and_landmarks     (src/stella_vslam/match/projection.cc:13-93)
  *   mode 1 (B200_GUIDED_LAST_FRAME): match::projection::match_current_and_last_frames (src/stella_vslam/match/projection.cc:95-207)
+ * and, on the same search primitive, the occasional (relocalisation / loop closure / mapping / initialisation) variants:
+ *   mode 1 with thr = hamm_dist_thr, t_x_right = NULL:        projection::match_frame_and_keyframe  (projection.cc:217-319)
+ *   mode 1 with thr = 50, check_orientation = 0:              projection::match_by_Sim3_transform   (projection.cc:321-416)
+ *   mode 2 (B200_GUIDED_INDEPENDENT) once per direction, then b200_match_cross_check:
+ *                                                             projection::match_keyframes_mutually  (projection.cc:418-630)
+ *   mode 3 (B200_GUIDED_FUSE) with thr = 50:                  fuse::detect_duplication              (match/fuse.cc:12-154)
+ *   mode 4 (B200_GUIDED_AREA) with thr = 50, lowe_ratio:      area::match_in_consistent_area        (match/area.cc:8-98); a later
+ *        query may take a keypoint over from an earlier one (its match_out entry goes back to -1, area.cc:75-81)
  * including the keypoint grid they search: data::assign_keypoints_to_grid / get_keypoints_in_cell
  * (src/stella_vslam/data/common.cc:83-190).  The caller (the adapter) does what needs the map: it walks the landmarks in the
  * reference's order, reprojects them (camera::base::reproject_to_image), predicts the pyramid level and fills one query per
  * landmark; q_valid[q] == 0 marks a landmark the reference skips before the search (will_be_erased, !is_observable_in_tracking,
  * reprojection failed / outside the image, last-frame outlier).  All pointers are HOST buffers.
  * Result: match_out[q] = index of the frame keypoint landmark q is attached to (frm.add_landmark(lm, idx)) or -1, n_matches;
- * t_occupied is updated in place (a keypoint that received a landmark is not offered to later landmarks, projection.cc:50-53,
- * 163-166).  `n_problems` independent frames are processed in one launch sequence. */
-enum { B200_GUIDED_LANDMARKS = 0, B200_GUIDED_LAST_FRAME = 1 };
+ * t_occupied is updated in place in modes 0, 1 and 3 (a keypoint that received a landmark is not offered to later landmarks,
+ * projection.cc:50-53, 163-166, 292-294, 388-390; fuse.cc:88-90); mode 2 reads it only, mode 4 ignores it.  `n_problems` independent frames are processed in one launch sequence. */
+enum { B200_GUIDED_LANDMARKS = 0, B200_GUIDED_LAST_FRAME = 1, B200_GUIDED_INDEPENDENT = 2, B200_GUIDED_FUSE = 3, B200_GUIDED_AREA = 4 };
 typedef struct b200_guided_problem {
     int32_t n_train;                  /* keypoints of the frame that is searched */
     const float* t_x;                 /* frm_obs_.undist_keypts_[i].pt.x */
@@ -182,13 +190,59 @@ typedef struct b200_guided_problem {
     const float* q_x_right;           /* reprojected x_right; read only when t_x_right != NULL */
     const float* q_angle;             /* last-frame keypoint angle; read only in mode 1 with check_orientation */
     const uint8_t* q_valid;           /* NULL = all valid */
+    const double* q_reproj;           /* mode 3 with do_reprojection_matching: n_queries x 2, the reprojection in double (fuse.cc:96-97) */
+    const float* inv_level_sigma_sq;  /* mode 3: orb_params_->inv_level_sigma_sq_, n_levels entries */
+    int32_t n_levels;
+    int32_t do_reprojection_matching; /* mode 3 (fuse.cc:19, :93) */
     int32_t* match_out;               /* out, n_queries */
     int32_t n_matches;                /* out */
 } b200_guided_problem_t;
-/* thr: HAMMING_DIST_THR_HIGH (100) in both reference callers; lowe_ratio is used by mode 0 only; max_candidates bounds the
+/* thr: the reference's `best <= thr` acceptance (100 for modes 0-2 in the callers cited, 50 for 3-4); lowe_ratio: modes 0 and 4; max_candidates bounds the
  * keypoints one search window may return (0 = default 256); B200_ERR_CAPACITY reports the size that would have been needed. */
 int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* problems, int mode, unsigned thr, float lowe_ratio,
                       int check_orientation, int max_candidates);
+/* Closing loop of match_keyframes_mutually (projection.cc:614-627) on two mode-2 results: mutual_out[i] = j iff idx2_in_1[i] == j
+ * and idx1_in_2[j] == i, else -1.  Host-side, no device work. */
+int b200_match_cross_check(const int32_t* idx2_in_1, int n1, const int32_t* idx1_in_2, int n2, int32_t* mutual_out, int32_t* n_mutual);
+/* All-pairs matchers with greedy state, other than brute_force_match:
+ *   variant 0 (B200_PAIRS_BOW):           match::bow_tree::match_frame_and_keyframe  (src/stella_vslam/match/bow_tree.cc:169-256)
+ *                                         match::bow_tree::match_keyframes           (bow_tree.cc:258-366)
+ *   variant 1 (B200_PAIRS_TRIANGULATION): match::robust::match_for_triangulation     (src/stella_vslam/match/robust.cc:14-146)
+ *                                         match::bow_tree::match_for_triangulation   (bow_tree.cc:11-167)
+ *                                         with match::check_epipolar_constraint      (match/base.h:67-79)
+ * Side 1 are the rows the reference's outer loop walks (keyframe / keyframe 1), side 2 the candidates (frame / keyframe 2).
+ * node1/node2: the BoW node each keypoint belongs to (the key of bow_feat_vec_ that lists it); a row only sees candidates of its
+ * own node.  NULL on both sides = every row sees every candidate (robust::).  valid1/valid2 carry the landmark tests of the
+ * variant (BOW: row has a live landmark, bow_tree.cc:192-199 / 284-291, candidate likewise for match_keyframes :303-309;
+ * TRIANGULATION: neither has a landmark, robust.cc:44-48, 66-69).  All pointers are HOST buffers.
+ * Result: match_out[i] = index on side 2 matched to row i, or -1; n_matches. */
+enum { B200_PAIRS_BOW = 0, B200_PAIRS_TRIANGULATION = 1 };
+typedef struct b200_pairs_problem {
+    int32_t n1;
+    const uint8_t* desc1;        /* n1 x 32 */
+    const float* angle1;         /* needed when check_orientation */
+    const uint8_t* valid1;       /* NULL = all */
+    const int32_t* node1;        /* NULL = no BoW gating (then node2 must be NULL too) */
+    const double* bearing1;      /* TRIANGULATION: n1 x 3 (frm_obs_.bearings_) */
+    const float* scale1;         /* TRIANGULATION: orb_params_->scale_factors_[octave] per row */
+    const uint8_t* stereo1;      /* TRIANGULATION: stereo_x_right_[i] >= 0; NULL = monocular */
+    int32_t n2;
+    const uint8_t* desc2;
+    const float* angle2;
+    const uint8_t* valid2;
+    const int32_t* node2;
+    const double* bearing2;
+    const uint8_t* stereo2;
+    double E_12[9];              /* TRIANGULATION: essential matrix, row-major */
+    double epiplane_in_keyfrm_2[3]; /* camera centre of keyframe 1 as a bearing in keyframe 2 (robust.cc:22-27) */
+    int32_t valid_epiplane;
+    float residual_rad_thr;
+    int32_t* match_out;          /* out, n1 */
+    int32_t n_matches;           /* out */
+} b200_pairs_problem_t;
+/* max_candidates bounds the gated candidates kept per row (0 = default 64); B200_ERR_CAPACITY reports the size needed. */
+int b200_match_pairs(b200_matcher_t h, int n_problems, b200_pairs_problem_t* problems, int variant, float lowe_ratio,
+                     int check_orientation, int max_candidates);
 /* Run on the caller's stream (a cudaStream_t; NULL is the legacy default stream); use_own != 0 restores the own stream. */
 int b200_matcher_set_stream(b200_matcher_t h, void* stream, int use_own);
 int b200_matcher_sync(b200_matcher_t h);

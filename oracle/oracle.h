@@ -84,10 +84,43 @@ typedef struct {
     const float* q_x_right;          /* reprojected x_right (used when t_x_right != NULL) */
     const float* q_angle;            /* mode 1 */
     const uint8_t* q_valid;          /* 0: skipped before the search (not reprojected / will_be_erased / outside the image); NULL = all */
+    const double* q_reproj;          /* mode 3: Q x 2 reprojection in double (fuse.cc:96-97) */
+    const float* inv_level_sigma_sq; /* mode 3: orb_params_->inv_level_sigma_sq_ */
+    int32_t do_reprojection_matching; /* mode 3 */
 } orc_guided_t;
-/* mode 0: projection::match_frame_and_landmarks (projection.cc:13-93); mode 1: match_current_and_last_frames (:95-207).
+/* mode 0: projection::match_frame_and_landmarks (projection.cc:13-93); mode 1: match_current_and_last_frames (:95-207),
+ * match_frame_and_keyframe (:217-319), match_by_Sim3_transform (:321-416); mode 2: one direction of match_keyframes_mutually
+ * (:418-630, stateless); mode 3: fuse::detect_duplication (fuse.cc:12-154); mode 4: area::match_in_consistent_area (area.cc:8-98).
  * match_out[q] = frame keypoint index or -1.  Returns the number of matches. */
 int orc_match_guided(const orc_guided_t* P, int mode, unsigned thr, float lowe_ratio, int check_orientation, int32_t* match_out);
+int orc_cross_check(const int32_t* idx2_in_1, int n1, const int32_t* idx1_in_2, int n2, int32_t* mutual_out);
+
+/* ---- all-pairs matchers with greedy state (pairs_oracle.c) ------------------------------------------------------------ */
+typedef struct {
+    int32_t n1;                  /* rows: keyframe 1 / the keyframe */
+    const uint8_t* desc1;
+    const float* angle1;
+    const uint8_t* valid1;       /* row takes part (BOW: live landmark; TRIANGULATION: no landmark yet); NULL = all */
+    const int32_t* node1;        /* BoW node id per keypoint or NULL */
+    const double* bearing1;      /* TRIANGULATION: n1 x 3 */
+    const float* scale1;         /* TRIANGULATION: scale_factors_[octave] per row */
+    const uint8_t* stereo1;      /* TRIANGULATION: stereo_x_right_ >= 0, or NULL */
+    int32_t n2;                  /* candidates: keyframe 2 / the frame */
+    const uint8_t* desc2;
+    const float* angle2;
+    const uint8_t* valid2;
+    const int32_t* node2;
+    const double* bearing2;
+    const uint8_t* stereo2;
+    double E_12[9];              /* row-major */
+    double epiplane_in_2[3];
+    int32_t valid_epiplane;
+    float residual_rad_thr;
+} orc_pairs_t;
+int orc_check_epipolar_constraint(const double* b1, const double* b2, const double* E, float residual_rad_thr, float scale_factor);
+/* variant 0: bow_tree::match_frame_and_keyframe / match_keyframes; 1: robust:: / bow_tree::match_for_triangulation.
+ * match_out[i] = matched candidate or -1 per row.  Returns the number of matches. */
+int orc_match_pairs(const orc_pairs_t* P, int variant, float lowe_ratio, int check_orientation, int32_t* match_out);
 
 /* ---- local bundle adjustment (lba_oracle.c; PARITY UNPINNED, see its header) ------------------------------------- */
 typedef struct {

@@ -218,12 +218,14 @@ class GuidedProblem(C.Structure):
                 ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float),
                 ("grid_cols", C.c_int32), ("grid_rows", C.c_int32), ("n_queries", C.c_int32),
                 ("q_desc", C.c_void_p), ("q_x", C.c_void_p), ("q_y", C.c_void_p), ("q_margin", C.c_void_p), ("q_min_level", C.c_void_p),
-                ("q_max_level", C.c_void_p), ("q_x_right", C.c_void_p), ("q_angle", C.c_void_p), ("q_valid", C.c_void_p)]
+                ("q_max_level", C.c_void_p), ("q_x_right", C.c_void_p), ("q_angle", C.c_void_p), ("q_valid", C.c_void_p),
+                ("q_reproj", C.c_void_p), ("inv_level_sigma_sq", C.c_void_p), ("do_reprojection_matching", C.c_int32)]
 
 
 _GUIDED_FIELDS = (("t_x", "f4"), ("t_y", "f4"), ("t_octave", "u1"), ("t_angle", "f4"), ("t_x_right", "f4"), ("t_desc", "u1"),
                   ("t_occupied", "u1"), ("q_desc", "u1"), ("q_x", "f4"), ("q_y", "f4"), ("q_margin", "f4"), ("q_min_level", "i1"),
-                  ("q_max_level", "i1"), ("q_x_right", "f4"), ("q_angle", "f4"), ("q_valid", "u1"))
+                  ("q_max_level", "i1"), ("q_x_right", "f4"), ("q_angle", "f4"), ("q_valid", "u1"), ("q_reproj", "f8"),
+                  ("inv_level_sigma_sq", "f4"))
 
 
 def match_guided(prob, mode, thr=100, lowe_ratio=0.8, check_orientation=True):
@@ -244,11 +246,59 @@ def match_guided(prob, mode, thr=100, lowe_ratio=0.8, check_orientation=True):
     S.n_train, S.n_queries = len(keep["t_x"]), len(keep["q_x"])
     S.min_x, S.max_x, S.min_y, S.max_y = [float(v) for v in prob["bounds"]]
     S.grid_cols, S.grid_rows = prob.get("grid", (64, 48))
+    S.do_reprojection_matching = int(bool(prob.get("do_reprojection_matching", False)))
     out = np.full(max(S.n_queries, 1), -2, np.int32)
     L = lib()
     L.orc_match_guided.argtypes = [C.POINTER(GuidedProblem), C.c_int, C.c_uint, C.c_float, C.c_int, C.c_void_p]
     n = L.orc_match_guided(C.byref(S), mode, thr, lowe_ratio, int(check_orientation), out.ctypes.data)
     return out[:S.n_queries].copy(), keep["t_occupied"], n
+
+
+def cross_check(idx2_in_1, idx1_in_2):
+    a, b = np.ascontiguousarray(idx2_in_1, np.int32), np.ascontiguousarray(idx1_in_2, np.int32)
+    out = np.full(max(len(a), 1), -2, np.int32)
+    n = lib().orc_cross_check(_p(a), len(a), _p(b), len(b), _p(out))
+    return out[:len(a)].copy(), n
+
+
+# ---- all-pairs matchers with greedy state (bow_tree / match_for_triangulation) ------------------------------------------
+class PairsProblem(C.Structure):
+    """orc_pairs_t (oracle.h)."""
+    _fields_ = [("n1", C.c_int32), ("desc1", C.c_void_p), ("angle1", C.c_void_p), ("valid1", C.c_void_p), ("node1", C.c_void_p),
+                ("bearing1", C.c_void_p), ("scale1", C.c_void_p), ("stereo1", C.c_void_p),
+                ("n2", C.c_int32), ("desc2", C.c_void_p), ("angle2", C.c_void_p), ("valid2", C.c_void_p), ("node2", C.c_void_p),
+                ("bearing2", C.c_void_p), ("stereo2", C.c_void_p),
+                ("E_12", C.c_double * 9), ("epiplane_in_2", C.c_double * 3), ("valid_epiplane", C.c_int32), ("residual_rad_thr", C.c_float)]
+
+
+_PAIRS_FIELDS = (("desc1", "u1"), ("angle1", "f4"), ("valid1", "u1"), ("node1", "i4"), ("bearing1", "f8"), ("scale1", "f4"), ("stereo1", "u1"),
+                 ("desc2", "u1"), ("angle2", "f4"), ("valid2", "u1"), ("node2", "i4"), ("bearing2", "f8"), ("stereo2", "u1"))
+
+
+def match_pairs(prob, variant, lowe_ratio=0.6, check_orientation=True):
+    """orc_match_pairs on a problem dict.  Returns (match_out per row, n)."""
+    S, keep = PairsProblem(), {}
+    for name, dt in _PAIRS_FIELDS:
+        v = prob.get(name)
+        if v is None:
+            setattr(S, name, None)
+            continue
+        keep[name] = np.ascontiguousarray(v, np.dtype(dt))
+        setattr(S, name, keep[name].ctypes.data)
+    S.n1, S.n2 = len(keep["desc1"].reshape(-1, 32)), len(keep["desc2"].reshape(-1, 32))
+    E = np.asarray(prob.get("E_12", np.zeros((3, 3))), np.float64).reshape(9)
+    epi = np.asarray(prob.get("epiplane_in_keyfrm_2", np.zeros(3)), np.float64).reshape(3)
+    for k in range(9):
+        S.E_12[k] = float(E[k])
+    for k in range(3):
+        S.epiplane_in_2[k] = float(epi[k])
+    S.valid_epiplane = int(bool(prob.get("valid_epiplane", False)))
+    S.residual_rad_thr = float(prob.get("residual_rad_thr", 0.0))
+    out = np.full(max(S.n1, 1), -2, np.int32)
+    L = lib()
+    L.orc_match_pairs.argtypes = [C.POINTER(PairsProblem), C.c_int, C.c_float, C.c_int, C.c_void_p]
+    n = L.orc_match_pairs(C.byref(S), variant, lowe_ratio, int(check_orientation), out.ctypes.data)
+    return out[:S.n1].copy(), n
 
 
 # ---- local BA ---------------------------------------------------------------------------------------------------------

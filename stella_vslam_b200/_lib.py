@@ -39,12 +39,13 @@ class GuidedProblem(C.Structure):
                 ("grid_cols", C.c_int32), ("grid_rows", C.c_int32), ("n_queries", C.c_int32),
                 ("q_desc", C.c_void_p), ("q_x", C.c_void_p), ("q_y", C.c_void_p), ("q_margin", C.c_void_p), ("q_min_level", C.c_void_p),
                 ("q_max_level", C.c_void_p), ("q_x_right", C.c_void_p), ("q_angle", C.c_void_p), ("q_valid", C.c_void_p),
+                ("q_reproj", C.c_void_p), ("inv_level_sigma_sq", C.c_void_p), ("n_levels", C.c_int32), ("do_reprojection_matching", C.c_int32),
                 ("match_out", C.c_void_p), ("n_matches", C.c_int32)]
 
 
 GUIDED_FIELDS = (("t_x", "f4"), ("t_y", "f4"), ("t_octave", "u1"), ("t_angle", "f4"), ("t_x_right", "f4"), ("t_desc", "u1"), ("t_occupied", "u1"),
                  ("q_desc", "u1"), ("q_x", "f4"), ("q_y", "f4"), ("q_margin", "f4"), ("q_min_level", "i1"), ("q_max_level", "i1"),
-                 ("q_x_right", "f4"), ("q_angle", "f4"), ("q_valid", "u1"))
+                 ("q_x_right", "f4"), ("q_angle", "f4"), ("q_valid", "u1"), ("q_reproj", "f8"), ("inv_level_sigma_sq", "f4"))
 
 
 def pack_guided_problem(prob, StructT=None):
@@ -67,8 +68,55 @@ def pack_guided_problem(prob, StructT=None):
     S.n_queries = len(keep["q_x"]) if "q_x" in keep else 0
     S.min_x, S.max_x, S.min_y, S.max_y = [float(v) for v in prob["bounds"]]
     S.grid_cols, S.grid_rows = prob.get("grid", (64, 48))
+    S.do_reprojection_matching = int(bool(prob.get("do_reprojection_matching", False)))
+    if hasattr(S, "n_levels"):
+        S.n_levels = len(keep["inv_level_sigma_sq"]) if "inv_level_sigma_sq" in keep else 0
     if hasattr(S, "match_out"):
         keep["match_out"] = np.full(max(S.n_queries, 1), -2, np.int32)
+        S.match_out = keep["match_out"].ctypes.data
+    return S, keep
+
+
+class PairsProblem(C.Structure):
+    """b200_pairs_problem_t (include/b200vslam.h)."""
+    _fields_ = [("n1", C.c_int32), ("desc1", C.c_void_p), ("angle1", C.c_void_p), ("valid1", C.c_void_p), ("node1", C.c_void_p),
+                ("bearing1", C.c_void_p), ("scale1", C.c_void_p), ("stereo1", C.c_void_p),
+                ("n2", C.c_int32), ("desc2", C.c_void_p), ("angle2", C.c_void_p), ("valid2", C.c_void_p), ("node2", C.c_void_p),
+                ("bearing2", C.c_void_p), ("stereo2", C.c_void_p),
+                ("E_12", C.c_double * 9), ("epiplane_in_keyfrm_2", C.c_double * 3), ("valid_epiplane", C.c_int32),
+                ("residual_rad_thr", C.c_float), ("match_out", C.c_void_p), ("n_matches", C.c_int32)]
+
+
+PAIRS_FIELDS = (("desc1", "u1"), ("angle1", "f4"), ("valid1", "u1"), ("node1", "i4"), ("bearing1", "f8"), ("scale1", "f4"), ("stereo1", "u1"),
+                ("desc2", "u1"), ("angle2", "f4"), ("valid2", "u1"), ("node2", "i4"), ("bearing2", "f8"), ("stereo2", "u1"))
+
+
+def pack_pairs_problem(prob, StructT=None):
+    """dict -> (struct, keep-alive arrays).  Keys: PAIRS_FIELDS (missing / None -> NULL), E_12 (3x3), epiplane_in_keyfrm_2 (3),
+    valid_epiplane, residual_rad_thr."""
+    import numpy as np
+    S = (StructT or PairsProblem)()
+    keep = {}
+    for name, dt in PAIRS_FIELDS:
+        v = prob.get(name)
+        if v is None:
+            setattr(S, name, None)
+            continue
+        a = np.ascontiguousarray(v, np.dtype(dt))
+        keep[name] = a
+        setattr(S, name, a.ctypes.data)
+    S.n1 = len(keep["desc1"].reshape(-1, 32)) if "desc1" in keep else 0
+    S.n2 = len(keep["desc2"].reshape(-1, 32)) if "desc2" in keep else 0
+    E = np.asarray(prob.get("E_12", np.zeros((3, 3))), np.float64).reshape(9)
+    epi = np.asarray(prob.get("epiplane_in_keyfrm_2", np.zeros(3)), np.float64).reshape(3)
+    for k in range(9):
+        S.E_12[k] = float(E[k])
+    for k in range(3):
+        S.epiplane_in_keyfrm_2[k] = float(epi[k])
+    S.valid_epiplane = int(bool(prob.get("valid_epiplane", False)))
+    S.residual_rad_thr = float(prob.get("residual_rad_thr", 0.0))
+    if hasattr(S, "match_out"):
+        keep["match_out"] = np.full(max(S.n1, 1), -2, np.int32)
         S.match_out = keep["match_out"].ctypes.data
     return S, keep
 
@@ -79,7 +127,7 @@ SYMBOLS = [
     "b200_orb_extract_device", "b200_orb_set_stream", "b200_orb_bind_outputs", "b200_orb_reserve", "b200_orb_fetch", "b200_orb_device_results", "b200_orb_sync", "b200_orb_level_info",
     "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_stage_ms", "b200_orb_enable_timing",
     "b200_matcher_create", "b200_matcher_destroy", "b200_hamming_matrix", "b200_match_bruteforce",
-    "b200_match_bruteforce_device", "b200_match_guided", "b200_matcher_set_stream", "b200_matcher_sync",
+    "b200_match_bruteforce_device", "b200_match_guided", "b200_match_cross_check", "b200_match_pairs", "b200_matcher_set_stream", "b200_matcher_sync",
     "b200_lba_create", "b200_lba_destroy", "b200_lba_solve", "b200_lba_last_profile",
 ]
 
@@ -124,6 +172,8 @@ def lib():
     L.b200_match_bruteforce_device.argtypes = [vp, i32, vp, vp, sz, vp, vp, vp, vp, sz, vp, vp, vp, i32, i32, C.c_float, i32,
                                                vp, i32, vp]
     L.b200_match_guided.argtypes = [vp, i32, C.POINTER(GuidedProblem), i32, C.c_uint, C.c_float, i32, i32]
+    L.b200_match_cross_check.argtypes = [vp, i32, vp, i32, vp, C.POINTER(i32)]
+    L.b200_match_pairs.argtypes = [vp, i32, C.POINTER(PairsProblem), i32, C.c_float, i32, i32]
     L.b200_matcher_set_stream.argtypes = [vp, vp, i32]
     _lib = L
     return L

@@ -352,8 +352,11 @@ struct GuidedDev {
     const float *q_x, *q_y, *q_margin, *q_x_right, *q_angle;
     const signed char *q_min_level, *q_max_level;
     const unsigned char* q_valid;
+    const double* q_reproj;           // mode 3
+    const float* inv_level_sigma_sq;  // mode 3, 256 entries
+    int do_reproj;
     // scratch + outputs of this problem
-    int *cell_start, *cell_items, *cell_cursor;
+    int *cell_start, *cell_items, *cell_cursor, *owner;
     uint2* lists;
     int* list_len;
     unsigned char* occupied;
@@ -441,11 +444,22 @@ __global__ void __launch_bounds__(128) guided_candidates_kernel(const GuidedDev*
                         if (0 <= max_level && max_level < oct) continue;
                         const float dx = __fsub_rn(g.t_x[idx], ref_x), dy = __fsub_rn(g.t_y[idx], ref_y);
                         if (!(fabsf(dx) < margin && fabsf(dy) < margin)) continue;
-                        if (g.t_x_right) {  // stereo gate (projection.cc:56-61, 168-173)
+                        if (mode <= 1 && g.t_x_right) {  // stereo gate (projection.cc:56-61, 168-173)
                             const float xr = g.t_x_right[idx];
                             if (0.f < xr && margin < fabsf(__fsub_rn(g.q_x_right[q], xr))) continue;
                         }
-                        if (mode == 1 && check_orientation && orientation_rejects(g.q_angle[q], g.t_angle[idx])) continue;
+                        if ((mode == 1 || mode == 4) && check_orientation && orientation_rejects(g.q_angle[q], g.t_angle[idx])) continue;
+                        if (mode == 3 && g.do_reproj) {  // chi-square reprojection gate (fuse.cc:93-120), evaluated like the reference: double
+                            const double e_x = __dsub_rn(g.q_reproj[2 * q], (double)g.t_x[idx]), e_y = __dsub_rn(g.q_reproj[2 * q + 1], (double)g.t_y[idx]);
+                            double err_sq = __dadd_rn(__dmul_rn(e_x, e_x), __dmul_rn(e_y, e_y));
+                            float chi_sq = 5.99146f;
+                            if (g.t_x_right && g.t_x_right[idx] >= 0.f) {
+                                const float e_xr = __fsub_rn(g.q_x_right[q], g.t_x_right[idx]);
+                                err_sq = __dadd_rn(err_sq, (double)__fmul_rn(e_xr, e_xr));
+                                chi_sq = 7.81473f;
+                            }
+                            if ((double)chi_sq < __dmul_rn(err_sq, (double)g.inv_level_sigma_sq[oct])) continue;
+                        }
                         const unsigned d = hamming256(q0, q1, g.t_desc[(size_t)idx * 2], g.t_desc[(size_t)idx * 2 + 1]);
                         if (len < g.cap) out[len] = make_uint2((d << 8) | (unsigned)oct, (unsigned)idx);
                         ++len;
@@ -460,16 +474,21 @@ __global__ void __launch_bounds__(128) guided_candidates_kernel(const GuidedDev*
     list_len[q] = len;
 }
 
-// the reference's best / second update in iteration order over the keypoints that are still free; returns the accepted index or -1
-__device__ __forceinline__ int guided_decide(const uint2* __restrict__ list, int len, const volatile unsigned* occupied, int mode, unsigned thr,
-                                             float lowe_ratio) {
-    unsigned best = kMaxDist, second = kMaxDist;
+// the reference's best / second update in iteration order over the keypoints whose state admits the candidate
+// (state: 0 = occupied, 0xFFFF = free; mode 4: Hamming distance of the match the keypoint currently holds, area.cc:49-51).
+// Returns the accepted index or -1; *best_out = its distance.
+__device__ __forceinline__ int guided_decide(const uint2* __restrict__ list, int len, const volatile unsigned short* state, int mode, unsigned thr,
+                                             float lowe_ratio, unsigned* best_out) {
+    // mode 5: bow_tree::match_frame_and_keyframe / match_keyframes; mode 6: match_for_triangulation, whose running best starts at
+    // the threshold and which skips every candidate above it (robust.cc:57-59, 83-85)
+    unsigned best = mode == 6 ? thr : (unsigned)kMaxDist, second = kMaxDist;
     int best_level = -1, second_level = -1, best_idx = -1;
+    const bool track_second = mode == 0 || mode >= 4;
     for (int k = 0; k < len; ++k) {
         const uint2 e = list[k];
-        const unsigned idx = e.y;
-        if ((occupied[idx >> 5] >> (idx & 31)) & 1u) continue;
-        const unsigned d = e.x >> 8;
+        const unsigned idx = e.y, d = e.x >> 8;
+        if ((unsigned)state[idx] <= d) continue;
+        if (mode == 6 && d > best) continue;
         const int oct = (int)(e.x & 0xFF);
         if (d < best) {
             second = best;
@@ -477,71 +496,194 @@ __device__ __forceinline__ int guided_decide(const uint2* __restrict__ list, int
             best = d;
             best_level = oct;
             best_idx = (int)idx;
-        } else if (mode == 0 && d < second) {
+        } else if (track_second && d < second) {
             second_level = oct;
             second = d;
         }
     }
+    *best_out = best;
     if (best_idx < 0 || best > thr) return -1;
     if (mode == 0 && best_level == second_level && (float)best > __fmul_rn(lowe_ratio, (float)second)) return -1;
+    if (mode >= 4 && __fmul_rn((float)second, lowe_ratio) < (float)best) return -1;
     return best_idx;
 }
 
-// G3: one warp; shared memory: [occupied bitmap][claim per keypoint].  A lane's decision is safe to commit when no lower lane of
-// the batch wants ANY keypoint of its list (that is the only way an earlier landmark can change a later one's outcome).
-__global__ void __launch_bounds__(32) guided_resolve_kernel(const GuidedDev* __restrict__ gs, int mode, unsigned thr, float lowe_ratio) {
+// G3: one warp; shared memory: [claim per keypoint (int)][state per keypoint (u16)].  A lane's decision is safe to commit when
+// no lower lane of the batch wants ANY keypoint of its list (that is the only way an earlier landmark can change a later one's
+// outcome).  Mode 2 is stateless: every decision commits at once.
+template <class Dev>
+__global__ void __launch_bounds__(32) guided_resolve_kernel(const Dev* __restrict__ gs, int mode, unsigned thr, float lowe_ratio) {
     extern __shared__ unsigned guided_smem[];
-    const GuidedDev g = gs[blockIdx.x];
+    const Dev g = gs[blockIdx.x];
     const uint2* lists = g.lists;
     const int* list_len = g.list_len;
     unsigned char* occupied_io = g.occupied;
-    int *match_out = g.match_out, *n_matches = g.n_matches;
-    const int lane = threadIdx.x, words = (g.n_train + 31) / 32;
-    unsigned* occupied = guided_smem;
-    int* claim = reinterpret_cast<int*>(guided_smem + words);
-    for (int w = lane; w < words; w += 32) {
-        unsigned bits = 0;
-        for (int b = 0; b < 32; ++b) {
-            const int i = w * 32 + b;
-            if (i < g.n_train && occupied_io[i]) bits |= 1u << b;
-        }
-        occupied[w] = bits;
+    int *match_out = g.match_out, *n_matches = g.n_matches, *owner = g.owner;
+    const int lane = threadIdx.x;
+    int* claim = reinterpret_cast<int*>(guided_smem);
+    unsigned short* state = reinterpret_cast<unsigned short*>(guided_smem + g.n_train);
+    for (int i = lane; i < g.n_train; i += 32) {
+        claim[i] = 255;
+        state[i] = mode == 4 ? (unsigned short)kMaxDist : ((occupied_io && occupied_io[i]) ? 0 : 0xFFFF);
+        if (mode == 4) owner[i] = -1;
     }
-    for (int i = lane; i < g.n_train; i += 32) claim[i] = 255;
+    for (int q = lane; q < g.n_queries; q += 32) match_out[q] = -1;
     __syncwarp();
     int total = 0;
     for (int base = 0; base < g.n_queries; base += 32) {
         const int q = base + lane;
         const int len = (q < g.n_queries) ? list_len[q] : 0;
         const uint2* list = lists + (size_t)min(q, g.n_queries - 1) * g.cap;
-        if (q < g.n_queries) match_out[q] = -1;
         unsigned pending = __ballot_sync(0xFFFFFFFFu, len > 0);
         while (pending) {
             const bool mine = (pending >> lane) & 1u;
-            const int acc = mine ? guided_decide(list, len, occupied, mode, thr, lowe_ratio) : -1;
-            if (acc >= 0) atomicMin(&claim[acc], lane);  // claim[idx] = lowest lane that wants idx this round
-            __syncwarp();
-            bool conflict = false;
-            if (mine)
-                for (int k = 0; k < len; ++k) conflict |= claim[list[k].y] < lane;
-            const unsigned unsafe = __ballot_sync(0xFFFFFFFFu, mine && conflict);
-            const int first_unsafe = unsafe ? __ffs(unsafe) - 1 : 32;
-            const unsigned commit = pending & ((first_unsafe >= 32) ? 0xFFFFFFFFu : ((1u << first_unsafe) - 1u));
-            const bool do_commit = (commit >> lane) & 1u;
-            __syncwarp();
-            if (acc >= 0) claim[acc] = 255;  // reset for the next round
-            if (do_commit && acc >= 0) {
-                atomicOr(&occupied[acc >> 5], 1u << (acc & 31));
-                match_out[q] = acc;
+            unsigned best = kMaxDist;
+            const int acc = mine ? guided_decide(list, len, state, mode, thr, lowe_ratio, &best) : -1;
+            unsigned commit = pending;
+            if (mode != 2) {
+                if (acc >= 0) atomicMin(&claim[acc], lane);  // claim[idx] = lowest lane that wants idx this round
+                __syncwarp();
+                bool conflict = false;
+                if (mine)
+                    for (int k = 0; k < len; ++k) conflict |= claim[list[k].y] < lane;
+                const unsigned unsafe = __ballot_sync(0xFFFFFFFFu, mine && conflict);
+                if (unsafe) commit = pending & ((1u << (__ffs(unsafe) - 1)) - 1u);
+                __syncwarp();
+                if (acc >= 0) claim[acc] = 255;  // reset for the next round
             }
-            total += __popc(__ballot_sync(0xFFFFFFFFu, do_commit && acc >= 0));
+            const bool do_commit = ((commit >> lane) & 1u) && acc >= 0;
+            int stolen = 0;
+            if (do_commit) {
+                match_out[q] = acc;
+                if (mode == 4) {  // area.cc:75-87: take the keypoint over from its previous owner
+                    const int prev = owner[acc];
+                    if (prev >= 0) {
+                        match_out[prev] = -1;
+                        stolen = 1;
+                    }
+                    owner[acc] = q;
+                    state[acc] = (unsigned short)best;
+                } else if (mode != 2) {
+                    state[acc] = 0;
+                }
+            }
+            total += __popc(__ballot_sync(0xFFFFFFFFu, do_commit)) - __popc(__ballot_sync(0xFFFFFFFFu, stolen));
             pending &= ~commit;
             __syncwarp();
         }
     }
     __syncwarp();
-    for (int i = lane; i < g.n_train; i += 32) occupied_io[i] = (occupied[i >> 5] >> (i & 31)) & 1u;
+    if (mode == 0 || mode == 1 || mode == 3)
+        for (int i = lane; i < g.n_train; i += 32) occupied_io[i] = state[i] == 0;
     if (lane == 0) *n_matches = total;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// All-pairs matchers with greedy state other than brute_force_match:
+//   match::bow_tree::match_frame_and_keyframe   src/stella_vslam/match/bow_tree.cc:169-256   (variant 0)
+//   match::bow_tree::match_keyframes            bow_tree.cc:258-366                          (variant 0)
+//   match::robust::match_for_triangulation      src/stella_vslam/match/robust.cc:14-146      (variant 1)
+//   match::bow_tree::match_for_triangulation    bow_tree.cc:11-167                           (variant 1, with node ids)
+// P1 evaluates every (row, candidate) pair once and records, per row and in candidate order, the candidates that pass the
+// state-independent gates with a distance that can still influence the outcome (<= list_thr); the sequential part is then the
+// same warp-batched replay as for the guided matchers (guided_resolve_kernel, modes 5 and 6).  A BoW node holds each keypoint
+// exactly once and rows of different nodes never compete for a candidate, so visiting rows in index order with the gate
+// node_1[i] == node_2[j] gives the merge-join's result.
+// ---------------------------------------------------------------------------------------------------------------
+struct PairsDev {
+    int n_queries, n_train, cap;  // rows (side 1), candidates (side 2)
+    const uint4 *desc1, *desc2;
+    const float *angle1, *angle2;
+    const unsigned char *valid1, *valid2, *stereo1, *stereo2;
+    const int *node1, *node2;
+    const double *bearing1, *bearing2;
+    const float* scale1;
+    double E[9], epi[3];
+    int valid_epiplane;
+    float residual_rad_thr;
+    uint2* lists;
+    int* list_len;
+    unsigned char* occupied;  // always null: every candidate starts free
+    int *match_out, *n_matches, *owner;
+};
+
+// match/base.h:67-79 in the reference's evaluation order (3x3 times 3, dot, norm; no contraction)
+__device__ __forceinline__ bool epipolar_inlier(const double* __restrict__ b1, const double* __restrict__ b2, const double* E, float thr, float scale) {
+    const double x = b2[0], y = b2[1], z = b2[2];
+    const double e0 = __dadd_rn(__dadd_rn(__dmul_rn(E[0], x), __dmul_rn(E[1], y)), __dmul_rn(E[2], z));
+    const double e1 = __dadd_rn(__dadd_rn(__dmul_rn(E[3], x), __dmul_rn(E[4], y)), __dmul_rn(E[5], z));
+    const double e2 = __dadd_rn(__dadd_rn(__dmul_rn(E[6], x), __dmul_rn(E[7], y)), __dmul_rn(E[8], z));
+    const double dot = __dadd_rn(__dadd_rn(__dmul_rn(e0, b1[0]), __dmul_rn(e1, b1[1])), __dmul_rn(e2, b1[2]));
+    const double norm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(e0, e0), __dmul_rn(e1, e1)), __dmul_rn(e2, e2)));
+    double c = __ddiv_rn(dot, norm);
+    c = fmax(-1.0, c);
+    c = fmin(1.0, c);
+    const double residual_rad = fabs(__dsub_rn(1.5707963267948966, acos(c)));
+    return residual_rad < (double)__fmul_rn(thr, scale);
+}
+
+constexpr int kPairRows = 64, kPairChunk = 256;
+
+__global__ void __launch_bounds__(kPairRows) pairs_candidates_kernel(const PairsDev* __restrict__ ps, int variant, unsigned list_thr,
+                                                                    int check_orientation, int* __restrict__ overflow) {
+    __shared__ uint4 s2[kPairChunk * 2];
+    __shared__ float sa[kPairChunk];
+    __shared__ int sn[kPairChunk];
+    __shared__ unsigned char sv[kPairChunk];
+    const PairsDev& g = ps[blockIdx.y];
+    const int n1 = g.n_queries, n2 = g.n_train;
+    if ((int)(blockIdx.x * kPairRows) >= n1) return;
+    const int row = blockIdx.x * kPairRows + threadIdx.x;
+    const bool active = row < n1 && (!g.valid1 || g.valid1[row]);
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    float qa = 0.f;
+    int qn = 0;
+    bool q_stereo = false;
+    if (active) {
+        q0 = g.desc1[(size_t)row * 2];
+        q1 = g.desc1[(size_t)row * 2 + 1];
+        if (check_orientation) qa = g.angle1[row];
+        if (g.node1) qn = g.node1[row];
+        q_stereo = g.stereo1 && g.stereo1[row];
+    }
+    uint2* out = g.lists + (size_t)min(row, n1 - 1) * g.cap;
+    int len = 0;
+    for (int c0 = 0; c0 < n2; c0 += kPairChunk) {
+        const int cn = min(kPairChunk, n2 - c0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cn * 2; t += blockDim.x) s2[t] = g.desc2[(size_t)c0 * 2 + t];
+        for (int t = threadIdx.x; t < cn; t += blockDim.x) {
+            sa[t] = check_orientation ? g.angle2[c0 + t] : 0.f;
+            sn[t] = g.node2 ? g.node2[c0 + t] : 0;
+            sv[t] = g.valid2 ? g.valid2[c0 + t] : 1;
+        }
+        __syncthreads();
+        if (!active) continue;
+#pragma unroll 4
+        for (int j = 0; j < cn; ++j) {
+            const unsigned dist = hamming256(q0, q1, s2[2 * j], s2[2 * j + 1]);
+            if (dist > list_thr) continue;
+            if (!sv[j] || sn[j] != qn) continue;
+            if (check_orientation && orientation_rejects(qa, sa[j])) continue;
+            if (variant == 1) {
+                const double* b2 = g.bearing2 + (size_t)(c0 + j) * 3;
+                if (g.valid_epiplane && !q_stereo && !(g.stereo2 && g.stereo2[c0 + j])) {  // robust.cc:87-98: too close to the epipole
+                    const double cos_dist = __dadd_rn(__dadd_rn(__dmul_rn(g.epi[0], b2[0]), __dmul_rn(g.epi[1], b2[1])), __dmul_rn(g.epi[2], b2[2]));
+                    if (0.99862953475 < cos_dist) continue;
+                }
+                if (!epipolar_inlier(g.bearing1 + (size_t)row * 3, b2, g.E, g.residual_rad_thr, g.scale1[row])) continue;
+            }
+            if (len < g.cap) out[len] = make_uint2(dist << 8, (unsigned)(c0 + j));
+            ++len;
+        }
+    }
+    if (row < n1) {
+        if (len > g.cap) {
+            atomicMax(overflow, len);
+            len = g.cap;
+        }
+        g.list_len[row] = len;
+    }
 }
 
 struct Matcher {
@@ -779,7 +921,7 @@ int b200_match_bruteforce(b200_matcher_t h, int n_problems, const uint8_t* desc1
 int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* problems, int mode, unsigned thr, float lowe_ratio,
                       int check_orientation, int max_candidates) {
     using b200::match::GuidedDev;
-    if (!h || n_problems < 0 || (mode != B200_GUIDED_LANDMARKS && mode != B200_GUIDED_LAST_FRAME) || max_candidates < 0) return B200_ERR_INVALID;
+    if (!h || n_problems < 0 || mode < B200_GUIDED_LANDMARKS || mode > B200_GUIDED_AREA || max_candidates < 0) return B200_ERR_INVALID;
     if (n_problems == 0) return B200_OK;
     if (!problems) return B200_ERR_INVALID;
     auto& m = h->m;
@@ -789,16 +931,18 @@ int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* p
     // layout of the arena: [GuidedDev x n][inputs of every problem][outputs of every problem][scratch]; the first two parts are
     // mirrored in pinned host memory and go up in one copy, the output part comes back in one copy.
     struct Lay {
-        size_t tx, ty, toct, tang, txr, tdesc, qdesc, qx, qy, qm, qlo, qhi, qxr, qang, qval;  // inputs
+        size_t tx, ty, toct, tang, txr, tdesc, qdesc, qx, qy, qm, qlo, qhi, qxr, qang, qval, qrep, sig;  // inputs
         size_t occ, mout, nm;                                                                // outputs
-        size_t cstart, citems, ccur, lists, llen;                                            // scratch
+        size_t cstart, citems, ccur, lists, llen, own;                                       // scratch
     };
     std::vector<Lay> lay(n_problems);
     size_t o = al(sizeof(GuidedDev) * (size_t)n_problems);
     int max_q = 0, max_train = 0;
     for (int p = 0; p < n_problems; ++p) {
         const b200_guided_problem_t& P = problems[p];
-        const bool need_angle = mode == B200_GUIDED_LAST_FRAME && check_orientation;
+        const bool need_angle = (mode == B200_GUIDED_LAST_FRAME || mode == B200_GUIDED_AREA) && check_orientation;
+        const bool need_reproj = mode == B200_GUIDED_FUSE && P.do_reprojection_matching;
+        const bool need_xr = P.t_x_right && (mode <= B200_GUIDED_LAST_FRAME || need_reproj);
         if (P.n_train < 0 || P.n_queries < 0 || P.grid_cols <= 0 || P.grid_rows <= 0 || !(P.max_x > P.min_x) || !(P.max_y > P.min_y)
             || (long long)P.grid_cols * P.grid_rows > (1 << 20)) {
             b200::set_error("b200_match_guided: bad sizes / image bounds in problem %d", p);
@@ -807,7 +951,8 @@ int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* p
         if ((P.n_train > 0 && (!P.t_x || !P.t_y || !P.t_octave || !P.t_desc || (need_angle && !P.t_angle)))
             || (P.n_queries > 0
                 && (!P.q_desc || !P.q_x || !P.q_y || !P.q_margin || !P.q_min_level || !P.q_max_level || !P.match_out
-                    || (need_angle && !P.q_angle) || (P.t_x_right && !P.q_x_right)))) {
+                    || (need_angle && !P.q_angle) || (need_xr && !P.q_x_right)
+                    || (need_reproj && (!P.q_reproj || !P.inv_level_sigma_sq || P.n_levels <= 0 || P.n_levels > 256))))) {
             b200::set_error("b200_match_guided: null buffer in problem %d", p);
             return B200_ERR_INVALID;
         }
@@ -828,6 +973,8 @@ int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* p
         L.qxr = o; o += al(4 * nq);
         L.qang = o; o += al(4 * nq);
         L.qval = o; o += al(nq);
+        L.qrep = o; o += al(16 * nq);
+        L.sig = o; o += al(4 * 256);
         L.occ = o; o += al(nt);  // in AND out: kept at the end of the problem's input block
         max_q = std::max(max_q, P.n_queries);
         max_train = std::max(max_train, P.n_train);
@@ -851,8 +998,9 @@ int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* p
         L.ccur = o; o += al(4 * cells);
         L.lists = o; o += al(8 * (size_t)cap * std::max(P.n_queries, 1));
         L.llen = o; o += al(4 * (size_t)std::max(P.n_queries, 1));
+        L.own = o; o += al(4 * (size_t)std::max(P.n_train, 1));
     }
-    const size_t rs_bytes = sizeof(unsigned) * ((size_t)b200::ceil_div(std::max(max_train, 1), 32) + (size_t)std::max(max_train, 1));
+    const size_t rs_bytes = (size_t)std::max(max_train, 1) * 6 + 16;  // claim (int) + state (u16) per keypoint
     if (rs_bytes > 200 * 1024) {
         b200::set_error("b200_match_guided: %d keypoints per frame exceed the on-chip occupancy table", max_train);
         return B200_ERR_CAPACITY;
@@ -884,7 +1032,13 @@ int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* p
         put(L.qxr, P.q_x_right, 4 * nq);
         put(L.qang, P.q_angle, 4 * nq);
         put(L.qval, P.q_valid, nq);
-        if (P.t_occupied) put(L.occ, P.t_occupied, nt);
+        const bool reproj = mode == B200_GUIDED_FUSE && P.do_reprojection_matching;
+        if (reproj) {
+            put(L.qrep, P.q_reproj, 16 * nq);
+            std::memset(hb + L.sig, 0, 4 * 256);
+            put(L.sig, P.inv_level_sigma_sq, 4 * (size_t)P.n_levels);
+        }
+        if (P.t_occupied && mode != B200_GUIDED_AREA) put(L.occ, P.t_occupied, nt);
         else std::memset(hb + L.occ, 0, nt);
         GuidedDev g{};
         g.n_train = P.n_train;
@@ -908,6 +1062,10 @@ int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* p
         g.q_min_level = (const signed char*)(db + L.qlo);
         g.q_max_level = (const signed char*)(db + L.qhi);
         g.q_valid = P.q_valid ? db + L.qval : nullptr;
+        g.q_reproj = (const double*)(db + L.qrep);
+        g.inv_level_sigma_sq = (const float*)(db + L.sig);
+        g.do_reproj = reproj ? 1 : 0;
+        g.owner = (int*)(db + L.own);
         g.cell_start = (int*)(db + L.cstart);
         g.cell_items = (int*)(db + L.citems);
         g.cell_cursor = (int*)(db + L.ccur);
@@ -926,14 +1084,15 @@ int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* p
     b200::match::guided_candidates_kernel<<<dim3(std::max(1, b200::ceil_div(max_q, 128)), n_problems), 128, 0, st>>>(dg, mode, check_orientation,
                                                                                                                      (int*)(db + o_overflow));
     if (rs_bytes > 48 * 1024)
-        B200_CUDA(cudaFuncSetAttribute(b200::match::guided_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_bytes));
-    b200::match::guided_resolve_kernel<<<n_problems, 32, rs_bytes, st>>>(dg, mode, thr, lowe_ratio);
+        B200_CUDA(cudaFuncSetAttribute(b200::match::guided_resolve_kernel<GuidedDev>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_bytes));
+    b200::match::guided_resolve_kernel<GuidedDev><<<n_problems, 32, rs_bytes, st>>>(dg, mode, thr, lowe_ratio);
     B200_CUDA(cudaGetLastError());
     // outputs: occupancy lives in the input block (copied back per problem only when asked for), the rest is contiguous
     B200_CUDA(cudaMemcpyAsync(hb + out_begin, db + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, st));
     size_t occ_bytes = 0;
+    const bool writes_occupancy = mode == B200_GUIDED_LANDMARKS || mode == B200_GUIDED_LAST_FRAME || mode == B200_GUIDED_FUSE;
     for (int p = 0; p < n_problems; ++p)
-        if (problems[p].t_occupied && problems[p].n_train > 0) {
+        if (writes_occupancy && problems[p].t_occupied && problems[p].n_train > 0) {
             B200_CUDA(cudaMemcpyAsync(hb + lay[p].occ, db + lay[p].occ, (size_t)problems[p].n_train, cudaMemcpyDeviceToHost, st));
             occ_bytes += (size_t)problems[p].n_train;
         }
@@ -949,8 +1108,164 @@ int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* p
         b200_guided_problem_t& P = problems[p];
         if (P.n_queries > 0) std::memcpy(P.match_out, hb + lay[p].mout, 4 * (size_t)P.n_queries);
         P.n_matches = *reinterpret_cast<const int*>(hb + lay[p].nm);
-        if (P.t_occupied && P.n_train > 0) std::memcpy(P.t_occupied, hb + lay[p].occ, (size_t)P.n_train);
+        if (writes_occupancy && P.t_occupied && P.n_train > 0) std::memcpy(P.t_occupied, hb + lay[p].occ, (size_t)P.n_train);
     }
+    return B200_OK;
+}
+
+int b200_match_pairs(b200_matcher_t h, int n_problems, b200_pairs_problem_t* problems, int variant, float lowe_ratio, int check_orientation,
+                     int max_candidates) {
+    using b200::match::PairsDev;
+    if (!h || n_problems < 0 || (variant != B200_PAIRS_BOW && variant != B200_PAIRS_TRIANGULATION) || max_candidates < 0) return B200_ERR_INVALID;
+    if (n_problems == 0) return B200_OK;
+    if (!problems) return B200_ERR_INVALID;
+    auto& m = h->m;
+    B200_CUDA(cudaSetDevice(m.device));
+    const int cap = max_candidates ? max_candidates : 64;
+    const bool tri = variant == B200_PAIRS_TRIANGULATION;
+    // distances that can still matter: the match itself needs <= 50; a second-best above T can no longer fail the ratio test
+    // (lowe * (T + 1) >= 50 >= best, bow_tree.cc:232-239).  Triangulation never looks above 50 (robust.cc:83-85).
+    unsigned list_thr = b200::match::kThrLow;
+    if (!tri)
+        while (list_thr < 255u && lowe_ratio * (float)(list_thr + 1) < (float)b200::match::kThrLow) ++list_thr;
+    auto al = [](size_t v) { return b200::round_up(v, (size_t)256); };
+    struct Item {
+        size_t off;
+        const void* src;
+        size_t bytes;
+    };
+    std::vector<Item> items;
+    size_t o = al(sizeof(PairsDev) * (size_t)n_problems);
+    auto add = [&](const void* src, size_t bytes) {
+        const size_t at = o;
+        items.push_back({at, src, src ? bytes : 0});
+        o += al(std::max(bytes, (size_t)1));
+        return at;
+    };
+    struct Lay {
+        size_t d1, a1, v1, nd1, b1, s1, st1, d2, a2, v2, nd2, b2, st2, mout, nm, lists, llen;
+    };
+    std::vector<Lay> lay(n_problems);
+    int max_n1 = 0, max_n2 = 0;
+    for (int p = 0; p < n_problems; ++p) {
+        const b200_pairs_problem_t& P = problems[p];
+        if (P.n1 < 0 || P.n2 < 0 || (P.n1 > 0 && (!P.desc1 || !P.match_out)) || (P.n2 > 0 && !P.desc2) || ((P.node1 == nullptr) != (P.node2 == nullptr))
+            || (check_orientation && ((P.n1 > 0 && !P.angle1) || (P.n2 > 0 && !P.angle2)))
+            || (tri && ((P.n1 > 0 && (!P.bearing1 || !P.scale1)) || (P.n2 > 0 && !P.bearing2)))) {
+            b200::set_error("b200_match_pairs: bad sizes or null buffer in problem %d", p);
+            return B200_ERR_INVALID;
+        }
+        Lay& L = lay[p];
+        const size_t n1 = (size_t)P.n1, n2 = (size_t)P.n2;
+        L.d1 = add(P.desc1, 32 * n1);
+        L.a1 = add(check_orientation ? P.angle1 : nullptr, 4 * n1);
+        L.v1 = add(P.valid1, n1);
+        L.nd1 = add(P.node1, 4 * n1);
+        L.b1 = add(tri ? P.bearing1 : nullptr, 24 * n1);
+        L.s1 = add(tri ? P.scale1 : nullptr, 4 * n1);
+        L.st1 = add(tri ? P.stereo1 : nullptr, n1);
+        L.d2 = add(P.desc2, 32 * n2);
+        L.a2 = add(check_orientation ? P.angle2 : nullptr, 4 * n2);
+        L.v2 = add(P.valid2, n2);
+        L.nd2 = add(P.node2, 4 * n2);
+        L.b2 = add(tri ? P.bearing2 : nullptr, 24 * n2);
+        L.st2 = add(tri ? P.stereo2 : nullptr, n2);
+        max_n1 = std::max(max_n1, P.n1);
+        max_n2 = std::max(max_n2, P.n2);
+    }
+    const size_t in_bytes = o, out_begin = o;
+    for (int p = 0; p < n_problems; ++p) {
+        lay[p].mout = o; o += al(4 * (size_t)std::max(problems[p].n1, 1));
+        lay[p].nm = o; o += al(4);
+    }
+    const size_t o_overflow = o;
+    o += al(4);
+    const size_t out_end = o;
+    for (int p = 0; p < n_problems; ++p) {
+        lay[p].lists = o; o += al(8 * (size_t)cap * std::max(problems[p].n1, 1));
+        lay[p].llen = o; o += al(4 * (size_t)std::max(problems[p].n1, 1));
+    }
+    const size_t rs_bytes = (size_t)std::max(max_n2, 1) * 6 + 16;
+    if (rs_bytes > 200 * 1024) {
+        b200::set_error("b200_match_pairs: %d keypoints per frame exceed the on-chip occupancy table", max_n2);
+        return B200_ERR_CAPACITY;
+    }
+    int rc;
+    if ((rc = m.grow((void**)&m.d_guided, &m.d_guided_cap, o))) return rc;
+    if ((rc = m.grow_pinned(&m.h_guided, &m.h_guided_cap, out_end))) return rc;
+    unsigned char *hb = m.h_guided, *db = m.d_guided;
+    for (const Item& it : items)
+        if (it.bytes) std::memcpy(hb + it.off, it.src, it.bytes);
+    PairsDev* hg = reinterpret_cast<PairsDev*>(hb);
+    for (int p = 0; p < n_problems; ++p) {
+        const b200_pairs_problem_t& P = problems[p];
+        const Lay& L = lay[p];
+        PairsDev g{};
+        g.n_queries = P.n1;
+        g.n_train = P.n2;
+        g.cap = cap;
+        g.desc1 = (const uint4*)(db + L.d1);
+        g.desc2 = (const uint4*)(db + L.d2);
+        g.angle1 = (const float*)(db + L.a1);
+        g.angle2 = (const float*)(db + L.a2);
+        g.valid1 = P.valid1 ? db + L.v1 : nullptr;
+        g.valid2 = P.valid2 ? db + L.v2 : nullptr;
+        g.stereo1 = (tri && P.stereo1) ? db + L.st1 : nullptr;
+        g.stereo2 = (tri && P.stereo2) ? db + L.st2 : nullptr;
+        g.node1 = P.node1 ? (const int*)(db + L.nd1) : nullptr;
+        g.node2 = P.node2 ? (const int*)(db + L.nd2) : nullptr;
+        g.bearing1 = (const double*)(db + L.b1);
+        g.bearing2 = (const double*)(db + L.b2);
+        g.scale1 = (const float*)(db + L.s1);
+        for (int k = 0; k < 9; ++k) g.E[k] = P.E_12[k];
+        for (int k = 0; k < 3; ++k) g.epi[k] = P.epiplane_in_keyfrm_2[k];
+        g.valid_epiplane = P.valid_epiplane;
+        g.residual_rad_thr = P.residual_rad_thr;
+        g.lists = (uint2*)(db + L.lists);
+        g.list_len = (int*)(db + L.llen);
+        g.occupied = nullptr;
+        g.match_out = (int*)(db + L.mout);
+        g.n_matches = (int*)(db + L.nm);
+        g.owner = nullptr;
+        hg[p] = g;
+    }
+    cudaStream_t st = m.stream;
+    B200_CUDA(cudaMemcpyAsync(db, hb, in_bytes, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemsetAsync(db + o_overflow, 0, 4, st));
+    const PairsDev* dg = reinterpret_cast<const PairsDev*>(db);
+    b200::match::pairs_candidates_kernel<<<dim3(std::max(1, b200::ceil_div(max_n1, b200::match::kPairRows)), n_problems), b200::match::kPairRows, 0,
+                                           st>>>(dg, variant, list_thr, check_orientation, (int*)(db + o_overflow));
+    if (rs_bytes > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(b200::match::guided_resolve_kernel<PairsDev>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_bytes));
+    b200::match::guided_resolve_kernel<PairsDev><<<n_problems, 32, rs_bytes, st>>>(dg, tri ? 6 : 5, (unsigned)b200::match::kThrLow, lowe_ratio);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpyAsync(hb + out_begin, db + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    m.last_h2d = in_bytes;
+    m.last_d2h = out_end - out_begin;
+    const int overflow = *reinterpret_cast<const int*>(hb + o_overflow);
+    if (overflow > 0) {
+        b200::set_error("b200_match_pairs: a row kept %d gated candidates, max_candidates is %d", overflow, cap);
+        return B200_ERR_CAPACITY;
+    }
+    for (int p = 0; p < n_problems; ++p) {
+        b200_pairs_problem_t& P = problems[p];
+        if (P.n1 > 0) std::memcpy(P.match_out, hb + lay[p].mout, 4 * (size_t)P.n1);
+        P.n_matches = *reinterpret_cast<const int*>(hb + lay[p].nm);
+    }
+    return B200_OK;
+}
+
+int b200_match_cross_check(const int32_t* idx2_in_1, int n1, const int32_t* idx1_in_2, int n2, int32_t* mutual_out, int32_t* n_mutual) {
+    if (n1 < 0 || n2 < 0 || (n1 > 0 && (!idx2_in_1 || !mutual_out)) || (n2 > 0 && !idx1_in_2)) return B200_ERR_INVALID;
+    int n = 0;
+    for (int i = 0; i < n1; ++i) {
+        const int j = idx2_in_1[i];
+        const bool keep = 0 <= j && j < n2 && idx1_in_2[j] == i;
+        mutual_out[i] = keep ? j : -1;
+        n += keep;
+    }
+    if (n_mutual) *n_mutual = n;
     return B200_OK;
 }
 

@@ -4,7 +4,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import GuidedProblem, check, lib, pack_guided_problem, ptr
+from ._lib import GuidedProblem, PairsProblem, check, lib, pack_guided_problem, pack_pairs_problem, ptr
 
 HAMMING_DIST_THR_LOW = 50    # match/base.h:15
 HAMMING_DIST_THR_HIGH = 100  # match/base.h:16
@@ -83,63 +83,220 @@ class robust(base):
         return [pairs[i, :n_pairs[i]].copy() for i in range(P)]
 
 
+GUIDED_LANDMARKS, GUIDED_LAST_FRAME, GUIDED_INDEPENDENT, GUIDED_FUSE, GUIDED_AREA = range(5)  # b200vslam.h
+
+
+def match_guided_batch(problems, mode, thr, lowe_ratio, check_orientation, max_candidates=0, device=0):
+    """b200_match_guided on flattened problem dicts (see _lib.pack_guided_problem).
+    Returns [(match_out, occupied_after | None, n_matches)] per problem."""
+    if not problems:
+        return []
+    arr = (GuidedProblem * len(problems))()
+    keeps = []
+    for i, pr in enumerate(problems):
+        S, keep = pack_guided_problem(pr)
+        arr[i] = S
+        keeps.append(keep)
+    check(lib().b200_match_guided(_matcher(device), len(problems), arr, mode, int(thr), float(lowe_ratio), int(check_orientation), max_candidates))
+    return [(k["match_out"][:arr[i].n_queries].copy(), k.get("t_occupied"), int(arr[i].n_matches)) for i, k in enumerate(keeps)]
+
+
+def _guided_problem(frm, desc, reproj, level, min_level, max_level, margin, x_right=None, angle=None, valid=None, occupied=None, **extra):
+    """A frame dict (t_x, t_y, t_octave, t_angle, t_desc, [t_x_right], bounds, grid, scale_factors) + per-landmark arrays."""
+    sf = np.asarray(frm["scale_factors"], np.float32)
+    level = np.asarray(level, np.int64)
+    reproj = np.asarray(reproj, np.float64).reshape(-1, 2)
+    pr = {k: v for k, v in frm.items() if k.startswith("t_") or k in ("bounds", "grid")}
+    if occupied is not None:
+        pr["t_occupied"] = occupied
+    pr.update(q_desc=desc, q_x=reproj[:, 0].astype(np.float32), q_y=reproj[:, 1].astype(np.float32), q_margin=np.float32(margin) * sf[level],
+              q_min_level=min_level, q_max_level=max_level, q_x_right=x_right, q_angle=angle, q_valid=valid, **extra)
+    return pr
+
+
+def _level_window(frm, level):
+    lv = np.asarray(level, np.int64)
+    return lv, np.maximum(0, lv - 1), np.minimum(len(frm["scale_factors"]) - 1, lv + 1)
+
+
 class projection(base):
-    """match::projection (match/projection.h:24-67): the two per-frame grid-guided matchers
-    match_frame_and_landmarks (projection.cc:13-93) and match_current_and_last_frames (:95-207).
+    """match::projection (match/projection.h:24-67).  A frame / keyframe is a dict with t_x, t_y, t_octave, t_angle, t_desc,
+    optional t_x_right, bounds=(min_x, max_x, min_y, max_y) = camera img_bounds_, grid=(64, 48), scale_factors.  The map-side
+    work of each method (walking landmarks, reprojecting, predicting the level, validity) is the caller's, as in the adapter."""
 
-    A frame is described by a dict `frm` with t_x, t_y, t_octave, t_angle, t_desc, optional t_x_right / t_occupied,
-    bounds=(min_x, max_x, min_y, max_y) = camera img_bounds_, grid=(64, 48), scale_factors (orb_params_->scale_factors_)."""
-
-    GUIDED_LANDMARKS, GUIDED_LAST_FRAME = 0, 1
+    GUIDED_LANDMARKS, GUIDED_LAST_FRAME = GUIDED_LANDMARKS, GUIDED_LAST_FRAME
 
     def __init__(self, lowe_ratio=0.6, check_orientation=True, device=0):
         super().__init__(lowe_ratio, check_orientation)
         self.device = device
 
     def match_guided_batch(self, problems, mode, thr=HAMMING_DIST_THR_HIGH, max_candidates=0):
-        """problems: flattened dicts (see _lib.pack_guided_problem).  Returns [(match_out, occupied_after | None, n_matches)]."""
-        if not problems:
-            return []
-        arr = (GuidedProblem * len(problems))()
-        keeps = []
-        for i, pr in enumerate(problems):
-            S, keep = pack_guided_problem(pr)
-            arr[i] = S
-            keeps.append(keep)
-        check(lib().b200_match_guided(_matcher(self.device), len(problems), arr, mode, thr, float(self.lowe_ratio_), int(self.check_orientation_),
-                                      max_candidates))
-        return [(k["match_out"][:arr[i].n_queries].copy(), k.get("t_occupied"), int(arr[i].n_matches)) for i, k in enumerate(keeps)]
+        return match_guided_batch(problems, mode, thr, self.lowe_ratio_, self.check_orientation_, max_candidates, self.device)
 
-    @staticmethod
-    def _query_fields(frm, desc, reproj, level, min_level, max_level, margin, x_right, angle, valid):
-        sf = np.asarray(frm["scale_factors"], np.float32)
-        level = np.asarray(level, np.int64)
-        reproj = np.asarray(reproj, np.float64).reshape(-1, 2)
-        pr = {k: v for k, v in frm.items() if k.startswith("t_") or k in ("bounds", "grid")}
-        pr.update(q_desc=desc, q_x=reproj[:, 0].astype(np.float32), q_y=reproj[:, 1].astype(np.float32),
-                  q_margin=np.float32(margin) * sf[level], q_min_level=min_level, q_max_level=max_level, q_x_right=x_right, q_angle=angle,
-                  q_valid=valid)
-        return pr
-
-    def match_frame_and_landmarks(self, frm, lm_desc, lm_to_reproj, lm_to_scale, margin=5.0, lm_to_x_right=None, valid=None):
-        """Landmark q (in local_landmarks order) reprojects to lm_to_reproj[q] at predicted level lm_to_scale[q];
-        valid[q] = 0 for landmarks without a reprojection or about to be erased (projection.cc:23-28)."""
-        n_levels = len(frm["scale_factors"])
-        lv = np.asarray(lm_to_scale, np.int64)
-        pr = self._query_fields(frm, lm_desc, lm_to_reproj, lv, np.maximum(0, lv - 1), np.minimum(n_levels - 1, lv + 1), margin, lm_to_x_right,
-                                None, valid)
-        return self.match_guided_batch([pr], self.GUIDED_LANDMARKS)[0]
+    def match_frame_and_landmarks(self, frm, lm_desc, lm_to_reproj, lm_to_scale, margin=5.0, lm_to_x_right=None, valid=None, occupied=None):
+        """projection.cc:13-93.  valid[q] = 0 for landmarks without a reprojection or about to be erased (:23-28)."""
+        lv, lo, hi = _level_window(frm, lm_to_scale)
+        pr = _guided_problem(frm, lm_desc, lm_to_reproj, lv, lo, hi, margin, lm_to_x_right, None, valid, occupied)
+        return self.match_guided_batch([pr], GUIDED_LANDMARKS)[0]
 
     def match_current_and_last_frames(self, curr_frm, last_desc, last_reproj, last_octave, last_angle, margin, last_x_right=None, valid=None,
-                                      assume_forward=False, assume_backward=False):
-        """Query q = keypoint q of the last frame that carries a landmark (valid[q]), reprojected into the current frame
-        (projection.cc:121-160); level window per :140-154."""
-        n_levels = len(curr_frm["scale_factors"])
-        lv = np.asarray(last_octave, np.int64)
-        lo, hi = np.maximum(0, lv - 1), np.minimum(n_levels - 1, lv + 1)
+                                      occupied=None, assume_forward=False, assume_backward=False):
+        """projection.cc:95-207; the level window follows :140-154."""
+        lv, lo, hi = _level_window(curr_frm, last_octave)
         if assume_forward:
             lo = lv
         elif assume_backward:
             hi = lv
-        pr = self._query_fields(curr_frm, last_desc, last_reproj, lv, lo, hi, margin, last_x_right, last_angle, valid)
-        return self.match_guided_batch([pr], self.GUIDED_LAST_FRAME)[0]
+        pr = _guided_problem(curr_frm, last_desc, last_reproj, lv, lo, hi, margin, last_x_right, last_angle, valid, occupied)
+        return self.match_guided_batch([pr], GUIDED_LAST_FRAME)[0]
+
+    def match_frame_and_keyframe(self, frm, lm_desc, reproj, pred_scale_level, keyfrm_angle, margin, hamm_dist_thr, valid=None, occupied=None):
+        """projection.cc:217-319: the keyframe's landmarks into a frame whose pose is a candidate (relocalisation); no stereo gate."""
+        lv, lo, hi = _level_window(frm, pred_scale_level)
+        mono = {k: v for k, v in frm.items() if k != "t_x_right"}
+        pr = _guided_problem(mono, lm_desc, reproj, lv, lo, hi, margin, None, keyfrm_angle, valid, occupied)
+        return self.match_guided_batch([pr], GUIDED_LAST_FRAME, thr=hamm_dist_thr)[0]
+
+    def match_by_Sim3_transform(self, keyfrm, lm_desc, reproj, pred_scale_level, margin, valid=None, occupied=None):
+        """projection.cc:321-416 (loop closure): thr = HAMMING_DIST_THR_LOW, no orientation, no stereo gate."""
+        lv, lo, hi = _level_window(keyfrm, pred_scale_level)
+        mono = {k: v for k, v in keyfrm.items() if k != "t_x_right"}
+        pr = _guided_problem(mono, lm_desc, reproj, lv, lo, hi, margin, None, None, valid, occupied)
+        return match_guided_batch([pr], GUIDED_LAST_FRAME, HAMMING_DIST_THR_LOW, self.lowe_ratio_, False, 0, self.device)[0]
+
+    def match_keyframes_mutually(self, keyfrm_1, keyfrm_2, lms_1, lms_2, margin):
+        """projection.cc:418-630.  lms_k = dict(desc, reproj (into the OTHER keyframe), level, valid) for the landmarks of keyframe k
+        (valid excludes null / erased / already matched / out-of-range ones, :461-496).  Returns (idx_2 per keypoint of 1 | -1, n)."""
+        prs = []
+        for target, lms in ((keyfrm_2, lms_1), (keyfrm_1, lms_2)):
+            lv, lo, hi = _level_window(target, lms["level"])
+            mono = {k: v for k, v in target.items() if k not in ("t_x_right", "t_occupied")}
+            prs.append(_guided_problem(mono, lms["desc"], lms["reproj"], lv, lo, hi, margin, None, None, lms.get("valid")))
+        (m12, _, _), (m21, _, _) = match_guided_batch(prs, GUIDED_INDEPENDENT, HAMMING_DIST_THR_HIGH, self.lowe_ratio_, False, 0, self.device)
+        return cross_check(m12, m21)
+
+
+def cross_check(idx2_in_1, idx1_in_2):
+    a, b = np.ascontiguousarray(idx2_in_1, np.int32), np.ascontiguousarray(idx1_in_2, np.int32)
+    out = np.full(max(len(a), 1), -2, np.int32)
+    n = C.c_int32(0)
+    check(lib().b200_match_cross_check(ptr(a), len(a), ptr(b), len(b), ptr(out), C.byref(n)))
+    return out[:len(a)].copy(), n.value
+
+
+class fuse(base):
+    """match::fuse (match/fuse.h, fuse.cc:12-154)."""
+
+    def __init__(self, lowe_ratio=0.6, check_orientation=True, device=0):
+        super().__init__(lowe_ratio, check_orientation)
+        self.device = device
+
+    def detect_duplication(self, keyfrm, lm_desc, reproj, pred_scale_level, margin, x_right=None, valid=None, do_reprojection_matching=False,
+                           inv_level_sigma_sq=None):
+        """Returns (best_idx per landmark | -1, n_fused); the caller splits the hits into duplicated_lms_in_keyfrm / new_connections
+        by whether keypoint best_idx already carries a landmark (fuse.cc:131-146)."""
+        lv, lo, hi = _level_window(keyfrm, pred_scale_level)
+        pr = _guided_problem(keyfrm, lm_desc, reproj, lv, lo, hi, margin, x_right, None, valid, None,
+                             q_reproj=np.asarray(reproj, np.float64).reshape(-1, 2), inv_level_sigma_sq=inv_level_sigma_sq,
+                             do_reprojection_matching=do_reprojection_matching)
+        got, _, n = match_guided_batch([pr], GUIDED_FUSE, HAMMING_DIST_THR_LOW, self.lowe_ratio_, False, 0, self.device)[0]
+        return got, n
+
+
+class area(base):
+    """match::area (match/area.h, area.cc:8-98): the initialiser's matcher."""
+
+    def __init__(self, lowe_ratio=0.9, check_orientation=True, device=0):
+        super().__init__(lowe_ratio, check_orientation)
+        self.device = device
+
+    def match_in_consistent_area(self, frm_1, frm_2, prev_matched_pts, margin):
+        """frm_k: frame dicts.  Returns (matched_indices_2_in_frm_1, n, updated prev_matched_pts) (area.cc:89-95)."""
+        oct1 = np.asarray(frm_1["t_octave"], np.int64)
+        n1 = len(oct1)
+        prev = np.array(prev_matched_pts, np.float32).reshape(-1, 2)
+        pr = {k: v for k, v in frm_2.items() if (k.startswith("t_") and k not in ("t_x_right", "t_occupied")) or k in ("bounds", "grid")}
+        pr.update(q_desc=frm_1["t_desc"], q_x=prev[:, 0], q_y=prev[:, 1], q_margin=np.full(n1, np.float32(int(margin))),
+                  q_min_level=np.zeros(n1, np.int8), q_max_level=np.zeros(n1, np.int8), q_angle=frm_1["t_angle"],
+                  q_valid=(oct1 <= 0).astype(np.uint8))
+        got, _, n = match_guided_batch([pr], GUIDED_AREA, HAMMING_DIST_THR_LOW, self.lowe_ratio_, self.check_orientation_, 0, self.device)[0]
+        hit = got >= 0
+        prev[hit, 0] = np.asarray(frm_2["t_x"], np.float32)[got[hit]]
+        prev[hit, 1] = np.asarray(frm_2["t_y"], np.float32)[got[hit]]
+        return got, n, prev
+
+
+PAIRS_BOW, PAIRS_TRIANGULATION = 0, 1  # b200vslam.h
+
+
+def match_pairs_batch(problems, variant, lowe_ratio, check_orientation, max_candidates=0, device=0):
+    """b200_match_pairs on problem dicts (see _lib.pack_pairs_problem).  Returns [(match_out per row, n_matches)]."""
+    if not problems:
+        return []
+    arr = (PairsProblem * len(problems))()
+    keeps = []
+    for i, pr in enumerate(problems):
+        S, keep = pack_pairs_problem(pr)
+        arr[i] = S
+        keeps.append(keep)
+    check(lib().b200_match_pairs(_matcher(device), len(problems), arr, variant, float(lowe_ratio), int(check_orientation), max_candidates))
+    return [(k["match_out"][:arr[i].n1].copy(), int(arr[i].n_matches)) for i, k in enumerate(keeps)]
+
+
+def _triangulation_problem(keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane, residual_rad_thr, with_nodes):
+    sf = np.asarray(keyfrm_1["scale_factors"], np.float32)
+    pr = dict(desc1=keyfrm_1["desc"], angle1=keyfrm_1["angle"], valid1=keyfrm_1.get("no_landmark"), bearing1=keyfrm_1["bearings"],
+              scale1=sf[np.asarray(keyfrm_1["octave"], np.int64)], stereo1=keyfrm_1.get("stereo"),
+              desc2=keyfrm_2["desc"], angle2=keyfrm_2["angle"], valid2=keyfrm_2.get("no_landmark"), bearing2=keyfrm_2["bearings"],
+              stereo2=keyfrm_2.get("stereo"), E_12=E_12, epiplane_in_keyfrm_2=epiplane_in_keyfrm_2, valid_epiplane=valid_epiplane,
+              residual_rad_thr=residual_rad_thr)
+    if with_nodes:
+        pr.update(node1=keyfrm_1["node"], node2=keyfrm_2["node"])
+    return pr
+
+
+def _pairs_of(match_out):
+    idx_1 = np.flatnonzero(match_out >= 0)
+    return np.stack([idx_1, match_out[idx_1]], 1).astype(np.int32)  # matched_idx_pairs, sorted by idx_1 (robust.cc:137-143)
+
+
+def _match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane=True, residual_rad_thr=0.01 * np.pi / 180.0,
+                             with_nodes=False):
+    pr = _triangulation_problem(keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane, residual_rad_thr, with_nodes)
+    got, n = match_pairs_batch([pr], PAIRS_TRIANGULATION, self.lowe_ratio_, self.check_orientation_, 0, self.device)[0]
+    return _pairs_of(got)
+
+
+def _robust_match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane=True, residual_rad_thr=0.01 * np.pi / 180.0):
+    """robust::match_for_triangulation (robust.cc:14-146).  keyfrm_k: dict(desc, angle, octave, bearings (n,3) f64, scale_factors,
+    no_landmark (u8: keypoint carries no landmark), stereo (u8) | None).  Returns matched_idx_pairs (n, 2)."""
+    return _match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane, residual_rad_thr, False)
+
+
+robust.match_for_triangulation = _robust_match_for_triangulation
+
+
+class bow_tree(base):
+    """match::bow_tree (match/bow_tree.h, bow_tree.cc).  Keyframes / frames are dicts as for robust.match_for_triangulation plus
+    node = the BoW node id of every keypoint (the bow_feat_vec_ entry that lists it)."""
+
+    def __init__(self, lowe_ratio=0.6, check_orientation=True, device=0):
+        super().__init__(lowe_ratio, check_orientation)
+        self.device = device
+
+    def match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane=True, residual_rad_thr=0.01 * np.pi / 180.0):
+        """bow_tree.cc:11-167."""
+        return _match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane, residual_rad_thr, True)
+
+    def match_frame_and_keyframe(self, keyfrm, frm):
+        """bow_tree.cc:169-256.  keyfrm["has_landmark"]: live landmark per keypoint.  Returns (frame index per keyframe keypoint | -1, n):
+        matched_lms_in_frm[out[i]] = keyfrm landmark i."""
+        pr = dict(desc1=keyfrm["desc"], angle1=keyfrm["angle"], valid1=keyfrm["has_landmark"], node1=keyfrm["node"],
+                  desc2=frm["desc"], angle2=frm["angle"], node2=frm["node"])
+        return match_pairs_batch([pr], PAIRS_BOW, self.lowe_ratio_, self.check_orientation_, 0, self.device)[0]
+
+    def match_keyframes(self, keyfrm_1, keyfrm_2):
+        """bow_tree.cc:258-366: both sides restricted to keypoints with live landmarks.  Returns (idx_2 per keypoint of 1 | -1, n)."""
+        pr = dict(desc1=keyfrm_1["desc"], angle1=keyfrm_1["angle"], valid1=keyfrm_1["has_landmark"], node1=keyfrm_1["node"],
+                  desc2=keyfrm_2["desc"], angle2=keyfrm_2["angle"], valid2=keyfrm_2["has_landmark"], node2=keyfrm_2["node"])
+        return match_pairs_batch([pr], PAIRS_BOW, self.lowe_ratio_, self.check_orientation_, 0, self.device)[0]

@@ -274,7 +274,12 @@ def make_guided_problem(seed, n_train=2000, n_queries=1500, mode=0, stereo=False
                 q_desc=q_desc, q_x=q_xy[:, 0].astype(np.float32), q_y=q_xy[:, 1].astype(np.float32), q_margin=q_margin,
                 q_min_level=lo.astype(np.int8), q_max_level=hi.astype(np.int8),
                 q_angle=((angle[src] + rng.normal(0, 18, n_queries)) % 360).astype(np.float32),
-                q_valid=(rng.random(n_queries) > 0.1).astype(np.uint8))
+                q_valid=(rng.random(n_queries) > 0.1).astype(np.uint8),
+                q_reproj=q_xy.copy(), inv_level_sigma_sq=(np.float32(1.0) / (sf * sf)).astype(np.float32),
+                do_reprojection_matching=(mode == 3))
+    if mode == 4:  # area::match_in_consistent_area: level-0 keypoints only, one integer margin
+        prob.update(q_min_level=np.zeros(n_queries, np.int8), q_max_level=np.zeros(n_queries, np.int8),
+                    q_margin=np.full(n_queries, np.float32(int(margin * 4))), q_valid=(level == 0).astype(np.uint8))
     if stereo:
         xr = (pts[:, 0] - rng.uniform(2, 60, n_train)).astype(np.float32)
         xr[rng.random(n_train) < 0.3] = -1.0                    # no stereo match for this keypoint

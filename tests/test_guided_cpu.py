@@ -38,6 +38,7 @@ def literal_guided(pr, mode, thr=100, lowe=0.8, check_orientation=True):
     occ = np.array(pr["t_occupied"], np.uint8).copy() if pr.get("t_occupied") is not None else np.zeros(n, np.uint8)
     xr = pr.get("t_x_right")
     out = np.full(len(pr["q_x"]), -1, np.int32)
+    dist_state, owner = np.full(n, 256, np.int64), np.full(n, -1, np.int64)
     for q in range(len(pr["q_x"])):
         if pr.get("q_valid") is not None and not pr["q_valid"][q]:
             continue
@@ -60,12 +61,33 @@ def literal_guided(pr, mode, thr=100, lowe=0.8, check_orientation=True):
                         continue
                     if not (abs(f32(pr["t_x"][idx]) - rx) < m and abs(f32(pr["t_y"][idx]) - ry) < m):
                         continue
+                    if mode == 4:  # area.cc:41-62
+                        if check_orientation and abs(_angle_diff(pr["q_angle"][q], pr["t_angle"][idx])) > 30.0:
+                            continue
+                        d = _popcount(pr["q_desc"][q], pr["t_desc"][idx])
+                        if dist_state[idx] <= d:
+                            continue
+                        if d < best:
+                            second, best, best_idx = best, d, idx
+                        elif d < second:
+                            second = d
+                        continue
                     if occ[idx]:
                         continue
-                    if xr is not None and xr[idx] > 0 and m < abs(f32(pr["q_x_right"][q]) - f32(xr[idx])):
+                    if mode <= 1 and xr is not None and xr[idx] > 0 and m < abs(f32(pr["q_x_right"][q]) - f32(xr[idx])):
                         continue
                     if mode == 1 and check_orientation and abs(_angle_diff(pr["q_angle"][q], pr["t_angle"][idx])) > 30.0:
                         continue
+                    if mode == 3 and pr.get("do_reprojection_matching"):  # fuse.cc:93-120
+                        e_x = float(pr["q_reproj"][q][0]) - float(f32(pr["t_x"][idx]))
+                        e_y = float(pr["q_reproj"][q][1]) - float(f32(pr["t_y"][idx]))
+                        inv_sigma = float(f32(pr["inv_level_sigma_sq"][o]))
+                        if xr is not None and xr[idx] >= 0:
+                            e_xr = f32(pr["q_x_right"][q]) - f32(xr[idx])
+                            if float(f32(7.81473)) < (e_x * e_x + e_y * e_y + float(f32(e_xr * e_xr))) * inv_sigma:
+                                continue
+                        elif float(f32(5.99146)) < (e_x * e_x + e_y * e_y) * inv_sigma:
+                            continue
                     d = _popcount(pr["q_desc"][q], pr["t_desc"][idx])
                     if d < best:
                         second, second_lv, best, best_lv, best_idx = best, best_lv, d, o, idx
@@ -75,8 +97,16 @@ def literal_guided(pr, mode, thr=100, lowe=0.8, check_orientation=True):
             continue
         if mode == 0 and best_lv == second_lv and f32(best) > f32(lowe) * f32(second):
             continue
+        if mode == 4:
+            if f32(second) * f32(lowe) < f32(best):
+                continue
+            if owner[best_idx] >= 0:
+                out[owner[best_idx]] = -1
+            owner[best_idx] = q
+            dist_state[best_idx] = best
+        elif mode != 2:
+            occ[best_idx] = 1
         out[q] = best_idx
-        occ[best_idx] = 1
     return out, occ
 
 
@@ -89,6 +119,34 @@ def test_oracle_matches_literal_walk(mode, stereo):
     assert np.array_equal(got, want)
     assert np.array_equal(occ, occ_want)
     assert n == (want >= 0).sum() > 50
+
+
+@pytest.mark.parametrize("mode,thr", [(2, 100), (3, 50), (4, 50)])
+@pytest.mark.parametrize("stereo", [False, True])
+def test_oracle_matches_literal_walk_occasional_variants(mode, thr, stereo):
+    pr = synth.make_guided_problem(40 + mode, n_train=700, n_queries=600, mode=mode, stereo=stereo)
+    if mode != 3:
+        pr["t_occupied"] = np.zeros(700, np.uint8) if mode == 4 else pr["t_occupied"]
+    got, occ, n = O.match_guided(pr, mode, thr=thr, lowe_ratio=0.9, check_orientation=True)
+    want, occ_want = literal_guided(pr, mode, thr=thr, lowe=0.9)
+    assert np.array_equal(got, want)
+    assert n == (want >= 0).sum() > 30
+    if mode == 3:
+        assert np.array_equal(occ, occ_want)
+    else:
+        assert np.array_equal(occ, pr["t_occupied"])               # modes 2 and 4 do not write occupancy back
+    if mode == 2:
+        assert len(np.unique(got[got >= 0])) < (got >= 0).sum()    # stateless: several landmarks may pick one keypoint
+    if mode == 4:
+        hit = got[got >= 0]
+        assert len(np.unique(hit)) == len(hit)                    # after stealing every keypoint has one owner
+
+
+def test_cross_check():
+    a = np.array([3, -1, 0, 2, 7], np.int32)
+    b = np.array([2, 1, 5, 0], np.int32)
+    out, n = O.cross_check(a, b)
+    assert out.tolist() == [3, -1, 0, -1, -1] and n == 2
 
 
 def test_oracle_guided_properties():

@@ -10,12 +10,11 @@ from stella_vslam_b200._lib import ERR_CAPACITY, B200Error
 pytestmark = pytest.mark.gpu
 
 
-def _check(problems, mode, lowe=0.8, check_orientation=True, max_candidates=0):
-    P = match.projection(lowe, check_orientation)
-    res = P.match_guided_batch(problems, mode, max_candidates=max_candidates)
+def _check(problems, mode, lowe=0.8, check_orientation=True, max_candidates=0, thr=100):
+    res = match.match_guided_batch(problems, mode, thr, lowe, check_orientation, max_candidates)
     total = 0
     for pr, (got, occ, n) in zip(problems, res):
-        want, occ_want, n_want = O.match_guided(pr, mode, lowe_ratio=lowe, check_orientation=check_orientation)
+        want, occ_want, n_want = O.match_guided(pr, mode, thr=thr, lowe_ratio=lowe, check_orientation=check_orientation)
         assert np.array_equal(got, want)
         assert n == n_want
         if pr.get("t_occupied") is not None:
@@ -89,3 +88,88 @@ def test_guided_named_methods():
     ref = dict(pr, q_margin=np.float32(10.0) * pr["scale_factors"][lv], q_min_level=lv, q_max_level=np.minimum(7, lv + 1))
     want, _, n_want = O.match_guided(ref, 1, check_orientation=True)
     assert np.array_equal(got, want) and n == n_want
+
+
+@pytest.mark.parametrize("mode,thr", [(2, 100), (3, 50), (4, 50)])
+@pytest.mark.parametrize("stereo", [False, True])
+def test_guided_occasional_variants(mode, thr, stereo):
+    """mode 2: one direction of match_keyframes_mutually; 3: fuse::detect_duplication with the chi-square gate; 4: area matcher."""
+    probs = [synth.make_guided_problem(60 + mode + k, n_train=2000, n_queries=2500, mode=mode, stereo=stereo) for k in range(3)]
+    if mode == 3:
+        probs[1]["do_reprojection_matching"] = False
+        for pr in probs:
+            pr["t_occupied"] = None
+    assert _check(probs, mode, lowe=0.9, thr=thr) > 300
+
+
+def test_guided_area_steals_under_contention():
+    pr = synth.make_guided_problem(77, n_train=120, n_queries=4000, mode=4)
+    pr["q_margin"][:] = 40.0
+    n = _check([pr], 4, lowe=1.0, thr=100, check_orientation=False)
+    assert 0 < n <= 120
+
+
+def _frame_of(pr):
+    return {k: v for k, v in pr.items() if (k.startswith("t_") and k != "t_occupied") or k in ("bounds", "grid", "scale_factors")}
+
+
+def test_keyframes_mutually_and_cross_check():
+    """Keyframe 2 sees a shuffled, slightly moved copy of keyframe 1's keypoints; landmark i of 1 reprojects near keypoint perm[i] of 2."""
+    a = synth.make_guided_problem(81, n_train=1500, n_queries=10, mode=2)
+    rng = np.random.default_rng(3)
+    perm = rng.permutation(1500)
+    kf1 = _frame_of(a)
+    kf2 = dict(kf1)
+    flips = rng.integers(0, 256, (1500, 32), dtype=np.uint8) & rng.integers(0, 256, (1500, 32), dtype=np.uint8) & rng.integers(0, 256, (1500, 32), dtype=np.uint8)
+    for k in ("t_x", "t_y", "t_octave", "t_angle"):
+        kf2[k] = np.empty_like(kf1[k])
+        kf2[k][perm] = kf1[k]
+    kf2["t_desc"] = np.empty_like(kf1["t_desc"])
+    kf2["t_desc"][perm] = kf1["t_desc"] ^ flips
+    kf2["t_x"] = (kf2["t_x"] + rng.normal(0, 1.5, 1500)).astype(np.float32)
+    inv = np.argsort(perm)
+    lv1, lv2 = kf1["t_octave"].astype(np.int64), kf2["t_octave"].astype(np.int64)
+    noise = lambda: rng.normal(0, 2.0, (1500, 2))
+    lms_1 = dict(desc=kf1["t_desc"], reproj=np.stack([kf2["t_x"][perm], kf2["t_y"][perm]], 1) + noise(), level=lv1, valid=rng.random(1500) > 0.1)
+    lms_2 = dict(desc=kf2["t_desc"], reproj=np.stack([kf1["t_x"][inv], kf1["t_y"][inv]], 1) + noise(), level=lv2, valid=rng.random(1500) > 0.1)
+    got, n = match.projection(0.8, True).match_keyframes_mutually(kf1, kf2, lms_1, lms_2, margin=7.5)
+
+    def one(target, lms, lv):
+        pr = dict({k: v for k, v in target.items() if k != "scale_factors"}, q_desc=lms["desc"], q_x=lms["reproj"][:, 0].astype(np.float32),
+                  q_y=lms["reproj"][:, 1].astype(np.float32), q_margin=np.float32(7.5) * target["scale_factors"][lv],
+                  q_min_level=np.maximum(0, lv - 1), q_max_level=np.minimum(7, lv + 1), q_valid=lms["valid"])
+        return O.match_guided(pr, 2, thr=100)[0]
+
+    want, n_want = O.cross_check(one(kf2, lms_1, lv1), one(kf1, lms_2, lv2))
+    assert np.array_equal(got, want) and n == n_want and n > 500
+    hit = got >= 0
+    assert (got[hit] == perm[hit]).mean() > 0.95
+
+
+def test_fuse_and_area_named_methods():
+    pr = synth.make_guided_problem(91, mode=3, stereo=True)
+    kf = _frame_of(pr)
+    lv = np.random.default_rng(1).integers(0, 8, len(pr["q_x"]))
+    got, n = match.fuse(0.6, True).detect_duplication(kf, pr["q_desc"], pr["q_reproj"], lv, 3.0, x_right=pr["q_x_right"], valid=pr["q_valid"],
+                                                      do_reprojection_matching=True, inv_level_sigma_sq=pr["inv_level_sigma_sq"])
+    ref = dict(pr, t_occupied=None, q_x=pr["q_reproj"][:, 0].astype(np.float32), q_y=pr["q_reproj"][:, 1].astype(np.float32),
+               q_margin=np.float32(3.0) * pr["scale_factors"][lv], q_min_level=np.maximum(0, lv - 1), q_max_level=np.minimum(7, lv + 1))
+    want, _, n_want = O.match_guided(ref, 3, thr=50)
+    assert np.array_equal(got, want) and n == n_want
+
+    f1 = synth.make_guided_problem(92, n_train=1800, n_queries=10, mode=4)
+    f2 = synth.make_guided_problem(93, n_train=1800, n_queries=10, mode=4)
+    f2["t_desc"][:900] = f1["t_desc"][:900]
+    f2["t_octave"][:900] = f1["t_octave"][:900]
+    f2["t_angle"][:900] = f1["t_angle"][:900]
+    f2["t_x"][:900], f2["t_y"][:900] = f1["t_x"][:900] + 3, f1["t_y"][:900] - 2
+    fr1, fr2 = _frame_of(f1), _frame_of(f2)
+    prev = np.stack([f1["t_x"], f1["t_y"]], 1)
+    got, n, new_prev = match.area(0.9, True).match_in_consistent_area(fr1, fr2, prev, 50)
+    ref = dict({k: v for k, v in fr2.items() if k != "t_x_right"}, q_desc=f1["t_desc"], q_x=f1["t_x"], q_y=f1["t_y"],
+               q_margin=np.full(1800, 50, np.float32), q_min_level=np.zeros(1800, np.int8), q_max_level=np.zeros(1800, np.int8),
+               q_angle=f1["t_angle"], q_valid=(f1["t_octave"] == 0).astype(np.uint8))
+    want, _, n_want = O.match_guided(ref, 4, thr=50, lowe_ratio=0.9)
+    assert np.array_equal(got, want) and n == n_want and n > 20
+    hit = want >= 0
+    assert np.array_equal(new_prev[hit, 0], f2["t_x"][want[hit]]) and np.array_equal(new_prev[~hit], prev[~hit])
