@@ -260,14 +260,14 @@ def _pairs_of(match_out):
     return np.stack([idx_1, match_out[idx_1]], 1).astype(np.int32)  # matched_idx_pairs, sorted by idx_1 (robust.cc:137-143)
 
 
-def _match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane=True, residual_rad_thr=0.01 * np.pi / 180.0,
+def _match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane=True, residual_rad_thr=0.2 * np.pi / 180.0,
                              with_nodes=False):
     pr = _triangulation_problem(keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane, residual_rad_thr, with_nodes)
     got, n = match_pairs_batch([pr], PAIRS_TRIANGULATION, self.lowe_ratio_, self.check_orientation_, 0, self.device)[0]
     return _pairs_of(got)
 
 
-def _robust_match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane=True, residual_rad_thr=0.01 * np.pi / 180.0):
+def _robust_match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane=True, residual_rad_thr=0.2 * np.pi / 180.0):
     """robust::match_for_triangulation (robust.cc:14-146).  keyfrm_k: dict(desc, angle, octave, bearings (n,3) f64, scale_factors,
     no_landmark (u8: keypoint carries no landmark), stereo (u8) | None).  Returns matched_idx_pairs (n, 2)."""
     return _match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane, residual_rad_thr, False)
@@ -284,7 +284,7 @@ class bow_tree(base):
         super().__init__(lowe_ratio, check_orientation)
         self.device = device
 
-    def match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane=True, residual_rad_thr=0.01 * np.pi / 180.0):
+    def match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane=True, residual_rad_thr=0.2 * np.pi / 180.0):
         """bow_tree.cc:11-167."""
         return _match_for_triangulation(self, keyfrm_1, keyfrm_2, E_12, epiplane_in_keyfrm_2, valid_epiplane, residual_rad_thr, True)
 

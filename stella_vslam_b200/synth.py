@@ -286,3 +286,70 @@ def make_guided_problem(seed, n_train=2000, n_queries=1500, mode=0, stereo=False
         prob["t_x_right"] = xr
         prob["q_x_right"] = (xr[src] + rng.normal(0, q_margin * 0.6)).astype(np.float32)
     return prob
+
+
+def make_keyframe_pair(seed, n1=2000, n2=2000, stereo=False, n_nodes=150, num_levels=8, scale_factor=1.2, bearing_noise=1.5e-3):
+    """Two keyframes looking at the same synthetic points, for the all-pairs matchers with greedy state (bow_tree::*,
+    robust::match_for_triangulation).  Returns (keyfrm_1, keyfrm_2, geometry): dicts with desc, angle, octave, bearings (unit,
+    f64), node (BoW node id), no_landmark / has_landmark (u8), stereo (u8 | None), scale_factors; geometry holds E_12 with
+    bearing_1 . (E_12 bearing_2) = 0 for true correspondences, the epipole of keyframe 1 in keyframe 2, and the pair list.
+    Corresponding keypoints share descriptors up to noise of varied strength; some rows have two look-alike candidates (ratio
+    test), some correspondences violate the epipolar constraint, some sit next to the epipole."""
+    rng = np.random.default_rng(seed)
+    sf = np.cumprod(np.concatenate([[np.float32(1.0)], np.full(num_levels - 1, np.float32(scale_factor))])).astype(np.float32)
+    n_common = int(0.7 * min(n1, n2))
+    # relative pose: x1 = R_12 x2 + t_12  (mostly forward motion, so the epipole lies inside the image)
+    R_12 = _rodrigues(rng.normal(0, 0.03, 3))
+    t_12 = np.array([0.15, -0.05, 0.6]) + rng.normal(0, 0.02, 3)
+    tx = np.array([[0, -t_12[2], t_12[1]], [t_12[2], 0, -t_12[0]], [-t_12[1], t_12[0], 0]])
+    E_12 = tx @ R_12
+    pts2 = np.stack([rng.uniform(-4, 4, n_common), rng.uniform(-3, 3, n_common), rng.uniform(4, 30, n_common)], 1)
+    near_epipole = rng.random(n_common) < 0.04           # along the baseline as seen from camera 2
+    c1_in_2 = -R_12.T @ t_12
+    pts2[near_epipole] = c1_in_2 * rng.uniform(8, 30, (near_epipole.sum(), 1)) + rng.normal(0, 0.15, (near_epipole.sum(), 3))
+    pts1 = pts2 @ R_12.T + t_12
+
+    def unit(v):
+        return v / np.linalg.norm(v, axis=1, keepdims=True)
+
+    def side(n, pts, perm):
+        b = unit(np.stack([rng.uniform(-0.8, 0.8, n), rng.uniform(-0.6, 0.6, n), np.ones(n)], 1))
+        b[perm] = unit(unit(pts) + rng.normal(0, bearing_noise, pts.shape))
+        return b
+
+    perm1, perm2 = rng.permutation(n1)[:n_common], rng.permutation(n2)[:n_common]
+    bearings1, bearings2 = side(n1, pts1, perm1), side(n2, pts2, perm2)
+    wrong = rng.random(n_common) < 0.1                   # correspondences that break the epipolar constraint
+    bearings2[perm2[wrong]] = unit(bearings2[perm2[wrong]] + rng.normal(0, 0.05, (wrong.sum(), 3)))
+    desc1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+    desc2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    strength = rng.integers(2, 6, n_common)
+    fl = np.full((n_common, 32), 255, np.uint8)
+    for k in range(6):
+        r = rng.integers(0, 256, (n_common, 32), dtype=np.uint8)
+        fl = np.where((strength > k)[:, None], fl & r, fl)
+    desc2[perm2] = desc1[perm1] ^ fl
+    octave1 = rng.choice(num_levels, n1, p=np.array([.3, .22, .16, .12, .08, .06, .04, .02])).astype(np.uint8)
+    octave2 = octave1[rng.integers(0, n1, n2)]
+    octave2[perm2] = octave1[perm1]
+    angle1 = rng.uniform(0, 360, n1).astype(np.float32)
+    angle2 = rng.uniform(0, 360, n2).astype(np.float32)
+    angle2[perm2] = (angle1[perm1] + rng.normal(0, 14, n_common)) % 360
+    node1, node2 = rng.integers(0, n_nodes, n1).astype(np.int32), rng.integers(0, n_nodes, n2).astype(np.int32)
+    same_node = rng.random(n_common) < 0.9
+    node2[perm2[same_node]] = node1[perm1[same_node]]
+    # look-alikes: a second candidate in the same node with a similar descriptor and the same bearing (passes every gate)
+    free2 = np.setdiff1d(np.arange(n2), perm2)
+    for k, j in zip(rng.permutation(n_common)[:len(free2) // 2], free2):
+        noise = rng.integers(0, 256, 32, dtype=np.uint8) & rng.integers(0, 256, 32, dtype=np.uint8) & rng.integers(0, 256, 32, dtype=np.uint8) \
+            & rng.integers(0, 256, 32, dtype=np.uint8)
+        desc2[j] = desc2[perm2[k]] ^ noise
+        bearings2[j], angle2[j], node2[j] = bearings2[perm2[k]], angle2[perm2[k]], node2[perm2[k]]
+    has_lm1, has_lm2 = (rng.random(n1) < 0.5).astype(np.uint8), (rng.random(n2) < 0.5).astype(np.uint8)
+
+    def kf(desc, angle, octave, bearings, node, has_lm, n):
+        return dict(desc=desc, angle=angle, octave=octave, bearings=np.ascontiguousarray(bearings), node=node, has_landmark=has_lm,
+                    no_landmark=(1 - has_lm).astype(np.uint8), stereo=(rng.random(n) < 0.4).astype(np.uint8) if stereo else None, scale_factors=sf)
+
+    geometry = dict(E_12=E_12, epiplane_in_keyfrm_2=c1_in_2 / np.linalg.norm(c1_in_2), valid_epiplane=True, perm1=perm1, perm2=perm2)
+    return kf(desc1, angle1, octave1, bearings1, node1, has_lm1, n1), kf(desc2, angle2, octave2, bearings2, node2, has_lm2, n2), geometry
