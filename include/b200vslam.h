@@ -108,6 +108,8 @@ int b200_orb_sync(b200_orb_t h);
 int b200_orb_level_info(b200_orb_t h, int level, int* width, int* height, size_t* pitch, float* scale_factor);
 int b200_orb_pyramid_level_device(b200_orb_t h, int frame, int level, const uint8_t** d_ptr);
 int b200_orb_pyramid_level_host(b200_orb_t h, int frame, int level, uint8_t* dst, size_t dst_pitch);
+/* Every level including 0 (the caller's device image, or the upload staging of b200_orb_extract), with its pitch and size. */
+int b200_orb_pyramid_level_view(b200_orb_t h, int frame, int level, const uint8_t** d_ptr, size_t* pitch, int* width, int* height);
 
 /* Per-stage kernel time of the last extract, in ms, measured with CUDA events on the instance stream.
  * stage: 0 pyramid, 1 FAST+NMS+grid arg-max, 2 ordered selection, 3 descriptor blur, 4 orientation+rBRIEF, 5 whole extract. */
@@ -243,6 +245,16 @@ typedef struct b200_pairs_problem {
 /* max_candidates bounds the gated candidates kept per row (0 = default 64); B200_ERR_CAPACITY reports the size needed. */
 int b200_match_pairs(b200_matcher_t h, int n_problems, b200_pairs_problem_t* problems, int variant, float lowe_ratio,
                      int check_orientation, int max_candidates);
+/* match::stereo::compute (src/stella_vslam/match/stereo.cc:20-114, helpers :116-251; constructed at system.cc:443 from the two
+ * extractors' image_pyramid_).  `left` / `right` are the extractor handles whose last extract produced the two rectified frames
+ * (frame index inside that extract's batch; both eyes may also be frames 0 and 1 of ONE handle): their pyramids are read where
+ * they already live on the device.  Keypoints / descriptors are HOST buffers (the caller may have filtered them).
+ * scale_factors_ / inv_scale_factors_ are the extractor's own (orb_params.cc:37-48).
+ * Out: stereo_x_right[i], depths[i] (-1 = no stereo match), n_matched = keypoints that keep one. */
+int b200_stereo_compute(b200_matcher_t h, b200_orb_t left, int frame_left, b200_orb_t right, int frame_right,
+                        const b200_keypoint_t* keypts_left, const uint8_t* descs_left, int n_left, const b200_keypoint_t* keypts_right,
+                        const uint8_t* descs_right, int n_right, float focal_x_baseline, float true_baseline, float* stereo_x_right,
+                        float* depths, int32_t* n_matched);
 /* Run on the caller's stream (a cudaStream_t; NULL is the legacy default stream); use_own != 0 restores the own stream. */
 int b200_matcher_set_stream(b200_matcher_t h, void* stream, int use_own);
 int b200_matcher_sync(b200_matcher_t h);

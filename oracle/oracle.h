@@ -95,6 +95,13 @@ typedef struct {
 int orc_match_guided(const orc_guided_t* P, int mode, unsigned thr, float lowe_ratio, int check_orientation, int32_t* match_out);
 int orc_cross_check(const int32_t* idx2_in_1, int n1, const int32_t* idx1_in_2, int n2, int32_t* mutual_out);
 
+/* ---- match::stereo (stereo_oracle.c): stereo::compute (stereo.cc:20-114).  pyr_*[l]: level l, tight stride = widths[l].
+ * Returns the number of keypoints that keep a stereo match. */
+int orc_stereo_compute(const uint8_t* const* pyr_left, const uint8_t* const* pyr_right, const int* widths, const int* heights,
+                       const orc_keypoint_t* kl, const uint8_t* dl, int n_left, const orc_keypoint_t* kr, const uint8_t* dr, int n_right,
+                       const float* scale_factors, const float* inv_scale_factors, float focal_x_baseline, float true_baseline,
+                       float* stereo_x_right, float* depths);
+
 /* ---- all-pairs matchers with greedy state (pairs_oracle.c) ------------------------------------------------------------ */
 typedef struct {
     int32_t n1;                  /* rows: keyframe 1 / the keyframe */

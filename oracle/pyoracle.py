@@ -301,6 +301,29 @@ def match_pairs(prob, variant, lowe_ratio=0.6, check_orientation=True):
     return out[:S.n1].copy(), n
 
 
+# ---- match::stereo ------------------------------------------------------------------------------------------------------------
+def stereo_compute(pyr_left, pyr_right, kps_left, desc_left, kps_right, desc_right, focal_x_baseline, true_baseline, scale_factor=1.2):
+    """stereo::compute (stereo.cc:20-114).  pyr_*: lists of tight u8 level images; kps_*: KP_DTYPE arrays.  Returns (x_right, depths)."""
+    n_levels = len(pyr_left)
+    pl = [np.ascontiguousarray(a, np.uint8) for a in pyr_left]
+    prr = [np.ascontiguousarray(a, np.uint8) for a in pyr_right]
+    widths = np.array([a.shape[1] for a in pl], np.int32)
+    heights = np.array([a.shape[0] for a in pl], np.int32)
+    lp = (C.c_void_p * n_levels)(*[a.ctypes.data for a in pl])
+    rp = (C.c_void_p * n_levels)(*[a.ctypes.data for a in prr])
+    sf, inv = scale_factors(scale_factor, n_levels)[:2]
+    kl, kr = np.ascontiguousarray(kps_left, KP_DTYPE), np.ascontiguousarray(kps_right, KP_DTYPE)
+    dl, dr = np.ascontiguousarray(desc_left, np.uint8), np.ascontiguousarray(desc_right, np.uint8)
+    xr, dep = np.zeros(max(len(kl), 1), np.float32), np.zeros(max(len(kl), 1), np.float32)
+    L = lib()
+    L.orc_stereo_compute.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    sf, inv = np.ascontiguousarray(sf, np.float32), np.ascontiguousarray(inv, np.float32)
+    n = L.orc_stereo_compute(lp, rp, _p(widths), _p(heights), _p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), _p(sf), _p(inv),
+                             focal_x_baseline, true_baseline, _p(xr), _p(dep))
+    return xr[:len(kl)].copy(), dep[:len(kl)].copy(), n
+
+
 # ---- local BA ---------------------------------------------------------------------------------------------------------
 class Camera(C.Structure):
     _fields_ = [("model", C.c_int32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),

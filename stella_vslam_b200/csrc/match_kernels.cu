@@ -686,6 +686,220 @@ __global__ void __launch_bounds__(kPairRows) pairs_candidates_kernel(const Pairs
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// match::stereo  (src/stella_vslam/match/stereo.cc:20-251): row-band candidates, arg-min Hamming < 75, 11x11 L1 patch correlation
+// over +-5 px on the keypoint's pyramid level, parabola sub-pixel, rejection above twice the median correlation.
+// Left keypoints are independent of each other: S1 (thread per left keypoint, right keypoints streamed through shared memory),
+// S2 (warp per left keypoint: patch correlation on the pyramid levels that the two extractors keep on the device),
+// S3 (one CTA: exact median by two-pass radix select, then the rejection).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kStereoMaxLevels = 16;
+constexpr unsigned kStereoThr = (100u + 50u) / 2u;  // stereo.h:99
+struct StereoLevel {
+    const unsigned char *left, *right;
+    unsigned long long pitch_l, pitch_r;
+    int w, h;
+    float sf, inv_sf;
+};
+struct StereoDev {
+    StereoLevel lv[kStereoMaxLevels];
+    int n_levels, n_left, n_right;
+    const b200_keypoint_t *kl, *kr;
+    const uint4 *dl, *dr;
+    float fxb, max_disp;
+    int* best_right;  // [n_left]
+    float *x_right, *depth;
+    int* corr;        // [n_left], -1 = no stereo match
+    int* n_kept;
+};
+
+constexpr int kStereoRows = 64, kStereoChunk = 256;
+
+__global__ void __launch_bounds__(kStereoRows) stereo_match_kernel(const StereoDev* __restrict__ sp) {
+    __shared__ uint4 sd[kStereoChunk * 2];
+    __shared__ float sx[kStereoChunk];
+    __shared__ int slo[kStereoChunk], shi[kStereoChunk], soct[kStereoChunk];
+    const StereoDev& g = *sp;
+    const int i = blockIdx.x * kStereoRows + threadIdx.x;
+    const bool active = i < g.n_left;
+    uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+    int row = -1, level = 0;
+    float min_x = 0.f, max_x = -1.f;
+    if (active) {
+        const b200_keypoint_t k = g.kl[i];
+        q0 = g.dl[(size_t)i * 2];
+        q1 = g.dl[(size_t)i * 2 + 1];
+        level = k.octave;
+        row = (int)k.y;                       // indices_right_in_row.at(y_left): float -> size_t truncation (stereo.cc:41)
+        min_x = __fsub_rn(k.x, g.max_disp);   // stereo.cc:47-48 (min_disp_ = 0)
+        max_x = k.x;
+    }
+    const bool searching = active && !(max_x < 0.f);
+    unsigned best = make_key(kStereoThr, 0);  // only strictly smaller distances win (stereo.cc:172)
+    for (int c0 = 0; c0 < g.n_right; c0 += kStereoChunk) {
+        const int cn = min(kStereoChunk, g.n_right - c0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < cn * 2; t += blockDim.x) sd[t] = g.dr[(size_t)c0 * 2 + t];
+        for (int t = threadIdx.x; t < cn; t += blockDim.x) {
+            const b200_keypoint_t k = g.kr[c0 + t];
+            const float r = __fmul_rn(2.0f, g.lv[min(max(k.octave, 0), g.n_levels - 1)].sf);  // stereo.cc:131-135
+            sx[t] = k.x;
+            shi[t] = __float2int_ru(__fadd_rn(k.y, r));
+            slo[t] = __float2int_rd(__fsub_rn(k.y, r));
+            soct[t] = k.octave;
+        }
+        __syncthreads();
+        if (!searching) continue;
+        for (int j = 0; j < cn; ++j) {
+            if (row < slo[j] || shi[j] < row) continue;
+            if (soct[j] < level - 1 || soct[j] > level + 1) continue;  // stereo.cc:158-160
+            if (sx[j] < min_x || max_x < sx[j]) continue;              // stereo.cc:163-166
+            const unsigned key = make_key(hamming256(q0, q1, sd[2 * j], sd[2 * j + 1]), (unsigned)(c0 + j));
+            if (key_dist(key) < key_dist(best)) best = key;           // first minimum in index order
+        }
+    }
+    if (active) g.best_right[i] = (key_dist(best) < kStereoThr) ? (int)key_idx(best) : -1;
+}
+
+__global__ void __launch_bounds__(128) stereo_subpixel_kernel(const StereoDev* __restrict__ sp) {
+    const StereoDev& g = *sp;
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (i >= g.n_left) return;
+    const int j = g.best_right[i];
+    float out_x = -1.f, out_depth = -1.f;
+    int out_corr = -1;
+    if (j >= 0) {
+        const b200_keypoint_t kl = g.kl[i];
+        const StereoLevel& L = g.lv[min(max(kl.octave, 0), g.n_levels - 1)];
+        const float x_right = g.kr[j].x;
+        const int sxl = __float2int_rn(__fmul_rn(kl.x, L.inv_sf)), syl = __float2int_rn(__fmul_rn(kl.y, L.inv_sf));
+        const int sxr = __float2int_rn(__fmul_rn(x_right, L.inv_sf));
+        constexpr int win = 5, slide = 5;
+        const bool in_range = !(sxr - slide - win < 0 || L.w <= sxr + slide + win);  // stereo.cc:193-197
+        // the reference's rowRange/colRange would assert outside the image; the extractor's 19-px border keeps patches inside
+        const bool patch_ok = sxl - win >= 0 && sxl + win < L.w && syl - win >= 0 && syl + win < L.h;
+        if (in_range && patch_ok) {
+            const unsigned char* pl = L.left + (size_t)syl * L.pitch_l + sxl;
+            const unsigned char* pr = L.right + (size_t)syl * L.pitch_r + sxr;
+            const int lc = pl[0];
+            int lv[4], dyv[4], dxv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int p = min(lane + 32 * u, 120);
+                dyv[u] = p / 11 - win;
+                dxv[u] = p % 11 - win;
+                lv[u] = (int)pl[(long long)dyv[u] * (long long)L.pitch_l + dxv[u]] - lc;
+            }
+            int best_corr = 0x7FFFFFFF, best_offset = 0, c_prev = 0, c1 = 0, c2 = 0, c3 = 0;
+            bool want_next = false;
+            for (int off = -slide; off <= slide; ++off) {
+                const int rc = pr[off];
+                int s = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (lane + 32 * u < 121) s += abs(lv[u] - ((int)pr[(long long)dyv[u] * (long long)L.pitch_r + dxv[u] + off] - rc));
+                s = __reduce_add_sync(0xFFFFFFFFu, s);
+                if (want_next) {
+                    c3 = s;
+                    want_next = false;
+                }
+                if (s < best_corr) {  // strict: the first minimum wins (stereo.cc:221-224)
+                    best_corr = s;
+                    best_offset = off;
+                    c1 = c_prev;
+                    c2 = s;
+                    want_next = true;
+                }
+                c_prev = s;
+            }
+            if (best_offset != -slide && best_offset != slide) {
+                const float f1 = (float)c1, f2 = (float)c2, f3 = (float)c3;
+                const double num = (double)__fsub_rn(f1, f3);
+                const double den = __dsub_rn(__dmul_rn(2.0, (double)__fadd_rn(f1, f3)), __dmul_rn(4.0, (double)f2));
+                const float x_delta = __double2float_rn(__ddiv_rn(num, den));
+                if (!(x_delta < -1.0f || 1.0f < x_delta)) {
+                    float best_x = __fmul_rn(L.sf, __fadd_rn((float)(sxr + best_offset), x_delta));
+                    float disp = __fsub_rn(kl.x, best_x);
+                    if (!(disp < 0.f || g.max_disp <= disp)) {
+                        if (disp <= 0.f) {  // stereo.cc:78-82
+                            disp = 0.01f;
+                            best_x = __fsub_rn(kl.x, disp);
+                        }
+                        out_depth = __fdiv_rn(g.fxb, disp);
+                        out_x = best_x;
+                        out_corr = best_corr;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) {
+        g.x_right[i] = out_x;
+        g.depth[i] = out_depth;
+        g.corr[i] = out_corr;
+    }
+}
+
+// exact median (element size/2 of the ascending order) of the valid correlations, then stereo.cc:96-113
+__global__ void __launch_bounds__(1024) stereo_median_kernel(const StereoDev* __restrict__ sp) {
+    __shared__ int hist[256];
+    __shared__ int sel_hi, sel_rank, n_valid, median, n_rejected;
+    const StereoDev& g = *sp;
+    const int tid = threadIdx.x;
+    if (tid < 256) hist[tid] = 0;
+    if (tid == 0) n_valid = 0, n_rejected = 0;
+    __syncthreads();
+    int local = 0;
+    for (int i = tid; i < g.n_left; i += blockDim.x) {
+        const int c = g.corr[i];
+        if (c >= 0) {
+            atomicAdd(&hist[min(c >> 8, 255)], 1);  // correlations are <= 121 * 510 < 65536
+            ++local;
+        }
+    }
+    atomicAdd(&n_valid, local);
+    __syncthreads();
+    if (n_valid == 0) {
+        if (tid == 0) *g.n_kept = 0;
+        return;
+    }
+    if (tid == 0) {
+        int k = n_valid / 2, b = 0;
+        while (k >= hist[b]) k -= hist[b++];
+        sel_hi = b;
+        sel_rank = k;
+    }
+    __syncthreads();
+    const int hi = sel_hi;
+    __syncthreads();
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < g.n_left; i += blockDim.x) {
+        const int c = g.corr[i];
+        if (c >= 0 && min(c >> 8, 255) == hi) atomicAdd(&hist[c & 255], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int k = sel_rank, b = 0;
+        while (k >= hist[b]) k -= hist[b++];
+        median = (hi << 8) | b;
+    }
+    __syncthreads();
+    const float thr = __double2float_rn(__dmul_rn(2.0, (double)(float)median));
+    int rejected = 0;
+    for (int i = tid; i < g.n_left; i += blockDim.x) {
+        const int c = g.corr[i];
+        if (c >= 0 && thr < (float)c) {
+            g.x_right[i] = -1.f;
+            g.depth[i] = -1.f;
+            ++rejected;
+        }
+    }
+    atomicAdd(&n_rejected, rejected);
+    __syncthreads();
+    if (tid == 0) *g.n_kept = n_valid - n_rejected;
+}
+
 struct Matcher {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -1253,6 +1467,107 @@ int b200_match_pairs(b200_matcher_t h, int n_problems, b200_pairs_problem_t* pro
         if (P.n1 > 0) std::memcpy(P.match_out, hb + lay[p].mout, 4 * (size_t)P.n1);
         P.n_matches = *reinterpret_cast<const int*>(hb + lay[p].nm);
     }
+    return B200_OK;
+}
+
+int b200_stereo_compute(b200_matcher_t h, b200_orb_t left, int frame_left, b200_orb_t right, int frame_right, const b200_keypoint_t* keypts_left,
+                        const uint8_t* descs_left, int n_left, const b200_keypoint_t* keypts_right, const uint8_t* descs_right, int n_right,
+                        float focal_x_baseline, float true_baseline, float* stereo_x_right, float* depths, int32_t* n_matched) {
+    using namespace b200::match;
+    if (!h || !left || !right || n_left < 0 || n_right < 0 || (n_left > 0 && (!keypts_left || !descs_left || !stereo_x_right || !depths))
+        || (n_right > 0 && (!keypts_right || !descs_right)) || !(true_baseline > 0.f)) {
+        b200::set_error("b200_stereo_compute: null argument, negative count or non-positive baseline");
+        return B200_ERR_INVALID;
+    }
+    if (n_matched) *n_matched = 0;
+    if (n_left == 0) return B200_OK;
+    auto& m = h->m;
+    B200_CUDA(cudaSetDevice(m.device));
+    StereoDev g{};
+    int rc;
+    for (int l = 0; l < kStereoMaxLevels; ++l) {
+        int wl = 0, hl = 0, wr = 0, hr = 0;
+        float sf = 0.f;
+        if (b200_orb_level_info(left, l, &wl, &hl, nullptr, &sf) != B200_OK) break;
+        if (b200_orb_level_info(right, l, &wr, &hr, nullptr, nullptr) != B200_OK || wl != wr || hl != hr) {
+            b200::set_error("b200_stereo_compute: the two extractors hold different pyramids at level %d", l);
+            return B200_ERR_INVALID;
+        }
+        StereoLevel& L = g.lv[l];
+        size_t pl = 0, pr = 0;
+        if ((rc = b200_orb_pyramid_level_view(left, frame_left, l, &L.left, &pl, &L.w, &L.h))) return rc;
+        if ((rc = b200_orb_pyramid_level_view(right, frame_right, l, &L.right, &pr, nullptr, nullptr))) return rc;
+        L.pitch_l = pl;
+        L.pitch_r = pr;
+        L.sf = sf;
+        g.n_levels = l + 1;
+    }
+    if (g.n_levels == 0) {
+        b200::set_error("b200_stereo_compute: the extractors hold no pyramid (run extract first)");
+        return B200_ERR_INVALID;
+    }
+    // inv_scale_factors_: the float recurrence of orb_params.cc:37-48, not 1 / sf
+    {
+        const float inv1 = 1.0f / g.lv[g.n_levels > 1 ? 1 : 0].sf;
+        g.lv[0].inv_sf = 1.0f;
+        for (int l = 1; l < g.n_levels; ++l) g.lv[l].inv_sf = inv1 * g.lv[l - 1].inv_sf;
+    }
+    for (int i = 0; i < n_left; ++i)
+        if (keypts_left[i].octave < 0 || keypts_left[i].octave >= g.n_levels) {
+            b200::set_error("b200_stereo_compute: left keypoint %d has octave %d", i, keypts_left[i].octave);
+            return B200_ERR_INVALID;
+        }
+    if ((rc = b200_orb_sync(left)) || (rc = b200_orb_sync(right))) return rc;
+    auto al = [](size_t v) { return b200::round_up(v, (size_t)256); };
+    size_t o = al(sizeof(StereoDev));
+    const size_t o_kl = o; o += al(sizeof(b200_keypoint_t) * (size_t)n_left);
+    const size_t o_kr = o; o += al(sizeof(b200_keypoint_t) * (size_t)std::max(n_right, 1));
+    const size_t o_dl = o; o += al((size_t)32 * n_left);
+    const size_t o_dr = o; o += al((size_t)32 * std::max(n_right, 1));
+    const size_t in_bytes = o, out_begin = o;
+    const size_t o_x = o; o += al(4 * (size_t)n_left);
+    const size_t o_dep = o; o += al(4 * (size_t)n_left);
+    const size_t o_nk = o; o += al(4);
+    const size_t out_end = o;
+    const size_t o_best = o; o += al(4 * (size_t)n_left);
+    const size_t o_corr = o; o += al(4 * (size_t)n_left);
+    if ((rc = m.grow((void**)&m.d_guided, &m.d_guided_cap, o))) return rc;
+    if ((rc = m.grow_pinned(&m.h_guided, &m.h_guided_cap, out_end))) return rc;
+    unsigned char *hb = m.h_guided, *db = m.d_guided;
+    g.n_left = n_left;
+    g.n_right = n_right;
+    g.kl = (const b200_keypoint_t*)(db + o_kl);
+    g.kr = (const b200_keypoint_t*)(db + o_kr);
+    g.dl = (const uint4*)(db + o_dl);
+    g.dr = (const uint4*)(db + o_dr);
+    g.fxb = focal_x_baseline;
+    g.max_disp = focal_x_baseline / true_baseline;  // stereo.cc:18
+    g.best_right = (int*)(db + o_best);
+    g.x_right = (float*)(db + o_x);
+    g.depth = (float*)(db + o_dep);
+    g.corr = (int*)(db + o_corr);
+    g.n_kept = (int*)(db + o_nk);
+    std::memcpy(hb, &g, sizeof(g));
+    std::memcpy(hb + o_kl, keypts_left, sizeof(b200_keypoint_t) * (size_t)n_left);
+    std::memcpy(hb + o_dl, descs_left, (size_t)32 * n_left);
+    if (n_right > 0) {
+        std::memcpy(hb + o_kr, keypts_right, sizeof(b200_keypoint_t) * (size_t)n_right);
+        std::memcpy(hb + o_dr, descs_right, (size_t)32 * n_right);
+    }
+    cudaStream_t st = m.stream;
+    B200_CUDA(cudaMemcpyAsync(db, hb, in_bytes, cudaMemcpyHostToDevice, st));
+    const StereoDev* dg = reinterpret_cast<const StereoDev*>(db);
+    stereo_match_kernel<<<b200::ceil_div(n_left, kStereoRows), kStereoRows, 0, st>>>(dg);
+    stereo_subpixel_kernel<<<b200::ceil_div(n_left, 4), 128, 0, st>>>(dg);
+    stereo_median_kernel<<<1, 1024, 0, st>>>(dg);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpyAsync(hb + out_begin, db + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    m.last_h2d = in_bytes;
+    m.last_d2h = out_end - out_begin;
+    std::memcpy(stereo_x_right, hb + o_x, 4 * (size_t)n_left);
+    std::memcpy(depths, hb + o_dep, 4 * (size_t)n_left);
+    if (n_matched) *n_matched = *reinterpret_cast<const int*>(hb + o_nk);
     return B200_OK;
 }
 

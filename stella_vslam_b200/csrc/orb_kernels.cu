@@ -825,6 +825,8 @@ struct Extractor {
     unsigned char* d_descs = nullptr;
     int* h_counts = nullptr;  // pinned
     int last_batch = 0;
+    const unsigned char* last_img0 = nullptr;  // level 0 of the last extract (see run())
+    size_t last_pitch0 = 0, last_fstride0 = 0;
     bool rect_mask_ready = false;
     TmapSet tmaps{};           // levels >= 1 are encoded once per configuration, level 0 per call (caller's pointer)
     bool tmaps_ok = false, last_used_tma = false;
@@ -1020,6 +1022,10 @@ struct Extractor {
     int run(const void* d_images, size_t pitch, size_t fstride, int batch, const void* d_mask, size_t mask_pitch, int frame0 = 0,
             bool record = true) {
         Images im{(const unsigned char*)d_images, pitch, fstride, d_pyr + (size_t)frame0 * pyr_fstride, pyr_fstride};
+        // level 0 of frame f of this extract: last_img0 + f * last_fstride0 (the caller's buffer, or the upload staging)
+        last_img0 = (const unsigned char*)d_images - (size_t)frame0 * fstride;
+        last_pitch0 = pitch;
+        last_fstride0 = fstride;
         const unsigned char* mask = (const unsigned char*)d_mask;
         unsigned long long mpitch = mask_pitch;
         if (!mask && rect_mask_ready) {  // orb_extractor.cc:50-64: image mask first, else rectangle mask
@@ -1304,6 +1310,25 @@ int b200_orb_pyramid_level_device(b200_orb_t h, int frame, int level, const uint
         return B200_ERR_INVALID;
     }
     *d_ptr = h->ex.d_pyr + (size_t)frame * h->ex.pyr_fstride + h->ex.geom.lv[level].offset;
+    return B200_OK;
+}
+
+int b200_orb_pyramid_level_view(b200_orb_t h, int frame, int level, const uint8_t** d_ptr, size_t* pitch, int* width, int* height) {
+    if (!h || !d_ptr || h->ex.width == 0 || level < 0 || level >= h->ex.geom.num_levels || frame < 0 || frame >= h->ex.last_batch) {
+        b200::set_error("b200_orb_pyramid_level_view: bad frame/level");
+        return B200_ERR_INVALID;
+    }
+    const auto& L = h->ex.geom.lv[level];
+    if (level == 0) {
+        if (!h->ex.last_img0) return B200_ERR_INVALID;
+        *d_ptr = h->ex.last_img0 + (size_t)frame * h->ex.last_fstride0;
+        if (pitch) *pitch = h->ex.last_pitch0;
+    } else {
+        *d_ptr = h->ex.d_pyr + (size_t)frame * h->ex.pyr_fstride + L.offset;
+        if (pitch) *pitch = (size_t)L.pitch;
+    }
+    if (width) *width = L.w;
+    if (height) *height = L.h;
     return B200_OK;
 }
 

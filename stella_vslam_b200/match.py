@@ -4,7 +4,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import GuidedProblem, PairsProblem, check, lib, pack_guided_problem, pack_pairs_problem, ptr
+from ._lib import KP_DTYPE, GuidedProblem, PairsProblem, check, lib, pack_guided_problem, pack_pairs_problem, ptr
 
 HAMMING_DIST_THR_LOW = 50    # match/base.h:15
 HAMMING_DIST_THR_HIGH = 100  # match/base.h:16
@@ -300,3 +300,34 @@ class bow_tree(base):
         pr = dict(desc1=keyfrm_1["desc"], angle1=keyfrm_1["angle"], valid1=keyfrm_1["has_landmark"], node1=keyfrm_1["node"],
                   desc2=keyfrm_2["desc"], angle2=keyfrm_2["angle"], valid2=keyfrm_2["has_landmark"], node2=keyfrm_2["node"])
         return match_pairs_batch([pr], PAIRS_BOW, self.lowe_ratio_, self.check_orientation_, 0, self.device)[0]
+
+
+class stereo:
+    """match::stereo (match/stereo.h:17-101, stereo.cc).  Constructed like the reference's (system.cc:443) from the two extractors
+    whose last extract() produced the rectified pair -- their image pyramids stay on the device -- plus the keypoints and
+    descriptors of both eyes.  frame_left / frame_right select a frame when both eyes went through one batched extract."""
+
+    hamm_dist_thr_ = (HAMMING_DIST_THR_HIGH + HAMMING_DIST_THR_LOW) // 2  # stereo.h:99
+
+    def __init__(self, extractor_left, extractor_right, keypts_left, keypts_right, descs_left, descs_right, focal_x_baseline, true_baseline,
+                 frame_left=0, frame_right=0, device=0):
+        self.extractor_left, self.extractor_right = extractor_left, extractor_right
+        self.frame_left, self.frame_right = frame_left, frame_right
+        self.keypts_left_ = np.ascontiguousarray(keypts_left, KP_DTYPE)
+        self.keypts_right_ = np.ascontiguousarray(keypts_right, KP_DTYPE)
+        self.descs_left_ = np.ascontiguousarray(descs_left, np.uint8).reshape(-1, 32)
+        self.descs_right_ = np.ascontiguousarray(descs_right, np.uint8).reshape(-1, 32)
+        self.focal_x_baseline_, self.true_baseline_ = float(focal_x_baseline), float(true_baseline)
+        self.device = device
+
+    def compute(self):
+        """stereo::compute (stereo.cc:20-114).  Returns (stereo_x_right, depths), -1 where no stereo match survives."""
+        n = len(self.keypts_left_)
+        x_right, depths = np.full(max(n, 1), -1, np.float32), np.full(max(n, 1), -1, np.float32)
+        kept = C.c_int32(0)
+        check(lib().b200_stereo_compute(_matcher(self.device), self.extractor_left._h, self.frame_left, self.extractor_right._h, self.frame_right,
+                                        ptr(self.keypts_left_), ptr(self.descs_left_), n, ptr(self.keypts_right_), ptr(self.descs_right_),
+                                        len(self.keypts_right_), self.focal_x_baseline_, self.true_baseline_, ptr(x_right), ptr(depths),
+                                        C.byref(kept)))
+        self.num_matched_ = kept.value
+        return x_right[:n], depths[:n]

@@ -353,3 +353,15 @@ def make_keyframe_pair(seed, n1=2000, n2=2000, stereo=False, n_nodes=150, num_le
 
     geometry = dict(E_12=E_12, epiplane_in_keyfrm_2=c1_in_2 / np.linalg.norm(c1_in_2), valid_epiplane=True, perm1=perm1, perm2=perm2)
     return kf(desc1, angle1, octave1, bearings1, node1, has_lm1, n1), kf(desc2, angle2, octave2, bearings2, node2, has_lm2, n2), geometry
+
+
+def make_stereo_pair(w=752, h=480, seed=77, disparities=(9, 23, 41), noise_sigma=2.0):
+    """(left, right) rectified frames: the right view shows the same pattern moved left by a disparity that differs per
+    horizontal band, with independent sensor noise, so match::stereo finds sub-pixel disparities around those values."""
+    pattern = _make_pattern(w, h, seed)
+    left = _render(pattern, w, h, seed, (0, 0), noise_sigma)
+    right = np.empty_like(left)
+    bands = np.linspace(0, h, len(disparities) + 1).astype(int)
+    for k, d in enumerate(disparities):
+        right[bands[k]:bands[k + 1]] = _render(pattern, w, h, seed + 1, (int(d), 0), noise_sigma)[bands[k]:bands[k + 1]]
+    return left, right
