@@ -44,6 +44,13 @@ b200_orb_t handle_of(const orb_extractor* self, const orb_params* prm, unsigned 
 }
 }  // namespace
 
+// the device handle behind an extractor that has extracted at least once (used by stereo_b200.cc); nullptr otherwise
+b200_orb_t b200_handle_of(const orb_extractor* self) {
+    std::lock_guard<std::mutex> lock(g_mtx);
+    auto it = g_handles.find(self);
+    return it == g_handles.end() ? nullptr : it->second;
+}
+
 orb_extractor::orb_extractor(const orb_params* orb_params, const unsigned int min_area, const descriptor_type desc_type,
                              const std::vector<std::vector<float>>& mask_rects)
     : orb_params_(orb_params), mask_rects_(mask_rects), min_area_sqrt_(std::sqrt(min_area)), desc_type_(desc_type) {
