@@ -18,6 +18,9 @@
 #include <cmath>
 #include <cstdlib>
 #include <new>
+#include <chrono>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -179,16 +182,41 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {  // determin
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Levenberg-Marquardt control block.  The whole two-round optimisation runs as ONE CUDA graph whose loops are WHILE conditional
+// nodes: the numeric kernels read lambda and the index of the current state from this block, three single-CTA control kernels
+// restate g2o's OptimizationAlgorithmLevenberg::solve / SparseOptimizer::optimize / terminate_action bookkeeping and set the
+// loop conditions.  By default the host steps the same kernels (one round trip per loop decision); B200_LBA_GRAPH=1 selects the
+// graph driver (see b200_lba_create for why it is opt-in).
+// ---------------------------------------------------------------------------------------------------------------
+struct Dual {
+    double* p[2];  // [current / trial] double buffers; LmCtl::cur says which one is current
+};
+struct LmCtl {
+    double lambda, ni, current_chi, last_chi, rho;
+    double lambda_init, chi2[2], lambda_final[2];
+    int cur, it, iterations, qmax, ok, stop_flag, round, skip_round2;
+    int inner_go, outer_go;
+    int iters_done[2];
+    int launches;
+    const volatile int* abort_word;  // mapped host word mirroring the caller's force_stop flag
+};
+__device__ __forceinline__ bool lm_aborted(const LmCtl* c) { return c->stop_flag || (c->abort_word && *c->abort_word); }
+
+// ---------------------------------------------------------------------------------------------------------------
 // K1: per edge -- residual, chi2, Huber weight, Hpl block and the landmark-side contribution
 //     out: chi[e] (plain chi2, only for active edges), Hpl[18][E], pl[9][E] (6 unique Hll + 3 bl), chi partials
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kEdgeThreads = 128;
 
-__global__ void __launch_bounds__(kEdgeThreads) edges_kernel(View v, const double* __restrict__ Rt, const double* __restrict__ pts,
-                                                             double* __restrict__ chi, double* __restrict__ Hpl, double* __restrict__ pl,
-                                                             double* __restrict__ chi_partials, int linearize,
-                                                             const double* __restrict__ chi_carry, int* __restrict__ fail_reset) {
+__global__ void __launch_bounds__(kEdgeThreads) edges_kernel(View v, Dual Rt2, Dual pts2, Dual chi2, double* __restrict__ Hpl,
+                                                             double* __restrict__ pl, double* __restrict__ chi_partials, int linearize,
+                                                             int on_trial, int* __restrict__ fail_reset, const LmCtl* __restrict__ ctl) {
     __shared__ double sh[kEdgeThreads];
+    const int sidx = (ctl->cur ^ on_trial) & 1;  // on_trial: evaluate the trial state, carrying inactive chi2 over from the current one
+    const double* __restrict__ Rt = Rt2.p[sidx];
+    const double* __restrict__ pts = pts2.p[sidx];
+    double* __restrict__ chi = chi2.p[sidx];
+    const double* __restrict__ chi_carry = on_trial ? chi2.p[sidx ^ 1] : nullptr;
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (fail_reset && e == 0) *fail_reset = 0;  // last kernel of a trial: re-arm the solver's failure flag
     double cost = 0.0;
@@ -280,8 +308,10 @@ __global__ void __launch_bounds__(128) points_kernel(View v, const double* __res
 // K3: keyframe-side blocks.  The edges of every free keyframe are cut into chunks of kPoseChunk; one warp reduces one
 //     chunk to 21 unique Hpp entries + 6 bp entries, pose_finish_kernel adds the chunk partials in index order.
 constexpr int kPoseChunk = 64;
-__global__ void __launch_bounds__(128) pose_chunks_kernel(View v, const int2* __restrict__ chunks, int n_chunks, const double* __restrict__ Rt,
-                                                          const double* __restrict__ pts, double* __restrict__ partials) {
+__global__ void __launch_bounds__(128) pose_chunks_kernel(View v, const int2* __restrict__ chunks, int n_chunks, Dual Rt2, Dual pts2,
+                                                          double* __restrict__ partials, const LmCtl* __restrict__ ctl) {
+    const double* __restrict__ Rt = Rt2.p[ctl->cur & 1];
+    const double* __restrict__ pts = pts2.p[ctl->cur & 1];
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (wid >= n_chunks) return;
     const int2 ch = chunks[wid];
@@ -339,10 +369,11 @@ __global__ void __launch_bounds__(128) pose_finish_kernel(int Kf, const int* __r
 }
 
 // K4: per landmark -- Dinv = (Hll + lambda I)^-1 (symmetric 3x3, cofactor inverse like Eigen's fixed-size path)
-__global__ void __launch_bounds__(128) dinv_kernel(int Lf, double lambda, const double* __restrict__ Hll, double* __restrict__ Dinv,
-                                                   int* __restrict__ fail) {
+__global__ void __launch_bounds__(128) dinv_kernel(int Lf, const LmCtl* __restrict__ ctl, const double* __restrict__ Hll,
+                                                   double* __restrict__ Dinv, int* __restrict__ fail) {
     const int lc = blockIdx.x * blockDim.x + threadIdx.x;
     if (lc >= Lf) return;
+    const double lambda = ctl->lambda;
     const double A0 = Hll[lc] + lambda, A1 = Hll[(size_t)Lf + lc], A2 = Hll[(size_t)2 * Lf + lc];
     const double A4 = Hll[(size_t)3 * Lf + lc] + lambda, A5 = Hll[(size_t)4 * Lf + lc], A8 = Hll[(size_t)5 * Lf + lc] + lambda;
     const double c0 = A4 * A8 - A5 * A5, c1 = A5 * A2 - A1 * A8, c2 = A1 * A5 - A4 * A2;
@@ -424,7 +455,7 @@ __global__ void __launch_bounds__(128) schur_chunks_kernel(View v, const SchurCh
         for (int i = 0; i < 42; ++i) partials[(size_t)wid * 42 + i] = acc[i];
 }
 
-__global__ void __launch_bounds__(128) schur_finish_kernel(double lambda, const SchurBlock* __restrict__ blocks, int n_blocks,
+__global__ void __launch_bounds__(128) schur_finish_kernel(const LmCtl* __restrict__ ctl, const SchurBlock* __restrict__ blocks, int n_blocks,
                                                            const double* __restrict__ partials, const double* __restrict__ Hpp,
                                                            const double* __restrict__ bp, double* __restrict__ M, int n, int ld) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -437,7 +468,7 @@ __global__ void __launch_bounds__(128) schur_finish_kernel(double lambda, const 
     if (el < 36) {
         const int r = el / 6, c = el - r * 6;
         double val = -sacc;
-        if (sb.i == sb.j) val += Hpp[(size_t)sb.i * 36 + el] + (r == c ? lambda : 0.0);
+        if (sb.i == sb.j) val += Hpp[(size_t)sb.i * 36 + el] + (r == c ? ctl->lambda : 0.0);
         M[(size_t)(6 * sb.j + c) * ld + 6 * sb.i + r] = val;  // lower triangle (j >= i)
         if (sb.i == sb.j) M[(size_t)(6 * sb.i + r) * ld + 6 * sb.j + c] = val;
     } else {
@@ -518,13 +549,18 @@ __device__ __forceinline__ void cluster_sync_all() {
 // The kernel runs as ONE thread-block cluster: every CTA repeats the cheap steps (1) and (2) on its own SM (so no panel
 // exchange is needed), the tiles of step (3) -- 60 % of the flops -- are dealt round-robin to the CTAs of the cluster, and a
 // cluster barrier (release/acquire) separates the panels.  CTA 0 writes the factor back and does the backward solve.
-__global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld, double* __restrict__ M, double lambda,
+__global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld, double* __restrict__ M, const LmCtl* __restrict__ ctl,
                                                                   const double* __restrict__ bp, double* __restrict__ xp, int K,
-                                                                  const int* __restrict__ pose_col, const double* __restrict__ q_cur,
-                                                                  const double* __restrict__ t_cur, double* __restrict__ q_new,
-                                                                  double* __restrict__ t_new, double* __restrict__ Rt_new,
+                                                                  const int* __restrict__ pose_col, Dual q2, Dual t2, Dual Rt2,
                                                                   double* __restrict__ result, int* __restrict__ fail) {
     extern __shared__ __align__(32) double dyn[];
+    const double lambda = ctl->lambda;
+    const int cur_idx = ctl->cur & 1;
+    const double* __restrict__ q_cur = q2.p[cur_idx];
+    const double* __restrict__ t_cur = t2.p[cur_idx];
+    double* __restrict__ q_new = q2.p[cur_idx ^ 1];
+    double* __restrict__ t_new = t2.p[cur_idx ^ 1];
+    double* __restrict__ Rt_new = Rt2.p[cur_idx ^ 1];
     double* D = dyn;                     // kNB x (kNB+1) diagonal block (lower, padded with the identity)
     double* Pn = dyn + kNB * (kNB + 1);  // kNB x mp panel, transposed (k-major); the 600 doubles in front keep it 32-byte aligned
     const int mp = (n + 1 + 3) & ~3;
@@ -718,11 +754,14 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld,
 
 // K7: back-substitution x_l = Dinv (bl - sum_e Hpl(e)^T x_p), trial landmark, scale partials.  Eight lanes share a landmark
 //     (they split its edges), sixteen landmarks per 128-thread CTA.
-__global__ void __launch_bounds__(128) backsub_kernel(View v, double lambda, const double* __restrict__ Dinv, const double* __restrict__ bl,
-                                                      const double* __restrict__ Hpl, const double* __restrict__ xp,
-                                                      const double* __restrict__ pts_cur, double* __restrict__ pts_new,
-                                                      double* __restrict__ scale_partials, const int* __restrict__ fail) {
+__global__ void __launch_bounds__(128) backsub_kernel(View v, const LmCtl* __restrict__ ctl, const double* __restrict__ Dinv,
+                                                      const double* __restrict__ bl, const double* __restrict__ Hpl,
+                                                      const double* __restrict__ xp, Dual pts2, double* __restrict__ scale_partials,
+                                                      const int* __restrict__ fail) {
     __shared__ double sh[128];
+    const double lambda = ctl->lambda;
+    const double* __restrict__ pts_cur = pts2.p[ctl->cur & 1];
+    double* __restrict__ pts_new = pts2.p[(ctl->cur & 1) ^ 1];
     const int sub = threadIdx.x & 7;
     const int l = blockIdx.x * 16 + (threadIdx.x >> 3);
     double sc = 0.0;
@@ -772,10 +811,14 @@ __global__ void __launch_bounds__(128) backsub_kernel(View v, double lambda, con
 
 // K8: outlier test (local_bundle_adjuster_g2o.cc:323-344, 357-375): chi2 of the last activation vs the chi-square
 //     threshold, or non-positive depth at the current estimate.  mode 0: mark level + drop the kernel; mode 1: report.
-__global__ void __launch_bounds__(128) outlier_kernel(View v, const double* __restrict__ Rt, const double* __restrict__ pts,
-                                                      const double* __restrict__ chi, int mode, unsigned char* __restrict__ out) {
+__global__ void __launch_bounds__(128) outlier_kernel(View v, Dual Rt2, Dual pts2, Dual chi2, int mode, unsigned char* __restrict__ out,
+                                                      const LmCtl* __restrict__ ctl) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= v.E) return;
+    if (mode == 0 && ctl->skip_round2) return;  // local_bundle_adjuster_g2o.cc:317-321: no second round after an abort
+    const double* __restrict__ Rt = Rt2.p[ctl->cur & 1];
+    const double* __restrict__ pts = pts2.p[ctl->cur & 1];
+    const double* __restrict__ chi = chi2.p[ctl->cur & 1];
     const EdgeS ed = v.edges[e];
     unsigned char o = 0;
     if (ed.can_outlier) {
@@ -799,6 +842,151 @@ __global__ void __launch_bounds__(128) outlier_kernel(View v, const double* __re
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// LM control kernels (one CTA each).  Sums of the per-CTA partials are taken by thread 0 in index order (staged through
+// shared memory), exactly like a host loop over the read-back array would.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kCtlThreads = 256;
+__device__ double ordered_sum(const double* __restrict__ p, int n, double* stage) {
+    double s = 0.0;
+    for (int base = 0; base < n; base += 1024) {
+        const int m = min(1024, n - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += blockDim.x) stage[i] = p[base + i];
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int i = 0; i < m; ++i) s += stage[i];
+    }
+    return s;  // valid in thread 0
+}
+__device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int use_graph, unsigned v) {
+    if (use_graph) cudaGraphSetConditional(h, v);
+}
+
+// start of SparseOptimizer::optimize(iterations): terminate_action at iteration -1 resets the stop flag (terminate_action.cc:46-51)
+__global__ void lm_round_begin_kernel(LmCtl* __restrict__ c, int iterations, int round, cudaGraphConditionalHandle h_outer, int use_graph) {
+    if (threadIdx.x) return;
+    c->round = round;
+    c->iterations = iterations;
+    c->iters_done[round] = 0;
+    c->launches += 1;
+    if (round == 1 && lm_aborted(c)) {  // local_bundle_adjuster_g2o.cc:317-321
+        c->skip_round2 = 1;
+        c->outer_go = 0;
+        set_cond(h_outer, use_graph, 0u);
+        return;
+    }
+    c->stop_flag = 0;
+    c->it = 0;
+    c->ok = 1;
+    c->outer_go = (iterations > 0 && !lm_aborted(c)) ? 1 : 0;
+    set_cond(h_outer, use_graph, (unsigned)c->outer_go);
+}
+
+// after computeActiveErrors + buildSystem: at the first iteration of a round take the robust chi2 and computeLambdaInit
+// (tau * max |H_jj| over all free vertices, tau = 1e-5); arm the trial loop
+__global__ void __launch_bounds__(kCtlThreads) lm_after_build_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb,
+                                                                     const double* __restrict__ r_diag, int lb, const double* __restrict__ Hpp,
+                                                                     int Kf, int n_build_launches, cudaGraphConditionalHandle h_inner,
+                                                                     int use_graph) {
+    __shared__ double stage[1024];
+    const bool first = c->it == 0;
+    double chi = 0.0;
+    if (first) chi = ordered_sum(r_chi, eb, stage);
+    if (threadIdx.x) return;
+    if (first) {
+        c->current_chi = chi;
+        double mx = 0.0;
+        for (int i = 0; i < lb; ++i) mx = fmax(mx, r_diag[i]);
+        for (int p = 0; p < Kf; ++p)
+            for (int a = 0; a < 6; ++a) mx = fmax(mx, fabs(Hpp[36 * (size_t)p + a * 7]));
+        c->lambda = 1e-5 * mx;
+        c->ni = 2.0;
+        if (c->round == 0) c->lambda_init = c->lambda;
+    }
+    c->qmax = 0;
+    c->rho = 0.0;
+    c->inner_go = 1;
+    c->launches += n_build_launches + 1;
+    set_cond(h_inner, use_graph, 1u);
+}
+
+// after one trial (solve, back-substitution, chi2 at the trial state): the accept / reject rule of
+// OptimizationAlgorithmLevenberg::solve, and when the trial loop ends the end-of-iteration bookkeeping of
+// SparseOptimizer::optimize + terminate_action (terminate_action.cc:52-73)
+__global__ void __launch_bounds__(kCtlThreads) lm_after_trial_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb,
+                                                                     const double* __restrict__ r_scale, int lb2,
+                                                                     const double* __restrict__ r_result, int n_trial_launches,
+                                                                     cudaGraphConditionalHandle h_inner, cudaGraphConditionalHandle h_outer,
+                                                                     int use_graph) {
+    __shared__ double stage[1024];
+    const bool ok2 = r_result[0] != 0.0;
+    const double chi_sum = ordered_sum(r_chi, eb, stage);
+    const double scale_sum = ordered_sum(r_scale, lb2, stage);
+    if (threadIdx.x) return;
+    c->launches += n_trial_launches + 1;
+    const double temp_chi = ok2 ? chi_sum : 1.7976931348623157e308;
+    double rho = c->current_chi - temp_chi;
+    double scale = ok2 ? r_result[1] + scale_sum : 0.0;  // computeScale
+    scale += 1e-3;
+    rho /= scale;
+    bool broke = false;
+    if (rho > 0 && isfinite(temp_chi) && ok2) {
+        double alpha = 1. - pow(2 * rho - 1, 3.0);
+        alpha = fmin(alpha, 2. / 3.);
+        c->lambda *= fmax(1. / 3., alpha);
+        c->ni = 2.0;
+        c->current_chi = temp_chi;
+        c->cur ^= 1;  // discardTop: keep the trial state
+    } else {
+        c->lambda *= c->ni;
+        c->ni *= 2.0;  // pop: the current state is untouched
+        if (!isfinite(c->lambda)) broke = true;
+    }
+    if (!broke) c->qmax++;
+    c->rho = rho;
+    const bool again = !broke && rho < 0 && c->qmax < 10 && !lm_aborted(c);
+    c->inner_go = again ? 1 : 0;
+    set_cond(h_inner, use_graph, again ? 1u : 0u);
+    if (again) return;
+    if (c->qmax == 10 || rho == 0 || !isfinite(c->lambda)) c->ok = 0;  // SolverResult::Terminate
+    const double chi_now = c->current_chi;
+    if (c->it == 0) {
+        c->last_chi = chi_now;
+    } else {
+        const double gain = (c->last_chi - chi_now) / chi_now;
+        c->last_chi = chi_now;
+        if (gain >= 0 && gain < 1e-3) c->stop_flag = 1;
+    }
+    c->chi2[c->round] = chi_now;
+    c->lambda_final[c->round] = c->lambda;
+    c->it++;
+    c->iters_done[c->round] = c->it;
+    const bool more = c->it < c->iterations && !lm_aborted(c) && c->ok;
+    c->outer_go = more ? 1 : 0;
+    set_cond(h_outer, use_graph, more ? 1u : 0u);
+}
+
+// end of a round: a round that ran no iteration still reports the chi2 of its (re-evaluated) state
+__global__ void __launch_bounds__(kCtlThreads) lm_round_end_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb, int round) {
+    __shared__ double stage[1024];
+    if (round == 1 && c->skip_round2) return;
+    const double chi = ordered_sum(r_chi, eb, stage);
+    if (threadIdx.x) return;
+    c->launches += 2;
+    if (c->iters_done[round] == 0) c->chi2[round] = chi;
+}
+
+// copy the final (current) keyframe and landmark states to fixed read-back buffers
+__global__ void __launch_bounds__(256) lm_export_kernel(const LmCtl* __restrict__ c, Dual q2, Dual t2, Dual pts2, int K, int L, double* __restrict__ qf,
+                                                        double* __restrict__ tf, double* __restrict__ pf) {
+    const int cur = c->cur & 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4 * K) qf[i] = q2.p[cur][i];
+    if (i < 3 * K) tf[i] = t2.p[cur][i];
+    if (i < 3 * L) pf[i] = pts2.p[cur][i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host
 // ---------------------------------------------------------------------------------------------------------------
 struct Solver {
@@ -814,6 +1002,10 @@ struct Solver {
     float last_ms = 0.f;
     int last_launches = 0;
     cudaEvent_t ev_sync = nullptr;
+    LmCtl* h_ctl = nullptr;       // pinned mirror of the device control block
+    int* h_abort = nullptr;       // pinned, device-visible mirror of the caller's force_stop flag
+    int* d_abort = nullptr;
+    bool host_loop = true;        // false (B200_LBA_GRAPH=1): run the LM loop as one conditional CUDA graph
     // (a blocking-sync event wait instead of this spin-wait measured slightly slower with 16 windows in flight on a 16-core host)
     cudaError_t wait(cudaStream_t st) { return cudaStreamSynchronize(st); }
 
@@ -842,6 +1034,8 @@ struct Solver {
         return B200_OK;
     }
 };
+
+static std::mutex g_graph_build_mutex;
 
 struct Carver {
     size_t off = 0;
@@ -995,6 +1189,7 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     // readback block: [chi partials eb][diag partials lb][scale partials lb2][result 2]
     const size_t res_n = (size_t)eb + (size_t)lb + (size_t)lb2 + 6;
     const size_t o_res = dv.take<double>(res_n), o_fail = dv.take<int>(1), o_out = dv.take<unsigned char>(E);
+    const size_t o_ctl = dv.take<LmCtl>(1), o_qf = dv.take<double>(4 * (size_t)K), o_tf = dv.take<double>(3 * (size_t)K), o_pf = dv.take<double>(3 * (size_t)L);
     int rc = S.ensure(dv.off + 256, upload_bytes, res_n + 36 * (size_t)std::max(Kf, 1));
     if (rc) return rc;
     unsigned char* hs = S.h_stage;
@@ -1042,159 +1237,198 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     double* r_diag = res + eb;           // lb
     double* r_scale = res + eb + lb;     // lb
     double* r_result = res + eb + lb + lb2;  // 2
-    double* h = S.h_res;
-    int cur = 0;
+    Dual dq{{qs[0], qs[1]}}, dt{{ts[0], ts[1]}}, dRt{{Rts[0], Rts[1]}}, dpts{{ptss[0], ptss[1]}}, dchi{{chis[0], chis[1]}};
+    LmCtl* ctl = (LmCtl*)(d + o_ctl);
+    LmCtl* hc = S.h_ctl;
+    std::memset(hc, 0, sizeof(LmCtl));
+    hc->ok = 1;
+    *S.h_abort = 0;
+    hc->abort_word = force_stop ? S.d_abort : nullptr;
+    B200_CUDA(cudaMemcpyAsync(ctl, hc, sizeof(LmCtl), cudaMemcpyHostToDevice, st));
+    const bool use_graph = !S.host_loop;
+    const int ug = use_graph ? 1 : 0;
 
-    auto sum = [](const double* p, int cnt) { double s = 0; for (int i = 0; i < cnt; ++i) s += p[i]; return s; };
-
-    // one round of SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg + terminate_action
-    auto optimize = [&](int iterations, int round) -> int {
-        uint8_t aux = 0;
-        volatile uint8_t* flag = force_stop ? force_stop : &aux;
-        *flag = 0;  // terminate_action at iteration -1 resets the stop flag (terminate_action.cc:46-51)
-        double lambda = 0, ni = 2, last_chi = 0, chi_now = 0, current_chi = 0;
-        int it = 0;
-        bool ok = true;
-        for (; it < iterations && !*flag && ok; ++it) {
-            // computeActiveErrors + buildSystem at the current state
-            if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], Hpl, pl, r_chi, 1, nullptr, nullptr);
-            points_kernel<<<lb, 128, 0, st>>>(v, pl, Hll, bl, r_diag);
-            if (n_pose_chunks) {
-                pose_chunks_kernel<<<ceil_div(n_pose_chunks, 4), 128, 0, st>>>(v, (const int2*)(d + o_pchunks), n_pose_chunks, Rts[cur], ptss[cur], ppart);
-                pose_finish_kernel<<<ceil_div(Kf * 27, 128), 128, 0, st>>>(Kf, (const int*)(d + o_pcstart), ppart, Hpp, bp);
-            } else if (Kf) {
-                B200_CUDA(cudaMemsetAsync(Hpp, 0, sizeof(double) * 36 * Kf, st));
-                B200_CUDA(cudaMemsetAsync(bp, 0, sizeof(double) * 6 * Kf, st));
-            }
-            launches += 4;
-            // The robust chi2 at the current state is needed on the host only at the first iteration of a round (afterwards it is the
-            // chi2 of the last accepted trial, computed by the same kernel in the same order), so later iterations enqueue the
-            // first trial right behind the build without a round trip.
-            if (it == 0) {
-                B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * (eb + lb), cudaMemcpyDeviceToHost, st));
-                if (Kf) B200_CUDA(cudaMemcpyAsync(h + res_n, Hpp, sizeof(double) * 36 * Kf, cudaMemcpyDeviceToHost, st));
-                B200_CUDA(S.wait(st));
-                current_chi = sum(h, eb);
-            }
-            if (it == 0) {  // computeLambdaInit: tau * max |H_jj| over all free vertices, tau = 1e-5
-                double mx = 0;
-                for (int i = 0; i < lb; ++i) mx = std::max(mx, h[eb + i]);
-                for (int p = 0; p < Kf; ++p)
-                    for (int a = 0; a < 6; ++a) mx = std::max(mx, std::fabs(h[res_n + 36 * (size_t)p + a * 7]));
-                lambda = 1e-5 * mx;
-                ni = 2;
-                if (round == 0 && stats) stats->lambda_init = lambda;
-            }
-            double rho = 0;
-            int qmax = 0;
-            do {
-                const int nxt = cur ^ 1;
-                if (Lf) dinv_kernel<<<ceil_div(Lf, 128), 128, 0, st>>>(Lf, lambda, Hll, Dinv, fail);
-                if (n_chunks)
-                    schur_chunks_kernel<<<ceil_div(n_chunks, 4), 128, 0, st>>>(v, (const SchurChunk*)(d + o_chunks), n_chunks, (const int2*)(d + o_pairs),
-                                                                              Hpl, Dinv, bl, part);
-                if (n_blocks)
-                    schur_finish_kernel<<<ceil_div(n_blocks * 42, 128), 128, 0, st>>>(lambda, (const SchurBlock*)(d + o_blocks), n_blocks, part, Hpp, bp, Hs,
-                                                                                     n, ld);
-                {
-                    cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = dim3(kCholCluster);
-                    cfg.blockDim = dim3(kCholThreads);
-                    cfg.dynamicSmemBytes = chol_smem;
-                    cfg.stream = st;
-                    cudaLaunchAttribute attr[1];
-                    attr[0].id = cudaLaunchAttributeClusterDimension;
-                    attr[0].val.clusterDim.x = kCholCluster;
-                    attr[0].val.clusterDim.y = 1;
-                    attr[0].val.clusterDim.z = 1;
-                    cfg.attrs = attr;
-                    cfg.numAttrs = 1;
-                    B200_CUDA(cudaLaunchKernelEx(&cfg, chol_solve_kernel, n, ld, Hs, lambda, (const double*)bp, xp, K, (const int*)(d + o_posecol),
-                                                 (const double*)qs[cur], (const double*)ts[cur], qs[nxt], ts[nxt], Rts[nxt], r_result, fail));
-                }
-                backsub_kernel<<<lb2, 128, 0, st>>>(v, lambda, Dinv, bl, Hpl, xp, ptss[cur], ptss[nxt], r_scale, fail);
-                if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[nxt], ptss[nxt], chis[nxt], Hpl, pl, r_chi, 0, chis[cur], fail);
-                else B200_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), st));
-                launches += 6;
-                B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * res_n, cudaMemcpyDeviceToHost, st));
-                B200_CUDA(S.wait(st));
-                const bool ok2 = h[eb + lb + lb2] != 0.0;
-                if (getenv("B200_LBA_DEBUG"))
-                    fprintf(stderr, "[lba] chol cycles: diag %.0f panel %.0f trailing %.0f backward %.0f\n", h[eb + lb + lb2 + 2], h[eb + lb + lb2 + 3],
-                            h[eb + lb + lb2 + 4], h[eb + lb + lb2 + 5]);
-                double temp_chi = ok2 ? sum(h, eb) : 1.7976931348623157e308;
-                rho = current_chi - temp_chi;
-                double scale = ok2 ? h[eb + lb + lb2 + 1] + sum(h + eb + lb, lb2) : 0.0;  // computeScale
-                scale += 1e-3;
-                rho /= scale;
-                if (rho > 0 && std::isfinite(temp_chi) && ok2) {
-                    double alpha = 1. - std::pow((2 * rho - 1), 3);
-                    alpha = std::min(alpha, 2. / 3.);
-                    lambda *= std::max(1. / 3., alpha);
-                    ni = 2;
-                    current_chi = temp_chi;
-                    cur = nxt;  // discardTop: keep the trial state
-                } else {
-                    lambda *= ni;
-                    ni *= 2;  // pop: the current state is untouched
-                    if (!std::isfinite(lambda)) break;
-                }
-                qmax++;
-            } while (rho < 0 && qmax < 10 && !*flag);
-            if (qmax == 10 || rho == 0 || !std::isfinite(lambda)) ok = false;  // SolverResult::Terminate
-            // postIteration: terminate_action (terminate_action.cc:52-73)
-            chi_now = current_chi;
-            if (it == 0) {
-                last_chi = chi_now;
-            } else {
-                const double gain = (last_chi - chi_now) / chi_now;
-                last_chi = chi_now;
-                if (gain >= 0 && gain < 1e-3) *flag = 1;
-            }
-            if (stats) {
-                stats->chi2[round] = chi_now;
-                stats->lambda_final[round] = lambda;
-            }
+    // the kernels of one buildSystem and of one LM trial (identical in graph and host-stepped mode)
+    auto launch_build = [&]() -> int {
+        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 1, 0, nullptr, ctl);
+        points_kernel<<<lb, 128, 0, st>>>(v, pl, Hll, bl, r_diag);
+        if (n_pose_chunks) {
+            pose_chunks_kernel<<<ceil_div(n_pose_chunks, 4), 128, 0, st>>>(v, (const int2*)(d + o_pchunks), n_pose_chunks, dRt, dpts, ppart, ctl);
+            pose_finish_kernel<<<ceil_div(Kf * 27, 128), 128, 0, st>>>(Kf, (const int*)(d + o_pcstart), ppart, Hpp, bp);
+        } else if (Kf) {
+            B200_CUDA(cudaMemsetAsync(Hpp, 0, sizeof(double) * 36 * Kf, st));
+            B200_CUDA(cudaMemsetAsync(bp, 0, sizeof(double) * 6 * Kf, st));
         }
-        // chi2 of every active edge at the final state (the terminate action's computeActiveErrors)
-        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], Hpl, pl, r_chi, 0, nullptr, nullptr);
-        launches += 1;
-        if (it == 0 && stats) {
-            B200_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * eb, cudaMemcpyDeviceToHost, st));
-            B200_CUDA(S.wait(st));
-            stats->chi2[round] = sum(h, eb);
-        }
-        B200_CUDA(cudaGetLastError());
-        return it;
+        return B200_OK;
     };
+    auto launch_trial = [&]() -> int {
+        if (Lf) dinv_kernel<<<ceil_div(Lf, 128), 128, 0, st>>>(Lf, ctl, Hll, Dinv, fail);
+        if (n_chunks)
+            schur_chunks_kernel<<<ceil_div(n_chunks, 4), 128, 0, st>>>(v, (const SchurChunk*)(d + o_chunks), n_chunks, (const int2*)(d + o_pairs), Hpl,
+                                                                      Dinv, bl, part);
+        if (n_blocks)
+            schur_finish_kernel<<<ceil_div(n_blocks * 42, 128), 128, 0, st>>>(ctl, (const SchurBlock*)(d + o_blocks), n_blocks, part, Hpp, bp, Hs, n, ld);
+        {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(kCholCluster);
+            cfg.blockDim = dim3(kCholThreads);
+            cfg.dynamicSmemBytes = chol_smem;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = kCholCluster;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            B200_CUDA(cudaLaunchKernelEx(&cfg, chol_solve_kernel, n, ld, Hs, (const LmCtl*)ctl, (const double*)bp, xp, K, (const int*)(d + o_posecol), dq,
+                                         dt, dRt, r_result, fail));
+        }
+        backsub_kernel<<<lb2, 128, 0, st>>>(v, ctl, Dinv, bl, Hpl, xp, dpts, r_scale, fail);
+        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 0, 1, fail, ctl);
+        else B200_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), st));
+        return B200_OK;
+    };
+    auto launch_round_tail = [&](int round) -> int {  // chi2 of every active edge at the final state (terminate action's computeActiveErrors)
+        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 0, 0, nullptr, ctl);
+        lm_round_end_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, round);
+        return B200_OK;
+    };
+    const int iters[2] = {iters1, iters2};
+    int rc2;
 
-    // 5. first optimisation (local_bundle_adjuster_g2o.cc:312-313)
-    const int n1 = optimize(iters1, 0);
-    if (n1 < 0) return n1;
-    if (stats) stats->iterations[0] = n1;
-    // 6. outliers + second optimisation (:317-348)
-    bool run_robust = true;
-    if (force_stop && *force_stop) run_robust = false;
-    if (run_robust) {
-        if (E) outlier_kernel<<<eb, 128, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], 0, nullptr);
-        launches += 1;
-        const int n2 = optimize(iters2, 1);
-        if (n2 < 0) return n2;
-        if (stats) stats->iterations[1] = n2;
+    if (use_graph) {
+        // ---- one graph: round 1 WHILE { build; WHILE { trial } } -> outliers -> round 2 WHILE { ... } -> report
+        // (graph construction is serialised across solver instances: concurrent capture-to-graph + instantiate of conditional
+        // graphs from several threads crashed inside the driver on 580.159; execution of the instantiated graphs is concurrent)
+        std::unique_lock<std::mutex> build_lock(g_graph_build_mutex);
+        cudaGraph_t g = nullptr;
+        B200_CUDA(cudaGraphCreate(&g, 0));
+        struct GraphGuard {
+            cudaGraph_t g;
+            cudaGraphExec_t ex = nullptr;
+            ~GraphGuard() {
+                if (ex) cudaGraphExecDestroy(ex);
+                if (g) cudaGraphDestroy(g);
+            }
+        } guard{g};
+        cudaGraphConditionalHandle ho[2], hi[2];
+        for (int r = 0; r < 2; ++r) {
+            B200_CUDA(cudaGraphConditionalHandleCreate(&ho[r], g, 0, cudaGraphCondAssignDefault));
+            B200_CUDA(cudaGraphConditionalHandleCreate(&hi[r], g, 0, cudaGraphCondAssignDefault));
+        }
+        // a WHILE node appended to the graph that `st` is currently capturing into; returns its (empty) body graph
+        auto add_while = [&](cudaGraph_t parent, cudaGraphConditionalHandle hnd, cudaGraph_t* body) -> int {
+            cudaStreamCaptureStatus cs;
+            const cudaGraphNode_t* deps = nullptr;
+            size_t n_deps = 0;
+            cudaGraph_t cap = nullptr;
+            B200_CUDA(cudaStreamGetCaptureInfo(st, &cs, nullptr, &cap, &deps, &n_deps));
+            cudaGraphNodeParams prm = {};
+            prm.type = cudaGraphNodeTypeConditional;
+            prm.conditional.handle = hnd;
+            prm.conditional.type = cudaGraphCondTypeWhile;
+            prm.conditional.size = 1;
+            cudaGraphNode_t node;
+            B200_CUDA(cudaGraphAddNode(&node, parent, deps, n_deps, &prm));
+            B200_CUDA(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
+            *body = prm.conditional.phGraph_out[0];
+            return B200_OK;
+        };
+        cudaGraph_t outer_body[2] = {nullptr, nullptr}, inner_body[2] = {nullptr, nullptr}, ended = nullptr;
+        B200_CUDA(cudaStreamBeginCaptureToGraph(st, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+        for (int r = 0; r < 2; ++r) {
+            lm_round_begin_kernel<<<1, 1, 0, st>>>(ctl, iters[r], r, ho[r], 1);
+            if (r == 1 && E) outlier_kernel<<<eb, 128, 0, st>>>(v, dRt, dpts, dchi, 0, nullptr, ctl);  // :323-344 (skips itself after an abort)
+            if ((rc2 = add_while(g, ho[r], &outer_body[r]))) return rc2;
+            if ((rc2 = launch_round_tail(r))) return rc2;
+        }
+        if (E) outlier_kernel<<<eb, 128, 0, st>>>(v, dRt, dpts, dchi, 1, d + o_out, ctl);  // :354-375
+        lm_export_kernel<<<ceil_div(std::max(std::max(4 * K, 3 * L), 1), 256), 256, 0, st>>>(ctl, dq, dt, dpts, K, L, (double*)(d + o_qf), (double*)(d + o_tf),
+                                                                                         (double*)(d + o_pf));
+        B200_CUDA(cudaStreamEndCapture(st, &ended));
+        for (int r = 0; r < 2; ++r) {
+            B200_CUDA(cudaStreamBeginCaptureToGraph(st, outer_body[r], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            if ((rc2 = launch_build())) return rc2;
+            lm_after_build_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, r_diag, lb, Hpp, Kf, 4, hi[r], 1);
+            if ((rc2 = add_while(outer_body[r], hi[r], &inner_body[r]))) return rc2;
+            B200_CUDA(cudaStreamEndCapture(st, &ended));
+            B200_CUDA(cudaStreamBeginCaptureToGraph(st, inner_body[r], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
+            if ((rc2 = launch_trial())) return rc2;
+            lm_after_trial_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, r_scale, lb2, r_result, 6, hi[r], ho[r], 1);
+            B200_CUDA(cudaStreamEndCapture(st, &ended));
+        }
+        B200_CUDA(cudaGraphInstantiate(&guard.ex, g, 0));
+        build_lock.unlock();
+        B200_CUDA(cudaGraphLaunch(guard.ex, st));
+        B200_CUDA(cudaMemcpyAsync(hc, ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaEventRecord(S.ev1, st));
+        // the caller's flag may be raised by another thread while the graph runs (mapping_module.cc:124): mirror it into the
+        // device-visible word that the control kernels test between iterations
+        if (force_stop) {
+            while (cudaEventQuery(S.ev1) == cudaErrorNotReady) {
+                if (*force_stop) *S.h_abort = 1;
+                std::this_thread::sleep_for(std::chrono::microseconds(30));
+            }
+        }
+        B200_CUDA(S.wait(st));
+    } else {
+        // ---- host-stepped: the same kernels, one round trip per loop decision
+        auto fetch = [&]() -> int {
+            B200_CUDA(cudaMemcpyAsync(hc, ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
+            B200_CUDA(S.wait(st));
+            if (force_stop && *force_stop) *S.h_abort = 1;
+            return B200_OK;
+        };
+        for (int r = 0; r < 2; ++r) {
+            lm_round_begin_kernel<<<1, 1, 0, st>>>(ctl, iters[r], r, cudaGraphConditionalHandle{}, 0);
+            if (r == 1 && E) outlier_kernel<<<eb, 128, 0, st>>>(v, dRt, dpts, dchi, 0, nullptr, ctl);
+            if ((rc2 = fetch())) return rc2;
+            while (hc->outer_go) {
+                if ((rc2 = launch_build())) return rc2;
+                lm_after_build_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, r_diag, lb, Hpp, Kf, 4, cudaGraphConditionalHandle{}, 0);
+                do {
+                    if ((rc2 = launch_trial())) return rc2;
+                    lm_after_trial_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, r_scale, lb2, r_result, 6, cudaGraphConditionalHandle{},
+                                                                    cudaGraphConditionalHandle{}, 0);
+                    if ((rc2 = fetch())) return rc2;
+                } while (hc->inner_go);
+            }
+            if ((rc2 = launch_round_tail(r))) return rc2;
+        }
+        if (E) outlier_kernel<<<eb, 128, 0, st>>>(v, dRt, dpts, dchi, 1, d + o_out, ctl);
+        lm_export_kernel<<<ceil_div(std::max(std::max(4 * K, 3 * L), 1), 256), 256, 0, st>>>(ctl, dq, dt, dpts, K, L, (double*)(d + o_qf), (double*)(d + o_tf),
+                                                                                         (double*)(d + o_pf));
+        B200_CUDA(cudaMemcpyAsync(hc, ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaEventRecord(S.ev1, st));
+        B200_CUDA(S.wait(st));
     }
-    // 7. outlier observations (:354-375)
-    if (E) outlier_kernel<<<eb, 128, 0, st>>>(v, Rts[cur], ptss[cur], chis[cur], 1, d + o_out);
-    launches += 1;
-    B200_CUDA(cudaEventRecord(S.ev1, st));
-    // results
+    B200_CUDA(cudaGetLastError());
+    if (getenv("B200_LBA_DEBUG")) {
+        double cyc[6];
+        B200_CUDA(cudaMemcpy(cyc, r_result, sizeof(cyc), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[lba] last chol_solve cycles: diag %.0f panel %.0f trailing %.0f backward %.0f (n = %d)\n", cyc[2], cyc[3], cyc[4], cyc[5], n);
+    }
+    launches = hc->launches + 3;
+    if (stats) {
+        stats->lambda_init = hc->lambda_init;
+        for (int r = 0; r < 2; ++r) {
+            stats->iterations[r] = hc->iters_done[r];
+            stats->chi2[r] = hc->chi2[r];
+            stats->lambda_final[r] = hc->lambda_final[r];
+        }
+    }
+    // terminate_action's gain-threshold stop writes the caller's flag (terminate_action.cc:66-70); an externally raised flag stays up
+    if (force_stop && hc->stop_flag) *force_stop = 1;
+    // results (exported from whichever buffer ended up current)
     std::vector<unsigned char> out_sorted(std::max(E, 1));
     std::vector<double> qf(4 * (size_t)std::max(K, 1)), tf(3 * (size_t)std::max(K, 1));
     if (E) B200_CUDA(cudaMemcpyAsync(out_sorted.data(), d + o_out, E, cudaMemcpyDeviceToHost, st));
     if (K) {
-        B200_CUDA(cudaMemcpyAsync(qf.data(), qs[cur], sizeof(double) * 4 * K, cudaMemcpyDeviceToHost, st));
-        B200_CUDA(cudaMemcpyAsync(tf.data(), ts[cur], sizeof(double) * 3 * K, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaMemcpyAsync(qf.data(), d + o_qf, sizeof(double) * 4 * K, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaMemcpyAsync(tf.data(), d + o_tf, sizeof(double) * 3 * K, cudaMemcpyDeviceToHost, st));
     }
-    if (L) B200_CUDA(cudaMemcpyAsync(points_out, ptss[cur], sizeof(double) * 3 * (size_t)L, cudaMemcpyDeviceToHost, st));
+    if (L) B200_CUDA(cudaMemcpyAsync(points_out, d + o_pf, sizeof(double) * 3 * (size_t)L, cudaMemcpyDeviceToHost, st));
     B200_CUDA(S.wait(st));
     B200_CUDA(cudaEventElapsedTime(&S.last_ms, S.ev0, S.ev1));
     S.last_launches = launches;
@@ -1244,6 +1478,14 @@ int b200_lba_create(int device, b200_lba_t* out) {
     if (e == cudaSuccess) e = cudaEventCreate(&h->s.ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->s.ev1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->s.ev_sync, cudaEventBlockingSync | cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->s.h_ctl, sizeof(b200::lba::LmCtl), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->s.h_abort, sizeof(int), cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&h->s.d_abort, h->s.h_abort, 0);
+    // The conditional-graph driver is opt-in (B200_LBA_GRAPH=1): it is parity-green and slightly faster for one window at a time
+    // (4.55 vs 4.94 ms GPU time), but four or more instances executing such graphs concurrently crashed inside driver 580.159
+    // (tools/lba_conc.py), and concurrent windows are the normal case here.
+    const char* gm = getenv("B200_LBA_GRAPH");
+    h->s.host_loop = !(gm && gm[0] == '1');
     if (e != cudaSuccess) {
         delete h;
         return b200::cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
@@ -1259,6 +1501,8 @@ int b200_lba_destroy(b200_lba_t h) {
     cudaFree(h->s.d_arena);
     if (h->s.h_stage) cudaFreeHost(h->s.h_stage);
     if (h->s.h_res) cudaFreeHost(h->s.h_res);
+    if (h->s.h_ctl) cudaFreeHost(h->s.h_ctl);
+    if (h->s.h_abort) cudaFreeHost(h->s.h_abort);
     if (h->s.ev0) cudaEventDestroy(h->s.ev0);
     if (h->s.ev1) cudaEventDestroy(h->s.ev1);
     if (h->s.ev_sync) cudaEventDestroy(h->s.ev_sync);

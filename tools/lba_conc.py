@@ -3,6 +3,8 @@ sys.path.insert(0, ".")
 from concurrent.futures import ThreadPoolExecutor
 from stella_vslam_b200 import optimize, synth
 pr = synth.make_ba_problem(50, 10, 10000, seed=0, model="stereo")
+import os
+print('host loop' if os.environ.get('B200_LBA_HOST_LOOP') == '1' else 'graph')
 for nthr in (1, 2, 4, 8, 16):
     hs = [optimize.local_bundle_adjuster() for _ in range(nthr)]
     with ThreadPoolExecutor(nthr) as ex:
