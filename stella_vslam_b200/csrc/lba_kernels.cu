@@ -203,6 +203,175 @@ struct LmCtl {
 __device__ __forceinline__ bool lm_aborted(const LmCtl* c) { return c->stop_flag || (c->abort_word && *c->abort_word); }
 
 // ---------------------------------------------------------------------------------------------------------------
+// LM control kernels (one CTA each).  Sums of the per-CTA partials are taken by thread 0 in index order (staged through
+// shared memory), exactly like a host loop over the read-back array would.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kCtlThreads = 256;
+__device__ double ordered_sum(const double* __restrict__ p, int n, double* stage) {
+    double s = 0.0;
+    for (int base = 0; base < n; base += 1024) {
+        const int m = min(1024, n - base);
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += blockDim.x) stage[i] = __ldcg(p + base + i);  // L2: partials may come from other CTAs of this launch
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int i = 0; i < m; ++i) s += stage[i];
+    }
+    return s;  // valid in thread 0
+}
+__device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int use_graph, unsigned v) {
+    if (use_graph) cudaGraphSetConditional(h, v);
+}
+
+// start of SparseOptimizer::optimize(iterations): terminate_action at iteration -1 resets the stop flag (terminate_action.cc:46-51)
+__global__ void lm_round_begin_kernel(LmCtl* __restrict__ c, int iterations, int round, cudaGraphConditionalHandle h_outer, int use_graph) {
+    if (threadIdx.x) return;
+    c->round = round;
+    c->iterations = iterations;
+    c->iters_done[round] = 0;
+    c->launches += 1;
+    if (round == 1 && lm_aborted(c)) {  // local_bundle_adjuster_g2o.cc:317-321
+        c->skip_round2 = 1;
+        c->outer_go = 0;
+        set_cond(h_outer, use_graph, 0u);
+        return;
+    }
+    c->stop_flag = 0;
+    c->it = 0;
+    c->ok = 1;
+    c->outer_go = (iterations > 0 && !lm_aborted(c)) ? 1 : 0;
+    set_cond(h_outer, use_graph, (unsigned)c->outer_go);
+}
+
+// after computeActiveErrors + buildSystem: at the first iteration of a round take the robust chi2 and computeLambdaInit
+// (tau * max |H_jj| over all free vertices, tau = 1e-5); arm the trial loop
+__device__ void lm_after_build(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb, const double* __restrict__ r_diag, int lb,
+                               const double* __restrict__ Hpp, int Kf, int n_build_launches, cudaGraphConditionalHandle h_inner, int use_graph,
+                               double* stage) {
+    const bool first = c->it == 0;
+    double chi = 0.0;
+    if (first) chi = ordered_sum(r_chi, eb, stage);
+    if (threadIdx.x) return;
+    if (first) {
+        c->current_chi = chi;
+        double mx = 0.0;
+        for (int i = 0; i < lb; ++i) mx = fmax(mx, __ldcg(r_diag + i));
+        for (int p = 0; p < Kf; ++p)
+            for (int a = 0; a < 6; ++a) mx = fmax(mx, fabs(__ldcg(Hpp + 36 * (size_t)p + a * 7)));
+        c->lambda = 1e-5 * mx;
+        c->ni = 2.0;
+        if (c->round == 0) c->lambda_init = c->lambda;
+    }
+    c->qmax = 0;
+    c->rho = 0.0;
+    c->inner_go = 1;
+    c->launches += n_build_launches;
+    set_cond(h_inner, use_graph, 1u);
+}
+__global__ void __launch_bounds__(kCtlThreads) lm_after_build_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb,
+                                                                     const double* __restrict__ r_diag, int lb, const double* __restrict__ Hpp,
+                                                                     int Kf, int n_build_launches, cudaGraphConditionalHandle h_inner,
+                                                                     int use_graph) {
+    __shared__ double stage[1024];
+    lm_after_build(c, r_chi, eb, r_diag, lb, Hpp, Kf, n_build_launches, h_inner, use_graph, stage);
+}
+
+// after one trial (solve, back-substitution, chi2 at the trial state): the accept / reject rule of
+// OptimizationAlgorithmLevenberg::solve, and when the trial loop ends the end-of-iteration bookkeeping of
+// SparseOptimizer::optimize + terminate_action (terminate_action.cc:52-73)
+__device__ void lm_after_trial(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb, const double* __restrict__ r_scale, int lb2,
+                               const double* __restrict__ r_result, int n_trial_launches, cudaGraphConditionalHandle h_inner,
+                               cudaGraphConditionalHandle h_outer, int use_graph, double* stage) {
+    const bool ok2 = __ldcg(r_result) != 0.0;
+    const double chi_sum = ordered_sum(r_chi, eb, stage);
+    const double scale_sum = ordered_sum(r_scale, lb2, stage);
+    if (threadIdx.x) return;
+    c->launches += n_trial_launches;
+    const double temp_chi = ok2 ? chi_sum : 1.7976931348623157e308;
+    double rho = c->current_chi - temp_chi;
+    double scale = ok2 ? __ldcg(r_result + 1) + scale_sum : 0.0;  // computeScale
+    scale += 1e-3;
+    rho /= scale;
+    bool broke = false;
+    if (rho > 0 && isfinite(temp_chi) && ok2) {
+        double alpha = 1. - pow(2 * rho - 1, 3.0);
+        alpha = fmin(alpha, 2. / 3.);
+        c->lambda *= fmax(1. / 3., alpha);
+        c->ni = 2.0;
+        c->current_chi = temp_chi;
+        c->cur ^= 1;  // discardTop: keep the trial state
+    } else {
+        c->lambda *= c->ni;
+        c->ni *= 2.0;  // pop: the current state is untouched
+        if (!isfinite(c->lambda)) broke = true;
+    }
+    if (!broke) c->qmax++;
+    c->rho = rho;
+    const bool again = !broke && rho < 0 && c->qmax < 10 && !lm_aborted(c);
+    c->inner_go = again ? 1 : 0;
+    set_cond(h_inner, use_graph, again ? 1u : 0u);
+    if (again) return;
+    if (c->qmax == 10 || rho == 0 || !isfinite(c->lambda)) c->ok = 0;  // SolverResult::Terminate
+    const double chi_now = c->current_chi;
+    if (c->it == 0) {
+        c->last_chi = chi_now;
+    } else {
+        const double gain = (c->last_chi - chi_now) / chi_now;
+        c->last_chi = chi_now;
+        if (gain >= 0 && gain < 1e-3) c->stop_flag = 1;
+    }
+    c->chi2[c->round] = chi_now;
+    c->lambda_final[c->round] = c->lambda;
+    c->it++;
+    c->iters_done[c->round] = c->it;
+    const bool more = c->it < c->iterations && !lm_aborted(c) && c->ok;
+    c->outer_go = more ? 1 : 0;
+    set_cond(h_outer, use_graph, more ? 1u : 0u);
+}
+__global__ void __launch_bounds__(kCtlThreads) lm_after_trial_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb,
+                                                                     const double* __restrict__ r_scale, int lb2,
+                                                                     const double* __restrict__ r_result, int n_trial_launches,
+                                                                     cudaGraphConditionalHandle h_inner, cudaGraphConditionalHandle h_outer,
+                                                                     int use_graph) {
+    __shared__ double stage[1024];
+    lm_after_trial(c, r_chi, eb, r_scale, lb2, r_result, n_trial_launches, h_inner, h_outer, use_graph, stage);
+}
+
+// "last CTA" election: after every CTA of the launch has published its results, exactly one of them (the last to arrive) sees
+// true and may consume them; it re-arms the ticket for the next launch.
+__device__ __forceinline__ bool last_cta_arrives(int* ticket, int* smem_flag) {
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        *smem_flag = (t == (int)gridDim.x - 1);
+        if (*smem_flag) *ticket = 0;
+    }
+    __syncthreads();
+    const bool last = *smem_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
+// what the tail of a fused launch needs to run the LM bookkeeping
+struct CtlTail {
+    LmCtl* ctl;
+    int* ticket;
+    const double *r_chi, *r_diag, *r_scale, *r_result, *Hpp;
+    int eb, lb, lb2, Kf, n_launches, use_graph;
+    cudaGraphConditionalHandle h_inner, h_outer;
+};
+
+// end of a round: a round that ran no iteration still reports the chi2 of its (re-evaluated) state
+__global__ void __launch_bounds__(kCtlThreads) lm_round_end_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb, int round) {
+    __shared__ double stage[1024];
+    if (round == 1 && c->skip_round2) return;
+    const double chi = ordered_sum(r_chi, eb, stage);
+    if (threadIdx.x) return;
+    c->launches += 2;
+    if (c->iters_done[round] == 0) c->chi2[round] = chi;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K1: per edge -- residual, chi2, Huber weight, Hpl block and the landmark-side contribution
 //     out: chi[e] (plain chi2, only for active edges), Hpl[18][E], pl[9][E] (6 unique Hll + 3 bl), chi partials
 // ---------------------------------------------------------------------------------------------------------------
@@ -210,7 +379,8 @@ constexpr int kEdgeThreads = 128;
 
 __global__ void __launch_bounds__(kEdgeThreads) edges_kernel(View v, Dual Rt2, Dual pts2, Dual chi2, double* __restrict__ Hpl,
                                                              double* __restrict__ pl, double* __restrict__ chi_partials, int linearize,
-                                                             int on_trial, int* __restrict__ fail_reset, const LmCtl* __restrict__ ctl) {
+                                                             int on_trial, int* __restrict__ fail_reset, const LmCtl* __restrict__ ctl,
+                                                             CtlTail tail) {
     __shared__ double sh[kEdgeThreads];
     const int sidx = (ctl->cur ^ on_trial) & 1;  // on_trial: evaluate the trial state, carrying inactive chi2 over from the current one
     const double* __restrict__ Rt = Rt2.p[sidx];
@@ -272,6 +442,13 @@ __global__ void __launch_bounds__(kEdgeThreads) edges_kernel(View v, Dual Rt2, D
     }
     const double s = block_sum(cost, sh);
     if (threadIdx.x == 0) chi_partials[blockIdx.x] = s;
+    if (tail.ticket) {  // trial evaluation: the last CTA runs the accept / reject bookkeeping on the complete partial sums
+        __shared__ int last_flag;
+        __shared__ double stage[1024];
+        if (!last_cta_arrives(tail.ticket, &last_flag)) return;
+        lm_after_trial(tail.ctl, tail.r_chi, tail.eb, tail.r_scale, tail.lb2, tail.r_result, tail.n_launches, tail.h_inner, tail.h_outer, tail.use_graph,
+                       stage);
+    }
 }
 
 // K2: per landmark -- Hll (6 unique), bl (3) from its contiguous edge range; partial max |diag|
@@ -306,54 +483,14 @@ __global__ void __launch_bounds__(128) points_kernel(View v, const double* __res
 }
 
 // K3: keyframe-side blocks.  The edges of every free keyframe are cut into chunks of kPoseChunk; one warp reduces one
-//     chunk to 21 unique Hpp entries + 6 bp entries, pose_finish_kernel adds the chunk partials in index order.
+//     chunk to 21 unique Hpp entries + 6 bp entries; the chunk partials are then added in index order.
 constexpr int kPoseChunk = 64;
-__global__ void __launch_bounds__(128) pose_chunks_kernel(View v, const int2* __restrict__ chunks, int n_chunks, Dual Rt2, Dual pts2,
-                                                          double* __restrict__ partials, const LmCtl* __restrict__ ctl) {
-    const double* __restrict__ Rt = Rt2.p[ctl->cur & 1];
-    const double* __restrict__ pts = pts2.p[ctl->cur & 1];
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (wid >= n_chunks) return;
-    const int2 ch = chunks[wid];
-    double acc[27];
-#pragma unroll
-    for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-    for (int k = ch.x + lane; k < ch.y; k += 32) {
-        const int e = v.pose_edges[k];
-        if (v.level[e]) continue;
-        const EdgeS ed = v.edges[e];
-        const Cam c = v.cams[ed.cam];
-        double err[3], pc[3], Ji[9], Jj[18];
-        const double* T = Rt + 12 * (size_t)ed.pose;
-        edge_residual(ed, c, T, pts + 3 * (size_t)ed.point, err, pc);
-        edge_jacobians(ed, c, T, pc, Ji, Jj);
-        const double w = (double)ed.inv_sigma_sq;
-        const double e2 = w * (err[0] * err[0] + err[1] * err[1] + err[2] * err[2]);
-        const double ww = w * (v.robust[e] ? huber_weight(e2, (double)ed.delta) : 1.0);
-        int t = 0;
-#pragma unroll
-        for (int a = 0; a < 6; ++a)
-#pragma unroll
-            for (int b = a; b < 6; ++b) acc[t++] += ww * (Jj[a] * Jj[b] + Jj[6 + a] * Jj[6 + b] + Jj[12 + a] * Jj[12 + b]);
-#pragma unroll
-        for (int a = 0; a < 6; ++a) acc[21 + a] += -ww * (Jj[a] * err[0] + Jj[6 + a] * err[1] + Jj[12 + a] * err[2]);
-    }
-#pragma unroll
-    for (int i = 0; i < 27; ++i)
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) acc[i] += __shfl_down_sync(0xFFFFFFFFu, acc[i], s);
-    if (lane == 0)
-#pragma unroll
-        for (int i = 0; i < 27; ++i) partials[(size_t)wid * 27 + i] = acc[i];
-}
-
-__global__ void __launch_bounds__(128) pose_finish_kernel(int Kf, const int* __restrict__ chunk_start, const double* __restrict__ partials,
-                                                          double* __restrict__ Hpp, double* __restrict__ bp) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void pose_finish_element(int idx, int Kf, const int* __restrict__ chunk_start, const double* __restrict__ partials,
+                                                    double* __restrict__ Hpp, double* __restrict__ bp) {
     const int p = idx / 27, t = idx - p * 27;
     if (p >= Kf) return;
     double r = 0.0;
-    for (int c = chunk_start[p]; c < chunk_start[p + 1]; ++c) r += partials[(size_t)c * 27 + t];
+    for (int c = chunk_start[p]; c < chunk_start[p + 1]; ++c) r += __ldcg(partials + (size_t)c * 27 + t);
     if (t < 21) {
         int a = 0, rem = t;
         while (rem >= 6 - a) {
@@ -366,6 +503,57 @@ __global__ void __launch_bounds__(128) pose_finish_kernel(int Kf, const int* __r
     } else {
         bp[(size_t)p * 6 + (t - 21)] = r;
     }
+}
+
+// One warp per chunk; the last CTA to finish adds the chunk partials of every keyframe in index order (what used to be a second
+// launch) and then runs the after-build LM bookkeeping (a third).
+__global__ void __launch_bounds__(128) pose_chunks_kernel(View v, const int2* __restrict__ chunks, int n_chunks, Dual Rt2, Dual pts2,
+                                                          double* __restrict__ partials, const LmCtl* __restrict__ ctl,
+                                                          const int* __restrict__ chunk_start, double* __restrict__ Hpp, double* __restrict__ bp,
+                                                          CtlTail tail) {
+    const double* __restrict__ Rt = Rt2.p[ctl->cur & 1];
+    const double* __restrict__ pts = pts2.p[ctl->cur & 1];
+    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (wid < n_chunks) {
+        const int2 ch = chunks[wid];
+        double acc[27];
+#pragma unroll
+        for (int i = 0; i < 27; ++i) acc[i] = 0.0;
+        for (int k = ch.x + lane; k < ch.y; k += 32) {
+            const int e = v.pose_edges[k];
+            if (v.level[e]) continue;
+            const EdgeS ed = v.edges[e];
+            const Cam c = v.cams[ed.cam];
+            double err[3], pc[3], Ji[9], Jj[18];
+            const double* T = Rt + 12 * (size_t)ed.pose;
+            edge_residual(ed, c, T, pts + 3 * (size_t)ed.point, err, pc);
+            edge_jacobians(ed, c, T, pc, Ji, Jj);
+            const double w = (double)ed.inv_sigma_sq;
+            const double e2 = w * (err[0] * err[0] + err[1] * err[1] + err[2] * err[2]);
+            const double ww = w * (v.robust[e] ? huber_weight(e2, (double)ed.delta) : 1.0);
+            int t = 0;
+#pragma unroll
+            for (int a = 0; a < 6; ++a)
+#pragma unroll
+                for (int b = a; b < 6; ++b) acc[t++] += ww * (Jj[a] * Jj[b] + Jj[6 + a] * Jj[6 + b] + Jj[12 + a] * Jj[12 + b]);
+#pragma unroll
+            for (int a = 0; a < 6; ++a) acc[21 + a] += -ww * (Jj[a] * err[0] + Jj[6 + a] * err[1] + Jj[12 + a] * err[2]);
+        }
+#pragma unroll
+        for (int i = 0; i < 27; ++i)
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) acc[i] += __shfl_down_sync(0xFFFFFFFFu, acc[i], s);
+        if (lane == 0)
+#pragma unroll
+            for (int i = 0; i < 27; ++i) partials[(size_t)wid * 27 + i] = acc[i];
+    }
+    __shared__ int last_flag;
+    __shared__ double stage[1024];
+    if (!last_cta_arrives(tail.ticket, &last_flag)) return;
+    for (int idx = threadIdx.x; idx < tail.Kf * 27; idx += blockDim.x) pose_finish_element(idx, tail.Kf, chunk_start, partials, Hpp, bp);
+    __threadfence();
+    __syncthreads();
+    lm_after_build(tail.ctl, tail.r_chi, tail.eb, tail.r_diag, tail.lb, tail.Hpp, tail.Kf, tail.n_launches, tail.h_inner, tail.use_graph, stage);
 }
 
 // K4: per landmark -- Dinv = (Hll + lambda I)^-1 (symmetric 3x3, cofactor inverse like Eigen's fixed-size path)
@@ -394,7 +582,7 @@ __global__ void __launch_bounds__(128) dinv_kernel(int Lf, const LmCtl* __restri
 // K5: Schur complement of the landmarks.  The (edge a, edge c) pairs that share a landmark are grouped by the upper
 //     block (i <= j) of the reduced system they fall into and cut into chunks of kSchurChunk pairs; one warp reduces one
 //     chunk:  partial = sum T(a) Hpl(c)^T,  T(a) = Hpl(a) Dinv(l)   (+ for diagonal blocks  sum T(a) bl(l)).
-//     schur_finish_kernel then adds the chunk partials of every block in index order (deterministic) into
+//     The chunk partials of every block are then added in index order (deterministic) into
 //     M = [Hpp + lambda I - sum ; (bp - sum)^T].
 constexpr int kSchurChunk = 64;
 struct SchurBlock {
@@ -412,12 +600,41 @@ __device__ __forceinline__ void load18(const double* __restrict__ p, double* out
         out[2 * i + 1] = v.y;
     }
 }
+// Adds the chunk partials of block b in index order into M = [Hpp + lambda I - sum ; (bp - sum)^T]; lanes cover the 42 elements.
+__device__ __forceinline__ void schur_finish_block(const SchurBlock sb, double lambda, const double* __restrict__ partials,
+                                                   const double* __restrict__ Hpp, const double* __restrict__ bp, double* __restrict__ M, int n, int ld,
+                                                   int lane) {
+    for (int el = lane; el < 42; el += 32) {
+        if (el >= 36 && sb.i != sb.j) continue;
+        double sacc = 0.0;
+        for (int c = sb.chunk_start; c < sb.chunk_end; ++c) sacc += __ldcg(partials + (size_t)c * 42 + el);
+        if (el < 36) {
+            const int r = el / 6, c = el - r * 6;
+            double val = -sacc;
+            if (sb.i == sb.j) val += Hpp[(size_t)sb.i * 36 + el] + (r == c ? lambda : 0.0);
+            M[(size_t)(6 * sb.j + c) * ld + 6 * sb.i + r] = val;  // lower triangle (j >= i)
+            if (sb.i == sb.j) M[(size_t)(6 * sb.i + r) * ld + 6 * sb.j + c] = val;
+        } else {
+            const int r = el - 36;
+            M[(size_t)n * ld + 6 * sb.i + r] = bp[(size_t)sb.i * 6 + r] - sacc;  // rhs row
+        }
+    }
+}
+
+// One warp per chunk (chunk.pad = its block).  The warp that completes a block's last chunk assembles that block of the reduced
+// system (what used to be a second launch); warps past the chunks fill the blocks that have no pair at all.
 __global__ void __launch_bounds__(128) schur_chunks_kernel(View v, const SchurChunk* __restrict__ chunks, int n_chunks,
                                                            const int2* __restrict__ pairs, const double* __restrict__ Hpl,
                                                            const double* __restrict__ Dinv, const double* __restrict__ bl,
-                                                           double* __restrict__ partials) {
+                                                           double* __restrict__ partials, const LmCtl* __restrict__ ctl,
+                                                           const SchurBlock* __restrict__ blocks, const int* __restrict__ empty_blocks, int n_empty,
+                                                           int* __restrict__ blk_done, const double* __restrict__ Hpp, const double* __restrict__ bp,
+                                                           double* __restrict__ M, int n, int ld) {
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (wid >= n_chunks) return;
+    if (wid >= n_chunks) {
+        if (wid - n_chunks < n_empty) schur_finish_block(blocks[empty_blocks[wid - n_chunks]], ctl->lambda, partials, Hpp, bp, M, n, ld, lane);
+        return;
+    }
     const SchurChunk ch = chunks[wid];
     double acc[42];
 #pragma unroll
@@ -450,31 +667,19 @@ __global__ void __launch_bounds__(128) schur_chunks_kernel(View v, const SchurCh
     for (int i = 0; i < 42; ++i)
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) acc[i] += __shfl_down_sync(0xFFFFFFFFu, acc[i], s);
-    if (lane == 0)
+    const SchurBlock sb = blocks[ch.pad];
+    int arrived = 0;
+    if (lane == 0) {
 #pragma unroll
         for (int i = 0; i < 42; ++i) partials[(size_t)wid * 42 + i] = acc[i];
-}
-
-__global__ void __launch_bounds__(128) schur_finish_kernel(const LmCtl* __restrict__ ctl, const SchurBlock* __restrict__ blocks, int n_blocks,
-                                                           const double* __restrict__ partials, const double* __restrict__ Hpp,
-                                                           const double* __restrict__ bp, double* __restrict__ M, int n, int ld) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = idx / 42, el = idx - b * 42;
-    if (b >= n_blocks) return;
-    const SchurBlock sb = blocks[b];
-    if (el >= 36 && sb.i != sb.j) return;
-    double sacc = 0.0;
-    for (int c = sb.chunk_start; c < sb.chunk_end; ++c) sacc += partials[(size_t)c * 42 + el];
-    if (el < 36) {
-        const int r = el / 6, c = el - r * 6;
-        double val = -sacc;
-        if (sb.i == sb.j) val += Hpp[(size_t)sb.i * 36 + el] + (r == c ? ctl->lambda : 0.0);
-        M[(size_t)(6 * sb.j + c) * ld + 6 * sb.i + r] = val;  // lower triangle (j >= i)
-        if (sb.i == sb.j) M[(size_t)(6 * sb.i + r) * ld + 6 * sb.j + c] = val;
-    } else {
-        const int r = el - 36;
-        M[(size_t)n * ld + 6 * sb.i + r] = bp[(size_t)sb.i * 6 + r] - sacc;  // rhs row
+        __threadfence();
+        arrived = atomicAdd(&blk_done[ch.pad], 1);
     }
+    arrived = __shfl_sync(0xFFFFFFFFu, arrived, 0);
+    if (arrived != sb.chunk_end - sb.chunk_start - 1) return;
+    __threadfence();
+    schur_finish_block(sb, ctl->lambda, partials, Hpp, bp, M, n, ld, lane);
+    if (lane == 0) blk_done[ch.pad] = 0;  // re-armed for the next trial
 }
 
 // K6: dense Cholesky of the reduced system (<= 6*Kf unknowns), solve, then the keyframe updates
@@ -841,141 +1046,6 @@ __global__ void __launch_bounds__(128) outlier_kernel(View v, Dual Rt2, Dual pts
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// LM control kernels (one CTA each).  Sums of the per-CTA partials are taken by thread 0 in index order (staged through
-// shared memory), exactly like a host loop over the read-back array would.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kCtlThreads = 256;
-__device__ double ordered_sum(const double* __restrict__ p, int n, double* stage) {
-    double s = 0.0;
-    for (int base = 0; base < n; base += 1024) {
-        const int m = min(1024, n - base);
-        __syncthreads();
-        for (int i = threadIdx.x; i < m; i += blockDim.x) stage[i] = p[base + i];
-        __syncthreads();
-        if (threadIdx.x == 0)
-            for (int i = 0; i < m; ++i) s += stage[i];
-    }
-    return s;  // valid in thread 0
-}
-__device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int use_graph, unsigned v) {
-    if (use_graph) cudaGraphSetConditional(h, v);
-}
-
-// start of SparseOptimizer::optimize(iterations): terminate_action at iteration -1 resets the stop flag (terminate_action.cc:46-51)
-__global__ void lm_round_begin_kernel(LmCtl* __restrict__ c, int iterations, int round, cudaGraphConditionalHandle h_outer, int use_graph) {
-    if (threadIdx.x) return;
-    c->round = round;
-    c->iterations = iterations;
-    c->iters_done[round] = 0;
-    c->launches += 1;
-    if (round == 1 && lm_aborted(c)) {  // local_bundle_adjuster_g2o.cc:317-321
-        c->skip_round2 = 1;
-        c->outer_go = 0;
-        set_cond(h_outer, use_graph, 0u);
-        return;
-    }
-    c->stop_flag = 0;
-    c->it = 0;
-    c->ok = 1;
-    c->outer_go = (iterations > 0 && !lm_aborted(c)) ? 1 : 0;
-    set_cond(h_outer, use_graph, (unsigned)c->outer_go);
-}
-
-// after computeActiveErrors + buildSystem: at the first iteration of a round take the robust chi2 and computeLambdaInit
-// (tau * max |H_jj| over all free vertices, tau = 1e-5); arm the trial loop
-__global__ void __launch_bounds__(kCtlThreads) lm_after_build_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb,
-                                                                     const double* __restrict__ r_diag, int lb, const double* __restrict__ Hpp,
-                                                                     int Kf, int n_build_launches, cudaGraphConditionalHandle h_inner,
-                                                                     int use_graph) {
-    __shared__ double stage[1024];
-    const bool first = c->it == 0;
-    double chi = 0.0;
-    if (first) chi = ordered_sum(r_chi, eb, stage);
-    if (threadIdx.x) return;
-    if (first) {
-        c->current_chi = chi;
-        double mx = 0.0;
-        for (int i = 0; i < lb; ++i) mx = fmax(mx, r_diag[i]);
-        for (int p = 0; p < Kf; ++p)
-            for (int a = 0; a < 6; ++a) mx = fmax(mx, fabs(Hpp[36 * (size_t)p + a * 7]));
-        c->lambda = 1e-5 * mx;
-        c->ni = 2.0;
-        if (c->round == 0) c->lambda_init = c->lambda;
-    }
-    c->qmax = 0;
-    c->rho = 0.0;
-    c->inner_go = 1;
-    c->launches += n_build_launches + 1;
-    set_cond(h_inner, use_graph, 1u);
-}
-
-// after one trial (solve, back-substitution, chi2 at the trial state): the accept / reject rule of
-// OptimizationAlgorithmLevenberg::solve, and when the trial loop ends the end-of-iteration bookkeeping of
-// SparseOptimizer::optimize + terminate_action (terminate_action.cc:52-73)
-__global__ void __launch_bounds__(kCtlThreads) lm_after_trial_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb,
-                                                                     const double* __restrict__ r_scale, int lb2,
-                                                                     const double* __restrict__ r_result, int n_trial_launches,
-                                                                     cudaGraphConditionalHandle h_inner, cudaGraphConditionalHandle h_outer,
-                                                                     int use_graph) {
-    __shared__ double stage[1024];
-    const bool ok2 = r_result[0] != 0.0;
-    const double chi_sum = ordered_sum(r_chi, eb, stage);
-    const double scale_sum = ordered_sum(r_scale, lb2, stage);
-    if (threadIdx.x) return;
-    c->launches += n_trial_launches + 1;
-    const double temp_chi = ok2 ? chi_sum : 1.7976931348623157e308;
-    double rho = c->current_chi - temp_chi;
-    double scale = ok2 ? r_result[1] + scale_sum : 0.0;  // computeScale
-    scale += 1e-3;
-    rho /= scale;
-    bool broke = false;
-    if (rho > 0 && isfinite(temp_chi) && ok2) {
-        double alpha = 1. - pow(2 * rho - 1, 3.0);
-        alpha = fmin(alpha, 2. / 3.);
-        c->lambda *= fmax(1. / 3., alpha);
-        c->ni = 2.0;
-        c->current_chi = temp_chi;
-        c->cur ^= 1;  // discardTop: keep the trial state
-    } else {
-        c->lambda *= c->ni;
-        c->ni *= 2.0;  // pop: the current state is untouched
-        if (!isfinite(c->lambda)) broke = true;
-    }
-    if (!broke) c->qmax++;
-    c->rho = rho;
-    const bool again = !broke && rho < 0 && c->qmax < 10 && !lm_aborted(c);
-    c->inner_go = again ? 1 : 0;
-    set_cond(h_inner, use_graph, again ? 1u : 0u);
-    if (again) return;
-    if (c->qmax == 10 || rho == 0 || !isfinite(c->lambda)) c->ok = 0;  // SolverResult::Terminate
-    const double chi_now = c->current_chi;
-    if (c->it == 0) {
-        c->last_chi = chi_now;
-    } else {
-        const double gain = (c->last_chi - chi_now) / chi_now;
-        c->last_chi = chi_now;
-        if (gain >= 0 && gain < 1e-3) c->stop_flag = 1;
-    }
-    c->chi2[c->round] = chi_now;
-    c->lambda_final[c->round] = c->lambda;
-    c->it++;
-    c->iters_done[c->round] = c->it;
-    const bool more = c->it < c->iterations && !lm_aborted(c) && c->ok;
-    c->outer_go = more ? 1 : 0;
-    set_cond(h_outer, use_graph, more ? 1u : 0u);
-}
-
-// end of a round: a round that ran no iteration still reports the chi2 of its (re-evaluated) state
-__global__ void __launch_bounds__(kCtlThreads) lm_round_end_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb, int round) {
-    __shared__ double stage[1024];
-    if (round == 1 && c->skip_round2) return;
-    const double chi = ordered_sum(r_chi, eb, stage);
-    if (threadIdx.x) return;
-    c->launches += 2;
-    if (c->iters_done[round] == 0) c->chi2[round] = chi;
-}
-
 // copy the final (current) keyframe and landmark states to fixed read-back buffers
 __global__ void __launch_bounds__(256) lm_export_kernel(const LmCtl* __restrict__ c, Dual q2, Dual t2, Dual pts2, int K, int L, double* __restrict__ qf,
                                                         double* __restrict__ tf, double* __restrict__ pf) {
@@ -1131,12 +1201,14 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     }
     std::vector<SchurBlock> blocks(std::max(1, n_blocks));
     std::vector<SchurChunk> chunks;
+    std::vector<int> empty_blocks;
     for (int i = 0, b = 0; i < Kf; ++i)
         for (int j = i; j < Kf; ++j, ++b) {
             const int c0 = (int)chunks.size();
             for (int sidx = blk_count[b]; sidx < blk_count[b + 1]; sidx += kSchurChunk)
-                chunks.push_back(SchurChunk{sidx, std::min(sidx + kSchurChunk, blk_count[b + 1]), i == j ? 1 : 0, 0});
+                chunks.push_back(SchurChunk{sidx, std::min(sidx + kSchurChunk, blk_count[b + 1]), i == j ? 1 : 0, b});
             blocks[b] = SchurBlock{i, j, c0, (int)chunks.size()};
+            if (c0 == (int)chunks.size()) empty_blocks.push_back(b);  // no pair falls into this block: it is just Hpp + lambda I or zero
         }
     const int n_chunks = (int)chunks.size();
     // pose-side chunks: kPoseChunk edges of one free keyframe per warp
@@ -1175,6 +1247,8 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     const size_t o_chunks = up.take<SchurChunk>(n_chunks), o_pchunks = up.take<int2>(n_pose_chunks), o_pcstart = up.take<int>(Kf + 1);
     const size_t o_q0 = up.take<double>(4 * (size_t)K), o_t0 = up.take<double>(3 * (size_t)K), o_Rt0 = up.take<double>(12 * (size_t)K);
     const size_t o_pts0 = up.take<double>(3 * (size_t)L);
+    const int n_empty = (int)empty_blocks.size();
+    const size_t o_empty = up.take<int>(n_empty), o_blkdone = up.take<int>(n_blocks), o_tickets = up.take<int>(2);  // counters upload as zeros
     const size_t upload_bytes = round_up(up.off, (size_t)256);
     Carver dv;
     dv.off = upload_bytes;
@@ -1211,6 +1285,7 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     put(o_t0, t0.data(), sizeof(double) * 3 * K);
     put(o_Rt0, Rt0.data(), sizeof(double) * 12 * K);
     put(o_pts0, P->points, sizeof(double) * 3 * (size_t)L);
+    put(o_empty, empty_blocks.data(), sizeof(int) * n_empty);
     unsigned char* d = S.d_arena;
     cudaStream_t st = S.stream;
     int launches = 0;
@@ -1249,25 +1324,38 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     const int ug = use_graph ? 1 : 0;
 
     // the kernels of one buildSystem and of one LM trial (identical in graph and host-stepped mode)
-    auto launch_build = [&]() -> int {
-        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 1, 0, nullptr, ctl);
+    auto tail_of = [&](int ticket_idx, int n_launches, cudaGraphConditionalHandle h_in, cudaGraphConditionalHandle h_out) {
+        CtlTail t{};
+        t.ctl = ctl;
+        t.ticket = (int*)(d + o_tickets) + ticket_idx;
+        t.r_chi = r_chi; t.r_diag = r_diag; t.r_scale = r_scale; t.r_result = r_result; t.Hpp = Hpp;
+        t.eb = E ? eb : 0; t.lb = lb; t.lb2 = lb2; t.Kf = Kf; t.n_launches = n_launches; t.use_graph = ug;
+        t.h_inner = h_in; t.h_outer = h_out;
+        return t;
+    };
+    // computeActiveErrors + buildSystem: 3 launches; the last CTA of the keyframe-side kernel also runs the LM bookkeeping
+    auto launch_build = [&](cudaGraphConditionalHandle h_in) -> int {
+        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 1, 0, nullptr, ctl, CtlTail{});
         points_kernel<<<lb, 128, 0, st>>>(v, pl, Hll, bl, r_diag);
         if (n_pose_chunks) {
-            pose_chunks_kernel<<<ceil_div(n_pose_chunks, 4), 128, 0, st>>>(v, (const int2*)(d + o_pchunks), n_pose_chunks, dRt, dpts, ppart, ctl);
-            pose_finish_kernel<<<ceil_div(Kf * 27, 128), 128, 0, st>>>(Kf, (const int*)(d + o_pcstart), ppart, Hpp, bp);
-        } else if (Kf) {
-            B200_CUDA(cudaMemsetAsync(Hpp, 0, sizeof(double) * 36 * Kf, st));
-            B200_CUDA(cudaMemsetAsync(bp, 0, sizeof(double) * 6 * Kf, st));
+            pose_chunks_kernel<<<ceil_div(n_pose_chunks, 4), 128, 0, st>>>(v, (const int2*)(d + o_pchunks), n_pose_chunks, dRt, dpts, ppart, ctl,
+                                                                          (const int*)(d + o_pcstart), Hpp, bp, tail_of(0, 3, h_in, h_in));
+        } else {
+            if (Kf) {
+                B200_CUDA(cudaMemsetAsync(Hpp, 0, sizeof(double) * 36 * Kf, st));
+                B200_CUDA(cudaMemsetAsync(bp, 0, sizeof(double) * 6 * Kf, st));
+            }
+            lm_after_build_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, r_diag, lb, Hpp, Kf, 3, h_in, ug);
         }
         return B200_OK;
     };
-    auto launch_trial = [&]() -> int {
+    // one LM trial: 5 launches; the last CTA of the trial's chi2 evaluation runs the accept / reject bookkeeping
+    auto launch_trial = [&](cudaGraphConditionalHandle h_in, cudaGraphConditionalHandle h_out) -> int {
         if (Lf) dinv_kernel<<<ceil_div(Lf, 128), 128, 0, st>>>(Lf, ctl, Hll, Dinv, fail);
-        if (n_chunks)
-            schur_chunks_kernel<<<ceil_div(n_chunks, 4), 128, 0, st>>>(v, (const SchurChunk*)(d + o_chunks), n_chunks, (const int2*)(d + o_pairs), Hpl,
-                                                                      Dinv, bl, part);
         if (n_blocks)
-            schur_finish_kernel<<<ceil_div(n_blocks * 42, 128), 128, 0, st>>>(ctl, (const SchurBlock*)(d + o_blocks), n_blocks, part, Hpp, bp, Hs, n, ld);
+            schur_chunks_kernel<<<ceil_div(std::max(n_chunks + n_empty, 1), 4), 128, 0, st>>>(
+                v, (const SchurChunk*)(d + o_chunks), n_chunks, (const int2*)(d + o_pairs), Hpl, Dinv, bl, part, ctl, (const SchurBlock*)(d + o_blocks),
+                (const int*)(d + o_empty), n_empty, (int*)(d + o_blkdone), Hpp, bp, Hs, n, ld);
         {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(kCholCluster);
@@ -1285,12 +1373,16 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
                                          dt, dRt, r_result, fail));
         }
         backsub_kernel<<<lb2, 128, 0, st>>>(v, ctl, Dinv, bl, Hpl, xp, dpts, r_scale, fail);
-        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 0, 1, fail, ctl);
-        else B200_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), st));
+        if (E) {
+            edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 0, 1, fail, ctl, tail_of(1, 5, h_in, h_out));
+        } else {
+            B200_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), st));
+            lm_after_trial_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, 0, r_scale, lb2, r_result, 5, h_in, h_out, ug);
+        }
         return B200_OK;
     };
     auto launch_round_tail = [&](int round) -> int {  // chi2 of every active edge at the final state (terminate action's computeActiveErrors)
-        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 0, 0, nullptr, ctl);
+        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 0, 0, nullptr, ctl, CtlTail{});
         lm_round_end_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, round);
         return B200_OK;
     };
@@ -1306,12 +1398,15 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
         B200_CUDA(cudaGraphCreate(&g, 0));
         struct GraphGuard {
             cudaGraph_t g;
+            std::unique_lock<std::mutex>* lk;
             cudaGraphExec_t ex = nullptr;
-            ~GraphGuard() {
+            ~GraphGuard() {  // (runs before build_lock's destructor; graph teardown is serialised like construction)
+                if (!lk->owns_lock()) lk->lock();
                 if (ex) cudaGraphExecDestroy(ex);
                 if (g) cudaGraphDestroy(g);
+                lk->unlock();
             }
-        } guard{g};
+        } guard{g, &build_lock};
         cudaGraphConditionalHandle ho[2], hi[2];
         for (int r = 0; r < 2; ++r) {
             B200_CUDA(cudaGraphConditionalHandleCreate(&ho[r], g, 0, cudaGraphCondAssignDefault));
@@ -1349,18 +1444,16 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
         B200_CUDA(cudaStreamEndCapture(st, &ended));
         for (int r = 0; r < 2; ++r) {
             B200_CUDA(cudaStreamBeginCaptureToGraph(st, outer_body[r], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-            if ((rc2 = launch_build())) return rc2;
-            lm_after_build_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, r_diag, lb, Hpp, Kf, 4, hi[r], 1);
+            if ((rc2 = launch_build(hi[r]))) return rc2;
             if ((rc2 = add_while(outer_body[r], hi[r], &inner_body[r]))) return rc2;
             B200_CUDA(cudaStreamEndCapture(st, &ended));
             B200_CUDA(cudaStreamBeginCaptureToGraph(st, inner_body[r], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-            if ((rc2 = launch_trial())) return rc2;
-            lm_after_trial_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, r_scale, lb2, r_result, 6, hi[r], ho[r], 1);
+            if ((rc2 = launch_trial(hi[r], ho[r]))) return rc2;
             B200_CUDA(cudaStreamEndCapture(st, &ended));
         }
         B200_CUDA(cudaGraphInstantiate(&guard.ex, g, 0));
-        build_lock.unlock();
         B200_CUDA(cudaGraphLaunch(guard.ex, st));
+        build_lock.unlock();
         B200_CUDA(cudaMemcpyAsync(hc, ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
         B200_CUDA(cudaEventRecord(S.ev1, st));
         // the caller's flag may be raised by another thread while the graph runs (mapping_module.cc:124): mirror it into the
@@ -1385,12 +1478,9 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
             if (r == 1 && E) outlier_kernel<<<eb, 128, 0, st>>>(v, dRt, dpts, dchi, 0, nullptr, ctl);
             if ((rc2 = fetch())) return rc2;
             while (hc->outer_go) {
-                if ((rc2 = launch_build())) return rc2;
-                lm_after_build_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, r_diag, lb, Hpp, Kf, 4, cudaGraphConditionalHandle{}, 0);
+                if ((rc2 = launch_build(cudaGraphConditionalHandle{}))) return rc2;
                 do {
-                    if ((rc2 = launch_trial())) return rc2;
-                    lm_after_trial_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, r_scale, lb2, r_result, 6, cudaGraphConditionalHandle{},
-                                                                    cudaGraphConditionalHandle{}, 0);
+                    if ((rc2 = launch_trial(cudaGraphConditionalHandle{}, cudaGraphConditionalHandle{}))) return rc2;
                     if ((rc2 = fetch())) return rc2;
                 } while (hc->inner_go);
             }

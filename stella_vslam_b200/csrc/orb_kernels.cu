@@ -227,13 +227,15 @@ __device__ __forceinline__ bool mask_zero(const unsigned char* mask, unsigned lo
 // the sm_100 packed 3-input min/max (VIMNMX3.U16x2): 16 window-3 + 16 window-9 + 8 reduction ops per polarity and lane
 // pair.  Working on the raw pixel values (not on differences) keeps everything unsigned and never negates a min/max
 // result (see the ptxas note in DESIGN.md).  Returns max(m - t_low, 0) per pixel, packed as 4 bytes.
+// (An exact early-out on the four even antipodal pairs -- every 9-arc holds one pixel of each pair -- was measured: it never
+// retires a whole warp on the bench stream and cost 3 %, so the arcs are always evaluated.)
 __device__ __forceinline__ unsigned fast_m4(const unsigned (&w)[7][3], unsigned neg_tlow2) {
     // circle offsets (dx, dy) in OpenCV order; row index = dy + 3, window = 4 bytes starting at column c0 + dx
     constexpr int DX[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
     constexpr int DY[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
     unsigned pe[16], po[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    const unsigned ve = __byte_perm(w[3][1], 0, 0x4240), vo = __byte_perm(w[3][1], 0, 0x4341);
+    auto extract = [&](int k) {
         const int dx = DX[k], r = DY[k] + 3;
         unsigned x;
         if (dx == 0) x = w[r][1];
@@ -241,8 +243,9 @@ __device__ __forceinline__ unsigned fast_m4(const unsigned (&w)[7][3], unsigned 
         else x = __byte_perm(w[r][0], w[r][1], 0x3210 + 0x1111 * (4 + dx));
         pe[k] = __byte_perm(x, 0, 0x4240);  // pixels 0 and 2 as u16x2
         po[k] = __byte_perm(x, 0, 0x4341);  // pixels 1 and 3
-    }
-    const unsigned ve = __byte_perm(w[3][1], 0, 0x4240), vo = __byte_perm(w[3][1], 0, 0x4341);
+    };
+#pragma unroll
+    for (int k = 0; k < 16; ++k) extract(k);
     unsigned res[2];
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
