@@ -1075,9 +1075,17 @@ struct Solver {
     LmCtl* h_ctl = nullptr;       // pinned mirror of the device control block
     int* h_abort = nullptr;       // pinned, device-visible mirror of the caller's force_stop flag
     int* d_abort = nullptr;
+    int chol_cluster = kCholCluster;  // CTAs sharing one factorisation (B200_LBA_CLUSTER overrides: 1, 2, 4 or 8)
     bool host_loop = true;        // false (B200_LBA_GRAPH=1): run the LM loop as one conditional CUDA graph
-    // (a blocking-sync event wait instead of this spin-wait measured slightly slower with 16 windows in flight on a 16-core host)
-    cudaError_t wait(cudaStream_t st) { return cudaStreamSynchronize(st); }
+    // Waiting for the stream: spinning (cudaStreamSynchronize) has the lowest latency for one window; with many windows in flight on
+    // a host with few cores the spinners starve the thread that feeds the front end, so B200_LBA_WAIT=block parks the thread on a
+    // blocking-sync event instead (default chosen in b200_lba_create).
+    bool block_wait = false;
+    cudaError_t wait(cudaStream_t st) {
+        if (!block_wait) return cudaStreamSynchronize(st);
+        cudaError_t e = cudaEventRecord(ev_sync, st);
+        return e != cudaSuccess ? e : cudaEventSynchronize(ev_sync);
+    }
 
     int ensure(size_t dev_bytes, size_t host_bytes, size_t res_doubles) {
         if (dev_bytes > arena_cap) {
@@ -1358,13 +1366,13 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
                 (const int*)(d + o_empty), n_empty, (int*)(d + o_blkdone), Hpp, bp, Hs, n, ld);
         {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(kCholCluster);
+            cfg.gridDim = dim3(S.chol_cluster);
             cfg.blockDim = dim3(kCholThreads);
             cfg.dynamicSmemBytes = chol_smem;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = kCholCluster;
+            attr[0].val.clusterDim.x = S.chol_cluster;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
@@ -1560,11 +1568,15 @@ int b200_lba_create(int device, b200_lba_t* out) {
     b200_lba_s* h = new (std::nothrow) b200_lba_s();
     if (!h) return B200_ERR_INVALID;
     h->s.device = device;
-    // local BA is a long chain of small dependent launches: give it the highest stream priority so its CTAs are not queued
-    // behind the wide front-end kernels that share the GPU (the mapping thread runs next to tracking, mapping_module.cc:63)
+    // Local BA is the mapping thread's work (mapping_module.cc:63): tracking must not wait for it.  Its ~130 small launches per
+    // window are latency-bound (each one leaves most SMs idle), so on the highest stream priority every one of them pre-empts the wide
+    // front-end grids for its whole duration (measured: FAST 2.0 -> 2.9 ms per 64 frames with four windows in flight); on the lowest
+    // priority its CTAs fill the gaps instead.  B200_LBA_PRIORITY=high|normal|low overrides.
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    cudaError_t e = cudaStreamCreateWithPriority(&h->s.stream, cudaStreamNonBlocking, prio_hi);
+    int prio = prio_lo;
+    if (const char* pe = getenv("B200_LBA_PRIORITY")) prio = (pe[0] == 'l') ? prio_lo : ((pe[0] == 'n') ? 0 : prio_hi);
+    cudaError_t e = cudaStreamCreateWithPriority(&h->s.stream, cudaStreamNonBlocking, prio);
     if (e == cudaSuccess) e = cudaEventCreate(&h->s.ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->s.ev1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->s.ev_sync, cudaEventBlockingSync | cudaEventDisableTiming);
@@ -1574,6 +1586,11 @@ int b200_lba_create(int device, b200_lba_t* out) {
     // The conditional-graph driver is opt-in (B200_LBA_GRAPH=1): it is parity-green and slightly faster for one window at a time
     // (4.55 vs 4.94 ms GPU time), but four or more instances executing such graphs concurrently crashed inside driver 580.159
     // (tools/lba_conc.py), and concurrent windows are the normal case here.
+    if (const char* cc = getenv("B200_LBA_CLUSTER")) {
+        const int c = atoi(cc);
+        if (c == 1 || c == 2 || c == 4 || c == 8) h->s.chol_cluster = c;
+    }
+    if (const char* w = getenv("B200_LBA_WAIT")) h->s.block_wait = w[0] == 'b';
     const char* gm = getenv("B200_LBA_GRAPH");
     h->s.host_loop = !(gm && gm[0] == '1');
     if (e != cudaSuccess) {
