@@ -279,6 +279,57 @@ __device__ __forceinline__ unsigned fast_m4(const unsigned (&w)[7][3], unsigned 
     return __byte_perm(res[0], res[1], 0x6240);  // bytes: px0, px1, px2, px3
 }
 
+// Candidate test for 4 pixels (exact superset of m > t_low).  Every 9-arc of the circle contains one pixel of each antipodal pair
+// {k, k+8}, hence   max_arcs min_arc p <= min_pairs max(p_k, p_k+8)   and   min_arcs max_arc p >= max_pairs min(p_k, p_k+8).
+// With the two compass pairs this bounds m from above; a pixel whose bound does not exceed t_low stores 0 without the arc
+// evaluation.  ~10 % of the pixels of a natural frame pass at t_low = 7, so the arcs are evaluated for those only (fast_score1).
+// Returns a 4-bit mask.
+__device__ __forceinline__ unsigned fast_candidates4(const unsigned (&w)[7][3], unsigned tlow2) {
+    const unsigned x0 = w[6][1], x8 = w[0][1];                                                          // (0, +3), (0, -3)
+    const unsigned x4 = __byte_perm(w[3][1], w[3][2], 0x6543), x12 = __byte_perm(w[3][0], w[3][1], 0x4321);  // (+3, 0), (-3, 0)
+    unsigned r[2];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const unsigned sel = half ? 0x4341u : 0x4240u;  // pixels (1, 3) / (0, 2) as u16x2
+        const unsigned p0 = __byte_perm(x0, 0, sel), p8 = __byte_perm(x8, 0, sel), p4 = __byte_perm(x4, 0, sel), p12 = __byte_perm(x12, 0, sel);
+        const unsigned v = __byte_perm(w[3][1], 0, sel);
+        const unsigned hi = __vminu2(__vmaxu2(p0, p8), __vmaxu2(p4, p12));
+        const unsigned lo = __vmaxu2(__vminu2(p0, p8), __vminu2(p4, p12));
+        // bound > t_low  <=>  hi > v + t_low  or  v > lo + t_low.  Only unsigned lane max and XOR: the signed packed subtract / relu
+        // forms of this test (vsub2 + vimax_s16x2_relu + viaddmax_s16x2_relu) came out wrong on sm_100a in this context (tools/fast_probe)
+        const unsigned vt = v + tlow2, lot = lo + tlow2;  // lanes <= 510: no carry between them
+        r[half] = (__vmaxu2(hi, vt) ^ vt) | (__vmaxu2(v, lot) ^ lot);
+    }
+    return ((r[0] & 0xFFFFu) ? 1u : 0u) | ((r[1] & 0xFFFFu) ? 2u : 0u) | ((r[0] >> 16) ? 4u : 0u) | ((r[1] >> 16) ? 8u : 0u);
+}
+
+// Exact FAST-9/16 score of ONE pixel at tile position p (same definition as fast_m4, scalar 3-input min/max): max(m - t_low, 0).
+__device__ __forceinline__ int fast_score1(const unsigned char* __restrict__ p, int t_low) {
+    constexpr int OFF[16] = {3 * kTilePitch,     3 * kTilePitch + 1,  2 * kTilePitch + 2,  kTilePitch + 3,  3,  -kTilePitch + 3, -2 * kTilePitch + 2, -3 * kTilePitch + 1,
+                             -3 * kTilePitch,    -3 * kTilePitch - 1, -2 * kTilePitch - 2, -kTilePitch - 3, -3, kTilePitch - 3,  2 * kTilePitch - 2,  3 * kTilePitch - 1};
+    int c[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) c[k] = p[OFF[k]];
+    const int v = p[0];
+    int mx3[16], mn3[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        mx3[k] = __vimax3_s32(c[k], c[(k + 1) & 15], c[(k + 2) & 15]);
+        mn3[k] = __vimin3_s32(c[k], c[(k + 1) & 15], c[(k + 2) & 15]);
+    }
+    int a = 255, b = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        a = min(a, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));  // min over arcs of the arc maximum
+        b = max(b, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));  // max over arcs of the arc minimum
+    }
+    // max(m - t_low, 0) with m = max(v - a, b - v, 0).  The dark and the bright excess cannot both be positive (two 9-arcs of a
+    // 16-circle share pixels), so the result is their sum: no max of a difference is formed, which keeps ptxas from emitting
+    // VIADDMNMX with a negated addend (measured wrong on sm_100a, like the VIMNMX3 case in DESIGN.md).
+    const int at = a + t_low, vt = v + t_low;
+    return (max(v, at) - at) + (max(b, vt) - vt);
+}
+
 constexpr int kFastThreads = 256;
 constexpr int kTileRows = kTileMax + 2;  // 72
 constexpr int kRawPitch = 96;            // TMA box width: the box must start on a 16-byte boundary of the row (x0 = 16 + 64 j),
@@ -298,6 +349,8 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     __shared__ __align__(128) unsigned char raw[kUseTma ? kTileRows * kRawPitch : 16];  // TMA landing zone
     __shared__ __align__(8) unsigned long long tma_bar;
     __shared__ int skip;
+    __shared__ unsigned short cand[(kTileMax - 6) * (kTileMax - 6)];  // (row << 8 | tile column) of the pixels that need the arc evaluation
+    __shared__ int n_cand;
 
     const CellDesc cd = cells[blockIdx.x];
     const int frame = blockIdx.y;
@@ -314,6 +367,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
                 || mask_zero(mask, mask_pitch, cd.min_y, max_x, L.sf) || mask_zero(mask, mask_pitch, max_y, max_x, L.sf);
         }
         skip = s;
+        n_cand = 0;
     }
     if constexpr (kUseTma) {
         // one elected thread: arm the mbarrier with the tile's byte count and issue the bulk-tensor copy of the 80 x 72 box
@@ -358,7 +412,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
 
     const int t_low = min(g.ini_thr, g.min_thr);
     const unsigned neg_tlow2 = (unsigned)((-t_low) & 0xFFFF) * 0x10001u;
-    // phase 1: score map.  thread = (word column wq, group of 4 rows); candidate columns lx in [3, cw-4] <=> tile column lx+1
+    // phase 1a: candidate test.  thread = (word column wq, group of 4 rows); candidate columns lx in [3, cw-4] <=> tile column lx+1
     {
         const int wq = tid & 15, rg = tid >> 4;       // 16 word columns x 16 row groups
         const int c0 = 4 + 4 * wq;                    // tile column of the first pixel of the word
@@ -376,11 +430,11 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
             }
             // pixels of this word that are candidates: lx0 + b <= cw - 4
             const int nvalid = min(4, cw - 3 - lx0);
-            const unsigned keep = (nvalid >= 4) ? 0xFFFFFFFFu : ((1u << (8 * nvalid)) - 1u);
+            const unsigned keep = (1u << nvalid) - 1u;
+            unsigned bits = 0;  // 4 rows x 4 pixels
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const int y = y0 + i;
-                if (y <= ch - 4) {
+                if (y0 + i <= ch - 4) {
                     unsigned ww[7][3];
 #pragma unroll
                     for (int r = 0; r < 7; ++r) {
@@ -388,9 +442,26 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
                         ww[r][1] = w[i + r][1];
                         ww[r][2] = w[i + r][2];
                     }
-                    *reinterpret_cast<unsigned*>(mmap + y * kTilePitch + c0) = fast_m4(ww, neg_tlow2) & keep;
+                    bits |= (fast_candidates4(ww, (unsigned)t_low * 0x10001u) & keep) << (4 * i);
                 }
             }
+            if (bits) {
+                int pos = atomicAdd(&n_cand, __popc(bits));
+                while (bits) {
+                    const int k = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    cand[pos++] = (unsigned short)(((y0 + (k >> 2)) << 8) | (c0 + (k & 3)));
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // phase 1b: exact score of the candidates (the score map is zero everywhere else)
+    {
+        const int n = n_cand;
+        for (int i = tid; i < n; i += kFastThreads) {
+            const int e = cand[i], y = e >> 8, c = e & 0xFF;
+            mmap[y * kTilePitch + c] = (unsigned char)fast_score1(tile + y * kTilePitch + c, t_low);
         }
     }
     __syncthreads();
