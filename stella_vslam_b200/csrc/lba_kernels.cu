@@ -1130,6 +1130,9 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
                  double* points_out, uint8_t* outlier_out, b200_lba_stats_t* stats) {
     const int K = P->n_poses, L = P->n_points, E = P->n_edges;
     if (stats) std::memset(stats, 0, sizeof(*stats));
+    const bool debug = getenv("B200_LBA_DEBUG") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
     // ---- flatten / sort on the host ------------------------------------------------------------------------------
     std::vector<int> pose_col(K), pt_col(L);
     int Kf = 0, Lf = 0;
@@ -1177,35 +1180,56 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     }
     // Schur pair list grouped by upper block (i <= j)
     const int n_blocks = Kf * (Kf + 1) / 2;
-    auto block_id = [Kf](int i, int j) { return i * Kf - i * (i - 1) / 2 + (j - i); };
+    // one pass over the landmarks lists every (a, c) with its block; a counting sort by block then gives the grouped list.  A
+    // keyframe observes a landmark once, so a landmark contributes at most one pair to a block and the pairs of a block stay in
+    // landmark order whatever the order inside a landmark: its free-keyframe edges are sorted by column first and only the
+    // upper-triangular combinations are formed.
     std::vector<int> blk_count(n_blocks + 1, 0);
+    size_t pair_bound = 0;
+    for (int l = 0; l < L; ++l) {
+        const size_t m = (size_t)(pt_start[l + 1] - pt_start[l]);
+        pair_bound += m * (m + 1) / 2;
+    }
+    std::vector<int2> gen_pairs(pair_bound + 1);
+    std::vector<int> gen_block(pair_bound + 1);
+    size_t n_gen = 0;
+    std::vector<int> loc_col, loc_idx;
     for (int l = 0; l < L; ++l) {
         if (pt_col[l] < 0) continue;
+        loc_col.clear();
+        loc_idx.clear();
         for (int a = pt_start[l]; a < pt_start[l + 1]; ++a) {
-            if (edges[a].pcol < 0) continue;
-            for (int c = pt_start[l]; c < pt_start[l + 1]; ++c) {
-                if (edges[c].pcol < 0 || edges[c].pcol < edges[a].pcol) continue;
-                if (edges[c].pcol == edges[a].pcol && c != a) continue;  // a keyframe observes a landmark once
-                blk_count[block_id(edges[a].pcol, edges[c].pcol) + 1]++;
+            const int pa = edges[a].pcol;
+            if (pa < 0) continue;
+            size_t pos = loc_col.size();  // insertion sort by column (a handful of entries)
+            loc_col.push_back(pa);
+            loc_idx.push_back(a);
+            while (pos > 0 && loc_col[pos - 1] > pa) {
+                loc_col[pos] = loc_col[pos - 1];
+                loc_idx[pos] = loc_idx[pos - 1];
+                --pos;
+            }
+            loc_col[pos] = pa;
+            loc_idx[pos] = a;
+        }
+        const int m = (int)loc_col.size();
+        for (int x = 0; x < m; ++x) {
+            const int pa = loc_col[x];
+            const int row = pa * Kf - pa * (pa - 1) / 2 - pa;  // block_id(pa, pc) = row + pc
+            for (int y = x; y < m; ++y) {
+                const int bid = row + loc_col[y];
+                gen_pairs[n_gen] = make_int2(loc_idx[x], loc_idx[y]);
+                gen_block[n_gen++] = bid;
+                blk_count[bid + 1]++;
             }
         }
     }
-    for (int b = 0; b < n_blocks; ++b) blk_count[b + 1] += blk_count[b];
+    for (int b2 = 0; b2 < n_blocks; ++b2) blk_count[b2 + 1] += blk_count[b2];
     const int n_pairs = blk_count[n_blocks];
     std::vector<int2> pairs(std::max(1, n_pairs));
     {
         std::vector<int> fill(blk_count.begin(), blk_count.end() - 1);
-        for (int l = 0; l < L; ++l) {
-            if (pt_col[l] < 0) continue;
-            for (int a = pt_start[l]; a < pt_start[l + 1]; ++a) {
-                if (edges[a].pcol < 0) continue;
-                for (int c = pt_start[l]; c < pt_start[l + 1]; ++c) {
-                    if (edges[c].pcol < 0 || edges[c].pcol < edges[a].pcol) continue;
-                    if (edges[c].pcol == edges[a].pcol && c != a) continue;
-                    pairs[fill[block_id(edges[a].pcol, edges[c].pcol)]++] = make_int2(a, c);
-                }
-            }
-        }
+        for (int i = 0; i < n_pairs; ++i) pairs[fill[gen_block[i]]++] = gen_pairs[i];
     }
     std::vector<SchurBlock> blocks(std::max(1, n_blocks));
     std::vector<SchurChunk> chunks;
@@ -1245,6 +1269,7 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
         cams[i] = Cam{c.model, c.fx, c.fy, c.cx, c.cy, c.fxb, c.cols, c.rows};
     }
 
+    if (debug) fprintf(stderr, "[lba] host plan %.3f ms (E = %d, pairs = %d, chunks = %d)\n", ms_since(t_begin), E, n_pairs, n_chunks);
     // ---- device arena ----------------------------------------------------------------------------------------------
     const int n = 6 * Kf;
     const int eb = ceil_div(std::max(E, 1), kEdgeThreads), lb = ceil_div(std::max(L, 1), 128), lb2 = ceil_div(std::max(L, 1), 16);
@@ -1294,6 +1319,7 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     put(o_Rt0, Rt0.data(), sizeof(double) * 12 * K);
     put(o_pts0, P->points, sizeof(double) * 3 * (size_t)L);
     put(o_empty, empty_blocks.data(), sizeof(int) * n_empty);
+    if (debug) fprintf(stderr, "[lba] host plan + staging %.3f ms (upload %.2f MB)\n", ms_since(t_begin), upload_bytes / 1e6);
     unsigned char* d = S.d_arena;
     cudaStream_t st = S.stream;
     int launches = 0;
