@@ -6,6 +6,7 @@
 //   b200::feature::orb_params      <->  stella_vslam::feature::orb_params      (feature/orb_params.h:11-54)
 //   b200::feature::orb_extractor   <->  stella_vslam::feature::orb_extractor   (feature/orb_extractor.h:46-122)
 //   b200::match::robust            <->  stella_vslam::match::robust            (match/robust.h, match/base.h:81-91)
+//   b200::match::projection / fuse / area / bow_tree / stereo  <->  match/projection.h, fuse.h, area.h, bow_tree.h, stereo.h
 //   b200::optimize::local_bundle_adjuster <-> stella_vslam::optimize::local_bundle_adjuster (optimize/local_bundle_adjuster.h:15-24)
 #pragma once
 
@@ -163,8 +164,140 @@ public:
         return (unsigned int)n;
     }
 
+    // match_for_triangulation (match/robust.cc:14-146): the problem carries bearings, E_12, the epipole and the "has no landmark"
+    // masks; returns matched_idx_pairs sorted by idx_1.
+    unsigned int match_for_triangulation(b200_pairs_problem_t& problem, std::vector<std::pair<unsigned int, unsigned int>>& matched_idx_pairs) const {
+        return run_pairs(h_, problem, B200_PAIRS_TRIANGULATION, lowe_ratio_, check_orientation_, matched_idx_pairs);
+    }
+    b200_matcher_t handle() const { return h_; }
+
+    static unsigned int run_pairs(b200_matcher_t h, b200_pairs_problem_t& problem, int variant, float lowe_ratio, bool check_orientation,
+                                  std::vector<std::pair<unsigned int, unsigned int>>& out) {
+        std::vector<int32_t> match((size_t)(problem.n1 > 0 ? problem.n1 : 1), -1);
+        problem.match_out = match.data();
+        check(b200_match_pairs(h, 1, &problem, variant, lowe_ratio, check_orientation ? 1 : 0, 0), "b200_match_pairs");
+        out.clear();
+        for (int i = 0; i < problem.n1; ++i)
+            if (match[i] >= 0) out.emplace_back((unsigned int)i, (unsigned int)match[i]);
+        problem.match_out = nullptr;
+        return (unsigned int)problem.n_matches;
+    }
+
 private:
     b200_matcher_t h_ = nullptr;
+};
+
+// One matcher handle (stream + staging) shared by the guided / all-pairs / stereo mirrors below.
+class device_matcher {
+public:
+    explicit device_matcher(int device = 0) { check(b200_matcher_create(device, &h_), "b200_matcher_create"); }
+    ~device_matcher() { b200_matcher_destroy(h_); }
+    device_matcher(const device_matcher&) = delete;
+    device_matcher& operator=(const device_matcher&) = delete;
+    b200_matcher_t get() const { return h_; }
+
+private:
+    b200_matcher_t h_ = nullptr;
+};
+
+// match::projection (match/projection.h:24-67).  The adapter fills one b200_guided_problem_t per call (landmarks in the reference's
+// order, reprojected; see reference_adapters/projection_b200.cc); match_out / n_matches come back in the struct.
+class projection final : public base {
+public:
+    explicit projection(float lowe_ratio = 0.6f, bool check_orientation = true, int device = 0) : base(lowe_ratio, check_orientation), m_(device) {}
+    unsigned int match_frame_and_landmarks(b200_guided_problem_t& p) const { return run(p, B200_GUIDED_LANDMARKS, HAMMING_DIST_THR_HIGH, false); }
+    unsigned int match_current_and_last_frames(b200_guided_problem_t& p) const {
+        return run(p, B200_GUIDED_LAST_FRAME, HAMMING_DIST_THR_HIGH, check_orientation_);
+    }
+    unsigned int match_frame_and_keyframe(b200_guided_problem_t& p, unsigned int hamm_dist_thr) const {
+        return run(p, B200_GUIDED_LAST_FRAME, hamm_dist_thr, check_orientation_);
+    }
+    unsigned int match_by_Sim3_transform(b200_guided_problem_t& p) const { return run(p, B200_GUIDED_LAST_FRAME, HAMMING_DIST_THR_LOW, false); }
+    // match_keyframes_mutually: p12 = landmarks of keyframe 1 searched in keyframe 2, p21 the other direction; mutual[i] = idx_2 or -1
+    unsigned int match_keyframes_mutually(b200_guided_problem_t& p12, b200_guided_problem_t& p21, std::vector<int32_t>& mutual) const {
+        b200_guided_problem_t both[2] = {p12, p21};
+        check(b200_match_guided(m_.get(), 2, both, B200_GUIDED_INDEPENDENT, HAMMING_DIST_THR_HIGH, lowe_ratio_, 0, 0), "b200_match_guided");
+        mutual.assign((size_t)(p12.n_queries > 0 ? p12.n_queries : 1), -1);
+        int32_t n = 0;
+        check(b200_match_cross_check(p12.match_out, p12.n_queries, p21.match_out, p21.n_queries, mutual.data(), &n), "b200_match_cross_check");
+        mutual.resize((size_t)p12.n_queries);
+        return (unsigned int)n;
+    }
+
+private:
+    unsigned int run(b200_guided_problem_t& p, int mode, unsigned int thr, bool orientation) const {
+        check(b200_match_guided(m_.get(), 1, &p, mode, thr, lowe_ratio_, orientation ? 1 : 0, 0), "b200_match_guided");
+        return (unsigned int)p.n_matches;
+    }
+    device_matcher m_;
+};
+
+class fuse final : public base {  // match/fuse.h, fuse.cc:12-154
+public:
+    explicit fuse(float lowe_ratio = 0.6f, bool check_orientation = true, int device = 0) : base(lowe_ratio, check_orientation), m_(device) {}
+    unsigned int detect_duplication(b200_guided_problem_t& p) const {
+        check(b200_match_guided(m_.get(), 1, &p, B200_GUIDED_FUSE, HAMMING_DIST_THR_LOW, lowe_ratio_, 0, 0), "b200_match_guided");
+        return (unsigned int)p.n_matches;
+    }
+
+private:
+    device_matcher m_;
+};
+
+class area final : public base {  // match/area.h, area.cc:8-98
+public:
+    explicit area(float lowe_ratio = 0.9f, bool check_orientation = true, int device = 0) : base(lowe_ratio, check_orientation), m_(device) {}
+    unsigned int match_in_consistent_area(b200_guided_problem_t& p) const {
+        check(b200_match_guided(m_.get(), 1, &p, B200_GUIDED_AREA, HAMMING_DIST_THR_LOW, lowe_ratio_, check_orientation_ ? 1 : 0, 0), "b200_match_guided");
+        return (unsigned int)p.n_matches;
+    }
+
+private:
+    device_matcher m_;
+};
+
+class bow_tree final : public base {  // match/bow_tree.h, bow_tree.cc:11-366 (node1 / node2 = BoW node of every keypoint)
+public:
+    explicit bow_tree(float lowe_ratio = 0.6f, bool check_orientation = true, int device = 0) : base(lowe_ratio, check_orientation), m_(device) {}
+    unsigned int match_for_triangulation(b200_pairs_problem_t& p, std::vector<std::pair<unsigned int, unsigned int>>& matched_idx_pairs) const {
+        return robust::run_pairs(m_.get(), p, B200_PAIRS_TRIANGULATION, lowe_ratio_, check_orientation_, matched_idx_pairs);
+    }
+    // match_frame_and_keyframe / match_keyframes: (row, candidate) pairs; the adapter maps them to matched_lms_in_frm / _in_keyfrm_1
+    unsigned int match_frame_and_keyframe(b200_pairs_problem_t& p, std::vector<std::pair<unsigned int, unsigned int>>& pairs) const {
+        return robust::run_pairs(m_.get(), p, B200_PAIRS_BOW, lowe_ratio_, check_orientation_, pairs);
+    }
+    unsigned int match_keyframes(b200_pairs_problem_t& p, std::vector<std::pair<unsigned int, unsigned int>>& pairs) const {
+        return robust::run_pairs(m_.get(), p, B200_PAIRS_BOW, lowe_ratio_, check_orientation_, pairs);
+    }
+
+private:
+    device_matcher m_;
+};
+
+// match::stereo (match/stereo.h:17-101): built from the two extractors whose pyramids stay on the device (system.cc:443)
+class stereo {
+public:
+    stereo(const feature::orb_extractor& left, const feature::orb_extractor& right, const std::vector<b200_keypoint_t>& keypts_left,
+           const std::vector<b200_keypoint_t>& keypts_right, const std::vector<uint8_t>& descs_left, const std::vector<uint8_t>& descs_right,
+           float focal_x_baseline, float true_baseline, int frame_left = 0, int frame_right = 0, int device = 0)
+        : left_(left), right_(right), kl_(keypts_left), kr_(keypts_right), dl_(descs_left), dr_(descs_right), fxb_(focal_x_baseline),
+          baseline_(true_baseline), fl_(frame_left), fr_(frame_right), m_(device) {}
+    void compute(std::vector<float>& stereo_x_right, std::vector<float>& depths) const {
+        stereo_x_right.assign(kl_.size(), -1.0f);
+        depths.assign(kl_.size(), -1.0f);
+        int32_t n = 0;
+        check(b200_stereo_compute(m_.get(), left_.handle(), fl_, right_.handle(), fr_, kl_.data(), dl_.data(), (int)kl_.size(), kr_.data(), dr_.data(),
+                                  (int)kr_.size(), fxb_, baseline_, stereo_x_right.data(), depths.data(), &n),
+              "b200_stereo_compute");
+    }
+
+private:
+    const feature::orb_extractor &left_, &right_;
+    const std::vector<b200_keypoint_t>&kl_, &kr_;
+    const std::vector<uint8_t>&dl_, &dr_;
+    float fxb_, baseline_;
+    int fl_, fr_;
+    device_matcher m_;
 };
 
 }  // namespace match
