@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(32) resolve_kernel(Side S1, Side S2, const uns
                                                      int* __restrict__ pairs_out, int* __restrict__ n_pairs, int use_smem) {
     const uint4* __restrict__ desc1 = S1.desc;
     const uint4* __restrict__ desc2 = S2.desc;
-    extern __shared__ __align__(16) unsigned resolve_smem[];  // [desc1 copy 32 B x n][angles][taken bitmap][idx_1 -> idx_2 table], as far as they fit
+    extern __shared__ __align__(16) unsigned resolve_smem[];  // [desc1 copy 32 B x n][angles][taken bitmap][idx_1 -> idx_2 table][claim table], as far as they fit
     const int p = blockIdx.x, lane = threadIdx.x;
     const int b1 = S1.off[p], n1 = S1.cnt[p];
     const int b2 = S2.off[p], n2 = S2.cnt[p];
@@ -238,10 +238,13 @@ __global__ void __launch_bounds__(32) resolve_kernel(Side S1, Side S2, const uns
     const int stage_words = (use_smem == 2) ? 9 * matched_stride : 0;  // 8 words of descriptor + 1 angle per keypoint
     unsigned* taken = use_smem ? resolve_smem + stage_words : taken_g + (size_t)p * taken_words;
     int* m21 = use_smem ? reinterpret_cast<int*>(resolve_smem + stage_words + taken_words) : matched + (size_t)p * matched_stride;
+    int* claim = use_smem ? reinterpret_cast<int*>(resolve_smem + stage_words + taken_words + matched_stride) : nullptr;
     int* pairs = pairs_out + 2 * (size_t)p * pairs_stride;
     lists += (size_t)p * list_rows * kTopK;
     for (int i = lane; i < (n1 + 31) / 32; i += 32) taken[i] = 0u;
     for (int i = lane; i < n1; i += 32) m21[i] = -1;
+    if (claim)
+        for (int i = lane; i < n1; i += 32) claim[i] = 255;
     __syncwarp();
     const uint4* d1 = desc1 + (size_t)b1 * 2;
     const unsigned char* a1p = S1.angle + (long long)b1 * S1.angle_stride;
@@ -276,12 +279,25 @@ __global__ void __launch_bounds__(32) resolve_kernel(Side S1, Side S2, const uns
             // conflicts with earlier accepting lanes of this round
             bool conflict = false;
             const unsigned my_best_idx = key_idx(best);
-            for (unsigned m = accept_mask; m; m &= m - 1) {
-                const int jl = __ffs(m) - 1;
-                const unsigned bj = __shfl_sync(0xFFFFFFFFu, my_best_idx, jl);
-                if (mine && lane > jl) {
+            if (claim) {
+                // claim[i] = lowest lane that accepts frame keypoint i this round; a lane conflicts when a lower lane claims any
+                // keypoint of its list (8 shared-memory probes instead of one shuffle round per accepting lane)
+                if (mine && st == 1) atomicMin(&claim[my_best_idx], lane);
+                __syncwarp();
+                if (mine) {
 #pragma unroll
-                    for (int k = 0; k < kTopK; ++k) conflict |= (keys[k] != kInfKey && key_idx(keys[k]) == bj);
+                    for (int k = 0; k < kTopK; ++k) conflict |= (keys[k] != kInfKey && claim[key_idx(keys[k])] < lane);
+                }
+                __syncwarp();
+                if (mine && st == 1) claim[my_best_idx] = 255;
+            } else {
+                for (unsigned m = accept_mask; m; m &= m - 1) {
+                    const int jl = __ffs(m) - 1;
+                    const unsigned bj = __shfl_sync(0xFFFFFFFFu, my_best_idx, jl);
+                    if (mine && lane > jl) {
+#pragma unroll
+                        for (int k = 0; k < kTopK; ++k) conflict |= (keys[k] != kInfKey && key_idx(keys[k]) == bj);
+                    }
                 }
             }
             const unsigned unsafe = __ballot_sync(0xFFFFFFFFu, mine && (conflict || st == 2));
@@ -963,7 +979,7 @@ struct Matcher {
         if ((rc = grow((void**)&d_matched, &matched_cap, sizeof(int) * (size_t)max_n1 * n_problems))) return rc;
         if ((rc = grow((void**)&d_taken, &taken_cap, sizeof(unsigned) * (size_t)taken_words * n_problems))) return rc;
         topk_kernel<<<dim3(row_blocks, n_problems), kRowsPerBlock, 0, stream>>>(S1, S2, (const unsigned char*)valid2, check_ori, d_lists);
-        const size_t state_bytes = sizeof(unsigned) * ((size_t)taken_words + (size_t)max_n1);
+        const size_t state_bytes = sizeof(unsigned) * ((size_t)taken_words + 2 * (size_t)max_n1);  // taken bitmap, idx_1 -> idx_2 table, claim table
         const size_t stage_bytes = sizeof(unsigned) * 9 * (size_t)max_n1;
         const int use_smem = (state_bytes + stage_bytes <= 200 * 1024) ? 2 : (state_bytes <= 200 * 1024 ? 1 : 0);
         const size_t rs_bytes = use_smem == 2 ? state_bytes + stage_bytes : state_bytes;
