@@ -18,6 +18,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <new>
+#include <sched.h>
+
 #include <chrono>
 #include <mutex>
 #include <thread>
@@ -1077,12 +1079,21 @@ struct Solver {
     int* d_abort = nullptr;
     int chol_cluster = kCholCluster;  // CTAs sharing one factorisation (B200_LBA_CLUSTER overrides: 1, 2, 4 or 8)
     bool host_loop = true;        // false (B200_LBA_GRAPH=1): run the LM loop as one conditional CUDA graph
-    // Waiting for the stream: spinning (cudaStreamSynchronize) has the lowest latency for one window; with many windows in flight on
-    // a host with few cores the spinners starve the thread that feeds the front end, so B200_LBA_WAIT=block parks the thread on a
-    // blocking-sync event instead (default chosen in b200_lba_create).
-    bool block_wait = false;
+    // Waiting for the stream (once per LM trial).  Windows are solved many at a time by as many host threads; measured on a 16-core
+    // quota with 16 windows in flight next to the front end: spinning in cudaStreamSynchronize gives the best median but starves
+    // the thread that feeds the front end every few runs (frames/s halved), a blocking-sync event costs 10-25 %, polling the stream
+    // with a 15 us nap in between is within 2 % of spinning and never collapsed.  B200_LBA_WAIT=spin|block|yield|nap overrides.
+    int wait_mode = 3;  // 0 spin (cudaStreamSynchronize), 1 blocking event, 2 poll + sched_yield, 3 poll + 15 us sleep
     cudaError_t wait(cudaStream_t st) {
-        if (!block_wait) return cudaStreamSynchronize(st);
+        if (wait_mode == 0) return cudaStreamSynchronize(st);
+        if (wait_mode >= 2) {
+            cudaError_t e;
+            while ((e = cudaStreamQuery(st)) == cudaErrorNotReady) {
+                if (wait_mode == 2) sched_yield();
+                else std::this_thread::sleep_for(std::chrono::microseconds(15));
+            }
+            return e;
+        }
         cudaError_t e = cudaEventRecord(ev_sync, st);
         return e != cudaSuccess ? e : cudaEventSynchronize(ev_sync);
     }
@@ -1616,7 +1627,7 @@ int b200_lba_create(int device, b200_lba_t* out) {
         const int c = atoi(cc);
         if (c == 1 || c == 2 || c == 4 || c == 8) h->s.chol_cluster = c;
     }
-    if (const char* w = getenv("B200_LBA_WAIT")) h->s.block_wait = w[0] == 'b';
+    if (const char* w = getenv("B200_LBA_WAIT")) h->s.wait_mode = w[0] == 'b' ? 1 : (w[0] == 'y' ? 2 : (w[0] == 'n' ? 3 : 0));  // spin | block | yield | nap
     const char* gm = getenv("B200_LBA_GRAPH");
     h->s.host_loop = !(gm && gm[0] == '1');
     if (e != cudaSuccess) {
