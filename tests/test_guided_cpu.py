@@ -172,3 +172,14 @@ def test_oracle_guided_empty():
                    q_max_level=np.zeros(0), q_angle=np.zeros(0), q_valid=np.zeros(0))
     got, occ, n = O.match_guided(empty_q, 0)
     assert n == 0 and len(got) == 0 and np.array_equal(occ, pr["t_occupied"])
+
+
+def test_library_cross_check_matches_oracle_without_gpu():
+    """b200_match_cross_check is host-side glue (the closing loop of match_keyframes_mutually): same answer as the oracle, no device."""
+    from stella_vslam_b200 import match
+    rng = np.random.default_rng(4)
+    a = rng.integers(-1, 50, 200).astype(np.int32)
+    b = rng.integers(-1, 200, 50).astype(np.int32)
+    got, n = match.cross_check(a, b)
+    want, n_want = O.cross_check(a, b)
+    assert np.array_equal(got, want) and n == n_want
