@@ -312,6 +312,16 @@ int b200_lba_destroy(b200_lba_t h);
  * pose_cw_out: K x 16, points_out: L x 3, outlier_out: E (1 = observation to erase, :354-375). */
 int b200_lba_solve(b200_lba_t h, const b200_lba_problem_t* problem, int iters1, int iters2, volatile uint8_t* force_stop,
                    double* pose_cw_out, double* points_out, uint8_t* outlier_out, b200_lba_stats_t* stats);
+/* optimize::pose_optimizer::optimize  (src/stella_vslam/optimize/pose_optimizer.h:24-40, pose_optimizer_g2o.cc:38-175; factory
+ * defaults num_trials_robust = 2, num_trials = 2, num_each_iter = 10, pose_optimizer_factory.h:18-47): motion-only bundle adjustment
+ * of `n_problems` frames in one launch.  Each problem uses the b200_lba_problem_t layout with exactly ONE pose (free), the landmarks
+ * the frame observes (all fixed) and one edge per observation (e_pose = 0; e_obs = undistorted x, y, x_right (< 0: monocular edge);
+ * e_inv_sigma_sq = inv_level_sigma_sq_[octave]; e_delta = sqrt(chi-square), :84-88); one camera per problem.
+ * Out: pose_cw_out [n_problems][16] row-major (the input pose when a frame has fewer than 5 observations, :116-118),
+ * outlier_flags = the problems' edges concatenated (outlier_flags.at(idx), :141-160), n_valid[p] = num_init_obs - num_bad_obs. */
+int b200_pose_optimize(b200_lba_t h, int n_problems, const b200_lba_problem_t* problems, int num_trials_robust, int num_trials,
+                       int num_each_iter, double* pose_cw_out, uint8_t* outlier_flags, uint32_t* n_valid);
+
 /* Device time (ms, CUDA events) spent in the kernels of the last solve, and the number of kernel launches. */
 int b200_lba_last_profile(b200_lba_t h, float* gpu_ms, int* launches);
 

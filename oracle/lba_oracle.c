@@ -484,11 +484,8 @@ static int optimize_rounds(lba_t* S, int iterations, volatile uint8_t* stop, orc
     return it;
 }
 
-int orc_lba_solve(const orc_lba_problem_t* P, int iters1, int iters2, volatile uint8_t* force_stop, double* pose_cw_out,
-                  double* points_out, uint8_t* outlier_out, orc_lba_stats_t* stats) {
-    /* local_bundle_adjuster_g2o.cc:308-310 */
-    if (force_stop && *force_stop) return 1;
-    lba_t S;
+static void state_init(lba_t* Sp, const orc_lba_problem_t* P) {
+#define S (*Sp)
     memset(&S, 0, sizeof(S));
     S.P = P;
     const int K = P->n_poses, L = P->n_points, E = P->n_edges;
@@ -518,6 +515,28 @@ int orc_lba_solve(const orc_lba_problem_t* P, int iters1, int iters2, volatile u
     S.Hpl = (double*)calloc(18 * (size_t)(E ? E : 1), sizeof(double));
     S.xp = (double*)calloc(6 * (size_t)(S.nfp ? S.nfp : 1), sizeof(double));
     S.xl = (double*)calloc(3 * (size_t)(S.nfl ? S.nfl : 1), sizeof(double));
+#undef S
+}
+static void state_free(lba_t* S) {
+    free(S->q); free(S->t); free(S->pts); free(S->pose_col); free(S->pt_col); free(S->level); free(S->robust); free(S->err);
+    free(S->Hpp); free(S->bp); free(S->Hll); free(S->bl); free(S->Hpl); free(S->xp); free(S->xl);
+}
+static void pose_to_mat(const lba_t* S, int k, double* M) { /* util::converter::to_eigen_mat(SE3Quat) */
+    double R[9];
+    quat_to_rot(S->q + 4 * k, R);
+    M[0] = R[0]; M[1] = R[1]; M[2] = R[2]; M[3] = S->t[3 * k];
+    M[4] = R[3]; M[5] = R[4]; M[6] = R[5]; M[7] = S->t[3 * k + 1];
+    M[8] = R[6]; M[9] = R[7]; M[10] = R[8]; M[11] = S->t[3 * k + 2];
+    M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
+}
+
+int orc_lba_solve(const orc_lba_problem_t* P, int iters1, int iters2, volatile uint8_t* force_stop, double* pose_cw_out,
+                  double* points_out, uint8_t* outlier_out, orc_lba_stats_t* stats) {
+    /* local_bundle_adjuster_g2o.cc:308-310 */
+    if (force_stop && *force_stop) return 1;
+    lba_t S;
+    state_init(&S, P);
+    const int K = P->n_poses, L = P->n_points, E = P->n_edges;
     if (stats) memset(stats, 0, sizeof(*stats));
 
     /* 5. first optimisation (:312-313) */
@@ -563,7 +582,44 @@ int orc_lba_solve(const orc_lba_problem_t* P, int iters1, int iters2, volatile u
         M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
     }
     memcpy(points_out, S.pts, sizeof(double) * 3 * L);
-    free(S.q); free(S.t); free(S.pts); free(S.pose_col); free(S.pt_col); free(S.level); free(S.robust); free(S.err);
-    free(S.Hpp); free(S.bp); free(S.Hll); free(S.bl); free(S.Hpl); free(S.xp); free(S.xl);
+    state_free(&S);
     return 0;
+}
+
+/* optimize::pose_optimizer_g2o::optimize (src/stella_vslam/optimize/pose_optimizer_g2o.cc:38-175) on a flattened frame: one free
+ * pose, the landmarks it observes (fixed), one unary edge per observation (internal/se3/perspective_pose_opt_edge.h,
+ * equirectangular_pose_opt_edge.h: the pose block of the corresponding reprojection edge), Huber(sqrt chi-square) on every edge.
+ * P must hold n_poses = 1 (free), every point fixed, e_pose = 0.  Returns num_init_obs - num_bad_obs (0 if fewer than 5 edges). */
+unsigned orc_pose_optimize(const orc_lba_problem_t* P, int num_trials_robust, int num_trials, int num_each_iter, double* pose_cw_out,
+                           uint8_t* outlier_flags) {
+    const int E = P->n_edges;
+    memcpy(pose_cw_out, P->pose_cw, sizeof(double) * 16);
+    for (int e = 0; e < E; ++e) outlier_flags[e] = 0;
+    if (E < 5) return 0; /* :116-118 */
+    lba_t S;
+    state_init(&S, P);
+    if (num_trials_robust == 0)
+        for (int e = 0; e < E; ++e) S.robust[e] = 0; /* :123-127 */
+    unsigned num_bad = 0;
+    for (int trial = 0; trial < num_trials_robust + num_trials; ++trial) {
+        optimize_rounds(&S, num_each_iter, NULL, NULL, 0); /* initializeOptimization (level-0 edges) + optimize(num_each_iter_) */
+        num_bad = 0;
+        for (int e = 0; e < E; ++e) {
+            if (outlier_flags[e]) edge_error(&S, e, S.err + 3 * e, NULL); /* :137-139: inactive edges are re-evaluated at the new pose */
+            const double thr = (edge_dim(P, e) == 2) ? (double)5.99146f : (double)7.81473f;
+            if (thr < edge_chi2(&S, e)) {
+                outlier_flags[e] = 1;
+                S.level[e] = 1;
+                ++num_bad;
+            } else {
+                outlier_flags[e] = 0;
+                S.level[e] = 0;
+            }
+            if (num_trials != 0 && trial + 1 == num_trials_robust) S.robust[e] = 0; /* :164-166 */
+        }
+        if ((unsigned)E - num_bad < 5) break; /* :169-171 */
+    }
+    pose_to_mat(&S, 0, pose_cw_out);
+    state_free(&S);
+    return (unsigned)E - num_bad;
 }

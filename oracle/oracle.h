@@ -167,6 +167,11 @@ typedef struct {
 int orc_lba_solve(const orc_lba_problem_t* P, int iters1, int iters2, volatile uint8_t* force_stop, double* pose_cw_out,
                   double* points_out, uint8_t* outlier_out, orc_lba_stats_t* stats);
 
+/* optimize::pose_optimizer_g2o::optimize (pose_optimizer_g2o.cc:38-175): motion-only BA of one frame.  P: one free pose, fixed
+ * points, one edge per observation.  Returns the number of inlier observations; outlier_flags[e] per edge. */
+unsigned orc_pose_optimize(const orc_lba_problem_t* P, int num_trials_robust, int num_trials, int num_each_iter, double* pose_cw_out,
+                           uint8_t* outlier_flags);
+
 /* timed CPU baseline driver (batch_oracle.c): n frames on n_threads pthreads, extract then match to predecessor */
 int orc_frontend_batch(const uint8_t* frames, int n_unique, int n, int w, int h, const orc_orb_config_t* cfg, int cap, float lowe,
                        int check_ori, int n_threads, int* counts, int* n_matches);

@@ -377,3 +377,15 @@ def lba_solve(prob, iters1=5, iters2=10, force_stop=None):
     rc = L_.orc_lba_solve(C.byref(P), iters1, iters2, _p(force_stop), _p(pose_out), _p(pts_out), _p(outl), C.byref(st))
     return dict(rc=rc, pose_cw=pose_out, points=pts_out, outliers=outl, iterations=list(st.iterations), n_outliers=st.n_outliers,
                 chi2=list(st.chi2), lambda_init=st.lambda_init, lambda_final=list(st.lambda_final))
+
+
+def pose_optimize(prob, num_trials_robust=2, num_trials=2, num_each_iter=10):
+    """orc_pose_optimize on a flattened frame (synth.make_pose_problem).  Returns (num_valid_obs, pose (4,4), outlier_flags bool)."""
+    P, keep = pack_lba_problem(prob)
+    pose = np.zeros((4, 4))
+    flags = np.zeros(max(P.n_edges, 1), np.uint8)
+    L = lib()
+    L.orc_pose_optimize.argtypes = [C.POINTER(LbaProblem), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_pose_optimize.restype = C.c_uint
+    n = L.orc_pose_optimize(C.byref(P), num_trials_robust, num_trials, num_each_iter, pose.ctypes.data, flags.ctypes.data)
+    return int(n), pose, flags[:P.n_edges].astype(bool)

@@ -37,6 +37,7 @@ def _bind():
     L.b200_lba_destroy.argtypes = [vp]
     L.b200_lba_solve.argtypes = [vp, C.POINTER(LbaProblem), C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(LbaStats)]
     L.b200_lba_last_profile.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    L.b200_pose_optimize.argtypes = [vp, C.c_int, C.POINTER(LbaProblem), C.c_int, C.c_int, C.c_int, vp, vp, vp]
     return L
 
 
@@ -116,6 +117,50 @@ class local_bundle_adjuster:
         return dict(pose_cw=pose_out, points=pts_out, outliers=outl, iterations=list(st.iterations), n_outliers=st.n_outliers,
                     chi2=list(st.chi2), lambda_init=st.lambda_init, lambda_final=list(st.lambda_final), gpu_ms=ms.value,
                     launches=launches.value)
+
+
+class pose_optimizer:
+    """optimize::pose_optimizer (optimize/pose_optimizer.h:24-40, pose_optimizer_g2o.{h,cc}; factory defaults
+    pose_optimizer_factory.h:18-47): motion-only BA of frames, one CUDA launch for a whole batch."""
+
+    def __init__(self, num_trials_robust=2, num_trials=2, num_each_iter=10, device=0):
+        self.num_trials_robust_, self.num_trials_, self.num_each_iter_ = int(num_trials_robust), int(num_trials), int(num_each_iter)
+        self._L = _bind()
+        self._h = C.c_void_p()
+        check(self._L.b200_lba_create(device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200_lba_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def optimize_batch(self, problems):
+        """problems: flattened frames (synth.make_pose_problem layout: one pose, fixed landmarks, one edge per observation).
+        Returns [(num_valid_obs, optimized_pose (4,4), outlier_flags (n,) bool)] like pose_optimizer::optimize (:38-44)."""
+        if not problems:
+            return []
+        packed = [pack_problem(pr) for pr in problems]
+        arr = (LbaProblem * len(problems))(*[pk[0] for pk in packed])
+        n_edges = [pk[0].n_edges for pk in packed]
+        pose = np.zeros((len(problems), 4, 4))
+        flags = np.zeros(max(sum(n_edges), 1), np.uint8)
+        valid = np.zeros(len(problems), np.uint32)
+        check(self._L.b200_pose_optimize(self._h, len(problems), arr, self.num_trials_robust_, self.num_trials_, self.num_each_iter_,
+                                         ptr(pose), ptr(flags), ptr(valid)))
+        out, off = [], 0
+        for i, ne in enumerate(n_edges):
+            out.append((int(valid[i]), pose[i].copy(), flags[off:off + ne].astype(bool)))
+            off += ne
+        return out
+
+    def optimize(self, problem):
+        return self.optimize_batch([problem])[0]
 
 
 def create(yaml_node=None, device=0):

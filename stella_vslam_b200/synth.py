@@ -224,6 +224,53 @@ def make_ba_problem(n_poses=50, n_fixed=10, n_points=10000, seed=0, model="stere
                 e_can_be_outlier=None, cams=[cam], gt_pose_cw=gt_pose, gt_points=pts)
 
 
+def make_pose_problem(seed=0, n_obs=1500, model="stereo", outlier_frac=0.1, pixel_sigma=1.0, rot_deg=1.0, trans_m=0.15):
+    """One frame for optimize::pose_optimizer in the flattened layout of b200_lba_problem_t: ONE free pose (perturbed), the
+    `n_obs` landmarks it observes (fixed, exact) and one edge per observation with level-dependent noise and gross outliers."""
+    rng = np.random.default_rng(seed)
+    equirect = model == "equirect"
+    cam = dict(model=1 if equirect else 0, fx=KITTI["fx"], fy=KITTI["fy"], cx=KITTI["cx"], cy=KITTI["cy"], fxb=KITTI["fxb"],
+               cols=3840.0 if equirect else float(KITTI["cols"]), rows=1920.0 if equirect else float(KITTI["rows"]))
+    Rcw = _rot_y(0.3 * rng.standard_normal()) @ _rodrigues(0.05 * rng.standard_normal(3))
+    tcw = rng.normal(0, 2.0, 3)
+    gt = np.eye(4)
+    gt[:3, :3], gt[:3, 3] = Rcw, tcw
+    depth = rng.uniform(4, 60, n_obs)
+    if equirect:
+        d = rng.standard_normal((n_obs, 3))
+        pc = d / np.linalg.norm(d, axis=1, keepdims=True) * depth[:, None]
+    else:
+        u, v = rng.uniform(20, cam["cols"] - 20, n_obs), rng.uniform(20, cam["rows"] - 20, n_obs)
+        pc = np.stack([(u - cam["cx"]) / cam["fx"] * depth, (v - cam["cy"]) / cam["fy"] * depth, depth], 1)
+    pw = (pc - tcw) @ Rcw                                # Rcw^T (pc - tcw)
+    inv_sigma = (np.float32(1.0) / np.cumprod(np.concatenate([[np.float32(1.0)], np.full(7, np.float32(1.2))])).astype(np.float32) ** 2).astype(np.float32)
+    lvl = rng.integers(0, 8, n_obs)
+    sig = pixel_sigma / np.sqrt(inv_sigma[lvl].astype(np.float64))
+    if equirect:
+        th, ph = np.arctan2(pc[:, 0], pc[:, 2]), -np.arcsin(pc[:, 1] / np.linalg.norm(pc, axis=1))
+        x, y = cam["cols"] * (0.5 + th / (2 * np.pi)), cam["rows"] * (0.5 - ph / np.pi)
+    else:
+        x, y = cam["fx"] * pc[:, 0] / pc[:, 2] + cam["cx"], cam["fy"] * pc[:, 1] / pc[:, 2] + cam["cy"]
+    xr = np.full(n_obs, -1.0)
+    if model == "stereo":
+        has = rng.random(n_obs) < 0.8
+        xr[has] = (x - cam["fxb"] / pc[:, 2] + sig * rng.standard_normal(n_obs))[has]
+        xr[xr < 0] = -1.0
+    x, y = x + sig * rng.standard_normal(n_obs), y + sig * rng.standard_normal(n_obs)
+    bad = rng.random(n_obs) < outlier_frac
+    x[bad] += rng.choice([-1, 1], bad.sum()) * rng.uniform(10, 60, bad.sum())
+    y[bad] += rng.choice([-1, 1], bad.sum()) * rng.uniform(10, 60, bad.sum())
+    dR = _rodrigues(np.deg2rad(rot_deg) * rng.standard_normal(3) / np.sqrt(3))
+    pose0 = np.eye(4)
+    pose0[:3, :3] = dR @ Rcw
+    pose0[:3, 3] = dR @ tcw + trans_m * rng.standard_normal(3) / np.sqrt(3)
+    chi = np.float32(np.sqrt(np.float32(7.81473))) if model == "stereo" else np.float32(np.sqrt(np.float32(5.99146)))  # setup-type dependent, :99-101
+    return dict(pose_cw=pose0[None], pose_fixed=np.zeros(1, np.uint8), points=pw, point_fixed=np.ones(n_obs, np.uint8),
+                e_pose=np.zeros(n_obs, np.int32), e_point=np.arange(n_obs, dtype=np.int32), e_cam=np.zeros(n_obs, np.uint8),
+                e_obs=np.stack([x, y, xr], 1).astype(np.float32), e_inv_sigma_sq=inv_sigma[lvl], e_delta=np.full(n_obs, chi, np.float32),
+                e_robust=None, e_can_be_outlier=None, cams=[cam], gt_pose_cw=gt, gt_outlier=bad)
+
+
 def make_guided_problem(seed, n_train=2000, n_queries=1500, mode=0, stereo=False, width=640, height=480, margin=5.0, num_levels=8,
                         scale_factor=1.2):
     """A synthetic problem for the grid-guided projection matchers (match.projection): a frame with `n_train` keypoints and
