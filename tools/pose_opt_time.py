@@ -4,7 +4,6 @@ sys.path.insert(0, ".")
 import ctypes as C
 import numpy as np
 from stella_vslam_b200 import optimize, synth
-from oracle import pyoracle as O
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 probs = [synth.make_pose_problem(k, n_obs=1500, model="stereo") for k in range(8)] * (B // 8)
 po = optimize.pose_optimizer()
@@ -12,5 +11,3 @@ po.optimize_batch(probs)
 t = time.perf_counter(); po.optimize_batch(probs); dt = time.perf_counter() - t
 ms = C.c_float(); po._L.b200_lba_last_profile(po._h, C.byref(ms), None)
 print(f"GPU: {B} frames x 1500 obs: wall {dt * 1e3:.2f} ms (incl. Python packing), kernel {ms.value:.3f} ms = {ms.value * 1e3 / B:.1f} us / frame")
-t = time.perf_counter(); [O.pose_optimize(p) for p in probs[:8]]; dt = time.perf_counter() - t
-print(f"CPU oracle: {dt * 1e3 / 8:.2f} ms / frame (1 core)")
