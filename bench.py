@@ -29,7 +29,7 @@ W, H = 1920, 1080
 TARGET_KPTS = 2000
 METRIC = "frames/sec (ORB+match+local BA) @1920x1080, 2000 kpts"
 LOWE, CHECK_ORI = 0.8, True  # robust matcher as constructed by frame_tracker (module/frame_tracker.cc:98)
-LBA_DEPTH = 4                 # local-BA windows stay in flight for up to this many steps (asynchronous mapping thread)
+LBA_DEPTH = int(os.environ.get("B200_BENCH_LBA_DEPTH", "4"))  # local-BA windows stay in flight for up to this many steps (asynchronous mapping thread)
 
 
 def parse_args():
