@@ -111,6 +111,22 @@ int b200_orb_pyramid_level_host(b200_orb_t h, int frame, int level, uint8_t* dst
 /* Every level including 0 (the caller's device image, or the upload staging of b200_orb_extract), with its pitch and size. */
 int b200_orb_pyramid_level_view(b200_orb_t h, int frame, int level, const uint8_t** d_ptr, size_t* pitch, int* width, int* height);
 
+/* The per-keypoint steps between extractor and matchers, for `n` keypoints in HOST buffers:
+ *   camera::perspective::undistort_keypoints     (src/stella_vslam/camera/perspective.cc:245-275: cv::undistortPoints with
+ *       TermCriteria(EPS | MAX_ITER, 20, 1e-6), R = I, P = K; also Perspective without distortion, e.g. KITTI)
+ *   camera::equirectangular::undistort_keypoints (the identity)
+ *   camera::base::convert_keypoints_to_bearings  (camera/base.cc:158-162; perspective.cc:117-122, equirectangular.cc:42-49)
+ * model: 0 perspective, 1 equirectangular.  undist_keypts (n) and bearings (n x 3 doubles) may each be NULL.
+ * Runs on the extractor's stream (after the extract whose keypoints it is given). */
+typedef struct {
+    int32_t model;
+    double fx, fy, cx, cy;
+    double k1, k2, p1, p2, k3; /* cv_dist_params_ */
+    double cols, rows;         /* equirectangular */
+} b200_camera_intrinsics_t;
+int b200_keypoints_undistort(b200_orb_t h, const b200_camera_intrinsics_t* cam, const b200_keypoint_t* keypts, int n,
+                             b200_keypoint_t* undist_keypts, double* bearings);
+
 /* Per-stage kernel time of the last extract, in ms, measured with CUDA events on the instance stream.
  * stage: 0 pyramid, 1 FAST+NMS+grid arg-max, 2 ordered selection, 3 descriptor blur, 4 orientation+rBRIEF, 5 whole extract. */
 int b200_orb_stage_ms(b200_orb_t h, int stage, float* ms);

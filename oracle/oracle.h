@@ -102,6 +102,12 @@ int orc_stereo_compute(const uint8_t* const* pyr_left, const uint8_t* const* pyr
                        const float* scale_factors, const float* inv_scale_factors, float focal_x_baseline, float true_baseline,
                        float* stereo_x_right, float* depths);
 
+/* ---- per-keypoint steps between extractor and matchers (camera_oracle.c) --------------------------------------------------- */
+void orc_undistort_points(const float* xy_in, int n, double fx, double fy, double cx, double cy, const double* dist5, int max_iter, double eps,
+                          float* xy_out);
+void orc_points_to_bearings(const float* xy, int n, int model, double fx, double fy, double cx, double cy, double cols, double rows,
+                            double* bearings);
+
 /* ---- all-pairs matchers with greedy state (pairs_oracle.c) ------------------------------------------------------------ */
 typedef struct {
     int32_t n1;                  /* rows: keyframe 1 / the keyframe */

@@ -389,3 +389,31 @@ def pose_optimize(prob, num_trials_robust=2, num_trials=2, num_each_iter=10):
     L.orc_pose_optimize.restype = C.c_uint
     n = L.orc_pose_optimize(C.byref(P), num_trials_robust, num_trials, num_each_iter, pose.ctypes.data, flags.ctypes.data)
     return int(n), pose, flags[:P.n_edges].astype(bool)
+
+
+def undistort_keypoints(camera, kps):
+    """camera::perspective::undistort_keypoints + convert_keypoints_to_bearings (camera_oracle.c).  Returns (undist_kps, bearings)."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    n = len(kps)
+    out = kps.copy()
+    xy = np.ascontiguousarray(np.stack([kps["x"], kps["y"]], 1), np.float32)
+    L = lib()
+    equi = camera.get("model", "perspective") == "equirectangular"
+    g = lambda k: float(camera.get(k, 0.0))
+    if not equi:
+        L.orc_undistort_points.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        L.orc_undistort_points.restype = None
+        dist = np.array([g("k1"), g("k2"), g("p1"), g("p2"), g("k3")], np.float64)
+        und = np.zeros_like(xy)
+        if n:
+            L.orc_undistort_points(xy.ctypes.data, n, g("fx"), g("fy"), g("cx"), g("cy"), dist.ctypes.data, 20, 1e-6, und.ctypes.data)
+        out["x"], out["y"] = und[:, 0], und[:, 1]
+        out["response"] = 0          # undist_keypts.resize(): default KeyPoint, only pt / angle / size / octave are set (perspective.cc:266-272)
+        xy = und
+    b = np.zeros((n, 3))
+    L.orc_points_to_bearings.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    L.orc_points_to_bearings.restype = None
+    if n:
+        xy = np.ascontiguousarray(xy, np.float32)
+        L.orc_points_to_bearings(xy.ctypes.data, n, 1 if equi else 0, g("fx"), g("fy"), g("cx"), g("cy"), g("cols"), g("rows"), b.ctypes.data)
+    return out, b

@@ -31,6 +31,13 @@ KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4
 _lib = None
 
 # every symbol include/b200vslam.h declares (tests check that the .so exports all of them)
+class CameraIntrinsics(C.Structure):
+    """b200_camera_intrinsics_t (include/b200vslam.h)."""
+    _fields_ = [("model", C.c_int32), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("k1", C.c_double), ("k2", C.c_double), ("p1", C.c_double), ("p2", C.c_double), ("k3", C.c_double),
+                ("cols", C.c_double), ("rows", C.c_double)]
+
+
 class GuidedProblem(C.Structure):
     """b200_guided_problem_t (include/b200vslam.h)."""
     _fields_ = [("n_train", C.c_int32), ("t_x", C.c_void_p), ("t_y", C.c_void_p), ("t_octave", C.c_void_p), ("t_angle", C.c_void_p),
@@ -125,7 +132,7 @@ SYMBOLS = [
     "b200_last_error", "b200_device_count", "b200_version", "b200_host_alloc", "b200_host_free",
     "b200_orb_default_params", "b200_orb_create", "b200_orb_destroy", "b200_orb_max_keypoints", "b200_orb_extract",
     "b200_orb_extract_device", "b200_orb_set_stream", "b200_orb_bind_outputs", "b200_orb_reserve", "b200_orb_fetch", "b200_orb_device_results", "b200_orb_sync", "b200_orb_level_info",
-    "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_pyramid_level_view", "b200_orb_stage_ms", "b200_orb_enable_timing",
+    "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_pyramid_level_view", "b200_keypoints_undistort", "b200_orb_stage_ms", "b200_orb_enable_timing",
     "b200_matcher_create", "b200_matcher_destroy", "b200_hamming_matrix", "b200_match_bruteforce",
     "b200_match_bruteforce_device", "b200_match_guided", "b200_match_cross_check", "b200_match_pairs", "b200_stereo_compute", "b200_matcher_set_stream", "b200_matcher_sync",
     "b200_lba_create", "b200_lba_destroy", "b200_lba_solve", "b200_pose_optimize", "b200_lba_last_profile",
@@ -176,6 +183,7 @@ def lib():
     L.b200_match_pairs.argtypes = [vp, i32, C.POINTER(PairsProblem), i32, C.c_float, i32, i32]
     L.b200_stereo_compute.argtypes = [vp, vp, i32, vp, i32, vp, vp, i32, vp, vp, i32, C.c_float, C.c_float, vp, vp, C.POINTER(i32)]
     L.b200_orb_pyramid_level_view.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(sz), C.POINTER(i32), C.POINTER(i32)]
+    L.b200_keypoints_undistort.argtypes = [vp, C.POINTER(CameraIntrinsics), vp, i32, vp, vp]
     L.b200_matcher_set_stream.argtypes = [vp, vp, i32]
     _lib = L
     return L

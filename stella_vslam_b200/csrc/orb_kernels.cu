@@ -1146,6 +1146,83 @@ struct Extractor {
     }
 };
 
+// ---------------------------------------------------------------------------------------------------------------
+// Per-keypoint steps between the extractor and the matchers:
+//   camera::perspective::undistort_keypoints  (src/stella_vslam/camera/perspective.cc:245-275) = cv::undistortPoints with
+//       TermCriteria(EPS | MAX_ITER, 20, 1e-6), R = I, P = K: fixed-point iteration in double, float output
+//   camera::base::convert_keypoints_to_bearings (camera/base.cc:158-162) with perspective / equirectangular convert_point_to_bearing
+//       (perspective.cc:117-122, equirectangular.cc:42-49)
+// One thread per keypoint; this file is compiled with -fmad=false, so the double arithmetic is evaluated as written.
+// ---------------------------------------------------------------------------------------------------------------
+struct CamModel {
+    int model;
+    double fx, fy, cx, cy, k1, k2, p1, p2, k3, cols, rows;
+};
+__global__ void __launch_bounds__(128) undistort_bearings_kernel(CamModel c, const b200_keypoint_t* __restrict__ in, int n,
+                                                                 b200_keypoint_t* __restrict__ out, double* __restrict__ bearings) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const b200_keypoint_t kp = in[i];
+    float ux = kp.x, uy = kp.y;
+    if (c.model == 0) {
+        const double ifx = 1. / c.fx, ify = 1. / c.fy;
+        const double u = kp.x, v = kp.y;
+        double x = (u - c.cx) * ifx, y = (v - c.cy) * ify;
+        const double x0 = x, y0 = y;
+        double error = 1.7976931348623157e308;
+        for (int j = 0; j < 20 && !(error < 1e-6); ++j) {
+            double r2 = x * x + y * y;
+            const double icdist = 1.0 / (1 + ((c.k3 * r2 + c.k2) * r2 + c.k1) * r2);  // k[5..7] = 0: the numerator is exactly 1
+            if (icdist < 0) {
+                x = (u - c.cx) * ifx;
+                y = (v - c.cy) * ify;
+                break;
+            }
+            const double deltaX = 2 * c.p1 * x * y + c.p2 * (r2 + 2 * x * x);
+            const double deltaY = c.p1 * (r2 + 2 * y * y) + 2 * c.p2 * x * y;
+            x = (x0 - deltaX) * icdist;
+            y = (y0 - deltaY) * icdist;
+            r2 = x * x + y * y;
+            const double r4 = r2 * r2, r6 = r4 * r2;
+            const double a1 = 2 * x * y, a2 = r2 + 2 * x * x, a3 = r2 + 2 * y * y;
+            const double cdist = 1 + c.k1 * r2 + c.k2 * r4 + c.k3 * r6;
+            const double xd0 = x * cdist + c.p1 * a1 + c.p2 * a2, yd0 = y * cdist + c.p1 * a3 + c.p2 * a1;
+            const double ex = (xd0 * c.fx + c.cx) - u, ey = (yd0 * c.fy + c.cy) - v;
+            error = sqrt(ex * ex + ey * ey);
+        }
+        ux = (float)(c.fx * x + c.cx);
+        uy = (float)(c.fy * y + c.cy);
+    }
+    if (out) {
+        b200_keypoint_t o;  // undist_keypts.resize(n): default cv::KeyPoint, then pt / angle / size / octave (perspective.cc:266-272)
+        o.x = ux;
+        o.y = uy;
+        o.size = kp.size;
+        o.angle = kp.angle;
+        o.response = (c.model == 0) ? 0.f : kp.response;  // equirectangular copies the keypoints as they are
+        o.octave = kp.octave;
+        out[i] = o;
+    }
+    if (bearings) {
+        double* b = bearings + 3 * (size_t)i;
+        if (c.model == 1) {
+            const double kTwoPi = 2.0 * 3.14159265358979323846, kPi = 3.14159265358979323846;
+            // cols_ / rows_ are unsigned int in the reference (camera/base.h:105-107): float / unsigned is a FLOAT division
+            const double lon = ((double)__fdiv_rn(ux, (float)(unsigned)c.cols) - 0.5) * kTwoPi;
+            const double lat = -((double)__fdiv_rn(uy, (float)(unsigned)c.rows) - 0.5) * kPi;
+            b[0] = cos(lat) * sin(lon);
+            b[1] = -sin(lat);
+            b[2] = cos(lat) * cos(lon);
+        } else {
+            const double xn = ((double)ux - c.cx) / c.fx, yn = ((double)uy - c.cy) / c.fy;
+            const double l2 = sqrt(xn * xn + yn * yn + 1.0);
+            b[0] = xn / l2;
+            b[1] = yn / l2;
+            b[2] = 1.0 / l2;
+        }
+    }
+}
+
 }  // namespace orb
 }  // namespace b200
 
@@ -1414,6 +1491,34 @@ int b200_orb_pyramid_level_host(b200_orb_t h, int frame, int level, uint8_t* dst
     if (!dst || dst_pitch < (size_t)L.w) return B200_ERR_INVALID;
     B200_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, d, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost, h->ex.stream));
     B200_CUDA(cudaStreamSynchronize(h->ex.stream));
+    return B200_OK;
+}
+
+int b200_keypoints_undistort(b200_orb_t h, const b200_camera_intrinsics_t* cam, const b200_keypoint_t* keypts, int n, b200_keypoint_t* undist_keypts,
+                             double* bearings) {
+    if (!h || !cam || n < 0 || (cam->model != 0 && cam->model != 1)) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;  // cv::undistortPoints does not accept an empty input (perspective.cc:246-250)
+    if (!keypts || (!undist_keypts && !bearings)) return B200_ERR_INVALID;
+    Extractor& ex = h->ex;
+    B200_CUDA(cudaSetDevice(ex.prm.device));
+    const size_t kb = sizeof(b200_keypoint_t) * (size_t)n, bb = sizeof(double) * 3 * (size_t)n;
+    unsigned char* d = nullptr;
+    B200_CUDA(cudaMallocAsync((void**)&d, 2 * kb + bb + 512, ex.stream));
+    b200_keypoint_t* d_in = reinterpret_cast<b200_keypoint_t*>(d);
+    b200_keypoint_t* d_out = reinterpret_cast<b200_keypoint_t*>(d + b200::round_up(kb, (size_t)256));
+    double* d_b = reinterpret_cast<double*>(d + 2 * b200::round_up(kb, (size_t)256));
+    cudaError_t e = cudaMemcpyAsync(d_in, keypts, kb, cudaMemcpyHostToDevice, ex.stream);
+    if (e == cudaSuccess) {
+        const b200::orb::CamModel c{cam->model, cam->fx, cam->fy, cam->cx, cam->cy, cam->k1, cam->k2, cam->p1, cam->p2, cam->k3, cam->cols, cam->rows};
+        b200::orb::undistort_bearings_kernel<<<b200::ceil_div(n, 128), 128, 0, ex.stream>>>(c, d_in, n, undist_keypts ? d_out : nullptr,
+                                                                                         bearings ? d_b : nullptr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && undist_keypts) e = cudaMemcpyAsync(undist_keypts, d_out, kb, cudaMemcpyDeviceToHost, ex.stream);
+    if (e == cudaSuccess && bearings) e = cudaMemcpyAsync(bearings, d_b, bb, cudaMemcpyDeviceToHost, ex.stream);
+    cudaFreeAsync(d, ex.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ex.stream);
+    if (e != cudaSuccess) return b200::cuda_fail(e, "b200_keypoints_undistort", __FILE__, __LINE__);
     return B200_OK;
 }
 

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import KP_DTYPE, OrbParams, check, lib, ptr
+from ._lib import KP_DTYPE, CameraIntrinsics, OrbParams, check, lib, ptr
 
 
 class descriptor_type:  # feature/orb_extractor.h:17-44
@@ -138,6 +138,21 @@ class orb_extractor:
             out.append(lv)
         self.image_pyramid_ = out
         return out
+
+    def undistort_keypoints(self, camera, dist_keypts, want_bearings=True):
+        """camera::perspective / equirectangular::undistort_keypoints + camera::base::convert_keypoints_to_bearings
+        (camera/perspective.cc:245-275, 117-122; equirectangular.cc:42-49; called right after extract, system.cc:386-395).
+        camera: dict(model="perspective"|"equirectangular", fx, fy, cx, cy, k1, k2, p1, p2, k3, cols, rows).
+        Returns (undist_keypts, bearings (n, 3) float64 | None)."""
+        kps = np.ascontiguousarray(dist_keypts, KP_DTYPE)
+        n = len(kps)
+        cam = CameraIntrinsics(1 if camera.get("model", "perspective") == "equirectangular" else 0, *[float(camera.get(k, 0.0)) for k in
+                               ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3", "cols", "rows")])
+        out = np.zeros(n, KP_DTYPE)
+        bearings = np.zeros((n, 3)) if want_bearings else None
+        if n:
+            check(lib().b200_keypoints_undistort(self._h, C.byref(cam), ptr(kps), n, ptr(out), ptr(bearings)))
+        return out, bearings
 
     def enable_timing(self, on=True):
         check(lib().b200_orb_enable_timing(self._h, int(on)))
