@@ -271,6 +271,13 @@ int b200_stereo_compute(b200_matcher_t h, b200_orb_t left, int frame_left, b200_
                         const b200_keypoint_t* keypts_left, const uint8_t* descs_left, int n_left, const b200_keypoint_t* keypts_right,
                         const uint8_t* descs_right, int n_right, float focal_x_baseline, float true_baseline, float* stereo_x_right,
                         float* depths, int32_t* n_matched);
+/* data::landmark::compute_descriptor (src/stella_vslam/data/landmark.cc:199-256), for `n_landmarks` landmarks at once
+ * (after local BA / fusion every touched landmark is refreshed, local_bundle_adjuster_g2o.cc:387-390, 408).  Landmark l owns the
+ * descriptors descs[32 * offsets[l] .. 32 * offsets[l+1]) -- the rows of its observing keyframes that are not about to be erased, in
+ * observation order.  best_idx[l] = index (within the landmark) of the descriptor with the smallest median Hamming distance to all of
+ * them, first on ties (-1 for a landmark without descriptors); desc_out (optional, n_landmarks x 32) = that descriptor. */
+int b200_landmark_descriptors(b200_matcher_t h, int n_landmarks, const uint8_t* descs, const int32_t* offsets, int32_t* best_idx,
+                              uint8_t* desc_out);
 /* Run on the caller's stream (a cudaStream_t; NULL is the legacy default stream); use_own != 0 restores the own stream. */
 int b200_matcher_set_stream(b200_matcher_t h, void* stream, int use_own);
 int b200_matcher_sync(b200_matcher_t h);

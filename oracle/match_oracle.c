@@ -87,3 +87,33 @@ int orc_brute_force_match(const uint8_t* desc1, const float* angle1, int n1, con
     free(taken_1);
     return n;
 }
+
+/* data::landmark::compute_descriptor (src/stella_vslam/data/landmark.cc:199-256): among the descriptors of a landmark's observations,
+ * the one whose median Hamming distance to all of them (itself included; element [0.5 (n-1)] of the sorted row) is smallest, first
+ * index on ties.  descs: n x 32.  Returns best_idx. */
+static int cmp_uint(const void* a, const void* b) {
+    const unsigned x = *(const unsigned*)a, y = *(const unsigned*)b;
+    return x < y ? -1 : (x > y);
+}
+int orc_landmark_descriptor(const uint8_t* descs, int n) {
+    if (n <= 0) return -1;
+    unsigned* d = (unsigned*)malloc(sizeof(unsigned) * (size_t)n * n);
+    unsigned* row = (unsigned*)malloc(sizeof(unsigned) * (size_t)n);
+    for (int i = 0; i < n; ++i) {
+        d[(size_t)i * n + i] = 0;
+        for (int j = i + 1; j < n; ++j) d[(size_t)i * n + j] = d[(size_t)j * n + i] = orc_hamming_32(descs + 32 * (size_t)i, descs + 32 * (size_t)j);
+    }
+    unsigned best = 256;
+    int best_idx = 0;
+    for (int i = 0; i < n; ++i) {
+        memcpy(row, d + (size_t)i * n, sizeof(unsigned) * (size_t)n);
+        qsort(row, (size_t)n, sizeof(unsigned), cmp_uint);
+        const unsigned med = row[(unsigned)(0.5 * (n - 1))];
+        if (med < best) {
+            best = med;
+            best_idx = i;
+        }
+    }
+    free(d); free(row);
+    return best_idx;
+}

@@ -62,6 +62,9 @@ float orc_angle_diff(float a1, float a2);
 int orc_brute_force_match(const uint8_t* desc1, const float* angle1, int n1, const uint8_t* desc2, const float* angle2,
                           const uint8_t* valid2, int n2, float lowe_ratio, int check_orientation, int32_t* pairs_out);
 
+/* data::landmark::compute_descriptor (data/landmark.cc:199-256): index of the representative descriptor among n x 32 bytes. */
+int orc_landmark_descriptor(const uint8_t* descs, int n);
+
 /* ---- grid-guided projection matchers (guided_oracle.c) ------------------------------------------------------------ */
 typedef struct {
     int32_t n_train;                 /* frame keypoints (the side that is searched) */

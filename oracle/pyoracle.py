@@ -417,3 +417,9 @@ def undistort_keypoints(camera, kps):
         xy = np.ascontiguousarray(xy, np.float32)
         L.orc_points_to_bearings(xy.ctypes.data, n, 1 if equi else 0, g("fx"), g("fy"), g("cx"), g("cy"), g("cols"), g("rows"), b.ctypes.data)
     return out, b
+
+
+def landmark_descriptor(descs):
+    """orc_landmark_descriptor: index of the representative descriptor (data/landmark.cc:199-256)."""
+    d = np.ascontiguousarray(descs, np.uint8).reshape(-1, 32)
+    return lib().orc_landmark_descriptor(_p(d), len(d))

@@ -916,6 +916,54 @@ __global__ void __launch_bounds__(1024) stereo_median_kernel(const StereoDev* __
     if (tid == 0) *g.n_kept = n_valid - n_rejected;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// data::landmark::compute_descriptor (src/stella_vslam/data/landmark.cc:199-256): the representative descriptor of a
+// landmark = the observation whose median Hamming distance to all observations is smallest (first index on ties).  One warp per
+// landmark; row by row the lanes compute the distances into shared memory and select the element [0.5 (n - 1)] of the sorted row
+// by counting (value v is the k-th smallest iff #(d < v) <= k < #(d <= v)).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kLmMaxObs = 512;  // observations of one landmark handled on chip
+__global__ void __launch_bounds__(128) landmark_descriptor_kernel(const uint4* __restrict__ descs, const int* __restrict__ offsets, int n_landmarks,
+                                                                  int* __restrict__ best_idx_out, uint4* __restrict__ desc_out) {
+    __shared__ unsigned short dist[4][kLmMaxObs];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int l = blockIdx.x * 4 + warp;
+    if (l >= n_landmarks) return;
+    const int o = offsets[l], n = offsets[l + 1] - o;
+    if (n <= 0 || n > kLmMaxObs) {
+        if (lane == 0) best_idx_out[l] = n <= 0 ? -1 : -2;  // -2: more observations than the kernel holds (reported by the host)
+        return;
+    }
+    const int k = (int)(0.5 * (n - 1));
+    unsigned best = kMaxDist;
+    int best_idx = 0;
+    unsigned short* d = dist[warp];
+    for (int i = 0; i < n; ++i) {
+        const uint4 a0 = descs[(size_t)(o + i) * 2], a1 = descs[(size_t)(o + i) * 2 + 1];
+        for (int j = lane; j < n; j += 32) d[j] = (unsigned short)hamming256(a0, a1, descs[(size_t)(o + j) * 2], descs[(size_t)(o + j) * 2 + 1]);
+        __syncwarp();
+        unsigned med = kMaxDist + 1;
+        for (int j = lane; j < n; j += 32) {
+            const unsigned v = d[j];
+            int lt = 0, le = 0;
+            for (int t = 0; t < n; ++t) {
+                const unsigned w = d[t];
+                lt += w < v;
+                le += w <= v;
+            }
+            if (lt <= k && k < le) med = min(med, v);
+        }
+        med = warp_min(med);
+        if (med < best) {
+            best = med;
+            best_idx = i;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) best_idx_out[l] = best_idx;
+    if (desc_out && lane < 2) desc_out[(size_t)l * 2 + lane] = descs[(size_t)(o + best_idx) * 2 + lane];
+}
+
 struct Matcher {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -1584,6 +1632,60 @@ int b200_stereo_compute(b200_matcher_t h, b200_orb_t left, int frame_left, b200_
     std::memcpy(stereo_x_right, hb + o_x, 4 * (size_t)n_left);
     std::memcpy(depths, hb + o_dep, 4 * (size_t)n_left);
     if (n_matched) *n_matched = *reinterpret_cast<const int*>(hb + o_nk);
+    return B200_OK;
+}
+
+int b200_landmark_descriptors(b200_matcher_t h, int n_landmarks, const uint8_t* descs, const int32_t* offsets, int32_t* best_idx, uint8_t* desc_out) {
+    if (!h || n_landmarks < 0) return B200_ERR_INVALID;
+    if (n_landmarks == 0) return B200_OK;
+    if (!offsets || !best_idx || offsets[0] != 0) {
+        b200::set_error("b200_landmark_descriptors: offsets must start at 0 and best_idx must be given");
+        return B200_ERR_INVALID;
+    }
+    for (int l = 0; l < n_landmarks; ++l)
+        if (offsets[l + 1] < offsets[l]) {
+            b200::set_error("b200_landmark_descriptors: offsets are not ascending at landmark %d", l);
+            return B200_ERR_INVALID;
+        }
+    const size_t total = (size_t)offsets[n_landmarks];
+    if (total > 0 && !descs) return B200_ERR_INVALID;
+    auto& m = h->m;
+    B200_CUDA(cudaSetDevice(m.device));
+    auto al = [](size_t v) { return b200::round_up(v, (size_t)256); };
+    size_t o = 0;
+    const size_t o_desc = o; o += al(32 * std::max(total, (size_t)1));
+    const size_t o_off = o; o += al(4 * ((size_t)n_landmarks + 1));
+    const size_t in_bytes = o, out_begin = o;
+    const size_t o_best = o; o += al(4 * (size_t)n_landmarks);
+    const size_t o_out = o; o += al(32 * (size_t)n_landmarks);
+    const size_t out_end = o;
+    int rc;
+    if ((rc = m.grow((void**)&m.d_guided, &m.d_guided_cap, o))) return rc;
+    if ((rc = m.grow_pinned(&m.h_guided, &m.h_guided_cap, out_end))) return rc;
+    unsigned char *hb = m.h_guided, *db = m.d_guided;
+    if (total) std::memcpy(hb + o_desc, descs, 32 * total);
+    std::memcpy(hb + o_off, offsets, 4 * ((size_t)n_landmarks + 1));
+    cudaStream_t st = m.stream;
+    B200_CUDA(cudaMemcpyAsync(db, hb, in_bytes, cudaMemcpyHostToDevice, st));
+    b200::match::landmark_descriptor_kernel<<<b200::ceil_div(n_landmarks, 4), 128, 0, st>>>((const uint4*)(db + o_desc), (const int*)(db + o_off), n_landmarks,
+                                                                                         (int*)(db + o_best), desc_out ? (uint4*)(db + o_out) : nullptr);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpyAsync(hb + out_begin, db + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    m.last_h2d = in_bytes;
+    m.last_d2h = out_end - out_begin;
+    std::memcpy(best_idx, hb + o_best, 4 * (size_t)n_landmarks);
+    for (int l = 0; l < n_landmarks; ++l)
+        if (best_idx[l] == -2) {
+            b200::set_error("b200_landmark_descriptors: landmark %d has %d observations, at most %d are supported", l, offsets[l + 1] - offsets[l],
+                            b200::match::kLmMaxObs);
+            return B200_ERR_CAPACITY;
+        }
+    if (desc_out) {
+        std::memcpy(desc_out, hb + o_out, 32 * (size_t)n_landmarks);
+        for (int l = 0; l < n_landmarks; ++l)
+            if (best_idx[l] < 0) std::memset(desc_out + 32 * (size_t)l, 0, 32);
+    }
     return B200_OK;
 }
 

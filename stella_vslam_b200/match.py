@@ -331,3 +331,16 @@ class stereo:
                                         C.byref(kept)))
         self.num_matched_ = kept.value
         return x_right[:n], depths[:n]
+
+
+def landmark_descriptors(desc_lists, device=0):
+    """data::landmark::compute_descriptor (data/landmark.cc:199-256) for many landmarks: desc_lists[l] = (n_l, 32) uint8 descriptors of
+    the landmark's observations.  Returns (best_idx (L,), representative descriptors (L, 32))."""
+    n = len(desc_lists)
+    cnt = np.array([len(d) for d in desc_lists], np.int32)
+    offsets = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(d, np.uint8).reshape(-1, 32) for d in desc_lists]) if n and cnt.sum() else np.zeros((1, 32), np.uint8))
+    best = np.full(max(n, 1), -9, np.int32)
+    out = np.zeros((max(n, 1), 32), np.uint8)
+    check(lib().b200_landmark_descriptors(_matcher(device), n, ptr(flat), ptr(offsets), ptr(best), ptr(out)))
+    return best[:n], out[:n]
