@@ -10,6 +10,8 @@
  * RobustKernelHuber, BlockSolver_6_3 Schur complement, OptimizationAlgorithmLevenberg (tau 1e-5, rho/scale rule,
  * <= 10 trials), SparseOptimizer::optimize loop, SE3Quat::exp.  tests/test_lba_cpu.py checks it against an independent
  * scipy dense Gauss-Newton/LM formulation on small problems; the CUDA path is held to 1e-5 relative against this file.
+ * orc_pose_optimize (optimize/pose_optimizer_g2o.cc:38-175) reuses the same edge and LM code with one free pose and
+ * fixed landmarks: equally unpinned (tests/test_pose_opt_cpu.py: protocol properties and ground truth on synthetic frames).
  */
 #define _GNU_SOURCE
 #include <math.h>

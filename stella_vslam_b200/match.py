@@ -1,6 +1,7 @@
 """Host-side mirror of the reference's match:: surface for the Hamming matchers
 (src/stella_vslam/match/base.h:15-91, match/robust.h, match/robust.cc:232-328)."""
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -10,15 +11,20 @@ HAMMING_DIST_THR_LOW = 50    # match/base.h:15
 HAMMING_DIST_THR_HIGH = 100  # match/base.h:16
 MAX_HAMMING_DIST = 256       # match/base.h:17
 
-_matchers = {}
+_tls = threading.local()
 
 
 def _matcher(device=0):
-    if device not in _matchers:
+    """One matcher handle (stream + staging buffers) per (thread, device): a handle must not be shared by concurrent callers, exactly
+    like the reference adapters keep theirs thread_local."""
+    cache = getattr(_tls, "matchers", None)
+    if cache is None:
+        cache = _tls.matchers = {}
+    if device not in cache:
         h = C.c_void_p()
         check(lib().b200_matcher_create(device, C.byref(h)))
-        _matchers[device] = h
-    return _matchers[device]
+        cache[device] = h
+    return cache[device]
 
 
 def hamming_matrix(desc_1, desc_2, device=0):
