@@ -21,6 +21,7 @@
 #include <sched.h>
 
 #include <chrono>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -1444,7 +1445,8 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
         std::vector<int> fill(pt_start.begin(), pt_start.end() - 1);
         for (int e = 0; e < E; ++e) order[fill[P->e_point[e]]++] = e;  // stable: original order within a landmark
     }
-    std::vector<EdgeS> edges(E);
+    std::unique_ptr<EdgeS[]> edges_buf(new EdgeS[std::max(E, 1)]);  // filled below: no zero-initialisation pass
+    EdgeS* edges = edges_buf.get();
     std::vector<unsigned char> robust(E);
     std::vector<int> pose_start(Kf + 1, 0), pose_edges;
     for (int s = 0; s < E; ++s) {
@@ -1483,10 +1485,12 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
         const size_t m = (size_t)(pt_start[l + 1] - pt_start[l]);
         pair_bound += m * (m + 1) / 2;
     }
-    std::vector<int2> gen_pairs(pair_bound + 1);
-    std::vector<int> gen_block(pair_bound + 1);
+    std::unique_ptr<int2[]> gen_pairs(new int2[pair_bound + 1]);
+    std::unique_ptr<int[]> gen_block(new int[pair_bound + 1]);
     size_t n_gen = 0;
     std::vector<int> loc_col, loc_idx;
+    loc_col.reserve(64);
+    loc_idx.reserve(64);
     for (int l = 0; l < L; ++l) {
         if (pt_col[l] < 0) continue;
         loc_col.clear();
@@ -1595,7 +1599,7 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
     unsigned char* hs = S.h_stage;
     std::memset(hs, 0, upload_bytes);
     auto put = [&](size_t off, const void* src, size_t bytes) { if (bytes) std::memcpy(hs + off, src, bytes); };
-    put(o_edges, edges.data(), sizeof(EdgeS) * E);
+    put(o_edges, edges, sizeof(EdgeS) * E);
     put(o_cams, cams.data(), sizeof(Cam) * P->n_cams);
     put(o_ptstart, pt_start.data(), sizeof(int) * (L + 1));
     put(o_posestart, pose_start.data(), sizeof(int) * (Kf + 1));
