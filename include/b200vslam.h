@@ -127,6 +127,17 @@ typedef struct {
 int b200_keypoints_undistort(b200_orb_t h, const b200_camera_intrinsics_t* cam, const b200_keypoint_t* keypts, int n,
                              b200_keypoint_t* undist_keypts, double* bearings);
 
+/* data::frame::can_observe (src/stella_vslam/data/frame.cc:59-84) for the `n` local landmarks a frame may see
+ * (tracking_module.cc:559-594): reprojection (camera/perspective.cc:130-148, equirectangular.cc:59-73), ORB scale range
+ * (data/landmark.h:88-92), viewing angle, predicted pyramid level (data/landmark.cc:336-353).  pose_cw: 4x4 row-major;
+ * img_bounds = {min_x, max_x, min_y, max_y} (camera::base::img_bounds_, perspective only); per landmark: pos_w (3 doubles),
+ * mean_normal (3 doubles), min / max valid distance (floats).  Out per landmark: observable (0/1) and, when observable, the
+ * reprojection (2 doubles), x_right and pred_scale_level -- the inputs of b200_match_guided mode 0. */
+int b200_frame_can_observe(b200_orb_t h, const b200_camera_intrinsics_t* cam, double focal_x_baseline, const float* img_bounds,
+                           const double* pose_cw, int n, const double* pos_w, const double* mean_normal, const float* min_valid_dist,
+                           const float* max_valid_dist, float ray_cos_thr, unsigned num_levels, float log_scale_factor, uint8_t* observable,
+                           double* reproj, float* x_right, uint32_t* pred_scale_level);
+
 /* Per-stage kernel time of the last extract, in ms, measured with CUDA events on the instance stream.
  * stage: 0 pyramid, 1 FAST+NMS+grid arg-max, 2 ordered selection, 3 descriptor blur, 4 orientation+rBRIEF, 5 whole extract. */
 int b200_orb_stage_ms(b200_orb_t h, int stage, float* ms);

@@ -78,3 +78,61 @@ void orc_points_to_bearings(const float* xy, int n, int model, double fx, double
         }
     }
 }
+
+/* data::frame::can_observe (src/stella_vslam/data/frame.cc:59-84) for n landmarks of the local map (tracking_module.cc:559-594):
+ * camera::perspective / equirectangular::reproject_to_image (perspective.cc:130-148, equirectangular.cc:59-73),
+ * landmark::is_inside_in_orb_scale (data/landmark.h:88-92), the viewing-angle test and landmark::predict_scale_level
+ * (data/landmark.cc:336-353; float ratio, logf, ceil).  Rt_cw: rot_cw row-major (9) then trans_cw (3); trans_wc: camera centre. */
+void orc_can_observe(int model, double fx, double fy, double cx, double cy, double fxb, double cols, double rows, const float* bounds,
+                     const double* Rt_cw, const double* trans_wc, int n, const double* pos_w, const double* mean_normal,
+                     const float* min_valid_dist, const float* max_valid_dist, float ray_cos_thr, unsigned num_levels, float log_scale_factor,
+                     uint8_t* observable, double* reproj, float* x_right, uint32_t* pred_scale_level) {
+    for (int i = 0; i < n; ++i) {
+        const double* p = pos_w + 3 * i;
+        observable[i] = 0;
+        reproj[2 * i] = reproj[2 * i + 1] = 0.0;
+        x_right[i] = 0.f;
+        pred_scale_level[i] = 0;
+        const double pcx = Rt_cw[0] * p[0] + Rt_cw[1] * p[1] + Rt_cw[2] * p[2] + Rt_cw[9];
+        const double pcy = Rt_cw[3] * p[0] + Rt_cw[4] * p[1] + Rt_cw[5] * p[2] + Rt_cw[10];
+        const double pcz = Rt_cw[6] * p[0] + Rt_cw[7] * p[1] + Rt_cw[8] * p[2] + Rt_cw[11];
+        double rx, ry;
+        float xr;
+        if (model == 1) {
+            const double nrm = sqrt(pcx * pcx + pcy * pcy + pcz * pcz);
+            const double bx = pcx / nrm, by = pcy / nrm, bz = pcz / nrm;
+            const double latitude = -asin(by), longitude = atan2(bx, bz);
+            rx = cols * (0.5 + longitude / (2.0 * M_PI));
+            ry = rows * (0.5 - latitude / M_PI);
+            xr = 0.0f;
+        } else {
+            if (pcz <= 0.0) continue;
+            const double z_inv = 1.0 / pcz;
+            rx = fx * pcx * z_inv + cx;
+            ry = fy * pcy * z_inv + cy;
+            xr = (float)(rx - fxb * z_inv);
+            if (!(bounds[0] < rx && rx < bounds[1] && bounds[2] < ry && ry < bounds[3])) continue;
+        }
+        const double vx = p[0] - trans_wc[0], vy = p[1] - trans_wc[1], vz = p[2] - trans_wc[2];
+        const double dist = sqrt(vx * vx + vy * vy + vz * vz);
+        const float margin_far = (float)1.3, margin_near = (float)(1.0 / 1.3), distf = (float)dist;
+        const float max_dist = margin_far * max_valid_dist[i], min_dist = margin_near * min_valid_dist[i];
+        if (!(min_dist <= distf && distf <= max_dist)) continue;
+        const double* nml = mean_normal + 3 * i;
+        const double ray_cos = (vx * nml[0] + vy * nml[1] + vz * nml[2]) / dist;
+        if (ray_cos < ray_cos_thr) continue;
+        const float ratio = max_valid_dist[i] / distf;
+        const int lvl = (int)ceilf(logf(ratio) / log_scale_factor);
+        /* predict_scale_level takes num_scale_levels as float (data/landmark.cc:336) */
+        const float nl = (float)num_levels;
+        uint32_t out;
+        if (lvl < 0) out = 0;
+        else if (nl <= (float)(unsigned)lvl) out = (uint32_t)(nl - 1);
+        else out = (uint32_t)lvl;
+        observable[i] = 1;
+        reproj[2 * i] = rx;
+        reproj[2 * i + 1] = ry;
+        x_right[i] = xr;
+        pred_scale_level[i] = out;
+    }
+}

@@ -111,6 +111,11 @@ void orc_undistort_points(const float* xy_in, int n, double fx, double fy, doubl
 void orc_points_to_bearings(const float* xy, int n, int model, double fx, double fy, double cx, double cy, double cols, double rows,
                             double* bearings);
 
+void orc_can_observe(int model, double fx, double fy, double cx, double cy, double fxb, double cols, double rows, const float* bounds,
+                     const double* Rt_cw, const double* trans_wc, int n, const double* pos_w, const double* mean_normal,
+                     const float* min_valid_dist, const float* max_valid_dist, float ray_cos_thr, unsigned num_levels, float log_scale_factor,
+                     uint8_t* observable, double* reproj, float* x_right, uint32_t* pred_scale_level);
+
 /* ---- all-pairs matchers with greedy state (pairs_oracle.c) ------------------------------------------------------------ */
 typedef struct {
     int32_t n1;                  /* rows: keyframe 1 / the keyframe */

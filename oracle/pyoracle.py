@@ -423,3 +423,29 @@ def landmark_descriptor(descs):
     """orc_landmark_descriptor: index of the representative descriptor (data/landmark.cc:199-256)."""
     d = np.ascontiguousarray(descs, np.uint8).reshape(-1, 32)
     return lib().orc_landmark_descriptor(_p(d), len(d))
+
+
+def can_observe(camera, pose_cw, landmarks, ray_cos_thr=0.5, img_bounds=None, num_levels=8, log_scale_factor=None):
+    """orc_can_observe (data::frame::can_observe).  Same arguments and result layout as feature.orb_extractor.can_observe."""
+    pos = np.ascontiguousarray(landmarks["pos_w"], np.float64).reshape(-1, 3)
+    nml = np.ascontiguousarray(landmarks["mean_normal"], np.float64).reshape(-1, 3)
+    lo = np.ascontiguousarray(landmarks["min_valid_dist"], np.float32)
+    hi = np.ascontiguousarray(landmarks["max_valid_dist"], np.float32)
+    n = len(pos)
+    g = lambda k: float(camera.get(k, 0.0))
+    bounds = np.ascontiguousarray(img_bounds if img_bounds is not None else (0.0, g("cols"), 0.0, g("rows")), np.float32)
+    T = np.ascontiguousarray(pose_cw, np.float64).reshape(4, 4)
+    Rt = np.concatenate([T[:3, :3].reshape(9), T[:3, 3]])
+    twc = np.array([-((T[0, r] * T[0, 3] + T[1, r] * T[1, 3]) + T[2, r] * T[2, 3]) for r in range(3)])
+    if log_scale_factor is None:
+        log_scale_factor = np.log(np.float32(1.2)).astype(np.float32) if hasattr(np.log(np.float32(1.2)), "astype") else np.float32(np.log(np.float32(1.2)))
+    ok, rp = np.zeros(max(n, 1), np.uint8), np.zeros((max(n, 1), 2))
+    xr, lv = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.uint32)
+    L = lib()
+    L.orc_can_observe.argtypes = [C.c_int] + [C.c_double] * 7 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_float, C.c_uint, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_can_observe.restype = None
+    L.orc_can_observe(1 if camera.get("model", "perspective") == "equirectangular" else 0, g("fx"), g("fy"), g("cx"), g("cy"), g("fxb"), g("cols"),
+                      g("rows"), _p(bounds), _p(Rt), _p(twc), n, _p(pos), _p(nml), _p(lo), _p(hi), float(ray_cos_thr), int(num_levels),
+                      float(log_scale_factor), _p(ok), _p(rp), _p(xr), _p(lv))
+    return dict(observable=ok[:n].astype(bool), reproj=rp[:n], x_right=xr[:n], pred_scale_level=lv[:n])

@@ -1223,6 +1223,75 @@ __global__ void __launch_bounds__(128) undistort_bearings_kernel(CamModel c, con
     }
 }
 
+// data::frame::can_observe (src/stella_vslam/data/frame.cc:59-84) for the landmarks of the local map (tracking_module.cc:559-594):
+// reproject_to_image (camera/perspective.cc:130-148, equirectangular.cc:59-73), landmark::is_inside_in_orb_scale
+// (data/landmark.h:88-92), the viewing-angle test and landmark::predict_scale_level (data/landmark.cc:336-353).  Thread per landmark.
+struct ObserveArgs {
+    CamModel cam;
+    double fxb;
+    float min_x, max_x, min_y, max_y;
+    double Rt[12], twc[3];
+    float ray_cos_thr, log_scale_factor;
+    unsigned num_levels;
+};
+__global__ void __launch_bounds__(128) can_observe_kernel(ObserveArgs a, int n, const double* __restrict__ pos_w, const double* __restrict__ mean_normal,
+                                                          const float* __restrict__ min_valid, const float* __restrict__ max_valid,
+                                                          unsigned char* __restrict__ observable, double* __restrict__ reproj,
+                                                          float* __restrict__ x_right, unsigned* __restrict__ level) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double px = pos_w[3 * (size_t)i], py = pos_w[3 * (size_t)i + 1], pz = pos_w[3 * (size_t)i + 2];
+    unsigned char ok = 0;
+    double rx = 0.0, ry = 0.0;
+    float xr = 0.f;
+    unsigned lvl_out = 0;
+    const double pcx = a.Rt[0] * px + a.Rt[1] * py + a.Rt[2] * pz + a.Rt[9];
+    const double pcy = a.Rt[3] * px + a.Rt[4] * py + a.Rt[5] * pz + a.Rt[10];
+    const double pcz = a.Rt[6] * px + a.Rt[7] * py + a.Rt[8] * pz + a.Rt[11];
+    bool in_image;
+    double qx, qy;
+    float qr;
+    if (a.cam.model == 1) {
+        const double nrm = sqrt(pcx * pcx + pcy * pcy + pcz * pcz);
+        const double bx = pcx / nrm, by = pcy / nrm, bz = pcz / nrm;
+        const double latitude = -asin(by), longitude = atan2(bx, bz);
+        qx = a.cam.cols * (0.5 + longitude / (2.0 * 3.14159265358979323846));
+        qy = a.cam.rows * (0.5 - latitude / 3.14159265358979323846);
+        qr = 0.f;
+        in_image = true;
+    } else {
+        const double z_inv = 1.0 / pcz;
+        qx = a.cam.fx * pcx * z_inv + a.cam.cx;
+        qy = a.cam.fy * pcy * z_inv + a.cam.cy;
+        qr = (float)(qx - a.fxb * z_inv);
+        in_image = pcz > 0.0 && (double)a.min_x < qx && qx < (double)a.max_x && (double)a.min_y < qy && qy < (double)a.max_y;
+    }
+    if (in_image) {
+        const double vx = px - a.twc[0], vy = py - a.twc[1], vz = pz - a.twc[2];
+        const double dist = sqrt(vx * vx + vy * vy + vz * vz);
+        const float distf = (float)dist;
+        const float max_dist = __fmul_rn(1.3f, max_valid[i]), min_dist = __fmul_rn((float)(1.0 / 1.3), min_valid[i]);
+        if (min_dist <= distf && distf <= max_dist) {
+            const double ray_cos = (vx * mean_normal[3 * (size_t)i] + vy * mean_normal[3 * (size_t)i + 1] + vz * mean_normal[3 * (size_t)i + 2]) / dist;
+            if (!(ray_cos < (double)a.ray_cos_thr)) {
+                const float ratio = __fdiv_rn(max_valid[i], distf);
+                const int lvl = (int)ceilf(__fdiv_rn(logf(ratio), a.log_scale_factor));
+                const float nl = (float)a.num_levels;
+                lvl_out = lvl < 0 ? 0u : ((nl <= (float)(unsigned)lvl) ? (unsigned)(nl - 1.f) : (unsigned)lvl);
+                ok = 1;
+                rx = qx;
+                ry = qy;
+                xr = qr;
+            }
+        }
+    }
+    observable[i] = ok;
+    reproj[2 * (size_t)i] = rx;
+    reproj[2 * (size_t)i + 1] = ry;
+    x_right[i] = xr;
+    level[i] = lvl_out;
+}
+
 }  // namespace orb
 }  // namespace b200
 
@@ -1519,6 +1588,62 @@ int b200_keypoints_undistort(b200_orb_t h, const b200_camera_intrinsics_t* cam, 
     cudaFreeAsync(d, ex.stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ex.stream);
     if (e != cudaSuccess) return b200::cuda_fail(e, "b200_keypoints_undistort", __FILE__, __LINE__);
+    return B200_OK;
+}
+
+int b200_frame_can_observe(b200_orb_t h, const b200_camera_intrinsics_t* cam, double focal_x_baseline, const float* img_bounds,
+                           const double* pose_cw, int n, const double* pos_w, const double* mean_normal, const float* min_valid_dist,
+                           const float* max_valid_dist, float ray_cos_thr, unsigned num_levels, float log_scale_factor, uint8_t* observable,
+                           double* reproj, float* x_right, uint32_t* pred_scale_level) {
+    if (!h || !cam || !pose_cw || n < 0 || (cam->model != 0 && cam->model != 1) || (cam->model == 0 && !img_bounds)) return B200_ERR_INVALID;
+    if (n == 0) return B200_OK;
+    if (!pos_w || !mean_normal || !min_valid_dist || !max_valid_dist || !observable || !reproj || !x_right || !pred_scale_level) return B200_ERR_INVALID;
+    Extractor& ex = h->ex;
+    B200_CUDA(cudaSetDevice(ex.prm.device));
+    b200::orb::ObserveArgs a{};
+    a.cam = b200::orb::CamModel{cam->model, cam->fx, cam->fy, cam->cx, cam->cy, cam->k1, cam->k2, cam->p1, cam->p2, cam->k3, cam->cols, cam->rows};
+    a.fxb = focal_x_baseline;
+    if (img_bounds) { a.min_x = img_bounds[0]; a.max_x = img_bounds[1]; a.min_y = img_bounds[2]; a.max_y = img_bounds[3]; }
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) a.Rt[3 * r + c] = pose_cw[4 * r + c];
+        a.Rt[9 + r] = pose_cw[4 * r + 3];
+    }
+    for (int r = 0; r < 3; ++r)  // trans_wc_ = -rot_cw^T trans_cw (data/frame.cc: update_pose_params)
+        a.twc[r] = -(a.Rt[r] * a.Rt[9] + a.Rt[3 + r] * a.Rt[10] + a.Rt[6 + r] * a.Rt[11]);
+    a.ray_cos_thr = ray_cos_thr;
+    a.log_scale_factor = log_scale_factor;
+    a.num_levels = num_levels;
+    auto al = [](size_t v) { return b200::round_up(v, (size_t)256); };
+    const size_t N = (size_t)n;
+    size_t o = 0;
+    const size_t o_p = o; o += al(24 * N);
+    const size_t o_n = o; o += al(24 * N);
+    const size_t o_lo = o; o += al(4 * N);
+    const size_t o_hi = o; o += al(4 * N);
+    const size_t o_ok = o; o += al(N);
+    const size_t o_rp = o; o += al(16 * N);
+    const size_t o_xr = o; o += al(4 * N);
+    const size_t o_lv = o; o += al(4 * N);
+    unsigned char* d = nullptr;
+    B200_CUDA(cudaMallocAsync((void**)&d, o, ex.stream));
+    cudaStream_t st = ex.stream;
+    cudaError_t e = cudaMemcpyAsync(d + o_p, pos_w, 24 * N, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_n, mean_normal, 24 * N, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_lo, min_valid_dist, 4 * N, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + o_hi, max_valid_dist, 4 * N, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        b200::orb::can_observe_kernel<<<b200::ceil_div(n, 128), 128, 0, st>>>(a, n, (const double*)(d + o_p), (const double*)(d + o_n), (const float*)(d + o_lo),
+                                                                          (const float*)(d + o_hi), d + o_ok, (double*)(d + o_rp), (float*)(d + o_xr),
+                                                                          (unsigned*)(d + o_lv));
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(observable, d + o_ok, N, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(reproj, d + o_rp, 16 * N, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(x_right, d + o_xr, 4 * N, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pred_scale_level, d + o_lv, 4 * N, cudaMemcpyDeviceToHost, st);
+    cudaFreeAsync(d, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return b200::cuda_fail(e, "b200_frame_can_observe", __FILE__, __LINE__);
     return B200_OK;
 }
 

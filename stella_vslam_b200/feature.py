@@ -154,6 +154,27 @@ class orb_extractor:
             check(lib().b200_keypoints_undistort(self._h, C.byref(cam), ptr(kps), n, ptr(out), ptr(bearings)))
         return out, bearings
 
+    def can_observe(self, camera, pose_cw, landmarks, ray_cos_thr=0.5, img_bounds=None):
+        """data::frame::can_observe (data/frame.cc:59-84) for the local landmarks (tracking_module.cc:559-594).
+        landmarks: dict(pos_w (n,3), mean_normal (n,3), min_valid_dist (n,), max_valid_dist (n,)).
+        Returns dict(observable bool (n,), reproj (n,2), x_right (n,), pred_scale_level (n,)) -- the inputs of
+        match.projection.match_frame_and_landmarks."""
+        pos = np.ascontiguousarray(landmarks["pos_w"], np.float64).reshape(-1, 3)
+        nml = np.ascontiguousarray(landmarks["mean_normal"], np.float64).reshape(-1, 3)
+        lo = np.ascontiguousarray(landmarks["min_valid_dist"], np.float32)
+        hi = np.ascontiguousarray(landmarks["max_valid_dist"], np.float32)
+        n = len(pos)
+        cam = CameraIntrinsics(1 if camera.get("model", "perspective") == "equirectangular" else 0, *[float(camera.get(k, 0.0)) for k in
+                               ("fx", "fy", "cx", "cy", "k1", "k2", "p1", "p2", "k3", "cols", "rows")])
+        bounds = np.ascontiguousarray(img_bounds if img_bounds is not None else (0.0, camera.get("cols", 0.0), 0.0, camera.get("rows", 0.0)), np.float32)
+        pose = np.ascontiguousarray(pose_cw, np.float64).reshape(4, 4)
+        ok, rp = np.zeros(max(n, 1), np.uint8), np.zeros((max(n, 1), 2))
+        xr, lv = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.uint32)
+        check(lib().b200_frame_can_observe(self._h, C.byref(cam), float(camera.get("fxb", 0.0)), ptr(bounds), ptr(pose), n, ptr(pos), ptr(nml), ptr(lo),
+                                           ptr(hi), float(ray_cos_thr), int(self.orb_params_.num_levels_), float(self.orb_params_.log_scale_factor_),
+                                           ptr(ok), ptr(rp), ptr(xr), ptr(lv)))
+        return dict(observable=ok[:n].astype(bool), reproj=rp[:n], x_right=xr[:n], pred_scale_level=lv[:n])
+
     def enable_timing(self, on=True):
         check(lib().b200_orb_enable_timing(self._h, int(on)))
 
