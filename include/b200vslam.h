@@ -289,6 +289,14 @@ int b200_stereo_compute(b200_matcher_t h, b200_orb_t left, int frame_left, b200_
  * them, first on ties (-1 for a landmark without descriptors); desc_out (optional, n_landmarks x 32) = that descriptor. */
 int b200_landmark_descriptors(b200_matcher_t h, int n_landmarks, const uint8_t* descs, const int32_t* offsets, int32_t* best_idx,
                               uint8_t* desc_out);
+/* data::landmark::update_mean_normal_and_obs_scale_variance (src/stella_vslam/data/landmark.cc:256-311) for
+ * `n_landmarks` landmarks.  Landmark l: position pos_w[3l..], observed from the camera centres
+ * cam_centers[3 * offsets[l] .. 3 * offsets[l+1]) (keyfrm->get_trans_wc() of its observations in the order the caller walks them);
+ * ref_center[3l..] / ref_scale_factor[l] = centre of its reference keyframe and scale_factors_[octave of its keypoint there];
+ * inv_scale_factor_last = inv_scale_factors_[num_levels - 1].  Out: mean_normal (n x 3), max_valid_dist, min_valid_dist. */
+int b200_landmark_geometry(b200_matcher_t h, int n_landmarks, const double* pos_w, const int32_t* offsets, const double* cam_centers,
+                           const double* ref_center, const float* ref_scale_factor, float inv_scale_factor_last, double* mean_normal,
+                           float* max_valid_dist, float* min_valid_dist);
 /* Run on the caller's stream (a cudaStream_t; NULL is the legacy default stream); use_own != 0 restores the own stream. */
 int b200_matcher_set_stream(b200_matcher_t h, void* stream, int use_own);
 int b200_matcher_sync(b200_matcher_t h);

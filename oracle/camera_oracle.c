@@ -136,3 +136,28 @@ void orc_can_observe(int model, double fx, double fy, double cx, double cy, doub
         pred_scale_level[i] = out;
     }
 }
+
+/* data::landmark::update_mean_normal_and_obs_scale_variance (src/stella_vslam/data/landmark.cc:256-311) for n landmarks.
+ * Landmark l is observed from the camera centres cam_centers[3 * offsets[l] .. 3 * offsets[l+1]) (keyfrm->get_trans_wc(), in the
+ * order the caller walks observations_ -- the reference's own order is that of a pointer-keyed map); ref_center / ref_scale_factor:
+ * the reference keyframe's centre and scale_factors_[octave of its keypoint]; inv_scale_factor_last = inv_scale_factors_[levels-1]. */
+void orc_landmark_geometry(int n, const double* pos_w, const int32_t* offsets, const double* cam_centers, const double* ref_center,
+                           const float* ref_scale_factor, float inv_scale_factor_last, double* mean_normal, float* max_valid_dist,
+                           float* min_valid_dist) {
+    for (int l = 0; l < n; ++l) {
+        const double* p = pos_w + 3 * l;
+        double m[3] = {0, 0, 0};
+        for (int o = offsets[l]; o < offsets[l + 1]; ++o) {
+            const double v[3] = {p[0] - cam_centers[3 * o], p[1] - cam_centers[3 * o + 1], p[2] - cam_centers[3 * o + 2]};
+            const double nrm = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            for (int k = 0; k < 3; ++k) m[k] = m[k] + (nrm > 0 ? v[k] / nrm : v[k]); /* Eigen normalized(): unchanged when the norm is 0 */
+        }
+        const double mn = sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2]);
+        for (int k = 0; k < 3; ++k) mean_normal[3 * l + k] = mn > 0 ? m[k] / mn : m[k];
+        const double r[3] = {p[0] - ref_center[3 * l], p[1] - ref_center[3 * l + 1], p[2] - ref_center[3 * l + 2]};
+        const double dist = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+        const float mx = (float)(dist * ref_scale_factor[l]);
+        max_valid_dist[l] = mx;
+        min_valid_dist[l] = mx * inv_scale_factor_last;
+    }
+}

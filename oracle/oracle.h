@@ -116,6 +116,10 @@ void orc_can_observe(int model, double fx, double fy, double cx, double cy, doub
                      const float* min_valid_dist, const float* max_valid_dist, float ray_cos_thr, unsigned num_levels, float log_scale_factor,
                      uint8_t* observable, double* reproj, float* x_right, uint32_t* pred_scale_level);
 
+void orc_landmark_geometry(int n, const double* pos_w, const int32_t* offsets, const double* cam_centers, const double* ref_center,
+                           const float* ref_scale_factor, float inv_scale_factor_last, double* mean_normal, float* max_valid_dist,
+                           float* min_valid_dist);
+
 /* ---- all-pairs matchers with greedy state (pairs_oracle.c) ------------------------------------------------------------ */
 typedef struct {
     int32_t n1;                  /* rows: keyframe 1 / the keyframe */

@@ -449,3 +449,19 @@ def can_observe(camera, pose_cw, landmarks, ray_cos_thr=0.5, img_bounds=None, nu
                       g("rows"), _p(bounds), _p(Rt), _p(twc), n, _p(pos), _p(nml), _p(lo), _p(hi), float(ray_cos_thr), int(num_levels),
                       float(log_scale_factor), _p(ok), _p(rp), _p(xr), _p(lv))
     return dict(observable=ok[:n].astype(bool), reproj=rp[:n], x_right=xr[:n], pred_scale_level=lv[:n])
+
+
+def landmark_geometry(pos_w, cam_center_lists, ref_center, ref_scale_factor, inv_scale_factor_last):
+    """orc_landmark_geometry (data/landmark.cc:256-311).  Same arguments / results as match.landmark_geometry."""
+    n = len(cam_center_lists)
+    cnt = np.array([len(c) for c in cam_center_lists], np.int32)
+    offsets = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(c, np.float64).reshape(-1, 3) for c in cam_center_lists]) if n and cnt.sum() else np.zeros((1, 3)))
+    pos, ref = np.ascontiguousarray(pos_w, np.float64).reshape(-1, 3), np.ascontiguousarray(ref_center, np.float64).reshape(-1, 3)
+    sf = np.ascontiguousarray(ref_scale_factor, np.float32)
+    mn, mx, mi = np.zeros((max(n, 1), 3)), np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32)
+    L = lib()
+    L.orc_landmark_geometry.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.orc_landmark_geometry.restype = None
+    L.orc_landmark_geometry(n, _p(pos), _p(offsets), _p(flat), _p(ref), _p(sf), float(inv_scale_factor_last), _p(mn), _p(mx), _p(mi))
+    return mn[:n], mx[:n], mi[:n]

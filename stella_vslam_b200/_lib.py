@@ -134,7 +134,7 @@ SYMBOLS = [
     "b200_orb_extract_device", "b200_orb_set_stream", "b200_orb_bind_outputs", "b200_orb_reserve", "b200_orb_fetch", "b200_orb_device_results", "b200_orb_sync", "b200_orb_level_info",
     "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_pyramid_level_view", "b200_keypoints_undistort", "b200_frame_can_observe", "b200_orb_stage_ms", "b200_orb_enable_timing",
     "b200_matcher_create", "b200_matcher_destroy", "b200_hamming_matrix", "b200_match_bruteforce",
-    "b200_match_bruteforce_device", "b200_match_guided", "b200_match_cross_check", "b200_match_pairs", "b200_stereo_compute", "b200_landmark_descriptors", "b200_matcher_set_stream", "b200_matcher_sync",
+    "b200_match_bruteforce_device", "b200_match_guided", "b200_match_cross_check", "b200_match_pairs", "b200_stereo_compute", "b200_landmark_descriptors", "b200_landmark_geometry", "b200_matcher_set_stream", "b200_matcher_sync",
     "b200_lba_create", "b200_lba_destroy", "b200_lba_solve", "b200_pose_optimize", "b200_lba_last_profile",
 ]
 
@@ -187,6 +187,7 @@ def lib():
     L.b200_landmark_descriptors.argtypes = [vp, i32, vp, vp, vp, vp]
     L.b200_frame_can_observe.argtypes = [vp, C.POINTER(CameraIntrinsics), C.c_double, vp, vp, i32, vp, vp, vp, vp, C.c_float, C.c_uint, C.c_float,
                                          vp, vp, vp, vp]
+    L.b200_landmark_geometry.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp]
     L.b200_matcher_set_stream.argtypes = [vp, vp, i32]
     _lib = L
     return L

@@ -964,6 +964,40 @@ __global__ void __launch_bounds__(128) landmark_descriptor_kernel(const uint4* _
     if (desc_out && lane < 2) desc_out[(size_t)l * 2 + lane] = descs[(size_t)(o + best_idx) * 2 + lane];
 }
 
+// data::landmark::update_mean_normal_and_obs_scale_variance (src/stella_vslam/data/landmark.cc:256-311): per landmark the
+// normalised mean of the unit viewing directions of its observations and the ORB scale range from its reference keyframe.
+// Thread per landmark; explicit round-to-nearest operations (this file is compiled with FMA contraction on).
+__device__ __forceinline__ double norm3(double x, double y, double z) {
+    return __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
+}
+__global__ void __launch_bounds__(128) landmark_geometry_kernel(int n, const double* __restrict__ pos_w, const int* __restrict__ offsets,
+                                                                const double* __restrict__ cam_centers, const double* __restrict__ ref_center,
+                                                                const float* __restrict__ ref_scale, float inv_scale_last,
+                                                                double* __restrict__ mean_normal, float* __restrict__ max_valid,
+                                                                float* __restrict__ min_valid) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n) return;
+    const double px = pos_w[3 * (size_t)l], py = pos_w[3 * (size_t)l + 1], pz = pos_w[3 * (size_t)l + 2];
+    double mx = 0.0, my = 0.0, mz = 0.0;
+    for (int o = offsets[l]; o < offsets[l + 1]; ++o) {
+        const double vx = __dsub_rn(px, cam_centers[3 * (size_t)o]), vy = __dsub_rn(py, cam_centers[3 * (size_t)o + 1]),
+                     vz = __dsub_rn(pz, cam_centers[3 * (size_t)o + 2]);
+        const double nrm = norm3(vx, vy, vz);
+        const bool pos = nrm > 0.0;  // Eigen normalized(): unchanged when the norm is 0
+        mx = __dadd_rn(mx, pos ? __ddiv_rn(vx, nrm) : vx);
+        my = __dadd_rn(my, pos ? __ddiv_rn(vy, nrm) : vy);
+        mz = __dadd_rn(mz, pos ? __ddiv_rn(vz, nrm) : vz);
+    }
+    const double mn = norm3(mx, my, mz);
+    mean_normal[3 * (size_t)l] = mn > 0.0 ? __ddiv_rn(mx, mn) : mx;
+    mean_normal[3 * (size_t)l + 1] = mn > 0.0 ? __ddiv_rn(my, mn) : my;
+    mean_normal[3 * (size_t)l + 2] = mn > 0.0 ? __ddiv_rn(mz, mn) : mz;
+    const double dist = norm3(__dsub_rn(px, ref_center[3 * (size_t)l]), __dsub_rn(py, ref_center[3 * (size_t)l + 1]), __dsub_rn(pz, ref_center[3 * (size_t)l + 2]));
+    const float mxv = __double2float_rn(__dmul_rn(dist, (double)ref_scale[l]));
+    max_valid[l] = mxv;
+    min_valid[l] = __fmul_rn(mxv, inv_scale_last);
+}
+
 struct Matcher {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -1686,6 +1720,54 @@ int b200_landmark_descriptors(b200_matcher_t h, int n_landmarks, const uint8_t* 
         for (int l = 0; l < n_landmarks; ++l)
             if (best_idx[l] < 0) std::memset(desc_out + 32 * (size_t)l, 0, 32);
     }
+    return B200_OK;
+}
+
+int b200_landmark_geometry(b200_matcher_t h, int n_landmarks, const double* pos_w, const int32_t* offsets, const double* cam_centers,
+                           const double* ref_center, const float* ref_scale_factor, float inv_scale_factor_last, double* mean_normal,
+                           float* max_valid_dist, float* min_valid_dist) {
+    if (!h || n_landmarks < 0) return B200_ERR_INVALID;
+    if (n_landmarks == 0) return B200_OK;
+    if (!pos_w || !offsets || !ref_center || !ref_scale_factor || !mean_normal || !max_valid_dist || !min_valid_dist || offsets[0] != 0) return B200_ERR_INVALID;
+    for (int l = 0; l < n_landmarks; ++l)
+        if (offsets[l + 1] < offsets[l]) return B200_ERR_INVALID;
+    const size_t N = (size_t)n_landmarks, total = (size_t)offsets[n_landmarks];
+    if (total > 0 && !cam_centers) return B200_ERR_INVALID;
+    auto& m = h->m;
+    B200_CUDA(cudaSetDevice(m.device));
+    auto al = [](size_t v) { return b200::round_up(v, (size_t)256); };
+    size_t o = 0;
+    const size_t o_p = o; o += al(24 * N);
+    const size_t o_off = o; o += al(4 * (N + 1));
+    const size_t o_c = o; o += al(24 * std::max(total, (size_t)1));
+    const size_t o_r = o; o += al(24 * N);
+    const size_t o_s = o; o += al(4 * N);
+    const size_t in_bytes = o, out_begin = o;
+    const size_t o_mn = o; o += al(24 * N);
+    const size_t o_mx = o; o += al(4 * N);
+    const size_t o_mi = o; o += al(4 * N);
+    const size_t out_end = o;
+    int rc;
+    if ((rc = m.grow((void**)&m.d_guided, &m.d_guided_cap, o))) return rc;
+    if ((rc = m.grow_pinned(&m.h_guided, &m.h_guided_cap, out_end))) return rc;
+    unsigned char *hb = m.h_guided, *db = m.d_guided;
+    std::memcpy(hb + o_p, pos_w, 24 * N);
+    std::memcpy(hb + o_off, offsets, 4 * (N + 1));
+    if (total) std::memcpy(hb + o_c, cam_centers, 24 * total);
+    std::memcpy(hb + o_r, ref_center, 24 * N);
+    std::memcpy(hb + o_s, ref_scale_factor, 4 * N);
+    cudaStream_t st = m.stream;
+    B200_CUDA(cudaMemcpyAsync(db, hb, in_bytes, cudaMemcpyHostToDevice, st));
+    b200::match::landmark_geometry_kernel<<<b200::ceil_div(n_landmarks, 128), 128, 0, st>>>(n_landmarks, (const double*)(db + o_p), (const int*)(db + o_off),
+                                                                                         (const double*)(db + o_c), (const double*)(db + o_r),
+                                                                                         (const float*)(db + o_s), inv_scale_factor_last,
+                                                                                         (double*)(db + o_mn), (float*)(db + o_mx), (float*)(db + o_mi));
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaMemcpyAsync(hb + out_begin, db + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(mean_normal, hb + o_mn, 24 * N);
+    std::memcpy(max_valid_dist, hb + o_mx, 4 * N);
+    std::memcpy(min_valid_dist, hb + o_mi, 4 * N);
     return B200_OK;
 }
 

@@ -350,3 +350,18 @@ def landmark_descriptors(desc_lists, device=0):
     out = np.zeros((max(n, 1), 32), np.uint8)
     check(lib().b200_landmark_descriptors(_matcher(device), n, ptr(flat), ptr(offsets), ptr(best), ptr(out)))
     return best[:n], out[:n]
+
+
+def landmark_geometry(pos_w, cam_center_lists, ref_center, ref_scale_factor, inv_scale_factor_last, device=0):
+    """data::landmark::update_mean_normal_and_obs_scale_variance (data/landmark.cc:256-311) for many landmarks.
+    cam_center_lists[l] = (n_l, 3) camera centres of the landmark's observations.  Returns (mean_normal (L,3), max_valid, min_valid)."""
+    n = len(cam_center_lists)
+    cnt = np.array([len(c) for c in cam_center_lists], np.int32)
+    offsets = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int32)
+    flat = np.ascontiguousarray(np.concatenate([np.asarray(c, np.float64).reshape(-1, 3) for c in cam_center_lists]) if n and cnt.sum() else np.zeros((1, 3)))
+    pos, ref = np.ascontiguousarray(pos_w, np.float64).reshape(-1, 3), np.ascontiguousarray(ref_center, np.float64).reshape(-1, 3)
+    sf = np.ascontiguousarray(ref_scale_factor, np.float32)
+    mn, mx, mi = np.zeros((max(n, 1), 3)), np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32)
+    check(lib().b200_landmark_geometry(_matcher(device), n, ptr(pos), ptr(offsets), ptr(flat), ptr(ref), ptr(sf), float(inv_scale_factor_last),
+                                       ptr(mn), ptr(mx), ptr(mi)))
+    return mn[:n], mx[:n], mi[:n]

@@ -58,3 +58,35 @@ def test_gpu_capacity_is_reported():
     with pytest.raises(B200Error) as e:
         match.landmark_descriptors([np.zeros((600, 32), np.uint8)])
     assert e.value.code == ERR_CAPACITY
+
+
+# ---- data::landmark::update_mean_normal_and_obs_scale_variance (data/landmark.cc:256-311) ------------------------------------
+def _geometry_case(seed, n):
+    rng = np.random.default_rng(seed)
+    pos = rng.normal(0, 20, (n, 3))
+    cams = [pos[l] + rng.normal(0, 8, (int(rng.integers(1, 12)), 3)) for l in range(n)]
+    cams[0][0] = pos[0]                                   # an observation from the landmark's own position: normalized() leaves the zero vector
+    ref = np.stack([c[int(rng.integers(0, len(c)))] for c in cams])
+    sf = (np.float32(1.2) ** rng.integers(0, 8, n)).astype(np.float32)
+    return pos, cams, ref, sf, np.float32(1.0) / np.float32(1.2) ** 7
+
+
+def test_geometry_oracle_matches_numpy():
+    pos, cams, ref, sf, inv_last = _geometry_case(5, 300)
+    mn, mx, mi = O.landmark_geometry(pos, cams, ref, sf, inv_last)
+    for l in range(len(pos)):
+        v = pos[l] - cams[l]
+        nr = np.linalg.norm(v, axis=1, keepdims=True)
+        m = np.where(nr > 0, v / np.where(nr > 0, nr, 1), v).sum(0)
+        assert np.allclose(mn[l], m / np.linalg.norm(m), atol=1e-13)
+        d = np.linalg.norm(pos[l] - ref[l])
+        assert np.isclose(mx[l], np.float32(d * float(sf[l])), rtol=1e-6) and mi[l] == np.float32(mx[l] * inv_last)
+
+
+@pytest.mark.gpu
+def test_geometry_gpu_matches_oracle():
+    from stella_vslam_b200 import match
+    pos, cams, ref, sf, inv_last = _geometry_case(6, 5000)
+    mn, mx, mi = match.landmark_geometry(pos, cams, ref, sf, inv_last)
+    mn_w, mx_w, mi_w = O.landmark_geometry(pos, cams, ref, sf, inv_last)
+    assert np.array_equal(mn, mn_w) and np.array_equal(mx, mx_w) and np.array_equal(mi, mi_w)   # same operations in the same order
