@@ -138,6 +138,15 @@ int b200_frame_can_observe(b200_orb_t h, const b200_camera_intrinsics_t* cam, do
                            const float* max_valid_dist, float ray_cos_thr, unsigned num_levels, float log_scale_factor, uint8_t* observable,
                            double* reproj, float* x_right, uint32_t* pred_scale_level);
 
+/* util::convert_to_grayscale (src/stella_vslam/util/image_converter.cc:8-39): cv::cvtColor(COLOR_{RGB,BGR}[A]2GRAY) of
+ * 8-bit frames, the step in front of the extractor (system.cc:370-378).  channels: 3 or 4; rgb_order != 0 <=> color_order_t::RGB.
+ * The host variant converts one frame; the device variant converts `batch` frames in place on the extractor's stream so that
+ * b200_orb_extract_device can follow without a copy (source frames 16-byte aligned, pitches multiples of 4). */
+int b200_convert_to_grayscale(b200_orb_t h, const uint8_t* src, int width, int height, size_t src_pitch, int channels, int rgb_order,
+                              uint8_t* gray, size_t gray_pitch);
+int b200_convert_to_grayscale_device(b200_orb_t h, const void* d_src, int width, int height, size_t src_pitch, size_t src_frame_stride,
+                                     int channels, int rgb_order, void* d_gray, size_t gray_pitch, size_t gray_frame_stride, int batch);
+
 /* Per-stage kernel time of the last extract, in ms, measured with CUDA events on the instance stream.
  * stage: 0 pyramid, 1 FAST+NMS+grid arg-max, 2 ordered selection, 3 descriptor blur, 4 orientation+rBRIEF, 5 whole extract. */
 int b200_orb_stage_ms(b200_orb_t h, int stage, float* ms);

@@ -53,6 +53,8 @@ int orc_orb_extract(const uint8_t* img, int w, int h, int stride, const uint8_t*
                     const orc_orb_config_t* cfg, orc_keypoint_t* kps, uint8_t* descs, int cap, int* level_counts,
                     int* raw_counts, uint8_t** pyramid_out);
 
+void orc_convert_to_grayscale(const uint8_t* src, int w, int h, int stride, int channels, int rgb_order, uint8_t* dst, int dstride);
+
 /* ---- matchers --------------------------------------------------------------------------------- */
 unsigned orc_hamming_32(const uint8_t* a, const uint8_t* b);
 unsigned orc_hamming_64(const uint8_t* a, const uint8_t* b);

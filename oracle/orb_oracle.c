@@ -474,3 +474,16 @@ done:
     free(sf);
     return overflow ? -1 : total;
 }
+
+/* util::convert_to_grayscale (src/stella_vslam/util/image_converter.cc:8-39): cv::cvtColor(COLOR_{RGB,BGR,RGBA,BGRA}2GRAY) on 8-bit
+ * images (EXT: OpenCV imgproc, RGB2Gray<uchar>: 15-bit coefficients R 9798, G 19235, B 3735, rounding 1 << 14; pinned against cv2 4.13
+ * by tests/test_gray.py).  channels: 3 or 4; rgb_order != 0: the first channel is R. */
+void orc_convert_to_grayscale(const uint8_t* src, int w, int h, int stride, int channels, int rgb_order, uint8_t* dst, int dstride) {
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* p = src + (size_t)y * stride + (size_t)x * channels;
+            const int c0 = p[0], g = p[1], c2 = p[2];
+            const int r = rgb_order ? c0 : c2, b = rgb_order ? c2 : c0;
+            dst[(size_t)y * dstride + x] = (uint8_t)((b * 3735 + g * 19235 + r * 9798 + (1 << 14)) >> 15);
+        }
+}

@@ -465,3 +465,15 @@ def landmark_geometry(pos_w, cam_center_lists, ref_center, ref_scale_factor, inv
     L.orc_landmark_geometry.restype = None
     L.orc_landmark_geometry(n, _p(pos), _p(offsets), _p(flat), _p(ref), _p(sf), float(inv_scale_factor_last), _p(mn), _p(mx), _p(mi))
     return mn[:n], mx[:n], mi[:n]
+
+
+def convert_to_grayscale(img, in_color_order="BGR"):
+    """orc_convert_to_grayscale: (h, w, 3|4) uint8 -> (h, w) uint8."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, c = img.shape
+    out = np.empty((h, w), np.uint8)
+    L = lib()
+    L.orc_convert_to_grayscale.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    L.orc_convert_to_grayscale.restype = None
+    L.orc_convert_to_grayscale(_p(img), w, h, img.strides[0], c, 1 if in_color_order == "RGB" else 0, _p(out), out.strides[0])
+    return out

@@ -132,7 +132,7 @@ SYMBOLS = [
     "b200_last_error", "b200_device_count", "b200_version", "b200_host_alloc", "b200_host_free",
     "b200_orb_default_params", "b200_orb_create", "b200_orb_destroy", "b200_orb_max_keypoints", "b200_orb_extract",
     "b200_orb_extract_device", "b200_orb_set_stream", "b200_orb_bind_outputs", "b200_orb_reserve", "b200_orb_fetch", "b200_orb_device_results", "b200_orb_sync", "b200_orb_level_info",
-    "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_pyramid_level_view", "b200_keypoints_undistort", "b200_frame_can_observe", "b200_orb_stage_ms", "b200_orb_enable_timing",
+    "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_pyramid_level_view", "b200_convert_to_grayscale", "b200_convert_to_grayscale_device", "b200_keypoints_undistort", "b200_frame_can_observe", "b200_orb_stage_ms", "b200_orb_enable_timing",
     "b200_matcher_create", "b200_matcher_destroy", "b200_hamming_matrix", "b200_match_bruteforce",
     "b200_match_bruteforce_device", "b200_match_guided", "b200_match_cross_check", "b200_match_pairs", "b200_stereo_compute", "b200_landmark_descriptors", "b200_landmark_geometry", "b200_matcher_set_stream", "b200_matcher_sync",
     "b200_lba_create", "b200_lba_destroy", "b200_lba_solve", "b200_pose_optimize", "b200_lba_last_profile",
@@ -188,6 +188,8 @@ def lib():
     L.b200_frame_can_observe.argtypes = [vp, C.POINTER(CameraIntrinsics), C.c_double, vp, vp, i32, vp, vp, vp, vp, C.c_float, C.c_uint, C.c_float,
                                          vp, vp, vp, vp]
     L.b200_landmark_geometry.argtypes = [vp, i32, vp, vp, vp, vp, vp, C.c_float, vp, vp, vp]
+    L.b200_convert_to_grayscale.argtypes = [vp, vp, i32, i32, sz, i32, i32, vp, sz]
+    L.b200_convert_to_grayscale_device.argtypes = [vp, vp, i32, i32, sz, sz, i32, i32, vp, sz, sz, i32]
     L.b200_matcher_set_stream.argtypes = [vp, vp, i32]
     _lib = L
     return L

@@ -1223,6 +1223,46 @@ __global__ void __launch_bounds__(128) undistort_bearings_kernel(CamModel c, con
     }
 }
 
+// util::convert_to_grayscale (src/stella_vslam/util/image_converter.cc:8-39) = cv::cvtColor(COLOR_{RGB,BGR}[A]2GRAY) for 8-bit frames:
+// gray = (B 3735 + G 19235 + R 9798 + 2^14) >> 15.  Pure streaming (3 or 4 bytes in, 1 byte out per pixel): one thread converts
+// four pixels from three (four) 32-bit loads into one 32-bit store; rows are independent so any pitch that is a multiple of 4 works.
+template <int kChannels>
+__global__ void __launch_bounds__(256) gray_kernel(const unsigned char* __restrict__ src, unsigned long long spitch, unsigned long long sframe,
+                                                   unsigned char* __restrict__ dst, unsigned long long dpitch, unsigned long long dframe, int w, int h,
+                                                   int rgb_order) {
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    const int x0 = gx * 4;
+    if (x0 >= w) return;
+    const unsigned char* srow = src + (size_t)f * sframe + (size_t)y * spitch;
+    unsigned char* drow = dst + (size_t)f * dframe + (size_t)y * dpitch;
+    const unsigned cr = rgb_order ? 9798u : 3735u, cb = rgb_order ? 3735u : 9798u;  // weight of channel 0 / channel 2
+    if (x0 + 4 <= w) {
+        const unsigned* p = reinterpret_cast<const unsigned*>(srow + (size_t)x0 * kChannels);
+        unsigned px[4];  // channel bytes of pixel k in the low 24 bits
+        if (kChannels == 4) {
+            px[0] = p[0]; px[1] = p[1]; px[2] = p[2]; px[3] = p[3];  // (rows are only 4-byte aligned in general)
+        } else {
+            const unsigned a = p[0], b = p[1], c = p[2];
+            px[0] = a;
+            px[1] = __funnelshift_r(a, b, 24);
+            px[2] = __funnelshift_r(b, c, 16);
+            px[3] = c >> 8;
+        }
+        unsigned out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const unsigned c0 = px[k] & 0xFF, c1 = (px[k] >> 8) & 0xFF, c2 = (px[k] >> 16) & 0xFF;
+            out |= ((c0 * cr + c1 * 19235u + c2 * cb + (1u << 14)) >> 15) << (8 * k);
+        }
+        *reinterpret_cast<unsigned*>(drow + x0) = out;
+    } else {
+        for (int x = x0; x < w; ++x) {
+            const unsigned char* q = srow + (size_t)x * kChannels;
+            drow[x] = (unsigned char)((q[0] * cr + q[1] * 19235u + q[2] * cb + (1u << 14)) >> 15);
+        }
+    }
+}
+
 // data::frame::can_observe (src/stella_vslam/data/frame.cc:59-84) for the landmarks of the local map (tracking_module.cc:559-594):
 // reproject_to_image (camera/perspective.cc:130-148, equirectangular.cc:59-73), landmark::is_inside_in_orb_scale
 // (data/landmark.h:88-92), the viewing-angle test and landmark::predict_scale_level (data/landmark.cc:336-353).  Thread per landmark.
@@ -1645,6 +1685,48 @@ int b200_frame_can_observe(b200_orb_t h, const b200_camera_intrinsics_t* cam, do
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return b200::cuda_fail(e, "b200_frame_can_observe", __FILE__, __LINE__);
     return B200_OK;
+}
+
+int b200_convert_to_grayscale_device(b200_orb_t h, const void* d_src, int width, int height, size_t src_pitch, size_t src_frame_stride, int channels,
+                                     int rgb_order, void* d_gray, size_t gray_pitch, size_t gray_frame_stride, int batch) {
+    if (!h || !d_src || !d_gray || width <= 0 || height <= 0 || batch <= 0 || (channels != 3 && channels != 4)
+        || src_pitch < (size_t)width * channels || gray_pitch < (size_t)width || (src_pitch & 3) || (gray_pitch & 3)
+        || ((uintptr_t)d_src & 15) || ((uintptr_t)d_gray & 3) || (src_frame_stride & 15) || (gray_frame_stride & 3)) {
+        b200::set_error("b200_convert_to_grayscale_device: 3 or 4 channels, pitches multiples of 4, source frames 16-byte aligned");
+        return B200_ERR_INVALID;
+    }
+    Extractor& ex = h->ex;
+    B200_CUDA(cudaSetDevice(ex.prm.device));
+    const dim3 grid(b200::ceil_div(b200::ceil_div(width, 4), 256), height, batch);
+    if (channels == 4)
+        b200::orb::gray_kernel<4><<<grid, 256, 0, ex.stream>>>((const unsigned char*)d_src, src_pitch, src_frame_stride, (unsigned char*)d_gray, gray_pitch,
+                                                             gray_frame_stride, width, height, rgb_order);
+    else
+        b200::orb::gray_kernel<3><<<grid, 256, 0, ex.stream>>>((const unsigned char*)d_src, src_pitch, src_frame_stride, (unsigned char*)d_gray, gray_pitch,
+                                                             gray_frame_stride, width, height, rgb_order);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+
+int b200_convert_to_grayscale(b200_orb_t h, const uint8_t* src, int width, int height, size_t src_pitch, int channels, int rgb_order, uint8_t* gray,
+                              size_t gray_pitch) {
+    if (!h || !src || !gray || width <= 0 || height <= 0 || (channels != 3 && channels != 4) || src_pitch < (size_t)width * channels
+        || gray_pitch < (size_t)width)
+        return B200_ERR_INVALID;
+    Extractor& ex = h->ex;
+    B200_CUDA(cudaSetDevice(ex.prm.device));
+    const size_t sp = b200::round_up((size_t)width * channels, (size_t)16), gp = b200::round_up((size_t)width, (size_t)16);
+    unsigned char* d = nullptr;
+    B200_CUDA(cudaMallocAsync((void**)&d, (sp + gp) * (size_t)height + 256, ex.stream));
+    unsigned char* d_gray = d + b200::round_up(sp * (size_t)height, (size_t)256);
+    cudaError_t e = cudaMemcpy2DAsync(d, sp, src, src_pitch, (size_t)width * channels, height, cudaMemcpyHostToDevice, ex.stream);
+    int rc = B200_OK;
+    if (e == cudaSuccess) rc = b200_convert_to_grayscale_device(h, d, width, height, sp, 0, channels, rgb_order, d_gray, gp, 0, 1);
+    if (e == cudaSuccess && rc == B200_OK) e = cudaMemcpy2DAsync(gray, gray_pitch, d_gray, gp, width, height, cudaMemcpyDeviceToHost, ex.stream);
+    cudaFreeAsync(d, ex.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ex.stream);
+    if (e != cudaSuccess) return b200::cuda_fail(e, "b200_convert_to_grayscale", __FILE__, __LINE__);
+    return rc;
 }
 
 int b200_orb_enable_timing(b200_orb_t h, int enable) {

@@ -175,6 +175,18 @@ class orb_extractor:
                                            ptr(ok), ptr(rp), ptr(xr), ptr(lv)))
         return dict(observable=ok[:n].astype(bool), reproj=rp[:n], x_right=xr[:n], pred_scale_level=lv[:n])
 
+    def convert_to_grayscale(self, img, in_color_order="BGR"):
+        """util::convert_to_grayscale (util/image_converter.cc:8-39): (h, w, 3|4) uint8 -> (h, w) uint8; a 1-channel image or
+        in_color_order == "Gray" is returned unchanged."""
+        img = np.asarray(img)
+        if img.ndim == 2 or in_color_order == "Gray":
+            return img
+        img = np.ascontiguousarray(img, np.uint8)
+        h, w, c = img.shape
+        out = np.empty((h, w), np.uint8)
+        check(lib().b200_convert_to_grayscale(self._h, ptr(img), w, h, img.strides[0], c, 1 if in_color_order == "RGB" else 0, ptr(out), out.strides[0]))
+        return out
+
     def enable_timing(self, on=True):
         check(lib().b200_orb_enable_timing(self._h, int(on)))
 
