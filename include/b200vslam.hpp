@@ -8,6 +8,7 @@
 //   b200::match::robust            <->  stella_vslam::match::robust            (match/robust.h, match/base.h:81-91)
 //   b200::match::projection / fuse / area / bow_tree / stereo  <->  match/projection.h, fuse.h, area.h, bow_tree.h, stereo.h
 //   b200::optimize::local_bundle_adjuster <-> stella_vslam::optimize::local_bundle_adjuster (optimize/local_bundle_adjuster.h:15-24)
+//   b200::optimize::pose_optimizer        <-> stella_vslam::optimize::pose_optimizer        (optimize/pose_optimizer.h:24-40)
 #pragma once
 
 #include <cmath>
@@ -328,6 +329,30 @@ public:
 
 private:
     const unsigned int num_first_iter_, num_second_iter_;
+    b200_lba_t h_ = nullptr;
+};
+
+class pose_optimizer {  // optimize/pose_optimizer.h:24-40 with Tracking.backend: "b200" (pose_optimizer_g2o.h:30-37 defaults)
+public:
+    explicit pose_optimizer(unsigned int num_trials_robust = 2, unsigned int num_trials = 2, unsigned int num_each_iter = 10, int device = 0)
+        : num_trials_robust_(num_trials_robust), num_trials_(num_trials), num_each_iter_(num_each_iter) {
+        check(b200_lba_create(device, &h_), "b200_lba_create");
+    }
+    ~pose_optimizer() { b200_lba_destroy(h_); }
+    pose_optimizer(const pose_optimizer&) = delete;
+    // one flattened frame (one free pose, fixed landmarks, one edge per observation); returns num_init_obs - num_bad_obs
+    unsigned int optimize(const b200_lba_problem_t& frame, double (&optimized_pose)[16], std::vector<bool>& outlier_flags) const {
+        std::vector<uint8_t> flags((size_t)(frame.n_edges > 0 ? frame.n_edges : 1));
+        uint32_t n_valid = 0;
+        check(b200_pose_optimize(h_, 1, &frame, (int)num_trials_robust_, (int)num_trials_, (int)num_each_iter_, optimized_pose, flags.data(), &n_valid),
+              "b200_pose_optimize");
+        outlier_flags.assign((size_t)frame.n_edges, false);
+        for (int e = 0; e < frame.n_edges; ++e) outlier_flags[e] = flags[e] != 0;
+        return n_valid;
+    }
+
+private:
+    const unsigned int num_trials_robust_, num_trials_, num_each_iter_;
     b200_lba_t h_ = nullptr;
 };
 
