@@ -1263,6 +1263,55 @@ __global__ void __launch_bounds__(256) gray_kernel(const unsigned char* __restri
     }
 }
 
+// 16 pixels per thread with 128-bit loads / stores for frames whose rows are 16-byte aligned (the usual case: 1920 x 3 = 5760 B).
+template <int kChannels>
+__global__ void __launch_bounds__(128) gray16_kernel(const unsigned char* __restrict__ src, unsigned long long spitch, unsigned long long sframe,
+                                                     unsigned char* __restrict__ dst, unsigned long long dpitch, unsigned long long dframe, int w, int h,
+                                                     int rgb_order) {
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+    const int x0 = gx * 16;
+    if (x0 >= w) return;
+    const unsigned char* srow = src + (size_t)f * sframe + (size_t)y * spitch;
+    unsigned char* drow = dst + (size_t)f * dframe + (size_t)y * dpitch;
+    const unsigned cr = rgb_order ? 9798u : 3735u, cb = rgb_order ? 3735u : 9798u;
+    if (x0 + 16 <= w) {
+        unsigned wds[4 * kChannels];  // 16 pixels = 12 (16) words
+        const uint4* p = reinterpret_cast<const uint4*>(srow + (size_t)x0 * kChannels);
+#pragma unroll
+        for (int i = 0; i < kChannels; ++i) {
+            const uint4 v = p[i];
+            wds[4 * i] = v.x; wds[4 * i + 1] = v.y; wds[4 * i + 2] = v.z; wds[4 * i + 3] = v.w;
+        }
+        unsigned out[4];
+#pragma unroll
+        for (int g4 = 0; g4 < 4; ++g4) {  // four pixels at a time, as in gray_kernel
+            unsigned px[4];
+            if (kChannels == 4) {
+                px[0] = wds[4 * g4]; px[1] = wds[4 * g4 + 1]; px[2] = wds[4 * g4 + 2]; px[3] = wds[4 * g4 + 3];
+            } else {
+                const unsigned a = wds[3 * g4], b = wds[3 * g4 + 1], c = wds[3 * g4 + 2];
+                px[0] = a;
+                px[1] = __funnelshift_r(a, b, 24);
+                px[2] = __funnelshift_r(b, c, 16);
+                px[3] = c >> 8;
+            }
+            unsigned o = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned c0 = px[k] & 0xFF, c1 = (px[k] >> 8) & 0xFF, c2 = (px[k] >> 16) & 0xFF;
+                o |= ((c0 * cr + c1 * 19235u + c2 * cb + (1u << 14)) >> 15) << (8 * k);
+            }
+            out[g4] = o;
+        }
+        *reinterpret_cast<uint4*>(drow + x0) = make_uint4(out[0], out[1], out[2], out[3]);
+    } else {
+        for (int x = x0; x < w; ++x) {
+            const unsigned char* q = srow + (size_t)x * kChannels;
+            drow[x] = (unsigned char)((q[0] * cr + q[1] * 19235u + q[2] * cb + (1u << 14)) >> 15);
+        }
+    }
+}
+
 // data::frame::can_observe (src/stella_vslam/data/frame.cc:59-84) for the landmarks of the local map (tracking_module.cc:559-594):
 // reproject_to_image (camera/perspective.cc:130-148, equirectangular.cc:59-73), landmark::is_inside_in_orb_scale
 // (data/landmark.h:88-92), the viewing-angle test and landmark::predict_scale_level (data/landmark.cc:336-353).  Thread per landmark.
@@ -1697,6 +1746,17 @@ int b200_convert_to_grayscale_device(b200_orb_t h, const void* d_src, int width,
     }
     Extractor& ex = h->ex;
     B200_CUDA(cudaSetDevice(ex.prm.device));
+    if (!(src_pitch & 15) && !(gray_pitch & 15) && !((uintptr_t)d_gray & 15) && !(gray_frame_stride & 15)) {  // 128-bit path
+        const dim3 grid16(b200::ceil_div(b200::ceil_div(width, 16), 128), height, batch);
+        if (channels == 4)
+            b200::orb::gray16_kernel<4><<<grid16, 128, 0, ex.stream>>>((const unsigned char*)d_src, src_pitch, src_frame_stride, (unsigned char*)d_gray,
+                                                                     gray_pitch, gray_frame_stride, width, height, rgb_order);
+        else
+            b200::orb::gray16_kernel<3><<<grid16, 128, 0, ex.stream>>>((const unsigned char*)d_src, src_pitch, src_frame_stride, (unsigned char*)d_gray,
+                                                                     gray_pitch, gray_frame_stride, width, height, rgb_order);
+        B200_CUDA(cudaGetLastError());
+        return B200_OK;
+    }
     const dim3 grid(b200::ceil_div(b200::ceil_div(width, 4), 256), height, batch);
     if (channels == 4)
         b200::orb::gray_kernel<4><<<grid, 256, 0, ex.stream>>>((const unsigned char*)d_src, src_pitch, src_frame_stride, (unsigned char*)d_gray, gray_pitch,

@@ -33,3 +33,28 @@ def test_gpu_matches_oracle(order, ch):
         assert np.array_equal(ex.convert_to_grayscale(img, order), O.convert_to_grayscale(img, order))
     gray = rng.integers(0, 256, (10, 10), dtype=np.uint8)
     assert ex.convert_to_grayscale(gray) is gray
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ch", [3, 4])
+def test_gpu_device_batch_both_paths(ch):
+    """The batched device entry: 128-bit path (16-byte aligned rows) and the 32-bit path (rows only 4-byte aligned)."""
+    import torch
+    from stella_vslam_b200 import feature
+    from stella_vslam_b200._lib import check, lib
+    ex = feature.orb_extractor(feature.orb_params(), 800)
+    for w, pad in ((1920, 0), (1000, 0), (1001, 1), (37, 0)):
+        b, h = 3, 21
+        sp = (w * ch + 3) // 4 * 4 + 4 * pad                     # source pitch: multiple of 4, multiple of 16 only for some widths
+        gp = (w + 3) // 4 * 4
+        src = torch.randint(0, 256, (b, h, sp), dtype=torch.uint8, device="cuda")
+        dst = torch.zeros((b, h, gp), dtype=torch.uint8, device="cuda")
+        fs = (h * sp + 15) // 16 * 16
+        srcbuf = torch.zeros(b * fs + 16, dtype=torch.uint8, device="cuda")
+        for f in range(b):
+            srcbuf[f * fs:f * fs + h * sp] = src[f].reshape(-1)
+        check(lib().b200_convert_to_grayscale_device(ex._h, srcbuf.data_ptr(), w, h, sp, fs, ch, 1, dst.data_ptr(), gp, h * gp, b))
+        torch.cuda.synchronize()
+        for f in range(b):
+            img = src[f].cpu().numpy()[:, :w * ch].reshape(h, w, ch)
+            assert np.array_equal(dst[f].cpu().numpy()[:, :w], O.convert_to_grayscale(img, "RGB")), (w, f)
