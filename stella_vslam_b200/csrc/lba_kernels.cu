@@ -1894,7 +1894,8 @@ int b200_lba_create(int device, b200_lba_t* out) {
     // Local BA is the mapping thread's work (mapping_module.cc:63): tracking must not wait for it.  Its ~130 small launches per
     // window are latency-bound (each one leaves most SMs idle), so on the highest stream priority every one of them pre-empts the wide
     // front-end grids for its whole duration (measured: FAST 2.0 -> 2.9 ms per 64 frames with four windows in flight); on the lowest
-    // priority its CTAs fill the gaps instead.  B200_LBA_PRIORITY=high|normal|low overrides.
+    // priority its CTAs fill the gaps instead (lowest == the default priority 0 of ordinary streams on this GPU; the range is [0, -5]).
+    // B200_LBA_PRIORITY=high|normal|low overrides.
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     int prio = prio_lo;
