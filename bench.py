@@ -24,6 +24,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# Up to 17 streams carry work at once here (the front end + 16 local-BA windows).  The driver multiplexes streams onto
+# CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8): a window whose stream shares a queue with the front end is serialised behind
+# the 2-3 steps of front-end work the device-resident arm keeps queued, which is the suspected cause of that arm's occasional
+# collapse.  Give every stream its own queue; must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 W, H = 1920, 1080
 TARGET_KPTS = 2000
