@@ -34,7 +34,11 @@ W, H = 1920, 1080
 TARGET_KPTS = 2000
 METRIC = "frames/sec (ORB+match+local BA) @1920x1080, 2000 kpts"
 LOWE, CHECK_ORI = 0.8, True  # robust matcher as constructed by frame_tracker (module/frame_tracker.cc:98)
-LBA_DEPTH = int(os.environ.get("B200_BENCH_LBA_DEPTH", "4"))  # local-BA windows stay in flight for up to this many steps (asynchronous mapping thread)
+# Local BA runs asynchronously next to the front end, like the reference's mapping thread (mapping_module.cc:63,206): the windows of
+# LBA_BATCH_STEPS consecutive steps are solved by ONE b200_lba_solve_batch call (lockstep launch sequence), up to LBA_INFLIGHT such
+# batches are in flight on their own streams, and every window submitted inside a timed region is joined before the closing event.
+LBA_BATCH_STEPS = float(os.environ.get("B200_BENCH_LBA_BATCH_STEPS", "1"))   # may be fractional: 0.5 = two batches per step
+LBA_INFLIGHT = int(os.environ.get("B200_BENCH_LBA_INFLIGHT", "4"))
 
 
 def parse_args():
@@ -271,35 +275,70 @@ def main():
     stream_id = multi_gpu.assign_streams(world, world, rank)[0]   # one stream per GPU (BASELINE config 5)
     assert stream_id == rank
 
-    # local BA: one KITTI-sized window (BASELINE config 4) per --lba-every frames, solved concurrently on a pool of handles
+    # local BA: one KITTI-sized window (BASELINE config 4) per --lba-every frames
     n_lba = 0 if args.no_lba else max(1, B // args.lba_every)
     lba_pool, lba_handles, lba_problem = None, [], None
+    lba_preps = {}
     if n_lba:
         from concurrent.futures import ThreadPoolExecutor
 
         from stella_vslam_b200 import optimize
         lba_problem = synth.make_ba_problem(50, 10, 10000, seed=rank, model="stereo")
-        # LBA_DEPTH generations of handles: the windows submitted in step s are joined in step s+LBA_DEPTH-1, i.e. local BA runs asynchronously
-        # next to tracking exactly like the reference's mapping thread (mapping_module.cc:63,206); every window submitted inside
-        # the timed region is joined before the closing event
-        lba_handles = [[optimize.local_bundle_adjuster(device=local_rank) for _ in range(n_lba)] for _ in range(LBA_DEPTH)]
-        lba_pool = ThreadPoolExecutor(LBA_DEPTH * n_lba)
-        lba_prepared = [[hd.prepare(lba_problem) for hd in gen] for gen in lba_handles]  # one packed problem + outputs per handle
-    lba_launches = [0]
-    lba_inflight = []
-    lba_gen = [0]
+        lba_handles = [optimize.local_bundle_adjuster(device=local_rank) for _ in range(LBA_INFLIGHT)]
+        lba_pool = ThreadPoolExecutor(LBA_INFLIGHT)
+    lba_state = {"launches": 0, "windows": 0, "pending": 0, "next": 0, "ref": None}
+    lba_inflight = []   # (future, handle index)
+
+    def lba_prep(hidx, n):
+        key = (hidx, n)
+        if key not in lba_preps:
+            lba_preps[key] = lba_handles[hidx].prepare_batch([lba_problem] * n)
+        return lba_preps[key]
+
+    def lba_run(hidx, n):
+        prep = lba_prep(hidx, n)
+        launches = lba_handles[hidx].optimize_prepared_batch(prep)
+        st = prep["st"][n - 1]
+        return launches, n, (list(st.iterations), st.n_outliers)
+
+    def lba_collect(fut):
+        launches, n, sig = fut.result()
+        lba_state["launches"] += launches
+        lba_state["windows"] += n
+        if lba_state["ref"] is None:
+            lba_state["ref"] = sig
+        assert sig == lba_state["ref"], "local-BA windows of the same problem disagree"
+
+    def lba_dispatch(n):
+        hidx = lba_state["next"]
+        lba_state["next"] = (hidx + 1) % LBA_INFLIGHT
+        for item in [it for it in lba_inflight if it[1] == hidx]:   # the handle's previous batch must be done
+            lba_collect(item[0])
+            lba_inflight.remove(item)
+        lba_inflight.append((lba_pool.submit(lba_run, hidx, n), hidx))
 
     def lba_submit():
         if not n_lba:
             return
-        g_ = lba_gen[0]
-        lba_inflight.append([lba_pool.submit(hd.optimize_prepared, pp) for hd, pp in zip(lba_handles[g_], lba_prepared[g_])])
-        lba_gen[0] = (lba_gen[0] + 1) % LBA_DEPTH
+        lba_state["pending"] += n_lba
+        per_batch = max(1, int(round(n_lba * LBA_BATCH_STEPS)))
+        while lba_state["pending"] >= per_batch:
+            lba_dispatch(per_batch)
+            lba_state["pending"] -= per_batch
 
-    def lba_join(keep=LBA_DEPTH - 1):
-        while len(lba_inflight) > keep:
-            for f in lba_inflight.pop(0):
-                lba_launches[0] = f.result()
+    def lba_join(keep=None):
+        """keep=None: only make room (at most LBA_INFLIGHT batches in flight); keep=0: flush the pending windows and join everything."""
+        if not n_lba:
+            return
+        if keep == 0:
+            if lba_state["pending"]:
+                lba_dispatch(lba_state["pending"])
+                lba_state["pending"] = 0
+            while lba_inflight:
+                lba_collect(lba_inflight.pop(0)[0])
+            return
+        while len(lba_inflight) > LBA_INFLIGHT:
+            lba_collect(lba_inflight.pop(0)[0])
 
     def step_device():
         lba_submit()
@@ -336,11 +375,14 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage_acc = np.zeros(6)
     barrier()
+    lba_state["launches"] = lba_state["windows"] = 0
     e0.record()
     for _ in range(args.steps):
         step_device()
     lba_join(0)          # every window submitted inside the timed region has completed
     e1.record()
+    lba_launches_value, lba_windows_value = lba_state["launches"], lba_state["windows"]
+    assert lba_windows_value == n_lba * args.steps
     barrier()
     ms_total = e0.elapsed_time(e1)
     # per-stage device times of the last timed step (events recorded on the same stream inside the timed region)
@@ -470,12 +512,13 @@ def main():
                    "l2": f"inputs larger than L2: {B} frames x {W * H / 1e6:.2f} MB + {B} pyramids",
                    "lba": (f"{n_lba} local-BA windows per step (one per {args.lba_every} frames): 50 keyframes (10 fixed), 10000 landmarks, "
                            f"{len(lba_problem['e_pose'])} stereo observations, 5+10 LM iterations, solved asynchronously next to the front end "
-                           f"(joined up to {LBA_DEPTH - 1} steps later; all joined inside the timed region)")
+                           f"(b200_lba_solve_batch: {max(1, int(round(n_lba * LBA_BATCH_STEPS)))} windows per launch sequence, up to {LBA_INFLIGHT} batches in flight; "
+                           f"all joined inside the timed region)")
                    if n_lba else "disabled"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * e2e_s / args.steps},
-        "gpu_launches": (13 + n_lba * lba_launches[0]) * args.steps,
+        "gpu_launches": 13 * args.steps + lba_launches_value,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "stage_ms": {n_: stage_ms[i] for i, n_ in enumerate(names + ["extract_total"])},

@@ -360,9 +360,29 @@ int b200_lba_destroy(b200_lba_t h);
  * sets it when it stops a round (terminate_action.cc:55-72 via g2o's setOptimizerStopFlag), which is what makes the
  * reference skip the second round after an early first-round stop (:317-321).
  * Returns B200_ERR_ABORTED (nothing written) when *force_stop is already set on entry (:308-310).
- * pose_cw_out: K x 16, points_out: L x 3, outlier_out: E (1 = observation to erase, :354-375). */
+ * With force_stop == NULL the gain stop of the first round lands in g2o's own auxiliary flag, which the second optimize() resets:
+ * the second round always runs.  Deviation: the reference's terminate_action also CLEARS the caller's flag at iteration -1 of each
+ * optimize() (terminate_action.cc:46-51), so an abort raised in the few microseconds between the entry test and the first iteration
+ * is lost there; here an externally raised flag is never cleared, it stops the solve at the next iteration boundary.
+ * At most 166 FREE keyframes (B200_ERR_INVALID beyond; fixed keyframes are not limited).
+ * pose_cw_out: K x 16, points_out: L x 3, outlier_out: E (1 = observation to erase, :354-375).  Same code path as the batch of one. */
 int b200_lba_solve(b200_lba_t h, const b200_lba_problem_t* problem, int iters1, int iters2, volatile uint8_t* force_stop,
                    double* pose_cw_out, double* points_out, uint8_t* outlier_out, b200_lba_stats_t* stats);
+/* Many independent windows in ONE launch sequence (the batched form is what makes local BA GPU-shaped).  The reference
+ * runs one optimize() per new keyframe on the mapping thread (mapping_module.cc:199-206); an integrator with several maps / streams
+ * (BASELINE config 5) or a backlog of keyframes hands all pending windows to one call.  The windows advance in lockstep, every
+ * kernel serves all of them (window = blockIdx.y, one thread-block cluster per window for the reduced-system Cholesky), the
+ * Levenberg-Marquardt decisions are taken on the device per window, and the plan (edges sorted by landmark, per-keyframe edge lists)
+ * is built on the device: the host copies the caller's arrays and enqueues.
+ *   force_stop[w]  : per-window abort flag as in b200_lba_solve (array may be NULL, entries may be NULL)
+ *   pose_cw_out[w] / points_out[w] / outlier_out[w] : per-window outputs (outlier_out or its entries may be NULL)
+ *   stats          : n_windows entries or NULL
+ *   status[w]      : B200_OK, B200_ERR_ABORTED (flag already set on entry: nothing written for that window) or B200_ERR_INVALID
+ * Limits: at most 166 FREE keyframes per window (the reduced system is factored on chip); fixed keyframes, landmarks and
+ * observations are limited by memory only.  Returns B200_OK if every window that ran is valid. */
+int b200_lba_solve_batch(b200_lba_t h, int n_windows, const b200_lba_problem_t* problems, int iters1, int iters2,
+                         volatile uint8_t* const* force_stop, double* const* pose_cw_out, double* const* points_out,
+                         uint8_t* const* outlier_out, b200_lba_stats_t* stats, int32_t* status);
 /* optimize::pose_optimizer::optimize  (src/stella_vslam/optimize/pose_optimizer.h:24-40, pose_optimizer_g2o.cc:38-175; factory
  * defaults num_trials_robust = 2, num_trials = 2, num_each_iter = 10, pose_optimizer_factory.h:18-47): motion-only bundle adjustment
  * of `n_problems` frames in one launch.  Each problem uses the b200_lba_problem_t layout with exactly ONE pose (free), the landmarks
@@ -373,6 +393,12 @@ int b200_lba_solve(b200_lba_t h, const b200_lba_problem_t* problem, int iters1, 
 int b200_pose_optimize(b200_lba_t h, int n_problems, const b200_lba_problem_t* problems, int num_trials_robust, int num_trials,
                        int num_each_iter, double* pose_cw_out, uint8_t* outlier_flags, uint32_t* n_valid);
 
+/* Profiling mode: an event after every launch of the following solves (adds a few microseconds per launch; off by default).
+ * b200_lba_kernel_ms reports, for the LAST batch, the summed device time and the number of intervals of
+ *   kernel 0 plan (5 launches, one interval), 1 landmark pass / build, 2 keyframe rows, 3 Schur rows, 4 reduced-system Cholesky,
+ *   5 back-substitution, 6 landmark pass / trial chi2, 7 everything after the last repetition (round tails, outliers, export). */
+int b200_lba_enable_profile(b200_lba_t h, int enable);
+int b200_lba_kernel_ms(b200_lba_t h, int kernel, float* total_ms, int* launches);
 /* Device time (ms, CUDA events) spent in the kernels of the last solve, and the number of kernel launches. */
 int b200_lba_last_profile(b200_lba_t h, float* gpu_ms, int* launches);
 

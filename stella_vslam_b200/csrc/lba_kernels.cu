@@ -10,10 +10,11 @@
 // and g2o's published algorithm (tag 20230223_git, not vendored): BaseBinaryEdge::constructQuadraticForm with
 // RobustKernelHuber, BlockSolver_6_3 (Schur complement over the landmarks), OptimizationAlgorithmLevenberg.
 //
-// Layout: edges are sorted by landmark (CSR), so every landmark-side quantity (Hll, bl, Dinv, back-substitution) is a
-// contiguous, atomics-free reduction; pose-side blocks are built by one CTA per free keyframe; the Schur complement is a
-// block-sparse  Hschur(i,j) = Hpp(i,j) - sum_l Hpl(i,l) Dinv(l) Hpl(j,l)^T  evaluated by one warp per (i,j) block over a
-// pair list built once per solve.  Everything is deterministic (fixed reduction orders, no floating-point atomics).
+// Layout: edges are sorted by landmark (CSR, built on the device), so every landmark-side quantity (Hll, bl, Dinv,
+// back-substitution) is a contiguous, atomics-free reduction; pose-side blocks are built by one CTA per free keyframe; the Schur
+// complement is a block-sparse  Hschur(i,j) = Hpp(i,j) - sum_l Hpl(i,l) Dinv(l) Hpl(j,l)^T  evaluated by one CTA per block row
+// whose 6x3 * 3x6 products are fp64 tensor-core instructions (DMMA).  Many windows are solved per launch sequence
+// (b200_lba_solve_batch).  Everything is deterministic (fixed reduction orders, no floating-point atomics).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -50,16 +51,6 @@ struct EdgeS {
     unsigned char cam, robust, can_outlier, pad;
 };
 
-struct View {
-    int K, L, E, Kf, Lf;
-    const EdgeS* edges;
-    const Cam* cams;
-    const int* pt_start;     // L+1 (all landmarks)
-    const int* pose_start;   // Kf+1
-    const int* pose_edges;   // edge ids grouped by free pose
-    unsigned char* level;    // E: 0 active, 1 outlier
-    unsigned char* robust;   // E: Huber on/off for the current round
-};
 
 // ---------------------------------------------------------------------------------------------------------------
 // geometry
@@ -184,170 +175,535 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {  // determin
     return r;
 }
 
+
+// The 6x3 block Hpl of an edge is a 160-byte record (18 doubles + 2 of padding), 32-byte aligned: a thread that reads a whole record
+// does it with five 256-bit loads, i.e. in whole 32-byte sectors (with 144-byte records and 128-bit loads half of every sector fetched
+// from L2 was wasted, and the Schur kernel runs at the L2 bandwidth).
+constexpr int kHplStride = 20;
+__device__ __forceinline__ void ld256(const double* p, double& a, double& b, double& c, double& d) {
+    asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void st256(double* p, double a, double b, double c, double d) {
+    asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ void load18(const double* __restrict__ p, double* out) {
+    double pad0, pad1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ld256(p + 4 * i, out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+    ld256(p + 16, out[16], out[17], pad0, pad1);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
-// Levenberg-Marquardt control block.  The whole two-round optimisation runs as ONE CUDA graph whose loops are WHILE conditional
-// nodes: the numeric kernels read lambda and the index of the current state from this block, three single-CTA control kernels
-// restate g2o's OptimizationAlgorithmLevenberg::solve / SparseOptimizer::optimize / terminate_action bookkeeping and set the
-// loop conditions.  By default the host steps the same kernels (one round trip per loop decision); B200_LBA_GRAPH=1 selects the
-// graph driver (see b200_lba_create for why it is opt-in).
+// Batched windows.  b200_lba_solve_batch solves n independent local-BA windows in LOCKSTEP: every kernel below takes the
+// array of per-window descriptors and uses blockIdx.y (or a cluster index) as the window, so one launch sequence serves the
+// whole batch.  Each window owns a Levenberg-Marquardt control block on the device; the numeric kernels read lambda, the
+// index of the current state and the "go" flags from it and skip windows that are not in the phase the kernel implements
+// (a window whose trial was rejected skips the next build, a window that has finished its round skips everything).  The LM
+// bookkeeping itself (g2o's OptimizationAlgorithmLevenberg::solve / SparseOptimizer::optimize / terminate_action) runs in
+// the LAST CTA of the producing kernel of that window, so the host never takes part in a decision: it enqueues repetitions of
+// {build; trial} and looks at the control blocks every few repetitions only to know when to stop enqueueing.
 // ---------------------------------------------------------------------------------------------------------------
-struct Dual {
-    double* p[2];  // [current / trial] double buffers; LmCtl::cur says which one is current
-};
 struct LmCtl {
     double lambda, ni, current_chi, last_chi, rho;
     double lambda_init, chi2[2], lambda_final[2];
     int cur, it, iterations, qmax, ok, stop_flag, round, skip_round2;
-    int inner_go, outer_go;
+    int outer_go;    // the window still iterates in this round
+    int need_build;  // the next repetition starts with buildSystem (0 after a rejected trial: H and b are unchanged)
     int iters_done[2];
-    int launches;
-    const volatile int* abort_word;  // mapped host word mirroring the caller's force_stop flag
+    int trials;      // LM trials run so far (statistics)
+    int pad;
+    const volatile int* abort_word;  // mapped host word mirroring the caller's force_stop flag (NULL: no flag)
 };
 __device__ __forceinline__ bool lm_aborted(const LmCtl* c) { return c->stop_flag || (c->abort_word && *c->abort_word); }
 
+// Everything a kernel needs to know about one window (device pointers into the solver's arena).
+struct WinDev {
+    int K, L, E, Kf, Lf, n, ld, n_cams;
+    int lbc;  // CTAs of the landmark pass = max(1, ceil(L / 16)) = number of chi2 / diagonal / scale partials
+    int pad0;
+    // inputs as the caller gave them (original edge order)
+    const int* e_pose;
+    const int* e_point;
+    const unsigned char* e_cam;
+    const unsigned char* e_robust;
+    const unsigned char* e_can_outlier;
+    const float* e_obs;
+    const float* e_isig;
+    const float* e_delta;
+    const int* pose_col;  // K: free-pose column or -1
+    const int* pt_col;    // L: free-landmark column or -1
+    const Cam* cams;
+    // plan (built on the device)
+    int* pt_cnt;      // L   (zeroed; histogram, then placement cursor)
+    int* pt_start;    // L+1
+    int* order;       // E: sorted slot -> original edge index
+    EdgeS* edges;     // E, sorted by landmark (original order inside a landmark)
+    int* epcol;       // E: free-pose column of the sorted edge (compact copy for the scans)
+    int* pose_cnt;    // Kf (zeroed)
+    int* pose_start;  // Kf+1
+    int* pose_edges;  // sorted-edge ids grouped by free pose, ascending (= landmark order)
+    int4* rowrec;     // aligned with pose_edges: {edge a, its landmark (-1: the landmark is fixed), first edge of that landmark, its edge count}
+    int schur_split;  // CTAs that share one block row of the Schur complement (a function of the window's own size only)
+    int pad1;
+    double* schur_part;  // [Kf][schur_split][Kf - i tiles of 64]: partial accumulator tiles when schur_split > 1
+    int* row_tickets;    // (zeroed) Kf "last CTA of the row" tickets
+    const double* zeros; // (zeroed) what the lanes outside a 6x3 fragment read: >= kSchurFan records
+    // pair-list form of the Schur complement (default): the (edge a, edge c) pairs that share a landmark, grouped by the upper block
+    // (i <= j) of the reduced system they fall into, in landmark order, cut into chunks of kSchurChunk pairs
+    unsigned long long* lm_mask;  // L x mask_words: bit p set <=> the (free) landmark has an edge of free keyframe column p
+    int mask_words, n_blocks;
+    int* blk_cnt;          // n_blocks: pairs per block
+    int* blk_pair_start;   // n_blocks + 1
+    int* blk_chunk_start;  // n_blocks + 1
+    int4* pairs;           // {a, c, free-landmark column, 0}
+    struct SchurBlock* blocks;
+    struct SchurChunk* chunks;
+    double* chunk_part;    // 42 doubles per chunk
+    int* blk_done;         // (zeroed) chunks of the block that have published their partial
+    unsigned char* level;   // E (zeroed): 0 active, 1 outlier
+    unsigned char* robust;  // E: Huber on/off in the current round
+    // state (current / trial double buffers; LmCtl::cur says which one is current)
+    double* q[2];
+    double* t[2];
+    double* Rt[2];
+    double* pts[2];
+    double* chi[2];
+    double *Hpl, *Hll, *bl, *Dinv, *Hpp, *bp, *M, *xp;
+    double *r_chi, *r_diag, *r_scale, *r_result;
+    int* fail;       // (zeroed) the linear solve of the current trial failed
+    int* tickets;    // (zeroed) 2 "last CTA" tickets
+    int* bad_input;  // (zeroed) 1 + index of the first edge with an invalid vertex / camera reference
+    LmCtl* ctl;
+    // export block (contiguous per window): qf[4K] tf[3K] pf[3L] out[E]
+    double *qf, *tf, *pf;
+    unsigned char* out;
+};
+
 // ---------------------------------------------------------------------------------------------------------------
-// LM control kernels (one CTA each).  Sums of the per-CTA partials are taken by thread 0 in index order (staged through
-// shared memory), exactly like a host loop over the read-back array would.
+// Plan: the host only copies the caller's arrays; sorting the edges by landmark and listing them by keyframe happens here.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kCtlThreads = 256;
+// P1: validate + histogram of edges per landmark
+__global__ void __launch_bounds__(256) plan_count_kernel(const WinDev* __restrict__ wins) {
+    const WinDev& W = wins[blockIdx.y];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= W.E) return;
+    const int p = W.e_point[e], k = W.e_pose[e];
+    if (p < 0 || p >= W.L || k < 0 || k >= W.K || (int)W.e_cam[e] >= W.n_cams) {
+        atomicMax(W.bad_input, e + 1);
+        return;
+    }
+    atomicAdd(&W.pt_cnt[p], 1);
+}
+// P2: exclusive scan of the histogram (one CTA per window); the histogram becomes the placement cursor (zero)
+__global__ void __launch_bounds__(1024) plan_scan_kernel(const WinDev* __restrict__ wins) {
+    const WinDev& W = wins[blockIdx.x];
+    if (*W.bad_input) return;
+    __shared__ int warp_sums[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < W.L; base += 1024) {
+        const int i = base + tid;
+        const int v = i < W.L ? W.pt_cnt[i] : 0;
+        int x = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xFFFFFFFFu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) warp_sums[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int s = warp_sums[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xFFFFFFFFu, s, d);
+                if (lane >= d) s += y;
+            }
+            warp_sums[lane] = s;
+        }
+        __syncthreads();
+        const int excl = carry + (warp ? warp_sums[warp - 1] : 0) + x - v;
+        if (i < W.L) {
+            W.pt_start[i] = excl;
+            W.pt_cnt[i] = 0;
+        }
+        carry += warp_sums[31];
+        __syncthreads();
+    }
+    if (tid == 0) W.pt_start[W.L] = carry;
+}
+// P3: place every edge somewhere inside its landmark's segment
+__global__ void __launch_bounds__(256) plan_place_kernel(const WinDev* __restrict__ wins) {
+    const WinDev& W = wins[blockIdx.y];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= W.E || *W.bad_input) return;
+    const int p = W.e_point[e];
+    W.order[W.pt_start[p] + atomicAdd(&W.pt_cnt[p], 1)] = e;
+}
+// P4: one thread per landmark puts its (few) edges back into the caller's order -- the placement above is not deterministic,
+//     the sorted segment is -- and writes the edge records; histogram of edges per free keyframe
+__global__ void __launch_bounds__(128) plan_sort_kernel(const WinDev* __restrict__ wins) {
+    const WinDev& W = wins[blockIdx.y];
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= W.L || *W.bad_input) return;
+    const int a = W.pt_start[l], b = W.pt_start[l + 1];
+    int* __restrict__ ord = W.order;
+    for (int i = a + 1; i < b; ++i) {
+        const int v = ord[i];
+        int j = i - 1;
+        while (j >= a && ord[j] > v) {
+            ord[j + 1] = ord[j];
+            --j;
+        }
+        ord[j + 1] = v;
+    }
+    const int lc = W.pt_col[l];
+    unsigned long long mask[3] = {0ull, 0ull, 0ull};  // free keyframe columns that observe this landmark (Kf <= 166)
+    for (int s = a; s < b; ++s) {
+        const int e = ord[s];
+        EdgeS d;
+        d.pose = W.e_pose[e];
+        d.pcol = W.pose_col[d.pose];
+        d.point = l;
+        d.lcol = lc;
+        d.ox = W.e_obs[3 * (size_t)e];
+        d.oy = W.e_obs[3 * (size_t)e + 1];
+        d.oxr = W.e_obs[3 * (size_t)e + 2];
+        d.inv_sigma_sq = W.e_isig[e];
+        d.delta = W.e_delta[e];
+        d.cam = W.e_cam[e];
+        d.robust = W.e_robust[e];
+        d.can_outlier = W.e_can_outlier[e];
+        d.pad = 0;
+        W.edges[s] = d;
+        W.epcol[s] = d.pcol;
+        W.robust[s] = d.robust;
+        if (d.pcol >= 0) {
+            atomicAdd(&W.pose_cnt[d.pcol], 1);
+            if (lc >= 0) mask[d.pcol >> 6] |= 1ull << (d.pcol & 63);
+        }
+    }
+    for (int w2 = 0; w2 < W.mask_words; ++w2) W.lm_mask[(size_t)l * W.mask_words + w2] = mask[w2];
+}
+// P5: one CTA per free keyframe lists its edges in ascending sorted-edge order (= landmark order) by an ordered compaction
+//     over the window's edges
+constexpr int kListThreads = 256;
+__global__ void __launch_bounds__(kListThreads) plan_pose_lists_kernel(const WinDev* __restrict__ wins) {
+    const WinDev& W = wins[blockIdx.y];
+    const int i = blockIdx.x;
+    if (i >= W.Kf || *W.bad_input) return;
+    __shared__ int s_start;
+    __shared__ int warp_cnt[kListThreads / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+        int s = 0;
+        for (int j = lane; j < i; j += 32) s += W.pose_cnt[j];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, d);
+        if (lane == 0) {
+            s_start = s;
+            W.pose_start[i] = s;
+            if (i == W.Kf - 1) W.pose_start[W.Kf] = s + W.pose_cnt[i];
+        }
+    }
+    __syncthreads();
+    int run = s_start;
+    for (int base = 0; base < W.E; base += kListThreads) {
+        const int s = base + tid;
+        const bool mine = s < W.E && W.epcol[s] == i;
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, mine);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int off = 0, tot = 0;
+#pragma unroll
+        for (int w2 = 0; w2 < kListThreads / 32; ++w2) {
+            const int c = warp_cnt[w2];
+            if (w2 < warp) off += c;
+            tot += c;
+        }
+        if (mine) {
+            const int slot = run + off + __popc(bal & ((1u << lane) - 1u));
+            W.pose_edges[slot] = s;
+            const EdgeS* ed = W.edges + s;
+            const int l = ed->point, c_lo = W.pt_start[l];
+            W.rowrec[slot] = make_int4(s, ed->lcol >= 0 ? l : -1, c_lo, W.pt_start[l + 1] - c_lo);
+        }
+        run += tot;
+        __syncthreads();
+    }
+}
+
+// P6-P8: the pair list of the Schur complement.  Block b = (i, j >= i) of the reduced system collects the landmarks seen by both
+//     keyframes; one warp per block walks keyframe i's edge list (landmark order) and tests bit j of each landmark's mask, so the
+//     pairs of a block come out in landmark order without any sort: count, scan over the blocks, emit.
+constexpr int kSchurChunk = 64;
+struct SchurBlock {
+    int i, j, chunk_start, chunk_end;
+};
+struct SchurChunk {
+    int start, end, diag, block;
+};
+__device__ __forceinline__ void block_to_ij(int b, int Kf, int& i, int& j) {  // b = i * Kf - i (i - 1) / 2 + (j - i)
+    const double t = 2.0 * Kf + 1.0;
+    i = (int)((t - sqrt(t * t - 8.0 * b)) * 0.5);
+    i = max(0, min(i, Kf - 1));
+    while (i > 0 && i * Kf - i * (i - 1) / 2 > b) --i;
+    while (i + 1 < Kf && (i + 1) * Kf - (i + 1) * i / 2 <= b) ++i;
+    j = i + (b - (i * Kf - i * (i - 1) / 2));
+}
+template <bool EMIT>
+__global__ void __launch_bounds__(128) plan_pairs_kernel(const WinDev* __restrict__ wins) {
+    const WinDev& W = wins[blockIdx.y];
+    const int lane = threadIdx.x & 31, b = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (b >= W.n_blocks || *W.bad_input) return;
+    int i, j;
+    block_to_ij(b, W.Kf, i, j);
+    const int a_lo = W.pose_start[i], a_hi = W.pose_start[i + 1], mw = W.mask_words;
+    int run = EMIT ? W.blk_pair_start[b] : 0;
+    for (int base = a_lo; base < a_hi; base += 32) {
+        const int pos = base + lane;
+        bool hit = false;
+        int4 rec = make_int4(0, -1, 0, 0);
+        if (pos < a_hi) {
+            rec = W.rowrec[pos];
+            if (rec.y >= 0) hit = (W.lm_mask[(size_t)rec.y * mw + (j >> 6)] >> (j & 63)) & 1ull;
+        }
+        const unsigned bal = __ballot_sync(0xFFFFFFFFu, hit);
+        if (EMIT && hit) {
+            int c = rec.z;
+            for (int q = 0; q < rec.w; ++q)
+                if (W.epcol[rec.z + q] == j) {
+                    c = rec.z + q;
+                    break;
+                }
+            W.pairs[run + __popc(bal & ((1u << lane) - 1u))] = make_int4(rec.x, c, W.pt_col[rec.y], 0);
+        }
+        run += __popc(bal);
+    }
+    if (!EMIT) {
+        if (lane == 0) W.blk_cnt[b] = run;
+        return;
+    }
+    const int ps = W.blk_pair_start[b], total = W.blk_pair_start[b + 1] - ps, cs = W.blk_chunk_start[b];
+    for (int ch = lane; ch * kSchurChunk < total; ch += 32)
+        W.chunks[cs + ch] = SchurChunk{ps + ch * kSchurChunk, ps + min(total, (ch + 1) * kSchurChunk), i == j ? 1 : 0, b};
+    if (lane == 0) W.blocks[b] = SchurBlock{i, j, cs, W.blk_chunk_start[b + 1]};
+}
+// exclusive scans of the pairs and of the chunks per block (one CTA per window)
+__global__ void __launch_bounds__(1024) plan_pair_scan_kernel(const WinDev* __restrict__ wins) {
+    const WinDev& W = wins[blockIdx.x];
+    if (*W.bad_input) return;
+    __shared__ int ws_p[32], ws_c[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nb = W.n_blocks;
+    int carry_p = 0, carry_c = 0;
+    for (int base = 0; base < nb; base += 1024) {
+        const int b = base + tid;
+        const int vp = b < nb ? W.blk_cnt[b] : 0, vc = ceil_div(vp, kSchurChunk);
+        int xp = vp, xc = vc;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int yp = __shfl_up_sync(0xFFFFFFFFu, xp, d), yc = __shfl_up_sync(0xFFFFFFFFu, xc, d);
+            if (lane >= d) {
+                xp += yp;
+                xc += yc;
+            }
+        }
+        if (lane == 31) {
+            ws_p[warp] = xp;
+            ws_c[warp] = xc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            int sp = ws_p[lane], sc = ws_c[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int yp = __shfl_up_sync(0xFFFFFFFFu, sp, d), yc = __shfl_up_sync(0xFFFFFFFFu, sc, d);
+                if (lane >= d) {
+                    sp += yp;
+                    sc += yc;
+                }
+            }
+            ws_p[lane] = sp;
+            ws_c[lane] = sc;
+        }
+        __syncthreads();
+        if (b < nb) {
+            W.blk_pair_start[b] = carry_p + (warp ? ws_p[warp - 1] : 0) + xp - vp;
+            W.blk_chunk_start[b] = carry_c + (warp ? ws_c[warp - 1] : 0) + xc - vc;
+        }
+        carry_p += ws_p[31];
+        carry_c += ws_c[31];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        W.blk_pair_start[nb] = carry_p;
+        W.blk_chunk_start[nb] = carry_c;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LM control.  Sums of the per-CTA partials are taken by thread 0 in index order (staged through shared memory), exactly
+// like a host loop over the read-back array would.
+// ---------------------------------------------------------------------------------------------------------------
 __device__ double ordered_sum(const double* __restrict__ p, int n, double* stage) {
     double s = 0.0;
     for (int base = 0; base < n; base += 1024) {
         const int m = min(1024, n - base);
         __syncthreads();
-        for (int i = threadIdx.x; i < m; i += blockDim.x) stage[i] = __ldcg(p + base + i);  // L2: partials may come from other CTAs of this launch
+        for (int i = threadIdx.x; i < m; i += blockDim.x) stage[i] = __ldcg(p + base + i);  // L2: the partials come from other CTAs of this launch
         __syncthreads();
         if (threadIdx.x == 0)
             for (int i = 0; i < m; ++i) s += stage[i];
     }
     return s;  // valid in thread 0
 }
-__device__ __forceinline__ void set_cond(cudaGraphConditionalHandle h, int use_graph, unsigned v) {
-    if (use_graph) cudaGraphSetConditional(h, v);
+
+// Dinv = (Hll + lambda I)^-1 for every free landmark of the window (symmetric 3x3, cofactor inverse like Eigen's fixed-size
+// path), by all threads of the control CTA right after lambda has been decided.
+__device__ void compute_dinv(const WinDev& W, double lambda) {
+    const int Lf = W.Lf;
+    const double* __restrict__ Hll = W.Hll;
+    double* __restrict__ Dinv = W.Dinv;
+    for (int lc = threadIdx.x; lc < Lf; lc += blockDim.x) {
+        const double A0 = __ldcg(Hll + lc) + lambda, A1 = __ldcg(Hll + (size_t)Lf + lc), A2 = __ldcg(Hll + (size_t)2 * Lf + lc);
+        const double A4 = __ldcg(Hll + (size_t)3 * Lf + lc) + lambda, A5 = __ldcg(Hll + (size_t)4 * Lf + lc), A8 = __ldcg(Hll + (size_t)5 * Lf + lc) + lambda;
+        const double c0 = A4 * A8 - A5 * A5, c1 = A5 * A2 - A1 * A8, c2 = A1 * A5 - A4 * A2;
+        const double det = A0 * c0 + A1 * c1 + A2 * c2;
+        if (det == 0.0 || !isfinite(det)) {
+            *W.fail = 1;
+            continue;
+        }
+        const double id = 1.0 / det;
+        Dinv[lc] = c0 * id;
+        Dinv[(size_t)Lf + lc] = c1 * id;
+        Dinv[(size_t)2 * Lf + lc] = c2 * id;
+        Dinv[(size_t)3 * Lf + lc] = (A0 * A8 - A2 * A2) * id;
+        Dinv[(size_t)4 * Lf + lc] = (A1 * A2 - A0 * A5) * id;
+        Dinv[(size_t)5 * Lf + lc] = (A0 * A4 - A1 * A1) * id;
+    }
 }
 
-// start of SparseOptimizer::optimize(iterations): terminate_action at iteration -1 resets the stop flag (terminate_action.cc:46-51)
-__global__ void lm_round_begin_kernel(LmCtl* __restrict__ c, int iterations, int round, cudaGraphConditionalHandle h_outer, int use_graph) {
-    if (threadIdx.x) return;
+// start of SparseOptimizer::optimize(iterations): terminate_action at iteration -1 resets the stop flag (terminate_action.cc:46-51).
+// One thread per window.
+__global__ void lm_round_begin_kernel(const WinDev* __restrict__ wins, int n_windows, int iterations, int round) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_windows) return;
+    LmCtl* c = wins[w].ctl;
     c->round = round;
     c->iterations = iterations;
     c->iters_done[round] = 0;
-    c->launches += 1;
-    if (round == 1 && lm_aborted(c)) {  // local_bundle_adjuster_g2o.cc:317-321
+    c->need_build = 1;
+    if (*wins[w].bad_input) {
         c->skip_round2 = 1;
         c->outer_go = 0;
-        set_cond(h_outer, use_graph, 0u);
+        return;
+    }
+    // local_bundle_adjuster_g2o.cc:317-321: the second round is skipped only when the CALLER's flag exists and is set (the gain stop
+    // of the first round sets it through terminate_action); without a caller flag the stop lands in g2o's own auxiliary flag, which
+    // iteration -1 of the next optimize() resets
+    if (round == 1 && c->abort_word && lm_aborted(c)) {
+        c->skip_round2 = 1;
+        c->outer_go = 0;
         return;
     }
     c->stop_flag = 0;
     c->it = 0;
     c->ok = 1;
-    c->outer_go = (iterations > 0 && !lm_aborted(c)) ? 1 : 0;
-    set_cond(h_outer, use_graph, (unsigned)c->outer_go);
+    c->outer_go = (iterations > 0 && !(c->abort_word && *c->abort_word)) ? 1 : 0;
 }
 
 // after computeActiveErrors + buildSystem: at the first iteration of a round take the robust chi2 and computeLambdaInit
-// (tau * max |H_jj| over all free vertices, tau = 1e-5); arm the trial loop
-__device__ void lm_after_build(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb, const double* __restrict__ r_diag, int lb,
-                               const double* __restrict__ Hpp, int Kf, int n_build_launches, cudaGraphConditionalHandle h_inner, int use_graph,
-                               double* stage) {
+// (tau * max |H_jj| over all free vertices, tau = 1e-5); arm the trial loop.  Run by the last CTA of the keyframe-side kernel.
+__device__ void lm_after_build(const WinDev& W, double* stage) {
+    LmCtl* c = W.ctl;
     const bool first = c->it == 0;
     double chi = 0.0;
-    if (first) chi = ordered_sum(r_chi, eb, stage);
-    if (threadIdx.x) return;
-    if (first) {
-        c->current_chi = chi;
-        double mx = 0.0;
-        for (int i = 0; i < lb; ++i) mx = fmax(mx, __ldcg(r_diag + i));
-        for (int p = 0; p < Kf; ++p)
-            for (int a = 0; a < 6; ++a) mx = fmax(mx, fabs(__ldcg(Hpp + 36 * (size_t)p + a * 7)));
-        c->lambda = 1e-5 * mx;
-        c->ni = 2.0;
-        if (c->round == 0) c->lambda_init = c->lambda;
+    if (first) chi = ordered_sum(W.r_chi, W.lbc, stage);
+    if (threadIdx.x == 0) {
+        if (first) {
+            c->current_chi = chi;
+            double mx = 0.0;
+            for (int i = 0; i < W.lbc; ++i) mx = fmax(mx, __ldcg(W.r_diag + i));
+            for (int p = 0; p < W.Kf; ++p)
+                for (int a = 0; a < 6; ++a) mx = fmax(mx, fabs(__ldcg(W.Hpp + 36 * (size_t)p + a * 7)));
+            c->lambda = 1e-5 * mx;
+            c->ni = 2.0;
+            if (c->round == 0) c->lambda_init = c->lambda;
+        }
+        c->qmax = 0;
+        c->rho = 0.0;
+        c->need_build = 0;
+        *W.fail = 0;
     }
-    c->qmax = 0;
-    c->rho = 0.0;
-    c->inner_go = 1;
-    c->launches += n_build_launches;
-    set_cond(h_inner, use_graph, 1u);
-}
-__global__ void __launch_bounds__(kCtlThreads) lm_after_build_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb,
-                                                                     const double* __restrict__ r_diag, int lb, const double* __restrict__ Hpp,
-                                                                     int Kf, int n_build_launches, cudaGraphConditionalHandle h_inner,
-                                                                     int use_graph) {
-    __shared__ double stage[1024];
-    lm_after_build(c, r_chi, eb, r_diag, lb, Hpp, Kf, n_build_launches, h_inner, use_graph, stage);
+    __syncthreads();
+    compute_dinv(W, c->lambda);
 }
 
 // after one trial (solve, back-substitution, chi2 at the trial state): the accept / reject rule of
 // OptimizationAlgorithmLevenberg::solve, and when the trial loop ends the end-of-iteration bookkeeping of
-// SparseOptimizer::optimize + terminate_action (terminate_action.cc:52-73)
-__device__ void lm_after_trial(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb, const double* __restrict__ r_scale, int lb2,
-                               const double* __restrict__ r_result, int n_trial_launches, cudaGraphConditionalHandle h_inner,
-                               cudaGraphConditionalHandle h_outer, int use_graph, double* stage) {
+// SparseOptimizer::optimize + terminate_action (terminate_action.cc:52-73).  Run by the last CTA of the trial's chi2 pass.
+__device__ void lm_after_trial(const WinDev& W, double* stage) {
+    LmCtl* c = W.ctl;
+    const double* r_result = W.r_result;
     const bool ok2 = __ldcg(r_result) != 0.0;
-    const double chi_sum = ordered_sum(r_chi, eb, stage);
-    const double scale_sum = ordered_sum(r_scale, lb2, stage);
-    if (threadIdx.x) return;
-    c->launches += n_trial_launches;
-    const double temp_chi = ok2 ? chi_sum : 1.7976931348623157e308;
-    double rho = c->current_chi - temp_chi;
-    double scale = ok2 ? __ldcg(r_result + 1) + scale_sum : 0.0;  // computeScale
-    scale += 1e-3;
-    rho /= scale;
-    bool broke = false;
-    if (rho > 0 && isfinite(temp_chi) && ok2) {
-        double alpha = 1. - pow(2 * rho - 1, 3.0);
-        alpha = fmin(alpha, 2. / 3.);
-        c->lambda *= fmax(1. / 3., alpha);
-        c->ni = 2.0;
-        c->current_chi = temp_chi;
-        c->cur ^= 1;  // discardTop: keep the trial state
-    } else {
-        c->lambda *= c->ni;
-        c->ni *= 2.0;  // pop: the current state is untouched
-        if (!isfinite(c->lambda)) broke = true;
+    const double chi_sum = ordered_sum(W.r_chi, W.lbc, stage);
+    const double scale_sum = ordered_sum(W.r_scale, W.lbc, stage);
+    __shared__ int s_again;
+    if (threadIdx.x == 0) {
+        c->trials += 1;
+        const double temp_chi = ok2 ? chi_sum : 1.7976931348623157e308;
+        double rho = c->current_chi - temp_chi;
+        double scale = ok2 ? __ldcg(r_result + 1) + scale_sum : 0.0;  // computeScale
+        scale += 1e-3;
+        rho /= scale;
+        bool broke = false;
+        if (rho > 0 && isfinite(temp_chi) && ok2) {
+            double alpha = 1. - pow(2 * rho - 1, 3.0);
+            alpha = fmin(alpha, 2. / 3.);
+            c->lambda *= fmax(1. / 3., alpha);
+            c->ni = 2.0;
+            c->current_chi = temp_chi;
+            c->cur ^= 1;  // discardTop: keep the trial state
+        } else {
+            c->lambda *= c->ni;
+            c->ni *= 2.0;  // pop: the current state is untouched
+            if (!isfinite(c->lambda)) broke = true;
+        }
+        if (!broke) c->qmax++;
+        c->rho = rho;
+        const bool again = !broke && rho < 0 && c->qmax < 10 && !lm_aborted(c);
+        s_again = again ? 1 : 0;
+        *W.fail = 0;  // re-armed for the next trial
+        if (!again) {
+            if (c->qmax == 10 || rho == 0 || !isfinite(c->lambda)) c->ok = 0;  // SolverResult::Terminate
+            const double chi_now = c->current_chi;
+            if (c->it == 0) {
+                c->last_chi = chi_now;
+            } else {
+                const double gain = (c->last_chi - chi_now) / chi_now;
+                c->last_chi = chi_now;
+                if (gain >= 0 && gain < 1e-3) c->stop_flag = 1;
+            }
+            c->chi2[c->round] = chi_now;
+            c->lambda_final[c->round] = c->lambda;
+            c->it++;
+            c->iters_done[c->round] = c->it;
+            c->need_build = 1;
+            c->outer_go = (c->it < c->iterations && !lm_aborted(c) && c->ok) ? 1 : 0;
+        }
     }
-    if (!broke) c->qmax++;
-    c->rho = rho;
-    const bool again = !broke && rho < 0 && c->qmax < 10 && !lm_aborted(c);
-    c->inner_go = again ? 1 : 0;
-    set_cond(h_inner, use_graph, again ? 1u : 0u);
-    if (again) return;
-    if (c->qmax == 10 || rho == 0 || !isfinite(c->lambda)) c->ok = 0;  // SolverResult::Terminate
-    const double chi_now = c->current_chi;
-    if (c->it == 0) {
-        c->last_chi = chi_now;
-    } else {
-        const double gain = (c->last_chi - chi_now) / chi_now;
-        c->last_chi = chi_now;
-        if (gain >= 0 && gain < 1e-3) c->stop_flag = 1;
-    }
-    c->chi2[c->round] = chi_now;
-    c->lambda_final[c->round] = c->lambda;
-    c->it++;
-    c->iters_done[c->round] = c->it;
-    const bool more = c->it < c->iterations && !lm_aborted(c) && c->ok;
-    c->outer_go = more ? 1 : 0;
-    set_cond(h_outer, use_graph, more ? 1u : 0u);
-}
-__global__ void __launch_bounds__(kCtlThreads) lm_after_trial_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb,
-                                                                     const double* __restrict__ r_scale, int lb2,
-                                                                     const double* __restrict__ r_result, int n_trial_launches,
-                                                                     cudaGraphConditionalHandle h_inner, cudaGraphConditionalHandle h_outer,
-                                                                     int use_graph) {
-    __shared__ double stage[1024];
-    lm_after_trial(c, r_chi, eb, r_scale, lb2, r_result, n_trial_launches, h_inner, h_outer, use_graph, stage);
+    __syncthreads();
+    if (s_again) compute_dinv(W, c->lambda);  // the next trial of this iteration: same H and b, new damping
 }
 
-// "last CTA" election: after every CTA of the launch has published its results, exactly one of them (the last to arrive) sees
-// true and may consume them; it re-arms the ticket for the next launch.
-__device__ __forceinline__ bool last_cta_arrives(int* ticket, int* smem_flag) {
+// "last CTA" election among the `n_ctas` CTAs that work on one window: after every one of them has published its results,
+// exactly one (the last to arrive) sees true and may consume them; it re-arms the ticket for the next launch.
+__device__ __forceinline__ bool last_cta_arrives(int* ticket, int n_ctas, int* smem_flag) {
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const int t = atomicAdd(ticket, 1);
-        *smem_flag = (t == (int)gridDim.x - 1);
+        *smem_flag = (t == n_ctas - 1);
         if (*smem_flag) *ticket = 0;
     }
     __syncthreads();
@@ -355,258 +711,380 @@ __device__ __forceinline__ bool last_cta_arrives(int* ticket, int* smem_flag) {
     if (last) __threadfence();
     return last;
 }
-// what the tail of a fused launch needs to run the LM bookkeeping
-struct CtlTail {
-    LmCtl* ctl;
-    int* ticket;
-    const double *r_chi, *r_diag, *r_scale, *r_result, *Hpp;
-    int eb, lb, lb2, Kf, n_launches, use_graph;
-    cudaGraphConditionalHandle h_inner, h_outer;
-};
 
-// end of a round: a round that ran no iteration still reports the chi2 of its (re-evaluated) state
-__global__ void __launch_bounds__(kCtlThreads) lm_round_end_kernel(LmCtl* __restrict__ c, const double* __restrict__ r_chi, int eb, int round) {
+// end of a round: a round that ran no iteration still reports the chi2 of its (re-evaluated) state.  One CTA per window.
+__global__ void __launch_bounds__(256) lm_round_end_kernel(const WinDev* __restrict__ wins, int round) {
     __shared__ double stage[1024];
-    if (round == 1 && c->skip_round2) return;
-    const double chi = ordered_sum(r_chi, eb, stage);
+    const WinDev& W = wins[blockIdx.x];
+    LmCtl* c = W.ctl;
+    if (*W.bad_input || (round == 1 && c->skip_round2)) return;
+    const double chi = ordered_sum(W.r_chi, W.lbc, stage);
     if (threadIdx.x) return;
-    c->launches += 2;
     if (c->iters_done[round] == 0) c->chi2[round] = chi;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K1: per edge -- residual, chi2, Huber weight, Hpl block and the landmark-side contribution
-//     out: chi[e] (plain chi2, only for active edges), Hpl[18][E], pl[9][E] (6 unique Hll + 3 bl), chi partials
+// K1: landmark pass.  Eight lanes share a landmark and split its edges; sixteen landmarks per 128-thread CTA.
+//   kBuild : computeActiveErrors + the landmark side of buildSystem at the CURRENT state -- per edge the residual, chi2, Huber
+//            weight, the 6x3 block Hpl (144-byte record) and the landmark's Hll (6 unique) / bl (3), reduced over the
+//            landmark's contiguous edge range in a fixed order; chi2 and max |diag| partials per CTA
+//   kTrial : chi2 of the TRIAL state (inactive edges carry the chi2 of their last activation over); the last CTA of the window
+//            runs the accept / reject bookkeeping
+//   kRoundEnd: chi2 of the current state after a round (terminate_action's computeActiveErrors)
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kEdgeThreads = 128;
+enum { kBuild = 0, kTrial = 1, kRoundEnd = 2 };
+constexpr int kLmThreads = 128;
 
-__global__ void __launch_bounds__(kEdgeThreads) edges_kernel(View v, Dual Rt2, Dual pts2, Dual chi2, double* __restrict__ Hpl,
-                                                             double* __restrict__ pl, double* __restrict__ chi_partials, int linearize,
-                                                             int on_trial, int* __restrict__ fail_reset, const LmCtl* __restrict__ ctl,
-                                                             CtlTail tail) {
-    __shared__ double sh[kEdgeThreads];
-    const int sidx = (ctl->cur ^ on_trial) & 1;  // on_trial: evaluate the trial state, carrying inactive chi2 over from the current one
-    const double* __restrict__ Rt = Rt2.p[sidx];
-    const double* __restrict__ pts = pts2.p[sidx];
-    double* __restrict__ chi = chi2.p[sidx];
-    const double* __restrict__ chi_carry = on_trial ? chi2.p[sidx ^ 1] : nullptr;
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (fail_reset && e == 0) *fail_reset = 0;  // last kernel of a trial: re-arm the solver's failure flag
+template <int MODE>
+__global__ void __launch_bounds__(kLmThreads, 4) landmark_kernel(const WinDev* __restrict__ wins) {
+    __shared__ double sh[kLmThreads];
+    const WinDev& W = wins[blockIdx.y];
+    if ((int)blockIdx.x >= W.lbc) return;
+    const LmCtl* ctl = W.ctl;
+    if (MODE == kBuild && !(ctl->outer_go && ctl->need_build)) return;
+    if (MODE == kTrial && !ctl->outer_go) return;
+    if (MODE == kRoundEnd && (*W.bad_input || (ctl->round == 1 && ctl->skip_round2))) return;
+    const int sidx = (ctl->cur ^ (MODE == kTrial ? 1 : 0)) & 1;
+    const double* __restrict__ Rt = W.Rt[sidx];
+    const double* __restrict__ pts = W.pts[sidx];
+    double* __restrict__ chi = W.chi[sidx];
+    const double* __restrict__ chi_carry = W.chi[sidx ^ 1];
+    const int sub = threadIdx.x & 7;
+    const int l = blockIdx.x * 16 + (threadIdx.x >> 3);
+    const bool valid = l < W.L;
+    const int a0 = valid ? W.pt_start[l] : 0, b0 = valid ? W.pt_start[l + 1] : 0;
+    const int lc = valid ? W.pt_col[l] : -1;
     double cost = 0.0;
-    if (e < v.E) {
-        const EdgeS ed = v.edges[e];
-        const bool active = v.level[e] == 0;
-        if (active) {
-            const Cam c = v.cams[ed.cam];
+    double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double P[3] = {0, 0, 0};
+    if (valid) {
+        P[0] = pts[3 * (size_t)l];
+        P[1] = pts[3 * (size_t)l + 1];
+        P[2] = pts[3 * (size_t)l + 2];
+    }
+    for (int e = a0 + sub; e < b0; e += 8) {
+        const EdgeS ed = W.edges[e];
+        double* __restrict__ rec = W.Hpl + (size_t)e * kHplStride;
+        if (W.level[e] == 0) {
+            const Cam c = W.cams[ed.cam];
             double err[3], pc[3];
-            const double* P = pts + 3 * (size_t)ed.point;
             const double* T = Rt + 12 * (size_t)ed.pose;
             edge_residual(ed, c, T, P, err, pc);
             const double w = (double)ed.inv_sigma_sq;
             const double e2 = w * (err[0] * err[0] + err[1] * err[1] + err[2] * err[2]);
             chi[e] = e2;
-            const bool rob = v.robust[e] != 0;
-            cost = rob ? huber_cost(e2, (double)ed.delta) : e2;
-            if (linearize) {
+            const bool rob = W.robust[e] != 0;
+            cost += rob ? huber_cost(e2, (double)ed.delta) : e2;
+            if (MODE == kBuild) {
                 double Ji[9], Jj[18];
                 edge_jacobians(ed, c, T, pc, Ji, Jj);
                 const double ww = w * (rob ? huber_weight(e2, (double)ed.delta) : 1.0);
-                const bool lfree = ed.lcol >= 0, pfree = ed.pcol >= 0;
-                // Hll (upper 6) and bl
-                double h[9];
-                h[0] = ww * (Ji[0] * Ji[0] + Ji[3] * Ji[3] + Ji[6] * Ji[6]);
-                h[1] = ww * (Ji[0] * Ji[1] + Ji[3] * Ji[4] + Ji[6] * Ji[7]);
-                h[2] = ww * (Ji[0] * Ji[2] + Ji[3] * Ji[5] + Ji[6] * Ji[8]);
-                h[3] = ww * (Ji[1] * Ji[1] + Ji[4] * Ji[4] + Ji[7] * Ji[7]);
-                h[4] = ww * (Ji[1] * Ji[2] + Ji[4] * Ji[5] + Ji[7] * Ji[8]);
-                h[5] = ww * (Ji[2] * Ji[2] + Ji[5] * Ji[5] + Ji[8] * Ji[8]);
-                h[6] = -ww * (Ji[0] * err[0] + Ji[3] * err[1] + Ji[6] * err[2]);
-                h[7] = -ww * (Ji[1] * err[0] + Ji[4] * err[1] + Ji[7] * err[2]);
-                h[8] = -ww * (Ji[2] * err[0] + Ji[5] * err[1] + Ji[8] * err[2]);
-#pragma unroll
-                for (int i = 0; i < 9; ++i) pl[(size_t)i * v.E + e] = lfree ? h[i] : 0.0;
+                const bool lfree = lc >= 0, pfree = ed.pcol >= 0;
+                if (lfree) {  // Hll (upper 6) and bl
+                    h[0] += ww * (Ji[0] * Ji[0] + Ji[3] * Ji[3] + Ji[6] * Ji[6]);
+                    h[1] += ww * (Ji[0] * Ji[1] + Ji[3] * Ji[4] + Ji[6] * Ji[7]);
+                    h[2] += ww * (Ji[0] * Ji[2] + Ji[3] * Ji[5] + Ji[6] * Ji[8]);
+                    h[3] += ww * (Ji[1] * Ji[1] + Ji[4] * Ji[4] + Ji[7] * Ji[7]);
+                    h[4] += ww * (Ji[1] * Ji[2] + Ji[4] * Ji[5] + Ji[7] * Ji[8]);
+                    h[5] += ww * (Ji[2] * Ji[2] + Ji[5] * Ji[5] + Ji[8] * Ji[8]);
+                    h[6] += -ww * (Ji[0] * err[0] + Ji[3] * err[1] + Ji[6] * err[2]);
+                    h[7] += -ww * (Ji[1] * err[0] + Ji[4] * err[1] + Ji[7] * err[2]);
+                    h[8] += -ww * (Ji[2] * err[0] + Ji[5] * err[1] + Ji[8] * err[2]);
+                }
                 // Hpl = Jj^T W Ji (6x3)
+                double hp[18];
 #pragma unroll
                 for (int a = 0; a < 6; ++a)
 #pragma unroll
                     for (int b = 0; b < 3; ++b) {
                         const double s = ww * (Jj[a] * Ji[b] + Jj[6 + a] * Ji[3 + b] + Jj[12 + a] * Ji[6 + b]);
-                        Hpl[(size_t)e * 18 + a * 3 + b] = (lfree && pfree) ? s : 0.0;
+                        hp[a * 3 + b] = (lfree && pfree) ? s : 0.0;
                     }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) st256(rec + 4 * i, hp[4 * i], hp[4 * i + 1], hp[4 * i + 2], hp[4 * i + 3]);
+                st256(rec + 16, hp[16], hp[17], 0.0, 0.0);
             }
-        } else if (linearize) {
+        } else if (MODE == kBuild) {
 #pragma unroll
-            for (int i = 0; i < 9; ++i) pl[(size_t)i * v.E + e] = 0.0;
-#pragma unroll
-            for (int i = 0; i < 18; ++i) Hpl[(size_t)e * 18 + i] = 0.0;
-        } else if (chi_carry) {
+            for (int i = 0; i < 5; ++i) st256(rec + 4 * i, 0.0, 0.0, 0.0, 0.0);
+        } else if (MODE == kTrial) {
             chi[e] = chi_carry[e];  // inactive edges keep the chi2 of their last activation across the current/trial swap
         }
     }
-    const double s = block_sum(cost, sh);
-    if (threadIdx.x == 0) chi_partials[blockIdx.x] = s;
-    if (tail.ticket) {  // trial evaluation: the last CTA runs the accept / reject bookkeeping on the complete partial sums
-        __shared__ int last_flag;
-        __shared__ double stage[1024];
-        if (!last_cta_arrives(tail.ticket, &last_flag)) return;
-        lm_after_trial(tail.ctl, tail.r_chi, tail.eb, tail.r_scale, tail.lb2, tail.r_result, tail.n_launches, tail.h_inner, tail.h_outer, tail.use_graph,
-                       stage);
-    }
-}
-
-// K2: per landmark -- Hll (6 unique), bl (3) from its contiguous edge range; partial max |diag|
-__global__ void __launch_bounds__(128) points_kernel(View v, const double* __restrict__ pl, double* __restrict__ Hll, double* __restrict__ bl,
-                                                     double* __restrict__ diag_partials) {
-    __shared__ double sh[128];
-    const int l = blockIdx.x * blockDim.x + threadIdx.x;
-    double mx = 0.0;
-    if (l < v.L) {
-        const int lc = v.edges[v.pt_start[l] < v.E ? v.pt_start[l] : 0].lcol;  // same for all edges of the landmark
-        const int a = v.pt_start[l], b = v.pt_start[l + 1];
-        if (a < b && lc >= 0) {
-            double h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-            for (int e = a; e < b; ++e)
+    if (MODE == kBuild) {
+        // fixed-order reduction over the 8 lanes of the landmark
 #pragma unroll
-                for (int i = 0; i < 9; ++i) h[i] += pl[(size_t)i * v.E + e];
+        for (int i = 0; i < 9; ++i)
 #pragma unroll
-            for (int i = 0; i < 6; ++i) Hll[(size_t)i * v.Lf + lc] = h[i];
+            for (int s = 4; s > 0; s >>= 1) h[i] += __shfl_down_sync(0xFFFFFFFFu, h[i], s, 8);
+        double mx = 0.0;
+        if (valid && sub == 0 && lc >= 0) {
+            const int Lf = W.Lf;
 #pragma unroll
-            for (int i = 0; i < 3; ++i) bl[(size_t)i * v.Lf + lc] = h[6 + i];
+            for (int i = 0; i < 6; ++i) W.Hll[(size_t)i * Lf + lc] = h[i];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) W.bl[(size_t)i * Lf + lc] = h[6 + i];
             mx = fmax(fabs(h[0]), fmax(fabs(h[3]), fabs(h[5])));
         }
-    }
-    // max is order independent
-    sh[threadIdx.x] = mx;
-    __syncthreads();
-    for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
-        if (threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+        // max is order independent
+        sh[threadIdx.x] = mx;
+        __syncthreads();
+        for (int s = blockDim.x >> 1; s > 0; s >>= 1) {
+            if (threadIdx.x < s) sh[threadIdx.x] = fmax(sh[threadIdx.x], sh[threadIdx.x + s]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) W.r_diag[blockIdx.x] = sh[0];
         __syncthreads();
     }
-    if (threadIdx.x == 0) diag_partials[blockIdx.x] = sh[0];
-}
-
-// K3: keyframe-side blocks.  The edges of every free keyframe are cut into chunks of kPoseChunk; one warp reduces one
-//     chunk to 21 unique Hpp entries + 6 bp entries; the chunk partials are then added in index order.
-constexpr int kPoseChunk = 64;
-__device__ __forceinline__ void pose_finish_element(int idx, int Kf, const int* __restrict__ chunk_start, const double* __restrict__ partials,
-                                                    double* __restrict__ Hpp, double* __restrict__ bp) {
-    const int p = idx / 27, t = idx - p * 27;
-    if (p >= Kf) return;
-    double r = 0.0;
-    for (int c = chunk_start[p]; c < chunk_start[p + 1]; ++c) r += __ldcg(partials + (size_t)c * 27 + t);
-    if (t < 21) {
-        int a = 0, rem = t;
-        while (rem >= 6 - a) {
-            rem -= 6 - a;
-            ++a;
-        }
-        const int b = a + rem;
-        Hpp[(size_t)p * 36 + a * 6 + b] = r;
-        Hpp[(size_t)p * 36 + b * 6 + a] = r;
-    } else {
-        bp[(size_t)p * 6 + (t - 21)] = r;
+    const double s = block_sum(cost, sh);
+    if (threadIdx.x == 0) W.r_chi[blockIdx.x] = s;
+    if (MODE == kTrial) {  // the last CTA of the window runs the accept / reject bookkeeping on the complete partial sums
+        __shared__ int last_flag;
+        __shared__ double stage[1024];
+        if (!last_cta_arrives(W.tickets + 1, W.lbc, &last_flag)) return;
+        lm_after_trial(W, stage);
     }
 }
 
-// One warp per chunk; the last CTA to finish adds the chunk partials of every keyframe in index order (what used to be a second
-// launch) and then runs the after-build LM bookkeeping (a third).
-__global__ void __launch_bounds__(128) pose_chunks_kernel(View v, const int2* __restrict__ chunks, int n_chunks, Dual Rt2, Dual pts2,
-                                                          double* __restrict__ partials, const LmCtl* __restrict__ ctl,
-                                                          const int* __restrict__ chunk_start, double* __restrict__ Hpp, double* __restrict__ bp,
-                                                          CtlTail tail) {
-    const double* __restrict__ Rt = Rt2.p[ctl->cur & 1];
-    const double* __restrict__ pts = pts2.p[ctl->cur & 1];
-    const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (wid < n_chunks) {
-        const int2 ch = chunks[wid];
+// K2: keyframe-side blocks, one CTA per free keyframe.  Its edges (in landmark order) are cut into one contiguous range per
+//     warp; a warp reduces its range to 21 unique Hpp entries + 6 bp entries and the warp partials are added in index order.
+//     The last CTA of the window then runs the after-build LM bookkeeping and inverts the damped landmark blocks.
+constexpr int kRowThreads = 256;
+__global__ void __launch_bounds__(kRowThreads) pose_rows_kernel(const WinDev* __restrict__ wins) {
+    const WinDev& W = wins[blockIdx.y];
+    const LmCtl* ctl = W.ctl;
+    if (!(ctl->outer_go && ctl->need_build)) return;
+    const int n_rows = max(W.Kf, 1);
+    if ((int)blockIdx.x >= n_rows) return;
+    __shared__ double part[kRowThreads / 32][27];
+    __shared__ int last_flag;
+    __shared__ double stage[1024];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if ((int)blockIdx.x < W.Kf) {
+        const int i = blockIdx.x;
+        const double* __restrict__ Rt = W.Rt[ctl->cur & 1];
+        const double* __restrict__ pts = W.pts[ctl->cur & 1];
+        const int a = W.pose_start[i], b = W.pose_start[i + 1];
+        const int per = round_up(ceil_div(max(b - a, 1), kRowThreads / 32), 32);
+        const int lo = a + warp * per, hi = min(b, lo + per);
         double acc[27];
 #pragma unroll
-        for (int i = 0; i < 27; ++i) acc[i] = 0.0;
-        for (int k = ch.x + lane; k < ch.y; k += 32) {
-            const int e = v.pose_edges[k];
-            if (v.level[e]) continue;
-            const EdgeS ed = v.edges[e];
-            const Cam c = v.cams[ed.cam];
+        for (int x = 0; x < 27; ++x) acc[x] = 0.0;
+        for (int k = lo + lane; k < hi; k += 32) {
+            const int e = W.pose_edges[k];
+            if (W.level[e]) continue;
+            const EdgeS ed = W.edges[e];
+            const Cam c = W.cams[ed.cam];
             double err[3], pc[3], Ji[9], Jj[18];
             const double* T = Rt + 12 * (size_t)ed.pose;
             edge_residual(ed, c, T, pts + 3 * (size_t)ed.point, err, pc);
             edge_jacobians(ed, c, T, pc, Ji, Jj);
             const double w = (double)ed.inv_sigma_sq;
             const double e2 = w * (err[0] * err[0] + err[1] * err[1] + err[2] * err[2]);
-            const double ww = w * (v.robust[e] ? huber_weight(e2, (double)ed.delta) : 1.0);
+            const double ww = w * (W.robust[e] ? huber_weight(e2, (double)ed.delta) : 1.0);
             int t = 0;
 #pragma unroll
-            for (int a = 0; a < 6; ++a)
+            for (int x = 0; x < 6; ++x)
 #pragma unroll
-                for (int b = a; b < 6; ++b) acc[t++] += ww * (Jj[a] * Jj[b] + Jj[6 + a] * Jj[6 + b] + Jj[12 + a] * Jj[12 + b]);
+                for (int y = x; y < 6; ++y) acc[t++] += ww * (Jj[x] * Jj[y] + Jj[6 + x] * Jj[6 + y] + Jj[12 + x] * Jj[12 + y]);
 #pragma unroll
-            for (int a = 0; a < 6; ++a) acc[21 + a] += -ww * (Jj[a] * err[0] + Jj[6 + a] * err[1] + Jj[12 + a] * err[2]);
+            for (int x = 0; x < 6; ++x) acc[21 + x] += -ww * (Jj[x] * err[0] + Jj[6 + x] * err[1] + Jj[12 + x] * err[2]);
         }
 #pragma unroll
-        for (int i = 0; i < 27; ++i)
+        for (int x = 0; x < 27; ++x)
 #pragma unroll
-            for (int s = 16; s > 0; s >>= 1) acc[i] += __shfl_down_sync(0xFFFFFFFFu, acc[i], s);
+            for (int s = 16; s > 0; s >>= 1) acc[x] += __shfl_down_sync(0xFFFFFFFFu, acc[x], s);
         if (lane == 0)
 #pragma unroll
-            for (int i = 0; i < 27; ++i) partials[(size_t)wid * 27 + i] = acc[i];
+            for (int x = 0; x < 27; ++x) part[warp][x] = acc[x];
+        __syncthreads();
+        if (tid < 27) {
+            double r = 0.0;
+#pragma unroll
+            for (int w2 = 0; w2 < kRowThreads / 32; ++w2) r += part[w2][tid];
+            if (tid < 21) {
+                int x = 0, rem = tid;
+                while (rem >= 6 - x) {
+                    rem -= 6 - x;
+                    ++x;
+                }
+                const int y = x + rem;
+                W.Hpp[(size_t)i * 36 + x * 6 + y] = r;
+                W.Hpp[(size_t)i * 36 + y * 6 + x] = r;
+            } else {
+                W.bp[(size_t)i * 6 + (tid - 21)] = r;
+            }
+        }
     }
-    __shared__ int last_flag;
-    __shared__ double stage[1024];
-    if (!last_cta_arrives(tail.ticket, &last_flag)) return;
-    for (int idx = threadIdx.x; idx < tail.Kf * 27; idx += blockDim.x) pose_finish_element(idx, tail.Kf, chunk_start, partials, Hpp, bp);
-    __threadfence();
-    __syncthreads();
-    lm_after_build(tail.ctl, tail.r_chi, tail.eb, tail.r_diag, tail.lb, tail.Hpp, tail.Kf, tail.n_launches, tail.h_inner, tail.use_graph, stage);
+    if (!last_cta_arrives(W.tickets, n_rows, &last_flag)) return;
+    lm_after_build(W, stage);
 }
 
-// K4: per landmark -- Dinv = (Hll + lambda I)^-1 (symmetric 3x3, cofactor inverse like Eigen's fixed-size path)
-__global__ void __launch_bounds__(128) dinv_kernel(int Lf, const LmCtl* __restrict__ ctl, const double* __restrict__ Hll,
-                                                   double* __restrict__ Dinv, int* __restrict__ fail) {
-    const int lc = blockIdx.x * blockDim.x + threadIdx.x;
-    if (lc >= Lf) return;
+// K3: Schur complement of the landmarks, one CTA per block ROW i of the reduced system:
+//        S(i,j) = sum_l Hpl(i,l) Dinv(l) Hpl(j,l)^T   (j >= i),     rhs_i = sum_l Hpl(i,l) Dinv(l) bl(l)
+//     The CTA walks the edges a of keyframe i in landmark order; for each one T = Hpl(a) Dinv(l) and then, for every edge c of the
+//     same landmark whose keyframe column is >= i (the landmark's edges are contiguous), the 6x6 product T Hpl(c)^T is ONE fp64
+//     tensor-core instruction (mma.sync m8n8k4: T padded to 8x4 as the A fragment, Hpl(c)^T padded to 4x8 as B -- for c == a column 6
+//     of B carries bl(l), so the same instruction yields the right-hand side) accumulated into the 8x8 accumulator tile of block
+//     (i, j) in shared memory, which is stored in fragment order (lane t owns elements 2t, 2t+1).  Every warp owns a contiguous
+//     part of keyframe i's edge list and a private set of accumulator tiles; the warps' tiles are added in index order, so the
+//     result is deterministic.  Output: block column i of  M = [Hpp + lambda I - S ; (bp - rhs)^T].
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+constexpr int kSchurMaxWarps = 4;
+// kSchurUnroll (template): edges a in flight per warp (memory-level parallelism: the loop is a chain of L2 latencies otherwise)
+constexpr int kSchurFan = 8;     // edges c of a's landmark whose B fragments are prefetched; longer landmarks take the slow path
+// element (rr, nn) of block (i, i + jb) from the complete accumulator tile value s
+__device__ __forceinline__ void schur_store(const WinDev& W, int i, int jb, int el, double s, double lambda) {
+    const int rr = el >> 3, nn = el & 7;
+    if (rr >= 6 || nn >= 7 || (nn == 6 && jb != 0)) return;
+    const int n = W.n, ld = W.ld;
+    double* __restrict__ M = W.M;
+    if (nn == 6) {
+        M[(size_t)n * ld + 6 * i + rr] = W.bp[(size_t)i * 6 + rr] - s;  // rhs row
+    } else if (jb == 0) {
+        if (nn >= rr) M[(size_t)(6 * i + nn) * ld + 6 * i + rr] = W.Hpp[(size_t)i * 36 + rr * 6 + nn] + (rr == nn ? lambda : 0.0) - s;
+    } else {
+        M[(size_t)(6 * (i + jb) + nn) * ld + 6 * i + rr] = -s;  // lower triangle (j > i)
+    }
+}
+template <int kSchurUnroll>
+__global__ void __launch_bounds__(32 * kSchurMaxWarps) schur_rows_kernel(const WinDev* __restrict__ wins, int n_warps) {
+    extern __shared__ __align__(16) double sacc[];  // [n_warps][Kf - i][64]
+    const WinDev& W = wins[blockIdx.y];
+    const LmCtl* ctl = W.ctl;
+    if (!ctl->outer_go) return;
+    const int Kf = W.Kf, i = blockIdx.x, split = W.schur_split, part = blockIdx.z;
+    if (i >= Kf || part >= split) return;
+    const int nb = Kf - i;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int r = lane >> 2, k = lane & 3;  // A fragment: T[r][k];  B fragment: B[k][r] = Hpl(c)[r][k]
+    if (warp < n_warps) {
+        double2* __restrict__ acc = reinterpret_cast<double2*>(sacc + (size_t)warp * nb * 64);
+        for (int jb = 0; jb < nb; ++jb) acc[jb * 32 + lane] = make_double2(0.0, 0.0);
+        __syncwarp();
+        // this CTA's share of keyframe i's edge list, then this warp's share of that
+        const int a_lo = W.pose_start[i], a_hi = W.pose_start[i + 1];
+        const int per_cta = ceil_div(max(a_hi - a_lo, 1), split);
+        const int c_lo_ = a_lo + part * per_cta, c_hi_ = min(a_hi, c_lo_ + per_cta);
+        const int per = ceil_div(max(c_hi_ - c_lo_, 1), n_warps);
+        const int lo = c_lo_ + warp * per, hi = min(c_hi_, lo + per);
+        const int Lf = W.Lf;
+        const double* __restrict__ Hpl = W.Hpl;
+        const double* __restrict__ Dinv = W.Dinv;
+        const double* __restrict__ bl = W.bl;
+        const int* __restrict__ epcol = W.epcol;
+        const int4* __restrict__ recs = W.rowrec;
+        // D is symmetric, stored as (00, 01, 02, 11, 12, 22): column k of D
+        const int d0 = (k == 0) ? 0 : ((k == 1) ? 1 : 2), d1 = (k == 0) ? 1 : ((k == 1) ? 3 : 4), d2 = (k == 0) ? 2 : ((k == 1) ? 4 : 5);
+        const double* __restrict__ D0 = Dinv + (size_t)d0 * Lf;
+        const double* __restrict__ D1 = Dinv + (size_t)d1 * Lf;
+        const double* __restrict__ D2 = Dinv + (size_t)d2 * Lf;
+        const bool a_lane = r < 6 && k < 3, rhs_lane = r == 6 && k < 3;
+        // Lanes outside the 6x3 fragments read a block of zeros instead of being predicated off: every load below is unconditional
+        // with an immediate offset (the address arithmetic was two thirds of the instructions of the predicated form).
+        const double* __restrict__ zeros = W.zeros;
+        const double* __restrict__ bl_k = rhs_lane ? bl + (size_t)k * Lf : zeros;
+        const int frag = a_lane ? r * 3 + k : 0, row3 = a_lane ? r * 3 : 0;
+        double2 cd = make_double2(0.0, 0.0);  // tile of the diagonal block (i, i) + rhs column: touched by every edge, kept in registers
+        for (int pos = lo; pos < hi; pos += kSchurUnroll) {
+            int4 rec[kSchurUnroll];
+#pragma unroll
+            for (int u = 0; u < kSchurUnroll; ++u) rec[u] = (pos + u < hi) ? recs[pos + u] : make_int4(0, -1, 0, 0);
+            double t[kSchurUnroll], bdiag[kSchurUnroll], bv[kSchurUnroll][kSchurFan];
+            int pcs[kSchurUnroll];
+            // every load of the group is issued before the first tensor-core instruction consumes one
+#pragma unroll
+            for (int u = 0; u < kSchurUnroll; ++u) {
+                const int a = rec[u].x, lc = rec[u].y >= 0 ? W.pt_col[rec[u].y] : 0, c0 = rec[u].z, cnt = rec[u].y >= 0 ? rec[u].w : 0;
+                const double* __restrict__ ha = a_lane ? Hpl + (size_t)a * kHplStride + row3 : zeros;
+                const double h0 = ha[0], h1 = ha[1], h2 = ha[2];
+                t[u] = h0 * D0[lc] + h1 * D1[lc] + h2 * D2[lc];  // T = Hpl(a) Dinv(l); zero outside the fragment
+                // B of the diagonal pair (c == a): Hpl(a)^T in columns 0..5, bl(l) in column 6 (the right-hand side)
+                bdiag[u] = a_lane ? (k == 0 ? h0 : (k == 1 ? h1 : h2)) : bl_k[rhs_lane ? lc : 0];
+                pcs[u] = (lane < cnt) ? epcol[c0 + lane] : -1;
+                const double* __restrict__ hb = a_lane ? Hpl + (size_t)c0 * kHplStride + frag : zeros;  // (Hpl has kSchurFan records of slack)
+#pragma unroll
+                for (int j = 0; j < kSchurFan; ++j) bv[u][j] = hb[j * kHplStride];
+            }
+#pragma unroll
+            for (int u = 0; u < kSchurUnroll; ++u) {
+                const int cnt = rec[u].y >= 0 ? rec[u].w : 0;
+                if (cnt == 0) continue;
+                dmma_m8n8k4(cd.x, cd.y, t[u], bdiag[u]);
+                // A keyframe observes a landmark once, so the other edges c of the landmark fall into DIFFERENT accumulator tiles: their
+                // read-modify-write chains (LDS -> DMMA -> STS) are independent and are issued phase by phase instead of pair by pair.
+                // (A landmark listing the same keyframe twice, or one seen by more than kSchurFan keyframes, takes the serial path.)
+                const bool mine = lane < cnt && pcs[u] > i;
+                const unsigned peers = __match_any_sync(0xFFFFFFFFu, mine ? pcs[u] : -2 - lane);
+                const bool serial = cnt > kSchurFan || __any_sync(0xFFFFFFFFu, __popc(peers) > 1);
+                if (!serial) {
+                    double2 cc[kSchurFan];
+                    int tile[kSchurFan];
+#pragma unroll
+                    for (int j = 0; j < kSchurFan; ++j) {
+                        const int pc = __shfl_sync(0xFFFFFFFFu, pcs[u], j);
+                        tile[j] = (j < cnt && pc > i) ? (pc - i) * 32 + lane : -1;
+                        if (tile[j] >= 0) cc[j] = acc[tile[j]];
+                    }
+#pragma unroll
+                    for (int j = 0; j < kSchurFan; ++j)
+                        if (tile[j] >= 0) dmma_m8n8k4(cc[j].x, cc[j].y, t[u], bv[u][j]);
+#pragma unroll
+                    for (int j = 0; j < kSchurFan; ++j)
+                        if (tile[j] >= 0) acc[tile[j]] = cc[j];
+                    continue;
+                }
+                for (int j = 0; j < cnt; ++j) {
+                    const int c = rec[u].z + j;
+                    const int pc = epcol[c];
+                    if (pc <= i) continue;
+                    const double bq = a_lane ? Hpl[(size_t)c * kHplStride + frag] : 0.0;
+                    double2* slot = acc + (pc - i) * 32 + lane;
+                    double2 cc1 = *slot;
+                    dmma_m8n8k4(cc1.x, cc1.y, t[u], bq);
+                    *slot = cc1;
+                }
+            }
+        }
+        acc[lane] = cd;  // tile 0
+    }
+    __syncthreads();
     const double lambda = ctl->lambda;
-    const double A0 = Hll[lc] + lambda, A1 = Hll[(size_t)Lf + lc], A2 = Hll[(size_t)2 * Lf + lc];
-    const double A4 = Hll[(size_t)3 * Lf + lc] + lambda, A5 = Hll[(size_t)4 * Lf + lc], A8 = Hll[(size_t)5 * Lf + lc] + lambda;
-    const double c0 = A4 * A8 - A5 * A5, c1 = A5 * A2 - A1 * A8, c2 = A1 * A5 - A4 * A2;
-    const double det = A0 * c0 + A1 * c1 + A2 * c2;
-    if (det == 0.0 || !isfinite(det)) {
-        *fail = 1;
+    if (split == 1) {  // the CTA holds the complete row: add the warps' tiles in index order and write the block column
+        for (int idx = tid; idx < nb * 64; idx += blockDim.x) {
+            double s = 0.0;
+            for (int w2 = 0; w2 < n_warps; ++w2) s += sacc[(size_t)w2 * nb * 64 + idx];
+            schur_store(W, i, idx >> 6, idx & 63, s, lambda);
+        }
         return;
     }
-    const double id = 1.0 / det;
-    Dinv[lc] = c0 * id;
-    Dinv[(size_t)Lf + lc] = c1 * id;
-    Dinv[(size_t)2 * Lf + lc] = c2 * id;
-    Dinv[(size_t)3 * Lf + lc] = (A0 * A8 - A2 * A2) * id;
-    Dinv[(size_t)4 * Lf + lc] = (A1 * A2 - A0 * A5) * id;
-    Dinv[(size_t)5 * Lf + lc] = (A0 * A4 - A1 * A1) * id;
-}
-
-// K5: Schur complement of the landmarks.  The (edge a, edge c) pairs that share a landmark are grouped by the upper
-//     block (i <= j) of the reduced system they fall into and cut into chunks of kSchurChunk pairs; one warp reduces one
-//     chunk:  partial = sum T(a) Hpl(c)^T,  T(a) = Hpl(a) Dinv(l)   (+ for diagonal blocks  sum T(a) bl(l)).
-//     The chunk partials of every block are then added in index order (deterministic) into
-//     M = [Hpp + lambda I - sum ; (bp - sum)^T].
-constexpr int kSchurChunk = 64;
-struct SchurBlock {
-    int i, j, chunk_start, chunk_end;
-};
-struct SchurChunk {
-    int start, end, diag, pad;
-};
-__device__ __forceinline__ void load18(const double* __restrict__ p, double* out) {
-    const double2* q = reinterpret_cast<const double2*>(p);  // 144-byte records, 16-byte aligned
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        const double2 v = q[i];
-        out[2 * i] = v.x;
-        out[2 * i + 1] = v.y;
+    // several CTAs share the row: publish this CTA's tiles, the last one to arrive adds the CTAs' tiles in index order
+    double* __restrict__ row_part = W.schur_part + ((size_t)Kf * (Kf + 1) / 2 - (size_t)nb * (nb + 1) / 2) * 64 * split;  // rows before i hold Kf .. nb+1 tiles
+    double* __restrict__ mine = row_part + (size_t)part * nb * 64;
+    for (int idx = tid; idx < nb * 64; idx += blockDim.x) {
+        double s = 0.0;
+        for (int w2 = 0; w2 < n_warps; ++w2) s += sacc[(size_t)w2 * nb * 64 + idx];
+        mine[idx] = s;
+    }
+    __shared__ int last_flag;
+    if (!last_cta_arrives(W.row_tickets + i, split, &last_flag)) return;
+    for (int idx = tid; idx < nb * 64; idx += blockDim.x) {
+        double s = 0.0;
+        for (int p2 = 0; p2 < split; ++p2) s += __ldcg(row_part + (size_t)p2 * nb * 64 + idx);
+        schur_store(W, i, idx >> 6, idx & 63, s, lambda);
     }
 }
-// Adds the chunk partials of block b in index order into M = [Hpp + lambda I - sum ; (bp - sum)^T]; lanes cover the 42 elements.
-__device__ __forceinline__ void schur_finish_block(const SchurBlock sb, double lambda, const double* __restrict__ partials,
-                                                   const double* __restrict__ Hpp, const double* __restrict__ bp, double* __restrict__ M, int n, int ld,
-                                                   int lane) {
+
+// K5 (default): Schur complement from the pair list.  One warp reduces one chunk of <= 64 pairs of one block, every lane a pair:
+//        partial = sum T(a) Hpl(c)^T,  T(a) = Hpl(a) Dinv(l)   (+ for diagonal blocks  sum T(a) bl(l))
+//     with 42 register accumulators; the warp that publishes a block's last chunk adds the chunk partials in index order
+//     (deterministic) into  M = [Hpp + lambda I - sum ; (bp - sum)^T].  Blocks without any pair are filled by the warps past the chunks.
+__device__ __forceinline__ void schur_finish_block(const WinDev& W, const SchurBlock sb, double lambda, int lane) {
+    const double* __restrict__ partials = W.chunk_part;
+    double* __restrict__ M = W.M;
+    const int n = W.n, ld = W.ld;
     for (int el = lane; el < 42; el += 32) {
         if (el >= 36 && sb.i != sb.j) continue;
         double sacc = 0.0;
@@ -614,42 +1092,44 @@ __device__ __forceinline__ void schur_finish_block(const SchurBlock sb, double l
         if (el < 36) {
             const int r = el / 6, c = el - r * 6;
             double val = -sacc;
-            if (sb.i == sb.j) val += Hpp[(size_t)sb.i * 36 + el] + (r == c ? lambda : 0.0);
+            if (sb.i == sb.j) val += W.Hpp[(size_t)sb.i * 36 + el] + (r == c ? lambda : 0.0);
             M[(size_t)(6 * sb.j + c) * ld + 6 * sb.i + r] = val;  // lower triangle (j >= i)
             if (sb.i == sb.j) M[(size_t)(6 * sb.i + r) * ld + 6 * sb.j + c] = val;
         } else {
             const int r = el - 36;
-            M[(size_t)n * ld + 6 * sb.i + r] = bp[(size_t)sb.i * 6 + r] - sacc;  // rhs row
+            M[(size_t)n * ld + 6 * sb.i + r] = W.bp[(size_t)sb.i * 6 + r] - sacc;  // rhs row
         }
     }
 }
-
-// One warp per chunk (chunk.pad = its block).  The warp that completes a block's last chunk assembles that block of the reduced
-// system (what used to be a second launch); warps past the chunks fill the blocks that have no pair at all.
-__global__ void __launch_bounds__(128) schur_chunks_kernel(View v, const SchurChunk* __restrict__ chunks, int n_chunks,
-                                                           const int2* __restrict__ pairs, const double* __restrict__ Hpl,
-                                                           const double* __restrict__ Dinv, const double* __restrict__ bl,
-                                                           double* __restrict__ partials, const LmCtl* __restrict__ ctl,
-                                                           const SchurBlock* __restrict__ blocks, const int* __restrict__ empty_blocks, int n_empty,
-                                                           int* __restrict__ blk_done, const double* __restrict__ Hpp, const double* __restrict__ bp,
-                                                           double* __restrict__ M, int n, int ld) {
+__global__ void __launch_bounds__(128) schur_chunks_kernel(const WinDev* __restrict__ wins) {
+    const WinDev& W = wins[blockIdx.y];
+    const LmCtl* ctl = W.ctl;
+    if (!ctl->outer_go) return;
     const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int n_blocks = W.n_blocks, n_chunks = W.blk_chunk_start[n_blocks];
     if (wid >= n_chunks) {
-        if (wid - n_chunks < n_empty) schur_finish_block(blocks[empty_blocks[wid - n_chunks]], ctl->lambda, partials, Hpp, bp, M, n, ld, lane);
+        const int e = wid - n_chunks;
+        if (e < n_blocks) {
+            const SchurBlock sb = W.blocks[e];
+            if (sb.chunk_start == sb.chunk_end) schur_finish_block(W, sb, ctl->lambda, lane);  // no pair: just Hpp + lambda I, or zero
+        }
         return;
     }
-    const SchurChunk ch = chunks[wid];
+    const SchurChunk ch = W.chunks[wid];
+    const int Lf = W.Lf;
+    const double* __restrict__ Hpl = W.Hpl;
+    const double* __restrict__ Dinv = W.Dinv;
     double acc[42];
 #pragma unroll
     for (int i = 0; i < 42; ++i) acc[i] = 0.0;
     for (int k = ch.start + lane; k < ch.end; k += 32) {
-        const int2 pr = pairs[k];
+        const int4 pr = W.pairs[k];
         double ha[18], hc[18], t[18];
-        load18(Hpl + (size_t)pr.x * 18, ha);
-        load18(Hpl + (size_t)pr.y * 18, hc);
-        const int lc = v.edges[pr.x].lcol;
-        const double D0 = Dinv[lc], D1 = Dinv[(size_t)v.Lf + lc], D2 = Dinv[(size_t)2 * v.Lf + lc];
-        const double D4 = Dinv[(size_t)3 * v.Lf + lc], D5 = Dinv[(size_t)4 * v.Lf + lc], D8 = Dinv[(size_t)5 * v.Lf + lc];
+        load18(Hpl + (size_t)pr.x * kHplStride, ha);
+        load18(Hpl + (size_t)pr.y * kHplStride, hc);
+        const int lc = pr.z;
+        const double D0 = Dinv[lc], D1 = Dinv[(size_t)Lf + lc], D2 = Dinv[(size_t)2 * Lf + lc];
+        const double D4 = Dinv[(size_t)3 * Lf + lc], D5 = Dinv[(size_t)4 * Lf + lc], D8 = Dinv[(size_t)5 * Lf + lc];
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
             t[r * 3] = ha[r * 3] * D0 + ha[r * 3 + 1] * D1 + ha[r * 3 + 2] * D2;
@@ -661,7 +1141,7 @@ __global__ void __launch_bounds__(128) schur_chunks_kernel(View v, const SchurCh
 #pragma unroll
             for (int c = 0; c < 6; ++c) acc[r * 6 + c] += t[r * 3] * hc[c * 3] + t[r * 3 + 1] * hc[c * 3 + 1] + t[r * 3 + 2] * hc[c * 3 + 2];
         if (ch.diag) {  // pr.x == pr.y: the edge of keyframe i to this landmark
-            const double b0 = bl[lc], b1 = bl[(size_t)v.Lf + lc], b2 = bl[(size_t)2 * v.Lf + lc];
+            const double b0 = W.bl[lc], b1 = W.bl[(size_t)Lf + lc], b2 = W.bl[(size_t)2 * Lf + lc];
 #pragma unroll
             for (int r = 0; r < 6; ++r) acc[36 + r] += t[r * 3] * b0 + t[r * 3 + 1] * b1 + t[r * 3 + 2] * b2;
         }
@@ -670,19 +1150,19 @@ __global__ void __launch_bounds__(128) schur_chunks_kernel(View v, const SchurCh
     for (int i = 0; i < 42; ++i)
 #pragma unroll
         for (int s = 16; s > 0; s >>= 1) acc[i] += __shfl_down_sync(0xFFFFFFFFu, acc[i], s);
-    const SchurBlock sb = blocks[ch.pad];
+    const SchurBlock sb = W.blocks[ch.block];
     int arrived = 0;
     if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < 42; ++i) partials[(size_t)wid * 42 + i] = acc[i];
+        for (int i = 0; i < 42; ++i) W.chunk_part[(size_t)wid * 42 + i] = acc[i];
         __threadfence();
-        arrived = atomicAdd(&blk_done[ch.pad], 1);
+        arrived = atomicAdd(&W.blk_done[ch.block], 1);
     }
     arrived = __shfl_sync(0xFFFFFFFFu, arrived, 0);
     if (arrived != sb.chunk_end - sb.chunk_start - 1) return;
     __threadfence();
-    schur_finish_block(sb, ctl->lambda, partials, Hpp, bp, M, n, ld, lane);
-    if (lane == 0) blk_done[ch.pad] = 0;  // re-armed for the next trial
+    schur_finish_block(W, sb, ctl->lambda, lane);
+    if (lane == 0) W.blk_done[ch.block] = 0;  // re-armed for the next trial
 }
 
 // K6: dense Cholesky of the reduced system (<= 6*Kf unknowns), solve, then the keyframe updates
@@ -757,18 +1237,26 @@ __device__ __forceinline__ void cluster_sync_all() {
 // The kernel runs as ONE thread-block cluster: every CTA repeats the cheap steps (1) and (2) on its own SM (so no panel
 // exchange is needed), the tiles of step (3) -- 60 % of the flops -- are dealt round-robin to the CTAs of the cluster, and a
 // cluster barrier (release/acquire) separates the panels.  CTA 0 writes the factor back and does the backward solve.
-__global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld, double* __restrict__ M, const LmCtl* __restrict__ ctl,
-                                                                  const double* __restrict__ bp, double* __restrict__ xp, int K,
-                                                                  const int* __restrict__ pose_col, Dual q2, Dual t2, Dual Rt2,
-                                                                  double* __restrict__ result, int* __restrict__ fail) {
+__global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(const WinDev* __restrict__ wins) {
+    const unsigned crank = cluster_ctarank(), csize = cluster_nctarank();
+    const WinDev& W = wins[blockIdx.x / csize];  // one cluster per window
+    const LmCtl* __restrict__ ctl = W.ctl;
+    if (!ctl->outer_go) return;  // (uniform over the cluster: nobody waits at a cluster barrier)
+    const int n = W.n, ld = W.ld, K = W.K;
+    double* __restrict__ M = W.M;
+    const double* __restrict__ bp = W.bp;
+    double* __restrict__ xp = W.xp;
+    const int* __restrict__ pose_col = W.pose_col;
+    double* __restrict__ result = W.r_result;
+    int* __restrict__ fail = W.fail;
     extern __shared__ __align__(32) double dyn[];
     const double lambda = ctl->lambda;
     const int cur_idx = ctl->cur & 1;
-    const double* __restrict__ q_cur = q2.p[cur_idx];
-    const double* __restrict__ t_cur = t2.p[cur_idx];
-    double* __restrict__ q_new = q2.p[cur_idx ^ 1];
-    double* __restrict__ t_new = t2.p[cur_idx ^ 1];
-    double* __restrict__ Rt_new = Rt2.p[cur_idx ^ 1];
+    const double* __restrict__ q_cur = W.q[cur_idx];
+    const double* __restrict__ t_cur = W.t[cur_idx];
+    double* __restrict__ q_new = W.q[cur_idx ^ 1];
+    double* __restrict__ t_new = W.t[cur_idx ^ 1];
+    double* __restrict__ Rt_new = W.Rt[cur_idx ^ 1];
     double* D = dyn;                     // kNB x (kNB+1) diagonal block (lower, padded with the identity)
     double* Pn = dyn + kNB * (kNB + 1);  // kNB x mp panel, transposed (k-major); the 600 doubles in front keep it 32-byte aligned
     const int mp = (n + 1 + 3) & ~3;
@@ -777,7 +1265,6 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld,
     __shared__ double sh[kCholThreads];
     __shared__ int bad;
     const int tid = threadIdx.x, nt = blockDim.x;
-    const unsigned crank = cluster_ctarank(), csize = cluster_nctarank();
     const bool lead = crank == 0;
     if (tid == 0) bad = *fail;
     __syncthreads();
@@ -962,20 +1449,27 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(int n, int ld,
 
 // K7: back-substitution x_l = Dinv (bl - sum_e Hpl(e)^T x_p), trial landmark, scale partials.  Eight lanes share a landmark
 //     (they split its edges), sixteen landmarks per 128-thread CTA.
-__global__ void __launch_bounds__(128) backsub_kernel(View v, const LmCtl* __restrict__ ctl, const double* __restrict__ Dinv,
-                                                      const double* __restrict__ bl, const double* __restrict__ Hpl,
-                                                      const double* __restrict__ xp, Dual pts2, double* __restrict__ scale_partials,
-                                                      const int* __restrict__ fail) {
+__global__ void __launch_bounds__(128) backsub_kernel(const WinDev* __restrict__ wins) {
     __shared__ double sh[128];
+    const WinDev& W = wins[blockIdx.y];
+    const LmCtl* __restrict__ ctl = W.ctl;
+    if ((int)blockIdx.x >= W.lbc || !ctl->outer_go) return;
+    struct { int L, Lf; const int* pt_start; const EdgeS* edges; } v = {W.L, W.Lf, W.pt_start, W.edges};
+    const double* __restrict__ Dinv = W.Dinv;
+    const double* __restrict__ bl = W.bl;
+    const double* __restrict__ Hpl = W.Hpl;
+    const double* __restrict__ xp = W.xp;
+    double* __restrict__ scale_partials = W.r_scale;
+    const int* __restrict__ fail = W.fail;
     const double lambda = ctl->lambda;
-    const double* __restrict__ pts_cur = pts2.p[ctl->cur & 1];
-    double* __restrict__ pts_new = pts2.p[(ctl->cur & 1) ^ 1];
+    const double* __restrict__ pts_cur = W.pts[ctl->cur & 1];
+    double* __restrict__ pts_new = W.pts[(ctl->cur & 1) ^ 1];
     const int sub = threadIdx.x & 7;
     const int l = blockIdx.x * 16 + (threadIdx.x >> 3);
     double sc = 0.0;
     const bool valid = l < v.L;
     const int a0 = valid ? v.pt_start[l] : 0, b0 = valid ? v.pt_start[l + 1] : 0;
-    const int lc = (a0 < b0) ? v.edges[a0].lcol : -1;
+    const int lc = valid ? W.pt_col[l] : -1;
     const bool solve = lc >= 0 && !*fail;
     double c0 = 0.0, c1 = 0.0, c2 = 0.0;
     if (solve) {
@@ -983,7 +1477,7 @@ __global__ void __launch_bounds__(128) backsub_kernel(View v, const LmCtl* __res
             const int pcol = v.edges[e].pcol;
             if (pcol < 0) continue;
             double h[18];
-            load18(Hpl + (size_t)e * 18, h);
+            load18(Hpl + (size_t)e * kHplStride, h);
 #pragma unroll
             for (int r = 0; r < 6; ++r) {
                 const double x = xp[6 * pcol + r];
@@ -1019,20 +1513,21 @@ __global__ void __launch_bounds__(128) backsub_kernel(View v, const LmCtl* __res
 
 // K8: outlier test (local_bundle_adjuster_g2o.cc:323-344, 357-375): chi2 of the last activation vs the chi-square
 //     threshold, or non-positive depth at the current estimate.  mode 0: mark level + drop the kernel; mode 1: report.
-__global__ void __launch_bounds__(128) outlier_kernel(View v, Dual Rt2, Dual pts2, Dual chi2, int mode, unsigned char* __restrict__ out,
-                                                      const LmCtl* __restrict__ ctl) {
+__global__ void __launch_bounds__(128) outlier_kernel(const WinDev* __restrict__ wins, int mode) {
+    const WinDev& W = wins[blockIdx.y];
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= v.E) return;
+    if (e >= W.E || *W.bad_input) return;
+    const LmCtl* __restrict__ ctl = W.ctl;
     if (mode == 0 && ctl->skip_round2) return;  // local_bundle_adjuster_g2o.cc:317-321: no second round after an abort
-    const double* __restrict__ Rt = Rt2.p[ctl->cur & 1];
-    const double* __restrict__ pts = pts2.p[ctl->cur & 1];
-    const double* __restrict__ chi = chi2.p[ctl->cur & 1];
-    const EdgeS ed = v.edges[e];
+    const double* __restrict__ Rt = W.Rt[ctl->cur & 1];
+    const double* __restrict__ pts = W.pts[ctl->cur & 1];
+    const double* __restrict__ chi = W.chi[ctl->cur & 1];
+    const EdgeS ed = W.edges[e];
     unsigned char o = 0;
     if (ed.can_outlier) {
         const double thr = (ed.oxr < 0.f) ? (double)5.99146f : (double)7.81473f;
         bool depth_ok = true;
-        if (v.cams[ed.cam].model != 1) {  // reproj_edge_wrapper.h:233-268 (equirectangular: always true)
+        if (W.cams[ed.cam].model != 1) {  // reproj_edge_wrapper.h:233-268 (equirectangular: always true)
             const double* T = Rt + 12 * (size_t)ed.pose;
             const double* P = pts + 3 * (size_t)ed.point;
             depth_ok = 0.0 < T[6] * P[0] + T[7] * P[1] + T[8] * P[2] + T[11];
@@ -1041,12 +1536,22 @@ __global__ void __launch_bounds__(128) outlier_kernel(View v, Dual Rt2, Dual pts
     }
     if (mode == 0) {
         if (ed.can_outlier) {
-            if (o) v.level[e] = 1;
-            v.robust[e] = 0;
+            if (o) W.level[e] = 1;
+            W.robust[e] = 0;
         }
     } else {
-        out[e] = o;
+        W.out[W.order[e]] = o;  // reported in the caller's edge order
     }
+}
+
+// copy the final (current) keyframe and landmark states into the window's export block
+__global__ void __launch_bounds__(256) lm_export_kernel(const WinDev* __restrict__ wins) {
+    const WinDev& W = wins[blockIdx.y];
+    const int cur = W.ctl->cur & 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4 * W.K) W.qf[i] = W.q[cur][i];
+    if (i < 3 * W.K) W.tf[i] = W.t[cur][i];
+    if (i < 3 * W.L) W.pf[i] = W.pts[cur][i];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1331,15 +1836,6 @@ __global__ void __launch_bounds__(kPoseThreads) pose_optimize_kernel(const PoseP
     }
 }
 
-// copy the final (current) keyframe and landmark states to fixed read-back buffers
-__global__ void __launch_bounds__(256) lm_export_kernel(const LmCtl* __restrict__ c, Dual q2, Dual t2, Dual pts2, int K, int L, double* __restrict__ qf,
-                                                        double* __restrict__ tf, double* __restrict__ pf) {
-    const int cur = c->cur & 1;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 4 * K) qf[i] = q2.p[cur][i];
-    if (i < 3 * K) tf[i] = t2.p[cur][i];
-    if (i < 3 * L) pf[i] = pts2.p[cur][i];
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // host
@@ -1357,15 +1853,23 @@ struct Solver {
     float last_ms = 0.f;
     int last_launches = 0;
     cudaEvent_t ev_sync = nullptr;
-    LmCtl* h_ctl = nullptr;       // pinned mirror of the device control block
-    int* h_abort = nullptr;       // pinned, device-visible mirror of the caller's force_stop flag
+    cudaEvent_t ev_ctl[2] = {nullptr, nullptr};  // completion of the two alternating control-block read-backs
+    int* h_abort = nullptr;       // pinned, device-visible mirrors of the callers' force_stop flags (one word per window)
     int* d_abort = nullptr;
+    int abort_cap = 0;
+    // profiling mode (b200_lba_enable_profile): an event after every launch; per-kernel sums of the last batch
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_ev;
+    std::vector<int> prof_kind;
+    float prof_ms[8] = {};
+    int prof_n[8] = {};
+    // Schur complement: pair lists reduced by scalar fp64 FMAs (default) or block rows with fp64 tensor-core products
+    // (B200_LBA_SCHUR_MODE=rows; tuning knobs B200_LBA_SCHUR=unroll,warps,ctas)
+    bool schur_rows = false;
+    int schur_unroll = 4, schur_warps = kSchurMaxWarps, schur_ctas = 160;
     int chol_cluster = kCholCluster;  // CTAs sharing one factorisation (B200_LBA_CLUSTER overrides: 1, 2, 4 or 8)
-    bool host_loop = true;        // false (B200_LBA_GRAPH=1): run the LM loop as one conditional CUDA graph
-    // Waiting for the stream (once per LM trial).  Windows are solved many at a time by as many host threads; measured on a 16-core
-    // quota with 16 windows in flight next to the front end: spinning in cudaStreamSynchronize gives the best median but starves
-    // the thread that feeds the front end every few runs (frames/s halved), a blocking-sync event costs 10-25 %, polling the stream
-    // with a 15 us nap in between is within 2 % of spinning and never collapsed.  B200_LBA_WAIT=spin|block|yield|nap overrides.
+    bool chol_cluster_pinned = false;
+    // Waiting for the stream (a few times per batch).  B200_LBA_WAIT=spin|block|yield|nap overrides.
     int wait_mode = 3;  // 0 spin (cudaStreamSynchronize), 1 blocking event, 2 poll + sched_yield, 3 poll + 15 us sleep
     cudaError_t wait(cudaStream_t st) {
         if (wait_mode == 0) return cudaStreamSynchronize(st);
@@ -1379,6 +1883,15 @@ struct Solver {
         }
         cudaError_t e = cudaEventRecord(ev_sync, st);
         return e != cudaSuccess ? e : cudaEventSynchronize(ev_sync);
+    }
+    cudaError_t wait_event(cudaEvent_t ev) {
+        if (wait_mode < 2) return cudaEventSynchronize(ev);
+        cudaError_t e;
+        while ((e = cudaEventQuery(ev)) == cudaErrorNotReady) {
+            if (wait_mode == 2) sched_yield();
+            else std::this_thread::sleep_for(std::chrono::microseconds(15));
+        }
+        return e;
     }
 
     int ensure(size_t dev_bytes, size_t host_bytes, size_t res_doubles) {
@@ -1405,9 +1918,17 @@ struct Solver {
         }
         return B200_OK;
     }
+    int ensure_abort(int n) {
+        if (n <= abort_cap) return B200_OK;
+        if (h_abort) B200_CUDA(cudaFreeHost(h_abort));
+        h_abort = nullptr;
+        abort_cap = 0;
+        B200_CUDA(cudaHostAlloc((void**)&h_abort, sizeof(int) * (size_t)n * 2, cudaHostAllocMapped));
+        B200_CUDA(cudaHostGetDevicePointer((void**)&d_abort, h_abort, 0));
+        abort_cap = n * 2;
+        return B200_OK;
+    }
 };
-
-static std::mutex g_graph_build_mutex;
 
 struct Carver {
     size_t off = 0;
@@ -1420,459 +1941,453 @@ struct Carver {
     }
 };
 
-static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2, volatile uint8_t* force_stop, double* pose_out,
-                 double* points_out, uint8_t* outlier_out, b200_lba_stats_t* stats) {
-    const int K = P->n_poses, L = P->n_points, E = P->n_edges;
-    if (stats) std::memset(stats, 0, sizeof(*stats));
+// per-window byte offsets into the arena
+struct WinOff {
+    size_t cams, e_pose, e_point, e_cam, e_robust, e_can, e_obs, e_isig, e_delta, pose_col, pt_col, q0, t0, Rt0, pts0;  // uploaded
+    size_t pt_cnt, pose_cnt, level, chi0, fail, tickets, bad, row_tickets, blk_done;                                                         // zeroed
+    size_t pt_start, order, edges, epcol, pose_start, pose_edges, rowrec, schur_part, lm_mask, blk_cnt, blk_pair_start, blk_chunk_start, pairs, blocks, chunks,
+        chunk_part, robust, q1, t1, Rt1, pts1, chi1, Hpl, Hll, bl, Dinv, Hpp, bp, M, xp, r_chi,
+        r_diag, r_scale, r_result;                                                                                    // scratch
+    size_t exp_begin, qf, tf, pf, out, exp_end;                                                                       // export block
+};
+
+// Solves the windows ws[0..nw) (indices into the caller's arrays) in lockstep.  status[w] is set for every window.
+static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int iters1, int iters2, volatile uint8_t* const* stops,
+                       double* const* pose_outs, double* const* points_outs, uint8_t* const* outlier_outs, b200_lba_stats_t* stats, int* status) {
     const bool debug = getenv("B200_LBA_DEBUG") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
-    // ---- flatten / sort on the host ------------------------------------------------------------------------------
-    std::vector<int> pose_col(K), pt_col(L);
-    int Kf = 0, Lf = 0;
-    for (int k = 0; k < K; ++k) pose_col[k] = P->pose_fixed[k] ? -1 : Kf++;
-    for (int l = 0; l < L; ++l) pt_col[l] = (P->point_fixed && P->point_fixed[l]) ? -1 : Lf++;
-    std::vector<int> pt_start(L + 1, 0), order(E);
-    for (int e = 0; e < E; ++e) {
-        if (P->e_point[e] < 0 || P->e_point[e] >= L || P->e_pose[e] < 0 || P->e_pose[e] >= K || P->e_cam[e] >= P->n_cams) {
-            set_error("b200_lba_solve: edge %d references an invalid vertex/camera", e);
-            return B200_ERR_INVALID;
+    std::vector<int> act;  // windows that take part
+    int ret = B200_OK;
+    for (int w = 0; w < n_all; ++w) {
+        if (stats) std::memset(&stats[w], 0, sizeof(stats[w]));
+        status[w] = B200_OK;
+        if (stops && stops[w] && *stops[w]) {
+            status[w] = B200_ERR_ABORTED;  // local_bundle_adjuster_g2o.cc:308-310
+            continue;
         }
-        pt_start[P->e_point[e] + 1]++;
+        int n_free = 0;
+        for (int k = 0; k < Ps[w].n_poses; ++k) n_free += Ps[w].pose_fixed[k] ? 0 : 1;
+        if (6 * n_free > 1000) {  // only FREE keyframes enter the reduced system; fixed ones are unlimited
+            set_error("b200_lba_solve: window %d has %d free keyframes; the on-chip Cholesky of the reduced system holds at most 166", w, n_free);
+            status[w] = B200_ERR_INVALID;
+            ret = B200_ERR_INVALID;
+            continue;
+        }
+        act.push_back(w);
     }
-    for (int l = 0; l < L; ++l) pt_start[l + 1] += pt_start[l];
-    {
-        std::vector<int> fill(pt_start.begin(), pt_start.end() - 1);
-        for (int e = 0; e < E; ++e) order[fill[P->e_point[e]]++] = e;  // stable: original order within a landmark
-    }
-    std::unique_ptr<EdgeS[]> edges_buf(new EdgeS[std::max(E, 1)]);  // filled below: no zero-initialisation pass
-    EdgeS* edges = edges_buf.get();
-    std::vector<unsigned char> robust(E);
-    std::vector<int> pose_start(Kf + 1, 0), pose_edges;
-    for (int s = 0; s < E; ++s) {
-        const int e = order[s];
-        EdgeS& d = edges[s];
-        d.pose = P->e_pose[e];
-        d.pcol = pose_col[d.pose];
-        d.point = P->e_point[e];
-        d.lcol = pt_col[d.point];
-        d.ox = P->e_obs[3 * e]; d.oy = P->e_obs[3 * e + 1]; d.oxr = P->e_obs[3 * e + 2];
-        d.inv_sigma_sq = P->e_inv_sigma_sq[e];
-        d.delta = P->e_delta[e];
-        d.cam = P->e_cam[e];
-        d.robust = P->e_robust ? P->e_robust[e] : 1;
-        d.can_outlier = P->e_can_be_outlier ? P->e_can_be_outlier[e] : 1;
-        d.pad = 0;
-        robust[s] = d.robust;
-        if (d.pcol >= 0) pose_start[d.pcol + 1]++;
-    }
-    for (int k = 0; k < Kf; ++k) pose_start[k + 1] += pose_start[k];
-    pose_edges.resize(std::max(1, pose_start[Kf]));
-    {
-        std::vector<int> fill(pose_start.begin(), pose_start.end() - 1);
-        for (int s = 0; s < E; ++s)
-            if (edges[s].pcol >= 0) pose_edges[fill[edges[s].pcol]++] = s;
-    }
-    // Schur pair list grouped by upper block (i <= j)
-    const int n_blocks = Kf * (Kf + 1) / 2;
-    // one pass over the landmarks lists every (a, c) with its block; a counting sort by block then gives the grouped list.  A
-    // keyframe observes a landmark once, so a landmark contributes at most one pair to a block and the pairs of a block stay in
-    // landmark order whatever the order inside a landmark: its free-keyframe edges are sorted by column first and only the
-    // upper-triangular combinations are formed.
-    std::vector<int> blk_count(n_blocks + 1, 0);
-    size_t pair_bound = 0;
-    for (int l = 0; l < L; ++l) {
-        const size_t m = (size_t)(pt_start[l + 1] - pt_start[l]);
-        pair_bound += m * (m + 1) / 2;
-    }
-    std::unique_ptr<int2[]> gen_pairs(new int2[pair_bound + 1]);
-    std::unique_ptr<int[]> gen_block(new int[pair_bound + 1]);
-    size_t n_gen = 0;
-    std::vector<int> loc_col, loc_idx;
-    loc_col.reserve(64);
-    loc_idx.reserve(64);
-    for (int l = 0; l < L; ++l) {
-        if (pt_col[l] < 0) continue;
-        loc_col.clear();
-        loc_idx.clear();
-        for (int a = pt_start[l]; a < pt_start[l + 1]; ++a) {
-            const int pa = edges[a].pcol;
-            if (pa < 0) continue;
-            size_t pos = loc_col.size();  // insertion sort by column (a handful of entries)
-            loc_col.push_back(pa);
-            loc_idx.push_back(a);
-            while (pos > 0 && loc_col[pos - 1] > pa) {
-                loc_col[pos] = loc_col[pos - 1];
-                loc_idx[pos] = loc_idx[pos - 1];
-                --pos;
+    const int nw = (int)act.size();
+    S.last_ms = 0.f;
+    S.last_launches = 0;
+    if (nw == 0) return ret;
+    // ---- per-window sizes and the free-vertex columns (O(K + L) on the host; everything O(E) happens on the device) ----------
+    struct HostWin {
+        int K, L, E, Kf, Lf, n, ld, lbc, split, mask_words, n_blocks, n_chunks_bound;
+        size_t n_pairs;
+        std::vector<int> pose_col, pt_col;
+    };
+    std::vector<HostWin> hw(nw);
+    int maxE = 1, maxL = 1, maxKf = 1, maxK = 1, max_n = 0, max_lbc = 1, max_split = 1, max_blocks = 1, max_chunk_warps = 1;
+    std::vector<int> deg;
+    for (int x = 0; x < nw; ++x) {
+        const b200_lba_problem_t& P = Ps[act[x]];
+        HostWin& h = hw[x];
+        h.K = P.n_poses; h.L = P.n_points; h.E = P.n_edges;
+        h.pose_col.resize(std::max(h.K, 1));
+        h.pt_col.resize(std::max(h.L, 1));
+        h.Kf = h.Lf = 0;
+        for (int k = 0; k < h.K; ++k) h.pose_col[k] = P.pose_fixed[k] ? -1 : h.Kf++;
+        if (P.point_fixed) {
+            for (int l = 0; l < h.L; ++l) h.pt_col[l] = P.point_fixed[l] ? -1 : h.Lf++;
+        } else {
+            for (int l = 0; l < h.L; ++l) h.pt_col[l] = l;
+            h.Lf = h.L;
+        }
+        h.n = 6 * h.Kf;
+        h.ld = h.n + 2;
+        h.lbc = std::max(1, ceil_div(h.L, 16));
+        // CTAs per block row of the Schur complement: enough CTAs for one window to fill the chip, chosen from the window's own size
+        // only so that a window gives the same bits whatever batch it is solved in
+        h.split = std::max(1, std::min(8, ceil_div(S.schur_ctas, std::max(h.Kf, 1))));
+        max_split = std::max(max_split, h.split);
+        // pairs of the Schur complement: every landmark with m free-keyframe observations contributes m (m + 1) / 2 (one counting pass
+        // over the observations; everything else that is O(E) happens on the device)
+        h.mask_words = std::max(1, ceil_div(h.Kf, 64));
+        h.n_blocks = h.Kf * (h.Kf + 1) / 2;
+        h.n_pairs = 0;
+        if (!S.schur_rows) {
+            deg.assign(std::max(h.L, 1), 0);
+            for (int e = 0; e < h.E; ++e) {
+                const int p = P.e_point[e], k = P.e_pose[e];
+                if (p >= 0 && p < h.L && k >= 0 && k < h.K && h.pose_col[k] >= 0 && h.pt_col[p] >= 0) deg[p]++;
             }
-            loc_col[pos] = pa;
-            loc_idx[pos] = a;
+            for (int l = 0; l < h.L; ++l) h.n_pairs += (size_t)deg[l] * (deg[l] + 1) / 2;
         }
-        const int m = (int)loc_col.size();
-        for (int x = 0; x < m; ++x) {
-            const int pa = loc_col[x];
-            const int row = pa * Kf - pa * (pa - 1) / 2 - pa;  // block_id(pa, pc) = row + pc
-            for (int y = x; y < m; ++y) {
-                const int bid = row + loc_col[y];
-                gen_pairs[n_gen] = make_int2(loc_idx[x], loc_idx[y]);
-                gen_block[n_gen++] = bid;
-                blk_count[bid + 1]++;
-            }
-        }
+        h.n_chunks_bound = (int)(h.n_pairs / kSchurChunk) + h.n_blocks + 1;
+        max_blocks = std::max(max_blocks, h.n_blocks);
+        max_chunk_warps = std::max(max_chunk_warps, h.n_chunks_bound + h.n_blocks);
+        maxE = std::max(maxE, h.E); maxL = std::max(maxL, h.L); maxKf = std::max(maxKf, h.Kf); maxK = std::max(maxK, h.K);
+        max_n = std::max(max_n, h.n); max_lbc = std::max(max_lbc, h.lbc);
     }
-    for (int b2 = 0; b2 < n_blocks; ++b2) blk_count[b2 + 1] += blk_count[b2];
-    const int n_pairs = blk_count[n_blocks];
-    std::vector<int2> pairs(std::max(1, n_pairs));
-    {
-        std::vector<int> fill(blk_count.begin(), blk_count.end() - 1);
-        for (int i = 0; i < n_pairs; ++i) pairs[fill[gen_block[i]]++] = gen_pairs[i];
+    // ---- arena layout -------------------------------------------------------------------------------------------------------
+    std::vector<WinOff> wo(nw);
+    Carver cv;
+    const size_t o_wins = cv.take<WinDev>(nw), o_ctl = cv.take<LmCtl>(nw);
+    for (int x = 0; x < nw; ++x) {
+        const HostWin& h = hw[x];
+        const b200_lba_problem_t& P = Ps[act[x]];
+        WinOff& o = wo[x];
+        const size_t E = h.E, K = h.K, L = h.L;
+        o.cams = cv.take<Cam>(P.n_cams); o.e_pose = cv.take<int>(E); o.e_point = cv.take<int>(E); o.e_cam = cv.take<unsigned char>(E);
+        o.e_robust = cv.take<unsigned char>(E); o.e_can = cv.take<unsigned char>(E); o.e_obs = cv.take<float>(3 * E); o.e_isig = cv.take<float>(E);
+        o.e_delta = cv.take<float>(E); o.pose_col = cv.take<int>(K); o.pt_col = cv.take<int>(L); o.q0 = cv.take<double>(4 * K);
+        o.t0 = cv.take<double>(3 * K); o.Rt0 = cv.take<double>(12 * K); o.pts0 = cv.take<double>(3 * L);
     }
-    std::vector<SchurBlock> blocks(std::max(1, n_blocks));
-    std::vector<SchurChunk> chunks;
-    std::vector<int> empty_blocks;
-    for (int i = 0, b = 0; i < Kf; ++i)
-        for (int j = i; j < Kf; ++j, ++b) {
-            const int c0 = (int)chunks.size();
-            for (int sidx = blk_count[b]; sidx < blk_count[b + 1]; sidx += kSchurChunk)
-                chunks.push_back(SchurChunk{sidx, std::min(sidx + kSchurChunk, blk_count[b + 1]), i == j ? 1 : 0, b});
-            blocks[b] = SchurBlock{i, j, c0, (int)chunks.size()};
-            if (c0 == (int)chunks.size()) empty_blocks.push_back(b);  // no pair falls into this block: it is just Hpp + lambda I or zero
-        }
-    const int n_chunks = (int)chunks.size();
-    // pose-side chunks: kPoseChunk edges of one free keyframe per warp
-    std::vector<int2> pose_chunks;          // (start, end) into pose_edges
-    std::vector<int> pose_chunk_start(Kf + 1, 0);
-    for (int k = 0; k < Kf; ++k) {
-        for (int sidx = pose_start[k]; sidx < pose_start[k + 1]; sidx += kPoseChunk)
-            pose_chunks.push_back(make_int2(sidx, std::min(sidx + kPoseChunk, pose_start[k + 1])));
-        pose_chunk_start[k + 1] = (int)pose_chunks.size();
+    const size_t upload_bytes = round_up(cv.off, (size_t)256);
+    cv.off = upload_bytes;
+    for (int x = 0; x < nw; ++x) {
+        const HostWin& h = hw[x];
+        WinOff& o = wo[x];
+        o.pt_cnt = cv.take<int>(h.L); o.pose_cnt = cv.take<int>(h.Kf); o.level = cv.take<unsigned char>(h.E); o.chi0 = cv.take<double>(h.E);
+        o.fail = cv.take<int>(1); o.tickets = cv.take<int>(2); o.bad = cv.take<int>(1); o.row_tickets = cv.take<int>(h.Kf);
+        o.blk_done = cv.take<int>(h.n_blocks);
     }
-    const int n_pose_chunks = (int)pose_chunks.size();
-    // initial state: util::converter::to_g2o_SE3 (util/converter.cc:17-21)
-    std::vector<double> q0(4 * (size_t)std::max(K, 1)), t0(3 * (size_t)std::max(K, 1)), Rt0(12 * (size_t)std::max(K, 1));
-    for (int k = 0; k < K; ++k) {
-        const double* M = P->pose_cw + 16 * (size_t)k;
-        const double R[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]};
-        rot_to_quat(R, &q0[4 * k]);
-        quat_normalize(&q0[4 * k]);
-        t0[3 * k] = M[3]; t0[3 * k + 1] = M[7]; t0[3 * k + 2] = M[11];
-        quat_to_rot(&q0[4 * k], &Rt0[12 * k]);
-        Rt0[12 * k + 9] = M[3]; Rt0[12 * k + 10] = M[7]; Rt0[12 * k + 11] = M[11];
+    const size_t o_zeros = cv.take<double>(kHplStride * (kSchurFan + 1));
+    const size_t zero_end = round_up(cv.off, (size_t)256);
+    cv.off = zero_end;
+    for (int x = 0; x < nw; ++x) {
+        const HostWin& h = hw[x];
+        WinOff& o = wo[x];
+        const size_t E = h.E, K = h.K, L = h.L, Kf = h.Kf, Lf = h.Lf;
+        o.pt_start = cv.take<int>(L + 1); o.order = cv.take<int>(E); o.edges = cv.take<EdgeS>(E); o.epcol = cv.take<int>(E);
+        o.pose_start = cv.take<int>(Kf + 1); o.pose_edges = cv.take<int>(E); o.rowrec = cv.take<int4>(E);
+        o.schur_part = cv.take<double>((S.schur_rows && h.split > 1) ? (size_t)h.split * 64 * (Kf * (Kf + 1) / 2) : 0);
+        o.lm_mask = cv.take<unsigned long long>(L * (size_t)h.mask_words); o.blk_cnt = cv.take<int>(h.n_blocks);
+        o.blk_pair_start = cv.take<int>(h.n_blocks + 1); o.blk_chunk_start = cv.take<int>(h.n_blocks + 1); o.pairs = cv.take<int4>(h.n_pairs);
+        o.blocks = cv.take<SchurBlock>(h.n_blocks); o.chunks = cv.take<SchurChunk>(h.n_chunks_bound);
+        o.chunk_part = cv.take<double>(42 * (size_t)h.n_chunks_bound); o.robust = cv.take<unsigned char>(E);
+        o.q1 = cv.take<double>(4 * K); o.t1 = cv.take<double>(3 * K); o.Rt1 = cv.take<double>(12 * K); o.pts1 = cv.take<double>(3 * L);
+        o.chi1 = cv.take<double>(E); o.Hpl = cv.take<double>(kHplStride * (E + kSchurFan)); o.Hll = cv.take<double>(6 * Lf); o.bl = cv.take<double>(3 * Lf);
+        o.Dinv = cv.take<double>(6 * Lf); o.Hpp = cv.take<double>(36 * Kf); o.bp = cv.take<double>(6 * Kf);
+        o.M = cv.take<double>((size_t)(h.n + 1) * h.ld); o.xp = cv.take<double>(h.n);
+        o.r_chi = cv.take<double>(h.lbc); o.r_diag = cv.take<double>(h.lbc); o.r_scale = cv.take<double>(h.lbc); o.r_result = cv.take<double>(8);
     }
-    std::vector<Cam> cams(std::max(1, P->n_cams));
-    for (int i = 0; i < P->n_cams; ++i) {
-        const b200_camera_t& c = P->cams[i];
-        cams[i] = Cam{c.model, c.fx, c.fy, c.cx, c.cy, c.fxb, c.cols, c.rows};
+    const size_t export_begin = round_up(cv.off, (size_t)256);
+    cv.off = export_begin;
+    for (int x = 0; x < nw; ++x) {
+        const HostWin& h = hw[x];
+        WinOff& o = wo[x];
+        o.qf = cv.take<double>(4 * (size_t)h.K); o.tf = cv.take<double>(3 * (size_t)h.K); o.pf = cv.take<double>(3 * (size_t)h.L);
+        o.out = cv.take<unsigned char>(h.E);
     }
-
-    if (debug) fprintf(stderr, "[lba] host plan %.3f ms (E = %d, pairs = %d, chunks = %d)\n", ms_since(t_begin), E, n_pairs, n_chunks);
-    // ---- device arena ----------------------------------------------------------------------------------------------
-    const int n = 6 * Kf;
-    const int eb = ceil_div(std::max(E, 1), kEdgeThreads), lb = ceil_div(std::max(L, 1), 128), lb2 = ceil_div(std::max(L, 1), 16);
-    Carver up;  // uploaded region (mirrors the pinned staging buffer)
-    const size_t o_edges = up.take<EdgeS>(E), o_cams = up.take<Cam>(P->n_cams), o_ptstart = up.take<int>(L + 1);
-    const size_t o_posestart = up.take<int>(Kf + 1), o_poseedges = up.take<int>(pose_edges.size()), o_robust = up.take<unsigned char>(E);
-    const size_t o_posecol = up.take<int>(K), o_blocks = up.take<SchurBlock>(n_blocks), o_pairs = up.take<int2>(n_pairs);
-    const size_t o_chunks = up.take<SchurChunk>(n_chunks), o_pchunks = up.take<int2>(n_pose_chunks), o_pcstart = up.take<int>(Kf + 1);
-    const size_t o_q0 = up.take<double>(4 * (size_t)K), o_t0 = up.take<double>(3 * (size_t)K), o_Rt0 = up.take<double>(12 * (size_t)K);
-    const size_t o_pts0 = up.take<double>(3 * (size_t)L);
-    const int n_empty = (int)empty_blocks.size();
-    const size_t o_empty = up.take<int>(n_empty), o_blkdone = up.take<int>(n_blocks), o_tickets = up.take<int>(2);  // counters upload as zeros
-    const size_t upload_bytes = round_up(up.off, (size_t)256);
-    Carver dv;
-    dv.off = upload_bytes;
-    const size_t o_q1 = dv.take<double>(4 * (size_t)K), o_t1 = dv.take<double>(3 * (size_t)K), o_Rt1 = dv.take<double>(12 * (size_t)K);
-    const size_t o_pts1 = dv.take<double>(3 * (size_t)L);
-    const size_t o_level = dv.take<unsigned char>(E), o_chi0 = dv.take<double>(E), o_chi1 = dv.take<double>(E);
-    const size_t o_Hpl = dv.take<double>(18 * (size_t)E), o_pl = dv.take<double>(9 * (size_t)E);
-    const size_t o_Hll = dv.take<double>(6 * (size_t)Lf), o_bl = dv.take<double>(3 * (size_t)Lf), o_Dinv = dv.take<double>(6 * (size_t)Lf);
-    const size_t o_part = dv.take<double>(42 * (size_t)n_chunks), o_ppart = dv.take<double>(27 * (size_t)n_pose_chunks), o_Hpp = dv.take<double>(36 * (size_t)Kf), o_bp = dv.take<double>(6 * (size_t)Kf);
-    const int ld = n + 2;
-    const size_t o_Hs = dv.take<double>((size_t)(n + 1) * ld), o_xp = dv.take<double>(n);
-    // readback block: [chi partials eb][diag partials lb][scale partials lb2][result 2]
-    const size_t res_n = (size_t)eb + (size_t)lb + (size_t)lb2 + 6;
-    const size_t o_res = dv.take<double>(res_n), o_fail = dv.take<int>(1), o_out = dv.take<unsigned char>(E);
-    const size_t o_ctl = dv.take<LmCtl>(1), o_qf = dv.take<double>(4 * (size_t)K), o_tf = dv.take<double>(3 * (size_t)K), o_pf = dv.take<double>(3 * (size_t)L);
-    int rc = S.ensure(dv.off + 256, upload_bytes, res_n + 36 * (size_t)std::max(Kf, 1));
+    const size_t export_bytes = round_up(cv.off, (size_t)256) - export_begin;
+    const size_t ctl_doubles = ceil_div(sizeof(LmCtl) * (size_t)nw, sizeof(double)) + 8;
+    int rc = S.ensure(cv.off + 512, upload_bytes, ceil_div(export_bytes, sizeof(double)) + 2 * ctl_doubles + 64);
     if (rc) return rc;
-    unsigned char* hs = S.h_stage;
-    std::memset(hs, 0, upload_bytes);
-    auto put = [&](size_t off, const void* src, size_t bytes) { if (bytes) std::memcpy(hs + off, src, bytes); };
-    put(o_edges, edges, sizeof(EdgeS) * E);
-    put(o_cams, cams.data(), sizeof(Cam) * P->n_cams);
-    put(o_ptstart, pt_start.data(), sizeof(int) * (L + 1));
-    put(o_posestart, pose_start.data(), sizeof(int) * (Kf + 1));
-    put(o_poseedges, pose_edges.data(), sizeof(int) * pose_edges.size());
-    put(o_robust, robust.data(), E);
-    put(o_posecol, pose_col.data(), sizeof(int) * K);
-    put(o_blocks, blocks.data(), sizeof(SchurBlock) * n_blocks);
-    put(o_chunks, chunks.data(), sizeof(SchurChunk) * n_chunks);
-    put(o_pchunks, pose_chunks.data(), sizeof(int2) * n_pose_chunks);
-    put(o_pcstart, pose_chunk_start.data(), sizeof(int) * (Kf + 1));
-    put(o_pairs, pairs.data(), sizeof(int2) * n_pairs);
-    put(o_q0, q0.data(), sizeof(double) * 4 * K);
-    put(o_t0, t0.data(), sizeof(double) * 3 * K);
-    put(o_Rt0, Rt0.data(), sizeof(double) * 12 * K);
-    put(o_pts0, P->points, sizeof(double) * 3 * (size_t)L);
-    put(o_empty, empty_blocks.data(), sizeof(int) * n_empty);
-    if (debug) fprintf(stderr, "[lba] host plan + staging %.3f ms (upload %.2f MB)\n", ms_since(t_begin), upload_bytes / 1e6);
+    if ((rc = S.ensure_abort(nw))) return rc;
     unsigned char* d = S.d_arena;
+    unsigned char* hs = S.h_stage;
+    LmCtl* h_ctl2[2] = {reinterpret_cast<LmCtl*>(S.h_res), reinterpret_cast<LmCtl*>(S.h_res + ctl_doubles)};  // read-back mirrors of the control blocks
+    LmCtl* h_ctl = h_ctl2[0];
+    unsigned char* h_export = reinterpret_cast<unsigned char*>(S.h_res + 2 * ctl_doubles + 8);
+    // ---- staging: the caller's arrays as they are, the initial keyframe states, the descriptors -------------------------------
+    WinDev* hwd = reinterpret_cast<WinDev*>(hs + o_wins);
+    LmCtl* hctl0 = reinterpret_cast<LmCtl*>(hs + o_ctl);
+    for (int x = 0; x < nw; ++x) {
+        const HostWin& h = hw[x];
+        const b200_lba_problem_t& P = Ps[act[x]];
+        const WinOff& o = wo[x];
+        const size_t E = h.E, K = h.K, L = h.L;
+        Cam* cams = reinterpret_cast<Cam*>(hs + o.cams);
+        for (int i = 0; i < P.n_cams; ++i) {
+            const b200_camera_t& c = P.cams[i];
+            cams[i] = Cam{c.model, c.fx, c.fy, c.cx, c.cy, c.fxb, c.cols, c.rows};
+        }
+        if (E) {
+            std::memcpy(hs + o.e_pose, P.e_pose, sizeof(int) * E);
+            std::memcpy(hs + o.e_point, P.e_point, sizeof(int) * E);
+            std::memcpy(hs + o.e_cam, P.e_cam, E);
+            if (P.e_robust) std::memcpy(hs + o.e_robust, P.e_robust, E);
+            else std::memset(hs + o.e_robust, 1, E);
+            if (P.e_can_be_outlier) std::memcpy(hs + o.e_can, P.e_can_be_outlier, E);
+            else std::memset(hs + o.e_can, 1, E);
+            std::memcpy(hs + o.e_obs, P.e_obs, sizeof(float) * 3 * E);
+            std::memcpy(hs + o.e_isig, P.e_inv_sigma_sq, sizeof(float) * E);
+            std::memcpy(hs + o.e_delta, P.e_delta, sizeof(float) * E);
+        }
+        if (K) std::memcpy(hs + o.pose_col, h.pose_col.data(), sizeof(int) * K);
+        if (L) {
+            std::memcpy(hs + o.pt_col, h.pt_col.data(), sizeof(int) * L);
+            std::memcpy(hs + o.pts0, P.points, sizeof(double) * 3 * L);
+        }
+        double* q0 = reinterpret_cast<double*>(hs + o.q0);
+        double* t0 = reinterpret_cast<double*>(hs + o.t0);
+        double* Rt0 = reinterpret_cast<double*>(hs + o.Rt0);
+        for (size_t k = 0; k < K; ++k) {  // util::converter::to_g2o_SE3 (util/converter.cc:17-21)
+            const double* M = P.pose_cw + 16 * k;
+            const double R[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]};
+            rot_to_quat(R, &q0[4 * k]);
+            quat_normalize(&q0[4 * k]);
+            t0[3 * k] = M[3]; t0[3 * k + 1] = M[7]; t0[3 * k + 2] = M[11];
+            quat_to_rot(&q0[4 * k], &Rt0[12 * k]);
+            Rt0[12 * k + 9] = M[3]; Rt0[12 * k + 10] = M[7]; Rt0[12 * k + 11] = M[11];
+        }
+        WinDev& W = hwd[x];
+        std::memset(&W, 0, sizeof(W));
+        W.K = h.K; W.L = h.L; W.E = h.E; W.Kf = h.Kf; W.Lf = h.Lf; W.n = h.n; W.ld = h.ld; W.n_cams = P.n_cams; W.lbc = h.lbc;
+        W.e_pose = (const int*)(d + o.e_pose); W.e_point = (const int*)(d + o.e_point); W.e_cam = d + o.e_cam; W.e_robust = d + o.e_robust;
+        W.e_can_outlier = d + o.e_can; W.e_obs = (const float*)(d + o.e_obs); W.e_isig = (const float*)(d + o.e_isig);
+        W.e_delta = (const float*)(d + o.e_delta); W.pose_col = (const int*)(d + o.pose_col); W.pt_col = (const int*)(d + o.pt_col);
+        W.cams = (const Cam*)(d + o.cams);
+        W.pt_cnt = (int*)(d + o.pt_cnt); W.pt_start = (int*)(d + o.pt_start); W.order = (int*)(d + o.order); W.edges = (EdgeS*)(d + o.edges);
+        W.epcol = (int*)(d + o.epcol); W.pose_cnt = (int*)(d + o.pose_cnt); W.pose_start = (int*)(d + o.pose_start);
+        W.pose_edges = (int*)(d + o.pose_edges); W.level = d + o.level; W.robust = d + o.robust;
+        W.rowrec = (int4*)(d + o.rowrec); W.schur_split = h.split; W.schur_part = (double*)(d + o.schur_part); W.row_tickets = (int*)(d + o.row_tickets);
+        W.zeros = (const double*)(d + o_zeros);
+        W.lm_mask = (unsigned long long*)(d + o.lm_mask); W.mask_words = h.mask_words; W.n_blocks = h.n_blocks; W.blk_cnt = (int*)(d + o.blk_cnt);
+        W.blk_pair_start = (int*)(d + o.blk_pair_start); W.blk_chunk_start = (int*)(d + o.blk_chunk_start); W.pairs = (int4*)(d + o.pairs);
+        W.blocks = (SchurBlock*)(d + o.blocks); W.chunks = (SchurChunk*)(d + o.chunks); W.chunk_part = (double*)(d + o.chunk_part);
+        W.blk_done = (int*)(d + o.blk_done);
+        W.q[0] = (double*)(d + o.q0); W.q[1] = (double*)(d + o.q1); W.t[0] = (double*)(d + o.t0); W.t[1] = (double*)(d + o.t1);
+        W.Rt[0] = (double*)(d + o.Rt0); W.Rt[1] = (double*)(d + o.Rt1); W.pts[0] = (double*)(d + o.pts0); W.pts[1] = (double*)(d + o.pts1);
+        W.chi[0] = (double*)(d + o.chi0); W.chi[1] = (double*)(d + o.chi1);
+        W.Hpl = (double*)(d + o.Hpl); W.Hll = (double*)(d + o.Hll); W.bl = (double*)(d + o.bl); W.Dinv = (double*)(d + o.Dinv);
+        W.Hpp = (double*)(d + o.Hpp); W.bp = (double*)(d + o.bp); W.M = (double*)(d + o.M); W.xp = (double*)(d + o.xp);
+        W.r_chi = (double*)(d + o.r_chi); W.r_diag = (double*)(d + o.r_diag); W.r_scale = (double*)(d + o.r_scale); W.r_result = (double*)(d + o.r_result);
+        W.fail = (int*)(d + o.fail); W.tickets = (int*)(d + o.tickets); W.bad_input = (int*)(d + o.bad);
+        W.ctl = (LmCtl*)(d + o_ctl) + x;
+        W.qf = (double*)(d + o.qf); W.tf = (double*)(d + o.tf); W.pf = (double*)(d + o.pf); W.out = d + o.out;
+        LmCtl& c = hctl0[x];
+        std::memset(&c, 0, sizeof(c));
+        c.ok = 1;
+        S.h_abort[x] = 0;
+        c.abort_word = (stops && stops[act[x]]) ? S.d_abort + x : nullptr;
+    }
+    if (debug) fprintf(stderr, "[lba] %d windows staged in %.3f ms (upload %.2f MB, arena %.1f MB)\n", nw, ms_since(t_begin), upload_bytes / 1e6, cv.off / 1e6);
     cudaStream_t st = S.stream;
     int launches = 0;
-    B200_CUDA(cudaEventRecord(S.ev0, st));
-    B200_CUDA(cudaMemcpyAsync(d, hs, upload_bytes, cudaMemcpyHostToDevice, st));
-    B200_CUDA(cudaMemsetAsync(d + o_level, 0, E ? E : 1, st));
-    B200_CUDA(cudaMemsetAsync(d + o_chi0, 0, sizeof(double) * (E ? E : 1), st));
-    B200_CUDA(cudaMemsetAsync(d + o_fail, 0, sizeof(int), st));
-
-    View v{K, L, E, Kf, Lf, (const EdgeS*)(d + o_edges), (const Cam*)(d + o_cams), (const int*)(d + o_ptstart), (const int*)(d + o_posestart),
-           (const int*)(d + o_poseedges), d + o_level, d + o_robust};
-    double* qs[2] = {(double*)(d + o_q0), (double*)(d + o_q1)};
-    double* ts[2] = {(double*)(d + o_t0), (double*)(d + o_t1)};
-    double* Rts[2] = {(double*)(d + o_Rt0), (double*)(d + o_Rt1)};
-    double* ptss[2] = {(double*)(d + o_pts0), (double*)(d + o_pts1)};
-    double* chis[2] = {(double*)(d + o_chi0), (double*)(d + o_chi1)};
-    double *Hpl = (double*)(d + o_Hpl), *pl = (double*)(d + o_pl), *Hll = (double*)(d + o_Hll), *bl = (double*)(d + o_bl);
-    double *Dinv = (double*)(d + o_Dinv), *part = (double*)(d + o_part), *ppart = (double*)(d + o_ppart), *Hpp = (double*)(d + o_Hpp), *bp = (double*)(d + o_bp);
-    double *Hs = (double*)(d + o_Hs), *xp = (double*)(d + o_xp), *res = (double*)(d + o_res);
-    const size_t chol_smem = sizeof(double) * ((size_t)kNB * (kNB + 1) + 4 + (size_t)((n + 1 + 3) & ~3) * kNB);
-    B200_CUDA(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
-    int* fail = (int*)(d + o_fail);
-    double* r_chi = res;                 // eb
-    double* r_diag = res + eb;           // lb
-    double* r_scale = res + eb + lb;     // lb
-    double* r_result = res + eb + lb + lb2;  // 2
-    Dual dq{{qs[0], qs[1]}}, dt{{ts[0], ts[1]}}, dRt{{Rts[0], Rts[1]}}, dpts{{ptss[0], ptss[1]}}, dchi{{chis[0], chis[1]}};
-    LmCtl* ctl = (LmCtl*)(d + o_ctl);
-    LmCtl* hc = S.h_ctl;
-    std::memset(hc, 0, sizeof(LmCtl));
-    hc->ok = 1;
-    *S.h_abort = 0;
-    hc->abort_word = force_stop ? S.d_abort : nullptr;
-    B200_CUDA(cudaMemcpyAsync(ctl, hc, sizeof(LmCtl), cudaMemcpyHostToDevice, st));
-    const bool use_graph = !S.host_loop;
-    const int ug = use_graph ? 1 : 0;
-
-    // the kernels of one buildSystem and of one LM trial (identical in graph and host-stepped mode)
-    auto tail_of = [&](int ticket_idx, int n_launches, cudaGraphConditionalHandle h_in, cudaGraphConditionalHandle h_out) {
-        CtlTail t{};
-        t.ctl = ctl;
-        t.ticket = (int*)(d + o_tickets) + ticket_idx;
-        t.r_chi = r_chi; t.r_diag = r_diag; t.r_scale = r_scale; t.r_result = r_result; t.Hpp = Hpp;
-        t.eb = E ? eb : 0; t.lb = lb; t.lb2 = lb2; t.Kf = Kf; t.n_launches = n_launches; t.use_graph = ug;
-        t.h_inner = h_in; t.h_outer = h_out;
-        return t;
-    };
-    // computeActiveErrors + buildSystem: 3 launches; the last CTA of the keyframe-side kernel also runs the LM bookkeeping
-    auto launch_build = [&](cudaGraphConditionalHandle h_in) -> int {
-        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 1, 0, nullptr, ctl, CtlTail{});
-        points_kernel<<<lb, 128, 0, st>>>(v, pl, Hll, bl, r_diag);
-        if (n_pose_chunks) {
-            pose_chunks_kernel<<<ceil_div(n_pose_chunks, 4), 128, 0, st>>>(v, (const int2*)(d + o_pchunks), n_pose_chunks, dRt, dpts, ppart, ctl,
-                                                                          (const int*)(d + o_pcstart), Hpp, bp, tail_of(0, 3, h_in, h_in));
-        } else {
-            if (Kf) {
-                B200_CUDA(cudaMemsetAsync(Hpp, 0, sizeof(double) * 36 * Kf, st));
-                B200_CUDA(cudaMemsetAsync(bp, 0, sizeof(double) * 6 * Kf, st));
-            }
-            lm_after_build_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, r_diag, lb, Hpp, Kf, 3, h_in, ug);
+    S.prof_kind.clear();
+    auto mark = [&](int kind) -> int {  // profiling: the time since the previous mark belongs to `kind`
+        if (!S.profile) return B200_OK;
+        const size_t idx = S.prof_kind.size();
+        if (idx >= S.prof_ev.size()) {
+            cudaEvent_t e;
+            B200_CUDA(cudaEventCreate(&e));
+            S.prof_ev.push_back(e);
         }
+        B200_CUDA(cudaEventRecord(S.prof_ev[idx], st));
+        S.prof_kind.push_back(kind);
         return B200_OK;
     };
-    // one LM trial: 5 launches; the last CTA of the trial's chi2 evaluation runs the accept / reject bookkeeping
-    auto launch_trial = [&](cudaGraphConditionalHandle h_in, cudaGraphConditionalHandle h_out) -> int {
-        if (Lf) dinv_kernel<<<ceil_div(Lf, 128), 128, 0, st>>>(Lf, ctl, Hll, Dinv, fail);
-        if (n_blocks)
-            schur_chunks_kernel<<<ceil_div(std::max(n_chunks + n_empty, 1), 4), 128, 0, st>>>(
-                v, (const SchurChunk*)(d + o_chunks), n_chunks, (const int2*)(d + o_pairs), Hpl, Dinv, bl, part, ctl, (const SchurBlock*)(d + o_blocks),
-                (const int*)(d + o_empty), n_empty, (int*)(d + o_blkdone), Hpp, bp, Hs, n, ld);
+    B200_CUDA(cudaEventRecord(S.ev0, st));
+    B200_CUDA(cudaMemcpyAsync(d, hs, upload_bytes, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemsetAsync(d + upload_bytes, 0, zero_end - upload_bytes, st));
+    if ((rc = mark(-1))) return rc;
+    const WinDev* wins = (const WinDev*)(d + o_wins);
+    const LmCtl* d_ctl = (const LmCtl*)(d + o_ctl);
+    // ---- plan on the device ----------------------------------------------------------------------------------------------------
+    plan_count_kernel<<<dim3(ceil_div(maxE, 256), nw), 256, 0, st>>>(wins);
+    plan_scan_kernel<<<nw, 1024, 0, st>>>(wins);
+    plan_place_kernel<<<dim3(ceil_div(maxE, 256), nw), 256, 0, st>>>(wins);
+    plan_sort_kernel<<<dim3(ceil_div(maxL, 128), nw), 128, 0, st>>>(wins);
+    plan_pose_lists_kernel<<<dim3(maxKf, nw), kListThreads, 0, st>>>(wins);
+    launches += 5;
+    if (!S.schur_rows) {
+        plan_pairs_kernel<false><<<dim3(ceil_div(max_blocks, 4), nw), 128, 0, st>>>(wins);
+        plan_pair_scan_kernel<<<nw, 1024, 0, st>>>(wins);
+        plan_pairs_kernel<true><<<dim3(ceil_div(max_blocks, 4), nw), 128, 0, st>>>(wins);
+        launches += 3;
+    }
+    if ((rc = mark(0))) return rc;
+    // ---- LM rounds in lockstep ---------------------------------------------------------------------------------------------------
+    const size_t chol_smem = sizeof(double) * ((size_t)kNB * (kNB + 1) + 4 + (size_t)((max_n + 1 + 3) & ~3) * kNB);
+    B200_CUDA(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
+    // warps per Schur row CTA: every warp owns Kf accumulator tiles of 512 bytes
+    int schur_warps = std::min(kSchurMaxWarps, std::max(1, S.schur_warps));
+    while (schur_warps > 1 && (size_t)schur_warps * maxKf * 512 > 200 * 1024) schur_warps >>= 1;
+    const size_t schur_smem = (size_t)schur_warps * maxKf * 512;
+    B200_CUDA(cudaFuncSetAttribute(schur_rows_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem));
+    B200_CUDA(cudaFuncSetAttribute(schur_rows_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_smem));
+    // 8-CTA clusters must sit inside one GPC: 16 of them do not fit the chip at once (measured: 270 vs 172 us per factorisation of
+    // 16 windows with clusters of 4), so batches use the smaller cluster; B200_LBA_CLUSTER pins it
+    const int chol_cluster = S.chol_cluster_pinned ? S.chol_cluster : (nw <= 2 ? 8 : 4);
+    auto launch_rep = [&]() -> int {
+        // computeActiveErrors + buildSystem (windows that start an iteration)
+        int rcm;
+        landmark_kernel<kBuild><<<dim3(max_lbc, nw), kLmThreads, 0, st>>>(wins);
+        if ((rcm = mark(1))) return rcm;
+        pose_rows_kernel<<<dim3(maxKf, nw), kRowThreads, 0, st>>>(wins);
+        if ((rcm = mark(2))) return rcm;
+        // one LM trial (every window that is still iterating)
+        if (!S.schur_rows) schur_chunks_kernel<<<dim3(ceil_div(max_chunk_warps, 4), nw), 128, 0, st>>>(wins);
+        else if (S.schur_unroll == 2) schur_rows_kernel<2><<<dim3(maxKf, nw, max_split), 32 * schur_warps, schur_smem, st>>>(wins, schur_warps);
+        else schur_rows_kernel<4><<<dim3(maxKf, nw, max_split), 32 * schur_warps, schur_smem, st>>>(wins, schur_warps);
+        if ((rcm = mark(3))) return rcm;
         {
             cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(S.chol_cluster);
+            cfg.gridDim = dim3(chol_cluster * nw);
             cfg.blockDim = dim3(kCholThreads);
             cfg.dynamicSmemBytes = chol_smem;
             cfg.stream = st;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = S.chol_cluster;
+            attr[0].val.clusterDim.x = chol_cluster;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            B200_CUDA(cudaLaunchKernelEx(&cfg, chol_solve_kernel, n, ld, Hs, (const LmCtl*)ctl, (const double*)bp, xp, K, (const int*)(d + o_posecol), dq,
-                                         dt, dRt, r_result, fail));
+            B200_CUDA(cudaLaunchKernelEx(&cfg, chol_solve_kernel, wins));
         }
-        backsub_kernel<<<lb2, 128, 0, st>>>(v, ctl, Dinv, bl, Hpl, xp, dpts, r_scale, fail);
-        if (E) {
-            edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 0, 1, fail, ctl, tail_of(1, 5, h_in, h_out));
-        } else {
-            B200_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), st));
-            lm_after_trial_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, 0, r_scale, lb2, r_result, 5, h_in, h_out, ug);
-        }
+        if ((rcm = mark(4))) return rcm;
+        backsub_kernel<<<dim3(max_lbc, nw), 128, 0, st>>>(wins);
+        if ((rcm = mark(5))) return rcm;
+        landmark_kernel<kTrial><<<dim3(max_lbc, nw), kLmThreads, 0, st>>>(wins);
+        if ((rcm = mark(6))) return rcm;
+        launches += 6;
         return B200_OK;
     };
-    auto launch_round_tail = [&](int round) -> int {  // chi2 of every active edge at the final state (terminate action's computeActiveErrors)
-        if (E) edges_kernel<<<eb, kEdgeThreads, 0, st>>>(v, dRt, dpts, dchi, Hpl, pl, r_chi, 0, 0, nullptr, ctl, CtlTail{});
-        lm_round_end_kernel<<<1, kCtlThreads, 0, st>>>(ctl, r_chi, E ? eb : 0, round);
+    // Read the control blocks back into mirror `b` (asynchronously) / wait for that copy.  The loop below always has the NEXT chunk
+    // of repetitions enqueued before it waits for the read-back of the previous one, so the GPU never idles on a host decision; a
+    // chunk enqueued for windows that have all finished costs a handful of empty launches.
+    auto fetch_issue = [&](int b) -> int {
+        B200_CUDA(cudaMemcpyAsync(h_ctl2[b], d_ctl, sizeof(LmCtl) * nw, cudaMemcpyDeviceToHost, st));
+        B200_CUDA(cudaEventRecord(S.ev_ctl[b], st));
         return B200_OK;
+    };
+    auto fetch_wait = [&](int b) -> int {
+        B200_CUDA(S.wait_event(S.ev_ctl[b]));
+        h_ctl = h_ctl2[b];
+        for (int x = 0; x < nw; ++x)  // the caller's flag may be raised by another thread meanwhile (mapping_module.cc:124)
+            if (stops && stops[act[x]] && *stops[act[x]]) S.h_abort[x] = 1;
+        return B200_OK;
+    };
+    auto fetch_ctl = [&]() -> int {
+        int r_ = fetch_issue(0);
+        return r_ ? r_ : fetch_wait(0);
     };
     const int iters[2] = {iters1, iters2};
     int rc2;
-
-    if (use_graph) {
-        // ---- one graph: round 1 WHILE { build; WHILE { trial } } -> outliers -> round 2 WHILE { ... } -> report
-        // (graph construction is serialised across solver instances: concurrent capture-to-graph + instantiate of conditional
-        // graphs from several threads crashed inside the driver on 580.159; execution of the instantiated graphs is concurrent)
-        std::unique_lock<std::mutex> build_lock(g_graph_build_mutex);
-        cudaGraph_t g = nullptr;
-        B200_CUDA(cudaGraphCreate(&g, 0));
-        struct GraphGuard {
-            cudaGraph_t g;
-            std::unique_lock<std::mutex>* lk;
-            cudaGraphExec_t ex = nullptr;
-            ~GraphGuard() {  // (runs before build_lock's destructor; graph teardown is serialised like construction)
-                if (!lk->owns_lock()) lk->lock();
-                if (ex) cudaGraphExecDestroy(ex);
-                if (g) cudaGraphDestroy(g);
-                lk->unlock();
-            }
-        } guard{g, &build_lock};
-        cudaGraphConditionalHandle ho[2], hi[2];
-        for (int r = 0; r < 2; ++r) {
-            B200_CUDA(cudaGraphConditionalHandleCreate(&ho[r], g, 0, cudaGraphCondAssignDefault));
-            B200_CUDA(cudaGraphConditionalHandleCreate(&hi[r], g, 0, cudaGraphCondAssignDefault));
-        }
-        // a WHILE node appended to the graph that `st` is currently capturing into; returns its (empty) body graph
-        auto add_while = [&](cudaGraph_t parent, cudaGraphConditionalHandle hnd, cudaGraph_t* body) -> int {
-            cudaStreamCaptureStatus cs;
-            const cudaGraphNode_t* deps = nullptr;
-            size_t n_deps = 0;
-            cudaGraph_t cap = nullptr;
-            B200_CUDA(cudaStreamGetCaptureInfo(st, &cs, nullptr, &cap, &deps, &n_deps));
-            cudaGraphNodeParams prm = {};
-            prm.type = cudaGraphNodeTypeConditional;
-            prm.conditional.handle = hnd;
-            prm.conditional.type = cudaGraphCondTypeWhile;
-            prm.conditional.size = 1;
-            cudaGraphNode_t node;
-            B200_CUDA(cudaGraphAddNode(&node, parent, deps, n_deps, &prm));
-            B200_CUDA(cudaStreamUpdateCaptureDependencies(st, &node, 1, cudaStreamSetCaptureDependencies));
-            *body = prm.conditional.phGraph_out[0];
-            return B200_OK;
-        };
-        cudaGraph_t outer_body[2] = {nullptr, nullptr}, inner_body[2] = {nullptr, nullptr}, ended = nullptr;
-        B200_CUDA(cudaStreamBeginCaptureToGraph(st, g, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-        for (int r = 0; r < 2; ++r) {
-            lm_round_begin_kernel<<<1, 1, 0, st>>>(ctl, iters[r], r, ho[r], 1);
-            if (r == 1 && E) outlier_kernel<<<eb, 128, 0, st>>>(v, dRt, dpts, dchi, 0, nullptr, ctl);  // :323-344 (skips itself after an abort)
-            if ((rc2 = add_while(g, ho[r], &outer_body[r]))) return rc2;
-            if ((rc2 = launch_round_tail(r))) return rc2;
-        }
-        if (E) outlier_kernel<<<eb, 128, 0, st>>>(v, dRt, dpts, dchi, 1, d + o_out, ctl);  // :354-375
-        lm_export_kernel<<<ceil_div(std::max(std::max(4 * K, 3 * L), 1), 256), 256, 0, st>>>(ctl, dq, dt, dpts, K, L, (double*)(d + o_qf), (double*)(d + o_tf),
-                                                                                         (double*)(d + o_pf));
-        B200_CUDA(cudaStreamEndCapture(st, &ended));
-        for (int r = 0; r < 2; ++r) {
-            B200_CUDA(cudaStreamBeginCaptureToGraph(st, outer_body[r], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-            if ((rc2 = launch_build(hi[r]))) return rc2;
-            if ((rc2 = add_while(outer_body[r], hi[r], &inner_body[r]))) return rc2;
-            B200_CUDA(cudaStreamEndCapture(st, &ended));
-            B200_CUDA(cudaStreamBeginCaptureToGraph(st, inner_body[r], nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal));
-            if ((rc2 = launch_trial(hi[r], ho[r]))) return rc2;
-            B200_CUDA(cudaStreamEndCapture(st, &ended));
-        }
-        B200_CUDA(cudaGraphInstantiate(&guard.ex, g, 0));
-        B200_CUDA(cudaGraphLaunch(guard.ex, st));
-        build_lock.unlock();
-        B200_CUDA(cudaMemcpyAsync(hc, ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
-        B200_CUDA(cudaEventRecord(S.ev1, st));
-        // the caller's flag may be raised by another thread while the graph runs (mapping_module.cc:124): mirror it into the
-        // device-visible word that the control kernels test between iterations
-        if (force_stop) {
-            while (cudaEventQuery(S.ev1) == cudaErrorNotReady) {
-                if (*force_stop) *S.h_abort = 1;
-                std::this_thread::sleep_for(std::chrono::microseconds(30));
+    for (int r = 0; r < 2; ++r) {
+        if (r == 1) {
+            // local_bundle_adjuster_g2o.cc:317-321 reads the caller's flag, which the gain stop of round 1 has set through
+            // terminate_action; the device takes the same decision from stop_flag / the mirrored word.  A round that does run starts
+            // with terminate_action's reset of that flag (terminate_action.cc:46-51).
+            if ((rc2 = fetch_ctl())) return rc2;
+            for (int x = 0; x < nw; ++x) {
+                volatile uint8_t* f = stops ? stops[act[x]] : nullptr;
+                if (!f) continue;
+                if (h_ctl[x].stop_flag || *f) {
+                    S.h_abort[x] = 1;
+                    *f = 1;
+                } else {
+                    S.h_abort[x] = 0;
+                }
             }
         }
-        B200_CUDA(S.wait(st));
-    } else {
-        // ---- host-stepped: the same kernels, one round trip per loop decision
-        auto fetch = [&]() -> int {
-            B200_CUDA(cudaMemcpyAsync(hc, ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
-            B200_CUDA(S.wait(st));
-            if (force_stop && *force_stop) *S.h_abort = 1;
-            return B200_OK;
-        };
-        for (int r = 0; r < 2; ++r) {
-            lm_round_begin_kernel<<<1, 1, 0, st>>>(ctl, iters[r], r, cudaGraphConditionalHandle{}, 0);
-            if (r == 1 && E) outlier_kernel<<<eb, 128, 0, st>>>(v, dRt, dpts, dchi, 0, nullptr, ctl);
-            if ((rc2 = fetch())) return rc2;
-            while (hc->outer_go) {
-                if ((rc2 = launch_build(cudaGraphConditionalHandle{}))) return rc2;
-                do {
-                    if ((rc2 = launch_trial(cudaGraphConditionalHandle{}, cudaGraphConditionalHandle{}))) return rc2;
-                    if ((rc2 = fetch())) return rc2;
-                } while (hc->inner_go);
-            }
-            if ((rc2 = launch_round_tail(r))) return rc2;
+        lm_round_begin_kernel<<<ceil_div(nw, 64), 64, 0, st>>>(wins, nw, iters[r], r);
+        ++launches;
+        if (r == 1) {
+            outlier_kernel<<<dim3(ceil_div(maxE, 128), nw), 128, 0, st>>>(wins, 0);  // :323-344 (skips itself after an abort)
+            ++launches;
         }
-        if (E) outlier_kernel<<<eb, 128, 0, st>>>(v, dRt, dpts, dchi, 1, d + o_out, ctl);
-        lm_export_kernel<<<ceil_div(std::max(std::max(4 * K, 3 * L), 1), 256), 256, 0, st>>>(ctl, dq, dt, dpts, K, L, (double*)(d + o_qf), (double*)(d + o_tf),
-                                                                                         (double*)(d + o_pf));
-        B200_CUDA(cudaMemcpyAsync(hc, ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
-        B200_CUDA(cudaEventRecord(S.ev1, st));
-        B200_CUDA(S.wait(st));
+        // repetitions of {build; trial}, enqueued in chunks; the read-back of chunk k is awaited only after chunk k+1 is enqueued
+        if (iters[r] > 0) {
+            const int first = std::min(iters[r], 4), later = 2;
+            int b = 0;
+            for (int i = 0; i < first; ++i)
+                if ((rc2 = launch_rep())) return rc2;
+            if ((rc2 = fetch_issue(b))) return rc2;
+            for (;;) {
+                for (int i = 0; i < later; ++i)
+                    if ((rc2 = launch_rep())) return rc2;
+                if ((rc2 = fetch_issue(b ^ 1))) return rc2;
+                if ((rc2 = fetch_wait(b))) return rc2;
+                bool any = false;
+                for (int x = 0; x < nw; ++x) any = any || h_ctl[x].outer_go;
+                b ^= 1;
+                if (!any) break;
+            }
+            if ((rc2 = fetch_wait(b))) return rc2;  // (the chunk enqueued last ran empty; its read-back is the final state)
+        }
+        landmark_kernel<kRoundEnd><<<dim3(max_lbc, nw), kLmThreads, 0, st>>>(wins);  // chi2 of every active edge at the final state
+        lm_round_end_kernel<<<nw, 256, 0, st>>>(wins, r);
+        launches += 2;
     }
+    outlier_kernel<<<dim3(ceil_div(maxE, 128), nw), 128, 0, st>>>(wins, 1);  // :354-375
+    lm_export_kernel<<<dim3(ceil_div(std::max(std::max(4 * maxK, 3 * maxL), 1), 256), nw), 256, 0, st>>>(wins);
+    launches += 2;
     B200_CUDA(cudaGetLastError());
-    if (getenv("B200_LBA_DEBUG")) {
-        double cyc[6];
-        B200_CUDA(cudaMemcpy(cyc, r_result, sizeof(cyc), cudaMemcpyDeviceToHost));
-        fprintf(stderr, "[lba] last chol_solve cycles: diag %.0f panel %.0f trailing %.0f backward %.0f (n = %d)\n", cyc[2], cyc[3], cyc[4], cyc[5], n);
-    }
-    launches = hc->launches + 3;
-    if (stats) {
-        stats->lambda_init = hc->lambda_init;
-        for (int r = 0; r < 2; ++r) {
-            stats->iterations[r] = hc->iters_done[r];
-            stats->chi2[r] = hc->chi2[r];
-            stats->lambda_final[r] = hc->lambda_final[r];
-        }
-    }
-    // terminate_action's gain-threshold stop writes the caller's flag (terminate_action.cc:66-70); an externally raised flag stays up
-    if (force_stop && hc->stop_flag) *force_stop = 1;
-    // results (exported from whichever buffer ended up current)
-    std::vector<unsigned char> out_sorted(std::max(E, 1));
-    std::vector<double> qf(4 * (size_t)std::max(K, 1)), tf(3 * (size_t)std::max(K, 1));
-    if (E) B200_CUDA(cudaMemcpyAsync(out_sorted.data(), d + o_out, E, cudaMemcpyDeviceToHost, st));
-    if (K) {
-        B200_CUDA(cudaMemcpyAsync(qf.data(), d + o_qf, sizeof(double) * 4 * K, cudaMemcpyDeviceToHost, st));
-        B200_CUDA(cudaMemcpyAsync(tf.data(), d + o_tf, sizeof(double) * 3 * K, cudaMemcpyDeviceToHost, st));
-    }
-    if (L) B200_CUDA(cudaMemcpyAsync(points_out, d + o_pf, sizeof(double) * 3 * (size_t)L, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(S.wait(st));
+    if ((rc = mark(7))) return rc;
+    B200_CUDA(cudaEventRecord(S.ev1, st));
+    B200_CUDA(cudaMemcpyAsync(h_export, d + export_begin, export_bytes, cudaMemcpyDeviceToHost, st));
+    std::vector<int> h_bad(nw, 0);
+    if ((rc2 = fetch_ctl())) return rc2;
+    for (int x = 0; x < nw; ++x) B200_CUDA(cudaMemcpyAsync(&h_bad[x], d + wo[x].bad, sizeof(int), cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
     B200_CUDA(cudaEventElapsedTime(&S.last_ms, S.ev0, S.ev1));
     S.last_launches = launches;
-    int n_out = 0;
-    for (int s = 0; s < E; ++s) {
-        if (outlier_out) outlier_out[order[s]] = out_sorted[s];
-        n_out += out_sorted[s];
+    for (int k2 = 0; k2 < 8; ++k2) {
+        S.prof_ms[k2] = 0.f;
+        S.prof_n[k2] = 0;
     }
-    if (stats) stats->n_outliers = n_out;
-    for (int k = 0; k < K; ++k) {  // util::converter::to_eigen_mat (util/converter.cc:23-25)
-        double* M = pose_out + 16 * (size_t)k;
-        if (P->pose_fixed[k]) {
-            std::memcpy(M, P->pose_cw + 16 * (size_t)k, sizeof(double) * 16);
+    for (size_t m = 1; m < S.prof_kind.size(); ++m) {
+        float ms = 0.f;
+        B200_CUDA(cudaEventElapsedTime(&ms, S.prof_ev[m - 1], S.prof_ev[m]));
+        const int kd = S.prof_kind[m];
+        if (kd >= 0 && kd < 8) {
+            S.prof_ms[kd] += ms;
+            S.prof_n[kd] += 1;
+        }
+    }
+    if (debug) fprintf(stderr, "[lba] batch of %d windows: %.3f ms wall, %.3f ms on the stream, %d launches\n", nw, ms_since(t_begin), S.last_ms, launches);
+    // ---- results ----------------------------------------------------------------------------------------------------------------
+    for (int x = 0; x < nw; ++x) {
+        const int w = act[x];
+        const HostWin& h = hw[x];
+        const b200_lba_problem_t& P = Ps[w];
+        const WinOff& o = wo[x];
+        if (h_bad[x]) {
+            set_error("b200_lba_solve: edge %d of window %d references an invalid vertex/camera", h_bad[x] - 1, w);
+            status[w] = B200_ERR_INVALID;
+            ret = B200_ERR_INVALID;
             continue;
         }
-        double R[9];
-        quat_to_rot(&qf[4 * k], R);
-        M[0] = R[0]; M[1] = R[1]; M[2] = R[2]; M[3] = tf[3 * k];
-        M[4] = R[3]; M[5] = R[4]; M[6] = R[5]; M[7] = tf[3 * k + 1];
-        M[8] = R[6]; M[9] = R[7]; M[10] = R[8]; M[11] = tf[3 * k + 2];
-        M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
+        const LmCtl& c = h_ctl[x];
+        if (stats) {
+            stats[w].lambda_init = c.lambda_init;
+            for (int r = 0; r < 2; ++r) {
+                stats[w].iterations[r] = c.iters_done[r];
+                stats[w].chi2[r] = c.chi2[r];
+                stats[w].lambda_final[r] = c.lambda_final[r];
+            }
+        }
+        // terminate_action's gain-threshold stop writes the caller's flag (terminate_action.cc:66-70); an externally raised flag stays up
+        if (stops && stops[w] && c.stop_flag) *stops[w] = 1;
+        const unsigned char* ex = h_export + (o.qf - export_begin);
+        const double* qf = reinterpret_cast<const double*>(ex);
+        const double* tf = reinterpret_cast<const double*>(h_export + (o.tf - export_begin));
+        const double* pf = reinterpret_cast<const double*>(h_export + (o.pf - export_begin));
+        const unsigned char* out = h_export + (o.out - export_begin);
+        int n_out = 0;
+        for (int e = 0; e < h.E; ++e) n_out += out[e];
+        if (outlier_outs && outlier_outs[w] && h.E) std::memcpy(outlier_outs[w], out, h.E);
+        if (stats) stats[w].n_outliers = n_out;
+        if (h.L) std::memcpy(points_outs[w], pf, sizeof(double) * 3 * (size_t)h.L);
+        for (int k = 0; k < h.K; ++k) {  // util::converter::to_eigen_mat (util/converter.cc:23-25)
+            double* M = pose_outs[w] + 16 * (size_t)k;
+            if (P.pose_fixed[k]) {
+                std::memcpy(M, P.pose_cw + 16 * (size_t)k, sizeof(double) * 16);
+                continue;
+            }
+            double R[9];
+            quat_to_rot(&qf[4 * k], R);
+            M[0] = R[0]; M[1] = R[1]; M[2] = R[2]; M[3] = tf[3 * k];
+            M[4] = R[3]; M[5] = R[4]; M[6] = R[5]; M[7] = tf[3 * k + 1];
+            M[8] = R[6]; M[9] = R[7]; M[10] = R[8]; M[11] = tf[3 * k + 2];
+            M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
+        }
     }
-    return B200_OK;
+    return ret;
 }
 
 }  // namespace lba
@@ -1881,6 +2396,16 @@ static int solve(Solver& S, const b200_lba_problem_t* P, int iters1, int iters2,
 struct b200_lba_s {
     b200::lba::Solver s;
 };
+
+static int lba_check_problem(const b200_lba_problem_t* P, const char* who) {
+    if (P->n_poses < 0 || P->n_points < 0 || P->n_edges < 0 || P->n_cams < 0 || (P->n_poses > 0 && (!P->pose_cw || !P->pose_fixed))
+        || (P->n_points > 0 && !P->points)
+        || (P->n_edges > 0 && (!P->e_pose || !P->e_point || !P->e_cam || !P->e_obs || !P->e_inv_sigma_sq || !P->e_delta || !P->cams))) {
+        b200::set_error("%s: inconsistent problem description", who);
+        return B200_ERR_INVALID;
+    }
+    return B200_OK;
+}
 
 extern "C" {
 
@@ -1891,11 +2416,9 @@ int b200_lba_create(int device, b200_lba_t* out) {
     b200_lba_s* h = new (std::nothrow) b200_lba_s();
     if (!h) return B200_ERR_INVALID;
     h->s.device = device;
-    // Local BA is the mapping thread's work (mapping_module.cc:63): tracking must not wait for it.  Its ~130 small launches per
-    // window are latency-bound (each one leaves most SMs idle), so on the highest stream priority every one of them pre-empts the wide
-    // front-end grids for its whole duration (measured: FAST 2.0 -> 2.9 ms per 64 frames with four windows in flight); on the lowest
-    // priority its CTAs fill the gaps instead (lowest == the default priority 0 of ordinary streams on this GPU; the range is [0, -5]).
-    // B200_LBA_PRIORITY=high|normal|low overrides.
+    // Local BA is the mapping thread's work (mapping_module.cc:63): tracking must not wait for it, so its stream has the LOWEST
+    // priority (its CTAs fill the gaps the front end leaves; lowest == the default priority 0 of ordinary streams on this GPU, the
+    // range is [0, -5]).  B200_LBA_PRIORITY=high|normal|low overrides.
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     int prio = prio_lo;
@@ -1904,19 +2427,25 @@ int b200_lba_create(int device, b200_lba_t* out) {
     if (e == cudaSuccess) e = cudaEventCreate(&h->s.ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&h->s.ev1);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->s.ev_sync, cudaEventBlockingSync | cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->s.h_ctl, sizeof(b200::lba::LmCtl), cudaHostAllocDefault);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&h->s.h_abort, sizeof(int), cudaHostAllocMapped);
-    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&h->s.d_abort, h->s.h_abort, 0);
-    // The conditional-graph driver is opt-in (B200_LBA_GRAPH=1): it is parity-green and slightly faster for one window at a time
-    // (4.55 vs 4.94 ms GPU time), but four or more instances executing such graphs concurrently crashed inside driver 580.159
-    // (tools/lba_conc.py), and concurrent windows are the normal case here.
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->s.ev_ctl[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->s.ev_ctl[1], cudaEventDisableTiming);
     if (const char* cc = getenv("B200_LBA_CLUSTER")) {
         const int c = atoi(cc);
-        if (c == 1 || c == 2 || c == 4 || c == 8) h->s.chol_cluster = c;
+        if (c == 1 || c == 2 || c == 4 || c == 8) {
+            h->s.chol_cluster = c;
+            h->s.chol_cluster_pinned = true;
+        }
+    }
+    if (const char* sm = getenv("B200_LBA_SCHUR_MODE")) h->s.schur_rows = sm[0] == 'r';
+    if (const char* sc = getenv("B200_LBA_SCHUR")) {
+        int u = 4, w2 = 4, c2 = 160;
+        if (sscanf(sc, "%d,%d,%d", &u, &w2, &c2) >= 1) {
+            h->s.schur_unroll = (u == 2) ? 2 : 4;
+            h->s.schur_warps = std::max(1, std::min(4, w2));
+            h->s.schur_ctas = std::max(1, c2);
+        }
     }
     if (const char* w = getenv("B200_LBA_WAIT")) h->s.wait_mode = w[0] == 'b' ? 1 : (w[0] == 'y' ? 2 : (w[0] == 'n' ? 3 : 0));  // spin | block | yield | nap
-    const char* gm = getenv("B200_LBA_GRAPH");
-    h->s.host_loop = !(gm && gm[0] == '1');
     if (e != cudaSuccess) {
         delete h;
         return b200::cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
@@ -1932,35 +2461,55 @@ int b200_lba_destroy(b200_lba_t h) {
     cudaFree(h->s.d_arena);
     if (h->s.h_stage) cudaFreeHost(h->s.h_stage);
     if (h->s.h_res) cudaFreeHost(h->s.h_res);
-    if (h->s.h_ctl) cudaFreeHost(h->s.h_ctl);
     if (h->s.h_abort) cudaFreeHost(h->s.h_abort);
     if (h->s.ev0) cudaEventDestroy(h->s.ev0);
     if (h->s.ev1) cudaEventDestroy(h->s.ev1);
     if (h->s.ev_sync) cudaEventDestroy(h->s.ev_sync);
+    for (cudaEvent_t e : h->s.prof_ev) cudaEventDestroy(e);
+    if (h->s.ev_ctl[0]) cudaEventDestroy(h->s.ev_ctl[0]);
+    if (h->s.ev_ctl[1]) cudaEventDestroy(h->s.ev_ctl[1]);
     if (h->s.stream) cudaStreamDestroy(h->s.stream);
     delete h;
     return B200_OK;
 }
 
+int b200_lba_solve_batch(b200_lba_t h, int n_windows, const b200_lba_problem_t* problems, int iters1, int iters2,
+                         volatile uint8_t* const* force_stop, double* const* pose_cw_out, double* const* points_out, uint8_t* const* outlier_out,
+                         b200_lba_stats_t* stats, int32_t* status) {
+    if (!h || n_windows < 0 || iters1 < 0 || iters2 < 0) return B200_ERR_INVALID;
+    if (n_windows == 0) return B200_OK;
+    if (!problems || !pose_cw_out || !points_out || !status) {
+        b200::set_error("b200_lba_solve_batch: null argument");
+        return B200_ERR_INVALID;
+    }
+    for (int w = 0; w < n_windows; ++w) {
+        if ((problems[w].n_poses > 0 && !pose_cw_out[w]) || (problems[w].n_points > 0 && !points_out[w])) {
+            b200::set_error("b200_lba_solve_batch: window %d has no output buffers", w);
+            return B200_ERR_INVALID;
+        }
+        const int rc = lba_check_problem(&problems[w], "b200_lba_solve_batch");
+        if (rc) return rc;
+    }
+    B200_CUDA(cudaSetDevice(h->s.device));
+    return b200::lba::solve_batch(h->s, n_windows, problems, iters1, iters2, force_stop, pose_cw_out, points_out, outlier_out, stats, status);
+}
+
 int b200_lba_solve(b200_lba_t h, const b200_lba_problem_t* P, int iters1, int iters2, volatile uint8_t* force_stop, double* pose_cw_out,
                    double* points_out, uint8_t* outlier_out, b200_lba_stats_t* stats) {
-    if (!h || !P || !pose_cw_out || !points_out) {
+    if (!h || !P || !pose_cw_out || !points_out || iters1 < 0 || iters2 < 0) {
         b200::set_error("b200_lba_solve: null argument");
         return B200_ERR_INVALID;
     }
-    if (P->n_poses < 0 || P->n_points < 0 || P->n_edges < 0 || P->n_cams < 0 || iters1 < 0 || iters2 < 0
-        || (P->n_poses > 0 && (!P->pose_cw || !P->pose_fixed)) || (P->n_points > 0 && !P->points)
-        || (P->n_edges > 0 && (!P->e_pose || !P->e_point || !P->e_cam || !P->e_obs || !P->e_inv_sigma_sq || !P->e_delta || !P->cams))) {
-        b200::set_error("b200_lba_solve: inconsistent problem description");
-        return B200_ERR_INVALID;
-    }
-    if (6 * (size_t)P->n_poses > 1000) {
-        b200::set_error("b200_lba_solve: more than 166 keyframes in one local window is not supported");
-        return B200_ERR_INVALID;
-    }
-    if (force_stop && *force_stop) return B200_ERR_ABORTED;  // local_bundle_adjuster_g2o.cc:308-310
+    int rc = lba_check_problem(P, "b200_lba_solve");
+    if (rc) return rc;
     B200_CUDA(cudaSetDevice(h->s.device));
-    return b200::lba::solve(h->s, P, iters1, iters2, force_stop, pose_cw_out, points_out, outlier_out, stats);
+    int32_t status = B200_OK;
+    volatile uint8_t* stops[1] = {force_stop};
+    double* poses[1] = {pose_cw_out};
+    double* pts[1] = {points_out};
+    uint8_t* outl[1] = {outlier_out};
+    rc = b200::lba::solve_batch(h->s, 1, P, iters1, iters2, stops, poses, pts, outl, stats, &status);
+    return rc ? rc : status;
 }
 
 int b200_pose_optimize(b200_lba_t h, int n_problems, const b200_lba_problem_t* problems, int num_trials_robust, int num_trials, int num_each_iter,
@@ -2044,6 +2593,19 @@ int b200_pose_optimize(b200_lba_t h, int n_problems, const b200_lba_problem_t* p
     S.last_launches = 1;
     for (int p = 0; p < n_problems; ++p)  // fewer than five observations: the reference returns before touching the pose (:116-118)
         if (problems[p].n_edges < 5) std::memcpy(pose_cw_out + 16 * (size_t)p, problems[p].pose_cw, sizeof(double) * 16);
+    return B200_OK;
+}
+
+int b200_lba_enable_profile(b200_lba_t h, int enable) {
+    if (!h) return B200_ERR_INVALID;
+    h->s.profile = enable != 0;
+    return B200_OK;
+}
+
+int b200_lba_kernel_ms(b200_lba_t h, int kernel, float* total_ms, int* launches) {
+    if (!h || kernel < 0 || kernel >= 8) return B200_ERR_INVALID;
+    if (total_ms) *total_ms = h->s.prof_ms[kernel];
+    if (launches) *launches = h->s.prof_n[kernel];
     return B200_OK;
 }
 

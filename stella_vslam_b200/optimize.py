@@ -36,6 +36,7 @@ def _bind():
     L.b200_lba_create.argtypes = [C.c_int, C.POINTER(vp)]
     L.b200_lba_destroy.argtypes = [vp]
     L.b200_lba_solve.argtypes = [vp, C.POINTER(LbaProblem), C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(LbaStats)]
+    L.b200_lba_solve_batch.argtypes = [vp, C.c_int, C.POINTER(LbaProblem), C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(LbaStats), vp]
     L.b200_lba_last_profile.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.b200_pose_optimize.argtypes = [vp, C.c_int, C.POINTER(LbaProblem), C.c_int, C.c_int, C.c_int, vp, vp, vp]
     return L
@@ -99,6 +100,52 @@ class local_bundle_adjuster:
         launches = C.c_int()
         self._L.b200_lba_last_profile(self._h, None, C.byref(launches))
         return launches.value
+
+    def prepare_batch(self, problems):
+        """Pack several windows once (ctypes structs, pointer tables, output buffers) for repeated optimize_prepared_batch() calls."""
+        packed = [pack_problem(pr) for pr in problems]
+        n = len(packed)
+        arr = (LbaProblem * n)(*[pk[0] for pk in packed])
+        pose = [np.zeros((pk[0].n_poses, 4, 4)) for pk in packed]
+        pts = [np.zeros((pk[0].n_points, 3)) for pk in packed]
+        outl = [np.zeros(max(pk[0].n_edges, 1), np.uint8) for pk in packed]
+        tab = lambda arrs: (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        return dict(n=n, arr=arr, keep=packed, pose=pose, pts=pts, outl=outl, pose_tab=tab(pose), pts_tab=tab(pts), outl_tab=tab(outl),
+                    st=(LbaStats * n)(), status=np.zeros(n, np.int32))
+
+    def optimize_prepared_batch(self, prep, force_stop_flags=None):
+        """b200_lba_solve_batch on a prepared batch.  force_stop_flags: optional list of 1-element uint8 arrays / None per window.
+        Returns the number of kernel launches the whole batch took; per-window status in prep["status"]."""
+        flags = None
+        if force_stop_flags is not None:
+            flags = (C.c_void_p * prep["n"])(*[(f.ctypes.data if f is not None else None) for f in force_stop_flags])
+        rc = self._L.b200_lba_solve_batch(self._h, prep["n"], prep["arr"], self.num_first_iter_, self.num_second_iter_, flags, prep["pose_tab"],
+                                          prep["pts_tab"], prep["outl_tab"], prep["st"], ptr(prep["status"]))
+        check(rc)
+        launches = C.c_int()
+        self._L.b200_lba_last_profile(self._h, None, C.byref(launches))
+        return launches.value
+
+    def optimize_batch(self, problems, force_stop_flags=None):
+        """Several independent windows in one launch sequence (b200_lba_solve_batch).  Returns one result per window: a dict like
+        optimize(), or None for a window whose flag was already set (local_bundle_adjuster_g2o.cc:308-310)."""
+        if not problems:
+            return []
+        prep = self.prepare_batch(problems)
+        launches = self.optimize_prepared_batch(prep, force_stop_flags)
+        ms = C.c_float()
+        self._L.b200_lba_last_profile(self._h, C.byref(ms), None)
+        out = []
+        for w in range(prep["n"]):
+            if prep["status"][w] == ERR_ABORTED:
+                out.append(None)
+                continue
+            st = prep["st"][w]
+            E = prep["arr"][w].n_edges
+            out.append(dict(pose_cw=prep["pose"][w], points=prep["pts"][w], outliers=prep["outl"][w][:E], iterations=list(st.iterations),
+                            n_outliers=st.n_outliers, chi2=list(st.chi2), lambda_init=st.lambda_init, lambda_final=list(st.lambda_final),
+                            gpu_ms=ms.value, launches=launches))
+        return out
 
     def optimize(self, problem, force_stop_flag=None):
         """problem: flattened window (dict).  force_stop_flag: optional 1-element uint8 array (read AND written, like the

@@ -112,3 +112,98 @@ def test_factory():
     with pytest.raises(RuntimeError):
         optimize.create({"backend": "gtsam"})                       # local_bundle_adjuster_factory.h:26,30
     assert optimize.create({"backend": "b200", "num_first_iter": 3}).num_first_iter_ == 3
+
+
+# ---- b200_lba_solve_batch: many windows per launch sequence --------------------------------------------------------------------
+
+def test_batch_vs_oracle_and_single(mods):
+    """Windows of different size / model / iteration count advance in lockstep; every one must equal the oracle, and (same code path,
+    deterministic reductions) the batch-of-one result bit for bit."""
+    O, optimize, synth = mods
+    specs = [("stereo", 12, 3, 600, 11), ("mono", 8, 2, 300, 12), ("equirect", 10, 2, 400, 13), ("stereo", 4, 1, 60, 14),
+             ("mono", 30, 6, 3000, 15), ("stereo", 3, 3, 20, 16)]
+    prs = [synth.make_ba_problem(K, F, L, seed=s, model=m) for m, K, F, L, s in specs]
+    ba = optimize.local_bundle_adjuster()
+    got = ba.optimize_batch(prs)
+    assert len(got) == len(prs)
+    assert got[0]["launches"] < 200, got[0]["launches"]          # one launch sequence for all six windows
+    for i, (g, pr) in enumerate(zip(got, prs)):
+        ref = O.lba_solve(pr)
+        check_same(g, ref, pr, same_iterations=(i != 5))           # (window 5: every keyframe fixed, see test_degenerate_inputs)
+        one = ba.optimize(pr)
+        assert np.array_equal(one["pose_cw"], g["pose_cw"]) and np.array_equal(one["points"], g["points"])
+        assert np.array_equal(one["outliers"], g["outliers"]) and one["iterations"] == g["iterations"]
+    ba.close()
+
+
+def test_batch_of_identical_full_size_windows(mods):
+    # 8 x BASELINE config 4 in one launch sequence: same result for every copy, launch count independent of the batch size
+    O, optimize, synth = mods
+    pr = synth.make_ba_problem(50, 10, 10000, seed=0, model="stereo")
+    ba = optimize.local_bundle_adjuster()
+    one = ba.optimize(pr)
+    got = ba.optimize_batch([pr] * 8)
+    for g in got:
+        assert np.array_equal(g["pose_cw"], one["pose_cw"]) and np.array_equal(g["points"], one["points"])
+        assert np.array_equal(g["outliers"], one["outliers"]) and g["iterations"] == one["iterations"]
+    assert got[0]["launches"] <= one["launches"] + 24
+    check_same(got[3], O.lba_solve(pr), pr)
+
+
+def test_no_flag_runs_second_round_after_gain_stop(mods):
+    # ADVICE r1: with force_stop == NULL the gain stop of round 1 lands in g2o's auxiliary flag, which optimize() resets:
+    # round 2 must run (local_bundle_adjuster_g2o.cc:317-321 only tests the CALLER's flag)
+    O, optimize, synth = mods
+    pr = synth.make_ba_problem(8, 3, 200, seed=2, model="mono")
+    ba = optimize.local_bundle_adjuster(50, 10)
+    got = ba.optimize(pr)
+    ref = O.lba_solve(pr, iters1=50, iters2=10)
+    assert ref["iterations"][0] < 50 and ref["iterations"][1] > 0     # round 1 ended on the gain threshold, round 2 ran
+    check_same(got, ref, pr)
+    pr = synth.make_ba_problem(20, 5, 1500, seed=21, model="stereo")
+    got = ba.optimize(pr)
+    check_same(got, O.lba_solve(pr, iters1=50, iters2=10), pr)
+
+
+def test_many_fixed_keyframes(mods):
+    # ADVICE r1: only FREE keyframes enter the reduced system; windows with well over 166 keyframes in total must be solved
+    O, optimize, synth = mods
+    pr = synth.make_ba_problem(200, 180, 1500, seed=31, model="stereo")
+    ba = optimize.local_bundle_adjuster()
+    check_same(ba.optimize(pr), O.lba_solve(pr), pr)
+    big = synth.make_ba_problem(170, 0, 200, seed=32, model="mono")     # 170 free keyframes: documented limit
+    with pytest.raises(RuntimeError):
+        ba.optimize(big)
+
+
+def test_batch_force_stop_flags_and_bad_edges(mods):
+    O, optimize, synth = mods
+    prs = [synth.make_ba_problem(8, 3, 200, seed=2, model="mono"), synth.make_ba_problem(6, 2, 100, seed=3, model="stereo"),
+           synth.make_ba_problem(8, 3, 200, seed=2, model="mono")]
+    ba = optimize.local_bundle_adjuster(50, 10)
+    flags = [np.array([0], np.uint8), np.array([1], np.uint8), None]
+    got = ba.optimize_batch(prs, flags)
+    assert got[1] is None and flags[1][0] == 1                         # set on entry: that window is not touched (:308-310)
+    rflag = np.array([0], np.uint8)
+    ref0 = O.lba_solve(prs[0], iters1=50, iters2=10, force_stop=rflag)
+    assert flags[0][0] == rflag[0] == 1 and got[0]["iterations"] == ref0["iterations"] and got[0]["iterations"][1] == 0
+    check_same(got[0], ref0, prs[0])
+    check_same(got[2], O.lba_solve(prs[2], iters1=50, iters2=10), prs[2])   # same window without a flag: second round runs
+    bad = dict(prs[1])
+    bad["e_point"] = prs[1]["e_point"].copy()
+    bad["e_point"][7] = 10 ** 6
+    with pytest.raises(RuntimeError):
+        ba.optimize(bad)
+    check_same(ba.optimize_batch([prs[1]])[0], O.lba_solve(prs[1], iters1=50, iters2=10), prs[1])  # the handle is still usable
+
+
+def test_unsorted_edge_order(mods):
+    # the ABI accepts the observations in any order; the device plan sorts them by landmark and reports outliers in the caller's order
+    O, optimize, synth = mods
+    pr = synth.make_ba_problem(12, 3, 600, seed=41, model="stereo")
+    perm = np.random.default_rng(5).permutation(len(pr["e_pose"]))
+    pr2 = dict(pr)
+    for k in ("e_pose", "e_point", "e_cam", "e_obs", "e_inv_sigma_sq", "e_delta"):
+        pr2[k] = np.ascontiguousarray(pr[k][perm])
+    ba = optimize.local_bundle_adjuster()
+    check_same(ba.optimize(pr2), O.lba_solve(pr2), pr2)
