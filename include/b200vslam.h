@@ -228,6 +228,11 @@ typedef struct b200_guided_problem {
     const float* q_x_right;           /* reprojected x_right; read only when t_x_right != NULL */
     const float* q_angle;             /* last-frame keypoint angle; read only in mode 1 with check_orientation */
     const uint8_t* q_valid;           /* NULL = all valid */
+    const uint8_t* q_has_observation; /* modes 0 / 1: landmark::has_observation() of the query landmark; NULL = all have.  A keypoint that
+                                         receives a landmark WITHOUT observations (a temporal landmark of a stereo / RGBD last frame) stays
+                                         open to later landmarks, exactly like the reference's test `lm && lm->has_observation()`
+                                         (projection.cc:50-53, 163-166); match_out then lists the keypoint for both and the adapter's
+                                         in-order add_landmark leaves the later one, as in the reference */
     const double* q_reproj;           /* mode 3 with do_reprojection_matching: n_queries x 2, the reprojection in double (fuse.cc:96-97) */
     const float* inv_level_sigma_sq;  /* mode 3: orb_params_->inv_level_sigma_sq_, n_levels entries */
     int32_t n_levels;

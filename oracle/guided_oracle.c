@@ -139,7 +139,9 @@ int orc_match_guided(const orc_guided_t* P, int mode, unsigned thr, float lowe_r
             owner[best_idx] = q;
             state[best_idx] = (uint16_t)best;
         } else if (mode != 2) {
-            state[best_idx] = 0; /* frm.add_landmark(...) / matched_lms.at(idx) = lm / already_matched_idx.insert(idx) */
+            /* frm.add_landmark(...) / matched_lms.at(idx) = lm / already_matched_idx.insert(idx).  The later test is
+             * `lm && lm->has_observation()` (projection.cc:50-53, 163-166): a landmark without observations does not close the keypoint */
+            if (!P->q_has_observation || P->q_has_observation[q]) state[best_idx] = 0;
         }
         match_out[q] = best_idx;
         ++n_matches;

@@ -89,6 +89,7 @@ typedef struct {
     const float* q_x_right;          /* reprojected x_right (used when t_x_right != NULL) */
     const float* q_angle;            /* mode 1 */
     const uint8_t* q_valid;          /* 0: skipped before the search (not reprojected / will_be_erased / outside the image); NULL = all */
+    const uint8_t* q_has_observation; /* modes 0 / 1: landmark::has_observation(); NULL = all (projection.cc:50-53, 163-166) */
     const double* q_reproj;          /* mode 3: Q x 2 reprojection in double (fuse.cc:96-97) */
     const float* inv_level_sigma_sq; /* mode 3: orb_params_->inv_level_sigma_sq_ */
     int32_t do_reprojection_matching; /* mode 3 */

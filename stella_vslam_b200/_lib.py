@@ -46,13 +46,14 @@ class GuidedProblem(C.Structure):
                 ("grid_cols", C.c_int32), ("grid_rows", C.c_int32), ("n_queries", C.c_int32),
                 ("q_desc", C.c_void_p), ("q_x", C.c_void_p), ("q_y", C.c_void_p), ("q_margin", C.c_void_p), ("q_min_level", C.c_void_p),
                 ("q_max_level", C.c_void_p), ("q_x_right", C.c_void_p), ("q_angle", C.c_void_p), ("q_valid", C.c_void_p),
-                ("q_reproj", C.c_void_p), ("inv_level_sigma_sq", C.c_void_p), ("n_levels", C.c_int32), ("do_reprojection_matching", C.c_int32),
+                ("q_has_observation", C.c_void_p), ("q_reproj", C.c_void_p), ("inv_level_sigma_sq", C.c_void_p), ("n_levels", C.c_int32), ("do_reprojection_matching", C.c_int32),
                 ("match_out", C.c_void_p), ("n_matches", C.c_int32)]
 
 
 GUIDED_FIELDS = (("t_x", "f4"), ("t_y", "f4"), ("t_octave", "u1"), ("t_angle", "f4"), ("t_x_right", "f4"), ("t_desc", "u1"), ("t_occupied", "u1"),
                  ("q_desc", "u1"), ("q_x", "f4"), ("q_y", "f4"), ("q_margin", "f4"), ("q_min_level", "i1"), ("q_max_level", "i1"),
-                 ("q_x_right", "f4"), ("q_angle", "f4"), ("q_valid", "u1"), ("q_reproj", "f8"), ("inv_level_sigma_sq", "f4"))
+                 ("q_x_right", "f4"), ("q_angle", "f4"), ("q_valid", "u1"), ("q_has_observation", "u1"), ("q_reproj", "f8"),
+                 ("inv_level_sigma_sq", "f4"))
 
 
 def pack_guided_problem(prob, StructT=None):

@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(128) guided_candidates_kernel(const GuidedDev*
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= g.n_queries) return;
     int len = 0;
-    if (!g.q_valid || g.q_valid[q]) {
+    if (!g.q_valid || (g.q_valid[q] & 1)) {
         const double inv_w = (double)g.grid_cols / (double)__fsub_rn(g.max_x, g.min_x), inv_h = (double)g.grid_rows / (double)__fsub_rn(g.max_y, g.min_y);
         const float ref_x = g.q_x[q], ref_y = g.q_y[q], margin = g.q_margin[q];
         const int min_level = g.q_min_level[q], max_level = g.q_max_level[q];
@@ -580,7 +580,9 @@ __global__ void __launch_bounds__(32) guided_resolve_kernel(const Dev* __restric
                     owner[acc] = q;
                     state[acc] = (unsigned short)best;
                 } else if (mode != 2) {
-                    state[acc] = 0;
+                    // projection.cc:50-53, 163-166: a keypoint is closed to later landmarks only while the landmark it carries
+                    // has_observation(); a temporal landmark (no observation yet) can be overwritten by a later one
+                    if (!g.q_valid || (g.q_valid[q] & 2)) state[acc] = 0;
                 }
             }
             total += __popc(__ballot_sync(0xFFFFFFFFu, do_commit)) - __popc(__ballot_sync(0xFFFFFFFFu, stolen));
@@ -620,6 +622,7 @@ struct PairsDev {
     uint2* lists;
     int* list_len;
     unsigned char* occupied;  // always null: every candidate starts free
+    const unsigned char* q_valid;  // always null (interface of the shared resolve kernel)
     int *match_out, *n_matches, *owner;
 };
 
@@ -1343,7 +1346,9 @@ int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* p
         put(L.qhi, P.q_max_level, nq);
         put(L.qxr, P.q_x_right, 4 * nq);
         put(L.qang, P.q_angle, 4 * nq);
-        put(L.qval, P.q_valid, nq);
+        if (P.q_valid || P.q_has_observation)  // bit 0: valid, bit 1: has_observation()
+            for (int q = 0; q < nq; ++q)
+                hb[L.qval + q] = (unsigned char)(((!P.q_valid || P.q_valid[q]) ? 1 : 0) | ((!P.q_has_observation || P.q_has_observation[q]) ? 2 : 0));
         const bool reproj = mode == B200_GUIDED_FUSE && P.do_reprojection_matching;
         if (reproj) {
             put(L.qrep, P.q_reproj, 16 * nq);
@@ -1373,7 +1378,7 @@ int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* p
         g.q_angle = (const float*)(db + L.qang);
         g.q_min_level = (const signed char*)(db + L.qlo);
         g.q_max_level = (const signed char*)(db + L.qhi);
-        g.q_valid = P.q_valid ? db + L.qval : nullptr;
+        g.q_valid = (P.q_valid || P.q_has_observation) ? db + L.qval : nullptr;
         g.q_reproj = (const double*)(db + L.qrep);
         g.inv_level_sigma_sq = (const float*)(db + L.sig);
         g.do_reproj = reproj ? 1 : 0;

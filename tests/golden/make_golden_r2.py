@@ -99,6 +99,13 @@ def main():
         knn = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(d2, d1, k=2)     # query = keyframe side (robust.cc outer loop), train = frame side
         best = np.array([[m[0].trainIdx, m[0].distance, m[1].trainIdx, m[1].distance] for m in knn], np.int32)
         out[f"d1_{ci}"], out[f"d2_{ci}"], out[f"knn_{ci}"] = d1, d2, best
+        if ci == 0:   # the full distance matrix from OpenCV's own Hamming kernel (rows = keyframe side, columns = frame side)
+            full = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(d2, d1, k=n1)
+            D = np.zeros((n2, n1), np.int16)
+            for q, ms in enumerate(full):
+                for m in ms:
+                    D[q, m.trainIdx] = int(m.distance)
+            out["dist_0"] = D
     np.savez_compressed(os.path.join(HERE, "match_bf_cv2.npz"), **out)
 
 

@@ -105,7 +105,9 @@ def literal_guided(pr, mode, thr=100, lowe=0.8, check_orientation=True):
             owner[best_idx] = q
             dist_state[best_idx] = best
         elif mode != 2:
-            occ[best_idx] = 1
+            # `lm && lm->has_observation()` (projection.cc:50-53, 163-166): a landmark without observations does not close the keypoint
+            if pr.get("q_has_observation") is None or pr["q_has_observation"][q]:
+                occ[best_idx] = 1
         out[q] = best_idx
     return out, occ
 
@@ -183,3 +185,20 @@ def test_library_cross_check_matches_oracle_without_gpu():
     got, n = match.cross_check(a, b)
     want, n_want = O.cross_check(a, b)
     assert np.array_equal(got, want) and n == n_want
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_landmarks_without_observations_do_not_close_keypoints(mode):
+    """projection.cc:50-53 / 163-166: the occupancy test is `lm && lm->has_observation()`.  Temporal landmarks (stereo / RGBD last
+    frame, no observation yet) leave the keypoint they were attached to open: a later landmark may take the same keypoint."""
+    pr = synth.make_guided_problem(91 + mode, n_train=1500, n_queries=2500, mode=mode, stereo=bool(mode))
+    rng = np.random.default_rng(7)
+    pr["q_has_observation"] = (rng.random(len(pr["q_x"])) > 0.5).astype(np.uint8)
+    got, occ, n = O.match_guided(pr, mode, lowe_ratio=0.8, check_orientation=True)
+    want, want_occ = literal_guided(pr, mode, lowe=0.8, check_orientation=True)
+    assert np.array_equal(got, want) and np.array_equal(occ.astype(bool), want_occ.astype(bool))
+    hit = got[got >= 0]
+    assert len(hit) > len(np.unique(hit)) > 100          # some keypoints were taken more than once ...
+    all_obs = dict(pr, q_has_observation=None)
+    base, _, _ = O.match_guided(all_obs, mode, lowe_ratio=0.8, check_orientation=True)
+    assert len(base[base >= 0]) == len(np.unique(base[base >= 0])) and not np.array_equal(base, got)   # ... which never happens otherwise

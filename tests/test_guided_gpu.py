@@ -173,3 +173,15 @@ def test_fuse_and_area_named_methods():
     assert np.array_equal(got, want) and n == n_want and n > 20
     hit = want >= 0
     assert np.array_equal(new_prev[hit, 0], f2["t_x"][want[hit]]) and np.array_equal(new_prev[~hit], prev[~hit])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_guided_landmarks_without_observations(mode):
+    # projection.cc:50-53, 163-166 (`lm && lm->has_observation()`): keypoints given to temporal landmarks stay open
+    probs = []
+    for k in range(3):
+        pr = synth.make_guided_problem(95 + 2 * k + mode, n_train=1800, n_queries=2600, mode=mode, stereo=bool(k & 1))
+        pr["q_has_observation"] = (np.random.default_rng(k).random(len(pr["q_x"])) > 0.4).astype(np.uint8)
+        probs.append(pr)
+    n = _check(probs, mode)
+    assert n > 300
