@@ -45,7 +45,6 @@ struct LevelGeom {
     int ncols;                    // FAST cell columns (for the scan-order key)
     float size;                   // (float)(unsigned)(31 * sf)  orb_extractor.cc:274
     int tab_x, tab_y;             // offsets into the resize tables (level l is resampled from level l-1)
-    int blur_tile_base, blur_tiles_x;
 };
 
 struct Geom {
@@ -57,10 +56,6 @@ struct Geom {
 
 struct CellDesc {                 // one FAST cell (orb_extractor.cc:199-217)
     unsigned short level, i, j, min_x, min_y, w, h, pad;
-};
-
-struct BlurTile {
-    unsigned short level, tx, ty, pad;
 };
 
 struct RawKp {                    // keypoint before orientation/description
@@ -606,87 +601,6 @@ __device__ __forceinline__ void blur_h4(unsigned w0, unsigned w1, unsigned w2, u
     h[3] = __dp4a(w1, TA, __dp4a(w2, TB, 0u));
 }
 
-__global__ void __launch_bounds__(256) blur_kernel(const __grid_constant__ Geom g, Images im, const BlurTile* __restrict__ tiles,
-                                                   unsigned char* __restrict__ blurred, unsigned long long blur_fstride) {
-    __shared__ __align__(16) unsigned in[kBlurInH * (kBlurInW / 4)];          // 38 x 18 words
-    __shared__ __align__(16) unsigned hp[(kBlurInH / 2) * kBlurTW];           // 19 pair-rows x 64 columns: (H[2r][c], H[2r+1][c]) as u16x2
-    __shared__ __align__(16) unsigned char outb[kBlurTH * kBlurTW];
-    const BlurTile bt = tiles[blockIdx.x];
-    const int frame = blockIdx.y, level = bt.level;
-    const LevelGeom& L = g.lv[level];
-    int pitch;
-    const unsigned char* src = level_ptr(im, g, level, frame, &pitch);
-    const int x0 = bt.tx * kBlurTW, y0 = bt.ty * kBlurTH;
-    const int tid = threadIdx.x;
-    // ---- input tile: aligned 32-bit loads for interior tiles, per-byte REFLECT_101 for tiles touching the border
-    const bool interior = x0 >= 4 && x0 + kBlurTW + 4 <= L.w && y0 >= 3 && y0 + kBlurTH + 3 <= L.h && ((pitch & 3) == 0)
-                          && ((reinterpret_cast<unsigned long long>(src) & 3ull) == 0);
-    if (interior) {
-        for (int idx = tid; idx < kBlurInH * (kBlurInW / 4); idx += 256) {
-            const int r = idx / (kBlurInW / 4), q = idx - r * (kBlurInW / 4);
-            in[idx] = *reinterpret_cast<const unsigned*>(src + (size_t)(y0 - 3 + r) * pitch + x0 - 4 + 4 * q);
-        }
-    } else {
-        for (int idx = tid; idx < kBlurInH * (kBlurInW / 4); idx += 256) {
-            const int r = idx / (kBlurInW / 4), q = idx - r * (kBlurInW / 4);
-            const int sy = reflect101(y0 - 3 + r, L.h);
-            unsigned v = 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) v |= (unsigned)src[(size_t)sy * pitch + reflect101(x0 - 4 + 4 * q + b, L.w)] << (8 * b);
-            in[idx] = v;
-        }
-    }
-    __syncthreads();
-    // ---- horizontal pass (exact: sum <= 65280), two rows x four columns per item, stored as vertical u16 pairs
-    for (int idx = tid; idx < (kBlurInH / 2) * (kBlurTW / 4); idx += 256) {
-        const int pr = idx / (kBlurTW / 4), q = idx - pr * (kBlurTW / 4);
-        const unsigned* r0 = in + (2 * pr) * (kBlurInW / 4) + q;
-        const unsigned* r1 = r0 + (kBlurInW / 4);
-        unsigned h0[4], h1[4];
-        blur_h4(r0[0], r0[1], r0[2], h0);
-        blur_h4(r1[0], r1[1], r1[2], h1);
-        uint4 o;
-        o.x = h0[0] | (h1[0] << 16);
-        o.y = h0[1] | (h1[1] << 16);
-        o.z = h0[2] | (h1[2] << 16);
-        o.w = h0[3] | (h1[3] << 16);
-        *reinterpret_cast<uint4*>(hp + pr * kBlurTW + 4 * q) = o;
-    }
-    __syncthreads();
-    // ---- vertical pass: Q16.16 accumulate with dp2a on the vertical pairs, round to nearest, saturate
-    {
-        // even output row y (tile rows y..y+6 = pairs y/2 .. y/2+3): taps (18,34)(48,56)(48,34)(18,0)
-        // odd  output row y (tile rows y-1..y+6, tap 0 first):        taps (0,18)(34,48)(56,48)(34,18)
-        constexpr unsigned E01 = 18u | (34u << 8) | (48u << 16) | (56u << 24), E23 = 48u | (34u << 8) | (18u << 16);
-        constexpr unsigned O01 = (18u << 8) | (34u << 16) | (48u << 24), O23 = 56u | (48u << 8) | (34u << 16) | (18u << 24);
-        const int c = tid & 63, rb = tid >> 6;  // column, block of 8 output rows
-        unsigned p[7];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) p[k] = hp[(4 * rb + k) * kBlurTW + c];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            unsigned e = __dp2a_lo(p[i], E01, 0u);
-            e = __dp2a_hi(p[i + 1], E01, e);
-            e = __dp2a_lo(p[i + 2], E23, e);
-            e = __dp2a_hi(p[i + 3], E23, e);
-            unsigned o = __dp2a_lo(p[i], O01, 0u);
-            o = __dp2a_hi(p[i + 1], O01, o);
-            o = __dp2a_lo(p[i + 2], O23, o);
-            o = __dp2a_hi(p[i + 3], O23, o);
-            outb[(8 * rb + 2 * i) * kBlurTW + c] = (unsigned char)min((e + 32768u) >> 16, 255u);
-            outb[(8 * rb + 2 * i + 1) * kBlurTW + c] = (unsigned char)min((o + 32768u) >> 16, 255u);
-        }
-    }
-    __syncthreads();
-    unsigned char* dst = blurred + (size_t)frame * blur_fstride + L.offset;
-    for (int idx = tid; idx < kBlurTH * kBlurTW / 4; idx += 256) {
-        const int r = idx / (kBlurTW / 4), c4 = (idx - r * (kBlurTW / 4)) * 4;
-        const int y = y0 + r;
-        if (y >= L.h || x0 + c4 >= L.pitch) continue;
-        *reinterpret_cast<unsigned*>(dst + (size_t)y * L.pitch + x0 + c4) = *reinterpret_cast<const unsigned*>(outb + r * kBlurTW + c4);
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // K5: IC-angle orientation on the un-blurred level + rBRIEF on the blurred level + scale correction.
 //     One warp per keypoint; lane u-15 sums column u of the disc, lane i produces descriptor byte i.
@@ -740,39 +654,175 @@ __device__ __forceinline__ float util_sin(float v) {
 }
 
 constexpr int kUploadChunk = 16;        // frames per upload/compute chunk of the host-buffer path
-constexpr int kDescWarps = 8;           // warps per block
-constexpr int kDescBlocksPerFrame = 64;  // blockIdx.x range; each warp strides over its frame's keypoints
+// K4+K5 fused: descriptor blur + IC-angle orientation + rBRIEF + scale correction, one warp per keypoint.
+//   The reference blurs the WHOLE level (cv::GaussianBlur 7x7 sigma 2 REFLECT_101, orb_extractor.cc:103) and then samples 512 points
+//   within radius 18.4 of every keypoint.  Both passes of the fixed-point Gaussian are integer (Q8.8 taps, one rounding at the very
+//   end), so the blurred value of a pixel depends only on its 7x7 neighbourhood: blurring just the 37x37 window a keypoint can sample
+//   gives the same bytes.  Per keypoint the warp
+//     1. receives the un-blurred 43 x 43 neighbourhood as ONE cp.async.bulk.tensor box (64 x 43 bytes, origin on a 16-byte boundary;
+//        out-of-image bytes arrive as zeros and the <= 2 rows / columns beyond the border are then filled in by REFLECT_101), while it
+//        still works on the previous keypoint (two tile buffers and two mbarriers per warp);
+//     2. runs the horizontal pass (dp4a, exact 16-bit sums stored as vertical pairs) and the vertical pass (dp2a, Q16.16, rounded) in its
+//        private shared memory -- the arithmetic of the former whole-level kernel, on 1 369 instead of 6.4 M pixels per frame;
+//     3. takes the intensity-centroid angle from the same un-blurred tile and the 256 rBRIEF comparisons from the blurred window.
+//   This removes the blurred pyramid (2 x 6.4 MB per frame of HBM traffic) and the sector-granular global gathers of the descriptor.
+constexpr int kDescWarps = 8;             // warps per block
+constexpr int kDescBlocksPerFrame = 37;   // blockIdx.x range (x batch = a multiple of the SM count for 64 frames); warps stride over keypoints
+constexpr int kFdR = 18;                  // largest |row| / |column| offset an rBRIEF sample can have (pattern radius 18.38)
+constexpr int kFdWin = 2 * kFdR + 1;      // 37: blurred window
+constexpr int kFdIn = kFdWin + 6;         // 43: un-blurred rows / columns it depends on
+constexpr int kFdTileW = 64;              // bytes per tile row = width of the TMA box
+constexpr int kFdTileBytes = 2816;        // 44 rows x 64 (43 used), a multiple of 128
+constexpr int kFdHpW = 40;                // columns of the horizontal / vertical pass (37 used)
+constexpr int kFdHpRows = 22;             // pair-rows of the horizontal pass (rows 0..43)
+struct FdWarp {
+    unsigned char tile[2][kFdTileBytes];
+    unsigned hp[kFdHpRows * kFdHpW];
+    unsigned char blur[kFdHpW * kFdHpW];
+    unsigned long long bar[2];
+    unsigned char pad[112];
+};
+static_assert(sizeof(FdWarp) % 128 == 0, "per-warp block keeps the TMA destinations 128-byte aligned");
 
-__global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_constant__ Geom g, Images im,
-                                                                   const unsigned char* __restrict__ blurred, unsigned long long blur_fstride,
+template <bool kUseTma>
+__global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_constant__ Geom g, const __grid_constant__ TmapSet tmaps, Images im,
                                                                    const RawKp* __restrict__ raw, int raw_stride, const int* __restrict__ counts,
                                                                    b200_keypoint_t* __restrict__ kps, unsigned char* __restrict__ descs,
-                                                                   int out_stride) {
+                                                                   int out_stride, int frame0) {
+    extern __shared__ __align__(128) unsigned char fd_smem[];
     const int frame = blockIdx.y;
     const int lane = threadIdx.x & 31;
+    FdWarp& S = reinterpret_cast<FdWarp*>(fd_smem)[threadIdx.x >> 5];
     const int warp = blockIdx.x * kDescWarps + (threadIdx.x >> 5);
     const int n = counts[frame];
+    constexpr int kStride = kDescBlocksPerFrame * kDescWarps;
     // this lane's 8 bit tests (x0,y0,x1,y1 as 4 int8 per word): a lane-varying constant-memory index would serialise
     // every access 32 ways, so the words are fetched once and kept in registers
     unsigned pat[8];
 #pragma unroll
     for (int b = 0; b < 8; ++b) pat[b] = reinterpret_cast<const unsigned*>(c_pattern)[lane * 8 + b];
-    for (int k = warp; k < n; k += kDescBlocksPerFrame * kDescWarps) {
-        const RawKp rk = raw[(size_t)frame * raw_stride + k];
+    if (kUseTma) {
+        if (lane == 0) {
+            mbar_init(&S.bar[0], 1);
+            mbar_init(&S.bar[1], 1);
+        }
+        __syncwarp();
+    }
+    const RawKp* __restrict__ rawf = raw + (size_t)frame * raw_stride;
+    // tile column of window column 0: the box starts at the 16-byte boundary at or below x - 22, so that the horizontal pass may read
+    // one byte to the left of the window (the dp4a grouping of blur_h4 is anchored one byte early)
+    auto issue = [&](int buf, const RawKp rk) {
+        if (lane == 0) {
+            mbar_expect_tx(&S.bar[buf], kFdTileW * kFdIn);
+            tma_load_3d(S.tile[buf], &tmaps.m[rk.level], ((int)rk.x - 22) & ~15, (int)rk.y - 21, frame + (rk.level ? frame0 : 0), &S.bar[buf]);
+        }
+    };
+    RawKp rk_next{};
+    if (warp < n) {
+        rk_next = rawf[warp];
+        if (kUseTma) issue(0, rk_next);
+    }
+    int it = 0;
+    for (int k = warp; k < n; k += kStride, ++it) {
+        const RawKp rk = rk_next;
+        const int cur = it & 1;
+        if (k + kStride < n) {
+            rk_next = rawf[k + kStride];
+            if (kUseTma) issue(cur ^ 1, rk_next);  // (the buffer was released by the __syncwarp that ended the previous iteration)
+        }
         const int level = rk.level;
         const LevelGeom& L = g.lv[level];
-        int pitch;
-        const unsigned char* img = level_ptr(im, g, level, frame, &pitch);
-        const unsigned char* c = img + (size_t)rk.y * pitch + rk.x;
-        // ---- ic_angle (orb_impl.cc:68-91): m10 = sum u*I, m01 = sum v*I over the radius-15 disc
+        const int kx = rk.x, ky = rk.y;
+        const int x_start = kUseTma ? ((kx - 22) & ~15) : kx - 22;
+        const int ox = kx - 21 - x_start;  // tile column of input column 0 (1..16)
+        unsigned char* __restrict__ tile = S.tile[cur];
+        if (kUseTma) {
+            mbar_wait(&S.bar[cur], (unsigned)(it >> 1) & 1u);
+            // REFLECT_101 for the (at most two) rows / columns of the neighbourhood that lie outside the level
+            if (ky - 21 < 0 || ky + 21 >= L.h || kx - 21 < 0 || kx + 21 >= L.w) {
+                for (int tr = 0; tr < kFdIn; ++tr) {
+                    const int iy = ky - 21 + tr;
+                    if (iy >= 0 && iy < L.h) continue;
+                    const int sr = reflect101(iy, L.h) - (ky - 21);
+                    if (lane < 16) reinterpret_cast<unsigned*>(tile + tr * kFdTileW)[lane] = reinterpret_cast<const unsigned*>(tile + sr * kFdTileW)[lane];
+                }
+                __syncwarp();
+                for (int tc = ox; tc < ox + kFdIn; ++tc) {
+                    const int ix = x_start + tc;
+                    if (ix >= 0 && ix < L.w) continue;
+                    const int sc = reflect101(ix, L.w) - x_start;
+                    for (int tr = lane; tr < kFdIn; tr += 32) tile[tr * kFdTileW + tc] = tile[tr * kFdTileW + sc];
+                }
+                __syncwarp();
+            }
+        } else {
+            int pitch;
+            const unsigned char* img = level_ptr(im, g, level, frame, &pitch);
+            for (int idx = lane; idx < kFdIn * kFdIn; idx += 32) {
+                const int tr = idx / kFdIn, j = idx - tr * kFdIn;
+                tile[tr * kFdTileW + ox + j] = img[(size_t)reflect101(ky - 21 + tr, L.h) * pitch + reflect101(kx - 21 + j, L.w)];
+            }
+            __syncwarp();
+        }
+        // ---- horizontal pass (exact: sum <= 65280): item = (pair-row, group of four columns), stored as vertical u16 pairs
+        {
+            const int bb0 = ox - 1, sh = (bb0 & 3) * 8, w0i = bb0 >> 2;
+            for (int idx = lane; idx < kFdHpRows * (kFdHpW / 4); idx += 32) {
+                const int pr = idx / (kFdHpW / 4), q = idx - pr * (kFdHpW / 4);
+                const unsigned* r0 = reinterpret_cast<const unsigned*>(tile + (2 * pr) * kFdTileW) + w0i + q;
+                const unsigned* r1 = r0 + kFdTileW / 4;
+                unsigned h0[4], h1[4];
+                {
+                    const unsigned a0 = r0[0], a1 = r0[1], a2 = r0[2], a3 = r0[3];
+                    blur_h4(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh), h0);
+                }
+                {
+                    const unsigned a0 = r1[0], a1 = r1[1], a2 = r1[2], a3 = r1[3];
+                    blur_h4(__funnelshift_r(a0, a1, sh), __funnelshift_r(a1, a2, sh), __funnelshift_r(a2, a3, sh), h1);
+                }
+                uint4 o;
+                o.x = h0[0] | (h1[0] << 16);
+                o.y = h0[1] | (h1[1] << 16);
+                o.z = h0[2] | (h1[2] << 16);
+                o.w = h0[3] | (h1[3] << 16);
+                *reinterpret_cast<uint4*>(S.hp + pr * kFdHpW + 4 * q) = o;
+            }
+        }
+        __syncwarp();
+        // ---- vertical pass: Q16.16 accumulate with dp2a on the vertical pairs, round to nearest, saturate.  item = (column, 8 rows)
+        {
+            constexpr unsigned E01 = 18u | (34u << 8) | (48u << 16) | (56u << 24), E23 = 48u | (34u << 8) | (18u << 16);
+            constexpr unsigned O01 = (18u << 8) | (34u << 16) | (48u << 24), O23 = 56u | (48u << 8) | (34u << 16) | (18u << 24);
+            for (int idx = lane; idx < kFdHpW * 5; idx += 32) {
+                const int rb = idx / kFdHpW, c = idx - rb * kFdHpW;
+                unsigned p[7];
+#pragma unroll
+                for (int t = 0; t < 7; ++t) p[t] = (4 * rb + t < kFdHpRows) ? S.hp[(4 * rb + t) * kFdHpW + c] : 0u;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    unsigned e = __dp2a_lo(p[i], E01, 0u);
+                    e = __dp2a_hi(p[i + 1], E01, e);
+                    e = __dp2a_lo(p[i + 2], E23, e);
+                    e = __dp2a_hi(p[i + 3], E23, e);
+                    unsigned o = __dp2a_lo(p[i], O01, 0u);
+                    o = __dp2a_hi(p[i + 1], O01, o);
+                    o = __dp2a_lo(p[i + 2], O23, o);
+                    o = __dp2a_hi(p[i + 3], O23, o);
+                    S.blur[(8 * rb + 2 * i) * kFdHpW + c] = (unsigned char)min((e + 32768u) >> 16, 255u);
+                    S.blur[(8 * rb + 2 * i + 1) * kFdHpW + c] = (unsigned char)min((o + 32768u) >> 16, 255u);
+                }
+            }
+        }
+        // ---- ic_angle (orb_impl.cc:68-91) on the un-blurred tile: m10 = sum u*I, m01 = sum v*I over the radius-15 disc
         int m10 = 0, m01 = 0;
         if (lane < 31) {
             const int u = lane - 15, au = abs(u);
+            const unsigned char* c = tile + 21 * kFdTileW + ox + 21 + u;
             int col = 0;
 #pragma unroll
             for (int v = -15; v <= 15; ++v) {
                 if (au <= c_umax[v < 0 ? -v : v]) {
-                    const int val = c[v * pitch + u];
+                    const int val = c[v * kFdTileW];
                     col += val;
                     m01 += v * val;
                 }
@@ -780,32 +830,35 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
             m10 = u * col;
         }
 #pragma unroll
-        for (int s = 16; s > 0; s >>= 1) {
-            m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, s);
-            m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, s);
+        for (int s2 = 16; s2 > 0; s2 >>= 1) {
+            m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, s2);
+            m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, s2);
         }
         const float angle = fast_atan2_deg((float)m01, (float)m10);
-        // ---- compute_orb_descriptor (orb_impl.cc:93-154) on the blurred level
+        __syncwarp();  // the blurred window is complete
+        // ---- compute_orb_descriptor (orb_impl.cc:93-154) on the blurred window
         const float arad = (float)((double)angle * 3.14159265358979323846 / 180.0);
         const float ca = util_cos(arad), sa = util_sin(arad);
-        const unsigned char* bc = blurred + (size_t)frame * blur_fstride + L.offset + (size_t)rk.y * L.pitch + rk.x;
-        const int bp = L.pitch;
+        const unsigned char* bc = S.blur + kFdR * kFdHpW + kFdR;
         unsigned val = 0;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
             const float x0 = (float)(int)(signed char)(pat[b] & 0xFF), y0 = (float)(int)(signed char)((pat[b] >> 8) & 0xFF);
             const float x1 = (float)(int)(signed char)((pat[b] >> 16) & 0xFF), y1 = (float)(int)(signed char)(pat[b] >> 24);
-            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
-            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
-            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
-            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
-            val |= (unsigned)(bc[r0 * bp + c0] < bc[r1 * bp + c1]) << b;
+            int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, sa), __fmul_rn(y0, ca)));
+            int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sa)));
+            int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, sa), __fmul_rn(y1, ca)));
+            int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sa)));
+            // (|offset| <= 18 by construction: pattern radius 18.38, |cos|, |sin| <= 1; the clamp only guards the shared-memory access)
+            r0 = max(-kFdR, min(kFdR, r0)); c0 = max(-kFdR, min(kFdR, c0));
+            r1 = max(-kFdR, min(kFdR, r1)); c1 = max(-kFdR, min(kFdR, c1));
+            val |= (unsigned)(bc[r0 * kFdHpW + c0] < bc[r1 * kFdHpW + c1]) << b;
         }
         const size_t o = (size_t)frame * out_stride + k;
         descs[o * 32 + lane] = (unsigned char)val;
         if (lane == 0) {
             b200_keypoint_t kp;
-            float x = (float)rk.x, y = (float)rk.y;
+            float x = (float)kx, y = (float)ky;
             if (level > 0) {  // correct_keypoint_scale (orb_extractor.cc:337-345)
                 x = __fmul_rn(x, L.sf);
                 y = __fmul_rn(y, L.sf);
@@ -818,6 +871,7 @@ __global__ void __launch_bounds__(kDescWarps * 32) describe_kernel(const __grid_
             kp.octave = level;
             kps[o] = kp;
         }
+        __syncwarp();  // every lane is done with tile[cur], hp and blur before they are reused
     }
 }
 
@@ -852,13 +906,14 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // 3-D u8 tensor map (x, y, frame) with a 96 x 72 x 1 box; false if the buffer does not meet TMA's alignment rules
 // (16-byte aligned base and strides; the kernel additionally keeps the box origin x on a 16-byte boundary)
-static bool make_level_tmap(CUtensorMap* out, const void* base, int w, int h, size_t pitch, size_t fstride, int frames) {
+static bool make_level_tmap(CUtensorMap* out, const void* base, int w, int h, size_t pitch, size_t fstride, int frames, int box_w = kRawPitch,
+                            int box_h = kTileRows) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
     if ((reinterpret_cast<unsigned long long>(base) & 15ull) || (pitch & 15) || (frames > 1 && (fstride & 15)) || w < 1 || h < 1) return false;
     const cuuint64_t dims[3] = {(cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)std::max(frames, 1)};
     const cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)(frames > 1 ? fstride : pitch * (size_t)h + ((16 - (pitch * (size_t)h) % 16) % 16))};
-    const cuuint32_t box[3] = {(cuuint32_t)kRawPitch, (cuuint32_t)kTileRows, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE)
@@ -885,12 +940,11 @@ struct Extractor {
     int width = 0, height = 0, batch_cap = 0;
     Geom geom{};
     std::vector<float> sf;
-    int n_cells = 0, n_blur_tiles = 0, raw_stride = 0;
+    int n_cells = 0, raw_stride = 0;
     size_t pyr_fstride = 0, img0_pitch = 0, img0_fstride = 0;
     // device arenas
-    unsigned char *d_img0 = nullptr, *d_pyr = nullptr, *d_blur = nullptr, *d_rect_mask = nullptr, *d_user_mask = nullptr;
+    unsigned char *d_img0 = nullptr, *d_pyr = nullptr, *d_rect_mask = nullptr, *d_user_mask = nullptr;
     CellDesc* d_cells = nullptr;
-    BlurTile* d_tiles = nullptr;
     ResizeTap* d_taps = nullptr;
     unsigned long long* d_grid = nullptr;
     RawKp* d_raw = nullptr;
@@ -903,6 +957,7 @@ struct Extractor {
     size_t last_pitch0 = 0, last_fstride0 = 0;
     bool rect_mask_ready = false;
     TmapSet tmaps{};           // levels >= 1 are encoded once per configuration, level 0 per call (caller's pointer)
+    TmapSet tmaps_desc{};      // the same levels with the 64 x 43 box of the descriptor kernel
     bool tmaps_ok = false, last_used_tma = false;
     int tmap_frames = 0;
     // caller-owned result buffers (b200_orb_bind_outputs); when null the instance's own arenas are used
@@ -916,12 +971,12 @@ struct Extractor {
     int res_stride() const { return out_kps ? out_stride : raw_stride; }
 
     void free_arenas() {
-        cudaFree(d_img0); cudaFree(d_pyr); cudaFree(d_blur); cudaFree(d_rect_mask); cudaFree(d_user_mask);
-        cudaFree(d_cells); cudaFree(d_tiles); cudaFree(d_taps); cudaFree(d_grid); cudaFree(d_raw);
+        cudaFree(d_img0); cudaFree(d_pyr); cudaFree(d_rect_mask); cudaFree(d_user_mask);
+        cudaFree(d_cells); cudaFree(d_taps); cudaFree(d_grid); cudaFree(d_raw);
         cudaFree(d_counts); cudaFree(d_level_counts); cudaFree(d_kps); cudaFree(d_descs);
         if (h_counts) cudaFreeHost(h_counts);
-        d_img0 = d_pyr = d_blur = d_rect_mask = d_user_mask = nullptr;
-        d_cells = nullptr; d_tiles = nullptr; d_taps = nullptr; d_grid = nullptr; d_raw = nullptr;
+        d_img0 = d_pyr = d_rect_mask = d_user_mask = nullptr;
+        d_cells = nullptr; d_taps = nullptr; d_grid = nullptr; d_raw = nullptr;
         d_counts = d_level_counts = nullptr; d_kps = nullptr; d_descs = nullptr; h_counts = nullptr;
         rect_mask_ready = false;
     }
@@ -986,7 +1041,6 @@ struct Extractor {
         const int nl = geom.num_levels;
         // FAST cells in the reference's scan order (orb_extractor.cc:199-217)
         std::vector<CellDesc> cells;
-        std::vector<BlurTile> tiles;
         std::vector<ResizeTap> taps;
         for (int l = 0; l < nl; ++l) {
             LevelGeom& L = geom.lv[l];
@@ -1009,10 +1063,6 @@ struct Extractor {
                     }
                 }
             }
-            L.blur_tile_base = (int)tiles.size();
-            L.blur_tiles_x = ceil_div(L.w, kBlurTW);
-            for (int ty = 0; ty < ceil_div(L.h, kBlurTH); ++ty)
-                for (int tx = 0; tx < L.blur_tiles_x; ++tx) tiles.push_back(BlurTile{(unsigned short)l, (unsigned short)tx, (unsigned short)ty, 0});
             // resize taps l-1 -> l (OpenCV resize.cpp: fx clamped at the borders, rows clipped)
             if (l > 0) {
                 const LevelGeom& S = geom.lv[l - 1];
@@ -1041,7 +1091,6 @@ struct Extractor {
             return B200_ERR_INVALID;
         }
         n_cells = (int)cells.size();
-        n_blur_tiles = (int)tiles.size();
         raw_stride = std::max(1, geom.grid_cells);
         unsigned long long total = 0;
         for (int l = 0; l < nl; ++l) total = geom.lv[l].offset + round_up((unsigned long long)geom.lv[l].pitch * geom.lv[l].h, 256ull);
@@ -1051,10 +1100,8 @@ struct Extractor {
 
         B200_CUDA(cudaMalloc(&d_img0, img0_fstride * batch));
         B200_CUDA(cudaMalloc(&d_pyr, pyr_fstride * batch));
-        B200_CUDA(cudaMalloc(&d_blur, pyr_fstride * batch));
         B200_CUDA(cudaMalloc(&d_user_mask, img0_fstride));
         B200_CUDA(cudaMalloc(&d_cells, sizeof(CellDesc) * std::max(1, n_cells)));
-        B200_CUDA(cudaMalloc(&d_tiles, sizeof(BlurTile) * std::max(1, n_blur_tiles)));
         B200_CUDA(cudaMalloc(&d_taps, sizeof(ResizeTap) * std::max<size_t>(1, taps.size())));
         B200_CUDA(cudaMalloc(&d_grid, sizeof(unsigned long long) * (size_t)raw_stride * batch));
         B200_CUDA(cudaMalloc(&d_raw, sizeof(RawKp) * (size_t)raw_stride * batch));
@@ -1064,7 +1111,6 @@ struct Extractor {
         B200_CUDA(cudaMalloc(&d_descs, (size_t)32 * raw_stride * batch));
         B200_CUDA(cudaHostAlloc(&h_counts, sizeof(int) * (kMaxLevels + 1) * batch, cudaHostAllocDefault));
         if (n_cells) B200_CUDA(cudaMemcpyAsync(d_cells, cells.data(), sizeof(CellDesc) * n_cells, cudaMemcpyHostToDevice, stream));
-        if (n_blur_tiles) B200_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(BlurTile) * n_blur_tiles, cudaMemcpyHostToDevice, stream));
         if (!taps.empty()) B200_CUDA(cudaMemcpyAsync(d_taps, taps.data(), sizeof(ResizeTap) * taps.size(), cudaMemcpyHostToDevice, stream));
         // create_rectangle_mask (orb_extractor.cc:138-151): zero set of the filled rectangles
         if (!mask_rects.empty()) {
@@ -1084,7 +1130,9 @@ struct Extractor {
         tmaps_ok = true;
         tmap_frames = batch;
         for (int l = 1; l < nl && tmaps_ok; ++l)
-            tmaps_ok = make_level_tmap(&tmaps.m[l], d_pyr + geom.lv[l].offset, geom.lv[l].w, geom.lv[l].h, geom.lv[l].pitch, pyr_fstride, batch);
+            tmaps_ok = make_level_tmap(&tmaps.m[l], d_pyr + geom.lv[l].offset, geom.lv[l].w, geom.lv[l].h, geom.lv[l].pitch, pyr_fstride, batch)
+                       && make_level_tmap(&tmaps_desc.m[l], d_pyr + geom.lv[l].offset, geom.lv[l].w, geom.lv[l].h, geom.lv[l].pitch, pyr_fstride, batch,
+                                          kFdTileW, kFdIn);
         width = w;
         height = h;
         batch_cap = batch;
@@ -1114,7 +1162,6 @@ struct Extractor {
         const bool tm = timing && record;
         unsigned long long* grid = d_grid + (size_t)frame0 * geom.grid_cells;
         RawKp* raw = d_raw + (size_t)frame0 * raw_stride;
-        unsigned char* blur = d_blur + (size_t)frame0 * pyr_fstride;
         int* counts = res_counts() + frame0;
         if (tm) B200_CUDA(cudaEventRecord(ev[0], stream));
         for (int l = 1; l < nl; ++l) {
@@ -1134,11 +1181,23 @@ struct Extractor {
         if (tm) B200_CUDA(cudaEventRecord(ev[2], stream));
         select_kernel<<<dim3(nl, batch), 256, 0, stream>>>(geom, grid, raw, raw_stride, counts, d_level_counts + (size_t)frame0 * kMaxLevels);
         if (tm) B200_CUDA(cudaEventRecord(ev[3], stream));
-        blur_kernel<<<dim3(n_blur_tiles, batch), 256, 0, stream>>>(geom, im, d_tiles, blur, pyr_fstride);
-        if (tm) B200_CUDA(cudaEventRecord(ev[4], stream));
-        describe_kernel<<<dim3(kDescBlocksPerFrame, batch), kDescWarps * 32, 0, stream>>>(
-            geom, im, blur, pyr_fstride, raw, raw_stride, counts, res_kps() + (size_t)frame0 * res_stride(),
-            res_descs() + (size_t)frame0 * res_stride() * 32, res_stride());
+        if (tm) B200_CUDA(cudaEventRecord(ev[4], stream));  // (stage 3, the separate blur pass, no longer exists: the descriptor kernel blurs its own windows)
+        {
+            const size_t smem = sizeof(FdWarp) * kDescWarps;
+            const bool tma = tmaps_ok
+                             && make_level_tmap(&tmaps_desc.m[0], d_images, geom.lv[0].w, geom.lv[0].h, pitch, fstride, batch, kFdTileW, kFdIn);
+            b200_keypoint_t* okps = res_kps() + (size_t)frame0 * res_stride();
+            unsigned char* odesc = res_descs() + (size_t)frame0 * res_stride() * 32;
+            if (tma) {
+                B200_CUDA(cudaFuncSetAttribute(describe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                describe_kernel<true><<<dim3(kDescBlocksPerFrame, batch), kDescWarps * 32, smem, stream>>>(geom, tmaps_desc, im, raw, raw_stride, counts, okps,
+                                                                                                          odesc, res_stride(), frame0);
+            } else {
+                B200_CUDA(cudaFuncSetAttribute(describe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                describe_kernel<false><<<dim3(kDescBlocksPerFrame, batch), kDescWarps * 32, smem, stream>>>(geom, tmaps_desc, im, raw, raw_stride, counts, okps,
+                                                                                                           odesc, res_stride(), frame0);
+            }
+        }
         if (tm) B200_CUDA(cudaEventRecord(ev[5], stream));
         B200_CUDA(cudaGetLastError());
         last_batch = frame0 + batch;
