@@ -147,8 +147,12 @@ int b200_convert_to_grayscale(b200_orb_t h, const uint8_t* src, int width, int h
 int b200_convert_to_grayscale_device(b200_orb_t h, const void* d_src, int width, int height, size_t src_pitch, size_t src_frame_stride,
                                      int channels, int rgb_order, void* d_gray, size_t gray_pitch, size_t gray_frame_stride, int batch);
 
+/* Raw FAST corners (after NMS, threshold choice and mask tests, before distribute_keypoints) of the first n frames of the last extract:
+ * the candidate count of orb_extractor.cc:237-259, which prices the FAST and selection kernels.  Synchronises. */
+int b200_orb_raw_corner_counts(b200_orb_t h, int32_t* counts, int n);
 /* Per-stage kernel time of the last extract, in ms, measured with CUDA events on the instance stream.
- * stage: 0 pyramid, 1 FAST+NMS+grid arg-max, 2 ordered selection, 3 descriptor blur, 4 orientation+rBRIEF, 5 whole extract. */
+ * stage: 0 pyramid, 1 FAST+NMS+grid arg-max, 2 ordered selection, 3 (unused: the descriptor blur is fused into stage 4),
+ * 4 window blur + orientation + rBRIEF, 5 whole extract. */
 int b200_orb_stage_ms(b200_orb_t h, int stage, float* ms);
 int b200_orb_enable_timing(b200_orb_t h, int enable);
 
@@ -187,6 +191,14 @@ int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, const void* d
                                  size_t angle2_stride, const void* d_valid2, const void* d_off2, const void* d_cnt2, int max_n1,
                                  int max_n2, float lowe_ratio, int check_orientation, void* d_pairs, int pairs_stride,
                                  void* d_n_pairs);
+/* Optional: run the sequential resolve pass of b200_match_bruteforce_device on a side stream.  The pass is the reference's greedy loop
+ * (robust.cc:253-315) -- one warp per problem, ~0.5 ms for 64 pairs of 2000 keypoints with 147 of 148 SMs idle -- so when it is enabled
+ * the caller's NEXT kernels on the matcher's stream (e.g. the next batch's extraction) overlap it.  Contract while enabled: d_pairs /
+ * d_n_pairs of a call, and the freedom to overwrite that call's input buffers, are reached on the matcher's stream only after the next
+ * b200_match_bruteforce_device call on this handle, b200_matcher_join (stream-ordered: the stream waits, the host does not) or
+ * b200_matcher_sync.  Off by default. */
+int b200_matcher_set_async_resolve(b200_matcher_t h, int enable);
+int b200_matcher_join(b200_matcher_t h);
 /* Grid-guided projection matchers
  *   mode 0 (B200_GUIDED_LANDMARKS): match::projection::match_frame_and_landmarks     (src/stella_vslam/match/projection.cc:13-93)
  *   mode 1 (B200_GUIDED_LAST_FRAME): match::projection::match_current_and_last_frames (src/stella_vslam/match/projection.cc:95-207)
@@ -311,6 +323,10 @@ int b200_landmark_descriptors(b200_matcher_t h, int n_landmarks, const uint8_t* 
 int b200_landmark_geometry(b200_matcher_t h, int n_landmarks, const double* pos_w, const int32_t* offsets, const double* cam_centers,
                            const double* ref_center, const float* ref_scale_factor, float inv_scale_factor_last, double* mean_normal,
                            float* max_valid_dist, float* min_valid_dist);
+/* Device time (ms, CUDA events) of the two passes of the last b200_match_bruteforce[_device] call while timing is enabled:
+ * stage 0 = all-pairs distances + per-row top-K lists, stage 1 = sequential resolve.  Synchronises the streams involved. */
+int b200_matcher_enable_timing(b200_matcher_t h, int enable);
+int b200_matcher_stage_ms(b200_matcher_t h, int stage, float* ms);
 /* Run on the caller's stream (a cudaStream_t; NULL is the legacy default stream); use_own != 0 restores the own stream. */
 int b200_matcher_set_stream(b200_matcher_t h, void* stream, int use_own);
 int b200_matcher_sync(b200_matcher_t h);

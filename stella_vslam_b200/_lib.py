@@ -133,9 +133,9 @@ SYMBOLS = [
     "b200_last_error", "b200_device_count", "b200_version", "b200_host_alloc", "b200_host_free",
     "b200_orb_default_params", "b200_orb_create", "b200_orb_destroy", "b200_orb_max_keypoints", "b200_orb_extract",
     "b200_orb_extract_device", "b200_orb_set_stream", "b200_orb_bind_outputs", "b200_orb_reserve", "b200_orb_fetch", "b200_orb_device_results", "b200_orb_sync", "b200_orb_level_info",
-    "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_pyramid_level_view", "b200_convert_to_grayscale", "b200_convert_to_grayscale_device", "b200_keypoints_undistort", "b200_frame_can_observe", "b200_orb_stage_ms", "b200_orb_enable_timing",
+    "b200_orb_pyramid_level_device", "b200_orb_pyramid_level_host", "b200_orb_pyramid_level_view", "b200_convert_to_grayscale", "b200_convert_to_grayscale_device", "b200_keypoints_undistort", "b200_frame_can_observe", "b200_orb_stage_ms", "b200_orb_enable_timing", "b200_orb_raw_corner_counts",
     "b200_matcher_create", "b200_matcher_destroy", "b200_hamming_matrix", "b200_match_bruteforce",
-    "b200_match_bruteforce_device", "b200_match_guided", "b200_match_cross_check", "b200_match_pairs", "b200_stereo_compute", "b200_landmark_descriptors", "b200_landmark_geometry", "b200_matcher_set_stream", "b200_matcher_sync",
+    "b200_match_bruteforce_device", "b200_match_guided", "b200_match_cross_check", "b200_match_pairs", "b200_stereo_compute", "b200_landmark_descriptors", "b200_landmark_geometry", "b200_matcher_set_stream", "b200_matcher_sync", "b200_matcher_set_async_resolve", "b200_matcher_join", "b200_matcher_enable_timing", "b200_matcher_stage_ms",
     "b200_lba_create", "b200_lba_destroy", "b200_lba_solve", "b200_lba_solve_batch", "b200_pose_optimize", "b200_lba_last_profile", "b200_lba_enable_profile", "b200_lba_kernel_ms",
 ]
 

@@ -1004,6 +1004,20 @@ __global__ void __launch_bounds__(128) landmark_geometry_kernel(int n, const dou
 struct Matcher {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // b200_matcher_set_async_resolve: the sequential resolve pass (64 warps on the whole chip, ~0.5 ms per 64 pairs) runs on a side
+    // stream so that the caller's next kernels (the next batch's extraction) fill the idle SMs; joined by the next matcher call
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_topk = nullptr, ev_resolved = nullptr;
+    bool async_resolve = false, resolve_pending = false;
+    bool timing = false;
+    cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
+    int join() {  // the main stream waits for the side stream's resolve
+        if (resolve_pending) {
+            B200_CUDA(cudaStreamWaitEvent(stream, ev_resolved, 0));
+            resolve_pending = false;
+        }
+        return B200_OK;
+    }
     // scratch (grown on demand)
     unsigned* d_lists = nullptr;
     size_t lists_cap = 0;
@@ -1046,13 +1060,14 @@ struct Matcher {
     }
 
     int run(int n_problems, const Side& S1, const Side& S2, const void* valid2, int max_n1, int max_n2, float lowe, int check_ori,
-            void* pairs, int pairs_stride, void* n_pairs) {
+            void* pairs, int pairs_stride, void* n_pairs, bool device_call = false) {
         if (n_problems <= 0) return B200_OK;
         if (max_n1 >= (1 << 22)) {
             set_error("brute-force matcher supports < 4194304 keypoints per frame");
             return B200_ERR_INVALID;
         }
         int rc;
+        if ((rc = join())) return rc;  // (the previous resolve still reads the candidate lists this call overwrites)
         max_n1 = std::max(max_n1, 1);
         if (pairs_stride < max_n1) {
             set_error("pairs_stride %d is smaller than the largest frame (%d keypoints)", pairs_stride, max_n1);
@@ -1063,17 +1078,30 @@ struct Matcher {
         if ((rc = grow((void**)&d_lists, &lists_cap, sizeof(unsigned) * kTopK * (size_t)list_rows * n_problems))) return rc;
         if ((rc = grow((void**)&d_matched, &matched_cap, sizeof(int) * (size_t)max_n1 * n_problems))) return rc;
         if ((rc = grow((void**)&d_taken, &taken_cap, sizeof(unsigned) * (size_t)taken_words * n_problems))) return rc;
+        if (timing) B200_CUDA(cudaEventRecord(ev_t[0], stream));
         topk_kernel<<<dim3(row_blocks, n_problems), kRowsPerBlock, 0, stream>>>(S1, S2, (const unsigned char*)valid2, check_ori, d_lists);
+        if (timing) B200_CUDA(cudaEventRecord(ev_t[1], stream));
         const size_t state_bytes = sizeof(unsigned) * ((size_t)taken_words + 2 * (size_t)max_n1);  // taken bitmap, idx_1 -> idx_2 table, claim table
         const size_t stage_bytes = sizeof(unsigned) * 9 * (size_t)max_n1;
         const int use_smem = (state_bytes + stage_bytes <= 200 * 1024) ? 2 : (state_bytes <= 200 * 1024 ? 1 : 0);
         const size_t rs_bytes = use_smem == 2 ? state_bytes + stage_bytes : state_bytes;
         if (use_smem && rs_bytes > 48 * 1024)
             B200_CUDA(cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_bytes));
-        resolve_kernel<<<n_problems, 32, use_smem ? rs_bytes : 0, stream>>>(S1, S2, (const unsigned char*)valid2, d_lists, lowe, check_ori, d_matched,
-                                                                            d_taken, taken_words, list_rows, max_n1, pairs_stride, (int*)pairs,
-                                                                            (int*)n_pairs, use_smem);
+        cudaStream_t rs = stream;
+        if (async_resolve && device_call) {
+            B200_CUDA(cudaEventRecord(ev_topk, stream));
+            B200_CUDA(cudaStreamWaitEvent(side_stream, ev_topk, 0));
+            rs = side_stream;
+        }
+        resolve_kernel<<<n_problems, 32, use_smem ? rs_bytes : 0, rs>>>(S1, S2, (const unsigned char*)valid2, d_lists, lowe, check_ori, d_matched,
+                                                                        d_taken, taken_words, list_rows, max_n1, pairs_stride, (int*)pairs,
+                                                                        (int*)n_pairs, use_smem);
         B200_CUDA(cudaGetLastError());
+        if (timing) B200_CUDA(cudaEventRecord(ev_t[2], rs));
+        if (rs != stream) {
+            B200_CUDA(cudaEventRecord(ev_resolved, side_stream));
+            resolve_pending = true;
+        }
         return B200_OK;
     }
 };
@@ -1097,6 +1125,10 @@ int b200_matcher_create(int device, b200_matcher_t* out) {
     if (!h) return B200_ERR_INVALID;
     h->m.device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&h->m.own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->m.side_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->m.ev_topk, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->m.ev_resolved, cudaEventDisableTiming);
+    for (int i = 0; i < 3 && e == cudaSuccess; ++i) e = cudaEventCreate(&h->m.ev_t[i]);
     if (e != cudaSuccess) {
         delete h;
         return b200::cuda_fail(e, "stream creation", __FILE__, __LINE__);
@@ -1110,26 +1142,64 @@ int b200_matcher_destroy(b200_matcher_t h) {
     if (!h) return B200_OK;
     cudaSetDevice(h->m.device);
     cudaStreamSynchronize(h->m.stream);
+    if (h->m.side_stream) cudaStreamSynchronize(h->m.side_stream);
     cudaFree(h->m.d_lists);
     cudaFree(h->m.d_matched);
     cudaFree(h->m.d_taken);
     cudaFree(h->m.d_stage);
     cudaFree(h->m.d_guided);
     if (h->m.h_guided) cudaFreeHost(h->m.h_guided);
+    for (int i = 0; i < 3; ++i)
+        if (h->m.ev_t[i]) cudaEventDestroy(h->m.ev_t[i]);
+    if (h->m.ev_topk) cudaEventDestroy(h->m.ev_topk);
+    if (h->m.ev_resolved) cudaEventDestroy(h->m.ev_resolved);
+    if (h->m.side_stream) cudaStreamDestroy(h->m.side_stream);
     if (h->m.own_stream) cudaStreamDestroy(h->m.own_stream);
     delete h;
     return B200_OK;
 }
 
+int b200_matcher_set_async_resolve(b200_matcher_t h, int enable) {
+    if (!h) return B200_ERR_INVALID;
+    int rc = h->m.join();
+    if (rc) return rc;
+    h->m.async_resolve = enable != 0;
+    return B200_OK;
+}
+
+int b200_matcher_enable_timing(b200_matcher_t h, int enable) {
+    if (!h) return B200_ERR_INVALID;
+    h->m.timing = enable != 0;
+    return B200_OK;
+}
+
+int b200_matcher_stage_ms(b200_matcher_t h, int stage, float* ms) {
+    if (!h || !ms || stage < 0 || stage > 1) return B200_ERR_INVALID;
+    B200_CUDA(cudaEventSynchronize(h->m.ev_t[stage + 1]));
+    B200_CUDA(cudaEventElapsedTime(ms, h->m.ev_t[stage], h->m.ev_t[stage + 1]));
+    return B200_OK;
+}
+
+int b200_matcher_join(b200_matcher_t h) {
+    if (!h) return B200_ERR_INVALID;
+    return h->m.join();
+}
+
 int b200_matcher_set_stream(b200_matcher_t h, void* stream, int use_own) {
     if (!h) return B200_ERR_INVALID;
     B200_CUDA(cudaStreamSynchronize(h->m.stream));
+    if (h->m.side_stream) B200_CUDA(cudaStreamSynchronize(h->m.side_stream));
+    h->m.resolve_pending = false;
     h->m.stream = use_own ? h->m.own_stream : (cudaStream_t)stream;
     return B200_OK;
 }
 
 int b200_matcher_sync(b200_matcher_t h) {
     if (!h) return B200_ERR_INVALID;
+    if (h->m.resolve_pending) {
+        B200_CUDA(cudaStreamSynchronize(h->m.side_stream));
+        h->m.resolve_pending = false;
+    }
     B200_CUDA(cudaStreamSynchronize(h->m.stream));
     return B200_OK;
 }
@@ -1147,7 +1217,7 @@ int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, const void* d
     B200_CUDA(cudaSetDevice(h->m.device));
     const Side S1{(const uint4*)d_desc1, (const unsigned char*)d_angle1, (long long)angle1_stride, (const int*)d_off1, (const int*)d_cnt1};
     const Side S2{(const uint4*)d_desc2, (const unsigned char*)d_angle2, (long long)angle2_stride, (const int*)d_off2, (const int*)d_cnt2};
-    return h->m.run(n_problems, S1, S2, d_valid2, max_n1, max_n2, lowe_ratio, check_orientation, d_pairs, pairs_stride, d_n_pairs);
+    return h->m.run(n_problems, S1, S2, d_valid2, max_n1, max_n2, lowe_ratio, check_orientation, d_pairs, pairs_stride, d_n_pairs, true);
 }
 
 int b200_match_bruteforce(b200_matcher_t h, int n_problems, const uint8_t* desc1, const void* angle1, size_t angle1_stride,

@@ -337,7 +337,7 @@ template <bool kUseTma>
 __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_constant__ Geom g, const __grid_constant__ TmapSet tmaps, Images im,
                                                                   const CellDesc* __restrict__ cells, const unsigned char* __restrict__ mask,
                                                                   unsigned long long mask_pitch, unsigned long long* __restrict__ grid,
-                                                                  int arena_frame0) {
+                                                                  int arena_frame0, int* __restrict__ raw_corners) {
     // tile column c holds cell column c - 1 (so the first candidate column, lx = 3, is 4-byte aligned); pitch 80
     __shared__ __align__(16) unsigned char tile[kTileRows * kTilePitch];
     __shared__ __align__(16) unsigned char mmap[kTileRows * kTilePitch];
@@ -407,12 +407,49 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
 
     const int t_low = min(g.ini_thr, g.min_thr);
     const unsigned neg_tlow2 = (unsigned)((-t_low) & 0xFFFF) * 0x10001u;
-    // phase 1a: candidate test.  thread = (word column wq, group of 4 rows); candidate columns lx in [3, cw-4] <=> tile column lx+1
-    {
+    // phase 1a: candidate test.  thread = (word column wq, group of 4 rows); candidate columns lx in [3, cw-4] <=> tile column lx+1.
+    // A pixel can only be a corner at threshold t if one pixel of each compass pair {(0,+3),(0,-3)} and {(+3,0),(-3,0)} differs from
+    // it by more than t (every 9-arc holds one pixel of each antipodal pair), whatever the sign: a superset of the u16x2 bound
+    // test above (10.7 % instead of 9.7 % of the bench stream's pixels pass at t = 7) that runs at BYTE width -- sm_100a has no
+    // native byte min/max or compare (the video intrinsics expand to 6-instruction sequences, measured in SASS) but it does have
+    // VABSDIFF4, and "|d| > t" on four bytes is three logic/add operations.  20 instead of 46 instructions per four pixels.
+    if (t_low <= 126) {
         const int wq = tid & 15, rg = tid >> 4;       // 16 word columns x 16 row groups
         const int c0 = 4 + 4 * wq;                    // tile column of the first pixel of the word
         const int lx0 = c0 - 1;                       // its cell column
         const int y0 = 3 + 4 * rg;                    // first candidate row of the group
+        if (lx0 <= cw - 4 && y0 <= ch - 4) {
+            const unsigned c7f = (unsigned)(0x7F - t_low) * 0x01010101u;
+            auto gt = [&](unsigned d) { return (((d & 0x7F7F7F7Fu) + c7f) | d) & 0x80808080u; };  // bit 7 of byte b: d_b > t_low
+            unsigned ctr[10];  // centre words of rows y0-3 .. y0+6
+#pragma unroll
+            for (int r = 0; r < 10; ++r) ctr[r] = *reinterpret_cast<const unsigned*>(tile + (y0 - 3 + r) * kTilePitch + c0);
+            unsigned acc = 0;  // byte b (pixel), bit i (row): candidate
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const unsigned* row = reinterpret_cast<const unsigned*>(tile + (y0 + i) * kTilePitch + c0 - 4);
+                const unsigned v = ctr[i + 3];
+                const unsigned p4 = __byte_perm(v, row[2], 0x6543), p12 = __byte_perm(row[0], v, 0x4321);  // (+3, 0), (-3, 0)
+                const unsigned gbits = (gt(__vabsdiffu4(ctr[i + 6], v)) | gt(__vabsdiffu4(ctr[i], v))) & (gt(__vabsdiffu4(p4, v)) | gt(__vabsdiffu4(p12, v)));
+                acc |= gbits >> (7 - i);
+            }
+            // pixels of this word that are candidates: lx0 + b <= cw - 4; rows y0 + i <= ch - 4
+            const int nvalid = min(4, cw - 3 - lx0), nrows = min(4, ch - 3 - y0);
+            acc &= (0xFFFFFFFFu >> (32 - 8 * nvalid)) & (((1u << nrows) - 1u) * 0x01010101u);
+            if (acc) {
+                int pos = atomicAdd(&n_cand, __popc(acc));
+                while (acc) {
+                    const int k = __ffs(acc) - 1;
+                    acc &= acc - 1;
+                    cand[pos++] = (unsigned short)(((y0 + (k & 7)) << 8) | (c0 + (k >> 3)));
+                }
+            }
+        }
+    } else {
+        const int wq = tid & 15, rg = tid >> 4;
+        const int c0 = 4 + 4 * wq;
+        const int lx0 = c0 - 1;
+        const int y0 = 3 + 4 * rg;
         if (lx0 <= cw - 4 && y0 <= ch - 4) {
             unsigned w[10][3];
 #pragma unroll
@@ -423,7 +460,6 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
                 w[r][1] = row[1];
                 w[r][2] = row[2];
             }
-            // pixels of this word that are candidates: lx0 + b <= cw - 4
             const int nvalid = min(4, cw - 3 - lx0);
             const unsigned keep = (1u << nvalid) - 1u;
             unsigned bits = 0;  // 4 rows x 4 pixels
@@ -491,6 +527,7 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     const int cell_has_ini = __syncthreads_or(any_ini);
     const int thr_rel = cell_has_ini ? ini_rel : min_rel;
     // phase 3: mask test per keypoint, selection-grid cell, ordered arg-max via 64-bit atomicMax
+    int n_raw = 0;  // FAST corners this thread hands to distribute_keypoints (the C of SURVEY 8d's byte formulas)
     if (kept) {
         int it = 0;
         for (int idx = tid; idx < n_words; idx += kFastThreads, ++it) {
@@ -513,8 +550,14 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
                 const unsigned order = ((unsigned)(cd.i * L.ncols + cd.j) << 14) | ((unsigned)ly << 7) | (unsigned)lx;
                 const unsigned long long val = ((unsigned long long)mv << 32) | (unsigned long long)(0xFFFFFFFFu - order);
                 atomicMax(grid + (size_t)frame * g.grid_cells + L.grid_base + cell, val);
+                ++n_raw;
             }
         }
+    }
+    if (raw_corners) {
+#pragma unroll
+        for (int s2 = 16; s2 > 0; s2 >>= 1) n_raw += __shfl_xor_sync(0xFFFFFFFFu, n_raw, s2);
+        if ((tid & 31) == 0 && n_raw) atomicAdd(raw_corners + frame, n_raw);
     }
 }
 
@@ -948,7 +991,7 @@ struct Extractor {
     ResizeTap* d_taps = nullptr;
     unsigned long long* d_grid = nullptr;
     RawKp* d_raw = nullptr;
-    int *d_counts = nullptr, *d_level_counts = nullptr;
+    int *d_counts = nullptr, *d_level_counts = nullptr, *d_raw_corners = nullptr;
     b200_keypoint_t* d_kps = nullptr;
     unsigned char* d_descs = nullptr;
     int* h_counts = nullptr;  // pinned
@@ -973,11 +1016,11 @@ struct Extractor {
     void free_arenas() {
         cudaFree(d_img0); cudaFree(d_pyr); cudaFree(d_rect_mask); cudaFree(d_user_mask);
         cudaFree(d_cells); cudaFree(d_taps); cudaFree(d_grid); cudaFree(d_raw);
-        cudaFree(d_counts); cudaFree(d_level_counts); cudaFree(d_kps); cudaFree(d_descs);
+        cudaFree(d_counts); cudaFree(d_level_counts); cudaFree(d_raw_corners); cudaFree(d_kps); cudaFree(d_descs);
         if (h_counts) cudaFreeHost(h_counts);
         d_img0 = d_pyr = d_rect_mask = d_user_mask = nullptr;
         d_cells = nullptr; d_taps = nullptr; d_grid = nullptr; d_raw = nullptr;
-        d_counts = d_level_counts = nullptr; d_kps = nullptr; d_descs = nullptr; h_counts = nullptr;
+        d_counts = d_level_counts = d_raw_corners = nullptr; d_kps = nullptr; d_descs = nullptr; h_counts = nullptr;
         rect_mask_ready = false;
     }
 
@@ -1107,6 +1150,7 @@ struct Extractor {
         B200_CUDA(cudaMalloc(&d_raw, sizeof(RawKp) * (size_t)raw_stride * batch));
         B200_CUDA(cudaMalloc(&d_counts, sizeof(int) * batch));
         B200_CUDA(cudaMalloc(&d_level_counts, sizeof(int) * kMaxLevels * batch));
+        B200_CUDA(cudaMalloc(&d_raw_corners, sizeof(int) * batch));
         B200_CUDA(cudaMalloc(&d_kps, sizeof(b200_keypoint_t) * (size_t)raw_stride * batch));
         B200_CUDA(cudaMalloc(&d_descs, (size_t)32 * raw_stride * batch));
         B200_CUDA(cudaHostAlloc(&h_counts, sizeof(int) * (kMaxLevels + 1) * batch, cudaHostAllocDefault));
@@ -1171,11 +1215,14 @@ struct Extractor {
         }
         if (tm) B200_CUDA(cudaEventRecord(ev[1], stream));
         B200_CUDA(cudaMemsetAsync(grid, 0, sizeof(unsigned long long) * (size_t)std::max(1, geom.grid_cells) * batch, stream));
+        B200_CUDA(cudaMemsetAsync(d_raw_corners + frame0, 0, sizeof(int) * batch, stream));
         if (n_cells) {
             // level 0 lives in the caller's buffer: encode its tensor map for this call (a host-side table fill, no GPU work)
             const bool tma = tmaps_ok && make_level_tmap(&tmaps.m[0], d_images, geom.lv[0].w, geom.lv[0].h, pitch, fstride, batch);
-            if (tma) fast_cells_kernel<true><<<dim3(n_cells, batch), kFastThreads, 0, stream>>>(geom, tmaps, im, d_cells, mask, mpitch, grid, frame0);
-            else fast_cells_kernel<false><<<dim3(n_cells, batch), kFastThreads, 0, stream>>>(geom, tmaps, im, d_cells, mask, mpitch, grid, frame0);
+            if (tma) fast_cells_kernel<true><<<dim3(n_cells, batch), kFastThreads, 0, stream>>>(geom, tmaps, im, d_cells, mask, mpitch, grid, frame0,
+                                                                                                   d_raw_corners + frame0);
+            else fast_cells_kernel<false><<<dim3(n_cells, batch), kFastThreads, 0, stream>>>(geom, tmaps, im, d_cells, mask, mpitch, grid, frame0,
+                                                                                                    d_raw_corners + frame0);
             last_used_tma = tma;
         }
         if (tm) B200_CUDA(cudaEventRecord(ev[2], stream));
@@ -1851,6 +1898,16 @@ int b200_convert_to_grayscale(b200_orb_t h, const uint8_t* src, int width, int h
 int b200_orb_enable_timing(b200_orb_t h, int enable) {
     if (!h) return B200_ERR_INVALID;
     h->ex.timing = enable != 0;
+    return B200_OK;
+}
+
+int b200_orb_raw_corner_counts(b200_orb_t h, int32_t* counts, int n) {
+    if (!h || !counts || n < 0) return B200_ERR_INVALID;
+    n = std::min(n, h->ex.last_batch);
+    if (n == 0 || !h->ex.d_raw_corners) return B200_OK;
+    B200_CUDA(cudaSetDevice(h->ex.prm.device));
+    B200_CUDA(cudaMemcpyAsync(counts, h->ex.d_raw_corners, sizeof(int) * n, cudaMemcpyDeviceToHost, h->ex.stream));
+    B200_CUDA(cudaStreamSynchronize(h->ex.stream));
     return B200_OK;
 }
 
