@@ -14,6 +14,8 @@
 // Both steps are exact, so the match pairs equal the reference's bit for bit.
 #include <algorithm>
 #include <climits>
+#include <cmath>
+#include <type_traits>
 #include <new>
 #include <cstring>
 #include <vector>
@@ -27,6 +29,7 @@ constexpr int kTopK = 8;            // candidates kept per keyframe keypoint
 constexpr int kRowsPerBlock = 64;   // one keyframe keypoint per thread (small CTAs: a 2000-row problem still yields 32 of them)
 constexpr int kChunk = 256;         // frame descriptors staged per shared-memory tile (8 KB)
 constexpr unsigned kInfKey = 0xFFFFFFFFu;
+constexpr unsigned kSentinelIdx = 0x3FFFFFu;  // index no keypoint can have (frames hold < 2^22 - 1 keypoints)
 constexpr int kThrLow = 50;         // HAMMING_DIST_THR_LOW  (match/base.h:15)
 constexpr int kMaxDist = 256;       // MAX_HAMMING_DIST      (match/base.h:17)
 
@@ -133,6 +136,249 @@ __global__ void __launch_bounds__(kRowsPerBlock) topk_kernel(Side S1, Side S2, c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// (1b) top-K candidate lists on the 5th-generation tensor cores.  The Hamming distance of two 256-bit descriptors is a dot
+//      product in disguise: with the bits mapped to +-1,  popcount(a ^ b) = (256 - <a, b>) / 2  -- exact in int32 -- so the all-pairs
+//      distance matrix of a (frame, keyframe) pair is a 2000 x 2000 x 256 int8 GEMM.  One CTA owns 256 keyframe rows (two 128-row
+//      M tiles, expanded once into shared memory in the canonical K-major no-swizzle UMMA layout: 8 x 16-byte core matrices) and
+//      walks the frame's keypoints in chunks of 128 (the B operand, expanded by the same threads): ONE thread issues
+//      tcgen05.mma.cta_group::1.kind::i8 (M 128, N 128, K 32; 8 per tile and chunk), the accumulators live in TMEM (2 tiles x 2
+//      buffers x 128 columns = all 512 columns) and tcgen05.commit signals an mbarrier.  While the tensor core works on chunk c the
+//      eight warps read chunk c-1 back with tcgen05.ld (thread = keyframe row = TMEM lane) and keep the 8 smallest
+//      (distance, index) keys that pass the orientation gate -- the selection of topk_kernel, bit for bit.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTcRows = 256;        // keyframe rows per CTA (2 M tiles)
+constexpr int kTcChunk = 128;       // frame keypoints per B chunk (= N of the MMA)
+constexpr int kTcThreads = 256;
+constexpr int kTcTileBytes = 128 * 256;  // one 128-row operand tile of +-1 bytes
+struct TcSmem {
+    unsigned char a[2][kTcTileBytes];
+    unsigned char b[2][kTcTileBytes];
+    uint2 lut[256];                 // descriptor byte -> 8 bytes of +-1
+    float ang[3][kTcChunk];         // three: the epilogue of chunk c-1 may still read its angles while chunk c+1 is being staged
+    unsigned long long bar[2];
+    unsigned tmem_base;
+    unsigned pad;
+};
+__device__ __forceinline__ unsigned long long umma_desc_k_major(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes) {
+    // cute::UMMA::SmemDescriptor: start address [0,14), leading byte offset [16,30), stride byte offset [32,46) (all >> 4), version 1 at
+    // [46,48), base offset 0, layout type SWIZZLE_NONE (0) at [61,64).  K-major canonical layout ((8,n),2):((1,SBO),LBO) in 16-byte units.
+    return (unsigned long long)((smem_addr >> 4) & 0x3FFFu) | ((unsigned long long)((lbo_bytes >> 4) & 0x3FFFu) << 16)
+           | ((unsigned long long)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void tc_mma_i8(unsigned tmem_d, unsigned long long da, unsigned long long db, unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+        ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(unsigned taddr, unsigned (&v)[32]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+                 "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                   "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                   "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(unsigned long long* bar, unsigned parity) {
+    // bounded: a tensor-core fault must surface as a launch error, never as a hung GPU
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    for (unsigned spin = 0; spin < (1u << 28); ++spin) {
+        unsigned done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+    }
+    asm volatile("trap;");
+}
+// +-1 expansion of one 16-byte half descriptor (8 K-chunks of 16 bytes) into the operand tile: row r of a 128-row tile, chunks c0..c0+7
+__device__ __forceinline__ void tc_expand_half(unsigned char* tile, const uint2* lut, int r, int c0, uint4 bits) {
+    unsigned char* dst = tile + (r >> 3) * 128 + (r & 7) * 16;
+    const unsigned w[4] = {bits.x, bits.y, bits.z, bits.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {  // chunk c0 + i <- descriptor bytes 2i, 2i+1 of this half
+        const unsigned hw = (w[i >> 1] >> (16 * (i & 1))) & 0xFFFFu;
+        const uint2 lo = lut[hw & 0xFFu], hi = lut[hw >> 8];
+        *reinterpret_cast<uint4*>(dst + (c0 + i) * 2048) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) topk_tc_kernel(Side S1, Side S2, const unsigned char* __restrict__ valid2, int check_orientation,
+                                                                unsigned* __restrict__ lists, int list_rows, unsigned cap) {
+    extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
+    TcSmem& sm = *reinterpret_cast<TcSmem*>(tc_smem_raw);
+    const uint4* __restrict__ desc1 = S1.desc;
+    const uint4* __restrict__ desc2 = S2.desc;
+    const int p = blockIdx.y;
+    const int b1 = S1.off[p], n1 = S1.cnt[p];
+    const int b2 = S2.off[p], n2 = S2.cnt[p];
+    const int row0 = blockIdx.x * kTcRows;
+    if (row0 >= n2) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // ---- one-time setup: TMEM, barriers, the byte -> +-1 table, the A operand (this CTA's keyframe rows)
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&sm.tmem_base)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&sm.bar[0])), "r"(1u));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&sm.bar[1])), "r"(1u));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        unsigned lo = 0, hi = 0;  // bit i of the byte -> byte i: +1 (0x01) if set, -1 (0xFF) if clear
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            lo |= (((tid >> i) & 1) ? 0x01u : 0xFFu) << (8 * i);
+            hi |= (((tid >> (4 + i)) & 1) ? 0x01u : 0xFFu) << (8 * i);
+        }
+        sm.lut[tid] = make_uint2(lo, hi);
+    }
+    __syncthreads();
+    const int my_row = row0 + tid;                  // thread = keyframe row = TMEM lane (tile = tid / 128)
+    const bool active = my_row < n2 && (!valid2 || valid2[b2 + my_row]);
+    {
+        uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
+        const bool real = my_row < n2;
+        if (real) {
+            h0 = desc2[(size_t)(b2 + my_row) * 2];
+            h1 = desc2[(size_t)(b2 + my_row) * 2 + 1];
+        }
+        unsigned char* tile = sm.a[tid >> 7];
+        const int r = tid & 127;
+        if (real) {
+            tc_expand_half(tile, sm.lut, r, 0, h0);
+            tc_expand_half(tile, sm.lut, r, 8, h1);
+        } else {  // rows past the keyframe: zeros (their lists are never written)
+            unsigned char* dst = tile + (r >> 3) * 128 + (r & 7) * 16;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) *reinterpret_cast<uint4*>(dst + c * 2048) = make_uint4(0, 0, 0, 0);
+        }
+    }
+    const float qa = active ? side_angle(S2, b2 + my_row) : 0.f;
+    unsigned top[kTopK];
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k) top[k] = kInfKey;
+    // Distance cap.  robust.cc:297-308 accepts a match only if best <= 50 and lowe * second >= best, so a second-best distance matters
+    // only while lowe * second < 50: a candidate farther than cap = ceil(50 / lowe) can change no decision and is not listed (random
+    // descriptor pairs are ~128 +- 8 apart, so this removes nearly every insertion).  Rows without a landmark list nothing.
+    unsigned thr = active ? make_key(cap + 1u, 0u) : 0u;
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 at [4,6)), A = B = signed int8 (1 at [7,10) and [10,13)), both K-major,
+    // N >> 3 at [17,23), M >> 4 at [24,29)
+    const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kTcChunk >> 3) << 17) | ((128u >> 4) << 24);
+    const unsigned a_addr[2] = {(unsigned)__cvta_generic_to_shared(sm.a[0]), (unsigned)__cvta_generic_to_shared(sm.a[1])};
+    const unsigned b_addr[2] = {(unsigned)__cvta_generic_to_shared(sm.b[0]), (unsigned)__cvta_generic_to_shared(sm.b[1])};
+    const int n_chunks = (n1 + kTcChunk - 1) / kTcChunk;
+    unsigned tmem = 0;
+    for (int c = 0; c <= n_chunks; ++c) {
+        if (c < n_chunks) {
+            // B operand of chunk c: 128 frame keypoints; thread = (row, half descriptor)
+            const int buf = c & 1, r = tid & 127, half = tid >> 7, j = c * kTcChunk + r;
+            uint4 bits = make_uint4(0, 0, 0, 0);
+            if (j < n1) {
+                bits = desc1[(size_t)(b1 + j) * 2 + half];
+                tc_expand_half(sm.b[buf], sm.lut, r, 8 * half, bits);
+                if (half == 0) sm.ang[c % 3][r] = side_angle(S1, b1 + j);
+            } else {
+                unsigned char* dst = sm.b[buf] + (r >> 3) * 128 + (r & 7) * 16;
+#pragma unroll
+                for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(dst + (8 * half + cc) * 2048) = make_uint4(0, 0, 0, 0);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core's async proxy
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        tmem = sm.tmem_base;
+        if (c < n_chunks && tid == 0) {
+            const int buf = c & 1;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {
+                const unsigned d_col = tmem + (unsigned)((buf * 2 + t) * kTcChunk);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks)  // K = 32 bytes per instruction = chunks 2 ks, 2 ks + 1 (2048 bytes apart)
+                    tc_mma_i8(d_col, umma_desc_k_major(a_addr[t] + ks * 4096, 2048, 128), umma_desc_k_major(b_addr[buf] + ks * 4096, 2048, 128), idesc,
+                              ks > 0 ? 1u : 0u);
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                             (unsigned)__cvta_generic_to_shared(&sm.bar[buf]))
+                         : "memory");
+        }
+        if (c > 0) {
+            // epilogue of chunk c - 1 while the tensor core runs chunk c
+            const int e = c - 1, buf = e & 1, c0 = e * kTcChunk;
+            tc_mbar_wait(&sm.bar[buf], (unsigned)(e >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((buf * 2 + (tid >> 7)) * kTcChunk);
+            // key = distance << 22 | index with distance = (256 - dot) / 2:  (256 - dot) << 21 has bit 21 clear (the dot product of two
+            // +-1 vectors of even length is even), so the key is one multiply-add.  Four keys are tested against the row's threshold with
+            // one 3-input minimum, one compare and one warp vote; only a group that holds a candidate for some row of the warp inserts.
+            // The threshold starts at the distance cap (see below), so candidates are rare: a warp's 32 rows see a few dozen in all.
+            const unsigned kbase = (256u << 21) + (unsigned)c0;
+            auto scan = [&](auto full_chunk) {
+#pragma unroll 1
+                for (int g = 0; g < kTcChunk / 32; ++g) {
+                    if (!decltype(full_chunk)::value && c0 + 32 * g >= n1) break;
+                    unsigned v[32];
+                    tc_ld32(taddr + 32 * g, v);
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        unsigned key[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            key[u] = (unsigned)((int)v[i + u] * -(1 << 21)) + (kbase + (unsigned)(32 * g + i + u));
+                            if (!decltype(full_chunk)::value && c0 + 32 * g + i + u >= n1) key[u] = kInfKey;  // zero padding of the last chunk
+                        }
+                        const unsigned m4 = min(__vimin3_u32(key[0], key[1], key[2]), key[3]);
+                        if (__any_sync(0xFFFFFFFFu, m4 < thr)) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (key[u] < thr) {
+                                    if (check_orientation && orientation_rejects(sm.ang[e % 3][32 * g + i + u], qa)) continue;
+                                    top[kTopK - 1] = key[u];
+#pragma unroll
+                                    for (int k = kTopK - 1; k > 0; --k) {
+                                        if (top[k] < top[k - 1]) {
+                                            const unsigned t2 = top[k];
+                                            top[k] = top[k - 1];
+                                            top[k - 1] = t2;
+                                        }
+                                    }
+                                    thr = min(thr, top[kTopK - 1]);
+                                }
+                            }
+                        }
+                    }
+                }
+            };
+            if (c0 + kTcChunk <= n1) scan(std::true_type{});
+            else scan(std::false_type{});
+        }
+    }
+    // lists shorter than 8: the slots name no candidate but state the bound "everything else is farther than the cap"
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k)
+        if (top[k] == kInfKey && cap < (unsigned)kMaxDist) top[k] = make_key(cap + 1u, kSentinelIdx);
+    if (my_row < n2) {
+        unsigned* o = lists + ((size_t)p * list_rows + my_row) * kTopK;
+#pragma unroll
+        for (int k = 0; k < kTopK; ++k) o[k] = top[k];
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // (2) in-order resolve + compaction.  One warp per problem.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned warp_min(unsigned v) {
@@ -181,7 +427,8 @@ __device__ void exact_row(const uint4* desc1, const unsigned char* angle1, long 
 
 // Decision of one keyframe keypoint from its sorted candidate list against the current `taken` set.
 //   returns 0: decided, no match; 1: decided, match with key *best; 2: undecidable from the list (exact row scan needed)
-__device__ __forceinline__ int decide_row(const unsigned (&keys)[kTopK], const volatile unsigned* taken, float lowe_ratio, unsigned* best) {
+__device__ __forceinline__ int decide_row(const unsigned (&keys)[kTopK], bool full, unsigned tail_dist, const volatile unsigned* taken, float lowe_ratio,
+                                          unsigned* best) {
     unsigned best_key = kInfKey, second_dist = kMaxDist;
     int n_live = 0;
 #pragma unroll
@@ -194,8 +441,7 @@ __device__ __forceinline__ int decide_row(const unsigned (&keys)[kTopK], const v
         else if (n_live == 1) second_dist = key_dist(key);
         ++n_live;
     }
-    const bool full = keys[kTopK - 1] != kInfKey;  // unlisted candidates exist only if the list is full
-    const unsigned tail_dist = key_dist(keys[kTopK - 1]);  // every unlisted distance is >= this
+    // full: unlisted candidates exist; every unlisted distance is >= tail_dist
     if (full && n_live < 2) {
         if (n_live == 1) {
             // best is exact; the true second distance lies in [tail_dist, 256]
@@ -269,11 +515,18 @@ __global__ void __launch_bounds__(32) resolve_kernel(Side S1, Side S2, const uns
             keys[0] = k0.x; keys[1] = k0.y; keys[2] = k0.z; keys[3] = k0.w;
             keys[4] = k1.x; keys[5] = k1.y; keys[6] = k1.z; keys[7] = k1.w;
         }
+        // A list is "full" when candidates exist that it does not name: its last entry then bounds their distance from below.  The
+        // tensor-core lister only names candidates up to a distance cap and pads with sentinel keys (cap + 1, impossible index).
+        const bool list_full = keys[kTopK - 1] != kInfKey;
+        const unsigned tail_dist = key_dist(keys[kTopK - 1]);
+#pragma unroll
+        for (int k = 0; k < kTopK; ++k)
+            if (key_idx(keys[k]) == kSentinelIdx) keys[k] = kInfKey;
         unsigned pending = __ballot_sync(0xFFFFFFFFu, has_row);
         while (pending) {
             const bool mine = (pending >> lane) & 1u;
             unsigned best = kInfKey;
-            const int st = mine ? decide_row(keys, taken, lowe_ratio, &best) : 0;
+            const int st = mine ? decide_row(keys, list_full, tail_dist, taken, lowe_ratio, &best) : 0;
             const unsigned accept_mask = __ballot_sync(0xFFFFFFFFu, mine && st == 1);
             const unsigned exact_mask = __ballot_sync(0xFFFFFFFFu, mine && st == 2);
             // conflicts with earlier accepting lanes of this round
@@ -1011,6 +1264,8 @@ struct Matcher {
     bool async_resolve = false, resolve_pending = false;
     bool timing = false;
     cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
+    // all-pairs distances + top-K on the tensor cores (tcgen05, int8 +-1 GEMM) or on the POPC pipe (B200_MATCH_TOPK=popc)
+    bool use_tensor_core = true;
     int join() {  // the main stream waits for the side stream's resolve
         if (resolve_pending) {
             B200_CUDA(cudaStreamWaitEvent(stream, ev_resolved, 0));
@@ -1062,7 +1317,7 @@ struct Matcher {
     int run(int n_problems, const Side& S1, const Side& S2, const void* valid2, int max_n1, int max_n2, float lowe, int check_ori,
             void* pairs, int pairs_stride, void* n_pairs, bool device_call = false) {
         if (n_problems <= 0) return B200_OK;
-        if (max_n1 >= (1 << 22)) {
+        if (max_n1 >= (1 << 22) - 1) {
             set_error("brute-force matcher supports < 4194304 keypoints per frame");
             return B200_ERR_INVALID;
         }
@@ -1079,7 +1334,15 @@ struct Matcher {
         if ((rc = grow((void**)&d_matched, &matched_cap, sizeof(int) * (size_t)max_n1 * n_problems))) return rc;
         if ((rc = grow((void**)&d_taken, &taken_cap, sizeof(unsigned) * (size_t)taken_words * n_problems))) return rc;
         if (timing) B200_CUDA(cudaEventRecord(ev_t[0], stream));
-        topk_kernel<<<dim3(row_blocks, n_problems), kRowsPerBlock, 0, stream>>>(S1, S2, (const unsigned char*)valid2, check_ori, d_lists);
+        if (use_tensor_core) {
+            const float need = lowe > 0.f ? std::ceil((float)kThrLow / lowe) + 1.f : (float)kMaxDist;
+            const unsigned cap = (unsigned)std::min((float)kMaxDist, std::max((float)kThrLow, need));
+            B200_CUDA(cudaFuncSetAttribute(topk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TcSmem) + 1024));
+            topk_tc_kernel<<<dim3(ceil_div(std::max(max_n2, 1), kTcRows), n_problems), kTcThreads, sizeof(TcSmem) + 1024, stream>>>(
+                S1, S2, (const unsigned char*)valid2, check_ori, d_lists, list_rows, cap);
+        } else {
+            topk_kernel<<<dim3(row_blocks, n_problems), kRowsPerBlock, 0, stream>>>(S1, S2, (const unsigned char*)valid2, check_ori, d_lists);
+        }
         if (timing) B200_CUDA(cudaEventRecord(ev_t[1], stream));
         const size_t state_bytes = sizeof(unsigned) * ((size_t)taken_words + 2 * (size_t)max_n1);  // taken bitmap, idx_1 -> idx_2 table, claim table
         const size_t stage_bytes = sizeof(unsigned) * 9 * (size_t)max_n1;
@@ -1134,6 +1397,7 @@ int b200_matcher_create(int device, b200_matcher_t* out) {
         return b200::cuda_fail(e, "stream creation", __FILE__, __LINE__);
     }
     h->m.stream = h->m.own_stream;
+    if (const char* tk = getenv("B200_MATCH_TOPK")) h->m.use_tensor_core = !(tk[0] == 'p');
     *out = h;
     return B200_OK;
 }
