@@ -38,14 +38,18 @@ __device__ __forceinline__ unsigned make_key(unsigned dist, unsigned idx) { retu
 __device__ __forceinline__ unsigned key_dist(unsigned key) { return key >> 22; }
 __device__ __forceinline__ unsigned key_idx(unsigned key) { return key & 0x3FFFFFu; }
 
-__device__ __forceinline__ float angle_diff(float a1, float a2) {  // util/angle.cc:7-16
+// util/angle.cc:7-16 compares and adds in double (float operands promoted).  With float operands these are the same decisions and the
+// same values in float arithmetic: -180, 180, 360 and 30 are exact floats, promoting a float is exact (so the comparisons agree), and
+// (float)((double)ret + 360.0) rounds an exactly representable double sum once -- which is what __fadd_rn(ret, 360.0f) does.  Float
+// keeps the test off the fp64 pipe (it sits in the selection path of every matcher).
+__device__ __forceinline__ float angle_diff(float a1, float a2) {
     float ret = __fsub_rn(a1, a2);
-    if ((double)ret <= -180.0) ret = (float)((double)ret + 360.0);
-    if ((double)ret > 180.0) ret = (float)((double)ret - 360.0);
+    if (ret <= -180.0f) ret = __fadd_rn(ret, 360.0f);
+    if (ret > 180.0f) ret = __fsub_rn(ret, 360.0f);
     return ret;
 }
 __device__ __forceinline__ bool orientation_rejects(float a1, float a2) {  // robust.cc:279
-    return (double)fabsf(angle_diff(a1, a2)) > 30.0;
+    return fabsf(angle_diff(a1, a2)) > 30.0f;
 }
 
 __device__ __forceinline__ unsigned hamming256(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
@@ -138,20 +142,21 @@ __global__ void __launch_bounds__(kRowsPerBlock) topk_kernel(Side S1, Side S2, c
 // ---------------------------------------------------------------------------------------------------------------
 // (1b) top-K candidate lists on the 5th-generation tensor cores.  The Hamming distance of two 256-bit descriptors is a dot
 //      product in disguise: with the bits mapped to +-1,  popcount(a ^ b) = (256 - <a, b>) / 2  -- exact in int32 -- so the all-pairs
-//      distance matrix of a (frame, keyframe) pair is a 2000 x 2000 x 256 int8 GEMM.  One CTA owns 256 keyframe rows (two 128-row
-//      M tiles, expanded once into shared memory in the canonical K-major no-swizzle UMMA layout: 8 x 16-byte core matrices) and
-//      walks the frame's keypoints in chunks of 128 (the B operand, expanded by the same threads): ONE thread issues
-//      tcgen05.mma.cta_group::1.kind::i8 (M 128, N 128, K 32; 8 per tile and chunk), the accumulators live in TMEM (2 tiles x 2
-//      buffers x 128 columns = all 512 columns) and tcgen05.commit signals an mbarrier.  While the tensor core works on chunk c the
-//      eight warps read chunk c-1 back with tcgen05.ld (thread = keyframe row = TMEM lane) and keep the 8 smallest
-//      (distance, index) keys that pass the orientation gate -- the selection of topk_kernel, bit for bit.
+//      distance matrix of a (frame, keyframe) pair is a 2000 x 2000 x 256 int8 GEMM.  One CTA owns 128 keyframe rows (one M tile,
+//      expanded once into shared memory in the canonical K-major no-swizzle UMMA layout: 8 x 16-byte core matrices) and walks the
+//      frame's keypoints in chunks of 128 (the B operand, expanded by the same threads): ONE thread issues
+//      tcgen05.mma.cta_group::1.kind::i8 (M 128, N 128, K 32; 8 per chunk), the accumulators live in TMEM (2 buffers x 128 columns;
+//      two CTAs per SM use all 512) and tcgen05.commit signals an mbarrier.  While the tensor core works on chunk c the four warps
+//      read chunk c-1 back with tcgen05.ld (thread = keyframe row = TMEM lane) and keep the smallest (distance, index) keys that
+//      pass the orientation gate -- the selection of topk_kernel up to a distance cap that cannot change a decision.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kTcRows = 256;        // keyframe rows per CTA (2 M tiles)
+constexpr int kTcRows = 128;        // keyframe rows per CTA (one M tile); two CTAs share an SM: one stages / waits while the other selects
 constexpr int kTcChunk = 128;       // frame keypoints per B chunk (= N of the MMA)
-constexpr int kTcThreads = 256;
+constexpr int kTcThreads = 128;
+constexpr unsigned kTcTmemCols = 256;  // two accumulator buffers of 128 columns (two resident CTAs use all 512)
 constexpr int kTcTileBytes = 128 * 256;  // one 128-row operand tile of +-1 bytes
 struct TcSmem {
-    unsigned char a[2][kTcTileBytes];
+    unsigned char a[kTcTileBytes];
     unsigned char b[2][kTcTileBytes];
     uint2 lut[256];                 // descriptor byte -> 8 bytes of +-1
     float ang[3][kTcChunk];         // three: the epilogue of chunk c-1 may still read its angles while chunk c+1 is being staged
@@ -211,7 +216,7 @@ __device__ __forceinline__ void tc_expand_half(unsigned char* tile, const uint2*
     }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) topk_tc_kernel(Side S1, Side S2, const unsigned char* __restrict__ valid2, int check_orientation,
+__global__ void __launch_bounds__(kTcThreads, 2) topk_tc_kernel(Side S1, Side S2, const unsigned char* __restrict__ valid2, int check_orientation,
                                                                 unsigned* __restrict__ lists, int list_rows, unsigned cap) {
     extern __shared__ __align__(1024) unsigned char tc_smem_raw[];
     TcSmem& sm = *reinterpret_cast<TcSmem*>(tc_smem_raw);
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) topk_tc_kernel(Side S1, Side S2
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // ---- one-time setup: TMEM, barriers, the byte -> +-1 table, the A operand (this CTA's keyframe rows)
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&sm.tmem_base)), "r"(512u)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(&sm.tmem_base)), "r"(kTcTmemCols)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -235,16 +240,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) topk_tc_kernel(Side S1, Side S2
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
-        unsigned lo = 0, hi = 0;  // bit i of the byte -> byte i: +1 (0x01) if set, -1 (0xFF) if clear
+        for (int e = tid; e < 256; e += kTcThreads) {  // bit i of the byte -> byte i: +1 (0x01) if set, -1 (0xFF) if clear
+            unsigned lo = 0, hi = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            lo |= (((tid >> i) & 1) ? 0x01u : 0xFFu) << (8 * i);
-            hi |= (((tid >> (4 + i)) & 1) ? 0x01u : 0xFFu) << (8 * i);
+            for (int i = 0; i < 4; ++i) {
+                lo |= (((e >> i) & 1) ? 0x01u : 0xFFu) << (8 * i);
+                hi |= (((e >> (4 + i)) & 1) ? 0x01u : 0xFFu) << (8 * i);
+            }
+            sm.lut[e] = make_uint2(lo, hi);
         }
-        sm.lut[tid] = make_uint2(lo, hi);
     }
     __syncthreads();
-    const int my_row = row0 + tid;                  // thread = keyframe row = TMEM lane (tile = tid / 128)
+    const int my_row = row0 + tid;                  // thread = keyframe row = TMEM lane
     const bool active = my_row < n2 && (!valid2 || valid2[b2 + my_row]);
     {
         uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
@@ -253,8 +260,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) topk_tc_kernel(Side S1, Side S2
             h0 = desc2[(size_t)(b2 + my_row) * 2];
             h1 = desc2[(size_t)(b2 + my_row) * 2 + 1];
         }
-        unsigned char* tile = sm.a[tid >> 7];
-        const int r = tid & 127;
+        unsigned char* tile = sm.a;
+        const int r = tid;
         if (real) {
             tc_expand_half(tile, sm.lut, r, 0, h0);
             tc_expand_half(tile, sm.lut, r, 8, h1);
@@ -275,23 +282,37 @@ __global__ void __launch_bounds__(kTcThreads, 1) topk_tc_kernel(Side S1, Side S2
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 at [4,6)), A = B = signed int8 (1 at [7,10) and [10,13)), both K-major,
     // N >> 3 at [17,23), M >> 4 at [24,29)
     const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kTcChunk >> 3) << 17) | ((128u >> 4) << 24);
-    const unsigned a_addr[2] = {(unsigned)__cvta_generic_to_shared(sm.a[0]), (unsigned)__cvta_generic_to_shared(sm.a[1])};
+    const unsigned a_addr = (unsigned)__cvta_generic_to_shared(sm.a);
     const unsigned b_addr[2] = {(unsigned)__cvta_generic_to_shared(sm.b[0]), (unsigned)__cvta_generic_to_shared(sm.b[1])};
     const int n_chunks = (n1 + kTcChunk - 1) / kTcChunk;
     unsigned tmem = 0;
+    // the descriptor bits (and angle) of this thread's row of the NEXT chunk are fetched one iteration ahead: the L2 latency hides behind
+    // the selection pass instead of standing in front of the tensor core
+    uint4 nb0 = make_uint4(0, 0, 0, 0), nb1 = nb0;
+    float nang = 0.f;
+    if (tid < n1) {
+        nb0 = desc1[(size_t)(b1 + tid) * 2];
+        nb1 = desc1[(size_t)(b1 + tid) * 2 + 1];
+        nang = side_angle(S1, b1 + tid);
+    }
     for (int c = 0; c <= n_chunks; ++c) {
         if (c < n_chunks) {
-            // B operand of chunk c: 128 frame keypoints; thread = (row, half descriptor)
-            const int buf = c & 1, r = tid & 127, half = tid >> 7, j = c * kTcChunk + r;
-            uint4 bits = make_uint4(0, 0, 0, 0);
+            // B operand of chunk c: 128 frame keypoints, thread = row
+            const int buf = c & 1, r = tid, j = c * kTcChunk + r;
             if (j < n1) {
-                bits = desc1[(size_t)(b1 + j) * 2 + half];
-                tc_expand_half(sm.b[buf], sm.lut, r, 8 * half, bits);
-                if (half == 0) sm.ang[c % 3][r] = side_angle(S1, b1 + j);
+                tc_expand_half(sm.b[buf], sm.lut, r, 0, nb0);
+                tc_expand_half(sm.b[buf], sm.lut, r, 8, nb1);
+                sm.ang[c % 3][r] = nang;
             } else {
                 unsigned char* dst = sm.b[buf] + (r >> 3) * 128 + (r & 7) * 16;
 #pragma unroll
-                for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(dst + (8 * half + cc) * 2048) = make_uint4(0, 0, 0, 0);
+                for (int cc = 0; cc < 16; ++cc) *reinterpret_cast<uint4*>(dst + cc * 2048) = make_uint4(0, 0, 0, 0);
+            }
+            const int jn = j + kTcChunk;
+            if (jn < n1) {
+                nb0 = desc1[(size_t)(b1 + jn) * 2];
+                nb1 = desc1[(size_t)(b1 + jn) * 2 + 1];
+                nang = side_angle(S1, b1 + jn);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core's async proxy
         }
@@ -301,14 +322,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) topk_tc_kernel(Side S1, Side S2
         tmem = sm.tmem_base;
         if (c < n_chunks && tid == 0) {
             const int buf = c & 1;
+            const unsigned d_col = tmem + (unsigned)(buf * kTcChunk);
 #pragma unroll
-            for (int t = 0; t < 2; ++t) {
-                const unsigned d_col = tmem + (unsigned)((buf * 2 + t) * kTcChunk);
-#pragma unroll
-                for (int ks = 0; ks < 8; ++ks)  // K = 32 bytes per instruction = chunks 2 ks, 2 ks + 1 (2048 bytes apart)
-                    tc_mma_i8(d_col, umma_desc_k_major(a_addr[t] + ks * 4096, 2048, 128), umma_desc_k_major(b_addr[buf] + ks * 4096, 2048, 128), idesc,
-                              ks > 0 ? 1u : 0u);
-            }
+            for (int ks = 0; ks < 8; ++ks)  // K = 32 bytes per instruction = chunks 2 ks, 2 ks + 1 (2048 bytes apart)
+                tc_mma_i8(d_col, umma_desc_k_major(a_addr + ks * 4096, 2048, 128), umma_desc_k_major(b_addr[buf] + ks * 4096, 2048, 128), idesc,
+                          ks > 0 ? 1u : 0u);
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                              (unsigned)__cvta_generic_to_shared(&sm.bar[buf]))
                          : "memory");
@@ -318,7 +336,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) topk_tc_kernel(Side S1, Side S2
             const int e = c - 1, buf = e & 1, c0 = e * kTcChunk;
             tc_mbar_wait(&sm.bar[buf], (unsigned)(e >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)((buf * 2 + (tid >> 7)) * kTcChunk);
+            const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(buf * kTcChunk);
             // key = distance << 22 | index with distance = (256 - dot) / 2:  (256 - dot) << 21 has bit 21 clear (the dot product of two
             // +-1 vectors of even length is even), so the key is one multiply-add.  Four keys are tested against the row's threshold with
             // one 3-input minimum, one compare and one warp vote; only a group that holds a candidate for some row of the warp inserts.
@@ -375,7 +393,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) topk_tc_kernel(Side S1, Side S2
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTcTmemCols) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------------------------
