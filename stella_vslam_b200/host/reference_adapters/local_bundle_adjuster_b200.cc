@@ -17,6 +17,8 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <stdexcept>
+
 #include "b200vslam.h"
 
 namespace stella_vslam {
@@ -65,8 +67,16 @@ void local_bundle_adjuster_b200::optimize(data::map_database* map_db, const std:
             const auto kf = obs.first.lock();
             if (kf && !kf->will_be_erased() && !local_kfs.count(kf->id_)) fixed_kfs.emplace(kf->id_, kf);
         }
+    // markers seen in the local keyframes (:81-96)
+    std::map<unsigned int, std::shared_ptr<data::marker>> local_mkrs;
+    for (const auto& id_kf : local_kfs)
+        for (const auto& mkr : id_kf.second->get_markers())
+            if (mkr) local_mkrs.emplace(mkr->id_, mkr);
+    // local_bundle_adjuster_g2o.cc:135-147: "ensure that there are always at least two fixed keyframes" moves local_keyfrms.begin() of
+    // an UNORDERED map -- whichever keyframe libstdc++'s bucket order yields, i.e. an arbitrary one.  Here the containers are ordered
+    // by id, so the OLDEST local keyframes are fixed: one valid instance of the reference's behaviour, and the same one on every run.
     if (use_additional_keyframes_for_monocular_ && !has_scale && fixed_kfs.size() < 2 && local_kfs.size() > 2 - fixed_kfs.size())
-        while (fixed_kfs.size() < 2) {  // local_bundle_adjuster_g2o.cc:135-147
+        while (fixed_kfs.size() < 2) {
             auto it = local_kfs.begin();
             fixed_kfs.insert(*it);
             local_kfs.erase(it);
@@ -97,6 +107,7 @@ void local_bundle_adjuster_b200::optimize(data::map_database* map_db, const std:
     std::vector<int32_t> e_pose, e_point;
     std::vector<uint8_t> e_cam;
     std::vector<float> e_obs, e_isq, e_delta;
+    std::vector<uint8_t> point_fixed, e_robust, e_can_be_outlier;
     const float d2 = std::sqrt(5.99146f), d3 = std::sqrt(7.81473f);  // :204-208
     for (const auto& p : local_lms) {
         const auto& lm = p.second;
@@ -106,6 +117,7 @@ void local_bundle_adjuster_b200::optimize(data::map_database* map_db, const std:
         lms.push_back(lm);
         const Vec3_t pw = lm->get_pos_in_world();
         points.insert(points.end(), {pw(0), pw(1), pw(2)});
+        point_fixed.push_back(0);
         for (const auto& obs : observations) {
             const auto kf = obs.first.lock();
             if (!kf || kf->will_be_erased() || !kf_index.count(kf->id_)) continue;
@@ -116,11 +128,42 @@ void local_bundle_adjuster_b200::optimize(data::map_database* map_db, const std:
             e_obs.insert(e_obs.end(), {kp.pt.x, kp.pt.y, kf->frm_obs_.stereo_x_right_.empty() ? -1.0f : kf->frm_obs_.stereo_x_right_.at(obs.second)});
             e_isq.push_back(kf->orb_params_->inv_level_sigma_sq_.at(kp.octave));
             e_delta.push_back(kf->camera_->setup_type_ == camera::setup_type_t::Monocular ? d2 : d3);
+            e_robust.push_back(1);
+            e_can_be_outlier.push_back(1);
         }
     }
-    // (marker corners, :251-304, map onto extra landmarks with point_fixed / e_robust = 0 / e_can_be_outlier = 0; omitted here for brevity)
+    // marker corners (:251-304): four point vertices per marker that was initialised before (or is kept fixed), one monocular edge per
+    // (corner, observing keyframe of the window) with information = identity, NO Huber kernel (use_huber_loss = false) and never
+    // outlier-tested (they live in mkr_reproj_edge_wraps, which steps 6-7 do not visit)
+    const size_t n_landmark_points = lms.size();
+    std::vector<std::pair<std::shared_ptr<data::marker>, size_t>> mkr_points;  // marker, index of its first corner in `points`
+    for (const auto& id_mkr : local_mkrs) {
+        const auto& mkr = id_mkr.second;
+        if (!mkr->keep_fixed_ && !mkr->initialized_before_) continue;
+        mkr_points.emplace_back(mkr, points.size() / 3);
+        for (unsigned int corner_idx = 0; corner_idx < mkr->corners_pos_w_.size(); ++corner_idx) {
+            const int32_t pi = static_cast<int32_t>(points.size() / 3);
+            const Vec3_t pw = mkr->corners_pos_w_[corner_idx];
+            points.insert(points.end(), {pw(0), pw(1), pw(2)});
+            point_fixed.push_back(mkr->keep_fixed_ ? 1 : 0);
+            for (const auto& id_kf : mkr->observations_) {
+                const auto& kf = id_kf.second;
+                if (!kf || kf->will_be_erased() || !kf_index.count(kf->id_)) continue;
+                const auto& undist_pt = kf->markers_2d_.at(mkr->id_).undist_corners_.at(corner_idx);
+                e_pose.push_back(kf_index.at(kf->id_));
+                e_point.push_back(pi);
+                e_cam.push_back(cam_index.at(kf->camera_));
+                e_obs.insert(e_obs.end(), {undist_pt.x, undist_pt.y, -1.0f});
+                e_isq.push_back(1.0f);
+                e_delta.push_back(mkr->keep_fixed_ ? 0.0f : d2);
+                e_robust.push_back(0);
+                e_can_be_outlier.push_back(0);
+            }
+        }
+    }
     b200_lba_problem_t prob{};
-    prob.n_poses = static_cast<int32_t>(kfs.size()); prob.n_points = static_cast<int32_t>(lms.size());
+    prob.n_poses = static_cast<int32_t>(kfs.size()); prob.n_points = static_cast<int32_t>(points.size() / 3);
+    prob.point_fixed = point_fixed.data(); prob.e_robust = e_robust.data(); prob.e_can_be_outlier = e_can_be_outlier.data();
     prob.n_edges = static_cast<int32_t>(e_pose.size()); prob.n_cams = static_cast<int32_t>(cams.size());
     prob.pose_cw = pose_cw.data(); prob.pose_fixed = pose_fixed.data(); prob.points = points.data();
     prob.e_pose = e_pose.data(); prob.e_point = e_point.data(); prob.e_cam = e_cam.data(); prob.e_obs = e_obs.data();
@@ -137,6 +180,7 @@ void local_bundle_adjuster_b200::optimize(data::map_database* map_db, const std:
     std::lock_guard<std::mutex> lock(data::map_database::mtx_database_);
     for (size_t e = 0; e < outlier.size(); ++e) {
         if (!outlier[e]) continue;
+        if (static_cast<size_t>(e_point[e]) >= n_landmark_points) continue;  // (marker corners are never flagged)
         const auto& kf = kfs[e_pose[e]];
         const auto& lm = lms[e_point[e]];
         if (lm->will_be_erased()) continue;
@@ -158,6 +202,14 @@ void local_bundle_adjuster_b200::optimize(data::map_database* map_db, const std:
         if (lms[l]->will_be_erased()) continue;
         lms[l]->set_pos_in_world(Vec3_t(points_out[3 * l], points_out[3 * l + 1], points_out[3 * l + 2]));
         lms[l]->update_mean_normal_and_obs_scale_variance();
+    }
+    for (const auto& mp : mkr_points) {  // :411-428 (a marker has its vertices iff it is listed in mkr_points: the mkr_has_vtx guard)
+        const auto& mkr = mp.first;
+        if (mkr->keep_fixed_ || !mkr->initialized_before_) continue;
+        for (size_t corner_idx = 0; corner_idx < 4 && corner_idx < mkr->corners_pos_w_.size(); ++corner_idx) {
+            const size_t pi = mp.second + corner_idx;
+            mkr->corners_pos_w_[corner_idx] = Vec3_t(points_out[3 * pi], points_out[3 * pi + 1], points_out[3 * pi + 2]);
+        }
     }
 }
 

@@ -15,7 +15,7 @@ namespace optimize {
 class local_bundle_adjuster_b200 : public local_bundle_adjuster {
 public:
     explicit local_bundle_adjuster_b200(const YAML::Node& yaml_node, unsigned int num_first_iter = 5, unsigned int num_second_iter = 10);
-    ~local_bundle_adjuster_b200() override;
+    ~local_bundle_adjuster_b200();  // (the reference interface declares no virtual destructor)
     void optimize(data::map_database* map_db, const std::shared_ptr<data::keyframe>& curr_keyfrm, bool* const force_stop_flag) const override;
 
 private:

@@ -12,6 +12,9 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <cassert>
+#include <stdexcept>
+
 #include "b200vslam.h"
 
 namespace stella_vslam {

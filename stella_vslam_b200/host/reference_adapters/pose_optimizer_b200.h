@@ -14,6 +14,17 @@
 #ifndef STELLA_VSLAM_OPTIMIZE_POSE_OPTIMIZER_B200_H
 #define STELLA_VSLAM_OPTIMIZE_POSE_OPTIMIZER_B200_H
 
+#include <memory>
+#include <vector>
+
+// (optimize/pose_optimizer.h names data::landmark without declaring it; the reference's own backends are only ever included after a
+//  header that does)
+namespace stella_vslam {
+namespace data {
+class landmark;
+}  // namespace data
+}  // namespace stella_vslam
+
 #include "stella_vslam/optimize/pose_optimizer.h"
 
 struct b200_lba_s;
@@ -24,7 +35,7 @@ namespace optimize {
 class pose_optimizer_b200 : public pose_optimizer {
 public:
     explicit pose_optimizer_b200(unsigned int num_trials_robust = 2, unsigned int num_trials = 2, unsigned int num_each_iter = 10);
-    ~pose_optimizer_b200() override;
+    ~pose_optimizer_b200();  // (the reference interface declares no virtual destructor)
     unsigned int optimize(const data::frame& frm, Mat44_t& optimized_pose, std::vector<bool>& outlier_flags) const override;
     unsigned int optimize(const data::keyframe* keyfrm, Mat44_t& optimized_pose, std::vector<bool>& outlier_flags) const override;
     unsigned int optimize(const Mat44_t& cam_pose_cw, const data::frame_observation& frm_obs, const feature::orb_params* orb_params,

@@ -5,6 +5,8 @@
 #include "stella_vslam/data/keyframe.h"
 #include "stella_vslam/data/landmark.h"
 
+#include <stdexcept>
+
 #include "b200vslam.h"
 
 namespace stella_vslam {

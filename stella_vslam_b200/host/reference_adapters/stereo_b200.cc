@@ -10,6 +10,8 @@
 #include "stella_vslam/feature/orb_extractor.h"
 #include "stella_vslam/match/stereo.h"
 
+#include <stdexcept>
+
 #include "b200vslam.h"
 
 namespace stella_vslam {
