@@ -157,7 +157,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from stella_vslam_b200 import synth
+        from workloads import synth
     frames = synth.make_stream(8, W, H, stream=0)
     min_area = args.min_area or 7000
     # calibrate min_area with the oracle itself (no GPU code on this arm)
@@ -225,7 +225,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from stella_vslam_b200 import _lib, feature, multi_gpu, synth
+    from stella_vslam_b200 import _lib, feature, multi_gpu
+    from workloads import synth
     from stella_vslam_b200._lib import check, lib, ptr
     L = lib()
     B = args.batch

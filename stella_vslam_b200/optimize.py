@@ -218,17 +218,3 @@ def create(yaml_node=None, device=0):
     if backend != "b200":
         raise RuntimeError(f"Invalid backend: {backend}")
     return local_bundle_adjuster(node.get("num_first_iter", 5), node.get("num_second_iter", 10), device)
-
-
-def _smoke(O):
-    """Used by __graft_entry__.smoke(): small stereo window, CUDA vs oracle."""
-    from . import synth
-    pr = synth.make_ba_problem(10, 3, 400, seed=5, model="stereo")
-    ref = O.lba_solve(pr)
-    ba = local_bundle_adjuster()
-    got = ba.optimize(pr)
-    assert got["iterations"] == ref["iterations"], (got["iterations"], ref["iterations"])
-    assert np.array_equal(got["outliers"], ref["outliers"])
-    scale = np.abs(ref["points"]).max()
-    assert np.abs(got["points"] - ref["points"]).max() <= 1e-5 * scale
-    assert np.abs(got["pose_cw"] - ref["pose_cw"]).max() <= 1e-5 * np.abs(ref["pose_cw"]).max()

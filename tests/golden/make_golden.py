@@ -26,7 +26,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-from stella_vslam_b200 import synth  # noqa: E402
+from workloads import synth  # noqa: E402
 
 f32 = np.float32
 

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle as O
-from stella_vslam_b200 import synth
+from workloads import synth
 
 KITTI = dict(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, fxb=386.1448, cols=1241, rows=376)
 LOG_SF = np.float32(np.log(np.float32(1.2)))

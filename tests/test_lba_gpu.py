@@ -12,7 +12,8 @@ REL = 1e-5
 @pytest.fixture(scope="module")
 def mods():
     from oracle import pyoracle as O
-    from stella_vslam_b200 import optimize, synth
+    from stella_vslam_b200 import optimize
+    from workloads import synth
     return O, optimize, synth
 
 

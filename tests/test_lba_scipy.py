@@ -16,7 +16,7 @@ from scipy.optimize import least_squares
 from scipy.spatial.transform import Rotation as R
 
 from oracle import pyoracle as O
-from stella_vslam_b200 import synth
+from workloads import synth
 
 
 class Problem:

@@ -10,7 +10,8 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def mods():
     from oracle import pyoracle as O
-    from stella_vslam_b200 import match, synth
+    from stella_vslam_b200 import match
+    from workloads import synth
     return O, match, synth
 
 

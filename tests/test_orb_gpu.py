@@ -15,7 +15,8 @@ FIELDS = ("x", "y", "size", "angle", "response", "octave")
 @pytest.fixture(scope="module")
 def mods():
     from oracle import pyoracle as O
-    from stella_vslam_b200 import feature, synth
+    from stella_vslam_b200 import feature
+    from workloads import synth
     return O, feature, synth
 
 

@@ -7,7 +7,8 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle as O
-from stella_vslam_b200 import match, synth
+from stella_vslam_b200 import match
+from workloads import synth
 
 
 def _popcount(a, b):

@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle as O
-from stella_vslam_b200 import match, synth
+from stella_vslam_b200 import match
+from workloads import synth
 from stella_vslam_b200._lib import ERR_CAPACITY, B200Error
 
 pytestmark = pytest.mark.gpu

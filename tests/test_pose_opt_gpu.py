@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle as O
-from stella_vslam_b200 import optimize, synth
+from stella_vslam_b200 import optimize
+from workloads import synth
 
 pytestmark = pytest.mark.gpu
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle as O
-from stella_vslam_b200 import synth
+from workloads import synth
 
 FXB, BASELINE = 435.2 * 0.11, 0.11  # EuRoC-like focal_x_baseline / true_baseline -> max_disp = fx
 

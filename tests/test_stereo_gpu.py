@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from oracle import pyoracle as O
-from stella_vslam_b200 import feature, match, synth
+from stella_vslam_b200 import feature, match
+from workloads import synth
 
 pytestmark = pytest.mark.gpu
 FXB, BASELINE = 435.2 * 0.11, 0.11

@@ -1,7 +1,8 @@
 import sys, time
 sys.path.insert(0, ".")
 from concurrent.futures import ThreadPoolExecutor
-from stella_vslam_b200 import optimize, synth
+from stella_vslam_b200 import optimize
+from workloads import synth
 pr = synth.make_ba_problem(50, 10, 10000, seed=0, model="stereo")
 import os
 print('host loop' if os.environ.get('B200_LBA_HOST_LOOP') == '1' else 'graph')

@@ -1,7 +1,7 @@
 import ctypes as C, os, sys
 sys.path.insert(0, ".")
 import numpy as np
-from stella_vslam_b200 import synth
+from workloads import synth
 from stella_vslam_b200.optimize import pack_problem
 os.environ["B200_LBA_DEBUG"] = "1"
 L = C.CDLL(os.path.join(os.path.dirname(__file__), "libprobe.so"))

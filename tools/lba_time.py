@@ -5,7 +5,8 @@ import ctypes as C
 import sys, time
 sys.path.insert(0, ".")
 import numpy as np
-from stella_vslam_b200 import optimize, synth
+from stella_vslam_b200 import optimize
+from workloads import synth
 model = sys.argv[1] if len(sys.argv) > 1 else "stereo"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 batches = [int(x) for x in sys.argv[3:]] or [1, 4, 16, 32]

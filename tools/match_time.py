@@ -5,7 +5,8 @@ import time
 import numpy as np
 
 sys.path.insert(0, ".")
-from stella_vslam_b200 import match, synth  # noqa: E402
+from stella_vslam_b200 import match  # noqa: E402
+from workloads import synth  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 

@@ -3,7 +3,8 @@ import sys, time
 sys.path.insert(0, ".")
 import ctypes as C
 import numpy as np
-from stella_vslam_b200 import optimize, synth
+from stella_vslam_b200 import optimize
+from workloads import synth
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 probs = [synth.make_pose_problem(k, n_obs=1500, model="stereo") for k in range(8)] * (B // 8)
 po = optimize.pose_optimizer()
