@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lba", action="store_true")
+    ap.add_argument("--no-tracking", action="store_true", help="skip the second workload (device-resident track_local_map chain)")
     ap.add_argument("--lba-every", type=int, default=16, help="one local-BA window (50 keyframes / 10k landmarks) per this many frames")
     return ap.parse_args()
 
@@ -454,6 +455,12 @@ def main():
             lba_kernel_ms.append((v_.value, n_.value))
         lba_iters = sum(prep16["st"][0].iterations)
 
+    # ---- second workload ("tracking step", rank 0): the device-resident chain undistort -> can_observe -> projection match -> pose
+    #      optimisation (b200_track_local_map) over the B frames the extractor has just left in HBM, one synthetic local map per frame
+    tracking = None
+    if not args.no_tracking and rank == 0:
+        tracking = tracking_workload(ex, sets[(step_no[0] - 1) & 1], B, W, H, stride, peak_for_tracking(), args)
+
     # ---- e2e: host buffers through the reference-facing C ABI calls ---------------------------------------------------
     cap = stride
     h_frames = _lib.pinned_empty((B, H, W), np.uint8)
@@ -643,11 +650,84 @@ def main():
         "cpu_baseline_1thread": cpu1,
         "cv2_orb_stage_1thread": cv2_stage,
         "stage_ms": {n_: stage_ms[i] for i, n_ in enumerate(names + ["extract_total"])},
+        "tracking": tracking,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def peak_for_tracking():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("hbm_gbs", 6650.0))
+    except Exception:
+        return 6650.0
+
+
+def tracking_workload(ex, last, B, W, H, stride, peak_gbs, args):
+    """frames/s of tracking_module::track_local_map's GPU-shaped part (search_local_landmarks + pose optimisation) for B frames whose
+    keypoints never leave the GPU.  The local map of every frame is synthetic (workloads/synth.py::make_tracking_frame) and lives in host
+    buffers -- the reference's map database does -- so every call uploads it and downloads the results: that IS the end-to-end call."""
+    from oracle import pyoracle as O          # cpu_baseline leg only
+    from stella_vslam_b200 import _lib, tracking
+    from workloads import synth
+    cam = dict(model="perspective", fx=1000.0, fy=1000.0, cx=W / 2.0, cy=H / 2.0, fxb=0.0, cols=float(W), rows=float(H), setup="monocular")
+    counts = last.counts[1:].cpu().numpy()
+    kps_all = np.ascontiguousarray(last.kps[1:].cpu().numpy()).view(_lib.KP_DTYPE).reshape(B, stride)
+    desc_all = last.desc[1:].cpu().numpy()
+    frames = [dict(synth.make_tracking_frame(kps_all[f, :counts[f]], desc_all[f, :counts[f]], cam, ex.orb_params_.scale_factors_, seed=900 + f,
+                                             pre_matched_frac=0.0), frame=f, kp_landmark=None) for f in range(B)]
+    tr = tracking.local_map_tracker(ex, cam)
+    packed = tr.pack(frames, stride)
+    for _ in range(3):
+        tr.run_packed(packed)
+    walls, stages = [], []
+    for _ in range(max(5, args.steps // 2)):
+        t0 = time.perf_counter()
+        tr.run_packed(packed)
+        walls.append(time.perf_counter() - t0)
+        stages.append(tr.stage_ms())
+    wall = float(np.median(walls))
+    st = {k: float(np.median([s_[k] for s_ in stages])) for k in stages[0]}
+    n_lm = float(np.mean([len(fr["landmarks"]["pos_w"]) for fr in frames]))
+    n_kp = float(counts.mean())
+    n_match = float(np.mean([T.n_matches for T in packed[0]]))
+    n_valid = float(np.mean([T.n_valid for T in packed[0]]))
+    h2d = int(sum(len(fr["landmarks"]["pos_w"]) * (24 + 24 + 4 + 4 + 32 + 2) for fr in frames))
+    d2h = int(sum(len(fr["landmarks"]["pos_w"]) * (1 + 4) for fr in frames) + B * (stride * 5 + 16 * 8 + 24))
+    # compulsory bytes per frame of every stage (inputs once + outputs once)
+    alg = {"undistort_observe": n_kp * (24 + 24 + 9) + n_lm * (56 + 2 + 21), "grid": n_kp * (8 + 4) + 64 * 48 * 8,
+           "candidates": n_lm * (32 + 18) + n_kp * (32 + 9) + n_match * 8, "resolve": n_lm * (8 + 4) + n_kp,
+           "edges": n_lm * 4 + n_kp * (24 + 4 + 1) + (n_match) * (48 + 4 + 24), "pose_optimize": n_match * (48 + 2)}
+    kern = {k: {"ms_per_step": st[k], "alg_bytes_per_unit": float(v), "units_per_launch": B,
+                "achieved_gbs": v * B / (st[k] * 1e-3) / 1e9 if st[k] > 0 else 0.0} for k, v in alg.items()}
+    for k in kern:
+        kern[k]["frac"] = kern[k]["achieved_gbs"] / peak_gbs
+    dom = max(kern, key=lambda k_: kern[k_]["ms_per_step"])
+    # CPU baseline: the oracle's stage-by-stage composition on one thread, a few frames
+    t0, n_cpu = time.perf_counter(), 0
+    prm = ex.orb_params_
+    while n_cpu < min(B, 4) or (time.perf_counter() - t0 < 3.0 and n_cpu < B):
+        fr = frames[n_cpu]
+        ref = O.track_local_map(cam, kps_all[n_cpu, :counts[n_cpu]], desc_all[n_cpu, :counts[n_cpu]], fr, prm.scale_factors_, prm.inv_level_sigma_sq_,
+                                prm.log_scale_factor_)
+        assert ref["n_matches"] == packed[0][n_cpu].n_matches and ref["n_valid"] == packed[0][n_cpu].n_valid, "tracking chain disagrees with the oracle"
+        n_cpu += 1
+    cpu_fps = n_cpu / (time.perf_counter() - t0)
+    return {"metric": "frames/sec (track_local_map: undistort + can_observe + projection match + pose optimisation) @1920x1080, 2000 kpts",
+            "value": B / (st["chain"] * 1e-3), "unit": "frames/s", "ms_per_step": st["chain"],
+            "config": {"workload": f"{B} frames device-resident after extraction, one local map of ~{n_lm:.0f} landmarks per frame (host buffers)",
+                       "keypoints_per_frame_mean": n_kp, "landmarks_per_frame_mean": n_lm, "matches_per_frame_mean": n_match,
+                       "inliers_per_frame_mean": n_valid, "launches_per_step": 9},
+            "e2e": {"value": B / wall, "unit": "frames/s", "ms_per_step": 1e3 * wall, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "stage_ms": st,
+            "roofline": {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s", "frac": kern[dom]["frac"],
+                         "traffic": None, "kernels": kern,
+                         "note": "compulsory bytes (inputs once + outputs once); these kernels are latency-bound: one warp per frame in the sequential "
+                                 "resolve, one CTA per frame in the pose optimiser"},
+            "cpu_baseline_1thread": {"value": cpu_fps, "unit": "frames/s", "cores": 1, "kind": "port",
+                                     "sample": f"{n_cpu} frames through oracle.pyoracle.track_local_map (results checked against the GPU chain)"}}
 
 
 if __name__ == "__main__":

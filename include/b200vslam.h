@@ -147,6 +147,24 @@ int b200_convert_to_grayscale(b200_orb_t h, const uint8_t* src, int width, int h
 int b200_convert_to_grayscale_device(b200_orb_t h, const void* d_src, int width, int height, size_t src_pitch, size_t src_frame_stride,
                                      int channels, int rgb_order, void* d_gray, size_t gray_pitch, size_t gray_frame_stride, int batch);
 
+/* Keyframe serialisation: the byte layouts in which data::keyframe stores what the extractor produced.
+ *   SQLite (data/keyframe.cc:298-347 to_db, :191-235 from_stmt): `undist_keypts` = the std::vector<cv::KeyPoint> as raw bytes (28 bytes per
+ *       keypoint: pt.x, pt.y, size, angle, response, octave, class_id), `descs` = cv::Mat rows, 32 bytes each;
+ *   JSON / msgpack (data/common.cc:57-81): a descriptor = eight uint32 read through `desc.ptr<uint32_t>()` -- on a little-endian host the
+ *       same 32 bytes, so `desc_blob` viewed as uint32[n][8] is convert_descriptors_to_json's payload.
+ * Exports frame `frame` of the last extract straight from HBM: the keypoints are undistorted on the device when `cam` is given
+ * (camera::*::undistort_keypoints -- the keyframe stores undist_keypts_), re-packed to cv::KeyPoint records (class_id = -1, response = 0
+ * for perspective cameras as perspective.cc:266-272 leaves it) and copied out with the descriptors.  *n = keypoints of the frame;
+ * B200_ERR_CAPACITY if cap is too small. */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} b200_cv_keypoint_t;
+int b200_orb_export_keyframe_blobs(b200_orb_t h, int frame, const b200_camera_intrinsics_t* cam, b200_cv_keypoint_t* keypts_blob,
+                                   uint8_t* desc_blob, int cap, int32_t* n);
+/* The inverse for a keyframe loaded from a map file (host-only byte shuffling, no GPU work): cv::KeyPoint records -> b200_keypoint_t. */
+int b200_keyframe_blob_to_keypoints(const b200_cv_keypoint_t* keypts_blob, int n, b200_keypoint_t* keypts);
+
 /* Raw FAST corners (after NMS, threshold choice and mask tests, before distribute_keypoints) of the first n frames of the last extract:
  * the candidate count of orb_extractor.cc:237-259, which prices the FAST and selection kernels.  Synchronises. */
 int b200_orb_raw_corner_counts(b200_orb_t h, int32_t* counts, int n);
@@ -404,6 +422,19 @@ int b200_lba_solve(b200_lba_t h, const b200_lba_problem_t* problem, int iters1, 
 int b200_lba_solve_batch(b200_lba_t h, int n_windows, const b200_lba_problem_t* problems, int iters1, int iters2,
                          volatile uint8_t* const* force_stop, double* const* pose_cw_out, double* const* points_out,
                          uint8_t* const* outlier_out, b200_lba_stats_t* stats, int32_t* status);
+/* optimize::global_bundle_adjuster (src/stella_vslam/optimize/global_bundle_adjuster.cc: optimize_impl :26-192, optimize :258-420,
+ * optimize_for_initialization :201-256; called by module/loop_bundle_adjuster.cc:54 and module/initializer.cc:281): the same flattened
+ * problem and kernels as the local bundle adjuster, ONE Levenberg-Marquardt round of `num_iter` iterations (global_bundle_adjuster.h:20-23:
+ * 10) with the terminate action at `gain_threshold` (1e-3 in optimize(), the caller's value in optimize_for_initialization), no outlier
+ * pass.  Every keyframe of the map is free except the spanning root (:80-81), so the reduced system has 6 x (keyframes - 1) unknowns: up
+ * to 1000 it is factored on chip like a local window; beyond that (limit 4000 free keyframes) the dense Cholesky runs panel by panel over
+ * the whole GPU from HBM -- two launches per 24 columns -- where the reference uses g2o's CSparse solver (:42-45).
+ * use_huber_kernel is the per-edge e_robust array (NULL = Huber on every edge); marker corners as in b200_lba_problem_t.
+ * Returns B200_ERR_ABORTED when the CALLER raised *force_stop (the reference returns false then, :340-342, and uses no result: the
+ * output buffers are unspecified); a stop
+ * by the gain threshold also sets the flag (terminate_action.cc:66-70) but is a normal return. */
+int b200_global_ba_solve(b200_lba_t h, const b200_lba_problem_t* problem, int num_iter, double gain_threshold, volatile uint8_t* force_stop,
+                         double* pose_cw_out, double* points_out, b200_lba_stats_t* stats);
 /* optimize::pose_optimizer::optimize  (src/stella_vslam/optimize/pose_optimizer.h:24-40, pose_optimizer_g2o.cc:38-175; factory
  * defaults num_trials_robust = 2, num_trials = 2, num_each_iter = 10, pose_optimizer_factory.h:18-47): motion-only bundle adjustment
  * of `n_problems` frames in one launch.  Each problem uses the b200_lba_problem_t layout with exactly ONE pose (free), the landmarks
@@ -413,6 +444,69 @@ int b200_lba_solve_batch(b200_lba_t h, int n_windows, const b200_lba_problem_t* 
  * outlier_flags = the problems' edges concatenated (outlier_flags.at(idx), :141-160), n_valid[p] = num_init_obs - num_bad_obs. */
 int b200_pose_optimize(b200_lba_t h, int n_problems, const b200_lba_problem_t* problems, int num_trials_robust, int num_trials,
                        int num_each_iter, double* pose_cw_out, uint8_t* outlier_flags, uint32_t* n_valid);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Device-resident tracking chain: the per-frame steady state of tracking_module::track_local_map for `n_frames` independent
+ * frames (one per camera / session / replayed log) in ONE launch sequence, reading the extractor's results where they lie
+ * in HBM -- nothing of the frame goes back to the host between the stages:
+ *   camera::*::undistort_keypoints            camera/perspective.cc:245-275 (frame construction, system.cc:386-395)
+ *   tracking_module::search_local_landmarks   tracking_module.cc:533-606: data::frame::can_observe (data/frame.cc:59-84) over the local
+ *                                             landmarks, then projection::match_frame_and_landmarks (match/projection.cc:13-93) with
+ *                                             lowe_ratio 0.8 and the margin the caller chose (:599-603), HAMMING_DIST_THR_HIGH
+ *   pose_optimizer::optimize                  optimize/pose_optimizer_g2o.cc:38-175 on the landmarks the frame now carries
+ *                                             (tracking_module::optimize_current_frame_with_local_map)
+ * Frame f is frame `frames[f].frame` of the LAST extract on `orb` (host- or device-image variant).  The landmark table of a frame
+ * lists, in the reference's iteration order, every landmark the stage touches: the local landmarks AND the landmarks the frame
+ * already carries (those with lm_skip = 1: tracking_module.cc:536-551 puts them into curr_landmark_ids and :561-563 skips them).
+ * All pointers are HOST buffers; they go up in one copy and the results come back in one copy.  The three handles' arenas are used
+ * and everything is enqueued on the extractor's stream; the call returns when the results are in the caller's buffers.
+ * Bit-exact against the stage-by-stage host ABI (b200_keypoints_undistort, b200_frame_can_observe, b200_match_guided mode 0) and
+ * within 1e-5 for the pose (b200_pose_optimize): same kernels / same device functions. */
+typedef struct b200_track_params {
+    b200_camera_intrinsics_t cam;
+    double focal_x_baseline;       /* camera::base::focal_x_baseline_ (0 for monocular) */
+    int32_t monocular;             /* setup_type_ == Monocular: edge threshold sqrt(chi2_2D), else sqrt(chi2_3D) (pose_optimizer_g2o.cc:84-88) */
+    float img_bounds[4];           /* min_x, max_x, min_y, max_y */
+    int32_t grid_cols, grid_rows;  /* 64 x 48 */
+    uint32_t num_levels;
+    float log_scale_factor;
+    const float* scale_factors;        /* num_levels */
+    const float* inv_level_sigma_sq;   /* num_levels */
+    float margin;                  /* margin_local_map_projection_(_unstable_) */
+    float lowe_ratio;              /* 0.8 (tracking_module.cc:599) */
+    uint32_t hamming_thr;          /* HAMMING_DIST_THR_HIGH = 100 */
+    float ray_cos_thr;             /* 0.5 (tracking_module.cc:588) */
+    int32_t num_trials_robust, num_trials, num_each_iter; /* 2 / 2 / 10 */
+    int32_t max_candidates;        /* 0 = 256 keypoints per search window */
+} b200_track_params_t;
+typedef struct b200_track_frame {
+    int32_t frame;                     /* index into the extractor's last batch */
+    const double* pose_cw;             /* 16, row-major: curr_frm_.pose_cw_ entering the stage */
+    int32_t n_keypoints_in;            /* entries of kp_x_right / kp_landmark (0 when both are NULL); must equal the frame's keypoint count */
+    const float* kp_x_right;           /* frm_obs_.stereo_x_right_, NULL when empty */
+    const int32_t* kp_landmark;        /* per keypoint: row of the landmark it already carries (not will_be_erased), -1 none; NULL = none */
+    int32_t n_landmarks;
+    const double* lm_pos_w;            /* 3 per landmark */
+    const double* lm_mean_normal;      /* 3 per landmark */
+    const float* lm_min_valid_dist;
+    const float* lm_max_valid_dist;
+    const uint8_t* lm_desc;            /* 32 per landmark */
+    const uint8_t* lm_skip;            /* 1 = not searched (already in the frame, will_be_erased, temporal-ratio test :565-585); NULL = none */
+    const uint8_t* lm_has_observation; /* landmark::has_observation(); NULL = all have */
+    int32_t kp_cap;                    /* capacity of kp_landmark_out / kp_outlier (>= the frame's keypoint count) */
+    uint8_t* lm_observable;            /* out, n_landmarks: searched and can_observe() held (the caller's increase_num_observable, :594) */
+    int32_t* kp_landmark_out;          /* out, per keypoint: landmark row after the search (frm.add_landmark applied in order), -1 none */
+    uint8_t* kp_outlier;               /* out, per keypoint: outlier_flags of the pose optimisation */
+    double pose_cw_out[16];            /* out (the input pose when fewer than 5 observations, :116-118) */
+    int32_t n_keypoints;               /* out */
+    int32_t n_matches;                 /* out: return value of match_frame_and_landmarks */
+    uint32_t n_valid;                  /* out: return value of pose_optimizer::optimize */
+} b200_track_frame_t;
+int b200_track_local_map(b200_orb_t orb, b200_matcher_t matcher, b200_lba_t opt, const b200_track_params_t* prm, int n_frames,
+                         b200_track_frame_t* frames);
+/* Device time of the last b200_track_local_map, per stage: 0 undistort + can_observe + query build, 1 grid, 2 candidates, 3 resolve,
+ * 4 edge build, 5 pose optimisation + scatter, 6 whole chain (CUDA events on the stream). */
+int b200_track_stage_ms(b200_matcher_t matcher, int stage, float* ms);
 
 /* Profiling mode: an event after every launch of the following solves (adds a few microseconds per launch; off by default).
  * b200_lba_kernel_ms reports, for the LAST batch, the summed device time and the number of intervals of

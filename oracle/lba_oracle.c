@@ -405,6 +405,7 @@ static void apply_update(lba_t* S) {
 
 /* SparseOptimizer::optimize(n) with OptimizationAlgorithmLevenberg + terminate_action (terminate_action.cc:36-76).
  * Returns the number of iterations run. */
+static double g_gain_thr = 1e-3; /* terminate_action::setGainThreshold; 1e-3 everywhere except optimize_for_initialization */
 static int optimize_rounds(lba_t* S, int iterations, volatile uint8_t* stop, orc_lba_stats_t* st, int round) {
     const orc_lba_problem_t* P = S->P;
     uint8_t aux_stop = 0;
@@ -474,7 +475,7 @@ static int optimize_rounds(lba_t* S, int iterations, volatile uint8_t* stop, orc
         } else {
             const double gain = (last_chi - chi) / chi;
             last_chi = chi;
-            if (gain >= 0 && gain < 1e-3) *flag = 1; /* setOptimizerStopFlag: writes the caller's force-stop flag */
+            if (gain >= 0 && gain < g_gain_thr) *flag = 1; /* setOptimizerStopFlag: writes the caller's force-stop flag */
         }
         if (st) {
             st->chi2[round] = chi;
@@ -570,6 +571,40 @@ int orc_lba_solve(const orc_lba_problem_t* P, int iters1, int iters2, volatile u
     }
     if (stats) stats->n_outliers = n_out;
     /* 8. write-back (:393-409): to_eigen_mat(SE3Quat) */
+    for (int k = 0; k < K; ++k) {
+        double* M = pose_cw_out + 16 * k;
+        if (P->pose_fixed[k]) {
+            memcpy(M, P->pose_cw + 16 * k, sizeof(double) * 16);
+            continue;
+        }
+        double R[9];
+        quat_to_rot(S.q + 4 * k, R);
+        M[0] = R[0]; M[1] = R[1]; M[2] = R[2]; M[3] = S.t[3 * k];
+        M[4] = R[3]; M[5] = R[4]; M[6] = R[5]; M[7] = S.t[3 * k + 1];
+        M[8] = R[6]; M[9] = R[7]; M[10] = R[8]; M[11] = S.t[3 * k + 2];
+        M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
+    }
+    memcpy(points_out, S.pts, sizeof(double) * 3 * L);
+    state_free(&S);
+    return 0;
+}
+
+/* optimize::global_bundle_adjuster (src/stella_vslam/optimize/global_bundle_adjuster.cc:26-192 optimize_impl, :258-420 optimize,
+ * :201-256 optimize_for_initialization) on a flattened problem: the same vertices and reprojection edges as the local bundle adjuster
+ * (every keyframe free except the spanning root, Huber on landmark edges when use_huber_kernel), ONE optimize(num_iter) with the
+ * terminate action at `gain_threshold` (1e-3 in optimize(), the caller's value in optimize_for_initialization), no outlier pass.
+ * g2o's LinearSolverCSparse there vs the dense Cholesky here: the same normal equations, the same solution up to rounding.
+ * Returns 1 when aborted by the caller's flag (:340-342: set and not by the terminate action), else 0. */
+int orc_global_ba_solve(const orc_lba_problem_t* P, int num_iter, double gain_threshold, volatile uint8_t* force_stop, double* pose_cw_out,
+                        double* points_out, orc_lba_stats_t* stats) {
+    lba_t S;
+    state_init(&S, P);
+    const int K = P->n_poses, L = P->n_points;
+    if (stats) memset(stats, 0, sizeof(*stats));
+    g_gain_thr = gain_threshold;
+    const int n1 = optimize_rounds(&S, num_iter, force_stop, stats, 0);
+    g_gain_thr = 1e-3;
+    if (stats) stats->iterations[0] = n1;
     for (int k = 0; k < K; ++k) {
         double* M = pose_cw_out + 16 * k;
         if (P->pose_fixed[k]) {

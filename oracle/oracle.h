@@ -187,6 +187,8 @@ typedef struct {
  * Returns 0, or 1 when *force_stop was already set (no write-back, :308-310). */
 int orc_lba_solve(const orc_lba_problem_t* P, int iters1, int iters2, volatile uint8_t* force_stop, double* pose_cw_out,
                   double* points_out, uint8_t* outlier_out, orc_lba_stats_t* stats);
+int orc_global_ba_solve(const orc_lba_problem_t* P, int num_iter, double gain_threshold, volatile uint8_t* force_stop, double* pose_cw_out,
+                        double* points_out, orc_lba_stats_t* stats);
 
 /* optimize::pose_optimizer_g2o::optimize (pose_optimizer_g2o.cc:38-175): motion-only BA of one frame.  P: one free pose, fixed
  * points, one edge per observation.  Returns the number of inlier observations; outlier_flags[e] per edge. */

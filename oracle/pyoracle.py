@@ -380,6 +380,18 @@ def lba_solve(prob, iters1=5, iters2=10, force_stop=None):
                 chi2=list(st.chi2), lambda_init=st.lambda_init, lambda_final=list(st.lambda_final))
 
 
+def global_ba_solve(prob, num_iter=10, gain_threshold=1e-3, force_stop=None):
+    """global_bundle_adjuster::optimize / optimize_for_initialization on the CPU oracle (one LM round, no outlier pass)."""
+    L_ = lib()
+    L_.orc_global_ba_solve.argtypes = [C.POINTER(LbaProblem), C.c_int, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(LbaStats)]
+    P, keep = pack_lba_problem(prob)
+    pose_out, pts_out = np.zeros((P.n_poses, 4, 4)), np.zeros((P.n_points, 3))
+    st = LbaStats()
+    rc = L_.orc_global_ba_solve(C.byref(P), int(num_iter), float(gain_threshold), _p(force_stop), _p(pose_out), _p(pts_out), C.byref(st))
+    return dict(rc=rc, pose_cw=pose_out, points=pts_out, iterations=st.iterations[0], chi2=st.chi2[0], lambda_init=st.lambda_init,
+                lambda_final=st.lambda_final[0])
+
+
 def pose_optimize(prob, num_trials_robust=2, num_trials=2, num_each_iter=10):
     """orc_pose_optimize on a flattened frame (synth.make_pose_problem).  Returns (num_valid_obs, pose (4,4), outlier_flags bool)."""
     P, keep = pack_lba_problem(prob)
@@ -478,3 +490,57 @@ def convert_to_grayscale(img, in_color_order="BGR"):
     L.orc_convert_to_grayscale.restype = None
     L.orc_convert_to_grayscale(_p(img), w, h, img.strides[0], c, 1 if in_color_order == "RGB" else 0, _p(out), out.strides[0])
     return out
+
+
+def track_local_map(camera, kps, desc, frame, scale_factors, inv_level_sigma_sq, log_scale_factor, margin=5.0, lowe_ratio=0.8, thr=100,
+                    ray_cos_thr=0.5, img_bounds=None, grid=(64, 48), monocular=True, num_trials_robust=2, num_trials=2, num_each_iter=10):
+    """The per-frame steady state of tracking_module::track_local_map, stage by stage with the oracle's functions:
+    undistort_keypoints (perspective.cc:245-275) -> search_local_landmarks (tracking_module.cc:533-606: can_observe over the local
+    landmarks, projection::match_frame_and_landmarks projection.cc:13-93) -> pose_optimizer::optimize (pose_optimizer_g2o.cc:38-175).
+    kps / desc: the frame's (distorted) keypoints and descriptors; frame: dict(pose_cw, landmarks, [kp_x_right], [kp_landmark]) as
+    stella_vslam_b200.tracking.local_map_tracker.pack takes it.  Returns the same dict as local_map_tracker.track."""
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    n_kp = len(kps)
+    lm = frame["landmarks"]
+    n_lm = len(np.asarray(lm["pos_w"]).reshape(-1, 3))
+    sf = np.asarray(scale_factors, np.float32)
+    num_levels = len(sf)
+    und, _ = undistort_keypoints(camera, kps)
+    g = lambda k: float(camera.get(k, 0.0))
+    bounds = img_bounds if img_bounds is not None else (0.0, g("cols"), 0.0, g("rows"))
+    co = can_observe(camera, frame["pose_cw"], lm, ray_cos_thr, bounds, num_levels, log_scale_factor)
+    skip = np.zeros(n_lm, bool) if lm.get("skip") is None else np.asarray(lm["skip"]).astype(bool)
+    has_obs = np.ones(n_lm, bool) if lm.get("has_observation") is None else np.asarray(lm["has_observation"]).astype(bool)
+    observable = co["observable"] & ~skip
+    kp_lm = np.full(n_kp, -1, np.int32) if frame.get("kp_landmark") is None else np.asarray(frame["kp_landmark"], np.int32).copy()
+    occupied = np.array([(l >= 0 and has_obs[l]) for l in kp_lm], np.uint8)          # `lm && lm->has_observation()` (projection.cc:50-53)
+    lvl = co["pred_scale_level"].astype(np.int64)
+    pr = dict(t_x=und["x"], t_y=und["y"], t_octave=und["octave"].astype(np.uint8), t_desc=np.ascontiguousarray(desc, np.uint8),
+              t_x_right=frame.get("kp_x_right"), t_occupied=occupied, bounds=bounds, grid=grid,
+              q_desc=np.ascontiguousarray(lm["desc"], np.uint8), q_x=co["reproj"][:, 0].astype(np.float32), q_y=co["reproj"][:, 1].astype(np.float32),
+              q_margin=np.float32(margin) * sf[lvl], q_min_level=np.maximum(0, lvl - 1), q_max_level=np.minimum(num_levels - 1, lvl + 1),
+              q_x_right=co["x_right"], q_valid=observable.astype(np.uint8), q_has_observation=has_obs.astype(np.uint8))
+    match_out, _, n_matches = match_guided(pr, 0, thr=thr, lowe_ratio=lowe_ratio, check_orientation=False)
+    for q in range(n_lm):                                   # frm.add_landmark(local_lm, best_idx) in iteration order (projection.cc:87)
+        if match_out[q] >= 0:
+            kp_lm[match_out[q]] = q
+    idx = np.nonzero(kp_lm >= 0)[0]                         # one edge per keypoint with a landmark, keypoint order (pose_optimizer_g2o.cc:88-111)
+    xr = np.full(n_kp, -1.0, np.float32) if frame.get("kp_x_right") is None else np.asarray(frame["kp_x_right"], np.float32)
+    isig = np.asarray(inv_level_sigma_sq, np.float32)
+    chi = np.float32(np.sqrt(np.float32(5.99146))) if monocular else np.float32(np.sqrt(np.float32(7.81473)))
+    pos = np.asarray(lm["pos_w"], np.float64).reshape(-1, 3)
+    cam = dict(model=1 if camera.get("model", "perspective") == "equirectangular" else 0, fx=g("fx"), fy=g("fy"), cx=g("cx"), cy=g("cy"),
+               fxb=g("fxb"), cols=g("cols"), rows=g("rows"))
+    ne = len(idx)
+    pp = dict(pose_cw=np.asarray(frame["pose_cw"], np.float64).reshape(1, 4, 4), pose_fixed=np.zeros(1, np.uint8), points=pos[kp_lm[idx]].reshape(-1, 3),
+              point_fixed=np.ones(ne, np.uint8), e_pose=np.zeros(ne, np.int32), e_point=np.arange(ne, dtype=np.int32), e_cam=np.zeros(ne, np.uint8),
+              e_obs=np.stack([und["x"][idx], und["y"][idx], xr[idx]], 1).astype(np.float32), e_inv_sigma_sq=isig[und["octave"][idx].astype(np.int64)],
+              e_delta=np.full(ne, chi, np.float32), e_robust=None, e_can_be_outlier=None, cams=[cam])
+    outlier = np.zeros(n_kp, bool)
+    if ne >= 5:
+        n_valid, pose, flags = pose_optimize(pp, num_trials_robust, num_trials, num_each_iter)
+        outlier[idx] = flags
+    else:
+        n_valid, pose = 0, np.asarray(frame["pose_cw"], np.float64).reshape(4, 4).copy()
+    return dict(observable=observable, kp_landmark=kp_lm, kp_outlier=outlier, pose_cw=pose, n_matches=int(n_matches), n_valid=int(n_valid),
+                n_keypoints=n_kp)

@@ -28,6 +28,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "track_chain.cuh"
 
 namespace b200 {
 namespace lba {
@@ -207,6 +208,7 @@ struct LmCtl {
     double lambda, ni, current_chi, last_chi, rho;
     double lambda_init, chi2[2], lambda_final[2];
     int cur, it, iterations, qmax, ok, stop_flag, round, skip_round2;
+    double gain_thr;  // terminate_action::setGainThreshold (1e-3 for local / global BA; the initializer passes its own)
     int outer_go;    // the window still iterates in this round
     int need_build;  // the next repetition starts with buildSystem (0 after a rejected trial: H and b are unchanged)
     int iters_done[2];
@@ -270,6 +272,7 @@ struct WinDev {
     double* chi[2];
     double *Hpl, *Hll, *bl, *Dinv, *Hpp, *bp, *M, *xp;
     double *r_chi, *r_diag, *r_scale, *r_result;
+    double *gP, *gD, *ginvd;  // reduced systems too large for the on-chip panel (global BA): panel (kNB x mp), diagonal block, 1 / L[j][j]
     int* fail;       // (zeroed) the linear solve of the current trial failed
     int* tickets;    // (zeroed) 2 "last CTA" tickets
     int* bad_input;  // (zeroed) 1 + index of the first edge with an invalid vertex / camera reference
@@ -585,12 +588,13 @@ __device__ void compute_dinv(const WinDev& W, double lambda) {
 
 // start of SparseOptimizer::optimize(iterations): terminate_action at iteration -1 resets the stop flag (terminate_action.cc:46-51).
 // One thread per window.
-__global__ void lm_round_begin_kernel(const WinDev* __restrict__ wins, int n_windows, int iterations, int round) {
+__global__ void lm_round_begin_kernel(const WinDev* __restrict__ wins, int n_windows, int iterations, int round, double gain_thr) {
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= n_windows) return;
     LmCtl* c = wins[w].ctl;
     c->round = round;
     c->iterations = iterations;
+    c->gain_thr = gain_thr;
     c->iters_done[round] = 0;
     c->need_build = 1;
     if (*wins[w].bad_input) {
@@ -682,7 +686,7 @@ __device__ void lm_after_trial(const WinDev& W, double* stage) {
             } else {
                 const double gain = (c->last_chi - chi_now) / chi_now;
                 c->last_chi = chi_now;
-                if (gain >= 0 && gain < 1e-3) c->stop_flag = 1;
+                if (gain >= 0 && gain < c->gain_thr) c->stop_flag = 1;
             }
             c->chi2[c->round] = chi_now;
             c->lambda_final[c->round] = c->lambda;
@@ -1447,6 +1451,215 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(const WinDev* 
     }
 }
 
+// ---- reduced systems beyond the on-chip panel (n > kCholOnChipMax: global bundle adjustment, global_bundle_adjuster.cc:42-45) ----
+// The same blocked right-looking factorisation, one panel = two launches over the whole chip instead of one cluster:
+//   gchol_panel_kernel : every CTA factors the (tiny) diagonal block itself, solves its 256 rows of the panel, writes them
+//                        transposed into the window's global panel buffer gP (L2 resident: kNB x n doubles)
+//   gchol_trail_kernel : rank-kNB update of the trailing matrix with 4x4 register tiles read from gP, and the write-back of the
+//                        panel's factor into M (columns the update does not touch)
+// and gchol_finish_kernel (one CTA): backward solve in global memory, computeScale's pose part, trial keyframe states.
+constexpr int kCholOnChipMax = 1000;
+constexpr int kCholGlobalMax = 24000;  // (n + 1)^2 doubles = 4.6 GB of the 180 GB
+constexpr int kGcholThreads = 256;
+__global__ void __launch_bounds__(kGcholThreads) gchol_panel_kernel(const WinDev* __restrict__ wins, int kb) {
+    const WinDev& W = wins[blockIdx.y];
+    const LmCtl* __restrict__ ctl = W.ctl;
+    const int n = W.n, ld = W.ld;
+    if (!ctl->outer_go || kb >= n || *W.fail) return;
+    const int nb = min(kNB, n - kb), r0 = kb + nb, m = n + 1 - r0, mp = (n + 1 + 3) & ~3;
+    if ((int)blockIdx.x * kGcholThreads >= m + 4) return;
+    double* __restrict__ M = W.M;
+    __shared__ double D[kNB * (kNB + 1)];
+    __shared__ double invd[kNB];
+    __shared__ int bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    if (tid < 32) {
+        double r[kNB];
+#pragma unroll
+        for (int k = 0; k < kNB; ++k) r[k] = (tid < nb && k <= tid) ? M[(size_t)(kb + tid) * ld + kb + k] : ((k == tid) ? 1.0 : 0.0);
+        int b = 0;
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) {
+            const double djj = __shfl_sync(0xFFFFFFFFu, r[j], j);
+            b |= (!(djj > 0.0) || !isfinite(djj)) ? 1 : 0;
+            const double inv = rsqrt(djj), dd = djj * inv;
+            if (tid == 0) invd[j] = inv;
+            r[j] = (tid == j) ? dd : ((tid > j) ? r[j] * inv : r[j]);
+            const double mine = (tid > j) ? r[j] : 0.0;
+#pragma unroll
+            for (int k = j + 1; k < kNB; ++k) {
+                const double lkj = __shfl_sync(0xFFFFFFFFu, r[j], k);
+                r[k] = fma(-((tid >= k) ? mine : 0.0), lkj, r[k]);
+            }
+        }
+        if (tid < kNB) {
+#pragma unroll
+            for (int k = 0; k < kNB; ++k) D[tid * (kNB + 1) + k] = r[k];
+        }
+        if (tid == 0 && b) bad = 1;
+    }
+    __syncthreads();
+    if (bad) {  // (every CTA reaches the same verdict from the same numbers; the flag stops the remaining panels)
+        if (blockIdx.x == 0 && tid == 0) {
+            *W.fail = 1;
+            W.r_result[0] = 0.0;
+        }
+        return;
+    }
+    if (blockIdx.x == 0) {
+        for (int idx = tid; idx < kNB * (kNB + 1); idx += kGcholThreads) W.gD[idx] = D[idx];
+        if (tid < kNB && kb + tid < n) W.ginvd[kb + tid] = invd[tid];
+    }
+    const int t = blockIdx.x * kGcholThreads + tid;
+    if (t < m) {
+        const double* row = M + (size_t)(r0 + t) * ld + kb;
+        double x[kNB];
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) x[j] = (j < nb) ? row[j] : 0.0;
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) {
+            x[j] *= invd[j];
+#pragma unroll
+            for (int k = j + 1; k < kNB; ++k) x[k] = fma(-x[j], D[k * (kNB + 1) + j], x[k]);
+        }
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) W.gP[(size_t)j * mp + t] = x[j];
+    } else if (t < min(mp, m + 4)) {  // the <= 3 padding rows read by the last 4-row tile
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) W.gP[(size_t)j * mp + t] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(kGcholThreads) gchol_trail_kernel(const WinDev* __restrict__ wins, int kb) {
+    const WinDev& W = wins[blockIdx.y];
+    const LmCtl* __restrict__ ctl = W.ctl;
+    const int n = W.n, ld = W.ld;
+    if (!ctl->outer_go || kb >= n || *W.fail) return;
+    const int nb = min(kNB, n - kb), r0 = kb + nb, m = n + 1 - r0, mp = (n + 1 + 3) & ~3;
+    double* __restrict__ M = W.M;
+    const double* __restrict__ Pn = W.gP;
+    const long long gid = (long long)blockIdx.x * kGcholThreads + threadIdx.x;
+    const int tm = (m + 3) >> 2;
+    const long long n_tiles = (long long)tm * (tm + 1) / 2;
+    if (gid < n_tiles) {
+        int tr = (int)((sqrt(8.0 * (double)gid + 1.0) - 1.0) * 0.5);
+        while ((long long)(tr + 1) * (tr + 2) / 2 <= gid) ++tr;
+        while ((long long)tr * (tr + 1) / 2 > gid) --tr;
+        const int tc = (int)(gid - (long long)tr * (tr + 1) / 2);
+        double acc[16];
+#pragma unroll
+        for (int a = 0; a < 16; ++a) acc[a] = 0.0;
+        const int rb = tr * 4, cb = tc * 4;
+#pragma unroll 4
+        for (int k = 0; k < kNB; ++k) {
+            const double2* pa = reinterpret_cast<const double2*>(Pn + (size_t)k * mp + rb);
+            const double2* pb = reinterpret_cast<const double2*>(Pn + (size_t)k * mp + cb);
+            const double2 a0 = pa[0], a1 = pa[1], b0 = pb[0], b1 = pb[1];
+            const double a[4] = {a0.x, a0.y, a1.x, a1.y}, b[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int w2 = 0; w2 < 4; ++w2) acc[u * 4 + w2] = fma(a[u], b[w2], acc[u * 4 + w2]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int w2 = 0; w2 < 4; ++w2) {
+                const int r = rb + u, c = cb + w2;
+                if (r < m && c <= r && r0 + c < n) M[(size_t)(r0 + r) * ld + r0 + c] -= acc[u * 4 + w2];
+            }
+    }
+    // factor of this panel -> M (columns kb .. kb + nb, which the update above neither reads nor writes)
+    const long long wb = (long long)m * nb + (long long)nb * nb;
+    for (long long idx = gid; idx < wb; idx += (long long)gridDim.x * kGcholThreads) {
+        if (idx < (long long)nb * nb) {
+            const int i = (int)(idx / nb), j = (int)(idx - (long long)i * nb);
+            if (j <= i) M[(size_t)(kb + i) * ld + kb + j] = W.gD[i * (kNB + 1) + j];
+        } else {
+            const long long id2 = idx - (long long)nb * nb;
+            const int t = (int)(id2 / nb), j = (int)(id2 - (long long)t * nb);
+            M[(size_t)(r0 + t) * ld + kb + j] = Pn[(size_t)j * mp + t];
+        }
+    }
+}
+
+constexpr int kGfinThreads = 1024;
+__global__ void __launch_bounds__(kGfinThreads) gchol_finish_kernel(const WinDev* __restrict__ wins) {
+    const WinDev& W = wins[blockIdx.x];
+    const LmCtl* __restrict__ ctl = W.ctl;
+    if (!ctl->outer_go) return;
+    const int n = W.n, ld = W.ld, K = W.K;
+    const double* __restrict__ M = W.M;
+    double* __restrict__ xs = W.xp;  // the solution is built in place in global memory (one CTA; __syncthreads orders it)
+    const double* __restrict__ invd = W.ginvd;
+    __shared__ double D[kNB * (kNB + 1)];
+    __shared__ double sh[kGfinThreads];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int bad = *W.fail;
+    const double lambda = ctl->lambda;
+    if (!bad) {
+        for (int i = tid; i < n; i += nt) xs[i] = M[(size_t)n * ld + i];
+        __syncthreads();
+        for (int kb = ((n - 1) / kNB) * kNB; kb >= 0; kb -= kNB) {
+            const int nb = min(kNB, n - kb);
+            for (int idx = tid; idx < kNB * kNB; idx += nt) {
+                const int i = idx / kNB, j = idx - i * kNB;
+                D[i * (kNB + 1) + j] = (i < nb && j <= i) ? M[(size_t)(kb + i) * ld + kb + j] : 0.0;
+            }
+            __syncthreads();
+            if (tid < 32) {
+                double y = (tid < nb) ? xs[kb + tid] : 0.0;
+#pragma unroll
+                for (int j = kNB - 1; j >= 0; --j) {
+                    const double xj = __shfl_sync(0xFFFFFFFFu, y, j) * ((j < nb) ? invd[kb + j] : 0.0);
+                    if (tid == j) y = xj;
+                    else if (tid < j) y = fma(-D[j * (kNB + 1) + tid], xj, y);
+                }
+                if (tid < nb) xs[kb + tid] = y;
+            }
+            __syncthreads();
+            for (int i = tid; i < kb; i += nt) {
+                double sacc = xs[i];
+                for (int k = 0; k < nb; ++k) sacc = fma(-M[(size_t)(kb + k) * ld + i], xs[kb + k], sacc);
+                xs[i] = sacc;
+            }
+            __syncthreads();
+        }
+        double sc = 0.0;
+        for (int i = tid; i < n; i += nt) sc += xs[i] * (lambda * xs[i] + W.bp[i]);
+        const double tot = block_sum(sc, sh);
+        if (tid == 0) {
+            W.r_result[0] = 1.0;
+            W.r_result[1] = tot;
+        }
+    }
+    __syncthreads();
+    const int cur_idx = ctl->cur & 1;
+    const double* __restrict__ q_cur = W.q[cur_idx];
+    const double* __restrict__ t_cur = W.t[cur_idx];
+    double* __restrict__ q_new = W.q[cur_idx ^ 1];
+    double* __restrict__ t_new = W.t[cur_idx ^ 1];
+    double* __restrict__ Rt_new = W.Rt[cur_idx ^ 1];
+    for (int k = tid; k < K; k += nt) {
+        double qn[4], tn[3];
+        const int pc = W.pose_col[k];
+        if (pc >= 0 && !bad) {
+            se3_oplus(q_cur + 4 * k, t_cur + 3 * k, xs + 6 * pc, qn, tn);
+        } else {
+            for (int i = 0; i < 4; ++i) qn[i] = q_cur[4 * k + i];
+            for (int i = 0; i < 3; ++i) tn[i] = t_cur[3 * k + i];
+        }
+        for (int i = 0; i < 4; ++i) q_new[4 * k + i] = qn[i];
+        for (int i = 0; i < 3; ++i) t_new[3 * k + i] = tn[i];
+        double R[9];
+        quat_to_rot(qn, R);
+        for (int i = 0; i < 9; ++i) Rt_new[12 * k + i] = R[i];
+        for (int i = 0; i < 3; ++i) Rt_new[12 * k + 9 + i] = tn[i];
+    }
+}
+
 // K7: back-substitution x_l = Dinv (bl - sum_e Hpl(e)^T x_p), trial landmark, scale partials.  Eight lanes share a landmark
 //     (they split its edges), sixteen landmarks per 128-thread CTA.
 __global__ void __launch_bounds__(128) backsub_kernel(const WinDev* __restrict__ wins) {
@@ -1870,6 +2083,7 @@ struct Solver {
     int chol_cluster = kCholCluster;  // CTAs sharing one factorisation (B200_LBA_CLUSTER overrides: 1, 2, 4 or 8)
     bool chol_cluster_pinned = false;
     // Waiting for the stream (a few times per batch).  B200_LBA_WAIT=spin|block|yield|nap overrides.
+    bool last_gain_stop = false;  // the last window of the last batch ended on terminate_action's gain threshold
     int wait_mode = 3;  // 0 spin (cudaStreamSynchronize), 1 blocking event, 2 poll + sched_yield, 3 poll + 15 us sleep
     cudaError_t wait(cudaStream_t st) {
         if (wait_mode == 0) return cudaStreamSynchronize(st);
@@ -1947,13 +2161,13 @@ struct WinOff {
     size_t pt_cnt, pose_cnt, level, chi0, fail, tickets, bad, row_tickets, blk_done;                                                         // zeroed
     size_t pt_start, order, edges, epcol, pose_start, pose_edges, rowrec, schur_part, lm_mask, blk_cnt, blk_pair_start, blk_chunk_start, pairs, blocks, chunks,
         chunk_part, robust, q1, t1, Rt1, pts1, chi1, Hpl, Hll, bl, Dinv, Hpp, bp, M, xp, r_chi,
-        r_diag, r_scale, r_result;                                                                                    // scratch
+        r_diag, r_scale, r_result, gP, gD, ginvd;                                                                     // scratch
     size_t exp_begin, qf, tf, pf, out, exp_end;                                                                       // export block
 };
 
 // Solves the windows ws[0..nw) (indices into the caller's arrays) in lockstep.  status[w] is set for every window.
 static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int iters1, int iters2, volatile uint8_t* const* stops,
-                       double* const* pose_outs, double* const* points_outs, uint8_t* const* outlier_outs, b200_lba_stats_t* stats, int* status) {
+                       double* const* pose_outs, double* const* points_outs, uint8_t* const* outlier_outs, b200_lba_stats_t* stats, int* status, int rounds = 2, double gain_thr = 1e-3, bool allow_large = false) {
     const bool debug = getenv("B200_LBA_DEBUG") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
@@ -1968,8 +2182,11 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
         }
         int n_free = 0;
         for (int k = 0; k < Ps[w].n_poses; ++k) n_free += Ps[w].pose_fixed[k] ? 0 : 1;
-        if (6 * n_free > 1000) {  // only FREE keyframes enter the reduced system; fixed ones are unlimited
-            set_error("b200_lba_solve: window %d has %d free keyframes; the on-chip Cholesky of the reduced system holds at most 166", w, n_free);
+        // only FREE keyframes enter the reduced system; fixed ones are unlimited.  Up to 166 free keyframes it is factored on chip
+        // (one cluster per window); beyond that -- global bundle adjustment -- panel by panel over the whole chip, dense in HBM
+        if (6 * n_free > (allow_large ? kCholGlobalMax : kCholOnChipMax)) {
+            set_error("b200_lba_solve: window %d has %d free keyframes; the limit of this entry point is %d", w, n_free,
+                      (allow_large ? kCholGlobalMax : kCholOnChipMax) / 6);
             status[w] = B200_ERR_INVALID;
             ret = B200_ERR_INVALID;
             continue;
@@ -2070,6 +2287,12 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
         o.chi1 = cv.take<double>(E); o.Hpl = cv.take<double>(kHplStride * (E + kSchurFan)); o.Hll = cv.take<double>(6 * Lf); o.bl = cv.take<double>(3 * Lf);
         o.Dinv = cv.take<double>(6 * Lf); o.Hpp = cv.take<double>(36 * Kf); o.bp = cv.take<double>(6 * Kf);
         o.M = cv.take<double>((size_t)(h.n + 1) * h.ld); o.xp = cv.take<double>(h.n);
+        o.gP = o.gD = o.ginvd = 0;
+        if (h.n > kCholOnChipMax) {
+            o.gP = cv.take<double>((size_t)kNB * ((h.n + 1 + 3) & ~3));
+            o.gD = cv.take<double>(kNB * (kNB + 1));
+            o.ginvd = cv.take<double>(h.n);
+        }
         o.r_chi = cv.take<double>(h.lbc); o.r_diag = cv.take<double>(h.lbc); o.r_scale = cv.take<double>(h.lbc); o.r_result = cv.take<double>(8);
     }
     const size_t export_begin = round_up(cv.off, (size_t)256);
@@ -2153,6 +2376,7 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
         W.chi[0] = (double*)(d + o.chi0); W.chi[1] = (double*)(d + o.chi1);
         W.Hpl = (double*)(d + o.Hpl); W.Hll = (double*)(d + o.Hll); W.bl = (double*)(d + o.bl); W.Dinv = (double*)(d + o.Dinv);
         W.Hpp = (double*)(d + o.Hpp); W.bp = (double*)(d + o.bp); W.M = (double*)(d + o.M); W.xp = (double*)(d + o.xp);
+        W.gP = (double*)(d + o.gP); W.gD = (double*)(d + o.gD); W.ginvd = (double*)(d + o.ginvd);
         W.r_chi = (double*)(d + o.r_chi); W.r_diag = (double*)(d + o.r_diag); W.r_scale = (double*)(d + o.r_scale); W.r_result = (double*)(d + o.r_result);
         W.fail = (int*)(d + o.fail); W.tickets = (int*)(d + o.tickets); W.bad_input = (int*)(d + o.bad);
         W.ctl = (LmCtl*)(d + o_ctl) + x;
@@ -2200,7 +2424,8 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
     }
     if ((rc = mark(0))) return rc;
     // ---- LM rounds in lockstep ---------------------------------------------------------------------------------------------------
-    const size_t chol_smem = sizeof(double) * ((size_t)kNB * (kNB + 1) + 4 + (size_t)((max_n + 1 + 3) & ~3) * kNB);
+    const bool large = max_n > kCholOnChipMax;
+    const size_t chol_smem = sizeof(double) * ((size_t)kNB * (kNB + 1) + 4 + (size_t)((std::min(max_n, kCholOnChipMax) + 1 + 3) & ~3) * kNB);
     B200_CUDA(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
     // warps per Schur row CTA: every warp owns Kf accumulator tiles of 512 bytes
     int schur_warps = std::min(kSchurMaxWarps, std::max(1, S.schur_warps));
@@ -2223,7 +2448,16 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
         else if (S.schur_unroll == 2) schur_rows_kernel<2><<<dim3(maxKf, nw, max_split), 32 * schur_warps, schur_smem, st>>>(wins, schur_warps);
         else schur_rows_kernel<4><<<dim3(maxKf, nw, max_split), 32 * schur_warps, schur_smem, st>>>(wins, schur_warps);
         if ((rcm = mark(3))) return rcm;
-        {
+        if (large) {  // panel by panel over the whole chip (every window of the batch takes this path; small ones finish early)
+            for (int kb = 0; kb < max_n; kb += kNB) {
+                const int m = max_n + 1 - std::min(kb + kNB, max_n);
+                const long long tm = (m + 3) >> 2, n_tiles = tm * (tm + 1) / 2;
+                gchol_panel_kernel<<<dim3(ceil_div(m + 4, kGcholThreads), nw), kGcholThreads, 0, st>>>(wins, kb);
+                gchol_trail_kernel<<<dim3((unsigned)std::max<long long>(1, (n_tiles + kGcholThreads - 1) / kGcholThreads), nw), kGcholThreads, 0, st>>>(wins, kb);
+                launches += 2;
+            }
+            gchol_finish_kernel<<<nw, kGfinThreads, 0, st>>>(wins);
+        } else {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(chol_cluster * nw);
             cfg.blockDim = dim3(kCholThreads);
@@ -2267,7 +2501,7 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
     };
     const int iters[2] = {iters1, iters2};
     int rc2;
-    for (int r = 0; r < 2; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         if (r == 1) {
             // local_bundle_adjuster_g2o.cc:317-321 reads the caller's flag, which the gain stop of round 1 has set through
             // terminate_action; the device takes the same decision from stop_flag / the mirrored word.  A round that does run starts
@@ -2284,7 +2518,7 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
                 }
             }
         }
-        lm_round_begin_kernel<<<ceil_div(nw, 64), 64, 0, st>>>(wins, nw, iters[r], r);
+        lm_round_begin_kernel<<<ceil_div(nw, 64), 64, 0, st>>>(wins, nw, iters[r], r, gain_thr);
         ++launches;
         if (r == 1) {
             outlier_kernel<<<dim3(ceil_div(maxE, 128), nw), 128, 0, st>>>(wins, 0);  // :323-344 (skips itself after an abort)
@@ -2313,7 +2547,7 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
         lm_round_end_kernel<<<nw, 256, 0, st>>>(wins, r);
         launches += 2;
     }
-    outlier_kernel<<<dim3(ceil_div(maxE, 128), nw), 128, 0, st>>>(wins, 1);  // :354-375
+    if (rounds == 2) outlier_kernel<<<dim3(ceil_div(maxE, 128), nw), 128, 0, st>>>(wins, 1);  // :354-375 (global BA marks nothing)
     lm_export_kernel<<<dim3(ceil_div(std::max(std::max(4 * maxK, 3 * maxL), 1), 256), nw), 256, 0, st>>>(wins);
     launches += 2;
     B200_CUDA(cudaGetLastError());
@@ -2363,14 +2597,15 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
         }
         // terminate_action's gain-threshold stop writes the caller's flag (terminate_action.cc:66-70); an externally raised flag stays up
         if (stops && stops[w] && c.stop_flag) *stops[w] = 1;
+        S.last_gain_stop = c.stop_flag != 0;
         const unsigned char* ex = h_export + (o.qf - export_begin);
         const double* qf = reinterpret_cast<const double*>(ex);
         const double* tf = reinterpret_cast<const double*>(h_export + (o.tf - export_begin));
         const double* pf = reinterpret_cast<const double*>(h_export + (o.pf - export_begin));
         const unsigned char* out = h_export + (o.out - export_begin);
         int n_out = 0;
-        for (int e = 0; e < h.E; ++e) n_out += out[e];
-        if (outlier_outs && outlier_outs[w] && h.E) std::memcpy(outlier_outs[w], out, h.E);
+        for (int e = 0; e < h.E && rounds == 2; ++e) n_out += out[e];
+        if (rounds == 2 && outlier_outs && outlier_outs[w] && h.E) std::memcpy(outlier_outs[w], out, h.E);
         if (stats) stats[w].n_outliers = n_out;
         if (h.L) std::memcpy(points_outs[w], pf, sizeof(double) * 3 * (size_t)h.L);
         for (int k = 0; k < h.K; ++k) {  // util::converter::to_eigen_mat (util/converter.cc:23-25)
@@ -2388,6 +2623,92 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
         }
     }
     return ret;
+}
+
+// ---- stage C of b200_track_local_map (track_chain.cuh) -------------------------------------------------------------------------
+// One CTA per frame: apply the matches of the search to the frame's landmark slots in the reference's order (frm.add_landmark,
+// projection.cc:87: a later landmark replaces an earlier one on the same keypoint), then one edge per keypoint that carries a
+// landmark, in keypoint order (pose_optimizer_g2o.cc:88-111).
+constexpr int kTrackEdgeThreads = 256;
+constexpr int kMatchedBias = 1 << 30;
+__global__ void __launch_bounds__(kTrackEdgeThreads) track_edges_kernel(chain::TrackShared sh, const chain::TrackFrameDev* __restrict__ frames,
+                                                                        PoseProb* __restrict__ probs, PoseEdge* __restrict__ edges_all,
+                                                                        int* __restrict__ edge_kp_all) {
+    __shared__ int warp_sum[kTrackEdgeThreads / 32];
+    __shared__ int s_base;
+    const chain::TrackFrameDev& F = frames[blockIdx.x];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = F.status[0];
+    int* slot = F.kp_landmark_out;
+    for (int i = tid; i < F.kp_cap; i += kTrackEdgeThreads) {
+        int l = -1;
+        if (i < n && F.kp_landmark && i < F.n_kp_in) {
+            l = F.kp_landmark[i];
+            if (l < 0 || l >= F.n_lm) l = -1;
+        }
+        slot[i] = l;
+        F.kp_outlier[i] = 0;
+    }
+    __syncthreads();
+    for (int q = tid; q < F.n_lm; q += kTrackEdgeThreads) {
+        const int k = F.match_out[q];
+        if (k >= 0 && k < n) atomicMax(&slot[k], q + kMatchedBias);
+    }
+    __syncthreads();
+    if (tid == 0) s_base = 0;
+    const PoseProb pb = probs[blockIdx.x];
+    PoseEdge* __restrict__ edges = edges_all + pb.edge_off;
+    int* __restrict__ edge_kp = edge_kp_all + pb.edge_off;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += kTrackEdgeThreads) {
+        const int i = i0 + tid;
+        int l = -1;
+        if (i < n) {
+            l = slot[i];
+            if (l >= kMatchedBias) l -= kMatchedBias;
+            slot[i] = l;
+        }
+        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, l >= 0);
+        if (lane == 0) warp_sum[warp] = __popc(ballot);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; ++w) before += warp_sum[w];
+        if (l >= 0) {
+            const int e = before + __popc(ballot & ((1u << lane) - 1u));
+            const b200_keypoint_t kp = F.undist[i];
+            PoseEdge pe;
+            pe.pw[0] = F.pos_w[3 * (size_t)l];
+            pe.pw[1] = F.pos_w[3 * (size_t)l + 1];
+            pe.pw[2] = F.pos_w[3 * (size_t)l + 2];
+            pe.ox = kp.x;
+            pe.oy = kp.y;
+            pe.oxr = F.kp_x_right ? F.kp_x_right[i] : -1.0f;  // stereo_x_right_.empty() ? -1 (:94)
+            pe.inv_sigma_sq = sh.inv_level_sigma_sq[kp.octave & 31];
+            pe.delta = sh.delta;
+            pe.pad = 0;
+            edges[e] = pe;
+            edge_kp[e] = i;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = s_base;
+            for (int w = 0; w < kTrackEdgeThreads / 32; ++w) t += warp_sum[w];
+            s_base = t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        probs[blockIdx.x].n = s_base;
+        F.status[2] = s_base;
+    }
+}
+
+__global__ void __launch_bounds__(256) track_scatter_kernel(const chain::TrackFrameDev* __restrict__ frames, const PoseProb* __restrict__ probs,
+                                                            const unsigned char* __restrict__ flags_all, const int* __restrict__ edge_kp_all) {
+    const PoseProb& pb = probs[blockIdx.y];
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= pb.n) return;
+    frames[blockIdx.y].kp_outlier[edge_kp_all[pb.edge_off + e]] = flags_all[pb.edge_off + e];
 }
 
 }  // namespace lba
@@ -2512,6 +2833,30 @@ int b200_lba_solve(b200_lba_t h, const b200_lba_problem_t* P, int iters1, int it
     return rc ? rc : status;
 }
 
+int b200_global_ba_solve(b200_lba_t h, const b200_lba_problem_t* P, int num_iter, double gain_threshold, volatile uint8_t* force_stop, double* pose_cw_out,
+                         double* points_out, b200_lba_stats_t* stats) {
+    if (!h || !P || !pose_cw_out || !points_out || num_iter < 0 || !(gain_threshold >= 0.0)) {
+        b200::set_error("b200_global_ba_solve: null argument");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(h->s.device));
+    // optimizer.setForceStopFlag(force_stop_flag): a flag that is already up stops the optimisation before its first iteration; the
+    // reference then reports "aborted" (:340-342)
+    if (force_stop && *force_stop) return B200_ERR_ABORTED;
+    volatile uint8_t* stops[1] = {force_stop};
+    double* poses[1] = {pose_cw_out};
+    double* pts[1] = {points_out};
+    uint8_t* outl[1] = {nullptr};
+    int status = B200_OK;
+    b200_lba_stats_t local{};
+    b200_lba_stats_t* st = stats ? stats : &local;
+    const int rc = b200::lba::solve_batch(h->s, 1, P, num_iter, 0, stops, poses, pts, outl, st, &status, 1, gain_threshold, true);
+    if (rc) return rc;
+    if (status) return status;
+    if (force_stop && *force_stop && !h->s.last_gain_stop) return B200_ERR_ABORTED;  // raised by the caller while the solve ran (:340-342)
+    return B200_OK;
+}
+
 int b200_pose_optimize(b200_lba_t h, int n_problems, const b200_lba_problem_t* problems, int num_trials_robust, int num_trials, int num_each_iter,
                        double* pose_cw_out, uint8_t* outlier_flags, uint32_t* n_valid) {
     using namespace b200::lba;
@@ -2617,3 +2962,51 @@ int b200_lba_last_profile(b200_lba_t h, float* gpu_ms, int* launches) {
 }
 
 }  // extern "C"
+
+namespace b200 {
+namespace chain {
+int track_stage_c(b200_lba_t opt, cudaStream_t st, const TrackShared& sh, const TrackFrameDev* d_frames, const TrackFrameDev* h_frames,
+                  const double* const* pose_cw, int n_frames, int max_kp, int trials_robust, int trials, int each_iter, double* d_pose_out,
+                  unsigned* d_n_valid, cudaEvent_t ev_edges_done) {
+    using namespace b200::lba;
+    if (!opt) return B200_ERR_INVALID;
+    Solver& S = opt->s;
+    size_t total = 0;
+    for (int f = 0; f < n_frames; ++f) total += (size_t)h_frames[f].kp_cap;
+    Carver up;
+    const size_t o_probs = up.take<PoseProb>(n_frames);
+    const size_t upload_bytes = round_up(up.off, (size_t)256);
+    Carver dv;
+    dv.off = upload_bytes;
+    const size_t o_edges = dv.take<PoseEdge>(total), o_kp = dv.take<int>(total), o_level = dv.take<unsigned char>(total), o_flags = dv.take<unsigned char>(total);
+    int rc = S.ensure(dv.off + 256, upload_bytes, 16);
+    if (rc) return rc;
+    PoseProb* hp = reinterpret_cast<PoseProb*>(S.h_stage + o_probs);
+    size_t off = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        PoseProb pb{};
+        pb.n = 0;
+        pb.edge_off = (int)off;
+        pb.cam = Cam{sh.model, sh.fx, sh.fy, sh.cx, sh.cy, sh.fxb, sh.cols, sh.rows};
+        const double* M = pose_cw[f];  // util::converter::to_g2o_SE3 (util/converter.cc:17-21)
+        const double R[9] = {M[0], M[1], M[2], M[4], M[5], M[6], M[8], M[9], M[10]};
+        rot_to_quat(R, pb.q);
+        quat_normalize(pb.q);
+        pb.t[0] = M[3]; pb.t[1] = M[7]; pb.t[2] = M[11];
+        hp[f] = pb;
+        off += (size_t)h_frames[f].kp_cap;
+    }
+    unsigned char* d = S.d_arena;
+    B200_CUDA(cudaMemcpyAsync(d, S.h_stage, upload_bytes, cudaMemcpyHostToDevice, st));
+    PoseProb* dp = reinterpret_cast<PoseProb*>(d + o_probs);
+    track_edges_kernel<<<n_frames, kTrackEdgeThreads, 0, st>>>(sh, d_frames, dp, (PoseEdge*)(d + o_edges), (int*)(d + o_kp));
+    if (ev_edges_done) B200_CUDA(cudaEventRecord(ev_edges_done, st));
+    pose_optimize_kernel<<<n_frames, kPoseThreads, 0, st>>>(dp, (const PoseEdge*)(d + o_edges), d + o_level, d + o_flags, trials_robust, trials, each_iter,
+                                                           d_pose_out, d_n_valid);
+    if (max_kp > 0) track_scatter_kernel<<<dim3(ceil_div(max_kp, 256), n_frames), 256, 0, st>>>(d_frames, dp, d + o_flags, (const int*)(d + o_kp));
+    B200_CUDA(cudaGetLastError());
+    S.last_launches = 3;
+    return B200_OK;
+}
+}  // namespace chain
+}  // namespace b200

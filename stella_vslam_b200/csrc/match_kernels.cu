@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "track_chain.cuh"
 
 namespace b200 {
 namespace match {
@@ -867,6 +868,13 @@ __global__ void __launch_bounds__(32) guided_resolve_kernel(const Dev* __restric
     if (lane == 0) *n_matches = total;
 }
 
+
+// b200_track_local_map: the keypoint count of a frame is known on the device only (the extractor's counter)
+__global__ void track_set_counts_kernel(GuidedDev* __restrict__ gs, const chain::TrackFrameDev* __restrict__ frames, int n) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < n) gs[f].n_train = frames[f].status[0];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // All-pairs matchers with greedy state other than brute_force_match:
 //   match::bow_tree::match_frame_and_keyframe   src/stella_vslam/match/bow_tree.cc:169-256   (variant 0)
@@ -1282,6 +1290,8 @@ struct Matcher {
     bool async_resolve = false, resolve_pending = false;
     bool timing = false;
     cudaEvent_t ev_t[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_track[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // b200_track_local_map stage boundaries
+    bool track_timed = false;
     // all-pairs distances + top-K on the tensor cores (tcgen05, int8 +-1 GEMM) or on the POPC pipe (B200_MATCH_TOPK=popc)
     bool use_tensor_core = true;
     int join() {  // the main stream waits for the side stream's resolve
@@ -1433,6 +1443,8 @@ int b200_matcher_destroy(b200_matcher_t h) {
     if (h->m.h_guided) cudaFreeHost(h->m.h_guided);
     for (int i = 0; i < 3; ++i)
         if (h->m.ev_t[i]) cudaEventDestroy(h->m.ev_t[i]);
+    for (int i = 0; i < 7; ++i)
+        if (h->m.ev_track[i]) cudaEventDestroy(h->m.ev_track[i]);
     if (h->m.ev_topk) cudaEventDestroy(h->m.ev_topk);
     if (h->m.ev_resolved) cudaEventDestroy(h->m.ev_resolved);
     if (h->m.side_stream) cudaStreamDestroy(h->m.side_stream);
@@ -1778,6 +1790,294 @@ int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* p
         if (P.n_queries > 0) std::memcpy(P.match_out, hb + lay[p].mout, 4 * (size_t)P.n_queries);
         P.n_matches = *reinterpret_cast<const int*>(hb + lay[p].nm);
         if (writes_occupancy && P.t_occupied && P.n_train > 0) std::memcpy(P.t_occupied, hb + lay[p].occ, (size_t)P.n_train);
+    }
+    return B200_OK;
+}
+
+int b200_track_stage_ms(b200_matcher_t h, int stage, float* ms) {
+    if (!h || !ms || stage < 0 || stage > 6 || !h->m.track_timed) return B200_ERR_INVALID;
+    if (stage == 6) B200_CUDA(cudaEventElapsedTime(ms, h->m.ev_track[0], h->m.ev_track[6]));
+    else B200_CUDA(cudaEventElapsedTime(ms, h->m.ev_track[stage], h->m.ev_track[stage + 1]));
+    return B200_OK;
+}
+
+// The device-resident tracking chain (see include/b200vslam.h).  Arena of the matcher handle:
+//   [TrackFrameDev x n][GuidedDev x n][caller inputs]  -- mirrored in pinned memory, one upload
+//   [outputs]                                          -- one download
+//   [stage-A products, guided scratch]
+int b200_track_local_map(b200_orb_t orb, b200_matcher_t h, b200_lba_t opt, const b200_track_params_t* prm, int n_frames, b200_track_frame_t* frames) {
+    using b200::chain::TrackFrameDev;
+    using b200::chain::TrackShared;
+    using b200::match::GuidedDev;
+    if (!orb || !h || !opt || !prm || n_frames < 0) return B200_ERR_INVALID;
+    if (n_frames == 0) return B200_OK;
+    if (!frames || !prm->scale_factors || !prm->inv_level_sigma_sq || prm->num_levels == 0 || prm->num_levels > 32 || prm->grid_cols <= 0
+        || prm->grid_rows <= 0 || (long long)prm->grid_cols * prm->grid_rows > (1 << 20) || !(prm->img_bounds[1] > prm->img_bounds[0])
+        || !(prm->img_bounds[3] > prm->img_bounds[2]) || (prm->cam.model != 0 && prm->cam.model != 1) || prm->max_candidates < 0
+        || prm->num_trials_robust < 0 || prm->num_trials < 0 || prm->num_each_iter < 0) {
+        b200::set_error("b200_track_local_map: invalid parameters");
+        return B200_ERR_INVALID;
+    }
+    auto& m = h->m;
+    const b200_keypoint_t* d_kps = nullptr;
+    const unsigned char* d_descs = nullptr;
+    const int* d_counts = nullptr;
+    int stride = 0, batch = 0, device = 0;
+    cudaStream_t st = nullptr;
+    int rc = b200::chain::orb_results(orb, &d_kps, &d_descs, &d_counts, &stride, &batch, &st, &device);
+    if (rc) return rc;
+    if (device != m.device) {
+        b200::set_error("b200_track_local_map: extractor and matcher live on different devices");
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(m.device));
+    const int cap = prm->max_candidates ? prm->max_candidates : 256;
+    auto al = [](size_t v) { return b200::round_up(v, (size_t)256); };
+    struct Lay {
+        size_t xr, kl, pos, nrm, lo, hi, desc, skip, hobs;                       // inputs
+        size_t obs, klo, kout, status, mout, nm;                                   // outputs
+        size_t und, tx, ty, toct, occ, qx, qy, qm, qxr, qlo, qhi, qval;           // stage A products
+        size_t cstart, citems, ccur, lists, llen, own;                            // guided scratch
+    };
+    std::vector<Lay> lay(n_frames);
+    int max_lm = 0;
+    size_t o = al(sizeof(TrackFrameDev) * (size_t)n_frames);
+    const size_t o_gd = o;
+    o += al(sizeof(GuidedDev) * (size_t)n_frames);
+    for (int f = 0; f < n_frames; ++f) {
+        const b200_track_frame_t& F = frames[f];
+        if (F.frame < 0 || F.frame >= batch || !F.pose_cw || F.n_landmarks < 0 || F.n_keypoints_in < 0 || F.kp_cap < 0
+            || ((F.kp_x_right || F.kp_landmark) && F.n_keypoints_in > stride) || !F.kp_landmark_out || !F.kp_outlier
+            || (F.n_landmarks > 0 && (!F.lm_pos_w || !F.lm_mean_normal || !F.lm_min_valid_dist || !F.lm_max_valid_dist || !F.lm_desc || !F.lm_observable))) {
+            b200::set_error("b200_track_local_map: frame %d: bad frame index, sizes or null buffers", f);
+            return B200_ERR_INVALID;
+        }
+        Lay& L = lay[f];
+        const size_t nk = (size_t)std::max(F.n_keypoints_in, 1), nl = (size_t)std::max(F.n_landmarks, 1);
+        L.xr = o; o += al(4 * nk);
+        L.kl = o; o += al(4 * nk);
+        L.pos = o; o += al(24 * nl);
+        L.nrm = o; o += al(24 * nl);
+        L.lo = o; o += al(4 * nl);
+        L.hi = o; o += al(4 * nl);
+        L.desc = o; o += al(32 * nl);
+        L.skip = o; o += al(nl);
+        L.hobs = o; o += al(nl);
+        max_lm = std::max(max_lm, F.n_landmarks);
+    }
+    const size_t in_bytes = o, out_begin = o;
+    const size_t kc = (size_t)std::max(stride, 1);
+    for (int f = 0; f < n_frames; ++f) {
+        Lay& L = lay[f];
+        const size_t nl = (size_t)std::max(frames[f].n_landmarks, 1);
+        L.obs = o; o += al(nl);
+        L.klo = o; o += al(4 * kc);
+        L.kout = o; o += al(kc);
+        L.status = o; o += al(16);
+        L.mout = o; o += al(4 * nl);
+        L.nm = o; o += al(4);
+    }
+    const size_t o_pose = o; o += al(8 * 16 * (size_t)n_frames);
+    const size_t o_nvalid = o; o += al(4 * (size_t)n_frames);
+    const size_t o_overflow = o; o += al(4);
+    const size_t out_end = o;
+    const size_t cells = (size_t)prm->grid_cols * prm->grid_rows;
+    for (int f = 0; f < n_frames; ++f) {
+        Lay& L = lay[f];
+        const size_t nl = (size_t)std::max(frames[f].n_landmarks, 1);
+        L.und = o; o += al(sizeof(b200_keypoint_t) * kc);
+        L.tx = o; o += al(4 * kc);
+        L.ty = o; o += al(4 * kc);
+        L.toct = o; o += al(kc);
+        L.occ = o; o += al(kc);
+        L.qx = o; o += al(4 * nl);
+        L.qy = o; o += al(4 * nl);
+        L.qm = o; o += al(4 * nl);
+        L.qxr = o; o += al(4 * nl);
+        L.qlo = o; o += al(nl);
+        L.qhi = o; o += al(nl);
+        L.qval = o; o += al(nl);
+        L.cstart = o; o += al(4 * (cells + 1));
+        L.citems = o; o += al(4 * kc);
+        L.ccur = o; o += al(4 * cells);
+        L.lists = o; o += al(8 * (size_t)cap * nl);
+        L.llen = o; o += al(4 * nl);
+        L.own = o; o += al(4 * kc);
+    }
+    const size_t rs_bytes = kc * 6 + 16;
+    if (rs_bytes > 200 * 1024) {
+        b200::set_error("b200_track_local_map: %d keypoints per frame exceed the on-chip occupancy table", stride);
+        return B200_ERR_CAPACITY;
+    }
+    if ((rc = m.grow((void**)&m.d_guided, &m.d_guided_cap, o))) return rc;
+    if ((rc = m.grow_pinned(&m.h_guided, &m.h_guided_cap, out_end))) return rc;
+    for (int i = 0; i < 7; ++i)
+        if (!m.ev_track[i]) B200_CUDA(cudaEventCreate(&m.ev_track[i]));
+    unsigned char *hb = m.h_guided, *db = m.d_guided;
+    TrackFrameDev* hf = reinterpret_cast<TrackFrameDev*>(hb);
+    GuidedDev* hg = reinterpret_cast<GuidedDev*>(hb + o_gd);
+    auto put = [&](size_t off, const void* src, size_t bytes) {
+        if (src && bytes) std::memcpy(hb + off, src, bytes);
+    };
+    TrackShared sh{};
+    sh.model = prm->cam.model;
+    sh.fx = prm->cam.fx; sh.fy = prm->cam.fy; sh.cx = prm->cam.cx; sh.cy = prm->cam.cy;
+    sh.k1 = prm->cam.k1; sh.k2 = prm->cam.k2; sh.p1 = prm->cam.p1; sh.p2 = prm->cam.p2; sh.k3 = prm->cam.k3;
+    sh.cols = prm->cam.cols; sh.rows = prm->cam.rows;
+    sh.fxb = prm->focal_x_baseline;
+    sh.min_x = prm->img_bounds[0]; sh.max_x = prm->img_bounds[1]; sh.min_y = prm->img_bounds[2]; sh.max_y = prm->img_bounds[3];
+    sh.ray_cos_thr = prm->ray_cos_thr;
+    sh.log_scale_factor = prm->log_scale_factor;
+    sh.margin = prm->margin;
+    sh.delta = prm->monocular ? std::sqrt(5.99146f) : std::sqrt(7.81473f);  // pose_optimizer_g2o.cc:73-88
+    sh.num_levels = prm->num_levels;
+    for (unsigned l = 0; l < 32; ++l) {
+        sh.scale_factors[l] = prm->scale_factors[std::min(l, prm->num_levels - 1)];
+        sh.inv_level_sigma_sq[l] = prm->inv_level_sigma_sq[std::min(l, prm->num_levels - 1)];
+    }
+    std::vector<const double*> poses(n_frames);
+    for (int f = 0; f < n_frames; ++f) {
+        const b200_track_frame_t& F = frames[f];
+        const Lay& L = lay[f];
+        const size_t nk = (size_t)F.n_keypoints_in, nl = (size_t)F.n_landmarks;
+        put(L.xr, F.kp_x_right, 4 * nk);
+        put(L.kl, F.kp_landmark, 4 * nk);
+        put(L.pos, F.lm_pos_w, 24 * nl);
+        put(L.nrm, F.lm_mean_normal, 24 * nl);
+        put(L.lo, F.lm_min_valid_dist, 4 * nl);
+        put(L.hi, F.lm_max_valid_dist, 4 * nl);
+        put(L.desc, F.lm_desc, 32 * nl);
+        put(L.skip, F.lm_skip, nl);
+        put(L.hobs, F.lm_has_observation, nl);
+        poses[f] = F.pose_cw;
+        TrackFrameDev t{};
+        t.kps = d_kps + (size_t)F.frame * stride;
+        t.n_kp = d_counts + F.frame;
+        t.kp_cap = stride;
+        t.n_kp_in = F.n_keypoints_in;
+        t.n_lm = F.n_landmarks;
+        t.kp_x_right = F.kp_x_right ? (const float*)(db + L.xr) : nullptr;
+        t.kp_landmark = F.kp_landmark ? (const int*)(db + L.kl) : nullptr;
+        t.pos_w = (const double*)(db + L.pos);
+        t.mean_normal = (const double*)(db + L.nrm);
+        t.min_d = (const float*)(db + L.lo);
+        t.max_d = (const float*)(db + L.hi);
+        t.lm_skip = F.lm_skip ? db + L.skip : nullptr;
+        t.lm_has_obs = F.lm_has_observation ? db + L.hobs : nullptr;
+        const double* P = F.pose_cw;
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) t.Rt[3 * r + c] = P[4 * r + c];
+            t.Rt[9 + r] = P[4 * r + 3];
+        }
+        for (int r = 0; r < 3; ++r) t.twc[r] = -(t.Rt[r] * t.Rt[9] + t.Rt[3 + r] * t.Rt[10] + t.Rt[6 + r] * t.Rt[11]);
+        t.undist = (b200_keypoint_t*)(db + L.und);
+        t.t_x = (float*)(db + L.tx);
+        t.t_y = (float*)(db + L.ty);
+        t.t_octave = db + L.toct;
+        t.occupied = db + L.occ;
+        t.observable = db + L.obs;
+        t.q_x = (float*)(db + L.qx);
+        t.q_y = (float*)(db + L.qy);
+        t.q_margin = (float*)(db + L.qm);
+        t.q_xr = (float*)(db + L.qxr);
+        t.q_lo = (signed char*)(db + L.qlo);
+        t.q_hi = (signed char*)(db + L.qhi);
+        t.q_valid = db + L.qval;
+        t.match_out = (const int*)(db + L.mout);
+        t.kp_landmark_out = (int*)(db + L.klo);
+        t.kp_outlier = db + L.kout;
+        t.status = (int*)(db + L.status);
+        hf[f] = t;
+        GuidedDev g{};
+        g.n_train = 0;  // set on the device from the extractor's counter
+        g.n_queries = F.n_landmarks;
+        g.grid_cols = prm->grid_cols;
+        g.grid_rows = prm->grid_rows;
+        g.cap = cap;
+        g.min_x = sh.min_x; g.max_x = sh.max_x; g.min_y = sh.min_y; g.max_y = sh.max_y;
+        g.t_x = t.t_x;
+        g.t_y = t.t_y;
+        g.t_angle = nullptr;
+        g.t_x_right = t.kp_x_right;
+        g.t_octave = t.t_octave;
+        g.t_desc = reinterpret_cast<const uint4*>(d_descs + (size_t)F.frame * stride * 32);
+        g.q_desc = (const uint4*)(db + L.desc);
+        g.q_x = t.q_x;
+        g.q_y = t.q_y;
+        g.q_margin = t.q_margin;
+        g.q_x_right = t.q_xr;
+        g.q_angle = nullptr;
+        g.q_min_level = t.q_lo;
+        g.q_max_level = t.q_hi;
+        g.q_valid = t.q_valid;
+        g.q_reproj = nullptr;
+        g.inv_level_sigma_sq = nullptr;
+        g.do_reproj = 0;
+        g.owner = (int*)(db + L.own);
+        g.cell_start = (int*)(db + L.cstart);
+        g.cell_items = (int*)(db + L.citems);
+        g.cell_cursor = (int*)(db + L.ccur);
+        g.lists = (uint2*)(db + L.lists);
+        g.list_len = (int*)(db + L.llen);
+        g.occupied = t.occupied;
+        g.match_out = (int*)(db + L.mout);
+        g.n_matches = (int*)(db + L.nm);
+        hg[f] = g;
+    }
+    if ((rc = m.join())) return rc;
+    B200_CUDA(cudaEventRecord(m.ev_track[0], st));
+    B200_CUDA(cudaMemcpyAsync(db, hb, in_bytes, cudaMemcpyHostToDevice, st));
+    B200_CUDA(cudaMemsetAsync(db + out_begin, 0, out_end - out_begin, st));
+    const TrackFrameDev* df = reinterpret_cast<const TrackFrameDev*>(db);
+    GuidedDev* dg = reinterpret_cast<GuidedDev*>(db + o_gd);
+    if ((rc = b200::chain::track_stage_a(st, sh, df, n_frames, stride, max_lm))) return rc;
+    b200::match::track_set_counts_kernel<<<b200::ceil_div(n_frames, 128), 128, 0, st>>>(dg, df, n_frames);
+    B200_CUDA(cudaEventRecord(m.ev_track[1], st));
+    b200::match::guided_grid_kernel<<<n_frames, 1024, 0, st>>>(dg);
+    B200_CUDA(cudaEventRecord(m.ev_track[2], st));
+    b200::match::guided_candidates_kernel<<<dim3(std::max(1, b200::ceil_div(max_lm, 128)), n_frames), 128, 0, st>>>(dg, B200_GUIDED_LANDMARKS, 0,
+                                                                                                                     (int*)(db + o_overflow));
+    B200_CUDA(cudaEventRecord(m.ev_track[3], st));
+    if (rs_bytes > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(b200::match::guided_resolve_kernel<GuidedDev>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_bytes));
+    b200::match::guided_resolve_kernel<GuidedDev><<<n_frames, 32, rs_bytes, st>>>(dg, B200_GUIDED_LANDMARKS, prm->hamming_thr, prm->lowe_ratio);
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaEventRecord(m.ev_track[4], st));
+    if ((rc = b200::chain::track_stage_c(opt, st, sh, df, hf, poses.data(), n_frames, stride, prm->num_trials_robust, prm->num_trials, prm->num_each_iter,
+                                         (double*)(db + o_pose), (unsigned*)(db + o_nvalid), m.ev_track[5])))
+        return rc;
+    B200_CUDA(cudaEventRecord(m.ev_track[6], st));
+    B200_CUDA(cudaMemcpyAsync(hb + out_begin, db + out_begin, out_end - out_begin, cudaMemcpyDeviceToHost, st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    m.track_timed = true;
+    m.last_h2d = in_bytes;
+    m.last_d2h = out_end - out_begin;
+    const int overflow = *reinterpret_cast<const int*>(hb + o_overflow);
+    if (overflow > 0) {
+        b200::set_error("b200_track_local_map: a search window returned %d keypoints, max_candidates is %d", overflow, cap);
+        return B200_ERR_CAPACITY;
+    }
+    for (int f = 0; f < n_frames; ++f) {
+        b200_track_frame_t& F = frames[f];
+        const Lay& L = lay[f];
+        const int* status = reinterpret_cast<const int*>(hb + L.status);
+        const int nk = status[0];
+        if (status[1]) {
+            b200::set_error("b200_track_local_map: frame %d has %d keypoints, the caller's per-keypoint arrays have %d", f, nk, F.n_keypoints_in);
+            return B200_ERR_INVALID;
+        }
+        if (nk > F.kp_cap) {
+            b200::set_error("b200_track_local_map: frame %d has %d keypoints, kp_cap is %d", f, nk, F.kp_cap);
+            return B200_ERR_CAPACITY;
+        }
+        F.n_keypoints = nk;
+        if (F.n_landmarks > 0) std::memcpy(F.lm_observable, hb + L.obs, (size_t)F.n_landmarks);
+        std::memcpy(F.kp_landmark_out, hb + L.klo, 4 * (size_t)nk);
+        std::memcpy(F.kp_outlier, hb + L.kout, (size_t)nk);
+        F.n_matches = *reinterpret_cast<const int*>(hb + L.nm);
+        F.n_valid = reinterpret_cast<const unsigned*>(hb + o_nvalid)[f];
+        if (status[2] < 5) std::memcpy(F.pose_cw_out, F.pose_cw, sizeof(double) * 16);  // :116-118: returns before touching the pose
+        else std::memcpy(F.pose_cw_out, hb + o_pose + sizeof(double) * 16 * (size_t)f, sizeof(double) * 16);
     }
     return B200_OK;
 }

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "track_chain.cuh"
 
 namespace b200 {
 namespace orb {
@@ -1264,12 +1265,10 @@ struct CamModel {
     int model;
     double fx, fy, cx, cy, k1, k2, p1, p2, k3, cols, rows;
 };
-__global__ void __launch_bounds__(128) undistort_bearings_kernel(CamModel c, const b200_keypoint_t* __restrict__ in, int n,
-                                                                 b200_keypoint_t* __restrict__ out, double* __restrict__ bearings) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const b200_keypoint_t kp = in[i];
-    float ux = kp.x, uy = kp.y;
+// camera::perspective::undistort_keypoints for one keypoint (cv::undistortPointsIter, 20 iterations / 1e-6); identity for equirectangular
+__device__ __forceinline__ void undistort_point(const CamModel& c, const b200_keypoint_t& kp, float& ux, float& uy) {
+    ux = kp.x;
+    uy = kp.y;
     if (c.model == 0) {
         const double ifx = 1. / c.fx, ify = 1. / c.fy;
         const double u = kp.x, v = kp.y;
@@ -1299,6 +1298,15 @@ __global__ void __launch_bounds__(128) undistort_bearings_kernel(CamModel c, con
         ux = (float)(c.fx * x + c.cx);
         uy = (float)(c.fy * y + c.cy);
     }
+}
+
+__global__ void __launch_bounds__(128) undistort_bearings_kernel(CamModel c, const b200_keypoint_t* __restrict__ in, int n,
+                                                                 b200_keypoint_t* __restrict__ out, double* __restrict__ bearings) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const b200_keypoint_t kp = in[i];
+    float ux, uy;
+    undistort_point(c, kp, ux, uy);
     if (out) {
         b200_keypoint_t o;  // undist_keypts.resize(n): default cv::KeyPoint, then pt / angle / size / octave (perspective.cc:266-272)
         o.x = ux;
@@ -1429,17 +1437,13 @@ struct ObserveArgs {
     float ray_cos_thr, log_scale_factor;
     unsigned num_levels;
 };
-__global__ void __launch_bounds__(128) can_observe_kernel(ObserveArgs a, int n, const double* __restrict__ pos_w, const double* __restrict__ mean_normal,
-                                                          const float* __restrict__ min_valid, const float* __restrict__ max_valid,
-                                                          unsigned char* __restrict__ observable, double* __restrict__ reproj,
-                                                          float* __restrict__ x_right, unsigned* __restrict__ level) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double px = pos_w[3 * (size_t)i], py = pos_w[3 * (size_t)i + 1], pz = pos_w[3 * (size_t)i + 2];
-    unsigned char ok = 0;
-    double rx = 0.0, ry = 0.0;
-    float xr = 0.f;
-    unsigned lvl_out = 0;
+__device__ __forceinline__ bool observe_landmark(const ObserveArgs& a, double px, double py, double pz, double nx, double ny, double nz, float min_valid_i,
+                                                 float max_valid_i, double& rx, double& ry, float& xr, unsigned& lvl_out) {
+    bool ok = false;
+    rx = 0.0;
+    ry = 0.0;
+    xr = 0.f;
+    lvl_out = 0;
     const double pcx = a.Rt[0] * px + a.Rt[1] * py + a.Rt[2] * pz + a.Rt[9];
     const double pcy = a.Rt[3] * px + a.Rt[4] * py + a.Rt[5] * pz + a.Rt[10];
     const double pcz = a.Rt[6] * px + a.Rt[7] * py + a.Rt[8] * pz + a.Rt[11];
@@ -1465,29 +1469,148 @@ __global__ void __launch_bounds__(128) can_observe_kernel(ObserveArgs a, int n, 
         const double vx = px - a.twc[0], vy = py - a.twc[1], vz = pz - a.twc[2];
         const double dist = sqrt(vx * vx + vy * vy + vz * vz);
         const float distf = (float)dist;
-        const float max_dist = __fmul_rn(1.3f, max_valid[i]), min_dist = __fmul_rn((float)(1.0 / 1.3), min_valid[i]);
+        const float max_dist = __fmul_rn(1.3f, max_valid_i), min_dist = __fmul_rn((float)(1.0 / 1.3), min_valid_i);
         if (min_dist <= distf && distf <= max_dist) {
-            const double ray_cos = (vx * mean_normal[3 * (size_t)i] + vy * mean_normal[3 * (size_t)i + 1] + vz * mean_normal[3 * (size_t)i + 2]) / dist;
+            const double ray_cos = (vx * nx + vy * ny + vz * nz) / dist;
             if (!(ray_cos < (double)a.ray_cos_thr)) {
-                const float ratio = __fdiv_rn(max_valid[i], distf);
+                const float ratio = __fdiv_rn(max_valid_i, distf);
                 const int lvl = (int)ceilf(__fdiv_rn(logf(ratio), a.log_scale_factor));
                 const float nl = (float)a.num_levels;
                 lvl_out = lvl < 0 ? 0u : ((nl <= (float)(unsigned)lvl) ? (unsigned)(nl - 1.f) : (unsigned)lvl);
-                ok = 1;
+                ok = true;
                 rx = qx;
                 ry = qy;
                 xr = qr;
             }
         }
     }
-    observable[i] = ok;
+    return ok;
+}
+
+__global__ void __launch_bounds__(128) can_observe_kernel(ObserveArgs a, int n, const double* __restrict__ pos_w, const double* __restrict__ mean_normal,
+                                                          const float* __restrict__ min_valid, const float* __restrict__ max_valid,
+                                                          unsigned char* __restrict__ observable, double* __restrict__ reproj,
+                                                          float* __restrict__ x_right, unsigned* __restrict__ level) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double rx, ry;
+    float xr;
+    unsigned lvl_out;
+    const bool ok = observe_landmark(a, pos_w[3 * (size_t)i], pos_w[3 * (size_t)i + 1], pos_w[3 * (size_t)i + 2], mean_normal[3 * (size_t)i],
+                                     mean_normal[3 * (size_t)i + 1], mean_normal[3 * (size_t)i + 2], min_valid[i], max_valid[i], rx, ry, xr, lvl_out);
+    observable[i] = ok ? 1 : 0;
     reproj[2 * (size_t)i] = rx;
     reproj[2 * (size_t)i + 1] = ry;
     x_right[i] = xr;
     level[i] = lvl_out;
 }
 
+// data::keyframe's `undist_keypts` blob (data/keyframe.cc:324-330): cv::KeyPoint records straight from the extractor's results
+__global__ void __launch_bounds__(128) keyframe_blob_kernel(CamModel c, int undistort, const b200_keypoint_t* __restrict__ in, const int* __restrict__ n_ptr,
+                                                            int cap, b200_cv_keypoint_t* __restrict__ out) {
+    const int n = min(*n_ptr, cap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const b200_keypoint_t kp = in[i];
+    b200_cv_keypoint_t o;
+    o.x = kp.x;
+    o.y = kp.y;
+    o.response = kp.response;
+    if (undistort) {
+        undistort_point(c, kp, o.x, o.y);
+        if (c.model == 0) o.response = 0.f;
+    }
+    o.size = kp.size;
+    o.angle = kp.angle;
+    o.octave = kp.octave;
+    o.class_id = -1;
+    out[i] = o;
+}
+
+// ---- stage A of b200_track_local_map (track_chain.cuh): the batched forms of the two kernels above, frame = blockIdx.y ----------
+__device__ __forceinline__ CamModel cam_of(const chain::TrackShared& sh) {
+    return CamModel{sh.model, sh.fx, sh.fy, sh.cx, sh.cy, sh.k1, sh.k2, sh.p1, sh.p2, sh.k3, sh.cols, sh.rows};
+}
+
+__global__ void __launch_bounds__(128) track_keypoints_kernel(chain::TrackShared sh, const chain::TrackFrameDev* __restrict__ frames) {
+    const chain::TrackFrameDev& F = frames[blockIdx.y];
+    const int n = min(*F.n_kp, F.kp_cap);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        F.status[0] = n;
+        F.status[1] = ((F.kp_x_right || F.kp_landmark) && F.n_kp_in != n) ? 1 : 0;
+    }
+    if (i >= n) return;
+    const b200_keypoint_t kp = F.kps[i];
+    float ux, uy;
+    undistort_point(cam_of(sh), kp, ux, uy);
+    b200_keypoint_t o;
+    o.x = ux;
+    o.y = uy;
+    o.size = kp.size;
+    o.angle = kp.angle;
+    o.response = (sh.model == 0) ? 0.f : kp.response;
+    o.octave = kp.octave;
+    F.undist[i] = o;
+    F.t_x[i] = ux;
+    F.t_y[i] = uy;
+    F.t_octave[i] = (unsigned char)kp.octave;
+    unsigned char occ = 0;
+    if (F.kp_landmark && i < F.n_kp_in) {  // `lm && lm->has_observation()` (projection.cc:50-53)
+        const int l = F.kp_landmark[i];
+        occ = (l >= 0 && l < F.n_lm && (!F.lm_has_obs || F.lm_has_obs[l])) ? 1 : 0;
+    }
+    F.occupied[i] = occ;
+}
+
+__global__ void __launch_bounds__(128) track_landmarks_kernel(chain::TrackShared sh, const chain::TrackFrameDev* __restrict__ frames) {
+    const chain::TrackFrameDev& F = frames[blockIdx.y];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F.n_lm) return;
+    ObserveArgs a;
+    a.cam = cam_of(sh);
+    a.fxb = sh.fxb;
+    a.min_x = sh.min_x; a.max_x = sh.max_x; a.min_y = sh.min_y; a.max_y = sh.max_y;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) a.Rt[k] = F.Rt[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) a.twc[k] = F.twc[k];
+    a.ray_cos_thr = sh.ray_cos_thr;
+    a.log_scale_factor = sh.log_scale_factor;
+    a.num_levels = sh.num_levels;
+    double rx, ry;
+    float xr;
+    unsigned lvl;
+    bool ok = !(F.lm_skip && F.lm_skip[i]);  // tracking_module.cc:561-586: skipped before can_observe
+    if (ok)
+        ok = observe_landmark(a, F.pos_w[3 * (size_t)i], F.pos_w[3 * (size_t)i + 1], F.pos_w[3 * (size_t)i + 2], F.mean_normal[3 * (size_t)i],
+                              F.mean_normal[3 * (size_t)i + 1], F.mean_normal[3 * (size_t)i + 2], F.min_d[i], F.max_d[i], rx, ry, xr, lvl);
+    else {
+        rx = ry = 0.0;
+        xr = 0.f;
+        lvl = 0;
+    }
+    F.observable[i] = ok ? 1 : 0;
+    // the query of projection::match_frame_and_landmarks (projection.cc:31-38): float reprojection, octave window, scaled margin
+    F.q_x[i] = (float)rx;
+    F.q_y[i] = (float)ry;
+    F.q_xr[i] = xr;
+    F.q_margin[i] = __fmul_rn(sh.margin, sh.scale_factors[lvl]);
+    F.q_lo[i] = (signed char)max(0, (int)lvl - 1);
+    F.q_hi[i] = (signed char)min((int)sh.num_levels - 1, (int)lvl + 1);
+    F.q_valid[i] = (unsigned char)((ok ? 1 : 0) | ((!F.lm_has_obs || F.lm_has_obs[i]) ? 2 : 0));
+}
+
 }  // namespace orb
+
+namespace chain {
+int track_stage_a(cudaStream_t st, const TrackShared& sh, const TrackFrameDev* d_frames, int n_frames, int max_kp, int max_lm) {
+    if (max_kp > 0) orb::track_keypoints_kernel<<<dim3(ceil_div(max_kp, 128), n_frames), 128, 0, st>>>(sh, d_frames);
+    if (max_lm > 0) orb::track_landmarks_kernel<<<dim3(ceil_div(max_lm, 128), n_frames), 128, 0, st>>>(sh, d_frames);
+    B200_CUDA(cudaGetLastError());
+    return B200_OK;
+}
+}  // namespace chain
 }  // namespace b200
 
 using b200::orb::Extractor;
@@ -1901,6 +2024,53 @@ int b200_orb_enable_timing(b200_orb_t h, int enable) {
     return B200_OK;
 }
 
+int b200_orb_export_keyframe_blobs(b200_orb_t h, int frame, const b200_camera_intrinsics_t* cam, b200_cv_keypoint_t* keypts_blob, uint8_t* desc_blob,
+                                   int cap, int32_t* n) {
+    if (!h || !n || cap < 0 || (cap > 0 && (!keypts_blob || !desc_blob)) || (cam && cam->model != 0 && cam->model != 1)) return B200_ERR_INVALID;
+    Extractor& ex = h->ex;
+    if (ex.width == 0 || frame < 0 || frame >= ex.last_batch) {
+        b200::set_error("b200_orb_export_keyframe_blobs: frame %d is not part of the last extract", frame);
+        return B200_ERR_INVALID;
+    }
+    B200_CUDA(cudaSetDevice(ex.prm.device));
+    const int stride = ex.res_stride();
+    const int m = std::min(cap, stride);
+    b200::orb::CamModel c{};
+    if (cam) c = b200::orb::CamModel{cam->model, cam->fx, cam->fy, cam->cx, cam->cy, cam->k1, cam->k2, cam->p1, cam->p2, cam->k3, cam->cols, cam->rows};
+    b200_cv_keypoint_t* d_blob = nullptr;
+    B200_CUDA(cudaMallocAsync((void**)&d_blob, sizeof(b200_cv_keypoint_t) * (size_t)std::max(m, 1), ex.stream));
+    cudaError_t e = cudaSuccess;
+    if (m > 0) {
+        b200::orb::keyframe_blob_kernel<<<b200::ceil_div(m, 128), 128, 0, ex.stream>>>(c, cam ? 1 : 0, ex.res_kps() + (size_t)frame * stride,
+                                                                                     ex.res_counts() + frame, m, d_blob);
+        e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(keypts_blob, d_blob, sizeof(b200_cv_keypoint_t) * (size_t)m, cudaMemcpyDeviceToHost, ex.stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(desc_blob, ex.res_descs() + (size_t)frame * stride * 32, (size_t)32 * m, cudaMemcpyDeviceToHost, ex.stream);
+    }
+    int count = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&count, ex.res_counts() + frame, sizeof(int), cudaMemcpyDeviceToHost, ex.stream);
+    cudaFreeAsync(d_blob, ex.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ex.stream);
+    if (e != cudaSuccess) return b200::cuda_fail(e, "b200_orb_export_keyframe_blobs", __FILE__, __LINE__);
+    *n = count;
+    if (count > cap) {
+        b200::set_error("b200_orb_export_keyframe_blobs: frame %d has %d keypoints, cap is %d", frame, count, cap);
+        return B200_ERR_CAPACITY;
+    }
+    return B200_OK;
+}
+
+int b200_keyframe_blob_to_keypoints(const b200_cv_keypoint_t* keypts_blob, int n, b200_keypoint_t* keypts) {
+    if (n < 0 || (n > 0 && (!keypts_blob || !keypts))) return B200_ERR_INVALID;
+    for (int i = 0; i < n; ++i) {
+        const b200_cv_keypoint_t& s = keypts_blob[i];
+        b200_keypoint_t o;
+        o.x = s.x; o.y = s.y; o.size = s.size; o.angle = s.angle; o.response = s.response; o.octave = s.octave;
+        keypts[i] = o;
+    }
+    return B200_OK;
+}
+
 int b200_orb_raw_corner_counts(b200_orb_t h, int32_t* counts, int n) {
     if (!h || !counts || n < 0) return B200_ERR_INVALID;
     n = std::min(n, h->ex.last_batch);
@@ -1918,3 +2088,23 @@ int b200_orb_stage_ms(b200_orb_t h, int stage, float* ms) {
 }
 
 }  // extern "C"
+
+namespace b200 {
+namespace chain {
+int orb_results(b200_orb_t orb, const b200_keypoint_t** d_kps, const unsigned char** d_descs, const int** d_counts, int* stride, int* batch,
+                cudaStream_t* stream, int* device) {
+    if (!orb || orb->ex.width == 0 || orb->ex.last_batch <= 0) {
+        set_error("b200_track_local_map: the extractor holds no results (call b200_orb_extract* first)");
+        return B200_ERR_INVALID;
+    }
+    *d_kps = orb->ex.res_kps();
+    *d_descs = orb->ex.res_descs();
+    *d_counts = orb->ex.res_counts();
+    *stride = orb->ex.res_stride();
+    *batch = orb->ex.last_batch;
+    *stream = orb->ex.stream;
+    *device = orb->ex.prm.device;
+    return B200_OK;
+}
+}  // namespace chain
+}  // namespace b200

@@ -39,6 +39,7 @@ def _bind():
     L.b200_lba_solve_batch.argtypes = [vp, C.c_int, C.POINTER(LbaProblem), C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(LbaStats), vp]
     L.b200_lba_last_profile.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int)]
     L.b200_pose_optimize.argtypes = [vp, C.c_int, C.POINTER(LbaProblem), C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.b200_global_ba_solve.argtypes = [vp, C.POINTER(LbaProblem), C.c_int, C.c_double, vp, vp, vp, C.POINTER(LbaStats)]
     return L
 
 
@@ -164,6 +165,47 @@ class local_bundle_adjuster:
         return dict(pose_cw=pose_out, points=pts_out, outliers=outl, iterations=list(st.iterations), n_outliers=st.n_outliers,
                     chi2=list(st.chi2), lambda_init=st.lambda_init, lambda_final=list(st.lambda_final), gpu_ms=ms.value,
                     launches=launches.value)
+
+
+class global_bundle_adjuster:
+    """optimize::global_bundle_adjuster (optimize/global_bundle_adjuster.h:18-62): one LM round over the whole map; Huber is the
+    problem's e_robust array (use_huber_kernel_)."""
+
+    def __init__(self, num_iter=10, use_huber_kernel=True, verbose=False, device=0):
+        self.num_iter_, self.use_huber_kernel_, self.verbose_ = int(num_iter), bool(use_huber_kernel), bool(verbose)
+        self._L = _bind()
+        self._h = C.c_void_p()
+        check(self._L.b200_lba_create(device, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.b200_lba_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def optimize(self, problem, force_stop_flag=None, gain_threshold=1e-3):
+        """global_bundle_adjuster::optimize (:258-420; gain threshold 1e-3) / optimize_for_initialization (:201-256; the caller's
+        gain_threshold).  Returns None when the caller's flag aborted the solve (the reference returns false), else a dict."""
+        pr = dict(problem)
+        if not self.use_huber_kernel_:
+            pr["e_robust"] = np.zeros(len(pr["e_pose"]), np.uint8)
+        P, keep = pack_problem(pr)
+        pose_out, pts_out = np.zeros((P.n_poses, 4, 4)), np.zeros((P.n_points, 3))
+        st = LbaStats()
+        rc = self._L.b200_global_ba_solve(self._h, C.byref(P), self.num_iter_, float(gain_threshold), ptr(force_stop_flag), ptr(pose_out),
+                                          ptr(pts_out), C.byref(st))
+        if rc == ERR_ABORTED:
+            return None
+        check(rc)
+        ms, launches = C.c_float(), C.c_int()
+        self._L.b200_lba_last_profile(self._h, C.byref(ms), C.byref(launches))
+        return dict(pose_cw=pose_out, points=pts_out, iterations=st.iterations[0], chi2=st.chi2[0], lambda_init=st.lambda_init,
+                    lambda_final=st.lambda_final[0], gpu_ms=ms.value, launches=launches.value)
 
 
 class pose_optimizer:

@@ -412,3 +412,70 @@ def make_stereo_pair(w=752, h=480, seed=77, disparities=(9, 23, 41), noise_sigma
     for k, d in enumerate(disparities):
         right[bands[k]:bands[k + 1]] = _render(pattern, w, h, seed + 1, (int(d), 0), noise_sigma)[bands[k]:bands[k + 1]]
     return left, right
+
+
+def make_tracking_frame(kps, desc, camera, scale_factors, seed=0, stereo=False, landmark_frac=0.7, clutter_frac=0.3, pre_matched_frac=0.15,
+                        pixel_sigma=1.0, rot_deg=0.5, trans_m=0.05, max_flips=30):
+    """A local map for one extracted frame (track_local_map workload): most keypoints get a landmark at a random depth (descriptor = the
+    keypoint's with a few flipped bits, position off by ~pixel_sigma pixels), plus clutter landmarks (random descriptors; some behind the
+    camera or outside the image), a few landmarks the frame already carries (kp_landmark, skipped by the search) and a few without
+    observations.  The pose handed to the tracker is the true pose perturbed by rot_deg / trans_m.  perspective cameras only."""
+    rng = np.random.default_rng(seed)
+    n_kp = len(kps)
+    sf = np.asarray(scale_factors, np.float64)
+    fx, fy, cx, cy = camera["fx"], camera["fy"], camera["cx"], camera["cy"]
+    Rcw = _rot_y(0.2 * rng.standard_normal()) @ _rodrigues(0.05 * rng.standard_normal(3))
+    tcw = rng.normal(0, 1.0, 3)
+    center = -Rcw.T @ tcw
+    pick = np.nonzero(rng.random(n_kp) < landmark_frac)[0]
+    z = rng.uniform(4, 40, len(pick))
+    u = kps["x"][pick].astype(np.float64) + pixel_sigma * rng.standard_normal(len(pick))
+    v = kps["y"][pick].astype(np.float64) + pixel_sigma * rng.standard_normal(len(pick))
+    pc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    n_cl = int(clutter_frac * len(pick))
+    zc = rng.uniform(-10, 60, n_cl)                                  # some behind the camera
+    uc, vc = rng.uniform(-200, camera["cols"] + 200, n_cl), rng.uniform(-100, camera["rows"] + 100, n_cl)
+    pcc = np.stack([(uc - cx) / fx * zc, (vc - cy) / fy * zc, zc], 1)
+    pc_all = np.concatenate([pc, pcc])
+    pw = (pc_all - tcw) @ Rcw
+    n_lm = len(pw)
+    ldesc = rng.integers(0, 256, (n_lm, 32), dtype=np.uint8)
+    for j, k in enumerate(pick):
+        row = desc[k].copy()
+        for b in rng.choice(256, int(rng.integers(0, max_flips + 1)), replace=False):
+            row[b >> 3] ^= np.uint8(1 << (b & 7))
+        ldesc[j] = row
+    octave = np.concatenate([kps["octave"][pick].astype(np.int64), rng.integers(0, len(sf), n_cl)])
+    dist = np.linalg.norm(pw - center, axis=1)
+    max_valid = (dist * sf[octave]).astype(np.float32)              # landmark::update_mean_normal_and_obs_scale_variance (landmark.cc:256-311)
+    min_valid = (max_valid / np.float32(sf[-1])).astype(np.float32)
+    normal = (pw - center) / np.maximum(dist, 1e-9)[:, None] + 0.2 * rng.standard_normal((n_lm, 3))
+    normal /= np.linalg.norm(normal, axis=1, keepdims=True)
+    flip = rng.random(n_lm) < 0.03                                   # seen from behind: fails the viewing-angle test
+    normal[flip] *= -1
+    kp_of = np.concatenate([pick, np.full(n_cl, -1)])
+    perm = rng.permutation(n_lm)                                     # the reference's local_landmarks_ order is arbitrary
+    pw, ldesc, max_valid, min_valid, normal, kp_of = pw[perm], ldesc[perm], max_valid[perm], min_valid[perm], normal[perm], kp_of[perm]
+    has_obs = (rng.random(n_lm) > 0.04).astype(np.uint8)
+    skip = np.zeros(n_lm, np.uint8)
+    kp_landmark = np.full(n_kp, -1, np.int32)
+    for l in np.nonzero((kp_of >= 0) & (rng.random(n_lm) < pre_matched_frac))[0]:   # carried over from the motion-model step
+        kp_landmark[kp_of[l]] = l
+        skip[l] = 1
+    skip[rng.random(n_lm) < 0.02] = 1                                # will_be_erased / temporal-ratio skips
+    kp_x_right = None
+    if stereo:
+        kp_x_right = np.full(n_kp, -1.0, np.float32)
+        zk = np.full(n_kp, np.nan)
+        zk[pick] = z
+        ok = ~np.isnan(zk) & (rng.random(n_kp) < 0.8)
+        kp_x_right[ok] = (kps["x"][ok] - camera["fxb"] / zk[ok] + 0.5 * rng.standard_normal(ok.sum())).astype(np.float32)
+    dR = _rodrigues(np.deg2rad(rot_deg) * rng.standard_normal(3) / np.sqrt(3))
+    pose = np.eye(4)
+    pose[:3, :3] = dR @ Rcw
+    pose[:3, 3] = dR @ tcw + trans_m * rng.standard_normal(3) / np.sqrt(3)
+    gt = np.eye(4)
+    gt[:3, :3], gt[:3, 3] = Rcw, tcw
+    return dict(pose_cw=pose, gt_pose_cw=gt, kp_landmark=kp_landmark, kp_x_right=kp_x_right,
+                landmarks=dict(pos_w=pw, mean_normal=normal, min_valid_dist=min_valid, max_valid_dist=max_valid, desc=ldesc, skip=skip,
+                               has_observation=has_obs))
