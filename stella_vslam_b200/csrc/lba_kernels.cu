@@ -1451,6 +1451,111 @@ __global__ void __launch_bounds__(kCholThreads) chol_solve_kernel(const WinDev* 
     }
 }
 
+// K5 (default since round 2b): the same pair-list chunks, but a chunk's block partial is formed as a small GEMM on the fp64 tensor cores:
+//        S (6 x 6 | rhs) = [T_1 ... T_P] (6 x 3P) . [H_1 | b_1 ... H_P | b_P]^T (3P x 7),   T_p = Hpl(a_p) Dinv(l_p),  H_p = Hpl(c_p)
+//     Phase 1 (lane = pair, 32 pairs per pass): load the two 160-byte records and Dinv, form T, park T and H (and bl for diagonal
+//     blocks) in the warp's shared-memory operand tiles, r-major with a row stride of 100 doubles (conflict-free fragment loads).
+//     Phase 2: 24 x mma.sync.m8n8k4.f64 (DMMA) per pass, two LDS + one DMMA per lane and step; the 8 x 8 accumulator tile lives in two
+//     registers per lane for the whole chunk.  Against the lane-per-pair kernel above this removes the 42-accumulator warp reduction
+//     (630 of ~1050 instructions per chunk) and the 168-register footprint.  Summation order is fixed => deterministic.
+constexpr int kSmmaKS = 100;                               // row stride of the operand tiles (K = 96 per pass, +4: bank spread)
+constexpr int kSmmaWarpDoubles = (6 + 7) * kSmmaKS;        // A: 6 rows, B: 7 rows (6 columns of H + the rhs column)
+__global__ void __launch_bounds__(128) schur_mma_kernel(const WinDev* __restrict__ wins) {
+    extern __shared__ __align__(16) double smma[];
+    const WinDev& W = wins[blockIdx.y];
+    const LmCtl* ctl = W.ctl;
+    if (!ctl->outer_go) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * 4 + warp;
+    const int n_blocks = W.n_blocks, n_chunks = W.blk_chunk_start[n_blocks];
+    if (wid >= n_chunks) {
+        const int e = wid - n_chunks;
+        if (e < n_blocks) {
+            const SchurBlock sb = W.blocks[e];
+            if (sb.chunk_start == sb.chunk_end) schur_finish_block(W, sb, ctl->lambda, lane);  // no pair: just Hpp + lambda I, or zero
+        }
+        return;
+    }
+    double* As = smma + (size_t)warp * kSmmaWarpDoubles;
+    double* Bs = As + 6 * kSmmaKS;
+    const SchurChunk ch = W.chunks[wid];
+    const int Lf = W.Lf;
+    const double* __restrict__ Hpl = W.Hpl;
+    const double* __restrict__ Dinv = W.Dinv;
+    const int g = lane >> 2, t4 = lane & 3;
+    const double* a_row = As + min(g, 5) * kSmmaKS + t4;  // rows 6, 7 of the tile are don't-care copies
+    const double* b_row = Bs + min(g, 6) * kSmmaKS + t4;
+    double c0 = 0.0, c1 = 0.0;
+    for (int base = ch.start; base < ch.end; base += 32) {
+        const int k = base + lane;
+        const int np = min(32, ch.end - base);
+        {
+            double t[18], hc[18], b3[3];
+            if (k < ch.end) {
+                const int4 pr = W.pairs[k];
+                double ha[18];
+                load18(Hpl + (size_t)pr.x * kHplStride, ha);
+                load18(Hpl + (size_t)pr.y * kHplStride, hc);
+                const int lc = pr.z;
+                const double D0 = Dinv[lc], D1 = Dinv[(size_t)Lf + lc], D2 = Dinv[(size_t)2 * Lf + lc];
+                const double D4 = Dinv[(size_t)3 * Lf + lc], D5 = Dinv[(size_t)4 * Lf + lc], D8 = Dinv[(size_t)5 * Lf + lc];
+#pragma unroll
+                for (int r = 0; r < 6; ++r) {
+                    t[r * 3] = ha[r * 3] * D0 + ha[r * 3 + 1] * D1 + ha[r * 3 + 2] * D2;
+                    t[r * 3 + 1] = ha[r * 3] * D1 + ha[r * 3 + 1] * D4 + ha[r * 3 + 2] * D5;
+                    t[r * 3 + 2] = ha[r * 3] * D2 + ha[r * 3 + 1] * D5 + ha[r * 3 + 2] * D8;
+                }
+                b3[0] = b3[1] = b3[2] = 0.0;
+                if (ch.diag) {
+                    b3[0] = W.bl[lc];
+                    b3[1] = W.bl[(size_t)Lf + lc];
+                    b3[2] = W.bl[(size_t)2 * Lf + lc];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 18; ++i) t[i] = hc[i] = 0.0;
+                b3[0] = b3[1] = b3[2] = 0.0;
+            }
+            double* ap = As + 3 * lane;
+            double* bp2 = Bs + 3 * lane;
+#pragma unroll
+            for (int r = 0; r < 6; ++r)
+#pragma unroll
+                for (int kk = 0; kk < 3; ++kk) {
+                    ap[r * kSmmaKS + kk] = t[r * 3 + kk];
+                    bp2[r * kSmmaKS + kk] = hc[r * 3 + kk];
+                }
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk) bp2[6 * kSmmaKS + kk] = b3[kk];
+        }
+        __syncwarp();
+        const int steps = (3 * np + 3) >> 2;  // (columns past 3 np inside the last step are zeros written by the idle lanes)
+#pragma unroll 4
+        for (int s2 = 0; s2 < steps; ++s2) dmma_m8n8k4(c0, c1, a_row[4 * s2], b_row[4 * s2]);
+        __syncwarp();
+    }
+    // accumulator tile -> chunk partial: lane (g, t4) holds S[g][2 t4], S[g][2 t4 + 1]; column 6 is the rhs part
+    double* part = W.chunk_part + (size_t)wid * 42;
+    if (g < 6) {
+        if (t4 < 3) {
+            part[g * 6 + 2 * t4] = c0;
+            part[g * 6 + 2 * t4 + 1] = c1;
+        } else {
+            part[36 + g] = c0;
+        }
+    }
+    __threadfence();
+    __syncwarp();
+    const SchurBlock sb = W.blocks[ch.block];
+    int arrived = 0;
+    if (lane == 0) arrived = atomicAdd(&W.blk_done[ch.block], 1);
+    arrived = __shfl_sync(0xFFFFFFFFu, arrived, 0);
+    if (arrived != sb.chunk_end - sb.chunk_start - 1) return;
+    __threadfence();
+    schur_finish_block(W, sb, ctl->lambda, lane);
+    if (lane == 0) W.blk_done[ch.block] = 0;  // re-armed for the next trial
+}
+
 // ---- reduced systems beyond the on-chip panel (n > kCholOnChipMax: global bundle adjustment, global_bundle_adjuster.cc:42-45) ----
 // The same blocked right-looking factorisation, one panel = two launches over the whole chip instead of one cluster:
 //   gchol_panel_kernel : every CTA factors the (tiny) diagonal block itself, solves its 256 rows of the panel, writes them
@@ -2079,6 +2184,7 @@ struct Solver {
     // Schur complement: pair lists reduced by scalar fp64 FMAs (default) or block rows with fp64 tensor-core products
     // (B200_LBA_SCHUR_MODE=rows; tuning knobs B200_LBA_SCHUR=unroll,warps,ctas)
     bool schur_rows = false;
+    int schur_mode = 0;  // 0: pair-list chunks on the fp64 tensor cores (default), 1: pair-list chunks with FMA, 2: DMMA rows
     int schur_unroll = 4, schur_warps = kSchurMaxWarps, schur_ctas = 160;
     int chol_cluster = kCholCluster;  // CTAs sharing one factorisation (B200_LBA_CLUSTER overrides: 1, 2, 4 or 8)
     bool chol_cluster_pinned = false;
@@ -2444,7 +2550,8 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
         pose_rows_kernel<<<dim3(maxKf, nw), kRowThreads, 0, st>>>(wins);
         if ((rcm = mark(2))) return rcm;
         // one LM trial (every window that is still iterating)
-        if (!S.schur_rows) schur_chunks_kernel<<<dim3(ceil_div(max_chunk_warps, 4), nw), 128, 0, st>>>(wins);
+        if (S.schur_mode == 0) schur_mma_kernel<<<dim3(ceil_div(max_chunk_warps, 4), nw), 128, 4 * kSmmaWarpDoubles * sizeof(double), st>>>(wins);
+        else if (S.schur_mode == 1) schur_chunks_kernel<<<dim3(ceil_div(max_chunk_warps, 4), nw), 128, 0, st>>>(wins);
         else if (S.schur_unroll == 2) schur_rows_kernel<2><<<dim3(maxKf, nw, max_split), 32 * schur_warps, schur_smem, st>>>(wins, schur_warps);
         else schur_rows_kernel<4><<<dim3(maxKf, nw, max_split), 32 * schur_warps, schur_smem, st>>>(wins, schur_warps);
         if ((rcm = mark(3))) return rcm;
@@ -2757,7 +2864,10 @@ int b200_lba_create(int device, b200_lba_t* out) {
             h->s.chol_cluster_pinned = true;
         }
     }
-    if (const char* sm = getenv("B200_LBA_SCHUR_MODE")) h->s.schur_rows = sm[0] == 'r';
+    if (const char* sm = getenv("B200_LBA_SCHUR_MODE")) {  // mma (default) | pairs | rows
+        h->s.schur_mode = sm[0] == 'r' ? 2 : (sm[0] == 'p' ? 1 : 0);
+        h->s.schur_rows = sm[0] == 'r';
+    }
     if (const char* sc = getenv("B200_LBA_SCHUR")) {
         int u = 4, w2 = 4, c2 = 160;
         if (sscanf(sc, "%d,%d,%d", &u, &w2, &c2) >= 1) {
