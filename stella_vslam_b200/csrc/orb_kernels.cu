@@ -303,22 +303,22 @@ __device__ __forceinline__ unsigned fast_candidates4(const unsigned (&w)[7][3], 
 __device__ __forceinline__ int fast_score1(const unsigned char* __restrict__ p, int t_low) {
     constexpr int OFF[16] = {3 * kTilePitch,     3 * kTilePitch + 1,  2 * kTilePitch + 2,  kTilePitch + 3,  3,  -kTilePitch + 3, -2 * kTilePitch + 2, -3 * kTilePitch + 1,
                              -3 * kTilePitch,    -3 * kTilePitch - 1, -2 * kTilePitch - 2, -kTilePitch - 3, -3, kTilePitch - 3,  2 * kTilePitch - 2,  3 * kTilePitch - 1};
-    int c[16];
+    // Both polarities in one pass of packed 16-bit lanes: low half = the ring pixel c, high half = 255 - c.  "min over the 16 arcs of
+    // the arc maximum" of the low halves is a (dark corners); of the high halves it is 255 - b, b = max over arcs of the arc minimum
+    // (bright corners).  40 VIMNMX3.S16x2 instead of 96 scalar min/max.
+    unsigned c[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) c[k] = p[OFF[k]];
+    for (int k = 0; k < 16; ++k) c[k] = (unsigned)p[OFF[k]] * 0xFFFF0001u + 0x00FF0000u;  // c | (255 - c) << 16
     const int v = p[0];
-    int mx3[16], mn3[16];
+    unsigned mx3[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        mx3[k] = __vimax3_s32(c[k], c[(k + 1) & 15], c[(k + 2) & 15]);
-        mn3[k] = __vimin3_s32(c[k], c[(k + 1) & 15], c[(k + 2) & 15]);
-    }
-    int a = 255, b = 0;
+    for (int k = 0; k < 16; ++k) mx3[k] = __vimax3_s16x2(c[k], c[(k + 1) & 15], c[(k + 2) & 15]);
+    unsigned ab = 0x00FF00FFu;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        a = min(a, __vimax3_s32(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]));  // min over arcs of the arc maximum
-        b = max(b, __vimin3_s32(mn3[k], mn3[(k + 3) & 15], mn3[(k + 6) & 15]));  // max over arcs of the arc minimum
-    }
+    for (int k = 0; k < 16; k += 2)  // two arcs per 3-input minimum
+        ab = __vimin3_s16x2(ab, __vimax3_s16x2(mx3[k], mx3[(k + 3) & 15], mx3[(k + 6) & 15]),
+                            __vimax3_s16x2(mx3[k + 1], mx3[(k + 4) & 15], mx3[(k + 7) & 15]));
+    const int a = (int)(ab & 0xFFFFu), b = 255 - (int)(ab >> 16);
     // max(m - t_low, 0) with m = max(v - a, b - v, 0).  The dark and the bright excess cannot both be positive (two 9-arcs of a
     // 16-circle share pixels), so the result is their sum: no max of a difference is formed, which keeps ptxas from emitting
     // VIADDMNMX with a negated addend (measured wrong on sm_100a, like the VIMNMX3 case in DESIGN.md).
@@ -498,30 +498,26 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     }
     __syncthreads();
     // phase 2: strict 3x3 local maximum of m (threshold independent), per-cell threshold choice
-    //          (orb_extractor.cc:228-235: retry the whole cell at min_fast_thr only if it is empty at ini_fast_thr)
+    //          (orb_extractor.cc:228-235: retry the whole cell at min_fast_thr only if it is empty at ini_fast_thr).
+    // Only the candidates of phase 1a can have a non-zero score, so the test walks the compacted candidate list (~10 % of the
+    // pixels) instead of the score map: one thread per candidate, eight neighbour bytes each.
     const int ini_rel = g.ini_thr - t_low, min_rel = g.min_thr - t_low;  // thresholds relative to the stored m - t_low
-    unsigned long long kept = 0;  // up to 5 words x 4 pixels per thread, one bit each
+    const int n_c = n_cand;
+    unsigned kept = 0;  // bit `it`: this thread's it-th candidate is a strict local maximum with a usable score
     bool any_ini = false;
-    const int n_words = (kTileMax - 6) * 16;  // 64 candidate rows x 16 words
     {
         int it = 0;
-        for (int idx = tid; idx < n_words; idx += kFastThreads, ++it) {
-            const int y = 3 + (idx >> 4), c0 = 4 + 4 * (idx & 15);
-            if (y > ch - 4) continue;
-            const unsigned word = *reinterpret_cast<const unsigned*>(mmap + y * kTilePitch + c0);
-            if (word == 0u) continue;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int mv = (word >> (8 * b)) & 0xFF;
-                // stored value is m - t_low; a keypoint needs score m - 1 >= 1
-                if (mv == 0 || mv + t_low < 2) continue;
-                const unsigned char* p = mmap + y * kTilePitch + c0 + b;
-                const bool is_max = mv > p[-1] && mv > p[1] && mv > p[-kTilePitch - 1] && mv > p[-kTilePitch] && mv > p[-kTilePitch + 1]
-                                    && mv > p[kTilePitch - 1] && mv > p[kTilePitch] && mv > p[kTilePitch + 1];
-                if (is_max) {
-                    kept |= 1ull << (it * 4 + b);
-                    any_ini |= (mv > ini_rel);
-                }
+        for (int i = tid; i < n_c; i += kFastThreads, ++it) {
+            const int e = cand[i];
+            const unsigned char* p = mmap + (e >> 8) * kTilePitch + (e & 0xFF);
+            const int mv = p[0];
+            // stored value is m - t_low; a keypoint needs score m - 1 >= 1
+            if (mv == 0 || mv + t_low < 2) continue;
+            const bool is_max = mv > p[-1] && mv > p[1] && mv > p[-kTilePitch - 1] && mv > p[-kTilePitch] && mv > p[-kTilePitch + 1]
+                                && mv > p[kTilePitch - 1] && mv > p[kTilePitch] && mv > p[kTilePitch + 1];
+            if (is_max) {
+                kept |= 1u << it;  // (at most 64 * 64 / 256 = 16 candidates per thread)
+                any_ini |= (mv > ini_rel);
             }
         }
     }
@@ -529,31 +525,24 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
     const int thr_rel = cell_has_ini ? ini_rel : min_rel;
     // phase 3: mask test per keypoint, selection-grid cell, ordered arg-max via 64-bit atomicMax
     int n_raw = 0;  // FAST corners this thread hands to distribute_keypoints (the C of SURVEY 8d's byte formulas)
-    if (kept) {
-        int it = 0;
-        for (int idx = tid; idx < n_words; idx += kFastThreads, ++it) {
-            const unsigned bits = (unsigned)(kept >> (it * 4)) & 0xFu;
-            if (!bits) continue;
-            const int y = 3 + (idx >> 4), c0 = 4 + 4 * (idx & 15);
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                if (!((bits >> b) & 1u)) continue;
-                const int mrel = mmap[y * kTilePitch + c0 + b];
-                if (mrel <= thr_rel) continue;
-                const int mv = mrel + t_low;
-                const int lx = c0 + b - 1, ly = y;
-                // keypt.pt += (j*64, i*64) (orb_extractor.cc:241-244): coordinates relative to the (19,19) border origin
-                const int px = lx + cd.j * kCell, py = ly + cd.i * kCell;
-                if (mask && mask_zero(mask, mask_pitch, (unsigned)(kBorder + py), (unsigned)(kBorder + px), L.sf)) continue;
-                const unsigned ix = (unsigned)((double)(float)px / L.delta_x);  // orb_extractor.cc:303-305
-                const unsigned iy = (unsigned)((double)(float)py / L.delta_y);
-                const unsigned cell = ix + iy * (unsigned)L.nx;
-                const unsigned order = ((unsigned)(cd.i * L.ncols + cd.j) << 14) | ((unsigned)ly << 7) | (unsigned)lx;
-                const unsigned long long val = ((unsigned long long)mv << 32) | (unsigned long long)(0xFFFFFFFFu - order);
-                atomicMax(grid + (size_t)frame * g.grid_cells + L.grid_base + cell, val);
-                ++n_raw;
-            }
-        }
+    while (kept) {
+        const int it = __ffs(kept) - 1;
+        kept &= kept - 1;
+        const int e = cand[tid + it * kFastThreads], y = e >> 8, c = e & 0xFF;
+        const int mrel = mmap[y * kTilePitch + c];
+        if (mrel <= thr_rel) continue;
+        const int mv = mrel + t_low;
+        const int lx = c - 1, ly = y;
+        // keypt.pt += (j*64, i*64) (orb_extractor.cc:241-244): coordinates relative to the (19,19) border origin
+        const int px = lx + cd.j * kCell, py = ly + cd.i * kCell;
+        if (mask && mask_zero(mask, mask_pitch, (unsigned)(kBorder + py), (unsigned)(kBorder + px), L.sf)) continue;
+        const unsigned ix = (unsigned)((double)(float)px / L.delta_x);  // orb_extractor.cc:303-305
+        const unsigned iy = (unsigned)((double)(float)py / L.delta_y);
+        const unsigned cell = ix + iy * (unsigned)L.nx;
+        const unsigned order = ((unsigned)(cd.i * L.ncols + cd.j) << 14) | ((unsigned)ly << 7) | (unsigned)lx;
+        const unsigned long long val = ((unsigned long long)mv << 32) | (unsigned long long)(0xFFFFFFFFu - order);
+        atomicMax(grid + (size_t)frame * g.grid_cells + L.grid_base + cell, val);
+        ++n_raw;
     }
     if (raw_corners) {
 #pragma unroll
