@@ -2631,24 +2631,23 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
             outlier_kernel<<<dim3(ceil_div(maxE, 128), nw), 128, 0, st>>>(wins, 0);  // :323-344 (skips itself after an abort)
             ++launches;
         }
-        // repetitions of {build; trial}, enqueued in chunks; the read-back of chunk k is awaited only after chunk k+1 is enqueued
+        // repetitions of {build; trial}: a round of `iterations` LM iterations needs at least that many trials unless it stops early, so
+        // that many repetitions are enqueued (in chunks of at most six) before the control blocks are read back; a window that stops
+        // early lets the rest of its chunk run empty (every kernel returns on its control block) and only rejected trials need more.
+        // (Round 2a enqueued speculative chunks ahead of every read-back: 5 of 20 repetitions of the bench window ran empty, ~90 us
+        // each for 16 windows.)
         if (iters[r] > 0) {
-            const int first = std::min(iters[r], 4), later = 2;
-            int b = 0;
-            for (int i = 0; i < first; ++i)
-                if ((rc2 = launch_rep())) return rc2;
-            if ((rc2 = fetch_issue(b))) return rc2;
+            int need = iters[r];
             for (;;) {
-                for (int i = 0; i < later; ++i)
+                const int chunk = std::max(1, std::min(need, 6));  // (bounded: an early gain stop wastes at most five repetitions)
+                for (int i = 0; i < chunk; ++i)
                     if ((rc2 = launch_rep())) return rc2;
-                if ((rc2 = fetch_issue(b ^ 1))) return rc2;
-                if ((rc2 = fetch_wait(b))) return rc2;
-                bool any = false;
-                for (int x = 0; x < nw; ++x) any = any || h_ctl[x].outer_go;
-                b ^= 1;
-                if (!any) break;
+                if ((rc2 = fetch_ctl())) return rc2;
+                need = 0;
+                for (int x = 0; x < nw; ++x)
+                    if (h_ctl[x].outer_go) need = std::max(need, std::max(1, h_ctl[x].iterations - h_ctl[x].it));
+                if (need == 0) break;
             }
-            if ((rc2 = fetch_wait(b))) return rc2;  // (the chunk enqueued last ran empty; its read-back is the final state)
         }
         landmark_kernel<kRoundEnd><<<dim3(max_lbc, nw), kLmThreads, 0, st>>>(wins);  // chi2 of every active edge at the final state
         lm_round_end_kernel<<<nw, 256, 0, st>>>(wins, r);

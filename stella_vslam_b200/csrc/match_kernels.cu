@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kRowsPerBlock) topk_kernel(Side S1, Side S2, c
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTcRows = 128;        // keyframe rows per CTA (one M tile); two CTAs share an SM: one stages / waits while the other selects
 constexpr int kTcChunk = 128;       // frame keypoints per B chunk (= N of the MMA)
-constexpr int kTcThreads = 128;
+constexpr int kTcThreads = 256;     // two warps per TMEM lane quarter: each takes one half of a chunk's 128 columns
 constexpr unsigned kTcTmemCols = 256;  // two accumulator buffers of 128 columns (two resident CTAs use all 512)
 constexpr int kTcTileBytes = 128 * 256;  // one 128-row operand tile of +-1 bytes
 struct TcSmem {
@@ -252,24 +252,22 @@ __global__ void __launch_bounds__(kTcThreads, 2) topk_tc_kernel(Side S1, Side S2
         }
     }
     __syncthreads();
-    const int my_row = row0 + tid;                  // thread = keyframe row = TMEM lane
+    // thread = (keyframe row = TMEM lane, column half): warps 0-3 select from columns 0-63 of every chunk, warps 4-7 from 64-127 (a warp
+    // may only read the TMEM lanes of its quarter, warp % 4); the two half lists of a row are merged at the end.  Eight resident warps
+    // per CTA instead of four: the selection pass is latency-bound (LDTM, dependent compare chains), not issue-bound.
+    const int rtid = tid & 127, half = tid >> 7;
+    const int my_row = row0 + rtid;
     const bool active = my_row < n2 && (!valid2 || valid2[b2 + my_row]);
     {
-        uint4 h0 = make_uint4(0, 0, 0, 0), h1 = h0;
+        // A operand: each thread expands ONE 16-byte half of its row's descriptor (8 of the 16 K-chunks)
         const bool real = my_row < n2;
-        if (real) {
-            h0 = desc2[(size_t)(b2 + my_row) * 2];
-            h1 = desc2[(size_t)(b2 + my_row) * 2 + 1];
-        }
         unsigned char* tile = sm.a;
-        const int r = tid;
         if (real) {
-            tc_expand_half(tile, sm.lut, r, 0, h0);
-            tc_expand_half(tile, sm.lut, r, 8, h1);
+            tc_expand_half(tile, sm.lut, rtid, 8 * half, desc2[(size_t)(b2 + my_row) * 2 + half]);
         } else {  // rows past the keyframe: zeros (their lists are never written)
-            unsigned char* dst = tile + (r >> 3) * 128 + (r & 7) * 16;
+            unsigned char* dst = tile + (rtid >> 3) * 128 + (rtid & 7) * 16;
 #pragma unroll
-            for (int c = 0; c < 16; ++c) *reinterpret_cast<uint4*>(dst + c * 2048) = make_uint4(0, 0, 0, 0);
+            for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + (8 * half + c) * 2048) = make_uint4(0, 0, 0, 0);
         }
     }
     const float qa = active ? side_angle(S2, b2 + my_row) : 0.f;
@@ -289,31 +287,28 @@ __global__ void __launch_bounds__(kTcThreads, 2) topk_tc_kernel(Side S1, Side S2
     unsigned tmem = 0;
     // the descriptor bits (and angle) of this thread's row of the NEXT chunk are fetched one iteration ahead: the L2 latency hides behind
     // the selection pass instead of standing in front of the tensor core
-    uint4 nb0 = make_uint4(0, 0, 0, 0), nb1 = nb0;
+    uint4 nb = make_uint4(0, 0, 0, 0);
     float nang = 0.f;
-    if (tid < n1) {
-        nb0 = desc1[(size_t)(b1 + tid) * 2];
-        nb1 = desc1[(size_t)(b1 + tid) * 2 + 1];
-        nang = side_angle(S1, b1 + tid);
+    if (rtid < n1) {
+        nb = desc1[(size_t)(b1 + rtid) * 2 + half];
+        if (half == 0) nang = side_angle(S1, b1 + rtid);
     }
     for (int c = 0; c <= n_chunks; ++c) {
         if (c < n_chunks) {
             // B operand of chunk c: 128 frame keypoints, thread = row
-            const int buf = c & 1, r = tid, j = c * kTcChunk + r;
+            const int buf = c & 1, r = rtid, j = c * kTcChunk + r;
             if (j < n1) {
-                tc_expand_half(sm.b[buf], sm.lut, r, 0, nb0);
-                tc_expand_half(sm.b[buf], sm.lut, r, 8, nb1);
-                sm.ang[c % 3][r] = nang;
+                tc_expand_half(sm.b[buf], sm.lut, r, 8 * half, nb);
+                if (half == 0) sm.ang[c % 3][r] = nang;
             } else {
                 unsigned char* dst = sm.b[buf] + (r >> 3) * 128 + (r & 7) * 16;
 #pragma unroll
-                for (int cc = 0; cc < 16; ++cc) *reinterpret_cast<uint4*>(dst + cc * 2048) = make_uint4(0, 0, 0, 0);
+                for (int cc = 0; cc < 8; ++cc) *reinterpret_cast<uint4*>(dst + (8 * half + cc) * 2048) = make_uint4(0, 0, 0, 0);
             }
             const int jn = j + kTcChunk;
             if (jn < n1) {
-                nb0 = desc1[(size_t)(b1 + jn) * 2];
-                nb1 = desc1[(size_t)(b1 + jn) * 2 + 1];
-                nang = side_angle(S1, b1 + jn);
+                nb = desc1[(size_t)(b1 + jn) * 2 + half];
+                if (half == 0) nang = side_angle(S1, b1 + jn);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core's async proxy
         }
@@ -337,16 +332,17 @@ __global__ void __launch_bounds__(kTcThreads, 2) topk_tc_kernel(Side S1, Side S2
             const int e = c - 1, buf = e & 1, c0 = e * kTcChunk;
             tc_mbar_wait(&sm.bar[buf], (unsigned)(e >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const unsigned taddr = tmem + ((unsigned)(warp * 32) << 16) + (unsigned)(buf * kTcChunk);
+            const unsigned taddr = tmem + ((unsigned)((warp & 3) * 32) << 16) + (unsigned)(buf * kTcChunk + half * (kTcChunk / 2));
             // key = distance << 22 | index with distance = (256 - dot) / 2:  (256 - dot) << 21 has bit 21 clear (the dot product of two
             // +-1 vectors of even length is even), so the key is one multiply-add.  Four keys are tested against the row's threshold with
             // one 3-input minimum, one compare and one warp vote; only a group that holds a candidate for some row of the warp inserts.
             // The threshold starts at the distance cap (see below), so candidates are rare: a warp's 32 rows see a few dozen in all.
-            const unsigned kbase = (256u << 21) + (unsigned)c0;
+            const int ch0 = c0 + half * (kTcChunk / 2);  // first frame keypoint of this thread's half of the chunk
+            const unsigned kbase = (256u << 21) + (unsigned)ch0;
             auto scan = [&](auto full_chunk) {
 #pragma unroll 1
-                for (int g = 0; g < kTcChunk / 32; ++g) {
-                    if (!decltype(full_chunk)::value && c0 + 32 * g >= n1) break;
+                for (int g = 0; g < kTcChunk / 64; ++g) {
+                    if (!decltype(full_chunk)::value && ch0 + 32 * g >= n1) break;
                     unsigned v[32];
                     tc_ld32(taddr + 32 * g, v);
 #pragma unroll
@@ -355,14 +351,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) topk_tc_kernel(Side S1, Side S2
 #pragma unroll
                         for (int u = 0; u < 4; ++u) {
                             key[u] = (unsigned)((int)v[i + u] * -(1 << 21)) + (kbase + (unsigned)(32 * g + i + u));
-                            if (!decltype(full_chunk)::value && c0 + 32 * g + i + u >= n1) key[u] = kInfKey;  // zero padding of the last chunk
+                            if (!decltype(full_chunk)::value && ch0 + 32 * g + i + u >= n1) key[u] = kInfKey;  // zero padding of the last chunk
                         }
                         const unsigned m4 = min(__vimin3_u32(key[0], key[1], key[2]), key[3]);
                         if (__any_sync(0xFFFFFFFFu, m4 < thr)) {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 if (key[u] < thr) {
-                                    if (check_orientation && orientation_rejects(sm.ang[e % 3][32 * g + i + u], qa)) continue;
+                                    if (check_orientation && orientation_rejects(sm.ang[e % 3][half * (kTcChunk / 2) + 32 * g + i + u], qa)) continue;
                                     top[kTopK - 1] = key[u];
 #pragma unroll
                                     for (int k = kTopK - 1; k > 0; --k) {
@@ -383,14 +379,38 @@ __global__ void __launch_bounds__(kTcThreads, 2) topk_tc_kernel(Side S1, Side S2
             else scan(std::false_type{});
         }
     }
-    // lists shorter than 8: the slots name no candidate but state the bound "everything else is farther than the cap"
+    // merge the two half lists of every row: the upper half parks its (sorted) keys in the B staging area, the lower half inserts them
+    __syncthreads();  // (nobody reads the operand tiles any more: the last MMA was committed and waited for)
+    unsigned* park = reinterpret_cast<unsigned*>(sm.b[0]);
+    if (half == 1) {
 #pragma unroll
-    for (int k = 0; k < kTopK; ++k)
-        if (top[k] == kInfKey && cap < (unsigned)kMaxDist) top[k] = make_key(cap + 1u, kSentinelIdx);
-    if (my_row < n2) {
-        unsigned* o = lists + ((size_t)p * list_rows + my_row) * kTopK;
+        for (int k = 0; k < kTopK; ++k) park[k * 128 + rtid] = top[k];
+    }
+    __syncthreads();
+    if (half == 0) {
 #pragma unroll
-        for (int k = 0; k < kTopK; ++k) o[k] = top[k];
+        for (int k2 = 0; k2 < kTopK; ++k2) {
+            const unsigned key = park[k2 * 128 + rtid];
+            if (key >= top[kTopK - 1]) continue;  // (both lists ascending: nothing after this one can enter either, but the unrolled form is branch-light)
+            top[kTopK - 1] = key;
+#pragma unroll
+            for (int k = kTopK - 1; k > 0; --k) {
+                if (top[k] < top[k - 1]) {
+                    const unsigned t2 = top[k];
+                    top[k] = top[k - 1];
+                    top[k - 1] = t2;
+                }
+            }
+        }
+        // lists shorter than 8: the slots name no candidate but state the bound "everything else is farther than the cap"
+#pragma unroll
+        for (int k = 0; k < kTopK; ++k)
+            if (top[k] == kInfKey && cap < (unsigned)kMaxDist) top[k] = make_key(cap + 1u, kSentinelIdx);
+        if (my_row < n2) {
+            unsigned* o = lists + ((size_t)p * list_rows + my_row) * kTopK;
+#pragma unroll
+            for (int k = 0; k < kTopK; ++k) o[k] = top[k];
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
