@@ -158,7 +158,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-        from workloads import synth
+    from workloads import synth
     frames = synth.make_stream(8, W, H, stream=0)
     min_area = args.min_area or 7000
     # calibrate min_area with the oracle itself (no GPU code on this arm)
