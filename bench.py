@@ -677,7 +677,7 @@ def main():
                 "ms_per_step": 1e3 * e2e_s / args.steps, "repeats_ms_per_step": [1e3 * t / args.steps for t in e2e_runs],
                 "note": "synchronous host-buffer calls b200_orb_extract / b200_match_bruteforce / b200_lba_solve_batch; the matcher call of "
                         "step k runs on a worker thread while step k+1 uploads and extracts (two host result sets); all joined inside the timed region"},
-        "gpu_launches": 13 * args.steps + lba_launches_value,
+        "gpu_launches": 12 * args.steps + lba_launches_value,   # per step: 7 resize + FAST + select + describe + top-K + resolve
         "roofline": roofline,
         "cpu_baseline": cpu,
         "cpu_baseline_1thread": cpu1,

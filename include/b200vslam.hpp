@@ -327,8 +327,57 @@ public:
         return true;
     }
 
+    // many windows per launch sequence (b200_lba_solve_batch); ok[w] = false for windows whose flag was already set
+    void optimize_batch(const std::vector<b200_lba_problem_t>& problems, const std::vector<volatile uint8_t*>& force_stop_flags,
+                        std::vector<std::vector<double>>& pose_cw_out, std::vector<std::vector<double>>& points_out,
+                        std::vector<std::vector<uint8_t>>& outlier_out, std::vector<bool>& ok) const {
+        const size_t n = problems.size();
+        pose_cw_out.resize(n); points_out.resize(n); outlier_out.resize(n);
+        std::vector<double*> pp(n), qq(n);
+        std::vector<uint8_t*> oo(n);
+        std::vector<int32_t> status(n, 0);
+        for (size_t w = 0; w < n; ++w) {
+            pose_cw_out[w].resize((size_t)16 * problems[w].n_poses);
+            points_out[w].resize((size_t)3 * problems[w].n_points);
+            outlier_out[w].resize((size_t)(problems[w].n_edges > 0 ? problems[w].n_edges : 1));
+            pp[w] = pose_cw_out[w].data(); qq[w] = points_out[w].data(); oo[w] = outlier_out[w].data();
+        }
+        const int rc = b200_lba_solve_batch(h_, (int)n, problems.data(), (int)num_first_iter_, (int)num_second_iter_,
+                                            force_stop_flags.empty() ? nullptr : force_stop_flags.data(), pp.data(), qq.data(), oo.data(), nullptr, status.data());
+        ok.assign(n, true);
+        for (size_t w = 0; w < n; ++w)
+            if (status[w] == B200_ERR_ABORTED) ok[w] = false;
+            else if (status[w] != B200_OK) check(status[w], "b200_lba_solve_batch");
+        if (rc != B200_OK && rc != B200_ERR_ABORTED) check(rc, "b200_lba_solve_batch");
+    }
+
 private:
     const unsigned int num_first_iter_, num_second_iter_;
+    b200_lba_t h_ = nullptr;
+};
+
+class global_bundle_adjuster {  // optimize/global_bundle_adjuster.h:18-62
+public:
+    explicit global_bundle_adjuster(unsigned int num_iter = 10, bool use_huber_kernel = true, int device = 0)
+        : num_iter_(num_iter), use_huber_kernel_(use_huber_kernel) {
+        check(b200_lba_create(device, &h_), "b200_lba_create");
+    }
+    ~global_bundle_adjuster() { b200_lba_destroy(h_); }
+    global_bundle_adjuster(const global_bundle_adjuster&) = delete;
+    // one LM round over the flattened map (problem.e_robust carries use_huber_kernel per edge); false = aborted by the caller's flag
+    bool optimize(const b200_lba_problem_t& problem, volatile uint8_t* force_stop_flag, std::vector<double>& pose_cw_out, std::vector<double>& points_out,
+                  double gain_threshold = 1e-3) const {
+        pose_cw_out.resize((size_t)16 * problem.n_poses);
+        points_out.resize((size_t)3 * problem.n_points);
+        const int rc = b200_global_ba_solve(h_, &problem, (int)num_iter_, gain_threshold, force_stop_flag, pose_cw_out.data(), points_out.data(), nullptr);
+        if (rc == B200_ERR_ABORTED) return false;
+        check(rc, "b200_global_ba_solve");
+        return true;
+    }
+    const unsigned int num_iter_;
+    const bool use_huber_kernel_;
+
+private:
     b200_lba_t h_ = nullptr;
 };
 
@@ -350,6 +399,7 @@ public:
         for (int e = 0; e < frame.n_edges; ++e) outlier_flags[e] = flags[e] != 0;
         return n_valid;
     }
+    b200_lba_t handle() const { return h_; }
 
 private:
     const unsigned int num_trials_robust_, num_trials_, num_each_iter_;
@@ -357,4 +407,22 @@ private:
 };
 
 }  // namespace optimize
+
+namespace tracking {
+// tracking_module::search_local_landmarks + pose_optimizer::optimize for a batch of frames that stay on the GPU (b200_track_local_map)
+class local_map_tracker {
+public:
+    local_map_tracker(const feature::orb_extractor& extractor, const b200_track_params_t& params, int device = 0)
+        : ex_(extractor), prm_(params), m_(device), opt_(params.num_trials_robust, params.num_trials, params.num_each_iter, device) {}
+    void track(std::vector<b200_track_frame_t>& frames) {
+        check(b200_track_local_map(ex_.handle(), m_.get(), opt_.handle(), &prm_, (int)frames.size(), frames.data()), "b200_track_local_map");
+    }
+
+private:
+    const feature::orb_extractor& ex_;
+    b200_track_params_t prm_;
+    match::device_matcher m_;
+    optimize::pose_optimizer opt_;
+};
+}  // namespace tracking
 }  // namespace b200

@@ -1,5 +1,6 @@
 // Compiles against include/b200vslam.hpp only (no OpenCV/Eigen).  Without a GPU it checks the "fails loudly" contract;
 // with a GPU it runs one extract + match + tiny BA through the C++ mirror classes.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -66,6 +67,45 @@ int main() {
         for (size_t i = 0; i < kps.size(); ++i) ok += xr[i] >= 0.f && xr[i] <= kps[i].x && depth[i] > 0.f;
         std::printf("stereo matches %zu\n", ok);
         if (ok < kps.size() / 8) return 10;
+    }
+    // tracking chain through the C++ mirror: every keypoint back-projected to depth 10 m with the identity pose is a landmark that
+    // reprojects onto itself, carries its own descriptor and is observable: the chain must attach (almost) all of them and keep the pose
+    {
+        const int n = (int)kps.size();
+        const double fx = 500.0, fy = 500.0, cx = 320.0, cy = 240.0;
+        std::vector<double> pos(3 * (size_t)n), nrm(3 * (size_t)n);
+        std::vector<float> lo(n), hi(n);
+        for (int i = 0; i < n; ++i) {
+            const double z = 10.0, X = (kps[i].x - cx) / fx * z, Y = (kps[i].y - cy) / fy * z, d = std::sqrt(X * X + Y * Y + z * z);
+            pos[3 * i] = X; pos[3 * i + 1] = Y; pos[3 * i + 2] = z;
+            nrm[3 * i] = X / d; nrm[3 * i + 1] = Y / d; nrm[3 * i + 2] = z / d;
+            hi[i] = (float)(d * prm.scale_factors_[kps[i].octave]);
+            lo[i] = hi[i] / prm.scale_factors_[7];
+        }
+        b200_track_params_t tp{};
+        tp.cam.model = 0; tp.cam.fx = fx; tp.cam.fy = fy; tp.cam.cx = cx; tp.cam.cy = cy; tp.cam.cols = w; tp.cam.rows = h;
+        tp.monocular = 1;
+        tp.img_bounds[0] = 0.f; tp.img_bounds[1] = (float)w; tp.img_bounds[2] = 0.f; tp.img_bounds[3] = (float)h;
+        tp.grid_cols = 64; tp.grid_rows = 48;
+        tp.num_levels = 8; tp.log_scale_factor = std::log(1.2f);
+        tp.scale_factors = prm.scale_factors_.data(); tp.inv_level_sigma_sq = prm.inv_level_sigma_sq_.data();
+        tp.margin = 5.0f; tp.lowe_ratio = 0.8f; tp.hamming_thr = 100; tp.ray_cos_thr = 0.5f;
+        tp.num_trials_robust = 2; tp.num_trials = 2; tp.num_each_iter = 10;
+        const double pose[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+        std::vector<uint8_t> observable(n), outlier(n);
+        std::vector<int32_t> slots(n, -2);
+        ex.extract(img.data(), w, h, w, nullptr, 0, kps, desc);  // (the chain reads the extractor's LAST batch)
+        b200_track_frame_t f{};
+        f.frame = 0; f.pose_cw = pose; f.n_landmarks = n; f.lm_pos_w = pos.data(); f.lm_mean_normal = nrm.data();
+        f.lm_min_valid_dist = lo.data(); f.lm_max_valid_dist = hi.data(); f.lm_desc = desc.data(); f.kp_cap = n;
+        f.lm_observable = observable.data(); f.kp_landmark_out = slots.data(); f.kp_outlier = outlier.data();
+        std::vector<b200_track_frame_t> frames(1, f);
+        b200::tracking::local_map_tracker tracker(ex, tp);
+        tracker.track(frames);
+        std::printf("tracking matches %d inliers %u\n", frames[0].n_matches, frames[0].n_valid);
+        if (frames[0].n_keypoints != n || frames[0].n_matches < n / 2 || frames[0].n_valid < (unsigned)(n / 2)) return 11;
+        for (int r = 0; r < 3; ++r)
+            if (std::fabs(frames[0].pose_cw_out[4 * r + 3]) > 1e-2) return 12;  // exact observations: the pose stays at the identity
     }
     std::vector<uint8_t> empty_desc;
     ex.extract(nullptr, 0, 0, 0, nullptr, 0, kps, empty_desc);  // empty image: silent return

@@ -29,4 +29,4 @@ def test_cpp_mirror_runs_on_gpu(tmp_path):
     exe = _build(tmp_path)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "keypoints" in r.stdout and "self matches" in r.stdout and "projection matches" in r.stdout and "stereo matches" in r.stdout
+    assert "keypoints" in r.stdout and "self matches" in r.stdout and "projection matches" in r.stdout and "stereo matches" in r.stdout and "tracking matches" in r.stdout
