@@ -144,24 +144,28 @@ __global__ void __launch_bounds__(128) resize_kernel(const __grid_constant__ Geo
     const int dy0 = blockIdx.y * kRzRows;
     if (dxq >= L.pitch) return;
     const int n_valid = min(4, L.w - dxq);  // <= 0 in the padding columns (written as zero)
-    int ofs[4], ofs1[4], w0[4], w1[4];
+    // The padding columns re-use the taps of the last valid column (in-bounds loads, no per-column predicates); their bytes are
+    // masked to zero at the store.
+    const unsigned store_mask = n_valid >= 4 ? 0xFFFFFFFFu : (n_valid <= 0 ? 0u : ((1u << (8 * n_valid)) - 1u));
+    int ofs[4], ofs1[4];
+    unsigned w01[4];  // w0 | w1 << 16: the horizontal tap pair as the 16-bit operand of one DP2A
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const ResizeTap t = taps[L.tab_x + min(dxq + k, L.w - 1)];
         ofs[k] = t.ofs;
         ofs1[k] = min((int)t.ofs + 1, sw - 1);  // weight 0 there
-        w0[k] = t.w0;
-        w1[k] = t.w1;
+        w01[k] = ((unsigned)t.w0 & 0xFFFFu) | ((unsigned)t.w1 << 16);
     }
     int rowA = -1, rowB = -1;  // clipped source rows whose horizontal interpolation is cached
-    int hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
-    auto hrow = [&](int sy, int (&h)[4]) {
+    unsigned hA[4] = {0, 0, 0, 0}, hB[4] = {0, 0, 0, 0};
+    auto hrow = [&](int sy, unsigned (&h)[4]) {
         const unsigned char* r = src + (size_t)sy * spitch;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) h[k] = (k < n_valid) ? ((int)r[ofs[k]] * w0[k] + (int)r[ofs1[k]] * w1[k]) >> 4 : 0;
+        for (int k = 0; k < 4; ++k) h[k] = __dp2a_lo(w01[k], (unsigned)r[ofs[k]] | ((unsigned)r[ofs1[k]] << 8), 0u) >> 4;
     };
     const int dy_end = min(dy0 + kRzRows, L.h);
-    for (int dy = dy0; dy < dy_end; ++dy) {
+    unsigned char* drow = dst + (size_t)dy0 * L.pitch + dxq;
+    for (int dy = dy0; dy < dy_end; ++dy, drow += L.pitch) {
         const ResizeTap ty = taps[L.tab_y + dy];
         const int s0 = min(max((int)ty.ofs, 0), sh - 1), s1 = min(max((int)ty.ofs + 1, 0), sh - 1);  // rows clipped like OpenCV
         if (s0 != rowA) {
@@ -182,13 +186,13 @@ __global__ void __launch_bounds__(128) resize_kernel(const __grid_constant__ Geo
             }
             rowB = s1;
         }
+        // ((b0 * S0) >> 16) as the high half of (b0 << 16) * S0: weights are in [0, 2048] and S in [0, 32640], so everything is
+        // non-negative and the result (<= 255: the weights of a pair sum to 2048) needs no saturation
+        const unsigned b0 = (unsigned)(int)ty.w0 << 16, b1 = (unsigned)(int)ty.w1 << 16;
         unsigned out = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int val = (((ty.w0 * hA[k]) >> 16) + ((ty.w1 * hB[k]) >> 16) + 2) >> 2;
-            out |= (unsigned)min(max(val, 0), 255) << (8 * k);
-        }
-        *reinterpret_cast<unsigned*>(dst + (size_t)dy * L.pitch + dxq) = out;
+        for (int k = 0; k < 4; ++k) out |= ((__umulhi(b0, hA[k]) + __umulhi(b1, hB[k]) + 2u) >> 2) << (8 * k);
+        *reinterpret_cast<unsigned*>(drow) = out & store_mask;
     }
 }
 
