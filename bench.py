@@ -613,12 +613,20 @@ def main():
                            "alg_bytes_per_unit": float(lba_alg[nm]), "units_per_launch": lba_batch_windows, "ms_per_launch": per_launch,
                            "achieved_gbs": gbs, "frac": gbs / peak_gbs}
     dom = max(kernels, key=lambda k_: kernels[k_]["ms_per_step"])
+    # DRAM traffic per launch of every kernel from the committed `ncu --set full` captures of the same kernels at the same sizes
+    # (profiles/r2_ncu_full_*.csv: dram__bytes_read.sum + dram__bytes_write.sum; 64 frames / 16 windows per launch like `achieved`).
+    # ncu replays kernels, so the capture cannot be re-taken inside a timed bench; the file travels with the repository.
+    traffic = ncu_traffic_per_launch()
+    for nm, tb in traffic.items():
+        if nm in kernels:
+            kernels[nm]["dram_bytes_per_launch_ncu"] = tb
     roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak_gbs, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": kernels[dom]["frac"], "traffic": traffic.get(dom), "traffic_source": "profiles/r2_ncu_full_{frontend,lba}.csv" if dom in traffic else None,
+                "peak_source": peak_src,
                 "note": ("per-kernel times come from an uncontended pass after the timed regions (front end alone; one batch of "
                          f"{lba_batch_windows} local-BA windows alone, profiling mode); dominant = largest device time per step over ALL kernels. "
                          "FAST is integer-ALU-bound and the matcher POPC-bound by construction; the HBM fraction is reported as the contract asks. "
-                         "traffic: see profiles/ (ncu --set full captures are not re-taken inside the bench)"),
+                         "traffic: bytes per launch from the committed ncu captures (profiles/), not re-measured in this run"),
                 "kernels": kernels}
 
     cpu = cpu1 = cv2_stage = None
@@ -689,6 +697,35 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def ncu_traffic_per_launch():
+    """kernel name of `roofline.kernels` -> DRAM bytes (read + write) per launch, from profiles/r2_ncu_full_*.csv (tools/ncu_summary.py)."""
+    import csv
+    names = {"resize_kernel": "pyramid", "fast_cells_kernel": "fast_nms_gridmax", "select_kernel": "select", "describe_kernel": "blur_orient_describe",
+             "topk_tc_kernel": "match_topk", "resolve_kernel": "match_resolve", "landmark_kernel<0>": "lba_landmark_build", "pose_rows_kernel": "lba_pose_rows",
+             "schur_mma_kernel": "lba_schur", "chol_solve_kernel": "lba_cholesky", "backsub_kernel": "lba_backsub", "landmark_kernel<1>": "lba_trial_chi2"}
+    out, seen = {}, {}
+    for fn in ("r2_ncu_full_frontend.csv", "r2_ncu_full_lba.csv"):
+        path = os.path.join(ROOT, "profiles", fn)
+        if not os.path.exists(path):
+            continue
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        scale = {"Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Gbyte": 1e9}
+        for r in rows[2:]:
+            key = next((v for k, v in names.items() if k in r[ik]), None)
+            if key is None:
+                continue
+            b = float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
+            if key == "pyramid":     # seven launches per step: sum the first seven
+                if seen.get(key, 0) < 7:
+                    out[key] = out.get(key, 0.0) + b
+                    seen[key] = seen.get(key, 0) + 1
+            elif key not in out:
+                out[key] = b
+    return out
 
 
 def peak_for_tracking():
