@@ -2184,6 +2184,7 @@ struct Solver {
     // Schur complement: pair lists reduced by scalar fp64 FMAs (default) or block rows with fp64 tensor-core products
     // (B200_LBA_SCHUR_MODE=rows; tuning knobs B200_LBA_SCHUR=unroll,warps,ctas)
     bool schur_rows = false;
+    bool force_offchip = false;
     int schur_mode = 0;  // 0: pair-list chunks on the fp64 tensor cores (default), 1: pair-list chunks with FMA, 2: DMMA rows
     int schur_unroll = 4, schur_warps = kSchurMaxWarps, schur_ctas = 160;
     int chol_cluster = kCholCluster;  // CTAs sharing one factorisation (B200_LBA_CLUSTER overrides: 1, 2, 4 or 8)
@@ -2394,7 +2395,7 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
         o.Dinv = cv.take<double>(6 * Lf); o.Hpp = cv.take<double>(36 * Kf); o.bp = cv.take<double>(6 * Kf);
         o.M = cv.take<double>((size_t)(h.n + 1) * h.ld); o.xp = cv.take<double>(h.n);
         o.gP = o.gD = o.ginvd = 0;
-        if (h.n > kCholOnChipMax) {
+        if (h.n > kCholOnChipMax || S.force_offchip) {
             o.gP = cv.take<double>((size_t)kNB * ((h.n + 1 + 3) & ~3));
             o.gD = cv.take<double>(kNB * (kNB + 1));
             o.ginvd = cv.take<double>(h.n);
@@ -2530,7 +2531,7 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
     }
     if ((rc = mark(0))) return rc;
     // ---- LM rounds in lockstep ---------------------------------------------------------------------------------------------------
-    const bool large = max_n > kCholOnChipMax;
+    const bool large = max_n > kCholOnChipMax || S.force_offchip;  // (B200_LBA_FORCE_OFFCHIP: the panel-by-panel path on any size, for tests)
     const size_t chol_smem = sizeof(double) * ((size_t)kNB * (kNB + 1) + 4 + (size_t)((std::min(max_n, kCholOnChipMax) + 1 + 3) & ~3) * kNB);
     B200_CUDA(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chol_smem));
     // warps per Schur row CTA: every warp owns Kf accumulator tiles of 512 bytes
@@ -2863,6 +2864,7 @@ int b200_lba_create(int device, b200_lba_t* out) {
             h->s.chol_cluster_pinned = true;
         }
     }
+    if (const char* fo = getenv("B200_LBA_FORCE_OFFCHIP")) h->s.force_offchip = fo[0] == '1';
     if (const char* sm = getenv("B200_LBA_SCHUR_MODE")) {  // mma (default) | pairs | rows
         h->s.schur_mode = sm[0] == 'r' ? 2 : (sm[0] == 'p' ? 1 : 0);
         h->s.schur_rows = sm[0] == 'r';

@@ -8,7 +8,7 @@ compute-sanitizer (tools/evidence_r2.sh):
 
 The full `pytest -m gpu` suite is 50-100x slower under the sanitizer than the GPU budget allows; these cases keep every kernel,
 the claim tables of the resolve kernels, the last-CTA control kernels of the local BA and the cluster barrier of the Cholesky in
-play at sizes that finish in minutes.  Select families with argv (orb match guided pairs stereo lba pose); default = all."""
+play at sizes that finish in minutes.  Select families with argv (orb match guided pairs stereo lba global_ba track pose); default = all."""
 import os
 import sys
 import time
@@ -116,6 +116,34 @@ def case_lba():
     return len(prs)
 
 
+def case_global_ba():
+    os.environ["B200_LBA_FORCE_OFFCHIP"] = "1"           # the panel-by-panel Cholesky of the global bundle adjuster on a small map
+    try:
+        pr = synth.make_ba_problem(8, 1, 150, seed=21, model="stereo")
+        got = optimize.global_bundle_adjuster(4).optimize(pr)
+        ref = O.global_ba_solve(pr, 4)
+        assert got["iterations"] == ref["iterations"]
+        assert np.abs(got["points"] - ref["points"]).max() <= 1e-5 * max(1.0, np.abs(ref["points"]).max())
+    finally:
+        os.environ.pop("B200_LBA_FORCE_OFFCHIP", None)
+    return got["iterations"]
+
+
+def case_track():
+    from stella_vslam_b200 import tracking
+    imgs = np.stack([synth.make_frame(320, 240, seed=3), synth.make_frame(320, 240, seed=4)])
+    ex = feature.orb_extractor(feature.orb_params(), 400, max_batch=2)
+    kps, descs = ex.extract_batch(imgs)
+    cam = dict(model="perspective", fx=300.0, fy=300.0, cx=160.0, cy=120.0, fxb=30.0, cols=320.0, rows=240.0, setup="stereo")
+    frames = [dict(synth.make_tracking_frame(kps[i], descs[i], cam, ex.orb_params_.scale_factors_, seed=9 + i, stereo=True), frame=i) for i in range(2)]
+    got = tracking.local_map_tracker(ex, cam).track(frames)
+    prm = ex.orb_params_
+    for i, (fr, g) in enumerate(zip(frames, got)):
+        ref = O.track_local_map(cam, kps[i], descs[i], fr, prm.scale_factors_, prm.inv_level_sigma_sq_, prm.log_scale_factor_, monocular=False)
+        assert np.array_equal(g["kp_landmark"], ref["kp_landmark"]) and np.array_equal(g["kp_outlier"], ref["kp_outlier"]) and g["n_valid"] == ref["n_valid"]
+    return sum(g["n_matches"] for g in got)
+
+
 def case_pose():
     pp = synth.make_pose_problem(1, n_obs=200, model="stereo")
     n_valid, pose, flags = optimize.pose_optimizer().optimize(pp)
@@ -124,7 +152,8 @@ def case_pose():
     return n_valid
 
 
-CASES = dict(orb=case_orb, match=case_match, guided=case_guided, pairs=case_pairs, stereo=case_stereo, lba=case_lba, pose=case_pose)
+CASES = dict(orb=case_orb, match=case_match, guided=case_guided, pairs=case_pairs, stereo=case_stereo, lba=case_lba, global_ba=case_global_ba,
+             track=case_track, pose=case_pose)
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(CASES)

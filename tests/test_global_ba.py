@@ -79,3 +79,24 @@ def test_force_stop_protocol():
     got2 = gba.optimize(pr, None, gain_threshold=0.3)           # optimize_for_initialization's own threshold
     ref2 = O.global_ba_solve(pr, 50, gain_threshold=0.3)
     assert got2["iterations"] == ref2["iterations"] < got["iterations"]
+
+
+@pytest.mark.gpu
+def test_off_chip_cholesky_equals_on_chip_on_small_systems(monkeypatch):
+    """The panel-by-panel factorisation (global BA) forced onto systems the on-chip kernel also solves: same panels, same tile arithmetic,
+    same backward solve -> the same states up to the last bits of one reduction (computeScale's sum runs in a different thread count)."""
+    from stella_vslam_b200 import optimize
+    for model, K, L, seed in [("stereo", 30, 2000, 1), ("mono", 25, 900, 4)]:
+        pr = synth.make_ba_problem(K, 2, L, seed=seed, model=model)
+        monkeypatch.delenv("B200_LBA_FORCE_OFFCHIP", raising=False)
+        on = optimize.global_bundle_adjuster(8).optimize(pr)
+        monkeypatch.setenv("B200_LBA_FORCE_OFFCHIP", "1")
+        gba = optimize.global_bundle_adjuster(8)
+        off = gba.optimize(pr)
+        lba = optimize.local_bundle_adjuster().optimize(pr)               # the local-BA protocol through the same path
+        monkeypatch.delenv("B200_LBA_FORCE_OFFCHIP")
+        assert off["launches"] > on["launches"] and off["iterations"] == on["iterations"]
+        assert np.allclose(off["pose_cw"], on["pose_cw"], rtol=1e-11, atol=1e-13) and np.allclose(off["points"], on["points"], rtol=1e-11, atol=1e-13)
+        ref = O.lba_solve(pr)
+        assert lba["iterations"] == ref["iterations"] and np.array_equal(lba["outliers"], ref["outliers"])
+        assert np.abs(lba["points"] - ref["points"]).max() <= REL * max(1.0, np.abs(ref["points"]).max())

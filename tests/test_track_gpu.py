@@ -68,6 +68,21 @@ def test_chain_with_distortion_and_frame_subset(mods):
     assert total > 200
 
 
+def test_chain_equirectangular(mods):
+    # BASELINE configs 1 / 2: equirectangular camera (identity undistortion, every reprojection inside the image, equirect pose edges)
+    O, feature, tracking, synth = mods
+    imgs = np.stack([synth.make_frame(1920, 960, seed=40 + i) for i in range(2)])
+    ex = feature.orb_extractor(feature.orb_params(), 2500, max_batch=2)
+    kps, descs = ex.extract_batch(imgs)
+    cam = dict(model="equirectangular", cols=1920.0, rows=960.0, fxb=0.0, setup="monocular")
+    frames = [dict(synth.make_tracking_frame(kps[i], descs[i], cam, ex.orb_params_.scale_factors_, seed=45 + i, pixel_sigma=0.7), frame=i) for i in range(2)]
+    tr = tracking.local_map_tracker(ex, cam)
+    total, got = _check(O, ex, tr, cam, kps, descs, frames, monocular=True)
+    assert total > 0.3 * sum(len(k) for k in kps)
+    for fr, g in zip(frames, got):
+        assert np.abs(g["pose_cw"] - fr["gt_pose_cw"]).max() < np.abs(fr["pose_cw"] - fr["gt_pose_cw"]).max()
+
+
 def test_chain_degenerate_frames(mods):
     O, feature, tracking, synth = mods
     imgs = np.stack([synth.make_frame(640, 480, seed=3), np.full((480, 640), 90, np.uint8)])    # second frame: no keypoints at all

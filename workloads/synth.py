@@ -419,11 +419,12 @@ def make_tracking_frame(kps, desc, camera, scale_factors, seed=0, stereo=False, 
     """A local map for one extracted frame (track_local_map workload): most keypoints get a landmark at a random depth (descriptor = the
     keypoint's with a few flipped bits, position off by ~pixel_sigma pixels), plus clutter landmarks (random descriptors; some behind the
     camera or outside the image), a few landmarks the frame already carries (kp_landmark, skipped by the search) and a few without
-    observations.  The pose handed to the tracker is the true pose perturbed by rot_deg / trans_m.  perspective cameras only."""
+    observations.  The pose handed to the tracker is the true pose perturbed by rot_deg / trans_m.  Perspective and equirectangular
+    cameras (the keypoints are taken as undistorted)."""
     rng = np.random.default_rng(seed)
     n_kp = len(kps)
     sf = np.asarray(scale_factors, np.float64)
-    fx, fy, cx, cy = camera["fx"], camera["fy"], camera["cx"], camera["cy"]
+    fx, fy, cx, cy = camera.get("fx", 1.0), camera.get("fy", 1.0), camera.get("cx", 0.0), camera.get("cy", 0.0)
     Rcw = _rot_y(0.2 * rng.standard_normal()) @ _rodrigues(0.05 * rng.standard_normal(3))
     tcw = rng.normal(0, 1.0, 3)
     center = -Rcw.T @ tcw
@@ -431,11 +432,22 @@ def make_tracking_frame(kps, desc, camera, scale_factors, seed=0, stereo=False, 
     z = rng.uniform(4, 40, len(pick))
     u = kps["x"][pick].astype(np.float64) + pixel_sigma * rng.standard_normal(len(pick))
     v = kps["y"][pick].astype(np.float64) + pixel_sigma * rng.standard_normal(len(pick))
-    pc = np.stack([(u - cx) / fx * z, (v - cy) / fy * z, z], 1)
+    equirect = camera.get("model", "perspective") == "equirectangular"
+
+    def back_project(uu, vv, depth):
+        if equirect:                                                 # camera/equirectangular.cc:42-49: pixel -> bearing
+            lon, lat = (uu / camera["cols"] - 0.5) * 2 * np.pi, -(vv / camera["rows"] - 0.5) * np.pi
+            b = np.stack([np.cos(lat) * np.sin(lon), -np.sin(lat), np.cos(lat) * np.cos(lon)], 1)
+            return b * depth[:, None]
+        return np.stack([(uu - cx) / fx * depth, (vv - cy) / fy * depth, depth], 1)
+
+    pc = back_project(u, v, z)
     n_cl = int(clutter_frac * len(pick))
-    zc = rng.uniform(-10, 60, n_cl)                                  # some behind the camera
+    zc = rng.uniform(4, 60, n_cl) if equirect else rng.uniform(-10, 60, n_cl)   # (perspective: some behind the camera)
     uc, vc = rng.uniform(-200, camera["cols"] + 200, n_cl), rng.uniform(-100, camera["rows"] + 100, n_cl)
-    pcc = np.stack([(uc - cx) / fx * zc, (vc - cy) / fy * zc, zc], 1)
+    if equirect:
+        uc, vc = np.clip(uc, 0, camera["cols"] - 1), np.clip(vc, 0, camera["rows"] - 1)
+    pcc = back_project(uc, vc, zc)
     pc_all = np.concatenate([pc, pcc])
     pw = (pc_all - tcw) @ Rcw
     n_lm = len(pw)
