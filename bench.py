@@ -599,10 +599,10 @@ def main():
             "lba_pose_rows": E_ * 24 + K_ * (56 + 288 + 48),
             "lba_schur": E_ * 160 + L_ * 72 + (6 * Kf_) ** 2 * 8,
             "lba_cholesky": (6 * Kf_) ** 2 * 8 * 2,
-            "lba_backsub": E_ * 160 + L_ * 48,
-            "lba_trial_chi2": E_ * 24 + L_ * 24 + E_ * 8,
+            # back-substitution + chi2 of the trial state + accept / reject (one kernel since round 2b)
+            "lba_backsub_trial": E_ * 160 + L_ * 48 + E_ * 24 + L_ * 24 + E_ * 8,
         }
-        idx = {"lba_landmark_build": 1, "lba_pose_rows": 2, "lba_schur": 3, "lba_cholesky": 4, "lba_backsub": 5, "lba_trial_chi2": 6}
+        idx = {"lba_landmark_build": 1, "lba_pose_rows": 2, "lba_schur": 3, "lba_cholesky": 4, "lba_backsub_trial": 5}
         windows_per_step = n_lba
         for nm, kk in idx.items():
             tot_ms, n_int = lba_kernel_ms[kk]
@@ -704,7 +704,7 @@ def ncu_traffic_per_launch():
     import csv
     names = {"resize_kernel": "pyramid", "fast_cells_kernel": "fast_nms_gridmax", "select_kernel": "select", "describe_kernel": "blur_orient_describe",
              "topk_tc_kernel": "match_topk", "resolve_kernel": "match_resolve", "landmark_kernel<0>": "lba_landmark_build", "pose_rows_kernel": "lba_pose_rows",
-             "schur_mma_kernel": "lba_schur", "chol_solve_kernel": "lba_cholesky", "backsub_kernel": "lba_backsub", "landmark_kernel<1>": "lba_trial_chi2"}
+             "schur_mma_kernel": "lba_schur", "chol_solve_kernel": "lba_cholesky", "backsub_kernel": "lba_backsub_trial"}
     out, seen = {}, {}
     for fn in ("r2_ncu_full_frontend.csv", "r2_ncu_full_lba.csv"):
         path = os.path.join(ROOT, "profiles", fn)

@@ -511,7 +511,8 @@ int b200_track_stage_ms(b200_matcher_t matcher, int stage, float* ms);
 /* Profiling mode: an event after every launch of the following solves (adds a few microseconds per launch; off by default).
  * b200_lba_kernel_ms reports, for the LAST batch, the summed device time and the number of intervals of
  *   kernel 0 plan (5 launches, one interval), 1 landmark pass / build, 2 keyframe rows, 3 Schur rows, 4 reduced-system Cholesky,
- *   5 back-substitution, 6 landmark pass / trial chi2, 7 everything after the last repetition (round tails, outliers, export). */
+ *   5 back-substitution + chi2 of the trial state, 6 (unused since the trial pass was fused into 5), 7 everything after the last
+ *   repetition (round tails, outliers, export). */
 int b200_lba_enable_profile(b200_lba_t h, int enable);
 int b200_lba_kernel_ms(b200_lba_t h, int kernel, float* total_ms, int* launches);
 /* Device time (ms, CUDA events) spent in the kernels of the last solve, and the number of kernel launches. */

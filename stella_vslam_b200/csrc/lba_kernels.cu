@@ -1812,6 +1812,7 @@ __global__ void __launch_bounds__(128) backsub_kernel(const WinDev* __restrict__
         c1 += __shfl_down_sync(0xFFFFFFFFu, c1, s, 8);
         c2 += __shfl_down_sync(0xFFFFFFFFu, c2, s, 8);
     }
+    double pn0 = 0.0, pn1 = 0.0, pn2 = 0.0;  // the landmark's trial position (lane 0 of its eight lanes)
     if (valid && sub == 0) {
         double p0 = pts_cur[3 * (size_t)l], p1 = pts_cur[3 * (size_t)l + 1], p2 = pts_cur[3 * (size_t)l + 2];
         if (solve) {
@@ -1824,9 +1825,46 @@ __global__ void __launch_bounds__(128) backsub_kernel(const WinDev* __restrict__
             p0 += x0; p1 += x1; p2 += x2;  // landmark_vertex::oplusImpl
         }
         pts_new[3 * (size_t)l] = p0; pts_new[3 * (size_t)l + 1] = p1; pts_new[3 * (size_t)l + 2] = p2;
+        pn0 = p0; pn1 = p1; pn2 = p2;
     }
     const double tot = block_sum(sc, sh);
     if (threadIdx.x == 0) scale_partials[blockIdx.x] = tot;
+    // ---- computeActiveErrors at the TRIAL state (round 2a: a separate launch, landmark_kernel<kTrial>): the eight lanes of the landmark
+    //      take its new position from lane 0 and walk its edges once more against the trial keyframe states the Cholesky kernel wrote
+    {
+        const int base = threadIdx.x & ~7 & 31;
+        pn0 = __shfl_sync(0xFFFFFFFFu, pn0, base);
+        pn1 = __shfl_sync(0xFFFFFFFFu, pn1, base);
+        pn2 = __shfl_sync(0xFFFFFFFFu, pn2, base);
+        const int tidx = (ctl->cur & 1) ^ 1;
+        const double* __restrict__ Rt = W.Rt[tidx];
+        double* __restrict__ chi = W.chi[tidx];
+        const double* __restrict__ chi_carry = W.chi[tidx ^ 1];
+        const double P[3] = {pn0, pn1, pn2};
+        double cost = 0.0;
+        for (int e = a0 + sub; e < b0; e += 8) {
+            if (W.level[e] == 0) {
+                const EdgeS ed = v.edges[e];
+                const Cam c = W.cams[ed.cam];
+                double err[3], pc[3];
+                edge_residual(ed, c, Rt + 12 * (size_t)ed.pose, P, err, pc);
+                const double w = (double)ed.inv_sigma_sq;
+                const double e2 = w * (err[0] * err[0] + err[1] * err[1] + err[2] * err[2]);
+                chi[e] = e2;
+                cost += W.robust[e] ? huber_cost(e2, (double)ed.delta) : e2;
+            } else {
+                chi[e] = chi_carry[e];  // inactive edges keep the chi2 of their last activation across the current/trial swap
+            }
+        }
+        __syncthreads();  // (sh is reused)
+        const double cs = block_sum(cost, sh);
+        if (threadIdx.x == 0) W.r_chi[blockIdx.x] = cs;
+        // the last CTA of the window runs the accept / reject bookkeeping on the complete partial sums
+        __shared__ int last_flag;
+        __shared__ double stage[1024];
+        if (!last_cta_arrives(W.tickets + 1, W.lbc, &last_flag)) return;
+        lm_after_trial(W, stage);
+    }
 }
 
 // K8: outlier test (local_bundle_adjuster_g2o.cc:323-344, 357-375): chi2 of the last activation vs the chi-square
@@ -2581,11 +2619,9 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
             B200_CUDA(cudaLaunchKernelEx(&cfg, chol_solve_kernel, wins));
         }
         if ((rcm = mark(4))) return rcm;
-        backsub_kernel<<<dim3(max_lbc, nw), 128, 0, st>>>(wins);
+        backsub_kernel<<<dim3(max_lbc, nw), 128, 0, st>>>(wins);  // back-substitution + chi2 of the trial state + accept / reject
         if ((rcm = mark(5))) return rcm;
-        landmark_kernel<kTrial><<<dim3(max_lbc, nw), kLmThreads, 0, st>>>(wins);
-        if ((rcm = mark(6))) return rcm;
-        launches += 6;
+        launches += 5;
         return B200_OK;
     };
     // Read the control blocks back into mirror `b` (asynchronously) / wait for that copy.  The loop below always has the NEXT chunk

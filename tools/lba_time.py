@@ -15,7 +15,7 @@ ba = optimize.local_bundle_adjuster()
 L = ba._L
 L.b200_lba_enable_profile.argtypes = [C.c_void_p, C.c_int]
 L.b200_lba_kernel_ms.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_int)]
-NAMES = ["plan", "landmark_build", "pose_rows", "schur_rows", "cholesky", "backsub", "trial_chi2", "tail"]
+NAMES = ["plan", "landmark_build", "pose_rows", "schur", "cholesky", "backsub+trial", "(unused)", "tail"]
 for nb in batches:
     prep = ba.prepare_batch([pr] * nb)
     for i in range(reps):
