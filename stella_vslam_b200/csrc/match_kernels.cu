@@ -278,7 +278,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) topk_tc_kernel(Side S1, Side S2
     // only while lowe * second < 50: a candidate farther than cap = ceil(50 / lowe) can change no decision and is not listed (random
     // descriptor pairs are ~128 +- 8 apart, so this removes nearly every insertion).  Rows without a landmark list nothing.
     unsigned thr = active ? make_key(cap + 1u, 0u) : 0u;
-    int dot_thr = 256 - 2 * (int)(thr >> 22);  // dot products below this cannot enter the row's list
     // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 at [4,6)), A = B = signed int8 (1 at [7,10) and [10,13)), both K-major,
     // N >> 3 at [17,23), M >> 4 at [24,29)
     const unsigned idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(kTcChunk >> 3) << 17) | ((128u >> 4) << 24);
@@ -348,17 +347,14 @@ __global__ void __launch_bounds__(kTcThreads, 2) topk_tc_kernel(Side S1, Side S2
                     tc_ld32(taddr + 32 * g, v);
 #pragma unroll
                     for (int i = 0; i < 32; i += 4) {
-                        // first test on the raw accumulators: a key can only beat the row's threshold if its dot product reaches
-                        // 256 - 2 * (threshold distance); two 3-input maxima, one compare and one vote per four distances.  The keys
-                        // are formed only for a group that holds a candidate for some row of the warp.
-                        const int dmax = max(__vimax3_s32((int)v[i], (int)v[i + 1], (int)v[i + 2]), (int)v[i + 3]);
-                        if (__any_sync(0xFFFFFFFFu, dmax >= dot_thr)) {
-                            unsigned key[4];
+                        unsigned key[4];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                key[u] = (unsigned)((int)v[i + u] * -(1 << 21)) + (kbase + (unsigned)(32 * g + i + u));
-                                if (!decltype(full_chunk)::value && ch0 + 32 * g + i + u >= n1) key[u] = kInfKey;  // zero padding of the last chunk
-                            }
+                        for (int u = 0; u < 4; ++u) {
+                            key[u] = (unsigned)((int)v[i + u] * -(1 << 21)) + (kbase + (unsigned)(32 * g + i + u));
+                            if (!decltype(full_chunk)::value && ch0 + 32 * g + i + u >= n1) key[u] = kInfKey;  // zero padding of the last chunk
+                        }
+                        const unsigned m4 = min(__vimin3_u32(key[0], key[1], key[2]), key[3]);
+                        if (__any_sync(0xFFFFFFFFu, m4 < thr)) {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
                                 if (key[u] < thr) {
@@ -373,7 +369,6 @@ __global__ void __launch_bounds__(kTcThreads, 2) topk_tc_kernel(Side S1, Side S2
                                         }
                                     }
                                     thr = min(thr, top[kTopK - 1]);
-                                    dot_thr = 256 - 2 * (int)(thr >> 22);
                                 }
                             }
                         }
