@@ -208,3 +208,16 @@ def test_unsorted_edge_order(mods):
         pr2[k] = np.ascontiguousarray(pr[k][perm])
     ba = optimize.local_bundle_adjuster()
     check_same(ba.optimize(pr2), O.lba_solve(pr2), pr2)
+
+
+def test_batch_of_32_mixed_windows(mods):
+    # >= 32 independent problems per launch sequence; mixed models / sizes, every window against the oracle
+    O, optimize, synth = mods
+    rng = np.random.default_rng(77)
+    specs = [(("mono", "stereo", "equirect")[i % 3], int(rng.integers(4, 14)), int(rng.integers(1, 4)), int(rng.integers(60, 500)), 200 + i) for i in range(32)]
+    prs = [synth.make_ba_problem(K, min(F, K - 1) if m != "mono" else min(max(F, 2), K - 1), L, seed=s, model=m) for m, K, F, L, s in specs]
+    ba = optimize.local_bundle_adjuster()
+    got = ba.optimize_batch(prs)
+    assert len(got) == 32 and got[0]["launches"] < 200
+    for g, pr in zip(got, prs):
+        check_same(g, O.lba_solve(pr), pr)
