@@ -223,6 +223,9 @@ def main():
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_note = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
+    if numa_note and os.environ.get("B200_BENCH_VERBOSE"):
+        print(f"[bench] rank {rank}: {numa_note}", file=sys.stderr, flush=True)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -674,6 +677,7 @@ def main():
                    "matches_per_frame_mean": float(n_mt.mean()), "raw_fast_corners_per_frame_mean": raw_c,
                    "l2": f"inputs larger than L2: {B} frames x {W * H / 1e6:.2f} MB + {B} pyramids",
                    "timing": f"median of {REPEATS} timed regions of {args.steps} steps each (repeat_stats)",
+                   "numa_binding_rank0": numa_note,
                    "lba": (f"{n_lba} local-BA windows per step (one per {args.lba_every} frames): 50 keyframes (10 fixed), 10000 landmarks, "
                            f"{len(lba_problem['e_pose'])} stereo observations, 5+10 LM iterations, solved asynchronously next to the front end "
                            f"(b200_lba_solve_batch: {max(1, int(round(n_lba * LBA_BATCH_STEPS)))} windows per launch sequence, up to {LBA_INFLIGHT} batches in flight; "
@@ -697,6 +701,31 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def bind_to_gpu_numa_node(torch, local_rank):
+    """One process per GPU: run this rank (and first-touch its pinned host buffers) on the CPU socket the GPU hangs off.  With eight ranks
+    on a two-socket host the end-to-end arm moves 8 x 157 MB per step over PCIe; buffers on the far socket cross the inter-socket link.
+    Best effort: silently does nothing where sysfs does not expose the topology.  B200_BENCH_NUMA=0 disables it."""
+    if os.environ.get("B200_BENCH_NUMA", "1") == "0":
+        return "disabled"
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return f"{bdf}: no NUMA node reported"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return f"{bdf}: node {node} has no allowed CPU"
+        os.sched_setaffinity(0, allowed)
+        return f"{bdf}: NUMA node {node}, {len(allowed)} CPUs"
+    except Exception as exc:  # containers without sysfs topology, old torch without pci ids ...
+        return f"unavailable ({type(exc).__name__})"
 
 
 def ncu_traffic_per_launch():
