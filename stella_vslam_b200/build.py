@@ -60,7 +60,7 @@ def build(force=False, verbose=False):
         if verbose and out.strip():
             print(out, file=sys.stderr)
     if force or procs or _stale(LIB, objs):
-        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static"]
+        cmd = [nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-cudart", "static", "-ldl"]
         if verbose:
             print(" ".join(cmd), file=sys.stderr)
         subprocess.check_call(cmd)

@@ -2313,6 +2313,7 @@ struct WinOff {
 // Solves the windows ws[0..nw) (indices into the caller's arrays) in lockstep.  status[w] is set for every window.
 static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int iters1, int iters2, volatile uint8_t* const* stops,
                        double* const* pose_outs, double* const* points_outs, uint8_t* const* outlier_outs, b200_lba_stats_t* stats, int* status, int rounds = 2, double gain_thr = 1e-3, bool allow_large = false) {
+    B200_RANGE("b200:lba:batch");
     const bool debug = getenv("B200_LBA_DEBUG") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto ms_since = [](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count(); };
@@ -2568,6 +2569,7 @@ static int solve_batch(Solver& S, int n_all, const b200_lba_problem_t* Ps, int i
         launches += 3;
     }
     if ((rc = mark(0))) return rc;
+    B200_RANGE("b200:lba:rounds+export");  // (the plan above is the part of b200:lba:batch outside this range)
     // ---- LM rounds in lockstep ---------------------------------------------------------------------------------------------------
     const bool large = max_n > kCholOnChipMax || S.force_offchip;  // (B200_LBA_FORCE_OFFCHIP: the panel-by-panel path on any size, for tests)
     const size_t chol_smem = sizeof(double) * ((size_t)kNB * (kNB + 1) + 4 + (size_t)((std::min(max_n, kCholOnChipMax) + 1 + 3) & ~3) * kNB);
@@ -3006,6 +3008,7 @@ int b200_global_ba_solve(b200_lba_t h, const b200_lba_problem_t* P, int num_iter
 
 int b200_pose_optimize(b200_lba_t h, int n_problems, const b200_lba_problem_t* problems, int num_trials_robust, int num_trials, int num_each_iter,
                        double* pose_cw_out, uint8_t* outlier_flags, uint32_t* n_valid) {
+    B200_RANGE("b200:lba:pose_optimize");
     using namespace b200::lba;
     if (!h || n_problems < 0 || num_trials_robust < 0 || num_trials < 0 || num_each_iter < 0) return B200_ERR_INVALID;
     if (n_problems == 0) return B200_OK;

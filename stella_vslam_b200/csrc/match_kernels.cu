@@ -1522,6 +1522,7 @@ int b200_match_bruteforce_device(b200_matcher_t h, int n_problems, const void* d
                                  const void* d_off1, const void* d_cnt1, const void* d_desc2, const void* d_angle2, size_t angle2_stride,
                                  const void* d_valid2, const void* d_off2, const void* d_cnt2, int max_n1, int max_n2, float lowe_ratio,
                                  int check_orientation, void* d_pairs, int pairs_stride, void* d_n_pairs) {
+    B200_RANGE("b200:match:bruteforce_device");
     if (!h || n_problems < 0 || max_n1 < 0 || max_n2 < 0) return B200_ERR_INVALID;
     if (n_problems == 0) return B200_OK;
     if (!d_off1 || !d_off2 || !d_cnt1 || !d_cnt2 || !d_pairs || !d_n_pairs || !d_desc1 || !d_angle1 || !d_desc2 || !d_angle2) {
@@ -1538,6 +1539,7 @@ int b200_match_bruteforce(b200_matcher_t h, int n_problems, const uint8_t* desc1
                           const int32_t* off1, const int32_t* cnt1, const uint8_t* desc2, const void* angle2, size_t angle2_stride,
                           const uint8_t* valid2, const int32_t* off2, const int32_t* cnt2, float lowe_ratio, int check_orientation,
                           int32_t* pairs, int pairs_stride, int32_t* n_pairs) {
+    B200_RANGE("b200:match:bruteforce");
     if (!h || n_problems < 0) return B200_ERR_INVALID;
     if (n_problems == 0) return B200_OK;
     if (!off1 || !off2 || !cnt1 || !cnt2 || !pairs || !n_pairs || angle1_stride < sizeof(float) || angle2_stride < sizeof(float)) {
@@ -1619,6 +1621,7 @@ int b200_match_bruteforce(b200_matcher_t h, int n_problems, const uint8_t* desc1
 
 int b200_match_guided(b200_matcher_t h, int n_problems, b200_guided_problem_t* problems, int mode, unsigned thr, float lowe_ratio,
                       int check_orientation, int max_candidates) {
+    B200_RANGE("b200:match:guided");
     using b200::match::GuidedDev;
     if (!h || n_problems < 0 || mode < B200_GUIDED_LANDMARKS || mode > B200_GUIDED_AREA || max_candidates < 0) return B200_ERR_INVALID;
     if (n_problems == 0) return B200_OK;
@@ -1826,6 +1829,7 @@ int b200_track_stage_ms(b200_matcher_t h, int stage, float* ms) {
 //   [outputs]                                          -- one download
 //   [stage-A products, guided scratch]
 int b200_track_local_map(b200_orb_t orb, b200_matcher_t h, b200_lba_t opt, const b200_track_params_t* prm, int n_frames, b200_track_frame_t* frames) {
+    B200_RANGE("b200:track:local_map");
     using b200::chain::TrackFrameDev;
     using b200::chain::TrackShared;
     using b200::match::GuidedDev;
@@ -2104,6 +2108,7 @@ int b200_track_local_map(b200_orb_t orb, b200_matcher_t h, b200_lba_t opt, const
 
 int b200_match_pairs(b200_matcher_t h, int n_problems, b200_pairs_problem_t* problems, int variant, float lowe_ratio, int check_orientation,
                      int max_candidates) {
+    B200_RANGE("b200:match:pairs");
     using b200::match::PairsDev;
     if (!h || n_problems < 0 || (variant != B200_PAIRS_BOW && variant != B200_PAIRS_TRIANGULATION) || max_candidates < 0) return B200_ERR_INVALID;
     if (n_problems == 0) return B200_OK;
@@ -2248,6 +2253,7 @@ int b200_match_pairs(b200_matcher_t h, int n_problems, b200_pairs_problem_t* pro
 int b200_stereo_compute(b200_matcher_t h, b200_orb_t left, int frame_left, b200_orb_t right, int frame_right, const b200_keypoint_t* keypts_left,
                         const uint8_t* descs_left, int n_left, const b200_keypoint_t* keypts_right, const uint8_t* descs_right, int n_right,
                         float focal_x_baseline, float true_baseline, float* stereo_x_right, float* depths, int32_t* n_matched) {
+    B200_RANGE("b200:match:stereo");
     using namespace b200::match;
     if (!h || !left || !right || n_left < 0 || n_right < 0 || (n_left > 0 && (!keypts_left || !descs_left || !stereo_x_right || !depths))
         || (n_right > 0 && (!keypts_right || !descs_right)) || !(true_baseline > 0.f)) {

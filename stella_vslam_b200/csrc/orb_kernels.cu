@@ -1679,6 +1679,7 @@ int b200_orb_max_keypoints(b200_orb_t h, int width, int height) {
 
 int b200_orb_extract_device(b200_orb_t h, const void* d_images, int width, int height, size_t pitch, size_t frame_stride, int batch,
                             const void* d_mask, size_t mask_pitch) {
+    B200_RANGE("b200:orb:extract_device");
     if (!h) return B200_ERR_INVALID;
     if (width == 0 || height == 0 || batch == 0) {  // orb_extractor.cc:30-32: empty image -> silent return
         h->ex.last_batch = 0;
@@ -1761,6 +1762,7 @@ int b200_orb_reserve(b200_orb_t h, int width, int height, int batch) {
 
 int b200_orb_extract(b200_orb_t h, const uint8_t* images, int width, int height, size_t pitch, size_t frame_stride, int batch,
                      const uint8_t* mask, size_t mask_pitch, b200_keypoint_t* kps, uint8_t* descs, int cap, int32_t* counts) {
+    B200_RANGE("b200:orb:extract");
     if (!h) return B200_ERR_INVALID;
     if (width == 0 || height == 0 || batch == 0) {
         h->ex.last_batch = 0;
