@@ -442,11 +442,17 @@ __global__ void __launch_bounds__(kFastThreads) fast_cells_kernel(const __grid_c
             const int nvalid = min(4, cw - 3 - lx0), nrows = min(4, ch - 3 - y0);
             acc &= (0xFFFFFFFFu >> (32 - 8 * nvalid)) & (((1u << nrows) - 1u) * 0x01010101u);
             if (acc) {
+                // sixteen predicated stores at prefix-popcount offsets instead of a loop over the set bits: the loop ran as long as the
+                // fullest thread of the warp (~10 iterations with 6 active lanes: 16 % of the kernel's instructions)
                 int pos = atomicAdd(&n_cand, __popc(acc));
-                while (acc) {
-                    const int k = __ffs(acc) - 1;
-                    acc &= acc - 1;
-                    cand[pos++] = (unsigned short)(((y0 + (k & 7)) << 8) | (c0 + (k >> 3)));
+                const unsigned enc0 = (unsigned)((y0 << 8) | c0);
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const unsigned nib = (acc >> (8 * b)) & 0xFu;  // rows y0 .. y0 + 3 of pixel c0 + b
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if ((nib >> i) & 1u) cand[pos + __popc(nib & ((1u << i) - 1u))] = (unsigned short)(enc0 + (unsigned)((i << 8) | b));
+                    pos += __popc(nib);
                 }
             }
         }
