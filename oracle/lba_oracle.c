@@ -9,7 +9,11 @@
  * terminate_action.cc -- and (b) g2o's published algorithm: BaseBinaryEdge::constructQuadraticForm with
  * RobustKernelHuber, BlockSolver_6_3 Schur complement, OptimizationAlgorithmLevenberg (tau 1e-5, rho/scale rule,
  * <= 10 trials), SparseOptimizer::optimize loop, SE3Quat::exp.  tests/test_lba_cpu.py checks it against an independent
- * scipy dense Gauss-Newton/LM formulation on small problems; the CUDA path is held to 1e-5 relative against this file.
+ * dense numpy Gauss-Newton step and numerical Jacobians on small problems.  Since round 2 the OPTIMUM it reaches is pinned:
+ * tests/test_lba_scipy.py minimises the same Huber cost over the same edges with scipy.optimize.least_squares (mono / stereo /
+ * equirectangular windows) and compares chi2, outlier set and the optimum itself; what stays unpinned is the LM PATH (iteration
+ * counts, lambda schedule, the terminate action), which only g2o itself could confirm.  The CUDA path is held to 1e-5 relative
+ * against this file.  orc_global_ba_solve (optimize/global_bundle_adjuster.cc) is one round of the same machinery.
  * orc_pose_optimize (optimize/pose_optimizer_g2o.cc:38-175) reuses the same edge and LM code with one free pose and
  * fixed landmarks: equally unpinned (tests/test_pose_opt_cpu.py: protocol properties and ground truth on synthetic frames).
  */

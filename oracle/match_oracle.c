@@ -1,7 +1,10 @@
 /*
  * oracle/match_oracle.c -- TEST INFRASTRUCTURE (see oracle.h).  CPU restatement of the 256-bit Hamming matchers.
- * Pinned by the reference's own known-answer tests (test/stella_vslam/match/base.cc:11-57) for the distance;
- * brute_force_match has no reference test ("parity unpinned" beyond the restatement itself).
+ * Pinned by the reference's own known-answer tests (test/stella_vslam/match/base.cc:11-57) for the distance, and since round 2 by
+ * cv2.BFMatcher(NORM_HAMMING) for the distance matrix and the best / second-best pair that brute_force_match consumes
+ * (tests/golden/match_bf_cv2.npz, tests/test_natural_golden.py).  The greedy part of brute_force_match (taken set, ratio test,
+ * orientation histogram, output order; robust.cc:253-325) has no reference test: "parity unpinned" beyond the restatement and its
+ * literal Python cross-check.
  */
 #include "oracle.h"
 
