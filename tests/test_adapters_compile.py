@@ -23,7 +23,7 @@ pytestmark = pytest.mark.skipif(not os.path.isdir(REF_SRC) or shutil.which("g++"
 def test_every_adapter_is_listed():
     names = {os.path.basename(p) for p in ADAPTERS}
     assert {"orb_extractor_b200.cc", "robust_brute_force_b200.cc", "projection_b200.cc", "stereo_b200.cc", "fuse_b200.cc",
-            "area_b200.cc", "bow_tree_b200.cc", "local_bundle_adjuster_b200.cc", "pose_optimizer_b200.cc", "global_bundle_adjuster_b200.cc"} <= names
+            "area_b200.cc", "bow_tree_b200.cc", "local_bundle_adjuster_b200.cc", "pose_optimizer_b200.cc", "global_bundle_adjuster_b200.cc", "track_local_map_b200.cc"} <= names
 
 
 @pytest.mark.parametrize("src", ADAPTERS, ids=[os.path.basename(p) for p in ADAPTERS])
